@@ -1,0 +1,327 @@
+"""Generate the committed golden fixtures by RUNNING THE REFERENCE ITSELF.
+
+Runs only inside the build container (needs /root/reference); the GPU box and the
+test-suite only read the ``*.npz`` files written next to this script.
+
+    python tests/golden/make_golden.py
+
+What is pinned (the reference has no tests, so the only pin is its
+own output on identical inputs):
+  * ``limbs_*.npz``  — full-resolution maps -> reference ``joint_dets``,
+    ``LimbsCollect.generate_limbs``, ``GreedyGroup.group_skeletons``;
+  * ``poses_*.npz``  — network-resolution maps -> reference
+    ``decoder_factory(args).generate_poses(features, flip_test=...)`` (includes the
+    reference's flip fusion and x4 bicubic / bilinear resize);
+  * ``group_fuzz.npz`` — random (L, K, 13) limb tables with heavy id collisions ->
+    reference ``group_skeletons`` (exercises merge / last-write-wins / cancellation);
+  * ``resize_*.npz`` — ATen ``F.interpolate`` bicubic / bilinear x4 on small maps;
+  * ``encoder_check`` — asserts oracle/scenes.py renders bit-identically to the
+    reference encoder.
+
+One shim is applied to the reference: ``topK_channel`` with ``idx // w``
+(torch 1.3.1 integer-division semantics).
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(1, '/root/reference')
+
+import decoder  # noqa: E402  (the reference)
+import decoder.heatmap as ref_heatmap  # noqa: E402
+from encoder.heatmap import HeatMapGenerator  # noqa: E402
+from encoder.offset import OffsetMapGenerator  # noqa: E402
+from config.coco_data import COCO_KEYPOINTS, COCO_PERSON_SKELETON  # noqa: E402
+
+from oracle import scenes  # noqa: E402
+from offsetguided_b200 import config as og_config  # noqa: E402
+
+
+def _topk_channel_int(scores, K=40):
+    n, c, h, w = scores.shape
+    topk_scores, topk_idxs = torch.topk(scores.view(n, c, -1), K)
+    return topk_scores, topk_idxs, topk_idxs // w, topk_idxs % w
+
+
+ref_heatmap.topK_channel = _topk_channel_int
+decoder.topK_channel = _topk_channel_int
+
+
+def reference_args(**over):
+    parser = argparse.ArgumentParser()
+    decoder.decoder_cli(parser)
+    args = parser.parse_args([])
+    args.headnets = ['hmp', 'omp']
+    args.strides = [4, 4]
+    args.batch_size = 1
+    args.include_scale = False
+    args.include_jitter_offset = False
+    for k, v in over.items():
+        setattr(args, k, v)
+    return args
+
+
+def canonical_dets(scores, inds):
+    """Reorder the reference's top-K rows to (value desc, index asc) — the order
+    of equal values is library-defined in torch.topk."""
+    scores = scores.copy()
+    inds = inds.copy()
+    n, c, k = scores.shape
+    for i in range(n):
+        for j in range(c):
+            order = np.lexsort((inds[i, j], -scores[i, j].astype(np.float64)))
+            scores[i, j] = scores[i, j][order]
+            inds[i, j] = inds[i, j][order]
+    return scores, inds
+
+
+def tie_report(nms, thre, k):
+    """Number of equal-valued pairs among the above-threshold peaks of a channel."""
+    ties = 0
+    n, c = nms.shape[:2]
+    for i in range(n):
+        for j in range(c):
+            v = nms[i, j][nms[i, j] >= thre]
+            ties += v.size - np.unique(v).size
+    return ties
+
+
+def add_noise(x, seed, amp):
+    """Seeded uniform noise floor; the fixture stores (seed, amp) instead of the
+    incompressible noisy map.  tests/golden_io.py applies the same formula."""
+    if amp <= 0:
+        return x
+    return x + np.random.RandomState(seed).uniform(0, amp, size=x.shape).astype(np.float32)
+
+
+def encoder_check():
+    rng = np.random.RandomState(7)
+    for (w, h, skel, kps, tmpl) in (
+            (640, 640, COCO_PERSON_SKELETON, 17, scenes.TEMPLATE_COCO),
+            (512, 384, og_config.CROWDPOSE_PERSON_SKELETON, 14, scenes.TEMPLATE_CROWDPOSE)):
+        persons = scenes.make_persons(rng, 6, w, h, tmpl, drop_prob=0.1)
+        ref_h = HeatMapGenerator([w, h], 4, 3, 7, 0.01).create_heatmaps(persons, {'joint_num': kps})
+        ref_o = OffsetMapGenerator([w, h], 4, 7, 1.0, skel).create_offsetmaps(persons, {'joint_num': kps})[0]
+        my_h = scenes.render_heatmaps(persons, w, h)
+        my_o = scenes.render_offsets(persons, w, h, skel)
+        assert np.array_equal(ref_h, my_h), 'heatmap renderer differs from the reference encoder'
+        assert np.array_equal(ref_o, my_o), 'offset renderer differs from the reference encoder'
+    print('encoder_check: oracle/scenes.py == reference encoder (bit-exact)')
+
+
+def make_limbs_case(name, seed, n, persons, w, h, keypoints, skeleton, template, topk,
+                    thre_hmp, person_thre, dist_max, noise, scale_range):
+    """Full-resolution maps rendered directly at stride 1 (sigma 3)."""
+    hs, os_ = [], []
+    for i in range(n):
+        rng = np.random.RandomState(seed + i)
+        p = scenes.make_persons(rng, persons, w, h, template, scale_range=scale_range)
+        hm = scenes.render_heatmaps(p, w, h, stride=1, sigma=3.0)
+        om = scenes.render_offsets(p, w, h, skeleton, stride=1, fill=9)
+        om[~np.isfinite(om)] = 0
+        hs.append(hm)
+        os_.append(om)
+    heat_clean = np.stack(hs).astype(np.float32)
+    offs = np.stack(os_).astype(np.float32)
+    heat = add_noise(heat_clean, seed + 500, noise)
+
+    collect = decoder.LimbsCollect(1, 1, topk=topk, thre_hmp=thre_hmp, min_len=0.5,
+                                   keypoints=keypoints, skeleton=skeleton)
+    group = decoder.GreedyGroup(person_thre, sort_dim=2, dist_max=dist_max, use_scale=True,
+                                keypoints=keypoints, skeleton=skeleton)
+    th, to = torch.from_numpy(heat), torch.from_numpy(offs)
+    nms = decoder.hmp_NMS(th)
+    d_s, d_i, _, _ = decoder.topK_channel(nms, K=topk)
+    limbs = collect.generate_limbs(th, [], to, []).numpy()
+    poses = [group.group_skeletons(l) for l in limbs]
+    ties = tie_report(nms.numpy(), thre_hmp, topk)
+    d_s, d_i = canonical_dets(d_s.numpy(), d_i.numpy())
+    print(f'{name}: heat {heat.shape} ties={ties} persons/img={[len(p) for p in poses]}')
+    assert ties == 0, 'fixture must be tie-free among above-threshold peaks'
+    np.savez_compressed(
+        os.path.join(HERE, name + '.npz'),
+        heat=heat_clean, noise_seed=seed + 500, noise_amp=noise,
+        offs=offs, skeleton=np.asarray(skeleton), n_keypoints=len(keypoints),
+        topk=topk, thre_hmp=thre_hmp, person_thre=person_thre, dist_max=dist_max,
+        min_len=0.5, det_scores=d_s, det_inds=d_i.astype(np.int32), limbs=limbs,
+        pose_counts=np.asarray([len(p) for p in poses]),
+        poses=np.concatenate(poses, axis=0) if poses else np.zeros((0, len(keypoints), 6), np.float32))
+
+
+def make_poses_case(name, seed, n, persons, w, h, topk, thre_hmp, person_thre, dist_max,
+                    flip_test, noise_amp):
+    """Network-resolution maps from the reference encoder, decoded through the
+    reference's PostProcess.generate_poses."""
+    kp_flips = og_config.heatmap_hflip(COCO_KEYPOINTS)
+    hgen = HeatMapGenerator([w, h], 4, 3, 7, 0.01)
+    ogen = OffsetMapGenerator([w, h], 4, 7, 1.0, COCO_PERSON_SKELETON)
+    hs, os_, hs_f, os_f, plist = [], [], [], [], []
+    for i in range(n):
+        rng = np.random.RandomState(seed + i)
+        p = scenes.make_persons(rng, persons, w, h)
+        plist.append(p)
+        hs.append(hgen.create_heatmaps(p, {'joint_num': 17}))
+        os_.append(ogen.create_offsetmaps(p, {'joint_num': 17})[0])
+        if flip_test:
+            pf = scenes.mirror_persons(p, w, kp_flips)
+            hs_f.append(hgen.create_heatmaps(pf, {'joint_num': 17}))
+            os_f.append(ogen.create_offsetmaps(pf, {'joint_num': 17})[0])
+    hmp = np.stack(hs + hs_f).astype(np.float32)
+    omp = np.stack(os_ + os_f).astype(np.float32)
+    omp[~np.isfinite(omp)] = 0
+    noise_seed = seed + 777
+    hmp_in = add_noise(hmp, noise_seed, noise_amp)
+
+    args = reference_args(topk=topk, thre_hmp=thre_hmp, person_thre=person_thre,
+                          dist_max=dist_max, batch_size=n)
+    proc = decoder.decoder_factory(args)
+    feats = [[[torch.from_numpy(hmp_in)], [[]], [[]]], [[torch.from_numpy(omp)], [[]], [[]]]]
+    poses = proc.generate_poses(feats, flip_test=flip_test)
+    proc.worker_pool.close()
+    proc.worker_pool.join()
+
+    # the intermediate the reference computed (for stage-wise parity)
+    th, to = torch.from_numpy(hmp_in), torch.from_numpy(omp)
+    if flip_test:
+        th, _, to, _, _ = proc.flip_augment(th, [], to, [], False, 2)
+    fused_h, fused_o = th.numpy().copy(), to.numpy().copy()
+    th = torch.nn.functional.interpolate(th, scale_factor=4, mode='bicubic')
+    to = torch.nn.functional.interpolate(to, scale_factor=4, mode='bilinear')
+    nms = decoder.hmp_NMS(th)
+    ties = tie_report(nms.numpy(), thre_hmp, topk)
+    limbs = proc.limb_collect.generate_limbs(th, [], to, []).numpy()
+    d_s, d_i, _, _ = decoder.topK_channel(nms, K=topk)
+    d_s, d_i = canonical_dets(d_s.numpy(), d_i.numpy())
+    print(f'{name}: hmp {hmp.shape} flip={flip_test} ties={ties} persons/img={[len(p) for p in poses]}')
+    assert ties == 0, 'fixture must be tie-free among above-threshold peaks'
+    np.savez_compressed(
+        os.path.join(HERE, name + '.npz'),
+        hmp=hmp, omp=omp, noise_seed=noise_seed, noise_amp=noise_amp, flip_test=flip_test,
+        topk=topk, thre_hmp=thre_hmp, person_thre=person_thre, dist_max=dist_max, min_len=0.5,
+        fused_h_sum=np.float64(fused_h.astype(np.float64).sum()),
+        fused_o_sum=np.float64(fused_o.astype(np.float64).sum()),
+        heat_hr_probe=th.numpy()[:, :, ::37, ::41].copy(),
+        offs_hr_probe=to.numpy()[:, :, ::37, ::41].copy(),
+        det_scores=d_s, det_inds=d_i.astype(np.int32), limbs=limbs,
+        pose_counts=np.asarray([len(p) for p in poses]),
+        poses=np.concatenate(poses, axis=0))
+
+
+def make_group_fuzz(n_cases=3000):
+    """Random limb tables -> reference group_skeletons.  Ids are drawn from small
+    pools so that re-connections, merges, duplicate-person writes and the
+    mask_sum cancellation all occur; limb scores are distinct within a limb type
+    (the reference's np.argsort is unstable on ties)."""
+    rng = np.random.RandomState(20260101)
+    cases = []
+    stats_total = {}
+    from oracle import ref_oracle
+    for ci in range(n_cases):
+        if ci % 4 == 3:
+            skel, kps = og_config.CROWDPOSE_PERSON_SKELETON, og_config.CROWDPOSE_KEYPOINTS
+        else:
+            skel, kps = COCO_PERSON_SKELETON, COCO_KEYPOINTS
+        c, nl = len(kps), len(skel)
+        k = int(rng.choice([4, 6, 8, 12, 16]))
+        pool = int(rng.choice([2, 3, 4, 6, 10]))
+        big_ids = (ci % 10 == 9)      # float32-rounded ids above 2**24 (config 4)
+        hw = 1024 * 1024 if big_ids else 160 * 160
+        # per keypoint type a small pool of candidate positions
+        cand_xy = rng.randint(1, 600, size=(c, pool, 2)).astype(np.float32)
+        cand_local = rng.randint(0, hw, size=(c, pool))
+        cand_v = rng.uniform(0.1, 1.0, size=(c, pool)).astype(np.float32)
+        limbs = np.zeros((nl, k, 13), dtype=np.float32)
+        for l, (jf, jt) in enumerate(skel):
+            scores = rng.permutation(np.linspace(0.05, 0.95, k)).astype(np.float32)
+            if ci % 3 == 2:      # later limb types score lower: replace_mask often fails
+                scores = (scores * (1.0 - 0.9 * l / nl) ** 2).astype(np.float32)
+            scores += rng.uniform(0, 1e-3, size=k).astype(np.float32)
+            assert np.unique(scores).size == k
+            for r in range(k):
+                a = rng.randint(pool)
+                b = rng.randint(pool)
+                x1, y1 = cand_xy[jf, a]
+                x2, y2 = cand_xy[jt, b]
+                if rng.uniform() < 0.08:
+                    x1 = np.float32(x1 - 100000)          # sub-threshold candidate
+                if rng.uniform() < 0.05:
+                    x2 = np.float32(0)                    # column-0 peak is dropped
+                ind1 = np.float32(cand_local[jf, a] + jf * hw)
+                ind2 = np.float32(cand_local[jt, b] + jt * hw)
+                dist = np.float32(rng.uniform(0, 60))
+                sc2 = np.float32(4.0 if rng.uniform() < 0.8 else rng.uniform(1, 80))
+                limbs[l, r] = (x1, y1, cand_v[jf, a], x2, y2, cand_v[jt, b], ind1, ind2,
+                               dist, rng.uniform(0.5, 100), scores[r], 4.0, sc2)
+        use_scale = bool(ci % 2)
+        sort_dim = 4 if ci % 5 == 4 else 2
+        person_thre = float(rng.choice([0.0, 0.06, 0.3]))
+        g = decoder.GreedyGroup(person_thre, sort_dim=sort_dim, dist_max=40, use_scale=use_scale,
+                                keypoints=kps, skeleton=skel)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = g.group_skeletons(limbs.copy())
+        st = {}
+        mine = ref_oracle.group_skeletons(limbs, skel, c, person_thre, sort_dim, 40, use_scale, st)
+        assert out.shape == mine.shape and np.array_equal(out, mine), f'oracle != reference on fuzz case {ci}'
+        for key, v in st.items():
+            stats_total[key] = stats_total.get(key, 0) + v
+        cases.append((limbs, np.asarray(skel), c, person_thre, sort_dim, use_scale, out, st))
+    print('group_fuzz: oracle == reference on', n_cases, 'cases; branch counts', stats_total)
+    # keep a subset as committed fixture (all were compared above)
+    rare = [c_ for c_ in cases if c_[7]['cancel_new'] > 0]
+    rare += sorted(cases, key=lambda c_: -c_[7]['share3'])[:10]
+    rare += sorted(cases, key=lambda c_: -c_[7]['case2'])[:10]
+    keep = rare + cases[:100]
+    print('group_fuzz: committing', len(keep), 'cases,', sum(c_[7]['cancel_new'] for c_ in keep),
+          'column-sum cancellations among them')
+    np.savez_compressed(
+        os.path.join(HERE, 'group_fuzz.npz'),
+        n=len(keep),
+        **{f'limbs_{i}': c_[0] for i, c_ in enumerate(keep)},
+        **{f'skel_{i}': c_[1] for i, c_ in enumerate(keep)},
+        **{f'meta_{i}': np.asarray([c_[2], c_[3], c_[4], int(c_[5])], dtype=np.float64)
+           for i, c_ in enumerate(keep)},
+        **{f'poses_{i}': c_[6] for i, c_ in enumerate(keep)})
+
+
+def make_resize():
+    rng = np.random.RandomState(5)
+    x = rng.uniform(-1, 1, size=(2, 3, 19, 27)).astype(np.float32)   # output H + W > 128: ATen's generic kernel
+    x[0, 0, 3:6, 4:9] = 0
+    t = torch.from_numpy(x)
+    bic = torch.nn.functional.interpolate(t, scale_factor=4, mode='bicubic').numpy()
+    bil = torch.nn.functional.interpolate(t, scale_factor=4, mode='bilinear').numpy()
+    x2 = rng.uniform(-1, 1, size=(1, 2, 40, 50)).astype(np.float32)
+    t2 = torch.from_numpy(x2)
+    bic2 = torch.nn.functional.interpolate(t2, scale_factor=2, mode='bicubic').numpy()
+    bil2 = torch.nn.functional.interpolate(t2, scale_factor=2, mode='bilinear').numpy()
+    np.savez_compressed(os.path.join(HERE, 'resize_small.npz'), x=x, bicubic4=bic, bilinear4=bil,
+                        x2=x2, bicubic2=bic2, bilinear2=bil2)
+    print('resize_small: written')
+
+
+def main():
+    torch.set_num_threads(8)
+    encoder_check()
+    make_resize()
+    make_group_fuzz()
+    make_limbs_case('limbs_coco_a', 1000, 2, 5, 192, 160, COCO_KEYPOINTS, COCO_PERSON_SKELETON,
+                    scenes.TEMPLATE_COCO, 32, 0.06, 0.06, 40, 0.0, (5.0, 9.0))
+    make_limbs_case('limbs_coco_noise', 2000, 2, 8, 200, 168, COCO_KEYPOINTS, COCO_PERSON_SKELETON,
+                    scenes.TEMPLATE_COCO, 32, 0.04, 0.04, 40, 0.02, (4.0, 8.0))
+    make_limbs_case('limbs_crowdpose', 3000, 2, 20, 256, 192, og_config.CROWDPOSE_KEYPOINTS,
+                    og_config.CROWDPOSE_PERSON_SKELETON, scenes.TEMPLATE_CROWDPOSE,
+                    64, 0.06, 0.06, 40, 0.0, (4.0, 8.0))
+    make_poses_case('poses_cfg1', 4000, 1, 5, 640, 640, 32, 0.06, 0.06, 40, False, 0.0)
+    make_poses_case('poses_cfg2_flip', 5000, 2, 5, 640, 640, 32, 0.04, 0.04, 40, True, 0.0)
+
+
+if __name__ == '__main__':
+    main()
