@@ -1,0 +1,187 @@
+/*
+ * og_decoder.h — C ABI of the B200-native OffsetGuided post-network decoder.
+ *
+ * Drop-in boundary for the reference's decoding path (paths relative to the
+ * reference repository hellojialee/OffsetGuided):
+ *
+ *     decoder/factory.py:52-96   PostProcess.generate_poses        (orchestration)
+ *     decoder/factory.py:98-146  PostProcess.flip_augment          (flip-test fusion)
+ *     decoder/heatmap.py:15-59   hmp_NMS / topK_channel / joint_dets
+ *     decoder/offset.py:8-43     scored_offset
+ *     decoder/collect.py:62-236  LimbsCollect.generate_limbs
+ *     decoder/group.py:39-240    GreedyGroup.group_skeletons
+ *
+ * Conventions
+ *   - plain C types only: device / host pointers, sizes, an opaque handle and a
+ *     CUDA stream passed as void* (cudaStream_t); no C++ exceptions cross the ABI;
+ *   - every function returns an og_status (0 = OG_OK); og_last_error() gives the
+ *     text of the last failure on the calling thread;
+ *   - all maps are float32, NCHW, contiguous; "dev" pointers are device memory of
+ *     the handle's GPU, "host" pointers are host memory (pinned memory makes the
+ *     copies asynchronous);
+ *   - a handle is bound to one GPU and one configuration and is not thread-safe;
+ *     distinct handles are independent (the image-sharding driver keeps one per GPU);
+ *   - there is no CPU fallback: every entry point launches sm_100a kernels.
+ *
+ * The reference is a Python package, so the binding a maintainer adds is a ctypes
+ * stub; offsetguided_b200/_lib.py is that stub.
+ */
+#ifndef OG_DECODER_H_
+#define OG_DECODER_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OG_ABI_VERSION 1
+#define OG_LIMB_COLS 13      /* decoder/collect.py:220-222 */
+#define OG_POSE_COLS 6       /* decoder/group.py:48  [x, y, v, s, limb_score, ind] */
+#define OG_MAX_KEYPOINTS 64
+#define OG_MAX_LIMBS 64
+#define OG_MAX_TOPK 128
+
+typedef enum og_status {
+    OG_OK = 0,
+    OG_ERR_INVALID_ARGUMENT = 1,
+    OG_ERR_CUDA = 2,
+    OG_ERR_OUT_OF_MEMORY = 3,
+    OG_ERR_CAPACITY = 4,          /* caller-provided output buffer too small */
+    OG_ERR_UNSUPPORTED = 5
+} og_status;
+
+/* Configuration = constructor arguments of LimbsCollect (decoder/collect.py:37-60)
+ * and GreedyGroup (decoder/group.py:29-37) plus the skeleton table
+ * (config/coco_data.py:12-15). */
+typedef struct og_config {
+    int32_t n_keypoints;          /* C */
+    int32_t n_limbs;              /* L */
+    const int32_t *limb_from;     /* [L] from-joint of every limb, skeleton order  */
+    const int32_t *limb_to;       /* [L] to-joint                                  */
+    int32_t topk;                 /* K  (--topk)                                   */
+    float thre_hmp;               /* --thre-hmp; score < thre -> moved off image   */
+    float min_len;                /* --min-len                                      */
+    float resize_factor;          /* off_stride / hmp_stride (collect.py:48)        */
+    float dist_max;               /* --dist-max                                     */
+    int32_t use_scale;            /* --use-scale: gate is max(dist_max, scale_t)    */
+    double person_thre;           /* --person-thre (compared in float64)            */
+    int32_t sort_dim;             /* --sort-dim: pose column the person score uses  */
+    int32_t device;               /* CUDA device ordinal, -1 = current              */
+    int32_t max_images;           /* initial capacity in images (grows on demand)   */
+} og_config;
+
+typedef struct og_handle og_handle;
+
+const char *og_last_error(void);
+const char *og_status_string(int status);
+int og_abi_version(void);
+
+int og_create(const og_config *cfg, og_handle **out);
+int og_destroy(og_handle *h);
+
+/* ---- decoder/heatmap.py -------------------------------------------------- */
+
+/* hmp_NMS (heatmap.py:15-35): out = heat * (maxpool3x3_zero_pad(heat) == heat). */
+int og_hmp_nms_f32(const float *heat_dev, float *out_dev,
+                   int n, int c, int h, int w, void *stream);
+
+/* topK_channel (heatmap.py:38-49): exact per-(n, c) top-K of an arbitrary score
+ * map, ordered (value desc, flat index asc).  out_* are [n, c, k]. */
+int og_topk_channel_f32(og_handle *h, const float *scores_dev,
+                        int n, int c, int hgt, int w, int k,
+                        float *out_score_dev, int32_t *out_index_dev, void *stream);
+
+/* joint_dets with the candidate threshold applied first (K1): fused 3x3 NMS +
+ * `value >= thre` + per-channel top-K.  Streams the heat map from HBM once.
+ * Slots beyond the number of surviving peaks hold score 0 / index -1;
+ * out_count_dev[n, c] = number of real candidates (<= k).
+ * With thre = -INFINITY this is exactly joint_dets (heatmap.py:52-59). */
+int og_nms_topk_f32(og_handle *h, const float *heat_dev,
+                    int n, int hgt, int w, float thre,
+                    float *out_score_dev, int32_t *out_index_dev,
+                    int32_t *out_count_dev, void *stream);
+
+/* ---- decoder/collect.py -------------------------------------------------- */
+
+/* generate_limbs from the candidate tables (K2, collect.py:100-233).
+ * offs_dev [n, 2L, h, w]; scales_dev [n, C, h, w] or NULL (scale = 4, collect.py:117).
+ * out_limbs_dev [n, L, K, 13]. */
+int og_limb_score_f32(og_handle *h, const float *det_score_dev, const int32_t *det_index_dev,
+                      const float *offs_dev, const float *scales_dev,
+                      int n, int hgt, int w, float *out_limbs_dev, void *stream);
+
+/* ---- decoder/group.py ---------------------------------------------------- */
+
+/* group_skeletons for n images (K3, one CTA per image).  limbs_dev [n, L, K, 13].
+ * Poses are packed into out_poses_dev [capacity_rows, C, 6]; image i owns rows
+ * [out_offset_dev[i], out_offset_dev[i] + out_count_dev[i]).  out_total_dev[0] is
+ * the number of rows all images produced; rows beyond capacity_rows are dropped
+ * (compare out_total with capacity_rows). */
+int og_group_f32(og_handle *h, const float *limbs_dev, int n,
+                 float *out_poses_dev, int32_t capacity_rows,
+                 int32_t *out_offset_dev, int32_t *out_count_dev, int32_t *out_total_dev,
+                 void *stream);
+
+/* ---- decoder/offset.py, decoder/factory.py ------------------------------- */
+
+/* scored_offset (offset.py:8-43) with a k x k window, out_dev [n, 2L, h, w]. */
+int og_scored_offset_f32(og_handle *h, const float *hmp_dev, const float *off_dev,
+                         int n, int hgt, int w, int kernel_size, float *out_dev, void *stream);
+
+/* flip_augment, vector-addition branch (factory.py:98-106, 128-139).
+ * Inputs hold n originals followed by n W-flipped copies. */
+int og_flip_fuse_f32(og_handle *h, const float *hmp2n_dev, const float *off2n_dev,
+                     const int32_t *kp_flip, const int32_t *limb_flip,
+                     const int32_t *limb_reserve, int n_reserve,
+                     int n, int hgt, int w, float *out_hmp_dev, float *out_off_dev, void *stream);
+
+/* F.interpolate(scale_factor=scale, align_corners=False) (factory.py:74-78);
+ * mode 0 = bilinear, 1 = bicubic (A = -0.75). in [planes, h, w] -> out [planes, h*s, w*s]. */
+int og_resize_f32(const float *in_dev, float *out_dev, int planes, int hgt, int w,
+                  int scale, int mode, void *stream);
+
+/* ---- whole path ----------------------------------------------------------- */
+
+/* generate_limbs + group_skeletons on full-resolution device maps:
+ * K1 -> K2 -> K3 stream-ordered, then an asynchronous copy of the packed poses
+ * into the handle's pinned staging buffer.  og_fetch_poses() synchronises. */
+int og_decode_maps(og_handle *h, const float *heat_dev, const float *offs_dev,
+                   const float *scales_dev, int n, int hgt, int w, void *stream);
+
+/* PostProcess.generate_poses on NETWORK-RESOLUTION maps held in HOST memory:
+ * H2D copy, optional flip fusion (hmp_host has 2n images then), x stride resize
+ * (mode as og_resize_f32), K1 -> K2 -> K3, D2H of the poses.
+ * kp_flip / limb_flip / limb_reserve may be NULL when flip_test == 0. */
+int og_decode_features_host(og_handle *h, const float *hmp_host, const float *off_host,
+                            int n, int hgt, int w, int hmp_stride, int off_stride,
+                            int resize_mode, int flip_test,
+                            const int32_t *kp_flip, const int32_t *limb_flip,
+                            const int32_t *limb_reserve, int n_reserve, void *stream);
+
+/* Same on device-resident network-resolution maps (what evaluate.py:215 hands over). */
+int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_dev,
+                           int n, int hgt, int w, int hmp_stride, int off_stride,
+                           int resize_mode, int flip_test,
+                           const int32_t *kp_flip, const int32_t *limb_flip,
+                           const int32_t *limb_reserve, int n_reserve, void *stream);
+
+/* Wait for the last og_decode_* call and expose its result.  *poses_host points
+ * into the handle's pinned buffer ([total, C, 6] float32, valid until the next
+ * decode call); offsets / counts are [n] int32. */
+int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offset_host,
+                   const int32_t **count_host, int32_t *total_rows);
+
+/* Copy the device-side intermediates of the last decode call (n images) into
+ * caller-provided device buffers (any may be NULL): det scores [n, C, K],
+ * det indices [n, C, K], limbs [n, L, K, 13].  For tests and debugging. */
+int og_copy_intermediates(og_handle *h, int n, float *det_score_dev, int32_t *det_index_dev,
+                          float *limbs_dev, void *stream);
+
+/* Number of kernels this library has launched through the handle so far. */
+int64_t og_launch_count(const og_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* OG_DECODER_H_ */

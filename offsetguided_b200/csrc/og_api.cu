@@ -1,0 +1,593 @@
+// C ABI of the decoder library (include/og_decoder.h): handle, buffer management,
+// stream-ordered composition of the kernels, host staging.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "og_common.cuh"
+
+namespace og {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace og
+
+using namespace og;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T *ptr = nullptr;
+    size_t cap = 0;    // elements
+    int ensure(size_t need) {
+        if (need <= cap) return OG_OK;
+        if (ptr) OG_CUDA_TRY(cudaFree(ptr));
+        ptr = nullptr;
+        cap = 0;
+        const size_t grow = need + need / 4;
+        OG_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&ptr), grow * sizeof(T)));
+        cap = grow;
+        return OG_OK;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+template <typename T>
+struct PinnedBuf {
+    T *ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t need) {
+        if (need <= cap) return OG_OK;
+        if (ptr) OG_CUDA_TRY(cudaFreeHost(ptr));
+        ptr = nullptr;
+        cap = 0;
+        const size_t grow = need + need / 4;
+        OG_CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&ptr), grow * sizeof(T)));
+        cap = grow;
+        return OG_OK;
+    }
+    void release() {
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct og_handle {
+    og_config cfg;
+    SkeletonDev sk;
+    int device;
+    int smem_rows;
+    size_t group_smem;
+    int64_t launches;
+
+    // K1
+    DevBuf<uint32_t> cand_count;
+    DevBuf<uint64_t> cand_keys;
+    DevBuf<float> det_score;
+    DevBuf<int32_t> det_index;
+    DevBuf<int32_t> det_count;
+    // K2 / K3
+    DevBuf<float> limbs;
+    DevBuf<float> slab;
+    DevBuf<unsigned char> out;         // [meta int32 x meta_words][poses float]
+    PinnedBuf<unsigned char> out_host;
+    // feature path
+    DevBuf<float> in_hmp, in_off;      // staged network-resolution inputs (host path)
+    DevBuf<float> fused_hmp, fused_off;
+    DevBuf<float> hr_hmp, hr_off;
+    DevBuf<int32_t> kp_flip, limb_flip;
+    DevBuf<uint8_t> limb_reserved;
+
+    // state of the last decode
+    cudaEvent_t done;
+    cudaStream_t last_stream;
+    int last_n;
+    size_t last_meta_bytes;
+    int last_rows_copied;
+    int last_capacity_rows;
+    int rows_hint;
+    bool pending;
+};
+
+namespace {
+
+inline size_t meta_bytes_for(int n) { return ((size_t)(2 * n + 1) * sizeof(int32_t) + 15) / 16 * 16; }
+inline size_t pose_row_bytes(const og_handle *h) {
+    return (size_t)h->cfg.n_keypoints * OG_POSE_COLS * sizeof(float);
+}
+
+int check_device(const og_handle *h) {
+    int cur = -1;
+    OG_CUDA_TRY(cudaGetDevice(&cur));
+    OG_REQUIRE(cur == h->device, "handle is bound to CUDA device %d but the current device is %d",
+               h->device, cur);
+    return OG_OK;
+}
+
+int check_maps(int n, int hgt, int w, int c) {
+    OG_REQUIRE(n >= 0 && hgt > 0 && w > 0, "bad map shape n=%d h=%d w=%d", n, hgt, w);
+    OG_REQUIRE((long long)c * hgt * w < (1LL << 31), "C*H*W = %lld does not fit 31 bits",
+               (long long)c * hgt * w);
+    return OG_OK;
+}
+
+int run_k1(og_handle *h, const float *heat, int n, int hgt, int w, float thre, float *score,
+           int32_t *index, int32_t *count, cudaStream_t s) {
+    const int planes = n * h->cfg.n_keypoints;
+    OG_TRY(h->cand_count.ensure(planes));
+    OG_TRY(h->cand_keys.ensure((size_t)planes * kCandCap));
+    return launch_nms_topk(heat, planes, hgt, w, thre, h->cfg.topk, h->cand_count.ptr,
+                           h->cand_keys.ptr, score, index, count, false, true, s, &h->launches);
+}
+
+int run_k3(og_handle *h, const float *limbs, int n, float *out_poses, int capacity_rows,
+           int32_t *out_offset, int32_t *out_count, int32_t *out_total, cudaStream_t s) {
+    const og_config &c = h->cfg;
+    GroupLaunch g;
+    g.n = n;
+    g.c = c.n_keypoints;
+    g.l = c.n_limbs;
+    g.k = c.topk;
+    g.sk = h->sk;
+    g.dist_max = c.dist_max;
+    g.use_scale = c.use_scale;
+    g.person_thre = c.person_thre;
+    g.sort_dim = c.sort_dim;
+    g.smem_rows = h->smem_rows;
+    g.slab = nullptr;
+    g.slab_stride = 0;
+    const int pmax = c.n_limbs * c.topk;
+    if (h->smem_rows < pmax) {
+        g.slab_stride = ((size_t)pmax * c.n_keypoints * 6 + 3) / 4 * 4;
+        OG_TRY(h->slab.ensure(g.slab_stride * (size_t)n));
+        g.slab = h->slab.ptr;
+    }
+    OG_CUDA_TRY(cudaMemsetAsync(out_total, 0, sizeof(int32_t), s));
+    OG_TRY(launch_group(g, limbs, out_poses, capacity_rows, out_offset, out_count, out_total, s));
+    h->launches += 1;
+    return OG_OK;
+}
+
+int decode_maps_impl(og_handle *h, const float *heat, const float *offs, const float *scales, int n,
+                     int hgt, int w, cudaStream_t s) {
+    const og_config &c = h->cfg;
+    OG_TRY(check_maps(n, hgt, w, c.n_keypoints));
+    const size_t dets = (size_t)n * c.n_keypoints * c.topk;
+    OG_TRY(h->det_score.ensure(dets));
+    OG_TRY(h->det_index.ensure(dets));
+    OG_TRY(h->det_count.ensure((size_t)n * c.n_keypoints));
+    OG_TRY(h->limbs.ensure((size_t)n * c.n_limbs * c.topk * OG_LIMB_COLS));
+    const int capacity_rows = n * c.n_limbs * c.topk;
+    const size_t mbytes = meta_bytes_for(n);
+    OG_TRY(h->out.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
+    int32_t *meta = reinterpret_cast<int32_t *>(h->out.ptr);
+    float *poses = reinterpret_cast<float *>(h->out.ptr + mbytes);
+
+    h->pending = false;
+    h->last_n = n;
+    h->last_meta_bytes = mbytes;
+    h->last_capacity_rows = capacity_rows;
+    h->last_stream = s;
+    if (n == 0) {
+        h->last_rows_copied = 0;
+        return OG_OK;
+    }
+    OG_TRY(run_k1(h, heat, n, hgt, w, c.thre_hmp, h->det_score.ptr, h->det_index.ptr,
+                  h->det_count.ptr, s));
+    OG_TRY(launch_limb_score(h->det_score.ptr, h->det_index.ptr, offs, scales, n, c.n_keypoints,
+                             c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp, c.min_len,
+                             c.resize_factor, h->limbs.ptr, s));
+    h->launches += 1;
+    OG_TRY(run_k3(h, h->limbs.ptr, n, poses, capacity_rows, meta, meta + n, meta + 2 * n, s));
+
+    // one asynchronous copy: meta + the first rows_hint pose rows
+    const int rows = std::min(capacity_rows, std::max(h->rows_hint, n * 32));
+    const size_t bytes = mbytes + (size_t)rows * pose_row_bytes(h);
+    OG_TRY(h->out_host.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
+    OG_CUDA_TRY(cudaMemcpyAsync(h->out_host.ptr, h->out.ptr, bytes, cudaMemcpyDeviceToHost, s));
+    OG_CUDA_TRY(cudaEventRecord(h->done, s));
+    h->last_rows_copied = rows;
+    h->pending = true;
+    return OG_OK;
+}
+
+int upload_flip_tables(og_handle *h, const int32_t *kp_flip, const int32_t *limb_flip,
+                       const int32_t *limb_reserve, int n_reserve, cudaStream_t s) {
+    const og_config &c = h->cfg;
+    OG_REQUIRE(kp_flip && limb_flip && (n_reserve == 0 || limb_reserve),
+               "flip_test needs the keypoint / limb flip tables");
+    uint8_t reserved[OG_MAX_LIMBS] = {0};
+    for (int i = 0; i < c.n_keypoints; ++i)
+        OG_REQUIRE(kp_flip[i] >= 0 && kp_flip[i] < c.n_keypoints, "kp_flip[%d] out of range", i);
+    for (int i = 0; i < c.n_limbs; ++i)
+        OG_REQUIRE(limb_flip[i] >= 0 && limb_flip[i] < c.n_limbs, "limb_flip[%d] out of range", i);
+    for (int i = 0; i < n_reserve; ++i) {
+        OG_REQUIRE(limb_reserve[i] >= 0 && limb_reserve[i] < c.n_limbs, "limb_reserve[%d] out of range", i);
+        reserved[limb_reserve[i]] = 1;
+    }
+    OG_TRY(h->kp_flip.ensure(c.n_keypoints));
+    OG_TRY(h->limb_flip.ensure(c.n_limbs));
+    OG_TRY(h->limb_reserved.ensure(c.n_limbs));
+    // synchronous small copies from pageable memory: safe with respect to the caller's arrays
+    OG_CUDA_TRY(cudaMemcpyAsync(h->kp_flip.ptr, kp_flip, sizeof(int32_t) * c.n_keypoints, cudaMemcpyHostToDevice, s));
+    OG_CUDA_TRY(cudaMemcpyAsync(h->limb_flip.ptr, limb_flip, sizeof(int32_t) * c.n_limbs, cudaMemcpyHostToDevice, s));
+    OG_CUDA_TRY(cudaMemcpyAsync(h->limb_reserved.ptr, reserved, c.n_limbs, cudaMemcpyHostToDevice, s));
+    OG_CUDA_TRY(cudaStreamSynchronize(s));
+    return OG_OK;
+}
+
+int decode_features_impl(og_handle *h, const float *hmp, const float *off, int n, int hgt, int w,
+                         int hmp_stride, int off_stride, int resize_mode, int flip_test,
+                         const int32_t *kp_flip, const int32_t *limb_flip,
+                         const int32_t *limb_reserve, int n_reserve, cudaStream_t s) {
+    const og_config &c = h->cfg;
+    OG_REQUIRE(hmp_stride >= 1 && off_stride >= 1, "strides must be >= 1");
+    OG_REQUIRE(hmp_stride == off_stride,
+               "heat and offset maps must reach the same resolution (collect.py:81): strides %d vs %d",
+               hmp_stride, off_stride);
+    OG_REQUIRE(resize_mode == 0 || resize_mode == 1, "resize_mode must be 0 (bilinear) or 1 (bicubic)");
+    const float *cur_h = hmp, *cur_o = off;
+    const size_t hw = (size_t)hgt * w;
+    if (flip_test) {
+        OG_TRY(upload_flip_tables(h, kp_flip, limb_flip, limb_reserve, n_reserve, s));
+        OG_TRY(h->fused_hmp.ensure((size_t)n * c.n_keypoints * hw));
+        OG_TRY(h->fused_off.ensure((size_t)n * 2 * c.n_limbs * hw));
+        OG_TRY(launch_flip_fuse(cur_h, cur_o, h->kp_flip.ptr, h->limb_flip.ptr, h->limb_reserved.ptr,
+                                n, c.n_keypoints, c.n_limbs, hgt, w, h->fused_hmp.ptr,
+                                h->fused_off.ptr, s));
+        h->launches += 1;
+        cur_h = h->fused_hmp.ptr;
+        cur_o = h->fused_off.ptr;
+    }
+    int H = hgt, W = w;
+    if (hmp_stride > 1) {
+        H = hgt * hmp_stride;
+        W = w * hmp_stride;
+        OG_TRY(check_maps(n, H, W, c.n_keypoints));
+        OG_TRY(h->hr_hmp.ensure((size_t)n * c.n_keypoints * H * W));
+        OG_TRY(h->hr_off.ensure((size_t)n * 2 * c.n_limbs * H * W));
+        OG_TRY(launch_resize(cur_h, h->hr_hmp.ptr, n * c.n_keypoints, hgt, w, hmp_stride, resize_mode, s));
+        OG_TRY(launch_resize(cur_o, h->hr_off.ptr, n * 2 * c.n_limbs, hgt, w, off_stride, 0, s));
+        h->launches += 2;
+        cur_h = h->hr_hmp.ptr;
+        cur_o = h->hr_off.ptr;
+    }
+    return decode_maps_impl(h, cur_h, cur_o, nullptr, n, H, W, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *og_last_error(void) { return og::g_error; }
+
+const char *og_status_string(int status) {
+    switch (status) {
+        case OG_OK: return "ok";
+        case OG_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case OG_ERR_CUDA: return "CUDA error";
+        case OG_ERR_OUT_OF_MEMORY: return "out of memory";
+        case OG_ERR_CAPACITY: return "output capacity exceeded";
+        case OG_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown status";
+    }
+}
+
+int og_abi_version(void) { return OG_ABI_VERSION; }
+
+int og_create(const og_config *cfg, og_handle **out) {
+    OG_REQUIRE(cfg && out, "og_create: null argument");
+    *out = nullptr;
+    OG_REQUIRE(cfg->n_keypoints >= 1 && cfg->n_keypoints <= OG_MAX_KEYPOINTS,
+               "n_keypoints %d outside [1, %d]", cfg->n_keypoints, OG_MAX_KEYPOINTS);
+    OG_REQUIRE(cfg->n_limbs >= 1 && cfg->n_limbs <= OG_MAX_LIMBS, "n_limbs %d outside [1, %d]",
+               cfg->n_limbs, OG_MAX_LIMBS);
+    OG_REQUIRE(cfg->topk >= 1 && cfg->topk <= OG_MAX_TOPK, "topk %d outside [1, %d]", cfg->topk,
+               OG_MAX_TOPK);
+    OG_REQUIRE(cfg->limb_from && cfg->limb_to, "skeleton tables missing");
+    OG_REQUIRE(cfg->sort_dim >= 0 && cfg->sort_dim < OG_POSE_COLS, "sort_dim %d outside [0, 6)",
+               cfg->sort_dim);
+    OG_REQUIRE((long long)cfg->n_limbs * cfg->topk < 32768, "n_limbs * topk must stay below 32768");
+    for (int i = 0; i < cfg->n_limbs; ++i) {
+        OG_REQUIRE(cfg->limb_from[i] >= 0 && cfg->limb_from[i] < cfg->n_keypoints &&
+                       cfg->limb_to[i] >= 0 && cfg->limb_to[i] < cfg->n_keypoints,
+                   "limb %d references a keypoint outside [0, %d)", i, cfg->n_keypoints);
+    }
+    int device = cfg->device;
+    if (device < 0) {
+        OG_CUDA_TRY(cudaGetDevice(&device));
+    } else {
+        int cur = -1;
+        OG_CUDA_TRY(cudaGetDevice(&cur));
+        OG_REQUIRE(cur == device, "og_create: make device %d current first (current is %d)", device, cur);
+    }
+    cudaDeviceProp prop;
+    OG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("this library is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major,
+                  prop.minor);
+        return OG_ERR_UNSUPPORTED;
+    }
+
+    og_handle *h = new (std::nothrow) og_handle();
+    if (!h) {
+        set_error("host allocation failed");
+        return OG_ERR_OUT_OF_MEMORY;
+    }
+    h->cfg = *cfg;
+    h->cfg.limb_from = nullptr;
+    h->cfg.limb_to = nullptr;
+    for (int i = 0; i < cfg->n_limbs; ++i) {
+        h->sk.from[i] = cfg->limb_from[i];
+        h->sk.to[i] = cfg->limb_to[i];
+    }
+    h->device = device;
+    h->launches = 0;
+    h->pending = false;
+    h->last_n = 0;
+    h->rows_hint = 0;
+    h->last_stream = nullptr;
+
+    // person-table rows held in shared memory: as many as fit beside the work arrays
+    GroupLaunch g;
+    g.c = cfg->n_keypoints;
+    g.l = cfg->n_limbs;
+    g.k = cfg->topk;
+    const int pmax = cfg->n_limbs * cfg->topk;
+    const size_t budget = std::min<size_t>(prop.sharedMemPerBlockOptin, 200 * 1024);
+    g.smem_rows = 0;
+    const size_t fixed = group_smem_bytes(g);
+    if (fixed + (size_t)16 * cfg->n_keypoints * 24 > budget) {
+        delete h;
+        set_error("n_limbs * topk = %d needs %zu bytes of shared work arrays; unsupported", pmax, fixed);
+        return OG_ERR_UNSUPPORTED;
+    }
+    int rows = (int)((budget - fixed) / ((size_t)cfg->n_keypoints * 24));
+    rows = std::min(rows, std::min(pmax, 256));
+    g.smem_rows = rows;
+    h->smem_rows = rows;
+    h->group_smem = group_smem_bytes(g);
+    int st = prepare_group_kernel(h->group_smem);
+    if (st != OG_OK) {
+        delete h;
+        return st;
+    }
+    cudaError_t err = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
+    if (err != cudaSuccess) {
+        delete h;
+        set_error("cudaEventCreate failed: %s", cudaGetErrorString(err));
+        return OG_ERR_CUDA;
+    }
+    *out = h;
+    return OG_OK;
+}
+
+int og_destroy(og_handle *h) {
+    if (!h) return OG_OK;
+    cudaDeviceSynchronize();
+    h->cand_count.release();
+    h->cand_keys.release();
+    h->det_score.release();
+    h->det_index.release();
+    h->det_count.release();
+    h->limbs.release();
+    h->slab.release();
+    h->out.release();
+    h->out_host.release();
+    h->in_hmp.release();
+    h->in_off.release();
+    h->fused_hmp.release();
+    h->fused_off.release();
+    h->hr_hmp.release();
+    h->hr_off.release();
+    h->kp_flip.release();
+    h->limb_flip.release();
+    h->limb_reserved.release();
+    cudaEventDestroy(h->done);
+    delete h;
+    return OG_OK;
+}
+
+int og_hmp_nms_f32(const float *heat_dev, float *out_dev, int n, int c, int h, int w, void *stream) {
+    OG_REQUIRE(heat_dev && out_dev, "og_hmp_nms_f32: null pointer");
+    OG_TRY(check_maps(n, h, w, c));
+    return launch_hmp_nms(heat_dev, out_dev, n * c, h, w, static_cast<cudaStream_t>(stream));
+}
+
+int og_topk_channel_f32(og_handle *h, const float *scores_dev, int n, int c, int hgt, int w, int k,
+                        float *out_score_dev, int32_t *out_index_dev, void *stream) {
+    OG_REQUIRE(h && scores_dev && out_score_dev && out_index_dev, "og_topk_channel_f32: null pointer");
+    OG_TRY(check_device(h));
+    OG_TRY(check_maps(n, hgt, w, c));
+    OG_REQUIRE(k >= 1 && k <= kCandCap && (long long)k <= (long long)hgt * w,
+               "k = %d outside [1, min(%d, H*W)]", k, kCandCap);
+    return launch_nms_topk(scores_dev, n * c, hgt, w, -INFINITY, k, nullptr, nullptr, out_score_dev,
+                           out_index_dev, nullptr, true, false, static_cast<cudaStream_t>(stream),
+                           &h->launches);
+}
+
+int og_nms_topk_f32(og_handle *h, const float *heat_dev, int n, int hgt, int w, float thre,
+                    float *out_score_dev, int32_t *out_index_dev, int32_t *out_count_dev,
+                    void *stream) {
+    OG_REQUIRE(h && heat_dev && out_score_dev && out_index_dev, "og_nms_topk_f32: null pointer");
+    OG_TRY(check_device(h));
+    OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
+    return run_k1(h, heat_dev, n, hgt, w, thre, out_score_dev, out_index_dev, out_count_dev,
+                  static_cast<cudaStream_t>(stream));
+}
+
+int og_limb_score_f32(og_handle *h, const float *det_score_dev, const int32_t *det_index_dev,
+                      const float *offs_dev, const float *scales_dev, int n, int hgt, int w,
+                      float *out_limbs_dev, void *stream) {
+    OG_REQUIRE(h && det_score_dev && det_index_dev && offs_dev && out_limbs_dev,
+               "og_limb_score_f32: null pointer");
+    OG_TRY(check_device(h));
+    OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
+    const og_config &c = h->cfg;
+    OG_TRY(launch_limb_score(det_score_dev, det_index_dev, offs_dev, scales_dev, n, c.n_keypoints,
+                             c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp, c.min_len, c.resize_factor,
+                             out_limbs_dev, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return OG_OK;
+}
+
+int og_group_f32(og_handle *h, const float *limbs_dev, int n, float *out_poses_dev,
+                 int32_t capacity_rows, int32_t *out_offset_dev, int32_t *out_count_dev,
+                 int32_t *out_total_dev, void *stream) {
+    OG_REQUIRE(h && limbs_dev && out_poses_dev && out_offset_dev && out_count_dev && out_total_dev,
+               "og_group_f32: null pointer");
+    OG_REQUIRE(n >= 0 && capacity_rows >= 0, "og_group_f32: negative size");
+    OG_TRY(check_device(h));
+    return run_k3(h, limbs_dev, n, out_poses_dev, capacity_rows, out_offset_dev, out_count_dev,
+                  out_total_dev, static_cast<cudaStream_t>(stream));
+}
+
+int og_scored_offset_f32(og_handle *h, const float *hmp_dev, const float *off_dev, int n, int hgt,
+                         int w, int kernel_size, float *out_dev, void *stream) {
+    OG_REQUIRE(h && hmp_dev && off_dev && out_dev, "og_scored_offset_f32: null pointer");
+    OG_REQUIRE(kernel_size >= 1 && (kernel_size & 1), "kernel_size must be odd and positive");
+    OG_TRY(check_device(h));
+    OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
+    OG_TRY(launch_scored_offset(hmp_dev, off_dev, n, h->cfg.n_keypoints, h->cfg.n_limbs, hgt, w,
+                                kernel_size, h->sk, out_dev, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return OG_OK;
+}
+
+int og_flip_fuse_f32(og_handle *h, const float *hmp2n_dev, const float *off2n_dev,
+                     const int32_t *kp_flip, const int32_t *limb_flip, const int32_t *limb_reserve,
+                     int n_reserve, int n, int hgt, int w, float *out_hmp_dev, float *out_off_dev,
+                     void *stream) {
+    OG_REQUIRE(h && hmp2n_dev && off2n_dev && out_hmp_dev && out_off_dev, "og_flip_fuse_f32: null pointer");
+    OG_TRY(check_device(h));
+    OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OG_TRY(upload_flip_tables(h, kp_flip, limb_flip, limb_reserve, n_reserve, s));
+    OG_TRY(launch_flip_fuse(hmp2n_dev, off2n_dev, h->kp_flip.ptr, h->limb_flip.ptr,
+                            h->limb_reserved.ptr, n, h->cfg.n_keypoints, h->cfg.n_limbs, hgt, w,
+                            out_hmp_dev, out_off_dev, s));
+    h->launches += 1;
+    return OG_OK;
+}
+
+int og_resize_f32(const float *in_dev, float *out_dev, int planes, int hgt, int w, int scale,
+                  int mode, void *stream) {
+    OG_REQUIRE(in_dev && out_dev, "og_resize_f32: null pointer");
+    OG_REQUIRE(planes >= 0 && hgt > 0 && w > 0 && scale >= 1, "og_resize_f32: bad shape");
+    OG_REQUIRE(mode == 0 || mode == 1, "og_resize_f32: mode must be 0 (bilinear) or 1 (bicubic)");
+    return launch_resize(in_dev, out_dev, planes, hgt, w, scale, mode, static_cast<cudaStream_t>(stream));
+}
+
+int og_decode_maps(og_handle *h, const float *heat_dev, const float *offs_dev,
+                   const float *scales_dev, int n, int hgt, int w, void *stream) {
+    OG_REQUIRE(h && heat_dev && offs_dev, "og_decode_maps: null pointer");
+    OG_TRY(check_device(h));
+    return decode_maps_impl(h, heat_dev, offs_dev, scales_dev, n, hgt, w, static_cast<cudaStream_t>(stream));
+}
+
+int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_dev, int n, int hgt,
+                           int w, int hmp_stride, int off_stride, int resize_mode, int flip_test,
+                           const int32_t *kp_flip, const int32_t *limb_flip,
+                           const int32_t *limb_reserve, int n_reserve, void *stream) {
+    OG_REQUIRE(h && hmp_dev && off_dev, "og_decode_features_dev: null pointer");
+    OG_TRY(check_device(h));
+    OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
+    return decode_features_impl(h, hmp_dev, off_dev, n, hgt, w, hmp_stride, off_stride, resize_mode,
+                                flip_test, kp_flip, limb_flip, limb_reserve, n_reserve,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int og_decode_features_host(og_handle *h, const float *hmp_host, const float *off_host, int n,
+                            int hgt, int w, int hmp_stride, int off_stride, int resize_mode,
+                            int flip_test, const int32_t *kp_flip, const int32_t *limb_flip,
+                            const int32_t *limb_reserve, int n_reserve, void *stream) {
+    OG_REQUIRE(h && hmp_host && off_host, "og_decode_features_host: null pointer");
+    OG_TRY(check_device(h));
+    OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const og_config &c = h->cfg;
+    const size_t n_in = (size_t)(flip_test ? 2 * n : n);
+    const size_t hw = (size_t)hgt * w;
+    OG_TRY(h->in_hmp.ensure(n_in * c.n_keypoints * hw));
+    OG_TRY(h->in_off.ensure(n_in * 2 * c.n_limbs * hw));
+    OG_CUDA_TRY(cudaMemcpyAsync(h->in_hmp.ptr, hmp_host, n_in * c.n_keypoints * hw * sizeof(float),
+                                cudaMemcpyHostToDevice, s));
+    OG_CUDA_TRY(cudaMemcpyAsync(h->in_off.ptr, off_host, n_in * 2 * c.n_limbs * hw * sizeof(float),
+                                cudaMemcpyHostToDevice, s));
+    return decode_features_impl(h, h->in_hmp.ptr, h->in_off.ptr, n, hgt, w, hmp_stride, off_stride,
+                                resize_mode, flip_test, kp_flip, limb_flip, limb_reserve, n_reserve, s);
+}
+
+int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offset_host,
+                   const int32_t **count_host, int32_t *total_rows) {
+    OG_REQUIRE(h && poses_host && offset_host && count_host && total_rows, "og_fetch_poses: null pointer");
+    *poses_host = nullptr;
+    *offset_host = nullptr;
+    *count_host = nullptr;
+    *total_rows = 0;
+    if (h->last_n == 0) return OG_OK;
+    OG_REQUIRE(h->pending, "og_fetch_poses: no decode call is pending");
+    OG_CUDA_TRY(cudaEventSynchronize(h->done));
+    const int n = h->last_n;
+    const int32_t *meta = reinterpret_cast<const int32_t *>(h->out_host.ptr);
+    const int total = meta[2 * n];
+    if (total > h->last_capacity_rows) {
+        set_error("internal: %d pose rows exceed the worst-case capacity %d", total, h->last_capacity_rows);
+        return OG_ERR_CAPACITY;
+    }
+    if (total > h->last_rows_copied) {       // rare: more persons than the speculative copy covered
+        const size_t row = pose_row_bytes(h);
+        const size_t at = h->last_meta_bytes + (size_t)h->last_rows_copied * row;
+        OG_CUDA_TRY(cudaMemcpyAsync(h->out_host.ptr + at, h->out.ptr + at,
+                                    (size_t)(total - h->last_rows_copied) * row,
+                                    cudaMemcpyDeviceToHost, h->last_stream));
+        OG_CUDA_TRY(cudaStreamSynchronize(h->last_stream));
+        h->last_rows_copied = total;
+    }
+    h->rows_hint = std::max(h->rows_hint, total + total / 2);
+    *offset_host = meta;
+    *count_host = meta + n;
+    *total_rows = total;
+    *poses_host = reinterpret_cast<const float *>(h->out_host.ptr + h->last_meta_bytes);
+    return OG_OK;
+}
+
+int og_copy_intermediates(og_handle *h, int n, float *det_score_dev, int32_t *det_index_dev,
+                          float *limbs_dev, void *stream) {
+    OG_REQUIRE(h, "og_copy_intermediates: null handle");
+    OG_REQUIRE(n >= 0 && n <= h->last_n, "og_copy_intermediates: n = %d but the last decode had %d images",
+               n, h->last_n);
+    OG_TRY(check_device(h));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const og_config &c = h->cfg;
+    const size_t dets = (size_t)n * c.n_keypoints * c.topk;
+    if (det_score_dev && dets)
+        OG_CUDA_TRY(cudaMemcpyAsync(det_score_dev, h->det_score.ptr, dets * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (det_index_dev && dets)
+        OG_CUDA_TRY(cudaMemcpyAsync(det_index_dev, h->det_index.ptr, dets * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    const size_t lim = (size_t)n * c.n_limbs * c.topk * OG_LIMB_COLS;
+    if (limbs_dev && lim)
+        OG_CUDA_TRY(cudaMemcpyAsync(limbs_dev, h->limbs.ptr, lim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return OG_OK;
+}
+
+int64_t og_launch_count(const og_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

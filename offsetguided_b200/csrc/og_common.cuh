@@ -1,0 +1,109 @@
+// Shared declarations of the sm_100a decoder library (internal; the public ABI is
+// include/og_decoder.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/og_decoder.h"
+
+namespace og {
+
+// ---- error plumbing --------------------------------------------------------
+void set_error(const char *fmt, ...);
+
+#define OG_CUDA_TRY(expr)                                                          \
+    do {                                                                           \
+        cudaError_t err__ = (expr);                                                \
+        if (err__ != cudaSuccess) {                                                \
+            og::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,       \
+                          cudaGetErrorString(err__));                              \
+            return err__ == cudaErrorMemoryAllocation ? OG_ERR_OUT_OF_MEMORY       \
+                                                       : OG_ERR_CUDA;              \
+        }                                                                          \
+    } while (0)
+
+#define OG_REQUIRE(cond, ...)                                                      \
+    do {                                                                           \
+        if (!(cond)) {                                                             \
+            og::set_error(__VA_ARGS__);                                            \
+            return OG_ERR_INVALID_ARGUMENT;                                        \
+        }                                                                          \
+    } while (0)
+
+#define OG_TRY(expr)                                                               \
+    do {                                                                           \
+        int st__ = (expr);                                                         \
+        if (st__ != OG_OK) return st__;                                            \
+    } while (0)
+
+// ---- K1 candidate buffers --------------------------------------------------
+// Survivors of "3x3 peak and value >= thre" are appended per (image, channel)
+// plane as 64-bit keys: high word = ~ordered(value), low word = flat index, so an
+// ascending key order is (value desc, index asc).
+constexpr int kCandCap = 2048;        // per-plane capacity; overflow -> radix path
+
+__device__ __forceinline__ uint32_t ordered_bits(float v) {
+    uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t make_key(float v, uint32_t idx) {
+    return ((uint64_t)(~ordered_bits(v)) << 32) | idx;
+}
+__device__ __forceinline__ float key_value(uint64_t key) {
+    return from_ordered_bits(~(uint32_t)(key >> 32));
+}
+
+// ---- launchers (one per .cu file) -------------------------------------------
+struct SkeletonDev {
+    int32_t from[OG_MAX_LIMBS];
+    int32_t to[OG_MAX_LIMBS];
+};
+
+int launch_hmp_nms(const float *heat, float *out, int planes, int h, int w, cudaStream_t s);
+
+// pass 1: stream the heat map, append survivors; pass 2: per-plane select.
+// `force_radix` skips pass 1 and runs the exact radix selection on every plane;
+// `apply_nms` = 0 selects on the raw map (topK_channel).
+int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int k,
+                    uint32_t *cand_count, uint64_t *cand_keys,
+                    float *out_score, int32_t *out_index, int32_t *out_count,
+                    bool force_radix, bool apply_nms, cudaStream_t s, int64_t *launches);
+
+int launch_limb_score(const float *det_score, const int32_t *det_index, const float *offs,
+                      const float *scales, int n, int c, int l, int k, int h, int w,
+                      const SkeletonDev &sk, float thre_hmp, float min_len, float resize_factor,
+                      float *out_limbs, cudaStream_t s);
+
+struct GroupLaunch {
+    int n, c, l, k;
+    SkeletonDev sk;
+    float dist_max;
+    int use_scale;
+    double person_thre;
+    int sort_dim;
+    int smem_rows;              // person-table rows kept in shared memory
+    float *slab;                // global person tables, one per image (fallback)
+    size_t slab_stride;         // floats between images, multiple of 4
+};
+size_t group_smem_bytes(const GroupLaunch &g);
+int prepare_group_kernel(size_t smem_bytes);
+int launch_group(const GroupLaunch &g, const float *limbs, float *out_poses, int capacity_rows,
+                 int32_t *out_offset, int32_t *out_count, int32_t *out_total, cudaStream_t s);
+
+int launch_scored_offset(const float *hmp, const float *off, int n, int c, int l, int h, int w,
+                         int ksize, const SkeletonDev &sk, float *out, cudaStream_t s);
+int launch_flip_fuse(const float *hmp2n, const float *off2n, const int32_t *kp_flip_dev,
+                     const int32_t *limb_flip_dev, const uint8_t *limb_reserved_dev,
+                     int n, int c, int l, int h, int w, float *out_hmp, float *out_off,
+                     cudaStream_t s);
+int launch_resize(const float *in, float *out, int planes, int h, int w, int scale, int mode,
+                  cudaStream_t s);
+
+}  // namespace og

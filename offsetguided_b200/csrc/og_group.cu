@@ -1,0 +1,474 @@
+// K3 — greedy limb-ordered keypoint grouping, one CTA per image
+// (reference decoder/group.py:39-240, which runs per image in a CPU process pool).
+//
+// The person table lives in shared memory as three planes per (person row, joint):
+//   ids   int32   global keypoint id (-1 = unset)          pose column 5
+//   score float   best limb score seen for the joint       pose column 4
+//   xyvs  float4  x, y, keypoint score, keypoint scale     pose columns 0..3
+// Persons are addressed through an `order` list (logical position -> table row), so
+// deleting merged persons is a compaction of that small list, never a row move.
+//
+// The numpy program is sequential only in appearance; per limb type it is
+//   (1) gate + sort + dedup the K limb rows          -> rank sort, O(K^2) compares
+//   (2) match every person against every kept limb   -> one thread per person
+//   (3) apply "both ends known" / "one end known"    -> one thread per person; the
+//       reference's fancy-index scatter semantics (row-major pair order, last pair
+//       wins, right-hand sides read before the statement) reduce to "the last kept
+//       limb k that matches person m", because each thread owns its person row
+//   (4) merge persons sharing exactly two ids        -> one thread per person a,
+//       partner = largest b; survivors read rows that are being deleted, which
+//       nobody writes
+//   (5) append unclaimed limbs as new persons, using the reference's column-sum
+//       rule including its (-1)+(+1) cancellation quirk (group.py:166).
+// The table has `smem_rows` rows; if an image needs more (never seen outside noise
+// inputs) the same CTA restarts that image with the table in a global slab of
+// L*K rows, which cannot overflow (every new person consumes one limb row).
+#include "og_common.cuh"
+
+namespace og {
+
+namespace {
+
+constexpr int kGroupThreads = 256;
+
+enum Flag { kNValid = 0, kAnyP1, kAnyP2, kAnyMerge, kOutOffset, kNumFlags = 8 };
+
+struct GroupArgs {
+    int C, L, K;
+    SkeletonDev sk;
+    float dist_max;
+    int use_scale;
+    double person_thre;
+    int sort_dim;
+    int smem_rows;
+    float *slab;     // per image: xyvs float4[PMAX*C], score float[PMAX*C], ids int[PMAX*C]
+    size_t slab_stride;
+};
+
+struct Layout {
+    size_t xyvs, score, ids, conn, k_int, p_i16, p_u8, p_f64, warp, flags, total;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// k_int: 10 int arrays of K; p_i16: 6 int16 arrays of PMAX
+__host__ __device__ inline Layout make_layout(int C, int L, int K, int smem_rows) {
+    const size_t pmax = (size_t)L * K;
+    Layout lo;
+    size_t at = 0;
+    lo.xyvs = at;  at += (size_t)smem_rows * C * 16;
+    lo.score = at; at += (size_t)smem_rows * C * 4;
+    lo.ids = at;   at += (size_t)smem_rows * C * 4;
+    lo.conn = at;  at += align_up((size_t)K * OG_LIMB_COLS * 4, 16);
+    lo.k_int = at; at += (size_t)10 * K * 4;
+    at = align_up(at, 8);
+    lo.p_f64 = at; at += pmax * 8;
+    lo.p_i16 = at; at += align_up((size_t)6 * pmax * 2, 4);
+    lo.p_u8 = at;  at += align_up(pmax, 4);
+    lo.warp = at;  at += 32 * 4;
+    lo.flags = at; at += kNumFlags * 4;
+    lo.total = align_up(at, 16);
+    return lo;
+}
+
+// Exclusive scan of a predicate over [0, n): pos[i] = number of true entries before
+// i (written for every i < n); returns the total.  All threads must call it.
+template <typename Pred>
+__device__ int block_scan(int n, Pred pred, int16_t *pos, int *s_warp) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int running = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool f = (i < n) && pred(i);
+        const unsigned ballot = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_warp[wid] = __popc(ballot);
+        __syncthreads();
+        int before = 0, tot = 0;
+        for (int w = 0; w < nw; ++w) {
+            const int c = s_warp[w];
+            if (w < wid) before += c;
+            tot += c;
+        }
+        if (i < n) pos[i] = (int16_t)(running + before + __popc(ballot & ((1u << lane) - 1u)));
+        running += tot;
+        __syncthreads();
+    }
+    return running;
+}
+
+// numpy's float32 pairwise summation for n <= 128 (loops_utils.h.src, probed).
+__device__ float numpy_sum_f32(const float *a, int n) {
+    if (n < 8) {
+        float s = 0.0f;
+        for (int i = 0; i < n; ++i) s = __fadd_rn(s, a[i]);
+        return s;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+    }
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) s = __fadd_rn(s, a[i]);
+    return s;
+}
+
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+    return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+__device__ __forceinline__ float unset_to_zero(float v) { return v == -1.0f ? 0.0f : v; }
+
+__global__ void __launch_bounds__(kGroupThreads)
+group_kernel(GroupArgs a, const float *__restrict__ limbs, float *__restrict__ out_poses,
+             int capacity_rows, int32_t *__restrict__ out_offset, int32_t *__restrict__ out_count,
+             int32_t *__restrict__ out_total) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int C = a.C, L = a.L, K = a.K;
+    const int pmax = L * K;
+    const Layout lo = make_layout(C, L, K, a.smem_rows);
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int img = blockIdx.x;
+
+    float *s_conn = reinterpret_cast<float *>(smem + lo.conn);
+    int *kbase = reinterpret_cast<int *>(smem + lo.k_int);
+    int *s_valid = kbase + 0 * K;
+    int *s_sorted = kbase + 1 * K;
+    int *s_keep = kbase + 2 * K;
+    int *s_kept = kbase + 3 * K;
+    int *s_kind1 = kbase + 4 * K;
+    int *s_kind2 = kbase + 5 * K;
+    float *s_kscore = reinterpret_cast<float *>(kbase + 6 * K);
+    int *s_n1 = kbase + 7 * K;
+    int *s_n2 = kbase + 8 * K;
+    int *s_isnew = kbase + 9 * K;
+    int16_t *pbase = reinterpret_cast<int16_t *>(smem + lo.p_i16);
+    int16_t *s_order = pbase + 0 * pmax;
+    int16_t *s_order2 = pbase + 1 * pmax;
+    int16_t *s_pk1 = pbase + 2 * pmax;
+    int16_t *s_pk2 = pbase + 3 * pmax;
+    int16_t *s_blast = pbase + 4 * pmax;
+    int16_t *s_pos = pbase + 5 * pmax;
+    uint8_t *s_del = smem + lo.p_u8;
+    double *s_ps = reinterpret_cast<double *>(smem + lo.p_f64);
+    int *s_warp = reinterpret_cast<int *>(smem + lo.warp);
+    volatile int *s_flag = reinterpret_cast<volatile int *>(smem + lo.flags);
+
+    const float *limbs_img = limbs + (size_t)img * L * K * OG_LIMB_COLS;
+
+    float4 *xyvs = nullptr;
+    float *score = nullptr;
+    int *ids = nullptr;
+    int mm = 0;
+
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int pcap;
+        if (attempt == 0) {
+            xyvs = reinterpret_cast<float4 *>(smem + lo.xyvs);
+            score = reinterpret_cast<float *>(smem + lo.score);
+            ids = reinterpret_cast<int *>(smem + lo.ids);
+            pcap = a.smem_rows;
+        } else {
+            float *base = a.slab + (size_t)img * a.slab_stride;
+            xyvs = reinterpret_cast<float4 *>(base);
+            score = base + (size_t)pmax * C * 4;
+            ids = reinterpret_cast<int *>(base + (size_t)pmax * C * 5);
+            pcap = pmax;
+        }
+        mm = 0;
+        int nalloc = 0;
+        bool overflow = false;
+        __syncthreads();
+
+        for (int li = 0; li < L && !overflow; ++li) {
+            const int jf = a.sk.from[li], jt = a.sk.to[li];
+            // ---- stage the K rows of this limb type
+            for (int i = tid; i < K * OG_LIMB_COLS; i += T) s_conn[i] = limbs_img[(size_t)li * K * OG_LIMB_COLS + i];
+            if (tid < kNumFlags) s_flag[tid] = 0;
+            __syncthreads();
+            // ---- gate (group.py:64-76)
+            for (int k = tid; k < K; k += T) {
+                const float *r = s_conn + k * OG_LIMB_COLS;
+                float lim = a.dist_max;
+                if (a.use_scale) lim = (r[12] != r[12]) ? r[12] : fmaxf(a.dist_max, r[12]);
+                const bool v = (r[8] < lim) && (r[0] > 0.f) && (r[4] > 0.f) && (r[3] > 0.f) &&
+                               (r[1] > 0.f) && (r[10] == r[10]);
+                s_valid[k] = v ? 1 : 0;
+            }
+            __syncthreads();
+            // ---- sort by limb score desc, ties by row asc (group.py:232, canonical stable)
+            for (int k = tid; k < K; k += T) {
+                if (!s_valid[k]) continue;
+                const float sc = s_conn[k * OG_LIMB_COLS + 10];
+                int rank = 0;
+                for (int j = 0; j < K; ++j) {
+                    if (!s_valid[j]) continue;
+                    const float sj = s_conn[j * OG_LIMB_COLS + 10];
+                    rank += (sj > sc || (sj == sc && j < k)) ? 1 : 0;
+                }
+                s_sorted[rank] = k;
+                atomicAdd(const_cast<int *>(&s_flag[kNValid]), 1);
+            }
+            __syncthreads();
+            const int nvalid = s_flag[kNValid];
+            // ---- keep the best row per to-joint id (group.py:233-239)
+            for (int r = tid; r < nvalid; r += T) {
+                const int t = (int)s_conn[s_sorted[r] * OG_LIMB_COLS + 7];
+                bool dup = false;
+                for (int r2 = 0; r2 < r && !dup; ++r2)
+                    dup = ((int)s_conn[s_sorted[r2] * OG_LIMB_COLS + 7] == t);
+                s_keep[r] = dup ? 0 : 1;
+            }
+            __syncthreads();
+            const int kk = block_scan(nvalid, [&](int r) { return s_keep[r] != 0; }, s_pos, s_warp);
+            for (int r = tid; r < nvalid; r += T) {
+                if (!s_keep[r]) continue;
+                const int j = s_pos[r], k = s_sorted[r];
+                s_kept[j] = k;
+                s_kind1[j] = (int)s_conn[k * OG_LIMB_COLS + 6];
+                s_kind2[j] = (int)s_conn[k * OG_LIMB_COLS + 7];
+                s_kscore[j] = s_conn[k * OG_LIMB_COLS + 10];
+                s_n1[j] = 0;
+                s_n2[j] = 0;
+            }
+            __syncthreads();
+            if (kk == 0) continue;                                         // group.py:84-85
+
+            // ---- match persons x kept limbs on the pre-update snapshot (group.py:87-109)
+            for (int m = tid; m < mm; m += T) {
+                const int row = s_order[m];
+                const int idf = ids[row * C + jf], idt = ids[row * C + jt];
+                const float sf = score[row * C + jf], st = score[row * C + jt];
+                int k1 = -1, k2 = -1;
+                for (int j = 0; j < kk; ++j) {
+                    const int ms = (idf == s_kind1[j] ? 1 : 0) + (idt == s_kind2[j] ? 1 : 0);
+                    if (ms == 0) continue;
+                    const float sc = s_kscore[j];
+                    const bool rep = (sc > st) || (sc > sf);
+                    if (ms == 2) {
+                        atomicAdd(&s_n2[j], 1);
+                        if (rep) k2 = j;
+                    } else {
+                        atomicAdd(&s_n1[j], 1);
+                        if (rep) k1 = j;
+                    }
+                }
+                s_pk1[m] = (int16_t)k1;
+                s_pk2[m] = (int16_t)k2;
+                if (k1 >= 0) s_flag[kAnyP1] = 1;
+                if (k2 >= 0) s_flag[kAnyP2] = 1;
+            }
+            __syncthreads();
+            // ---- apply: both ends known (group.py:114-119), then one end known (:124-135)
+            for (int m = tid; m < mm; m += T) {
+                const int row = s_order[m];
+                const int k2 = s_pk2[m];
+                if (k2 >= 0) {
+                    const float sc = s_kscore[k2];
+                    score[row * C + jf] = fmaxf(sc, score[row * C + jf]);
+                    score[row * C + jt] = fmaxf(sc, score[row * C + jt]);
+                }
+                const int k1 = s_pk1[m];
+                if (k1 >= 0) {
+                    const float *r = s_conn + s_kept[k1] * OG_LIMB_COLS;
+                    ids[row * C + jf] = s_kind1[k1];
+                    ids[row * C + jt] = s_kind2[k1];
+                    xyvs[row * C + jf] = make_float4(r[0], r[1], r[2], r[11]);
+                    xyvs[row * C + jt] = make_float4(r[3], r[4], r[5], r[12]);
+                    const float sc = s_kscore[k1];
+                    score[row * C + jf] = fmaxf(sc, score[row * C + jf]);
+                    score[row * C + jt] = fmaxf(sc, score[row * C + jt]);
+                }
+            }
+            __syncthreads();
+            // ---- merge persons sharing exactly two keypoint ids (group.py:140-155)
+            int mm_after = mm;
+            if (mm >= 2) {
+                for (int p = tid; p < mm; p += T) {
+                    s_blast[p] = -1;
+                    s_del[p] = 0;
+                }
+                __syncthreads();
+                for (int p = tid; p < mm; p += T) {
+                    const int rowa = s_order[p];
+                    for (int q = p + 1; q < mm; ++q) {
+                        const int rowb = s_order[q];
+                        int cnt = 0;
+                        for (int c = 0; c < C; ++c) {
+                            const int ia = ids[rowa * C + c];
+                            cnt += (ia != -1 && ia == ids[rowb * C + c]) ? 1 : 0;
+                        }
+                        if (cnt == 2) {
+                            s_blast[p] = (int16_t)q;     // ascending q: the last partner wins
+                            s_del[q] = 1;
+                            s_flag[kAnyMerge] = 1;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (s_flag[kAnyMerge]) {
+                    for (int p = tid; p < mm; p += T) {
+                        const int q = s_blast[p];
+                        if (q < 0 || s_del[p]) continue;      // deleted rows are never read again
+                        const int rowa = s_order[p], rowb = s_order[q];
+                        for (int c = 0; c < C; ++c) {
+                            ids[rowa * C + c] = max(ids[rowa * C + c], ids[rowb * C + c]);
+                            score[rowa * C + c] = fmaxf(score[rowa * C + c], score[rowb * C + c]);
+                            xyvs[rowa * C + c] = max4(xyvs[rowa * C + c], xyvs[rowb * C + c]);
+                        }
+                    }
+                    mm_after = block_scan(mm, [&](int p) { return s_del[p] == 0; }, s_pos, s_warp);
+                    for (int p = tid; p < mm; p += T)
+                        if (!s_del[p]) s_order2[s_pos[p]] = s_order[p];
+                    __syncthreads();
+                    int16_t *tmp = s_order;
+                    s_order = s_order2;
+                    s_order2 = tmp;
+                }
+            }
+            // ---- unclaimed limbs start new persons (group.py:166-177)
+            {
+                const int w2 = s_flag[kAnyP2] ? -1 : 2;
+                const int w1 = s_flag[kAnyP1] ? -1 : 1;
+                for (int j = tid; j < kk; j += T) s_isnew[j] = (s_n2[j] * w2 + s_n1[j] * w1 == 0) ? 1 : 0;
+            }
+            __syncthreads();
+            const int nnew = block_scan(kk, [&](int j) { return s_isnew[j] != 0; }, s_pos, s_warp);
+            if (nalloc + nnew > pcap) {
+                overflow = true;          // uniform: restart this image on the global slab
+                continue;
+            }
+            for (int j = tid; j < kk; j += T) {
+                if (!s_isnew[j]) continue;
+                s_sorted[s_pos[j]] = j;                        // s_sorted is free now: new list
+                s_order[mm_after + s_pos[j]] = (int16_t)(nalloc + s_pos[j]);
+            }
+            __syncthreads();
+            for (int e = tid; e < nnew * C; e += T) {
+                const int q = e / C, c = e - q * C;
+                const int j = s_sorted[q];
+                const int at = (nalloc + q) * C + c;
+                const float *r = s_conn + s_kept[j] * OG_LIMB_COLS;
+                if (c == jt) {
+                    ids[at] = s_kind2[j];
+                    xyvs[at] = make_float4(r[3], r[4], r[5], r[12]);
+                    score[at] = s_kscore[j];
+                } else if (c == jf) {
+                    ids[at] = s_kind1[j];
+                    xyvs[at] = make_float4(r[0], r[1], r[2], r[11]);
+                    score[at] = s_kscore[j];
+                } else {
+                    ids[at] = -1;
+                    xyvs[at] = make_float4(-1.f, -1.f, -1.f, -1.f);
+                    score[at] = -1.0f;
+                }
+            }
+            nalloc += nnew;
+            mm = mm_after + nnew;
+            __syncthreads();
+        }
+        if (!overflow) break;
+    }
+
+    // ---- person score, threshold, stable descending sort (group.py:188-219)
+    for (int m = tid; m < mm; m += T) {
+        const int row = s_order[m];
+        float vals[OG_MAX_KEYPOINTS];
+        int n = 0;
+        for (int c = 0; c < C; ++c) {
+            float v;
+            const float4 q = xyvs[row * C + c];
+            switch (a.sort_dim) {
+                case 0: v = q.x; break;
+                case 1: v = q.y; break;
+                case 2: v = q.z; break;
+                case 3: v = q.w; break;
+                case 4: v = score[row * C + c]; break;
+                default: v = (float)ids[row * C + c]; break;
+            }
+            if (v > 0.0f) vals[n++] = v;
+        }
+        const double ps = (double)numpy_sum_f32(vals, n) / (double)n;      // 0/0 -> NaN, kept
+        s_ps[m] = ps;
+        s_del[m] = (ps < a.person_thre) ? 1 : 0;
+    }
+    __syncthreads();
+    const int nk = block_scan(mm, [&](int m) { return s_del[m] == 0; }, s_pos, s_warp);
+    for (int m = tid; m < mm; m += T)
+        if (!s_del[m]) s_order2[s_pos[m]] = (int16_t)m;        // kept persons, original order
+    __syncthreads();
+    for (int q = tid; q < nk; q += T) {
+        double ps = s_ps[s_order2[q]];
+        if (ps != ps) ps = -1.0e300;        // documented deviation: NaN scores sort last
+        int rank = 0;
+        for (int q2 = 0; q2 < nk; ++q2) {
+            double p2 = s_ps[s_order2[q2]];
+            if (p2 != p2) p2 = -1.0e300;
+            rank += (p2 > ps || (p2 == ps && q2 < q)) ? 1 : 0;
+        }
+        s_blast[q] = (int16_t)rank;
+    }
+    if (tid == 0) {
+        const int off = atomicAdd(out_total, nk);
+        s_flag[kOutOffset] = off;
+        out_offset[img] = off;
+        out_count[img] = nk;
+    }
+    __syncthreads();
+    const int off = s_flag[kOutOffset];
+    for (int e = tid; e < nk * C; e += T) {
+        const int q = e / C, c = e - q * C;
+        const int dst = off + s_blast[q];
+        if (dst >= capacity_rows) continue;
+        const int row = s_order[s_order2[q]];
+        const float4 v = xyvs[row * C + c];
+        float *o = out_poses + ((size_t)dst * C + c) * OG_POSE_COLS;
+        o[0] = unset_to_zero(v.x);
+        o[1] = unset_to_zero(v.y);
+        o[2] = unset_to_zero(v.z);
+        o[3] = unset_to_zero(v.w);
+        o[4] = unset_to_zero(score[row * C + c]);
+        o[5] = unset_to_zero((float)ids[row * C + c]);
+    }
+}
+
+GroupArgs to_args(const GroupLaunch &g) {
+    GroupArgs a;
+    a.C = g.c;
+    a.L = g.l;
+    a.K = g.k;
+    a.sk = g.sk;
+    a.dist_max = g.dist_max;
+    a.use_scale = g.use_scale;
+    a.person_thre = g.person_thre;
+    a.sort_dim = g.sort_dim;
+    a.smem_rows = g.smem_rows;
+    a.slab = g.slab;
+    a.slab_stride = g.slab_stride;
+    return a;
+}
+
+}  // namespace
+
+size_t group_smem_bytes(const GroupLaunch &g) { return make_layout(g.c, g.l, g.k, g.smem_rows).total; }
+
+int prepare_group_kernel(size_t smem_bytes) {
+    OG_CUDA_TRY(cudaFuncSetAttribute(group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes));
+    return OG_OK;
+}
+
+int launch_group(const GroupLaunch &g, const float *limbs, float *out_poses, int capacity_rows,
+                 int32_t *out_offset, int32_t *out_count, int32_t *out_total, cudaStream_t s) {
+    if (g.n == 0) return OG_OK;
+    const size_t smem = group_smem_bytes(g);
+    group_kernel<<<g.n, kGroupThreads, smem, s>>>(to_args(g), limbs, out_poses, capacity_rows,
+                                                  out_offset, out_count, out_total);
+    OG_CUDA_TRY(cudaGetLastError());
+    return OG_OK;
+}
+
+}  // namespace og

@@ -1,0 +1,128 @@
+// K2 — limb candidate scoring (reference decoder/collect.py:100-233).
+//
+// One CTA per (limb type, image).  The K to-joint candidates are staged in shared
+// memory; thread k owns from-candidate k: it gathers the guiding offset at its
+// peak pixel, adds it to the peak position, scans the K to-candidates for the
+// nearest one (first index wins ties, exactly like Tensor.min), and writes the 13
+// limb columns.  Everything is float32 with the reference's rounding sequence:
+// separate multiply / add where eager torch runs separate kernels, and
+// sqrt(fma(dy, dy, dx*dx)) for Tensor.norm over an (x, y) pair (probed against
+// ATen's CPU kernel).  ~40 eager launches of the reference collapse into this one.
+#include "og_common.cuh"
+
+namespace og {
+
+namespace {
+
+struct ToCand {
+    float x, y, score, scale;
+    int32_t index;
+};
+
+__device__ __forceinline__ float norm2(float dx, float dy) {
+    return __fsqrt_rn(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+__global__ void __launch_bounds__(128)
+limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict__ det_index,
+                  const float *__restrict__ offs, const float *__restrict__ scales,
+                  int C, int L, int K, int H, int W, SkeletonDev sk, float thre_hmp,
+                  float min_len, float resize_factor, float *__restrict__ out_limbs) {
+    __shared__ ToCand s_to[OG_MAX_TOPK];
+    const int l = blockIdx.x;
+    const int n = blockIdx.y;
+    const int jf = sk.from[l], jt = sk.to[l];
+    const long long HW = (long long)H * W;
+
+    // candidate k of channel j: position, score; sub-threshold candidates (and the
+    // empty slots K1 leaves behind, index -1) are moved 100000 px off the image
+    // (collect.py:253, integer arithmetic before the float conversion)
+    auto candidate = [&](int j, int k, float &x, float &y, float &s, int32_t &idx) {
+        const size_t at = ((size_t)n * C + j) * K + k;
+        s = det_score[at];
+        idx = det_index[at];
+        int xi = 0, yi = 0;
+        if (idx >= 0) {
+            yi = idx / W;
+            xi = idx - yi * W;
+        }
+        if (s < thre_hmp) {
+            xi -= 100000;
+            yi -= 100000;
+        }
+        x = (float)xi;
+        y = (float)yi;
+    };
+
+    for (int m = threadIdx.x; m < K; m += blockDim.x) {
+        ToCand t;
+        candidate(jt, m, t.x, t.y, t.score, t.index);
+        t.scale = 4.0f;                                              // collect.py:120
+        if (scales != nullptr && t.index >= 0)
+            t.scale = __ldg(scales + ((size_t)n * C + jt) * HW + t.index);   // collect.py:114
+        s_to[m] = t;
+    }
+    __syncthreads();
+
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float x1, y1, s1;
+        int32_t idx1;
+        candidate(jf, k, x1, y1, s1, idx1);
+        float ox = 0.0f, oy = 0.0f, scale1 = 4.0f;
+        if (idx1 >= 0) {
+            const float *o = offs + ((size_t)n * 2 * L + 2 * l) * HW + idx1;   // collect.py:143-147
+            ox = __ldg(o);
+            oy = __ldg(o + HW);
+            if (scales != nullptr) scale1 = __ldg(scales + ((size_t)n * C + jf) * HW + idx1);
+        }
+        const float gx = __fadd_rn(x1, __fmul_rn(ox, resize_factor));         // collect.py:152
+        const float gy = __fadd_rn(y1, __fmul_rn(oy, resize_factor));
+
+        float best = norm2(__fsub_rn(gx, s_to[0].x), __fsub_rn(gy, s_to[0].y));
+        int best_m = 0;
+        for (int m = 1; m < K; ++m) {                                          // collect.py:171-177
+            const float d = norm2(__fsub_rn(gx, s_to[m].x), __fsub_rn(gy, s_to[m].y));
+            if (d < best) {
+                best = d;
+                best_m = m;
+            }
+        }
+        const ToCand t = s_to[best_m];
+        const float len = fmaxf(norm2(__fsub_rn(x1, t.x), __fsub_rn(y1, t.y)), min_len);   // :204
+        const float score = __fmul_rn(__fmul_rn(s1, t.score), expf(__fdiv_rn(-best, len)));  // :208
+        const long long g1 = (long long)idx1 + (long long)jf * HW;             // collect.py:198-199
+        const long long g2 = (long long)t.index + (long long)jt * HW;
+
+        float *o = out_limbs + (((size_t)n * L + l) * K + k) * OG_LIMB_COLS;    // collect.py:223-233
+        o[0] = x1;
+        o[1] = y1;
+        o[2] = s1;
+        o[3] = t.x;
+        o[4] = t.y;
+        o[5] = t.score;
+        o[6] = __ll2float_rn(g1);
+        o[7] = __ll2float_rn(g2);
+        o[8] = best;
+        o[9] = len;
+        o[10] = score;
+        o[11] = scale1;
+        o[12] = t.scale;
+    }
+}
+
+}  // namespace
+
+int launch_limb_score(const float *det_score, const int32_t *det_index, const float *offs,
+                      const float *scales, int n, int c, int l, int k, int h, int w,
+                      const SkeletonDev &sk, float thre_hmp, float min_len, float resize_factor,
+                      float *out_limbs, cudaStream_t s) {
+    if (n == 0) return OG_OK;
+    const int threads = k <= 32 ? 32 : (k <= 64 ? 64 : 128);
+    dim3 grid(l, n);
+    limb_score_kernel<<<grid, threads, 0, s>>>(det_score, det_index, offs, scales, c, l, k, h, w, sk,
+                                              thre_hmp, min_len, resize_factor, out_limbs);
+    OG_CUDA_TRY(cudaGetLastError());
+    return OG_OK;
+}
+
+}  // namespace og

@@ -1,0 +1,387 @@
+// K1 — fused 3x3 max-pool NMS + candidate threshold + per-channel top-K.
+//
+// Replaces the reference's eager chain F.pad -> F.max_pool2d -> == -> .float() -> *
+// -> torch.topk (decoder/heatmap.py:15-59) and the `score < thre_hmp` filter of
+// decoder/collect.py:253, which together make ~6 full passes over the
+// (N, C, H, W) heat map.  Here the map is streamed from HBM exactly once:
+//
+//   pass 1  nms_candidates_kernel   one warp per (plane, 128-column strip, row
+//           chunk); 128-bit ld.global.nc loads, a rolling 3-row window of
+//           horizontal maxima in registers, neighbours across lanes through warp
+//           shuffles, zero padding at the image border (reference pads with 0,
+//           not -inf).  The few survivors (peak and value >= thre) are appended
+//           to a per-plane candidate list as sortable 64-bit keys.
+//   pass 2  select_topk_kernel      one CTA per plane ranks the candidates by
+//           (value desc, flat index asc) and writes the first K.
+//
+// A plane with more than kCandCap survivors (noise maps, thre <= 0, or the
+// stand-alone topK_channel API) is handled inside pass 2 by an exact MSB-first
+// radix selection over the plane itself, so the result is the exact top-K for
+// every input — there is no approximate or host-side fallback.
+#include "og_common.cuh"
+
+namespace og {
+
+namespace {
+
+constexpr int kRowsPerWarp = 64;     // rows of one warp's strip (halo re-read 2/64)
+constexpr int kUnroll = 8;           // rows fetched ahead per lane (8 x 16 B in flight)
+constexpr int kSelectThreads = 256;
+constexpr int kRadixBins = 2048;
+
+__device__ __forceinline__ float4 ldg_stream_f4(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// NMS value of one pixel as the reference defines it: heat * (maxpool == heat).
+template <bool kThrePositive>
+__device__ __forceinline__ bool survives(float v, float m, float thre, float &nv) {
+    if (kThrePositive) {            // thre > 0: non-peaks (value 0) can never pass
+        nv = v;
+        return v >= fmaxf(m, thre);
+    }
+    nv = (v == m) ? v : 0.0f;
+    return nv >= thre;
+}
+
+template <bool kThrePositive, bool kVec4>
+__global__ void __launch_bounds__(256)
+nms_candidates_kernel(const float *__restrict__ heat, int planes, int H, int W, float thre,
+                      uint32_t *__restrict__ cand_count, uint64_t *__restrict__ cand_keys) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int strips = (W + 127) >> 7;
+    const int chunks = (H + kRowsPerWarp - 1) / kRowsPerWarp;
+    const long long total = (long long)planes * chunks * strips;
+    if (warp >= total) return;
+    const int strip = (int)(warp % strips);
+    const long long t = warp / strips;
+    const int chunk = (int)(t % chunks);
+    const int plane = (int)(t / chunks);
+
+    const int x0 = (strip << 7) + (lane << 2);
+    const float *__restrict__ p = heat + (size_t)plane * H * W;
+    const int r_begin = chunk * kRowsPerWarp;
+    const int r_end = min(H, r_begin + kRowsPerWarp);
+
+    // lane 0 / lane 31 fetch the column just outside the warp's strip
+    int hx = -1;
+    if (lane == 0 && x0 > 0) hx = x0 - 1;
+    if (lane == 31 && x0 + 4 < W) hx = x0 + 4;
+
+    auto load_row = [&](int r, float4 &v, float &e) {
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        e = 0.f;
+        if (r >= 0 && r < H) {
+            const float *row = p + (size_t)r * W;
+            if (kVec4) {
+                if (x0 < W) v = ldg_stream_f4(row + x0);
+            } else {
+                if (x0 + 0 < W) v.x = __ldg(row + x0 + 0);
+                if (x0 + 1 < W) v.y = __ldg(row + x0 + 1);
+                if (x0 + 2 < W) v.z = __ldg(row + x0 + 2);
+                if (x0 + 3 < W) v.w = __ldg(row + x0 + 3);
+            }
+            if (hx >= 0) e = __ldg(row + hx);
+        }
+    };
+    auto hmax_row = [&](const float4 &v, float e) {
+        float left = __shfl_up_sync(0xffffffffu, v.w, 1);
+        float right = __shfl_down_sync(0xffffffffu, v.x, 1);
+        if (lane == 0) left = e;
+        if (lane == 31) right = e;
+        return make_float4(max3(left, v.x, v.y), max3(v.x, v.y, v.z),
+                           max3(v.y, v.z, v.w), max3(v.z, v.w, right));
+    };
+    auto emit = [&](float v, float m, int x, int r) {
+        float nv;
+        if (x < W && survives<kThrePositive>(v, m, thre, nv)) {
+            nv += 0.0f;     // -0 -> +0 so that equal values have equal keys
+            const uint32_t pos = atomicAdd(&cand_count[plane], 1u);
+            if (pos < (uint32_t)kCandCap)
+                cand_keys[(size_t)plane * kCandCap + pos] = make_key(nv, (uint32_t)(r * W + x));
+        }
+    };
+
+    float4 v_cur, h_prev, h_cur;
+    {
+        float4 v;
+        float e;
+        load_row(r_begin - 1, v, e);
+        h_prev = hmax_row(v, e);
+        load_row(r_begin, v_cur, e);
+        h_cur = hmax_row(v_cur, e);
+    }
+    for (int r = r_begin; r < r_end; r += kUnroll) {
+        float4 vn[kUnroll];
+        float en[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (r + u < r_end) load_row(r + 1 + u, vn[u], en[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (r + u < r_end) {
+                const float4 h_next = hmax_row(vn[u], en[u]);
+                const int row = r + u;
+                emit(v_cur.x, max3(h_prev.x, h_cur.x, h_next.x), x0 + 0, row);
+                emit(v_cur.y, max3(h_prev.y, h_cur.y, h_next.y), x0 + 1, row);
+                emit(v_cur.z, max3(h_prev.z, h_cur.z, h_next.z), x0 + 2, row);
+                emit(v_cur.w, max3(h_prev.w, h_cur.w, h_next.w), x0 + 3, row);
+                h_prev = h_cur;
+                h_cur = h_next;
+                v_cur = vn[u];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pass 2
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float nms_value(const float *__restrict__ p, int H, int W, int i,
+                                           bool apply_nms) {
+    float v = __ldg(p + i);
+    if (apply_nms) {
+        const int y = i / W, x = i - y * W;
+        float m = 0.0f;   // zero padding takes part in the maximum at the border only
+        bool border = (y == 0) | (x == 0) | (y == H - 1) | (x == W - 1);
+        if (!border) m = v;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = x + dx;
+                if (xx < 0 || xx >= W) continue;
+                m = fmaxf(m, __ldg(p + yy * W + xx));
+            }
+        }
+        v = (v == m) ? v : 0.0f;
+    }
+    return v + 0.0f;
+}
+
+// Rank `n` distinct keys held in shared memory and write the K smallest.
+__device__ void write_ranked(const uint64_t *keys, int n, int K, float *out_score,
+                             int32_t *out_index) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t key = keys[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (keys[j] < key) ? 1 : 0;
+        if (rank < K) {
+            out_score[rank] = key_value(key);
+            out_index[rank] = (int32_t)(uint32_t)key;
+        }
+    }
+    for (int r = n + threadIdx.x; r < K; r += blockDim.x) {
+        out_score[r] = 0.0f;
+        out_index[r] = -1;
+    }
+}
+
+__global__ void __launch_bounds__(kSelectThreads)
+select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int K,
+                   const uint32_t *__restrict__ cand_count,
+                   const uint64_t *__restrict__ cand_keys, float *__restrict__ out_score,
+                   int32_t *__restrict__ out_index, int32_t *__restrict__ out_count,
+                   int force_radix, int apply_nms) {
+    __shared__ uint64_t s_keys[kCandCap];
+    __shared__ uint32_t s_hist[kRadixBins];
+    __shared__ uint32_t s_part[kSelectThreads];
+    __shared__ uint32_t s_scalar[4];
+
+    const int plane = blockIdx.x;
+    const int tid = threadIdx.x;
+    float *o_score = out_score + (size_t)plane * K;
+    int32_t *o_index = out_index + (size_t)plane * K;
+
+    const uint32_t n_cand = force_radix ? (uint32_t)kCandCap + 1u : cand_count[plane];
+    if (n_cand <= (uint32_t)kCandCap) {
+        const int n = (int)n_cand;
+        for (int i = tid; i < n; i += blockDim.x) s_keys[i] = cand_keys[(size_t)plane * kCandCap + i];
+        __syncthreads();
+        write_ranked(s_keys, n, K, o_score, o_index);
+        if (tid == 0 && out_count) out_count[plane] = min(n, K);
+        return;
+    }
+
+    // ---- exact radix selection over the plane (rare path) ----
+    const float *__restrict__ p = heat + (size_t)plane * H * W;
+    const int HW = H * W;
+    const bool nms = apply_nms != 0;
+    uint32_t prefix = 0, prefix_mask = 0;
+    uint32_t remaining = (uint32_t)K;
+    uint32_t total_q = 0;
+    const int shifts[3] = {21, 10, 0};
+    const int widths[3] = {11, 11, 10};
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = shifts[pass];
+        const uint32_t mask = (1u << widths[pass]) - 1u;
+        for (int b = tid; b < kRadixBins; b += blockDim.x) s_hist[b] = 0;
+        __syncthreads();
+        for (int i = tid; i < HW; i += blockDim.x) {
+            const float nv = nms_value(p, H, W, i, nms);
+            if (nv >= thre) {
+                const uint32_t key = ~ordered_bits(nv);
+                if ((key & prefix_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & mask], 1u);
+            }
+        }
+        __syncthreads();
+        // 256 partial sums of 8 bins each, then thread 0 walks them
+        {
+            uint32_t acc = 0;
+            for (int b = 0; b < kRadixBins / kSelectThreads; ++b)
+                acc += s_hist[tid * (kRadixBins / kSelectThreads) + b];
+            s_part[tid] = acc;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t cum = 0, tot = 0;
+            for (int t = 0; t < kSelectThreads; ++t) tot += s_part[t];
+            if (pass == 0) {
+                s_scalar[2] = tot;
+                if (tot < remaining) remaining = tot;       // fewer than K qualify
+            }
+            uint32_t chosen = 0;
+            if (remaining > 0) {
+                int t = 0;
+                while (t < kSelectThreads - 1 && cum + s_part[t] < remaining) cum += s_part[t++];
+                int b = t * (kRadixBins / kSelectThreads);
+                while (b < kRadixBins - 1 && cum + s_hist[b] < remaining) cum += s_hist[b++];
+                chosen = (uint32_t)b;
+            }
+            s_scalar[0] = chosen;
+            s_scalar[1] = remaining - cum;     // still needed inside the chosen bin
+        }
+        __syncthreads();
+        prefix |= s_scalar[0] << shift;
+        prefix_mask |= mask << shift;
+        remaining = s_scalar[1];
+        total_q = s_scalar[2];
+        __syncthreads();
+    }
+    const uint32_t k_eff = min((uint32_t)K, total_q);
+    if (k_eff == 0) {
+        write_ranked(s_keys, 0, K, o_score, o_index);
+        if (tid == 0 && out_count) out_count[plane] = 0;
+        return;
+    }
+    const uint32_t kth = prefix;                 // key of the k_eff-th element
+    const uint32_t n_equal_needed = remaining;   // how many of value == kth to take
+    const uint32_t n_less = k_eff - n_equal_needed;
+
+    if (tid == 0) s_scalar[3] = 0;
+    __syncthreads();
+    for (int i = tid; i < HW; i += blockDim.x) {
+        const float nv = nms_value(p, H, W, i, nms);
+        if (nv >= thre) {
+            const uint32_t key = ~ordered_bits(nv);
+            if (key < kth) {
+                const uint32_t pos = atomicAdd(&s_scalar[3], 1u);
+                s_keys[pos] = ((uint64_t)key << 32) | (uint32_t)i;
+            }
+        }
+    }
+    __syncthreads();
+    // the lowest-index elements among those equal to the k-th value, in index order
+    uint32_t taken = 0;
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int base = 0; base < HW && taken < n_equal_needed; base += blockDim.x) {
+        const int i = base + tid;
+        bool flag = false;
+        if (i < HW) {
+            const float nv = nms_value(p, H, W, i, nms);
+            flag = (nv >= thre) && (~ordered_bits(nv) == kth);
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) s_part[wid] = __popc(ballot);
+        __syncthreads();
+        uint32_t before = 0, chunk_total = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            const uint32_t c = s_part[w];
+            if (w < wid) before += c;
+            chunk_total += c;
+        }
+        const uint32_t pos = taken + before + __popc(ballot & ((1u << lane) - 1u));
+        if (flag && pos < n_equal_needed) s_keys[n_less + pos] = ((uint64_t)kth << 32) | (uint32_t)i;
+        taken += chunk_total;
+        __syncthreads();
+    }
+    write_ranked(s_keys, (int)k_eff, K, o_score, o_index);
+    if (tid == 0 && out_count) out_count[plane] = (int)k_eff;
+}
+
+__global__ void hmp_nms_kernel(const float *__restrict__ heat, float *__restrict__ out,
+                               int planes, int H, int W) {
+    const long long total = (long long)planes * H * W;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(g % W);
+        const int y = (int)((g / W) % H);
+        const float *p = heat + (g - (long long)y * W - x);
+        const float v = p[y * W + x];
+        float m = 0.0f;
+        if (y > 0 && x > 0 && y < H - 1 && x < W - 1) m = v;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= H) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = x + dx;
+                if (xx < 0 || xx >= W) continue;
+                m = fmaxf(m, __ldg(p + yy * W + xx));
+            }
+        }
+        out[g] = v * ((m == v) ? 1.0f : 0.0f);      // heat * keep_mask (heatmap.py:35)
+    }
+}
+
+}  // namespace
+
+int launch_hmp_nms(const float *heat, float *out, int planes, int h, int w, cudaStream_t s) {
+    const long long total = (long long)planes * h * w;
+    if (total == 0) return OG_OK;
+    const int threads = 256;
+    long long want = (total + threads - 1) / threads;
+    const int blocks = (int)(want > 148LL * 32 ? 148LL * 32 : want);
+    hmp_nms_kernel<<<blocks, threads, 0, s>>>(heat, out, planes, h, w);
+    OG_CUDA_TRY(cudaGetLastError());
+    return OG_OK;
+}
+
+int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int k,
+                    uint32_t *cand_count, uint64_t *cand_keys, float *out_score,
+                    int32_t *out_index, int32_t *out_count, bool force_radix, bool apply_nms,
+                    cudaStream_t s, int64_t *launches) {
+    if (planes == 0) return OG_OK;
+    if (!force_radix) {
+        OG_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t) * planes, s));
+        const int strips = (w + 127) / 128;
+        const int chunks = (h + kRowsPerWarp - 1) / kRowsPerWarp;
+        const long long warps = (long long)planes * strips * chunks;
+        const int threads = 256;
+        const long long blocks = (warps + (threads / 32) - 1) / (threads / 32);
+        const bool vec4 = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
+        const bool pos = thre > 0.0f;
+        auto kern = pos ? (vec4 ? nms_candidates_kernel<true, true> : nms_candidates_kernel<true, false>)
+                        : (vec4 ? nms_candidates_kernel<false, true> : nms_candidates_kernel<false, false>);
+        kern<<<(unsigned)blocks, threads, 0, s>>>(heat, planes, h, w, thre, cand_count, cand_keys);
+        OG_CUDA_TRY(cudaGetLastError());
+        if (launches) *launches += 1;
+    }
+    select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
+                                                        out_score, out_index, out_count,
+                                                        force_radix ? 1 : 0, apply_nms ? 1 : 0);
+    OG_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += 1;
+    return OG_OK;
+}
+
+}  // namespace og

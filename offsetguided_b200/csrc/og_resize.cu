@@ -1,0 +1,180 @@
+// Map-level stages of PostProcess.generate_poses that precede limb collection
+// (reference decoder/factory.py:67-78, 98-146 and decoder/offset.py:8-43):
+// flip-test fusion, x stride resize (bicubic A=-0.75 / bilinear, align_corners=False)
+// and the optional scored_offset re-averaging.
+//
+// Rounding follows ATen's CPU kernels so that peak positions downstream are
+// bit-identical to the reference run on CPU tensors: the generic interpolation loop
+// accumulates  round(t1*w1) -> fma(t0, w0, .) -> fma(t2, w2, .) -> fma(t3, w3, .)
+// along x and then along y (probed against torch 2.11, tests/golden/resize_small.npz).
+// Interpolation weights are exact for power-of-two strides (the reference uses 4).
+#include "og_common.cuh"
+
+namespace og {
+
+namespace {
+
+__device__ __forceinline__ void cubic_weights(float t, float w[4]) {
+    const float A = -0.75f;
+    const float x0 = t + 1.0f, x3 = 2.0f - t, x2 = 1.0f - t;
+    w[0] = ((A * x0 - 5.0f * A) * x0 + 8.0f * A) * x0 - 4.0f * A;
+    w[1] = ((A + 2.0f) * t - (A + 3.0f)) * t * t + 1.0f;
+    w[2] = ((A + 2.0f) * x2 - (A + 3.0f)) * x2 * x2 + 1.0f;
+    w[3] = ((A * x3 - 5.0f * A) * x3 + 8.0f * A) * x3 - 4.0f * A;
+}
+
+// taps of one axis; returns the tap count (2 or 4)
+__device__ __forceinline__ int axis_taps(int dst, int n_in, float inv_scale, bool cubic,
+                                         int idx[4], float w[4]) {
+    float real = inv_scale * ((float)dst + 0.5f) - 0.5f;
+    if (!cubic) real = fmaxf(real, 0.0f);
+    const float fl = floorf(real);
+    const int base = (int)fl;
+    const float t = fminf(fmaxf(real - fl, 0.0f), 1.0f);
+    if (cubic) {
+        cubic_weights(t, w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) idx[j] = min(max(base + j - 1, 0), n_in - 1);
+        return 4;
+    }
+    idx[0] = min(base, n_in - 1);
+    idx[1] = min(base + 1, n_in - 1);
+    w[0] = 1.0f - t;
+    w[1] = t;
+    return 2;
+}
+
+__device__ __forceinline__ float combine(const float *v, const float *w, int taps) {
+    float acc = __fmul_rn(v[1], w[1]);
+    acc = __fmaf_rn(v[0], w[0], acc);
+    for (int j = 2; j < taps; ++j) acc = __fmaf_rn(v[j], w[j], acc);
+    return acc;
+}
+
+__global__ void resize_kernel(const float *__restrict__ in, float *__restrict__ out, int planes,
+                              int h, int w, int scale, int cubic) {
+    const int oh = h * scale, ow = w * scale;
+    const float inv = 1.0f / (float)scale;
+    const long long total = (long long)planes * oh * ow;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(g % ow);
+        const int oy = (int)((g / ow) % oh);
+        const int pl = (int)(g / ((long long)ow * oh));
+        const float *p = in + (size_t)pl * h * w;
+        int ix[4], iy[4];
+        float wx[4], wy[4];
+        const int taps = axis_taps(ox, w, inv, cubic != 0, ix, wx);
+        axis_taps(oy, h, inv, cubic != 0, iy, wy);
+        float rows[4];
+        for (int j = 0; j < taps; ++j) {
+            float v[4];
+            for (int i = 0; i < taps; ++i) v[i] = __ldg(p + iy[j] * w + ix[i]);
+            rows[j] = combine(v, wx, taps);
+        }
+        out[g] = combine(rows, wy, taps);
+    }
+}
+
+__global__ void flip_fuse_kernel(const float *__restrict__ hmp2n, const float *__restrict__ off2n,
+                                 const int32_t *__restrict__ kp_flip,
+                                 const int32_t *__restrict__ limb_flip,
+                                 const uint8_t *__restrict__ limb_reserved, int n, int c, int l,
+                                 int h, int w, float *__restrict__ out_hmp,
+                                 float *__restrict__ out_off) {
+    const long long hw = (long long)h * w;
+    const long long n_h = (long long)n * c * hw;
+    const long long n_o = (long long)n * 2 * l * hw;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_h + n_o;
+         g += (long long)gridDim.x * blockDim.x) {
+        if (g < n_h) {
+            const int x = (int)(g % w);
+            const int y = (int)((g / w) % h);
+            const int ch = (int)((g / hw) % c);
+            const int img = (int)(g / (hw * c));
+            const float a = hmp2n[g];
+            const float b = hmp2n[(((long long)(n + img) * c + kp_flip[ch]) * h + y) * w + (w - 1 - x)];
+            out_hmp[g] = __fmul_rn(__fadd_rn(a, b), 0.5f);                  // factory.py:106
+        } else {
+            const long long q = g - n_h;
+            const int x = (int)(q % w);
+            const int y = (int)((q / w) % h);
+            const int ch = (int)((q / hw) % (2 * l));
+            const int img = (int)(q / (hw * 2 * l));
+            const int limb = ch >> 1, comp = ch & 1;
+            const float a = off2n[q];
+            float r = a;                                                    // factory.py:134
+            if (!limb_reserved[limb]) {
+                float b = off2n[(((long long)(n + img) * 2 * l + 2 * limb_flip[limb] + comp) * h + y) * w + (w - 1 - x)];
+                if (comp == 0) b = -b;                                      // factory.py:132
+                r = __fmul_rn(__fadd_rn(a, b), 0.5f);                       // factory.py:133
+            }
+            out_off[q] = r;
+        }
+    }
+}
+
+// out[n, 2l+comp] = sumpool_k(hmp[jf] * off) / (sumpool_k(hmp[jf]) + 1e-6)
+__global__ void scored_offset_kernel(const float *__restrict__ hmp, const float *__restrict__ off,
+                                     int n, int c, int l, int h, int w, int ksize, SkeletonDev sk,
+                                     float *__restrict__ out) {
+    const long long hw = (long long)h * w;
+    const long long total = (long long)n * 2 * l * hw;
+    const int pad = (ksize - 1) / 2;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(g % w);
+        const int y = (int)((g / w) % h);
+        const int ch = (int)((g / hw) % (2 * l));
+        const int img = (int)(g / (hw * 2 * l));
+        const float *hp = hmp + ((long long)img * c + sk.from[ch >> 1]) * hw;
+        const float *op = off + ((long long)img * 2 * l + ch) * hw;
+        float s_w = 0.0f, s_wo = 0.0f;
+        for (int yy = max(y - pad, 0); yy <= min(y + pad, h - 1); ++yy)
+            for (int xx = max(x - pad, 0); xx <= min(x + pad, w - 1); ++xx) {
+                const float hv = __ldg(hp + yy * w + xx);
+                s_w = __fadd_rn(s_w, hv);
+                s_wo = __fadd_rn(s_wo, __fmul_rn(hv, __ldg(op + yy * w + xx)));
+            }
+        out[g] = __fdiv_rn(s_wo, __fadd_rn(s_w, 1e-6f));
+    }
+}
+
+inline int grid_for(long long total, int threads) {
+    long long b = (total + threads - 1) / threads;
+    return (int)(b < 1 ? 1 : (b > 148LL * 64 ? 148LL * 64 : b));
+}
+
+}  // namespace
+
+int launch_resize(const float *in, float *out, int planes, int h, int w, int scale, int mode,
+                  cudaStream_t s) {
+    const long long total = (long long)planes * h * scale * w * scale;
+    if (total == 0) return OG_OK;
+    resize_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, planes, h, w, scale, mode);
+    OG_CUDA_TRY(cudaGetLastError());
+    return OG_OK;
+}
+
+int launch_flip_fuse(const float *hmp2n, const float *off2n, const int32_t *kp_flip_dev,
+                     const int32_t *limb_flip_dev, const uint8_t *limb_reserved_dev, int n, int c,
+                     int l, int h, int w, float *out_hmp, float *out_off, cudaStream_t s) {
+    const long long total = (long long)n * (c + 2 * l) * h * w;
+    if (total == 0) return OG_OK;
+    flip_fuse_kernel<<<grid_for(total, 256), 256, 0, s>>>(hmp2n, off2n, kp_flip_dev, limb_flip_dev,
+                                                         limb_reserved_dev, n, c, l, h, w, out_hmp,
+                                                         out_off);
+    OG_CUDA_TRY(cudaGetLastError());
+    return OG_OK;
+}
+
+int launch_scored_offset(const float *hmp, const float *off, int n, int c, int l, int h, int w,
+                         int ksize, const SkeletonDev &sk, float *out, cudaStream_t s) {
+    const long long total = (long long)n * 2 * l * h * w;
+    if (total == 0) return OG_OK;
+    scored_offset_kernel<<<grid_for(total, 256), 256, 0, s>>>(hmp, off, n, c, l, h, w, ksize, sk, out);
+    OG_CUDA_TRY(cudaGetLastError());
+    return OG_OK;
+}
+
+}  // namespace og

@@ -1,0 +1,232 @@
+"""Post-processing entry point (reference decoder/factory.py): ``decoder_cli``,
+``decoder_factory(args)`` -> ``PostProcess``, ``PostProcess.generate_poses``."""
+import logging
+import re
+
+import torch
+
+from .. import config
+from ..config import (COCO_KEYPOINTS, COCO_PERSON_SKELETON,
+                      COCO_PERSON_WITH_REDUNDANT_SKELETON, DENSER_COCO_PERSON_SKELETON,
+                      REDUNDANT_CONNECTIONS, KINEMATIC_TREE_SKELETON)
+from ..engine import DecoderEngine
+from .collect import LimbsCollect
+from .group import GreedyGroup
+from . import offset as _offset
+
+LOG = logging.getLogger(__name__)
+
+
+def boolean_string(s):
+    """'False' / 'True' command-line values (reference utils/util.py:4-8)."""
+    if s not in {'False', 'True'}:
+        raise ValueError('Not a valid boolean string')
+    return s == 'True'
+
+
+class PostProcess(torch.nn.Module):
+    """Network outputs -> per-image pose arrays (reference decoder/factory.py:21-96).
+
+    Constructor arguments are the reference's.  No worker pool is forked: grouping runs
+    on the GPU (one CTA per image) in the same stream as the rest of the decoder.
+    """
+
+    def __init__(self, batch_size, hmp_stride, off_stride, inter_mode, keypoints, skeleton,
+                 limb_collector, limb_grouper, include_scale=False, include_jitter_offset=False,
+                 hmp_index=0, omp_index=1, feat_stage=-1):
+        super(PostProcess, self).__init__()
+        self.batch_size = batch_size
+        self.inter_mode = inter_mode
+        self.hmp_stride = hmp_stride
+        self.off_stride = off_stride
+        self.keypoints = keypoints
+        self.skeleton = skeleton
+        self.limb_collect = limb_collector
+        self.limb_group = limb_grouper
+        self.hmp_index = hmp_index
+        self.omp_index = omp_index
+        self.feat_stage = feat_stage
+        self.include_scale = include_scale
+        self.include_jitter_offset = include_jitter_offset
+        self.keypoints_flips = config.heatmap_hflip(keypoints)
+        self.limbs_flips = config.offset_hflip(keypoints, skeleton)
+        self.worker_pool = None          # the reference forks Pool(batch_size) here
+        self._engines = {}
+        LOG.info('use the inferred feature maps at stage %d, heatmap index is %d, offsetmap index '
+                 'is %d, interpolate the predicted heatmaps using %s, grouping on the GPU',
+                 feat_stage, hmp_index, omp_index, inter_mode)
+
+    def _engine(self, device):
+        key = (device.type, device.index)
+        if key not in self._engines:
+            lc, lg = self.limb_collect, self.limb_group
+            self._engines[key] = DecoderEngine(
+                len(self.keypoints), self.skeleton, topk=lc.K, thre_hmp=lc.thre_hmp,
+                min_len=lc.min_len, resize_factor=lc.resize_factor, dist_max=lg.dist_max,
+                use_scale=lg.use_scale, person_thre=lg.person_thre, sort_dim=lg.sort_dim,
+                device=device)
+        return self._engines[key]
+
+    def generate_poses(self, features, flip_test=False, cat_flip_offs=False, scored_off=False):
+        """Decode a batch (reference decoder/factory.py:52-96).
+
+        ``features[hmp_index] = (out_hmps, out_bghmp, out_jomps)`` and
+        ``features[omp_index] = (out_offsets, out_spreads, out_scales)``, each a list over
+        stacks; stage ``feat_stage`` is used.  With ``flip_test`` the batch holds the
+        originals followed by their W-flipped copies.  Tensors may live on the GPU (the
+        normal case, right after ``model(images)``) or on the host.
+
+        Returns a list with one (M_i, C, 6) float32 array per image.
+        """
+        out_hmps, out_bghmp, out_jomps = features[self.hmp_index]
+        out_offsets, out_spreads, out_scales = features[self.omp_index]
+        hmps = out_hmps[self.feat_stage]
+        jomps = out_jomps[self.feat_stage]
+        offs = out_offsets[self.feat_stage]
+        scmps = out_scales[self.feat_stage]
+
+        if cat_flip_offs:
+            raise NotImplementedError('cat_flip_offs (4-D offset vectors) is not implemented')
+        if self.include_jitter_offset and isinstance(jomps, torch.Tensor):
+            raise NotImplementedError('jitter-offset refinement is not implemented')
+        use_scale_maps = self.include_scale and isinstance(scmps, torch.Tensor)
+
+        if scored_off or use_scale_maps:
+            return self._generate_poses_staged(hmps, offs, scmps if use_scale_maps else None,
+                                               flip_test, scored_off)
+        device = hmps.device if hmps.is_cuda else torch.device('cuda', torch.cuda.current_device())
+        eng = self._engine(device)
+        tables = (self.keypoints_flips, self.limbs_flips[0], self.limbs_flips[1]) if flip_test else None
+        return eng.decode_features(hmps, offs, self.hmp_stride, self.off_stride, self.inter_mode, tables)
+
+    def _generate_poses_staged(self, hmps, offs, scmps, flip_test, scored_off):
+        """Optional stages (scored_off, keypoint-scale maps): the same kernels, called
+        stage by stage through the C ABI."""
+        from .. import _lib
+        from ..engine import as_cuda_f32, _ptr, _stream_ptr
+        lib = _lib.load()
+        hmps = as_cuda_f32(hmps)
+        device = hmps.device
+        offs = as_cuda_f32(offs, device)
+        eng = self._engine(device)
+        mode = {'bilinear': 0, 'bicubic': 1}[self.inter_mode]
+        if scmps is not None:
+            scmps = as_cuda_f32(scmps, device)
+        with torch.cuda.device(device):
+            s = _stream_ptr(device)
+            if flip_test:
+                n = hmps.shape[0] // 2
+                fh = torch.empty((n,) + tuple(hmps.shape[1:]), dtype=torch.float32, device=device)
+                fo = torch.empty((n,) + tuple(offs.shape[1:]), dtype=torch.float32, device=device)
+                kp = _lib.int32_array(self.keypoints_flips)
+                lf = _lib.int32_array(self.limbs_flips[0])
+                lr = _lib.int32_array(self.limbs_flips[1])
+                _lib.check(lib.og_flip_fuse_f32(eng._h, _ptr(hmps), _ptr(offs), kp, lf, lr,
+                                                len(self.limbs_flips[1]), n, hmps.shape[2],
+                                                hmps.shape[3], _ptr(fh), _ptr(fo), s))
+                if scmps is not None:        # factory.py:141-144
+                    flipped = torch.flip(scmps[n:], [-1])[:, self.keypoints_flips]
+                    scmps = (scmps[:n] + flipped) / 2
+                hmps, offs = fh, fo
+            if scored_off:
+                jf, jt = _offset.pack_jtypes(self.skeleton)
+                offs = _offset.scored_offset(hmps, offs, jf, jt, kernel_size=3)
+
+            def up(x, stride, m):
+                if stride == 1:
+                    return x
+                n, c, h, w = x.shape
+                out = torch.empty((n, c, h * stride, w * stride), dtype=torch.float32, device=device)
+                _lib.check(lib.og_resize_f32(_ptr(x.contiguous()), _ptr(out), n * c, h, w, stride, m, s))
+                return out
+            hmps_hr = up(hmps, self.hmp_stride, mode)
+            offs_hr = up(offs, self.off_stride, 0)
+            scmps_hr = up(scmps, self.off_stride, mode) if scmps is not None else None
+            return eng.decode_maps(hmps_hr, offs_hr, scmps_hr)
+
+
+def decoder_cli(parser):
+    """Command-line flags of the decoder (reference decoder/factory.py:149-188)."""
+    group = parser.add_argument_group('limb collections in post-processing')
+    group.add_argument('--resize-mode', default='bicubic', choices=['bilinear', 'bicubic'], type=str,
+                       help='interpolation mode for resizing the keypoint heatmaps.')
+    group.add_argument('--topk', default=48, type=int,
+                       help='select the top K responses on each heatmaps, and hence leads to top K '
+                            'limbs of each type. A bigger topk may not leads to better performance')
+    group.add_argument('--thre-hmp', default=0.06, type=float,
+                       help='candidate kepoints below this response value are moved outside the '
+                            'image boarder')
+    group.add_argument('--min-len', default=0.5, type=float,
+                       help='length in pixels, clamp the candidate limbs of zero length to min_len')
+    group.add_argument('--feat-stage', default=-1, type=int,
+                       help='use the inferred feature maps at this stage to generate results')
+
+    group = parser.add_argument_group('greedy grouping in post-processing')
+    group.add_argument('--person-thre', default=0.06, type=float,
+                       help='threshold for pose instance scores, but COCO evaluates the top k instances')
+    group.add_argument('--sort-dim', default=2, choices=[2, 4], type=int,
+                       help='sort the person poses by the values at the this axis. 2th dim means '
+                            'keypoints score, 4th dim means limb score.')
+    group.add_argument('--dist-max', default=20, type=float,
+                       help='abandon limbs with delta offsets bigger than dist_max, only useful when '
+                            'keypoint scales are not used because use-scale will overlap the smaller '
+                            'dist-max')
+    group.add_argument('--use-scale', default=True, type=boolean_string,
+                       help='only effective when we set --include-scale in the network; use the '
+                            'inferred keypoint scales as the criterion to keep limbs (keypoint pairs)')
+    group.add_argument('--use-jitter-offset', default=True, type=boolean_string,
+                       help='only effective when we set --include-jitter-offset in the network; use '
+                            'the inferred jitter offset to refine the keypoint localization')
+
+
+_OMP_SKELETONS = {
+    'omp': COCO_PERSON_SKELETON, 'omp19': COCO_PERSON_SKELETON, 'omps': COCO_PERSON_SKELETON,
+    'offset': COCO_PERSON_SKELETON, 'offsets': COCO_PERSON_SKELETON,
+    'omp16': KINEMATIC_TREE_SKELETON,
+    'omp31': COCO_PERSON_WITH_REDUNDANT_SKELETON,
+    'omp44': DENSER_COCO_PERSON_SKELETON,
+    'omp25': REDUNDANT_CONNECTIONS, 'omps25': REDUNDANT_CONNECTIONS,
+}
+
+
+def parse_heads(head_name, stride):
+    """Head name -> keypoints / skeleton and stride (reference decoder/factory.py:191-231).
+    Unlike the reference, 'hmp17' / 'hmps17' resolve to the COCO keypoints instead of
+    leaving the variable unbound."""
+    m = re.match('hmp[s]?([0-9]+)$', head_name)
+    if head_name in ('hmp', 'hmps', 'heatmap', 'heatmaps') or m is not None:
+        if m is not None:
+            n_keypoints = int(m.group(1))
+            assert n_keypoints == 17, f'{n_keypoints} keypoints not supported'
+        return {'keypoints': COCO_KEYPOINTS, 'hmp_stride': stride}
+    if head_name in _OMP_SKELETONS:
+        return {'skeleton': _OMP_SKELETONS[head_name], 'omp_stride': stride}
+    if re.match('omp[s]?([0-9]+)$', head_name) is not None:
+        raise Exception('unknown skeleton type of head')
+    raise Exception('unknown head to create an encoder: {}'.format(head_name))
+
+
+def decoder_factory(args):
+    """Build the PostProcess of a parsed command line (reference decoder/factory.py:234-267).
+    Reads args.headnets, strides, topk, thre_hmp, min_len, include_jitter_offset,
+    include_scale, use_jitter_offset, person_thre, sort_dim, dist_max, use_scale,
+    batch_size, resize_mode, feat_stage."""
+    temp_dic = {}
+    for hd_name, stride in zip(args.headnets, args.strides):
+        temp_dic.update(parse_heads(hd_name, stride))
+
+    limb_handler = LimbsCollect(temp_dic['hmp_stride'], temp_dic['omp_stride'],
+                                topk=args.topk, thre_hmp=args.thre_hmp, min_len=args.min_len,
+                                include_jitter_offset=args.include_jitter_offset,
+                                include_scale=args.include_scale,
+                                use_jitter_offset=args.use_jitter_offset,
+                                keypoints=temp_dic['keypoints'], skeleton=temp_dic['skeleton'])
+    skeleton_grouper = GreedyGroup(args.person_thre, sort_dim=args.sort_dim,
+                                   dist_max=args.dist_max, use_scale=args.use_scale,
+                                   keypoints=temp_dic['keypoints'], skeleton=temp_dic['skeleton'])
+    return PostProcess(args.batch_size, temp_dic['hmp_stride'], temp_dic['omp_stride'],
+                       args.resize_mode, keypoints=temp_dic['keypoints'],
+                       skeleton=temp_dic['skeleton'], limb_collector=limb_handler,
+                       limb_grouper=skeleton_grouper, include_scale=args.include_scale,
+                       include_jitter_offset=args.include_jitter_offset,
+                       feat_stage=args.feat_stage)

@@ -1,0 +1,219 @@
+"""Host-side owner of one ``og_handle`` (one GPU, one decoder configuration).
+
+PyTorch is used for device memory, streams and the numpy bridge only; every
+computation is a call into libogdecoder.so through ``_lib``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def as_cuda_f32(t, device=None):
+    """Contiguous float32 CUDA view/copy of a tensor (CPU tensors are uploaded)."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t))
+    if not t.is_cuda:
+        if not torch.cuda.is_available():
+            raise _lib.OgError('a CUDA device is required: the decoder has no CPU fallback')
+        t = t.to(device if device is not None else 'cuda')
+    return t.contiguous().float()
+
+
+class DecoderEngine(object):
+    """One configured decoder bound to one CUDA device."""
+
+    def __init__(self, n_keypoints, skeleton, *, topk, thre_hmp=0.06, min_len=0.5,
+                 resize_factor=1.0, dist_max=20.0, use_scale=True, person_thre=0.06,
+                 sort_dim=2, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.OgError('a CUDA device is required: the decoder has no CPU fallback')
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.n_keypoints = int(n_keypoints)
+        self.skeleton = [(int(a), int(b)) for a, b in skeleton]
+        self.n_limbs = len(self.skeleton)
+        self.topk = int(topk)
+        self._from = _lib.int32_array([a for a, _ in self.skeleton])
+        self._to = _lib.int32_array([b for _, b in self.skeleton])
+        cfg = _lib.OgConfig(
+            n_keypoints=self.n_keypoints, n_limbs=self.n_limbs,
+            limb_from=ctypes.cast(self._from, _lib.c_int32_p),
+            limb_to=ctypes.cast(self._to, _lib.c_int32_p),
+            topk=self.topk, thre_hmp=float(thre_hmp), min_len=float(min_len),
+            resize_factor=float(resize_factor), dist_max=float(dist_max),
+            use_scale=1 if use_scale else 0, person_thre=float(person_thre),
+            sort_dim=int(sort_dim), device=self.device.index, max_images=0)
+        self.thre_hmp = float(thre_hmp)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.og_create(ctypes.byref(cfg), ctypes.byref(handle)))
+        self._h = handle
+
+    def close(self):
+        if getattr(self, '_h', None):
+            with torch.cuda.device(self.device):
+                self.lib.og_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self.lib.og_launch_count(self._h))
+
+    # ---- single stages -----------------------------------------------------
+    def nms_topk(self, heat, thre=None):
+        """K1.  heat (N, C, H, W) CUDA f32 -> scores (N, C, K) f32, inds (N, C, K) i32,
+        counts (N, C) i32."""
+        heat = as_cuda_f32(heat, self.device)
+        n, c, h, w = heat.shape
+        assert c == self.n_keypoints, 'heat map channel count differs from the keypoint list'
+        scores = torch.empty((n, c, self.topk), dtype=torch.float32, device=self.device)
+        inds = torch.empty((n, c, self.topk), dtype=torch.int32, device=self.device)
+        counts = torch.empty((n, c), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.og_nms_topk_f32(
+                self._h, _ptr(heat), n, h, w, float(self.thre_hmp if thre is None else thre),
+                _ptr(scores), _ptr(inds), _ptr(counts), _stream_ptr(self.device)))
+        return scores, inds, counts
+
+    def topk_channel(self, scores_map, k):
+        scores_map = as_cuda_f32(scores_map, self.device)
+        n, c, h, w = scores_map.shape
+        scores = torch.empty((n, c, k), dtype=torch.float32, device=self.device)
+        inds = torch.empty((n, c, k), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.og_topk_channel_f32(
+                self._h, _ptr(scores_map), n, c, h, w, int(k), _ptr(scores), _ptr(inds),
+                _stream_ptr(self.device)))
+        return scores, inds
+
+    def limb_score(self, det_scores, det_inds, offs, scales=None):
+        """K2.  -> limbs (N, L, K, 13) CUDA f32."""
+        offs = as_cuda_f32(offs, self.device)
+        n, l2, h, w = offs.shape
+        assert l2 == 2 * self.n_limbs, 'offset map channel count differs from 2 * limbs'
+        det_scores = as_cuda_f32(det_scores, self.device)
+        det_inds = det_inds.to(self.device, torch.int32).contiguous()
+        if scales is not None:
+            scales = as_cuda_f32(scales, self.device)
+        limbs = torch.empty((n, self.n_limbs, self.topk, _lib.OG_LIMB_COLS),
+                            dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.og_limb_score_f32(
+                self._h, _ptr(det_scores), _ptr(det_inds), _ptr(offs), _ptr(scales), n, h, w,
+                _ptr(limbs), _stream_ptr(self.device)))
+        return limbs
+
+    def group(self, limbs):
+        """K3.  limbs (N, L, K, 13) -> list of N numpy arrays (M_i, C, 6)."""
+        limbs = as_cuda_f32(limbs, self.device)
+        n = limbs.shape[0]
+        assert tuple(limbs.shape[1:]) == (self.n_limbs, self.topk, _lib.OG_LIMB_COLS), \
+            'check the skeleton config and input limbs Tensor'
+        cap = max(1, n * self.n_limbs * self.topk)
+        poses = torch.empty((cap, self.n_keypoints, _lib.OG_POSE_COLS), dtype=torch.float32,
+                            device=self.device)
+        meta = torch.empty((2 * n + 1,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.og_group_f32(
+                self._h, _ptr(limbs), n, _ptr(poses), cap, _ptr(meta[:n]), _ptr(meta[n:2 * n]),
+                _ptr(meta[2 * n:]), _stream_ptr(self.device)))
+        meta_h = meta.cpu().numpy()
+        total = int(meta_h[2 * n])
+        poses_h = poses[:total].cpu().numpy()
+        return [poses_h[meta_h[i]:meta_h[i] + meta_h[n + i]].copy() for i in range(n)]
+
+    # ---- whole path ----------------------------------------------------------
+    def _fetch(self, n):
+        poses_p = _lib.c_float_p()
+        off_p = _lib.c_int32_p()
+        cnt_p = _lib.c_int32_p()
+        total = ctypes.c_int32(0)
+        _lib.check(self.lib.og_fetch_poses(self._h, ctypes.byref(poses_p), ctypes.byref(off_p),
+                                           ctypes.byref(cnt_p), ctypes.byref(total)))
+        if n == 0:
+            return []
+        c = self.n_keypoints
+        offs = np.ctypeslib.as_array(off_p, shape=(n,))
+        cnts = np.ctypeslib.as_array(cnt_p, shape=(n,))
+        if total.value == 0:
+            return [np.zeros((0, c, _lib.OG_POSE_COLS), dtype=np.float32) for _ in range(n)]
+        rows = np.ctypeslib.as_array(poses_p, shape=(total.value, c, _lib.OG_POSE_COLS))
+        return [rows[offs[i]:offs[i] + cnts[i]].copy() for i in range(n)]
+
+    def decode_maps(self, heat, offs, scales=None):
+        """generate_limbs + group_skeletons on full-resolution maps (K1 -> K2 -> K3)."""
+        heat = as_cuda_f32(heat, self.device)
+        offs = as_cuda_f32(offs, self.device)
+        assert heat.shape[-2:] == offs.shape[-2:], 'spatial resolution should be equal'
+        if scales is not None:
+            scales = as_cuda_f32(scales, self.device)
+        n, c, h, w = heat.shape
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.og_decode_maps(self._h, _ptr(heat), _ptr(offs), _ptr(scales),
+                                               n, h, w, _stream_ptr(self.device)))
+            return self._fetch(n)
+
+    def decode_features(self, hmp, off, hmp_stride, off_stride, resize_mode='bicubic',
+                        flip_tables=None, fetch=True):
+        """PostProcess.generate_poses on network-resolution maps.  ``hmp`` / ``off`` are
+        either CUDA tensors or CPU tensors (pinned memory gives asynchronous copies).
+        ``flip_tables`` = (kp_flips, limb_flips, limb_reserve) enables flip fusion; the
+        inputs then hold the originals followed by the W-flipped copies."""
+        mode = {'bilinear': 0, 'bicubic': 1}[resize_mode]
+        on_host = not hmp.is_cuda
+        assert hmp.is_cuda == off.is_cuda, 'heat and offset maps must live on the same side'
+        hmp = hmp.contiguous().float()
+        off = off.contiguous().float()
+        n_in, c, h, w = hmp.shape
+        flip = flip_tables is not None
+        n = n_in // 2 if flip else n_in
+        if flip:
+            kp, lf, lr = flip_tables
+            kp_a, lf_a, lr_a = _lib.int32_array(kp), _lib.int32_array(lf), _lib.int32_array(lr)
+            args = (ctypes.cast(kp_a, _lib.c_int32_p), ctypes.cast(lf_a, _lib.c_int32_p),
+                    ctypes.cast(lr_a, _lib.c_int32_p), len(lr))
+        else:
+            args = (None, None, None, 0)
+        fn = self.lib.og_decode_features_host if on_host else self.lib.og_decode_features_dev
+        with torch.cuda.device(self.device):
+            _lib.check(fn(self._h, _ptr(hmp), _ptr(off), n, h, w, int(hmp_stride), int(off_stride),
+                          mode, 1 if flip else 0, *args, _stream_ptr(self.device)))
+            self._keepalive = (hmp, off)
+            if not fetch:
+                return n
+            return self._fetch(n)
+
+    def fetch(self, n):
+        with torch.cuda.device(self.device):
+            return self._fetch(n)
+
+    def last_intermediates(self, n):
+        """Copies of the last decode call's dets (scores, indices) and limbs."""
+        c, k, l = self.n_keypoints, self.topk, self.n_limbs
+        ds = torch.empty((n, c, k), dtype=torch.float32, device=self.device)
+        di = torch.empty((n, c, k), dtype=torch.int32, device=self.device)
+        lb = torch.empty((n, l, k, _lib.OG_LIMB_COLS), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.og_copy_intermediates(self._h, n, _ptr(ds), _ptr(di), _ptr(lb),
+                                                      _stream_ptr(self.device)))
+        return ds, di, lb

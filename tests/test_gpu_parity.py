@@ -1,0 +1,345 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the oracle on
+seeded inputs and against the committed reference outputs (tests/golden).
+
+Bar (BASELINE.json north_star): peak coordinates, top-K indices and person
+assignments bit-exact; keypoint / limb / person scores within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+from oracle import ref_oracle as ro
+from oracle import scenes
+from offsetguided_b200 import config as cfg
+from offsetguided_b200 import decoder
+from offsetguided_b200.engine import DecoderEngine
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5      # tolerance north_star states for floating-point scores
+
+
+def _engine(d, c, skeleton, **over):
+    kw = dict(topk=d['topk'], thre_hmp=d['thre_hmp'], min_len=d['min_len'], resize_factor=1.0,
+              dist_max=d['dist_max'], use_scale=True, person_thre=d['person_thre'], sort_dim=2)
+    kw.update(over)
+    return DecoderEngine(c, skeleton, **kw)
+
+
+# --------------------------------------------------------------------------- K1
+@pytest.mark.parametrize('name', ['limbs_coco_a', 'limbs_coco_noise', 'limbs_crowdpose'])
+def test_k1_matches_reference_dets(cuda_device, name):
+    d = gio.load_limbs_case(name)
+    eng = _engine(d, d['n_keypoints'], d['skeleton'])
+    s, i, cnt = eng.nms_topk(torch.from_numpy(d['heat']).cuda())
+    s, i, cnt = s.cpu().numpy(), i.cpu().numpy(), cnt.cpu().numpy()
+    live = d['det_scores'] >= np.float32(d['thre_hmp'])
+    assert np.array_equal(cnt, live.sum(-1))
+    assert np.array_equal(s[live], d['det_scores'][live])
+    assert np.array_equal(i[live], d['det_inds'][live])
+    assert np.all(i[~live] == -1) and np.all(s[~live] == 0)
+
+
+def test_k1_exact_joint_dets_radix_path(cuda_device):
+    """thre = -inf: every pixel qualifies, all planes take the radix path; the result
+    must be the exact top-K of the NMS map including zero filler by lowest index."""
+    rng = np.random.RandomState(0)
+    heat = rng.uniform(0, 1, size=(2, 3, 70, 90)).astype(np.float32)
+    heat[0, 1] = 0                      # constant plane: all ties
+    heat[1, 2, 10:20, 10:30] = 0.5      # plateau block
+    eng = DecoderEngine(3, [(0, 1), (1, 2)], topk=40)
+    s, i, _ = eng.nms_topk(torch.from_numpy(heat).cuda(), thre=float('-inf'))
+    ref_s, ref_i, _, _ = ro.joint_dets(heat, 40)
+    assert np.array_equal(i.cpu().numpy(), ref_i)
+    assert np.array_equal(s.cpu().numpy(), ref_s)
+
+
+def test_k1_overflow_planes_fall_back_to_radix(cuda_device):
+    """Noise maps: > 2048 peaks per plane above the threshold."""
+    rng = np.random.RandomState(1)
+    heat = rng.uniform(0, 1, size=(1, 17, 200, 256)).astype(np.float32)
+    eng = DecoderEngine(17, cfg.COCO_PERSON_SKELETON, topk=32, thre_hmp=0.04)
+    s, i, cnt = eng.nms_topk(torch.from_numpy(heat).cuda())
+    ref_s, ref_i, _, _ = ro.joint_dets(heat, 32)
+    assert np.array_equal(i.cpu().numpy(), ref_i) and np.array_equal(s.cpu().numpy(), ref_s)
+    assert np.all(cnt.cpu().numpy() == 32)
+
+
+@pytest.mark.parametrize('shape', [(1, 2, 5, 7), (1, 1, 1, 1), (2, 3, 33, 130), (1, 2, 64, 128),
+                                   (1, 1, 65, 129), (1, 2, 130, 516), (1, 1, 3, 1030)])
+def test_k1_ragged_shapes_and_borders(cuda_device, shape):
+    rng = np.random.RandomState(sum(shape))
+    heat = rng.uniform(-0.2, 1, size=shape).astype(np.float32)
+    heat[..., 0, :] = rng.uniform(-1, 1, size=shape[:2] + (shape[3],))     # border values
+    heat[..., :, -1] = rng.uniform(-1, 1, size=shape[:3])
+    k = min(16, shape[2] * shape[3])
+    eng = DecoderEngine(shape[1], [(0, 0)], topk=k, thre_hmp=0.3)
+    s, i, cnt = eng.nms_topk(torch.from_numpy(heat).cuda())
+    nms = ro.hmp_nms(heat)
+    nms[nms < np.float32(0.3)] = -1          # threshold first
+    ref_s, ref_i, _, _ = ro.topk_channel(nms, k)
+    live = ref_s >= np.float32(0.3)
+    assert np.array_equal(cnt.cpu().numpy(), live.sum(-1))
+    assert np.array_equal(i.cpu().numpy()[live], ref_i[live])
+    assert np.array_equal(s.cpu().numpy()[live], ref_s[live])
+    # the stand-alone API on the same map
+    out = decoder.hmp_NMS(torch.from_numpy(heat).cuda())
+    assert np.array_equal(out.cpu().numpy(), ro.hmp_nms(heat))
+    ts, ti, ty, tx = decoder.topK_channel(out, K=k)
+    rs, ri, ry, rx = ro.topk_channel(ro.hmp_nms(heat), k)
+    assert np.array_equal(ti.cpu().numpy(), ri) and np.array_equal(ts.cpu().numpy(), rs)
+    assert np.array_equal(ty.cpu().numpy(), ry) and np.array_equal(tx.cpu().numpy(), rx)
+    assert ti.dtype == torch.int64
+
+
+def test_k1_unaligned_base_pointer(cuda_device):
+    rng = np.random.RandomState(5)
+    buf = torch.from_numpy(rng.uniform(0, 1, size=(1 + 2 * 40 * 64,)).astype(np.float32)).cuda()
+    heat = buf[1:].view(1, 2, 40, 64)          # 4-byte aligned only
+    assert heat.data_ptr() % 16 != 0
+    eng = DecoderEngine(2, [(0, 1)], topk=8, thre_hmp=0.5)
+    s, i, _ = eng.nms_topk(heat)
+    nms = ro.hmp_nms(heat.cpu().numpy())
+    rs, ri, _, _ = ro.topk_channel(nms, 8)
+    assert np.array_equal(i.cpu().numpy(), ri) and np.array_equal(s.cpu().numpy(), rs)
+
+
+# --------------------------------------------------------------------------- K2
+@pytest.mark.parametrize('name', ['limbs_coco_a', 'limbs_coco_noise', 'limbs_crowdpose'])
+def test_k2_limbs_match_reference(cuda_device, name):
+    d = gio.load_limbs_case(name)
+    lc = decoder.LimbsCollect(1, 1, topk=d['topk'], thre_hmp=d['thre_hmp'], min_len=d['min_len'],
+                              keypoints=list(range(d['n_keypoints'])), skeleton=d['skeleton'])
+    limbs = lc.generate_limbs(torch.from_numpy(d['heat']).cuda(), [], torch.from_numpy(d['offs']).cuda(), [])
+    assert limbs.is_cuda and tuple(limbs.shape) == d['limbs'].shape
+    got = limbs.cpu().numpy()
+    assert gio.compare_limbs(got, d['limbs'], d['thre_hmp'], rtol=RTOL) > 100
+    both = (d['limbs'][..., 2] >= np.float32(d['thre_hmp'])) & (d['limbs'][..., 5] >= np.float32(d['thre_hmp']))
+    # distances follow ATen's fma formula: bit-exact
+    assert np.array_equal(got[both][:, 8], d['limbs'][both][:, 8])
+    assert np.array_equal(got[both][:, 9], d['limbs'][both][:, 9])
+
+
+def test_k2_scale_maps_and_float32_ids(cuda_device):
+    """include_scale gather (collect.py:111-116) and global ids above 2**24 stored as
+    rounded float32."""
+    rng = np.random.RandomState(9)
+    h, w = 1024, 1024
+    skel = [(0, 16), (16, 1)]
+    heat = np.zeros((1, 17, h, w), np.float32)
+    offs = np.zeros((1, 4, h, w), np.float32)
+    sc = rng.uniform(1, 30, size=(1, 17, h, w)).astype(np.float32)
+    pts = rng.randint(5, 1000, size=(6, 2))
+    for (x, y) in pts:
+        heat[0, 0, y, x] = rng.uniform(0.3, 1)
+        heat[0, 16, y + 3, x + 2] = rng.uniform(0.3, 1)
+        heat[0, 1, y + 5, x - 3] = rng.uniform(0.3, 1)
+        offs[0, 0, y, x], offs[0, 1, y, x] = 2.25, 2.75
+        offs[0, 2, y + 3, x + 2], offs[0, 3, y + 3, x + 2] = -5.5, 2.5
+    eng = DecoderEngine(17, skel, topk=8, thre_hmp=0.1, min_len=0.5)
+    s, i, _ = eng.nms_topk(torch.from_numpy(heat).cuda())
+    got = eng.limb_score(s, i, torch.from_numpy(offs).cuda(), torch.from_numpy(sc).cuda()).cpu().numpy()
+    ref = ro.generate_limbs(heat, offs, skel, 8, 0.1, 0.5, 1, 1, scmps_hr=sc)
+    assert gio.compare_limbs(got, ref, 0.1, rtol=RTOL) >= 10
+    assert got[0, 1, :6, 6].max() > 2 ** 24       # ids of channel 16 exceed 2**24
+
+
+# --------------------------------------------------------------------------- K3
+def test_k3_group_fuzz_bit_exact(cuda_device):
+    cases = gio.load_group_fuzz()
+    for ci, c in enumerate(cases):
+        g = decoder.GreedyGroup(c['person_thre'], sort_dim=c['sort_dim'], dist_max=40,
+                                use_scale=c['use_scale'], keypoints=list(range(c['n_keypoints'])),
+                                skeleton=c['skeleton'])
+        got = g.group_skeletons(c['limbs'])
+        assert got.dtype == np.float32
+        assert got.shape == c['poses'].shape, f'case {ci}: person count {got.shape} vs {c["poses"].shape}'
+        assert np.array_equal(got, c['poses']), f'case {ci}'
+
+
+@pytest.mark.parametrize('name', ['limbs_coco_a', 'limbs_coco_noise', 'limbs_crowdpose'])
+def test_k3_on_reference_limbs_bit_exact(cuda_device, name):
+    d = gio.load_limbs_case(name)
+    g = decoder.GreedyGroup(d['person_thre'], sort_dim=2, dist_max=d['dist_max'], use_scale=True,
+                            keypoints=list(range(d['n_keypoints'])), skeleton=d['skeleton'])
+    got = g.group_batch(d['limbs'])
+    for p, r in zip(got, gio.split_poses(d['poses'], d['pose_counts'])):
+        gio.compare_poses(p, r, exact=True)
+
+
+def test_k3_random_tables_against_oracle(cuda_device):
+    """Fresh seeded fuzz (not from the fixture), incl. pure-noise tables that overflow the
+    shared-memory person table and restart on the global slab."""
+    rng = np.random.RandomState(77)
+    skel = cfg.COCO_PERSON_SKELETON
+    for case in range(40):
+        k = int(rng.choice([8, 32, 64]))
+        pool = int(rng.choice([3, 8, 400]))
+        limbs = np.zeros((19, k, 13), np.float32)
+        xy = rng.randint(1, 600, size=(17, pool, 2)).astype(np.float32)
+        ids = rng.randint(0, 640 * 640, size=(17, pool))
+        for l, (jf, jt) in enumerate(skel):
+            sc = (rng.permutation(k) + rng.uniform(0.1, 0.9, size=k)).astype(np.float32) / k
+            for r in range(k):
+                a, b = rng.randint(pool), rng.randint(pool)
+                limbs[l, r] = (xy[jf, a, 0], xy[jf, a, 1], 0.5, xy[jt, b, 0], xy[jt, b, 1], 0.6,
+                               ids[jf, a] + jf * 409600, ids[jt, b] + jt * 409600,
+                               rng.uniform(0, 50), 10, sc[r], 4, 4)
+        g = decoder.GreedyGroup(0.06, sort_dim=2, dist_max=40, use_scale=True)
+        got = g.group_skeletons(limbs)
+        ref = ro.group_skeletons(limbs, skel, 17, 0.06, 2, 40, True)
+        assert got.shape == ref.shape and np.array_equal(got, ref), f'case {case} k={k} pool={pool}'
+
+
+def test_k3_empty_and_degenerate(cuda_device):
+    g = decoder.GreedyGroup(0.06, sort_dim=2, dist_max=40, use_scale=False)
+    out = g.group_skeletons(np.zeros((19, 4, 13), np.float32))
+    assert out.shape == (0, 17, 6) and out.dtype == np.float32
+    with pytest.raises(AssertionError):
+        g.group_skeletons(np.zeros((18, 4, 13), np.float32))
+
+
+# --------------------------------------------------------------------------- maps
+def test_resize_and_flip_bit_exact(cuda_device):
+    from offsetguided_b200 import _lib
+    from offsetguided_b200.engine import _ptr, _stream_ptr
+    lib = _lib.load()
+    d = gio.load('resize_small')
+    for key, xk, scale, mode in (('bicubic4', 'x', 4, 1), ('bilinear4', 'x', 4, 0),
+                                 ('bicubic2', 'x2', 2, 1), ('bilinear2', 'x2', 2, 0)):
+        x = torch.from_numpy(d[xk]).cuda()
+        n, c, h, w = x.shape
+        out = torch.empty((n, c, h * scale, w * scale), device='cuda')
+        _lib.check(lib.og_resize_f32(_ptr(x), _ptr(out), n * c, h, w, scale, mode, _stream_ptr(x.device)))
+        assert np.array_equal(out.cpu().numpy(), d[key]), key      # == ATen CPU, bit for bit
+    # flip fusion vs the oracle
+    rng = np.random.RandomState(2)
+    hm = rng.uniform(0, 1, size=(4, 17, 12, 20)).astype(np.float32)
+    om = rng.uniform(-9, 9, size=(4, 38, 12, 20)).astype(np.float32)
+    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, cfg.COCO_PERSON_SKELETON)
+    eng = DecoderEngine(17, cfg.COCO_PERSON_SKELETON, topk=4)
+    fh = torch.empty((2, 17, 12, 20), device='cuda')
+    fo = torch.empty((2, 38, 12, 20), device='cuda')
+    _lib.check(lib.og_flip_fuse_f32(eng._h, _ptr(torch.from_numpy(hm).cuda()), _ptr(torch.from_numpy(om).cuda()),
+                                    _lib.int32_array(kp), _lib.int32_array(fl), _lib.int32_array(rs), len(rs),
+                                    2, 12, 20, _ptr(fh), _ptr(fo), _stream_ptr(fh.device)))
+    rh, rr = ro.flip_augment(hm, om, kp, fl, rs)
+    assert np.array_equal(fh.cpu().numpy(), rh) and np.array_equal(fo.cpu().numpy(), rr)
+
+
+def test_scored_offset_matches_oracle(cuda_device):
+    rng = np.random.RandomState(4)
+    hm = rng.uniform(0, 1, size=(2, 17, 20, 24)).astype(np.float32)
+    om = rng.uniform(-9, 9, size=(2, 38, 20, 24)).astype(np.float32)
+    jf, jt = ro.pack_jtypes(cfg.COCO_PERSON_SKELETON)
+    for ks in (3, 7):
+        got = decoder.scored_offset(torch.from_numpy(hm).cuda(), torch.from_numpy(om).cuda(), jf, jt, ks)
+        ref = ro.scored_offset(hm, om, jf, jt, ks)
+        np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=RTOL, atol=1e-6)
+
+
+# --------------------------------------------------------------------------- whole path
+@pytest.mark.parametrize('name', ['limbs_coco_a', 'limbs_coco_noise', 'limbs_crowdpose'])
+def test_decode_maps_matches_reference(cuda_device, name):
+    d = gio.load_limbs_case(name)
+    eng = _engine(d, d['n_keypoints'], d['skeleton'])
+    poses = eng.decode_maps(torch.from_numpy(d['heat']).cuda(), torch.from_numpy(d['offs']).cuda())
+    ref = gio.split_poses(d['poses'], d['pose_counts'])
+    assert len(poses) == len(ref)
+    for p, r in zip(poses, ref):
+        gio.compare_poses(p, r, rtol=RTOL)
+
+
+def _args(**over):
+    import argparse
+    p = argparse.ArgumentParser()
+    decoder.decoder_cli(p)
+    a = p.parse_args([])
+    a.headnets, a.strides, a.batch_size = ['hmp', 'omp'], [4, 4], 8
+    a.include_scale = a.include_jitter_offset = False
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a
+
+
+@pytest.mark.parametrize('name,host', [('poses_cfg1', False), ('poses_cfg2_flip', False),
+                                       ('poses_cfg1', True), ('poses_cfg2_flip', True)])
+def test_generate_poses_matches_reference(cuda_device, name, host):
+    """BASELINE configs 1 and 2 through the reference-facing API, device and host inputs."""
+    d = gio.load_poses_case(name)
+    pp = decoder.decoder_factory(_args(topk=d['topk'], thre_hmp=d['thre_hmp'], person_thre=d['person_thre'],
+                                       dist_max=d['dist_max']))
+    hmp, omp = torch.from_numpy(d['hmp']), torch.from_numpy(d['omp'])
+    if host:
+        hmp, omp = hmp.pin_memory(), omp.pin_memory()
+    else:
+        hmp, omp = hmp.cuda(), omp.cuda()
+    feats = [[[hmp], [[]], [[]]], [[omp], [[]], [[]]]]
+    poses = pp.generate_poses(feats, flip_test=d['flip_test'])
+    ref = gio.split_poses(d['poses'], d['pose_counts'])
+    assert len(poses) == len(ref)
+    for p, r in zip(poses, ref):
+        assert p.dtype == np.float32
+        gio.compare_poses(p, r, rtol=RTOL)
+    n = len(ref)
+    ds, di, lb = pp._engine(torch.device('cuda', 0)).last_intermediates(n)
+    live = d['det_scores'] >= np.float32(d['thre_hmp'])
+    assert np.array_equal(di.cpu().numpy()[live], d['det_inds'][live])         # bit-exact peaks
+    assert np.array_equal(ds.cpu().numpy()[live], d['det_scores'][live])       # after bicubic x4
+    assert gio.compare_limbs(lb.cpu().numpy(), d['limbs'], d['thre_hmp'], rtol=RTOL) > 50
+
+
+def test_generate_poses_scored_off_and_last_partial_batch(cuda_device):
+    d = gio.load_poses_case('poses_cfg2_flip')
+    pp = decoder.decoder_factory(_args(topk=32, thre_hmp=0.04, person_thre=0.04, dist_max=40))
+    hmp, omp = torch.from_numpy(d['hmp']).cuda(), torch.from_numpy(d['omp']).cuda()
+    feats = [[[hmp], [[]], [[]]], [[omp], [[]], [[]]]]
+    got = pp.generate_poses(feats, flip_test=True, scored_off=True)
+    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, cfg.COCO_PERSON_SKELETON)
+    fh, fo = ro.flip_augment(d['hmp'], d['omp'], kp, fl, rs)
+    jf, jt = ro.pack_jtypes(cfg.COCO_PERSON_SKELETON)
+    fo = ro.scored_offset(fh, fo, jf, jt, 3)
+    ref = ro.generate_poses(fh, fo, cfg.COCO_PERSON_SKELETON, 17, topk=32, thre_hmp=0.04, min_len=0.5,
+                            person_thre=0.04, dist_max=40, use_scale=True)
+    assert len(got) == len(ref) == 2
+    for p, r in zip(got, ref):
+        assert p.shape == r.shape
+        assert np.array_equal(p[..., 5], r[..., 5])
+        np.testing.assert_allclose(p, r, rtol=1e-4, atol=1e-3)
+    # a smaller last batch through the same PostProcess
+    feats1 = [[[hmp[[0, 2]]], [[]], [[]]], [[omp[[0, 2]]], [[]], [[]]]]
+    one = pp.generate_poses(feats1, flip_test=True)
+    two = pp.generate_poses(feats, flip_test=True)
+    assert len(one) == 1 and np.array_equal(one[0], two[0])
+
+
+def test_decode_full_size_properties(cuda_device):
+    """BASELINE sizes (640x640, batch 8): oracle comparison on 2 images plus
+    size-independent properties on all: determinism, batch-order equivariance,
+    dets sorted, persons sorted by score."""
+    skel = cfg.COCO_PERSON_SKELETON
+    heat, offs = scenes.synth_hires_batch(123, 8, 6, 640, 640, skel)
+    eng = DecoderEngine(17, skel, topk=32, thre_hmp=0.04, min_len=0.5, dist_max=40,
+                        use_scale=True, person_thre=0.04)
+    th, to = torch.from_numpy(heat).cuda(), torch.from_numpy(offs).cuda()
+    poses = eng.decode_maps(th, to)
+    ds, di, lb = eng.last_intermediates(8)
+    again = eng.decode_maps(th, to)
+    perm = [3, 1, 7, 0, 5, 2, 6, 4]
+    shuffled = eng.decode_maps(th[perm], to[perm])
+    for i in range(8):
+        assert np.array_equal(poses[i], again[i])
+        assert np.array_equal(shuffled[i], poses[perm[i]])
+        v = poses[i][:, :, 2]
+        sc = np.array([r[r > 0].mean() for r in v])
+        assert np.all(np.diff(sc) <= 1e-6)
+        assert len(poses[i]) >= 5
+    s = ds.cpu().numpy()
+    assert np.all(np.diff(s, axis=-1) <= 0)
+    ref_limbs = ro.generate_limbs(heat[:2], offs[:2], skel, 32, 0.04, 0.5, 1, 1)
+    assert gio.compare_limbs(lb.cpu().numpy()[:2], ref_limbs, 0.04, rtol=RTOL) > 150
+    for i in range(2):
+        ref = ro.group_skeletons(ref_limbs[i], skel, 17, 0.04, 2, 40, True)
+        gio.compare_poses(poses[i], ref, rtol=RTOL)

@@ -1,0 +1,121 @@
+"""CPU suite: host-side logic of the drop-in package and the C-ABI surface."""
+import argparse
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from offsetguided_b200 import config as cfg
+from offsetguided_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_flip_tables_match_reference_probe():
+    # values probed from the reference
+    assert cfg.heatmap_hflip(cfg.COCO_KEYPOINTS) == [0, 2, 1, 4, 3, 6, 5, 8, 7, 10, 9, 12, 11, 14, 13, 16, 15]
+    flips, reserve = cfg.offset_hflip(cfg.COCO_KEYPOINTS, cfg.COCO_PERSON_SKELETON)
+    assert flips == [1, 0, 2, 4, 3, 5, 7, 6, 10, 11, 8, 9, 13, 12, 14, 17, 18, 15, 16]
+    assert reserve == [2, 5, 14]
+
+
+def test_skeleton_tables():
+    assert len(cfg.COCO_PERSON_SKELETON) == 19
+    assert len(cfg.KINEMATIC_TREE_SKELETON) == 16
+    assert len(cfg.COCO_PERSON_WITH_REDUNDANT_SKELETON) == 31
+    assert len(cfg.DENSER_COCO_PERSON_SKELETON) == 44
+    assert len(cfg.REDUNDANT_CONNECTIONS) == 29
+    for a, b in cfg.CROWDPOSE_PERSON_SKELETON:
+        assert 0 <= a < 14 and 0 <= b < 14 and a != b
+    fl, rs = cfg.offset_hflip(cfg.CROWDPOSE_KEYPOINTS, cfg.CROWDPOSE_PERSON_SKELETON)
+    assert sorted(fl) == list(range(len(cfg.CROWDPOSE_PERSON_SKELETON)))
+
+
+def _args(**over):
+    from offsetguided_b200 import decoder
+    p = argparse.ArgumentParser()
+    decoder.decoder_cli(p)
+    a = p.parse_args([])
+    a.headnets = ['hmp', 'omp']
+    a.strides = [4, 4]
+    a.batch_size = 8
+    a.include_scale = False
+    a.include_jitter_offset = False
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a
+
+
+def test_cli_defaults_match_reference():
+    a = _args()
+    assert (a.resize_mode, a.topk, a.thre_hmp, a.min_len, a.feat_stage) == ('bicubic', 48, 0.06, 0.5, -1)
+    assert (a.person_thre, a.sort_dim, a.dist_max, a.use_scale, a.use_jitter_offset) == (0.06, 2, 20, True, True)
+    p = argparse.ArgumentParser()
+    from offsetguided_b200 import decoder
+    decoder.decoder_cli(p)
+    b = p.parse_args('--topk 32 --thre-hmp 0.04 --person-thre 0.04 --dist-max 40 --use-scale False'.split())
+    assert b.topk == 32 and b.use_scale is False and b.dist_max == 40.0
+    with pytest.raises(SystemExit):
+        p.parse_args(['--use-scale', 'maybe'])
+
+
+def test_decoder_factory_builds_without_gpu():
+    from offsetguided_b200 import decoder
+    pp = decoder.decoder_factory(_args(topk=32, dist_max=40))
+    assert isinstance(pp, decoder.PostProcess)
+    assert pp.skeleton == cfg.COCO_PERSON_SKELETON and pp.keypoints == cfg.COCO_KEYPOINTS
+    assert pp.limb_collect.K == 32 and pp.limb_collect.resize_factor == 1.0
+    assert pp.limb_group.dist_max == 40 and pp.limb_group.n_keypoints == 17
+    assert pp.limb_collect.jtypes_f[:3] == [0, 0, 1] and pp.limb_collect.jtypes_t[:3] == [1, 2, 2]
+    pp16 = decoder.decoder_factory(_args(headnets=['hmps', 'omp16']))
+    assert pp16.skeleton == cfg.KINEMATIC_TREE_SKELETON
+    with pytest.raises(Exception):
+        decoder.decoder_factory(_args(headnets=['hmp', 'omp99']))
+    with pytest.raises(Exception):
+        decoder.decoder_factory(_args(headnets=['foo', 'omp']))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build()
+    assert os.path.exists(path)
+    header = open(os.path.join(ROOT, 'include', 'og_decoder.h')).read()
+    declared = set(re.findall(r'\b(og_[a-z0-9_]+)\s*\(', header))
+    declared -= {'og_status'}
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(path)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in og_decoder.h but not exported'
+    assert declared == set(_lib.SIGNATURES), 'ctypes stub and header disagree'
+    loaded = _lib.load()
+    assert loaded.og_abi_version() == 1
+    assert loaded.og_status_string(0) == b'ok'
+
+
+def test_config_struct_layout_matches_header():
+    # field order / types of og_config as the header declares them
+    header = open(os.path.join(ROOT, 'include', 'og_decoder.h')).read()
+    body = header[header.index('typedef struct og_config {'):header.index('} og_config;')]
+    names = re.findall(r'^\s*(?:const\s+)?\w+\s+\*?([a-z_]+);', body, flags=re.M)
+    assert names == [f[0] for f in _lib.OgConfig._fields_]
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from offsetguided_b200 import decoder
+    with pytest.raises(Exception):
+        decoder.hmp_NMS(torch.zeros(1, 1, 8, 8))
+    with pytest.raises(Exception):
+        decoder.GreedyGroup(0.06).group_skeletons(np.zeros((19, 4, 13), np.float32))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'offsetguided_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src.replace('no oracle', ''), f'{f} mentions the oracle'
