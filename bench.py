@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the OffsetGuided post-network decoder on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" decodes one batch of synthetic network outputs: BASELINE.json configs[1]
+settings (COCO skeleton, flip-test fusion, x4 resize to 640x640, topk 32, thre-hmp 0.04,
+person-thre 0.04, dist-max 40) at the north-star batch of 64 images per GPU.
+
+  value     images/s of the hot path (K1 NMS+top-K -> K2 limb scoring -> K3 grouping, poses
+            copied to pinned memory) on full-resolution maps RESIDENT IN HBM, CUDA-event
+            timed on the launching stream, max over ranks;
+  e2e       images/s through the reference-facing API PostProcess.generate_poses with
+            HOST (pinned) network-resolution maps: H2D copy, flip fusion, x4 resize,
+            K1..K3 and the D2H read of the poses are all inside the timed region;
+  roofline  K1 (both passes) algorithmic bytes N*C*H*W*4 over its CUDA-event duration,
+            against the measured HBM copy peak (MEASURED_PEAKS.json);
+  cpu_baseline  the oracle port of the reference decoder (oracle/) on the host cores, on
+            a bounded sample of the same workload.
+
+Multi-GPU: images are independent, every rank decodes its own batch (weak scaling, no
+collective on the data path); launched by torchrun for N > 1.
+`--impl reference` times the CPU oracle port alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'decoded images/s @640 long-edge'
+UNIT = 'images/s'
+TOPK, THRE_HMP, PERSON_THRE, DIST_MAX, MIN_LEN = 32, 0.04, 0.04, 40.0, 0.5
+PERSONS = 6
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='images per GPU per step')
+    ap.add_argument('--long-edge', type=int, default=640)
+    ap.add_argument('--no-flip', action='store_true', help='e2e without flip-test inputs')
+    ap.add_argument('--cpu-sample', type=int, default=0, help='images of the CPU sample (0 = auto)')
+    ap.add_argument('--hot-only', action='store_true',
+                    help='run only the HBM-resident hot path (for ncu captures; prints no bench line)')
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        'workload': 'BASELINE configs[1] settings at batch %d per GPU: COCO 17 keypoints / 19 limbs, '
+                    'network maps %dx%d (x4 -> %dx%d), %s, topk=%d, thre_hmp=%.2f, person_thre=%.2f, '
+                    'dist_max=%d' % (args.batch, args.long_edge // 4, args.long_edge // 4, args.long_edge,
+                                     args.long_edge, 'no flip' if args.no_flip else 'flip-test fusion',
+                                     TOPK, THRE_HMP, PERSON_THRE, int(DIST_MAX)),
+        'images_per_gpu_per_step': args.batch,
+        'global_batch': args.batch * n_gpus,
+        'parallelism': 'image-sharded x%d, no collective' % n_gpus,
+        'l2_policy': 'hot-path inputs are 5.8 GB per step (heat 1.78 GB + offsets 3.98 GB) >> 126 MB L2',
+        'persons_per_image': PERSONS,
+    }
+
+
+# --------------------------------------------------------------------------- inputs
+def lowres_inputs(seed, n, long_edge, flip):
+    """Network-resolution maps as the reference encoder renders them (oracle/scenes.py
+    restates encoder/heatmap.py and encoder/offset.py); flipped half from mirrored persons."""
+    from oracle import scenes
+    from offsetguided_b200 import config as cfg
+    skel = cfg.COCO_PERSON_SKELETON
+    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    distinct = min(n, 16)
+    hs, os_, hf, of = [], [], [], []
+    for i in range(distinct):
+        rng = np.random.RandomState(seed + i)
+        p = scenes.make_persons(rng, PERSONS, long_edge, long_edge,
+                                scale_range=(long_edge / 64.0, long_edge / 27.0))
+        hs.append(scenes.render_heatmaps(p, long_edge, long_edge) +
+                  rng.uniform(0, 0.02, size=(17, long_edge // 4, long_edge // 4)).astype(np.float32))
+        os_.append(scenes.render_offsets(p, long_edge, long_edge, skel))
+        if flip:
+            pf = scenes.mirror_persons(p, long_edge, kp)
+            hf.append(scenes.render_heatmaps(pf, long_edge, long_edge) +
+                      rng.uniform(0, 0.02, size=(17, long_edge // 4, long_edge // 4)).astype(np.float32))
+            of.append(scenes.render_offsets(pf, long_edge, long_edge, skel))
+    reps = (n + distinct - 1) // distinct
+
+    def tile(lst):
+        return np.concatenate([np.stack(lst)] * reps)[:n]
+    hmp = tile(hs)
+    omp = tile(os_)
+    if flip:
+        hmp = np.concatenate((hmp, tile(hf)))
+        omp = np.concatenate((omp, tile(of)))
+    omp[~np.isfinite(omp)] = 0
+    return hmp.astype(np.float32), omp.astype(np.float32)
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_decode_fn():
+    """The oracle port of the reference decoder: multi-threaded C restatement when it has
+    been built (oracle/og_oracle.c), else the numpy restatement (single thread)."""
+    from offsetguided_b200 import config as cfg
+    skel = cfg.COCO_PERSON_SKELETON
+    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel)
+    try:
+        from oracle import c_oracle
+        c_oracle.load()
+        cores = c_oracle.num_threads()
+
+        def run(hmp, omp, flip):
+            return c_oracle.generate_poses(hmp, omp, skel, 17, topk=TOPK, thre_hmp=THRE_HMP,
+                                           min_len=MIN_LEN, person_thre=PERSON_THRE, dist_max=DIST_MAX,
+                                           use_scale=True, flip_test=flip, kp_flips=kp, limb_flips=fl,
+                                           limb_reserve=rs)
+        return run, cores, 'oracle/og_oracle.c (C + OpenMP restatement of the reference decoder)'
+    except Exception:
+        from oracle import ref_oracle as ro
+
+        def run(hmp, omp, flip):
+            return ro.generate_poses(hmp, omp, skel, 17, topk=TOPK, thre_hmp=THRE_HMP, min_len=MIN_LEN,
+                                     person_thre=PERSON_THRE, dist_max=DIST_MAX, use_scale=True,
+                                     flip_test=flip, kp_flips=kp, limb_flips=fl, limb_reserve=rs)
+        return run, 1, 'oracle/ref_oracle.py (numpy restatement of the reference decoder)'
+
+
+def time_cpu(args, n_images, repeats):
+    run, cores, what = cpu_decode_fn()
+    flip = not args.no_flip
+    hmp, omp = lowres_inputs(9000, n_images, args.long_edge, flip)
+    run(hmp[:1] if not flip else np.concatenate((hmp[:1], hmp[n_images:n_images + 1])),
+        omp[:1] if not flip else np.concatenate((omp[:1], omp[n_images:n_images + 1])), flip)   # warm
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        poses = run(hmp, omp, flip)
+        times.append(time.perf_counter() - t0)
+        assert len(poses) == n_images
+    best = min(times)
+    return n_images / best, cores, what, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    run, cores, what = cpu_decode_fn()
+    n_images = args.cpu_sample or (8 if cores > 1 else 1)
+    flip = not args.no_flip
+    hmp, omp = lowres_inputs(9000, n_images, args.long_edge, flip)
+    for _ in range(min(args.warmup, 1)):
+        run(hmp, omp, flip)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(hmp, omp, flip)
+    dt = time.perf_counter() - t0
+    value = n_images * args.steps / dt
+    sample = '%d images per step (of the %d-image batch), %d steps, %s' % (n_images, args.batch, args.steps, what)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': workload_config(args, args.gpus),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from offsetguided_b200 import config as cfg
+    from offsetguided_b200 import decoder
+    from offsetguided_b200.engine import DecoderEngine
+    from oracle import scenes
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    n_gpus = world
+
+    skel = cfg.COCO_PERSON_SKELETON
+    B, E = args.batch, args.long_edge
+    flip = not args.no_flip
+
+    # ---- hot path on HBM-resident full-resolution maps
+    distinct = min(B, 8)
+    heat_np, offs_np = scenes.synth_hires_batch(1000 * (rank + 1), distinct, PERSONS, E, E, skel)
+    heat = torch.from_numpy(heat_np).to(dev).repeat((B + distinct - 1) // distinct, 1, 1, 1)[:B].contiguous()
+    offs = torch.from_numpy(offs_np).to(dev).repeat((B + distinct - 1) // distinct, 1, 1, 1)[:B].contiguous()
+    del heat_np, offs_np
+    eng = DecoderEngine(17, skel, topk=TOPK, thre_hmp=THRE_HMP, min_len=MIN_LEN, dist_max=DIST_MAX,
+                        use_scale=True, person_thre=PERSON_THRE, device=dev)
+    eng.enable_stage_timing(True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        poses = eng.decode_maps(heat, offs)
+    n_persons = sum(len(p) for p in poses)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = eng.launch_count
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stages = []
+    start.record()
+    for _ in range(args.steps):
+        eng.decode_maps(heat, offs)
+        stages.append(eng.last_stage_times_ms())
+    stop.record()
+    barrier()
+    hot_ms = start.elapsed_time(stop)
+    hot_launches = eng.launch_count - launches0
+    if args.hot_only:
+        sampler.stop()
+        print('hot-only: %.3f ms/step, stages %s' % (hot_ms / args.steps, stages[-1]), file=sys.stderr)
+        return
+
+    # ---- end to end through the reference-facing API, host buffers
+    ap = argparse.ArgumentParser()
+    decoder.decoder_cli(ap)
+    dargs = ap.parse_args(['--topk', str(TOPK), '--thre-hmp', str(THRE_HMP), '--person-thre', str(PERSON_THRE),
+                           '--dist-max', str(DIST_MAX)])
+    dargs.headnets, dargs.strides, dargs.batch_size = ['hmp', 'omp'], [4, 4], B
+    dargs.include_scale = dargs.include_jitter_offset = False
+    post = decoder.decoder_factory(dargs)
+    hmp_np, omp_np = lowres_inputs(5000 * (rank + 1), B, E, flip)
+    hmp_h = torch.from_numpy(hmp_np).pin_memory()
+    omp_h = torch.from_numpy(omp_np).pin_memory()
+    feats = [[[hmp_h], [[]], [[]]], [[omp_h], [[]], [[]]]]
+    e2e_eng = post._engine(dev)
+    for _ in range(args.warmup):
+        out = post.generate_poses(feats, flip_test=flip)
+    e2e_l0 = e2e_eng.launch_count
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = post.generate_poses(feats, flip_test=flip)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+    e2e_launches = e2e_eng.launch_count - e2e_l0
+    h2d = hmp_h.numel() * 4 + omp_h.numel() * 4
+    d2h = sum(p.nbytes for p in out) + (2 * B + 1) * 4
+
+    # ---- max over ranks
+    times = torch.tensor([hot_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    hot_ms, e2e_ms = [float(v) for v in times.cpu()]
+
+    if rank == 0:
+        k1_ms = statistics.mean(s['k1_stream'] + s['k1_select'] for s in stages)
+        k1_stream_ms = statistics.mean(s['k1_stream'] for s in stages)
+        stage_mean = {k: statistics.mean(s[k] for s in stages) for k in stages[0]}
+        alg_bytes = B * 17 * E * E * 4 + B * 17 * TOPK * 8
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+        try:
+            mp = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+            peak, peak_src = float(mp['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+        achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'k1_traffic.json')))['dram_bytes_per_launch']
+        except Exception:
+            pass
+        cpu_n = args.cpu_sample or 0
+        run, cores, what = cpu_decode_fn()
+        cpu_n = cpu_n or (16 if cores > 1 else 1)
+        cpu_value, cores, what, cpu_times = time_cpu(args, cpu_n, 2 if cores > 1 else 1)
+        line = {
+            'metric': METRIC, 'value': n_gpus * B * args.steps / (hot_ms * 1e-3), 'unit': UNIT,
+            'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': hot_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args, n_gpus),
+            'e2e': {'value': n_gpus * B * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': e2e_ms / args.steps,
+                    'api': 'decoder_factory(args).generate_poses(features, flip_test=%s), pinned host maps' % flip},
+            'gpu_launches': hot_launches + e2e_launches,
+            'gpu_launches_detail': {'hot_path': hot_launches, 'e2e': e2e_launches},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                         'kernel': 'K1 = nms_candidates_kernel + select_topk_kernel',
+                         'algorithmic_bytes_per_launch': alg_bytes, 'ms_per_launch': k1_ms,
+                         'stream_pass_only_gbs': alg_bytes / (k1_stream_ms * 1e-3) / 1e9},
+            'stage_ms': stage_mean,
+            'persons_per_step': n_persons,
+            'cpu_baseline': {'value': cpu_value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': '%d images of the same workload (flip fusion + x4 resize + NMS/top-K '
+                                       '+ limbs + grouping), best of %d, %s' % (cpu_n, len(cpu_times), what)},
+            'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

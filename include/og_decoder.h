@@ -181,6 +181,13 @@ int og_copy_intermediates(og_handle *h, int n, float *det_score_dev, int32_t *de
 /* Number of kernels this library has launched through the handle so far. */
 int64_t og_launch_count(const og_handle *h);
 
+/* Per-stage device timing of og_decode_* calls with CUDA events recorded on the
+ * launching stream.  og_last_stage_times_ms() waits for the last decode and fills
+ * out6 = { input copy + flip + resize, K1 pass 1 (NMS stream), K1 pass 2 (select),
+ *          K2, K3, pose D2H } in milliseconds. */
+int og_enable_stage_timing(og_handle *h, int enable);
+int og_last_stage_times_ms(og_handle *h, float *out6);
+
 #ifdef __cplusplus
 }
 #endif

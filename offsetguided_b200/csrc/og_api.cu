@@ -104,6 +104,12 @@ struct og_handle {
     int last_capacity_rows;
     int rows_hint;
     bool pending;
+
+    // optional per-stage timing (og_enable_stage_timing)
+    bool timing;
+    bool timing_valid;
+    bool prep_marked;
+    cudaEvent_t ev[7];      // start, after prep, after K1 pass 1, K1 pass 2, K2, K3, D2H
 };
 
 namespace {
@@ -128,13 +134,19 @@ int check_maps(int n, int hgt, int w, int c) {
     return OG_OK;
 }
 
+inline int mark(og_handle *h, int which, cudaStream_t s) {
+    if (h->timing) OG_CUDA_TRY(cudaEventRecord(h->ev[which], s));
+    return OG_OK;
+}
+
 int run_k1(og_handle *h, const float *heat, int n, int hgt, int w, float thre, float *score,
-           int32_t *index, int32_t *count, cudaStream_t s) {
+           int32_t *index, int32_t *count, cudaStream_t s, cudaEvent_t after_pass1 = nullptr) {
     const int planes = n * h->cfg.n_keypoints;
     OG_TRY(h->cand_count.ensure(planes));
     OG_TRY(h->cand_keys.ensure((size_t)planes * kCandCap));
     return launch_nms_topk(heat, planes, hgt, w, thre, h->cfg.topk, h->cand_count.ptr,
-                           h->cand_keys.ptr, score, index, count, false, true, s, &h->launches);
+                           h->cand_keys.ptr, score, index, count, false, true, s, &h->launches,
+                           after_pass1);
 }
 
 int run_k3(og_handle *h, const float *limbs, int n, float *out_poses, int capacity_rows,
@@ -189,19 +201,28 @@ int decode_maps_impl(og_handle *h, const float *heat, const float *offs, const f
         h->last_rows_copied = 0;
         return OG_OK;
     }
+    h->timing_valid = false;
+    if (!h->prep_marked) OG_TRY(mark(h, 0, s));
+    OG_TRY(mark(h, 1, s));
+    h->prep_marked = false;
     OG_TRY(run_k1(h, heat, n, hgt, w, c.thre_hmp, h->det_score.ptr, h->det_index.ptr,
-                  h->det_count.ptr, s));
+                  h->det_count.ptr, s, h->timing ? h->ev[2] : nullptr));
+    OG_TRY(mark(h, 3, s));
     OG_TRY(launch_limb_score(h->det_score.ptr, h->det_index.ptr, offs, scales, n, c.n_keypoints,
                              c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp, c.min_len,
                              c.resize_factor, h->limbs.ptr, s));
     h->launches += 1;
+    OG_TRY(mark(h, 4, s));
     OG_TRY(run_k3(h, h->limbs.ptr, n, poses, capacity_rows, meta, meta + n, meta + 2 * n, s));
+    OG_TRY(mark(h, 5, s));
 
     // one asynchronous copy: meta + the first rows_hint pose rows
     const int rows = std::min(capacity_rows, std::max(h->rows_hint, n * 32));
     const size_t bytes = mbytes + (size_t)rows * pose_row_bytes(h);
     OG_TRY(h->out_host.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
     OG_CUDA_TRY(cudaMemcpyAsync(h->out_host.ptr, h->out.ptr, bytes, cudaMemcpyDeviceToHost, s));
+    OG_TRY(mark(h, 6, s));
+    h->timing_valid = h->timing;
     OG_CUDA_TRY(cudaEventRecord(h->done, s));
     h->last_rows_copied = rows;
     h->pending = true;
@@ -245,6 +266,10 @@ int decode_features_impl(og_handle *h, const float *hmp, const float *off, int n
     OG_REQUIRE(resize_mode == 0 || resize_mode == 1, "resize_mode must be 0 (bilinear) or 1 (bicubic)");
     const float *cur_h = hmp, *cur_o = off;
     const size_t hw = (size_t)hgt * w;
+    if (!h->prep_marked) {
+        OG_TRY(mark(h, 0, s));
+        h->prep_marked = h->timing;
+    }
     if (flip_test) {
         OG_TRY(upload_flip_tables(h, kp_flip, limb_flip, limb_reserve, n_reserve, s));
         OG_TRY(h->fused_hmp.ensure((size_t)n * c.n_keypoints * hw));
@@ -344,6 +369,10 @@ int og_create(const og_config *cfg, og_handle **out) {
     h->last_n = 0;
     h->rows_hint = 0;
     h->last_stream = nullptr;
+    h->timing = false;
+    h->timing_valid = false;
+    h->prep_marked = false;
+    for (int i = 0; i < 7; ++i) h->ev[i] = nullptr;
 
     // person-table rows held in shared memory: as many as fit beside the work arrays
     GroupLaunch g;
@@ -401,6 +430,8 @@ int og_destroy(og_handle *h) {
     h->limb_flip.release();
     h->limb_reserved.release();
     cudaEventDestroy(h->done);
+    for (int i = 0; i < 7; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
     return OG_OK;
 }
@@ -527,6 +558,8 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
     const size_t hw = (size_t)hgt * w;
     OG_TRY(h->in_hmp.ensure(n_in * c.n_keypoints * hw));
     OG_TRY(h->in_off.ensure(n_in * 2 * c.n_limbs * hw));
+    OG_TRY(mark(h, 0, s));
+    h->prep_marked = h->timing;
     OG_CUDA_TRY(cudaMemcpyAsync(h->in_hmp.ptr, hmp_host, n_in * c.n_keypoints * hw * sizeof(float),
                                 cudaMemcpyHostToDevice, s));
     OG_CUDA_TRY(cudaMemcpyAsync(h->in_off.ptr, off_host, n_in * 2 * c.n_limbs * hw * sizeof(float),
@@ -589,5 +622,26 @@ int og_copy_intermediates(og_handle *h, int n, float *det_score_dev, int32_t *de
 }
 
 int64_t og_launch_count(const og_handle *h) { return h ? h->launches : 0; }
+
+int og_enable_stage_timing(og_handle *h, int enable) {
+    OG_REQUIRE(h, "og_enable_stage_timing: null handle");
+    OG_TRY(check_device(h));
+    if (enable) {
+        for (int i = 0; i < 7; ++i)
+            if (!h->ev[i]) OG_CUDA_TRY(cudaEventCreate(&h->ev[i]));
+    }
+    h->timing = enable != 0;
+    h->timing_valid = false;
+    h->prep_marked = false;
+    return OG_OK;
+}
+
+int og_last_stage_times_ms(og_handle *h, float *out6) {
+    OG_REQUIRE(h && out6, "og_last_stage_times_ms: null pointer");
+    OG_REQUIRE(h->timing_valid, "og_last_stage_times_ms: enable stage timing and decode first");
+    OG_CUDA_TRY(cudaEventSynchronize(h->ev[6]));
+    for (int i = 0; i < 6; ++i) OG_CUDA_TRY(cudaEventElapsedTime(&out6[i], h->ev[i], h->ev[i + 1]));
+    return OG_OK;
+}
 
 }  // extern "C"

@@ -74,7 +74,8 @@ int launch_hmp_nms(const float *heat, float *out, int planes, int h, int w, cuda
 int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int k,
                     uint32_t *cand_count, uint64_t *cand_keys,
                     float *out_score, int32_t *out_index, int32_t *out_count,
-                    bool force_radix, bool apply_nms, cudaStream_t s, int64_t *launches);
+                    bool force_radix, bool apply_nms, cudaStream_t s, int64_t *launches,
+                    cudaEvent_t after_pass1 = nullptr);
 
 int launch_limb_score(const float *det_score, const int32_t *det_index, const float *offs,
                       const float *scales, int n, int c, int l, int k, int h, int w,

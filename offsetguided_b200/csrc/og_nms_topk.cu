@@ -359,7 +359,7 @@ int launch_hmp_nms(const float *heat, float *out, int planes, int h, int w, cuda
 int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int k,
                     uint32_t *cand_count, uint64_t *cand_keys, float *out_score,
                     int32_t *out_index, int32_t *out_count, bool force_radix, bool apply_nms,
-                    cudaStream_t s, int64_t *launches) {
+                    cudaStream_t s, int64_t *launches, cudaEvent_t after_pass1) {
     if (planes == 0) return OG_OK;
     if (!force_radix) {
         OG_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t) * planes, s));
@@ -376,6 +376,7 @@ int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int
         OG_CUDA_TRY(cudaGetLastError());
         if (launches) *launches += 1;
     }
+    if (after_pass1) OG_CUDA_TRY(cudaEventRecord(after_pass1, s));
     select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
                                                         out_score, out_index, out_count,
                                                         force_radix ? 1 : 0, apply_nms ? 1 : 0);

@@ -207,6 +207,17 @@ class DecoderEngine(object):
         with torch.cuda.device(self.device):
             return self._fetch(n)
 
+    def enable_stage_timing(self, on=True):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.og_enable_stage_timing(self._h, 1 if on else 0))
+
+    def last_stage_times_ms(self):
+        """{prep, k1_stream, k1_select, k2, k3, d2h} of the last decode call, in ms."""
+        out = (ctypes.c_float * 6)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.og_last_stage_times_ms(self._h, out))
+        return dict(zip(('prep', 'k1_stream', 'k1_select', 'k2', 'k3', 'd2h'), [float(v) for v in out]))
+
     def last_intermediates(self, n):
         """Copies of the last decode call's dets (scores, indices) and limbs."""
         c, k, l = self.n_keypoints, self.topk, self.n_limbs

@@ -221,7 +221,8 @@ def test_resize_and_flip_bit_exact(cuda_device):
     eng = DecoderEngine(17, cfg.COCO_PERSON_SKELETON, topk=4)
     fh = torch.empty((2, 17, 12, 20), device='cuda')
     fo = torch.empty((2, 38, 12, 20), device='cuda')
-    _lib.check(lib.og_flip_fuse_f32(eng._h, _ptr(torch.from_numpy(hm).cuda()), _ptr(torch.from_numpy(om).cuda()),
+    hm_d, om_d = torch.from_numpy(hm).cuda(), torch.from_numpy(om).cuda()
+    _lib.check(lib.og_flip_fuse_f32(eng._h, _ptr(hm_d), _ptr(om_d),
                                     _lib.int32_array(kp), _lib.int32_array(fl), _lib.int32_array(rs), len(rs),
                                     2, 12, 20, _ptr(fh), _ptr(fo), _stream_ptr(fh.device)))
     rh, rr = ro.flip_augment(hm, om, kp, fl, rs)
