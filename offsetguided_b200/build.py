@@ -39,20 +39,24 @@ def needs_build():
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile the library if it is missing or older than its sources."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=None, out=None):
+    """Compile the library if it is missing or older than its sources.
+    ``defines`` / ``out`` build a tuning variant (e.g. {'OG_K1_UNROLL': 4}) elsewhere."""
+    if out is None and not force and not needs_build():
         return LIB_PATH
+    out = out or LIB_PATH
     cmd = [find_nvcc()] + NVCC_FLAGS
+    for key, val in (defines or {}).items():
+        cmd.append('-D%s=%s' % (key, val))
     if verbose:
         cmd += ['-Xptxas', '-v']
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB_PATH]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ['-o', out]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == '__main__':

@@ -24,8 +24,19 @@ namespace og {
 
 namespace {
 
-constexpr int kRowsPerWarp = 64;     // rows of one warp's strip (halo re-read 2/64)
-constexpr int kUnroll = 8;           // rows fetched ahead per lane (8 x 16 B in flight)
+// tuning knobs (profiles/k1_tuning.md records the sweep on B200)
+#ifndef OG_K1_ROWS
+#define OG_K1_ROWS 32
+#endif
+#ifndef OG_K1_UNROLL
+#define OG_K1_UNROLL 8
+#endif
+#ifndef OG_K1_THREADS
+#define OG_K1_THREADS 256
+#endif
+constexpr int kRowsPerWarp = OG_K1_ROWS;   // rows of one warp's 128-column strip
+constexpr int kUnroll = OG_K1_UNROLL;      // rows fetched ahead per lane (x 16 B in flight)
+constexpr int kK1Threads = OG_K1_THREADS;
 constexpr int kSelectThreads = 256;
 constexpr int kRadixBins = 2048;
 
@@ -51,7 +62,7 @@ __device__ __forceinline__ bool survives(float v, float m, float thre, float &nv
 }
 
 template <bool kThrePositive, bool kVec4>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kK1Threads)
 nms_candidates_kernel(const float *__restrict__ heat, int planes, int H, int W, float thre,
                       uint32_t *__restrict__ cand_count, uint64_t *__restrict__ cand_keys) {
     const int lane = threadIdx.x & 31;
@@ -70,14 +81,13 @@ nms_candidates_kernel(const float *__restrict__ heat, int planes, int H, int W, 
     const int r_begin = chunk * kRowsPerWarp;
     const int r_end = min(H, r_begin + kRowsPerWarp);
 
-    // lane 0 / lane 31 fetch the column just outside the warp's strip
+    // lane 0 / lane 31 own the column just outside the warp's strip (slow path only)
     int hx = -1;
     if (lane == 0 && x0 > 0) hx = x0 - 1;
     if (lane == 31 && x0 + 4 < W) hx = x0 + 4;
 
-    auto load_row = [&](int r, float4 &v, float &e) {
-        v = make_float4(0.f, 0.f, 0.f, 0.f);
-        e = 0.f;
+    auto load_row = [&](int r) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);      // zero padding outside the image
         if (r >= 0 && r < H) {
             const float *row = p + (size_t)r * W;
             if (kVec4) {
@@ -88,8 +98,11 @@ nms_candidates_kernel(const float *__restrict__ heat, int planes, int H, int W, 
                 if (x0 + 2 < W) v.z = __ldg(row + x0 + 2);
                 if (x0 + 3 < W) v.w = __ldg(row + x0 + 3);
             }
-            if (hx >= 0) e = __ldg(row + hx);
         }
+        return v;
+    };
+    auto halo = [&](int r) {
+        return (hx >= 0 && r >= 0 && r < H) ? __ldg(p + (size_t)r * W + hx) : 0.0f;
     };
     auto hmax_row = [&](const float4 &v, float e) {
         float left = __shfl_up_sync(0xffffffffu, v.w, 1);
@@ -108,37 +121,56 @@ nms_candidates_kernel(const float *__restrict__ heat, int planes, int H, int W, 
                 cand_keys[(size_t)plane * kCandCap + pos] = make_key(nv, (uint32_t)(r * W + x));
         }
     };
+    // Full 3x3 test of one row; executed by the whole warp, only for rows in which some
+    // lane holds a value >= thre (a few percent of the rows of a real heat map).  The three
+    // rows are re-read (L2 hits: this warp or its neighbours streamed them just before).
+    auto check_row = [&](int row) {
+        const float4 mid = load_row(row);
+        const float4 h0 = hmax_row(load_row(row - 1), halo(row - 1));
+        const float4 h1 = hmax_row(mid, halo(row));
+        const float4 h2 = hmax_row(load_row(row + 1), halo(row + 1));
+        emit(mid.x, max3(h0.x, h1.x, h2.x), x0 + 0, row);
+        emit(mid.y, max3(h0.y, h1.y, h2.y), x0 + 1, row);
+        emit(mid.z, max3(h0.z, h1.z, h2.z), x0 + 2, row);
+        emit(mid.w, max3(h0.w, h1.w, h2.w), x0 + 3, row);
+    };
 
-    float4 v_cur, h_prev, h_cur;
-    {
-        float4 v;
-        float e;
-        load_row(r_begin - 1, v, e);
-        h_prev = hmax_row(v, e);
-        load_row(r_begin, v_cur, e);
-        h_cur = hmax_row(v_cur, e);
+    // streaming pass: rows r_begin .. r_end-1 lie inside the image, no bounds tests needed
+    auto stream_row = [&](const float *row) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kVec4) {
+            if (x0 < W) v = ldg_stream_f4(row);
+        } else {
+            if (x0 + 0 < W) v.x = __ldg(row + 0);
+            if (x0 + 1 < W) v.y = __ldg(row + 1);
+            if (x0 + 2 < W) v.z = __ldg(row + 2);
+            if (x0 + 3 < W) v.w = __ldg(row + 3);
+        }
+        return v;
+    };
+    auto is_hot = [&](const float4 &v) {
+        return kThrePositive ? (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= thre) : true;
+    };
+    const float *row = p + (size_t)r_begin * W + x0;
+    int r = r_begin;
+    for (; r + kUnroll <= r_end; r += kUnroll) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = stream_row(row + (size_t)u * W);
+        row += (size_t)kUnroll * W;
+        unsigned hot = 0;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) hot |= is_hot(v[u]) ? (1u << u) : 0u;
+        hot = __reduce_or_sync(0xffffffffu, hot);
+        while (hot) {                       // warp-uniform
+            const int u = __ffs(hot) - 1;
+            hot &= hot - 1;
+            check_row(r + u);
+        }
     }
-    for (int r = r_begin; r < r_end; r += kUnroll) {
-        float4 vn[kUnroll];
-        float en[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            if (r + u < r_end) load_row(r + 1 + u, vn[u], en[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            if (r + u < r_end) {
-                const float4 h_next = hmax_row(vn[u], en[u]);
-                const int row = r + u;
-                emit(v_cur.x, max3(h_prev.x, h_cur.x, h_next.x), x0 + 0, row);
-                emit(v_cur.y, max3(h_prev.y, h_cur.y, h_next.y), x0 + 1, row);
-                emit(v_cur.z, max3(h_prev.z, h_cur.z, h_next.z), x0 + 2, row);
-                emit(v_cur.w, max3(h_prev.w, h_cur.w, h_next.w), x0 + 3, row);
-                h_prev = h_cur;
-                h_cur = h_next;
-                v_cur = vn[u];
-            }
-        }
+    for (; r < r_end; ++r, row += W) {      // fewer than kUnroll rows left
+        const float4 v = stream_row(row);
+        if (__any_sync(0xffffffffu, is_hot(v))) check_row(r);
     }
 }
 
@@ -366,7 +398,7 @@ int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int
         const int strips = (w + 127) / 128;
         const int chunks = (h + kRowsPerWarp - 1) / kRowsPerWarp;
         const long long warps = (long long)planes * strips * chunks;
-        const int threads = 256;
+        const int threads = kK1Threads;
         const long long blocks = (warps + (threads / 32) - 1) / (threads / 32);
         const bool vec4 = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
         const bool pos = thre > 0.0f;
