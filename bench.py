@@ -306,13 +306,16 @@ def run_b200(args):
     omp_h = torch.from_numpy(omp_np).pin_memory()
     feats = [[[hmp_h], [[]], [[]]], [[omp_h], [[]], [[]]]]
     e2e_eng = post._engine(dev)
+    e2e_eng.enable_stage_timing(True)
     for _ in range(args.warmup):
         out = post.generate_poses(feats, flip_test=flip)
     e2e_l0 = e2e_eng.launch_count
     barrier()
     t0 = time.perf_counter()
+    e2e_stages = []
     for _ in range(args.steps):
         out = post.generate_poses(feats, flip_test=flip)
+        e2e_stages.append(e2e_eng.last_stage_times_ms())
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -357,6 +360,8 @@ def run_b200(args):
             'e2e': {'value': n_gpus * B * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_ms / args.steps,
+                    'stage_ms': {k: statistics.mean(s[k] for s in e2e_stages) for k in e2e_stages[0]},
+                    'fused_redos': e2e_eng.fused_redo_count,
                     'api': 'decoder_factory(args).generate_poses(features, flip_test=%s), pinned host maps' % flip},
             'gpu_launches': hot_launches + e2e_launches,
             'gpu_launches_detail': {'hot_path': hot_launches, 'e2e': e2e_launches},

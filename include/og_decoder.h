@@ -181,6 +181,16 @@ int og_copy_intermediates(og_handle *h, int n, float *det_score_dev, int32_t *de
 /* Number of kernels this library has launched through the handle so far. */
 int64_t og_launch_count(const og_handle *h);
 
+/* og_decode_features_* use a fused path by default (strides 2/4/8, thre_hmp > 0): flip
+ * fusion + resize + NMS in one kernel over the network-resolution maps, offsets sampled at
+ * the candidates; results are bit-identical to the materialising path.  If a heat-map plane
+ * yields more than 2048 candidates (noise-like input) og_fetch_poses re-runs the batch on the
+ * GPU through the materialising path; the input buffers of og_decode_features_dev must
+ * therefore stay valid until og_fetch_poses returns.  og_set_fused(h, 0) disables the fused
+ * path; og_fused_redo_count reports how many batches were re-run. */
+int og_set_fused(og_handle *h, int enable);
+int64_t og_fused_redo_count(const og_handle *h);
+
 /* Per-stage device timing of og_decode_* calls with CUDA events recorded on the
  * launching stream.  og_last_stage_times_ms() waits for the last decode and fills
  * out6 = { input copy + flip + resize, K1 pass 1 (NMS stream), K1 pass 2 (select),

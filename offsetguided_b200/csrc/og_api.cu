@@ -105,6 +105,19 @@ struct og_handle {
     int rows_hint;
     bool pending;
 
+    // fused network-resolution path (no materialised full-resolution maps)
+    bool fused_enabled;
+    int64_t fused_redos;              // batches re-run through the materialising path
+    bool last_fused;                  // the pending decode used the fused path
+    bool tables_valid;                // device flip tables match the cached host copies
+    int32_t kp_cache[OG_MAX_KEYPOINTS];
+    int32_t limb_cache[OG_MAX_LIMBS];
+    uint8_t reserved_cache[OG_MAX_LIMBS];
+    struct {                          // arguments of the pending features decode (for the redo)
+        const float *hmp, *off;
+        int n, hgt, w, hmp_stride, off_stride, resize_mode, flip;
+    } last_args;
+
     // optional per-stage timing (og_enable_stage_timing)
     bool timing;
     bool timing_valid;
@@ -114,7 +127,8 @@ struct og_handle {
 
 namespace {
 
-inline size_t meta_bytes_for(int n) { return ((size_t)(2 * n + 1) * sizeof(int32_t) + 15) / 16 * 16; }
+// meta words: offset[n], count[n], total, overflow flag of the fused path
+inline size_t meta_bytes_for(int n) { return ((size_t)(2 * n + 2) * sizeof(int32_t) + 15) / 16 * 16; }
 inline size_t pose_row_bytes(const og_handle *h) {
     return (size_t)h->cfg.n_keypoints * OG_POSE_COLS * sizeof(float);
 }
@@ -150,7 +164,8 @@ int run_k1(og_handle *h, const float *heat, int n, int hgt, int w, float thre, f
 }
 
 int run_k3(og_handle *h, const float *limbs, int n, float *out_poses, int capacity_rows,
-           int32_t *out_offset, int32_t *out_count, int32_t *out_total, cudaStream_t s) {
+           int32_t *out_offset, int32_t *out_count, int32_t *out_total, cudaStream_t s,
+           bool zero_total = true) {
     const og_config &c = h->cfg;
     GroupLaunch g;
     g.n = n;
@@ -171,14 +186,23 @@ int run_k3(og_handle *h, const float *limbs, int n, float *out_poses, int capaci
         OG_TRY(h->slab.ensure(g.slab_stride * (size_t)n));
         g.slab = h->slab.ptr;
     }
-    OG_CUDA_TRY(cudaMemsetAsync(out_total, 0, sizeof(int32_t), s));
+    if (zero_total) OG_CUDA_TRY(cudaMemsetAsync(out_total, 0, sizeof(int32_t), s));
     OG_TRY(launch_group(g, limbs, out_poses, capacity_rows, out_offset, out_count, out_total, s));
     h->launches += 1;
     return OG_OK;
 }
 
-int decode_maps_impl(og_handle *h, const float *heat, const float *offs, const float *scales, int n,
-                     int hgt, int w, cudaStream_t s) {
+// Shared body of every decode call.  K1 is either the full-resolution stream
+// (heat != nullptr) or the fused network-resolution kernel (lowres_hmp != nullptr).
+struct K1Fused {
+    const float *hmp;       // network-resolution heat maps (n or 2n images)
+    int h, w, scale;
+    bool cubic, flip;
+};
+
+int decode_core(og_handle *h, const float *heat, const K1Fused *fused, const float *offs,
+                const OffsetSource *offs_lowres, const float *scales, int n, int hgt, int w,
+                cudaStream_t s) {
     const og_config &c = h->cfg;
     OG_TRY(check_maps(n, hgt, w, c.n_keypoints));
     const size_t dets = (size_t)n * c.n_keypoints * c.topk;
@@ -189,6 +213,7 @@ int decode_maps_impl(og_handle *h, const float *heat, const float *offs, const f
     const int capacity_rows = n * c.n_limbs * c.topk;
     const size_t mbytes = meta_bytes_for(n);
     OG_TRY(h->out.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
+    OG_TRY(h->out_host.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
     int32_t *meta = reinterpret_cast<int32_t *>(h->out.ptr);
     float *poses = reinterpret_cast<float *>(h->out.ptr + mbytes);
 
@@ -197,29 +222,44 @@ int decode_maps_impl(og_handle *h, const float *heat, const float *offs, const f
     h->last_meta_bytes = mbytes;
     h->last_capacity_rows = capacity_rows;
     h->last_stream = s;
-    if (n == 0) {
-        h->last_rows_copied = 0;
-        return OG_OK;
-    }
+    h->last_fused = fused != nullptr;
     h->timing_valid = false;
     if (!h->prep_marked) OG_TRY(mark(h, 0, s));
     OG_TRY(mark(h, 1, s));
     h->prep_marked = false;
-    OG_TRY(run_k1(h, heat, n, hgt, w, c.thre_hmp, h->det_score.ptr, h->det_index.ptr,
-                  h->det_count.ptr, s, h->timing ? h->ev[2] : nullptr));
+    if (n == 0) {
+        h->last_rows_copied = 0;
+        return OG_OK;
+    }
+    OG_CUDA_TRY(cudaMemsetAsync(meta + 2 * n, 0, 2 * sizeof(int32_t), s));     // total, overflow
+    if (fused) {
+        const int planes = n * c.n_keypoints;
+        OG_TRY(h->cand_count.ensure(planes));
+        OG_TRY(h->cand_keys.ensure((size_t)planes * kCandCap));
+        OG_TRY(launch_fused_candidates(fused->hmp, h->kp_flip.ptr, n, c.n_keypoints, fused->h,
+                                       fused->w, fused->scale, fused->cubic, fused->flip, c.thre_hmp,
+                                       h->cand_count.ptr, h->cand_keys.ptr, s));
+        OG_TRY(mark(h, 2, s));
+        OG_TRY(launch_select_topk(nullptr, planes, hgt, w, c.thre_hmp, c.topk, h->cand_count.ptr,
+                                  h->cand_keys.ptr, h->det_score.ptr, h->det_index.ptr,
+                                  h->det_count.ptr, meta + 2 * n + 1, s));
+        h->launches += 2;
+    } else {
+        OG_TRY(run_k1(h, heat, n, hgt, w, c.thre_hmp, h->det_score.ptr, h->det_index.ptr,
+                      h->det_count.ptr, s, h->timing ? h->ev[2] : nullptr));
+    }
     OG_TRY(mark(h, 3, s));
-    OG_TRY(launch_limb_score(h->det_score.ptr, h->det_index.ptr, offs, scales, n, c.n_keypoints,
-                             c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp, c.min_len,
+    OG_TRY(launch_limb_score(h->det_score.ptr, h->det_index.ptr, offs, offs_lowres, scales, n,
+                             c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp, c.min_len,
                              c.resize_factor, h->limbs.ptr, s));
     h->launches += 1;
     OG_TRY(mark(h, 4, s));
-    OG_TRY(run_k3(h, h->limbs.ptr, n, poses, capacity_rows, meta, meta + n, meta + 2 * n, s));
+    OG_TRY(run_k3(h, h->limbs.ptr, n, poses, capacity_rows, meta, meta + n, meta + 2 * n, s, false));
     OG_TRY(mark(h, 5, s));
 
-    // one asynchronous copy: meta + the first rows_hint pose rows
-    const int rows = std::min(capacity_rows, std::max(h->rows_hint, n * 32));
+    // one asynchronous copy: meta + the pose rows the previous batches suggest
+    const int rows = std::min(capacity_rows, h->rows_hint > 0 ? h->rows_hint : n * 32);
     const size_t bytes = mbytes + (size_t)rows * pose_row_bytes(h);
-    OG_TRY(h->out_host.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
     OG_CUDA_TRY(cudaMemcpyAsync(h->out_host.ptr, h->out.ptr, bytes, cudaMemcpyDeviceToHost, s));
     OG_TRY(mark(h, 6, s));
     h->timing_valid = h->timing;
@@ -227,6 +267,11 @@ int decode_maps_impl(og_handle *h, const float *heat, const float *offs, const f
     h->last_rows_copied = rows;
     h->pending = true;
     return OG_OK;
+}
+
+int decode_maps_impl(og_handle *h, const float *heat, const float *offs, const float *scales, int n,
+                     int hgt, int w, cudaStream_t s) {
+    return decode_core(h, heat, nullptr, offs, nullptr, scales, n, hgt, w, s);
 }
 
 int upload_flip_tables(og_handle *h, const int32_t *kp_flip, const int32_t *limb_flip,
@@ -243,6 +288,10 @@ int upload_flip_tables(og_handle *h, const int32_t *kp_flip, const int32_t *limb
         OG_REQUIRE(limb_reserve[i] >= 0 && limb_reserve[i] < c.n_limbs, "limb_reserve[%d] out of range", i);
         reserved[limb_reserve[i]] = 1;
     }
+    if (h->tables_valid && memcmp(h->kp_cache, kp_flip, sizeof(int32_t) * c.n_keypoints) == 0 &&
+        memcmp(h->limb_cache, limb_flip, sizeof(int32_t) * c.n_limbs) == 0 &&
+        memcmp(h->reserved_cache, reserved, c.n_limbs) == 0)
+        return OG_OK;                      // device copies are current
     OG_TRY(h->kp_flip.ensure(c.n_keypoints));
     OG_TRY(h->limb_flip.ensure(c.n_limbs));
     OG_TRY(h->limb_reserved.ensure(c.n_limbs));
@@ -251,13 +300,18 @@ int upload_flip_tables(og_handle *h, const int32_t *kp_flip, const int32_t *limb
     OG_CUDA_TRY(cudaMemcpyAsync(h->limb_flip.ptr, limb_flip, sizeof(int32_t) * c.n_limbs, cudaMemcpyHostToDevice, s));
     OG_CUDA_TRY(cudaMemcpyAsync(h->limb_reserved.ptr, reserved, c.n_limbs, cudaMemcpyHostToDevice, s));
     OG_CUDA_TRY(cudaStreamSynchronize(s));
+    memcpy(h->kp_cache, kp_flip, sizeof(int32_t) * c.n_keypoints);
+    memcpy(h->limb_cache, limb_flip, sizeof(int32_t) * c.n_limbs);
+    memcpy(h->reserved_cache, reserved, c.n_limbs);
+    h->tables_valid = true;
     return OG_OK;
 }
 
 int decode_features_impl(og_handle *h, const float *hmp, const float *off, int n, int hgt, int w,
                          int hmp_stride, int off_stride, int resize_mode, int flip_test,
                          const int32_t *kp_flip, const int32_t *limb_flip,
-                         const int32_t *limb_reserve, int n_reserve, cudaStream_t s) {
+                         const int32_t *limb_reserve, int n_reserve, cudaStream_t s,
+                         bool allow_fused = true) {
     const og_config &c = h->cfg;
     OG_REQUIRE(hmp_stride >= 1 && off_stride >= 1, "strides must be >= 1");
     OG_REQUIRE(hmp_stride == off_stride,
@@ -270,8 +324,31 @@ int decode_features_impl(og_handle *h, const float *hmp, const float *off, int n
         OG_TRY(mark(h, 0, s));
         h->prep_marked = h->timing;
     }
-    if (flip_test) {
+    h->last_args.hmp = hmp;
+    h->last_args.off = off;
+    h->last_args.n = n;
+    h->last_args.hgt = hgt;
+    h->last_args.w = w;
+    h->last_args.hmp_stride = hmp_stride;
+    h->last_args.off_stride = off_stride;
+    h->last_args.resize_mode = resize_mode;
+    h->last_args.flip = flip_test;
+    if (flip_test && kp_flip != nullptr)
         OG_TRY(upload_flip_tables(h, kp_flip, limb_flip, limb_reserve, n_reserve, s));
+    OG_REQUIRE(!flip_test || h->tables_valid, "flip_test needs the keypoint / limb flip tables");
+
+    // Fused path: candidates straight from the network-resolution maps, offsets sampled at
+    // the candidates; no full-resolution map is written.  thre_hmp <= 0 (every pixel is a
+    // candidate) and other strides use the materialising path below.
+    if (allow_fused && h->fused_enabled && c.thre_hmp > 0.0f && fused_scale_supported(hmp_stride)) {
+        OG_TRY(check_maps(n, hgt * hmp_stride, w * hmp_stride, c.n_keypoints));
+        K1Fused k1 = {hmp, hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
+        OffsetSource src = {off, hgt, w, off_stride, flip_test ? 1 : 0, n, h->limb_flip.ptr,
+                            h->limb_reserved.ptr};
+        return decode_core(h, nullptr, &k1, nullptr, &src, nullptr, n, hgt * hmp_stride,
+                           w * hmp_stride, s);
+    }
+    if (flip_test) {
         OG_TRY(h->fused_hmp.ensure((size_t)n * c.n_keypoints * hw));
         OG_TRY(h->fused_off.ensure((size_t)n * 2 * c.n_limbs * hw));
         OG_TRY(launch_flip_fuse(cur_h, cur_o, h->kp_flip.ptr, h->limb_flip.ptr, h->limb_reserved.ptr,
@@ -373,6 +450,10 @@ int og_create(const og_config *cfg, og_handle **out) {
     h->timing_valid = false;
     h->prep_marked = false;
     for (int i = 0; i < 7; ++i) h->ev[i] = nullptr;
+    h->fused_enabled = true;
+    h->fused_redos = 0;
+    h->last_fused = false;
+    h->tables_valid = false;
 
     // person-table rows held in shared memory: as many as fit beside the work arrays
     GroupLaunch g;
@@ -472,7 +553,7 @@ int og_limb_score_f32(og_handle *h, const float *det_score_dev, const int32_t *d
     OG_TRY(check_device(h));
     OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
     const og_config &c = h->cfg;
-    OG_TRY(launch_limb_score(det_score_dev, det_index_dev, offs_dev, scales_dev, n, c.n_keypoints,
+    OG_TRY(launch_limb_score(det_score_dev, det_index_dev, offs_dev, nullptr, scales_dev, n, c.n_keypoints,
                              c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp, c.min_len, c.resize_factor,
                              out_limbs_dev, static_cast<cudaStream_t>(stream)));
     h->launches += 1;
@@ -580,6 +661,18 @@ int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offse
     OG_CUDA_TRY(cudaEventSynchronize(h->done));
     const int n = h->last_n;
     const int32_t *meta = reinterpret_cast<const int32_t *>(h->out_host.ptr);
+    if (h->last_fused && meta[2 * n + 1] != 0) {
+        // Some plane produced more than kCandCap candidates (noise-like input): the fused
+        // kernel cannot re-scan a map it never materialised, so this batch is decoded again
+        // on the GPU through the materialising path, which selects exactly for any input.
+        h->fused_redos += 1;
+        OG_TRY(decode_features_impl(h, h->last_args.hmp, h->last_args.off, h->last_args.n,
+                                    h->last_args.hgt, h->last_args.w, h->last_args.hmp_stride,
+                                    h->last_args.off_stride, h->last_args.resize_mode,
+                                    h->last_args.flip, nullptr, nullptr, nullptr, 0, h->last_stream,
+                                    false));
+        OG_CUDA_TRY(cudaEventSynchronize(h->done));
+    }
     const int total = meta[2 * n];
     if (total > h->last_capacity_rows) {
         set_error("internal: %d pose rows exceed the worst-case capacity %d", total, h->last_capacity_rows);
@@ -594,7 +687,7 @@ int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offse
         OG_CUDA_TRY(cudaStreamSynchronize(h->last_stream));
         h->last_rows_copied = total;
     }
-    h->rows_hint = std::max(h->rows_hint, total + total / 2);
+    h->rows_hint = total + total / 2 + 16;      // speculative D2H size of the next batch
     *offset_host = meta;
     *count_host = meta + n;
     *total_rows = total;
@@ -622,6 +715,14 @@ int og_copy_intermediates(og_handle *h, int n, float *det_score_dev, int32_t *de
 }
 
 int64_t og_launch_count(const og_handle *h) { return h ? h->launches : 0; }
+
+int og_set_fused(og_handle *h, int enable) {
+    OG_REQUIRE(h, "og_set_fused: null handle");
+    h->fused_enabled = enable != 0;
+    return OG_OK;
+}
+
+int64_t og_fused_redo_count(const og_handle *h) { return h ? h->fused_redos : 0; }
 
 int og_enable_stage_timing(og_handle *h, int enable) {
     OG_REQUIRE(h, "og_enable_stage_timing: null handle");

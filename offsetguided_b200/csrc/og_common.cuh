@@ -76,11 +76,33 @@ int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int
                     float *out_score, int32_t *out_index, int32_t *out_count,
                     bool force_radix, bool apply_nms, cudaStream_t s, int64_t *launches,
                     cudaEvent_t after_pass1 = nullptr);
+// pass 2 alone on candidate lists some other kernel filled; with heat == nullptr a plane
+// with more than kCandCap candidates cannot be re-scanned and raises *overflow_flag.
+int launch_select_topk(const float *heat, int planes, int h, int w, float thre, int k,
+                       const uint32_t *cand_count, const uint64_t *cand_keys, float *out_score,
+                       int32_t *out_index, int32_t *out_count, int32_t *overflow_flag,
+                       cudaStream_t s);
 
+// Offsets still at network resolution (fused path): K2 samples them bilinearly at the
+// candidate pixels instead of gathering from a materialised full-resolution map.
+struct OffsetSource {
+    const float *maps;              // [n or 2n][2L][h][w]
+    int h, w, scale;                // network resolution and the x scale to decode resolution
+    int flip, n;                    // flip: maps = n originals then n mirrored copies
+    const int32_t *limb_flip;       // device tables (flip only)
+    const uint8_t *limb_reserved;
+};
+
+// `offs` = materialised full-resolution offsets, or nullptr with `lowres` set.
 int launch_limb_score(const float *det_score, const int32_t *det_index, const float *offs,
-                      const float *scales, int n, int c, int l, int k, int h, int w,
-                      const SkeletonDev &sk, float thre_hmp, float min_len, float resize_factor,
-                      float *out_limbs, cudaStream_t s);
+                      const OffsetSource *lowres, const float *scales, int n, int c, int l, int k,
+                      int h, int w, const SkeletonDev &sk, float thre_hmp, float min_len,
+                      float resize_factor, float *out_limbs, cudaStream_t s);
+
+bool fused_scale_supported(int scale);
+int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n, int c, int h, int w,
+                            int scale, bool cubic, bool flip, float thre, uint32_t *cand_count,
+                            uint64_t *cand_keys, cudaStream_t s);
 
 struct GroupLaunch {
     int n, c, l, k;

@@ -1,0 +1,170 @@
+// K1f — flip fusion + x S resize + 3x3 NMS + threshold fused into one pass over the
+// NETWORK-RESOLUTION heat maps.
+//
+// The reference materialises the x4 bicubic map (decoder/factory.py:74-75, 27.9 MB per
+// image written, then re-read ~6 times by hmp_NMS / topk).  Here a CTA loads a 16 x 32
+// low-resolution tile (+2 halo cells, fused with the mirrored copy when flip-testing) into
+// shared memory, interpolates rows along x into shared memory once, and every thread
+// produces its full-resolution values with one 4-tap (2-tap) combine along y.  Values are
+// bit-identical to the materialised map (same taps, same accumulation order as ATen's CPU
+// kernel), so the candidates are too.  A value >= thre (rare) triggers the 3x3 test, which
+// recomputes the eight neighbours from the same shared rows; full-resolution maps are never
+// written.  HBM traffic: C*h*w*4 bytes per image (1.74 MB instead of 55.7 MB).
+#include "og_common.cuh"
+#include "og_interp.cuh"
+
+namespace og {
+
+namespace {
+
+constexpr int kTileW = 32;       // low-resolution cells per tile
+constexpr int kTileH = 16;
+constexpr int kFusedThreads = 256;
+
+template <int S, bool kCubic, bool kFlip>
+__global__ void __launch_bounds__(kFusedThreads)
+fused_nms_candidates_kernel(const float *__restrict__ hmp, const int32_t *__restrict__ kp_flip,
+                            int N, int C, int h, int w, float thre,
+                            uint32_t *__restrict__ cand_count, uint64_t *__restrict__ cand_keys) {
+    constexpr int HALO = kCubic ? 2 : 1;
+    constexpr int TAPS = kCubic ? 4 : 2;
+    constexpr int LW = kTileW + 2 * HALO, LH = kTileH + 2 * HALO;
+    constexpr int XW = S * kTileW + 2, YH = S * kTileH + 2;       // incl. the 1-pixel NMS ring
+    __shared__ float s_lo[LH][LW + 1];
+    __shared__ float s_hb[LH][XW];
+    __shared__ float s_xw[TAPS][XW];
+    __shared__ float s_yw[TAPS][YH];
+    __shared__ int s_xb[XW];
+    __shared__ int s_yb[YH];
+
+    const int tid = threadIdx.x;
+    const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
+    int bid = blockIdx.x;
+    const int tx = bid % tiles_x;
+    bid /= tiles_x;
+    const int ty = bid % tiles_y;
+    const int plane = bid / tiles_y;
+    const int n = plane / C, c = plane - n * C;
+    const int cx0 = tx * kTileW, cy0 = ty * kTileH;
+    const int W = w * S, H = h * S;
+
+    // 1. low-resolution tile, border cells replicated (= ATen's tap clamping), fused with
+    //    the mirrored copy: (orig + flip_W(flipped)[kp_flip]) / 2   (factory.py:101-106)
+    const float *a = hmp + ((size_t)n * C + c) * h * w;
+    const float *b = nullptr;
+    if (kFlip) b = hmp + ((size_t)(N + n) * C + kp_flip[c]) * h * w;
+    for (int i = tid; i < LH * LW; i += kFusedThreads) {
+        const int ly = i / LW, lx = i - ly * LW;
+        const int gy = min(max(cy0 - HALO + ly, 0), h - 1);
+        const int gx = min(max(cx0 - HALO + lx, 0), w - 1);
+        float v = __ldg(a + gy * w + gx);
+        if (kFlip) v = __fmul_rn(__fadd_rn(v, __ldg(b + gy * w + (w - 1 - gx))), 0.5f);
+        s_lo[ly][lx] = v;
+    }
+    // 2. tap tables of the full-resolution columns / rows this tile produces
+    const float inv = 1.0f / (float)S;
+    for (int j = tid; j < XW + YH; j += kFusedThreads) {
+        float wt[4];
+        if (j < XW) {
+            const int first = axis_first_tap(S * cx0 - 1 + j, inv, kCubic, wt);
+            s_xb[j] = first - (cx0 - HALO);
+#pragma unroll
+            for (int t = 0; t < TAPS; ++t) s_xw[t][j] = wt[t];
+        } else {
+            const int jj = j - XW;
+            const int first = axis_first_tap(S * cy0 - 1 + jj, inv, kCubic, wt);
+            s_yb[jj] = first - (cy0 - HALO);
+#pragma unroll
+            for (int t = 0; t < TAPS; ++t) s_yw[t][jj] = wt[t];
+        }
+    }
+    __syncthreads();
+    // 3. interpolate every tile row along x
+    for (int i = tid; i < LH * XW; i += kFusedThreads) {
+        const int ly = i / XW, j = i - ly * XW;
+        const float *row = &s_lo[ly][s_xb[j]];
+        s_hb[ly][j] = kCubic ? combine4(row[0], row[1], row[2], row[3], s_xw[0][j], s_xw[1][j],
+                                        s_xw[TAPS - 2][j], s_xw[TAPS - 1][j])
+                             : combine2(row[0], row[1], s_xw[0][j], s_xw[1][j]);
+    }
+    __syncthreads();
+
+    auto value_at = [&](int jy, int jx) {
+        const int yb = s_yb[jy];
+        return kCubic ? combine4(s_hb[yb][jx], s_hb[yb + 1][jx], s_hb[yb + TAPS - 2][jx],
+                                 s_hb[yb + TAPS - 1][jx], s_yw[0][jy], s_yw[1][jy],
+                                 s_yw[TAPS - 2][jy], s_yw[TAPS - 1][jy])
+                      : combine2(s_hb[yb][jx], s_hb[yb + 1][jx], s_yw[0][jy], s_yw[1][jy]);
+    };
+    // 4. full-resolution values, threshold first; the 3x3 test only for the few survivors
+    for (int i = tid; i < kTileH * S * kTileW; i += kFusedThreads) {
+        const int cy = i / (S * kTileW);
+        const int jx = i - cy * (S * kTileW) + 1;
+        const int X = S * cx0 + jx - 1;
+        if (X >= W) continue;
+#pragma unroll
+        for (int p = 0; p < S; ++p) {
+            const int jy = cy * S + p + 1;
+            const int Y = S * cy0 + jy - 1;
+            if (Y >= H) break;
+            const float v = value_at(jy, jx);
+            if (v >= thre) {
+                float m = 0.0f;          // zero padding outside the image (heatmap.py:31)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        if (dy == 0 && dx == 0) continue;
+                        const int yn = Y + dy, xn = X + dx;
+                        if (yn < 0 || yn >= H || xn < 0 || xn >= W) continue;
+                        m = fmaxf(m, value_at(jy + dy, jx + dx));
+                    }
+                if (v >= m) {
+                    const uint32_t pos = atomicAdd(&cand_count[plane], 1u);
+                    if (pos < (uint32_t)kCandCap)
+                        cand_keys[(size_t)plane * kCandCap + pos] = make_key(v + 0.0f, (uint32_t)(Y * W + X));
+                }
+            }
+        }
+    }
+}
+
+template <int S>
+int launch_s(const float *hmp, const int32_t *kp_flip, int n, int c, int h, int w, bool cubic,
+             bool flip, float thre, uint32_t *cand_count, uint64_t *cand_keys, cudaStream_t s) {
+    const int tiles = ((w + kTileW - 1) / kTileW) * ((h + kTileH - 1) / kTileH);
+    const long long blocks = (long long)n * c * tiles;
+    if (blocks > 0x7fffffffLL) {
+        set_error("fused K1: grid of %lld blocks is too large", blocks);
+        return OG_ERR_INVALID_ARGUMENT;
+    }
+    const dim3 grid((unsigned)blocks);
+    if (cubic) {
+        if (flip) fused_nms_candidates_kernel<S, true, true><<<grid, kFusedThreads, 0, s>>>(hmp, kp_flip, n, c, h, w, thre, cand_count, cand_keys);
+        else fused_nms_candidates_kernel<S, true, false><<<grid, kFusedThreads, 0, s>>>(hmp, kp_flip, n, c, h, w, thre, cand_count, cand_keys);
+    } else {
+        if (flip) fused_nms_candidates_kernel<S, false, true><<<grid, kFusedThreads, 0, s>>>(hmp, kp_flip, n, c, h, w, thre, cand_count, cand_keys);
+        else fused_nms_candidates_kernel<S, false, false><<<grid, kFusedThreads, 0, s>>>(hmp, kp_flip, n, c, h, w, thre, cand_count, cand_keys);
+    }
+    OG_CUDA_TRY(cudaGetLastError());
+    return OG_OK;
+}
+
+}  // namespace
+
+bool fused_scale_supported(int scale) { return scale == 2 || scale == 4 || scale == 8; }
+
+int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n, int c, int h, int w,
+                            int scale, bool cubic, bool flip, float thre, uint32_t *cand_count,
+                            uint64_t *cand_keys, cudaStream_t s) {
+    if (n == 0) return OG_OK;
+    OG_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t) * (size_t)n * c, s));
+    switch (scale) {
+        case 2: return launch_s<2>(hmp, kp_flip_dev, n, c, h, w, cubic, flip, thre, cand_count, cand_keys, s);
+        case 4: return launch_s<4>(hmp, kp_flip_dev, n, c, h, w, cubic, flip, thre, cand_count, cand_keys, s);
+        case 8: return launch_s<8>(hmp, kp_flip_dev, n, c, h, w, cubic, flip, thre, cand_count, cand_keys, s);
+        default:
+            set_error("fused K1: scale %d is not instantiated", scale);
+            return OG_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace og

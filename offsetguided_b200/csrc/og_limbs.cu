@@ -9,6 +9,7 @@
 // sqrt(fma(dy, dy, dx*dx)) for Tensor.norm over an (x, y) pair (probed against
 // ATen's CPU kernel).  ~40 eager launches of the reference collapse into this one.
 #include "og_common.cuh"
+#include "og_interp.cuh"
 
 namespace og {
 
@@ -23,9 +24,42 @@ __device__ __forceinline__ float norm2(float dx, float dy) {
     return __fsqrt_rn(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
+// Guiding offset (component comp of limb l) at full-resolution pixel (X, Y) when the offset
+// maps are still at network resolution: bilinear x S sampling on the fly, optionally fused
+// with the flip-test average (factory.py:128-139) — bit-identical to gathering from the
+// materialised F.interpolate(offs, scale_factor=S, mode='bilinear') map.
+__device__ __forceinline__ float sample_offset(const OffsetSource &src, int img, int L, int l,
+                                               int comp, int X, int Y) {
+    const int h = src.h, w = src.w;
+    const size_t hw = (size_t)h * w;
+    const float *a = src.maps + ((size_t)img * 2 * L + 2 * l + comp) * hw;
+    const bool mirrored = src.flip && !src.limb_reserved[l];
+    const float *b = mirrored
+                         ? src.maps + ((size_t)(src.n + img) * 2 * L + 2 * src.limb_flip[l] + comp) * hw
+                         : nullptr;
+    auto at = [&](int yy, int xx) {
+        float v = __ldg(a + yy * w + xx);
+        if (mirrored) {
+            float m = __ldg(b + yy * w + (w - 1 - xx));
+            if (comp == 0) m = -m;
+            v = __fmul_rn(__fadd_rn(v, m), 0.5f);
+        }
+        return v;
+    };
+    if (src.scale == 1) return at(Y, X);
+    const float inv = 1.0f / (float)src.scale;
+    int ix[4], iy[4];
+    float wx[4], wy[4];
+    axis_taps(X, w, inv, false, ix, wx);
+    axis_taps(Y, h, inv, false, iy, wy);
+    const float r0 = combine2(at(iy[0], ix[0]), at(iy[0], ix[1]), wx[0], wx[1]);
+    const float r1 = combine2(at(iy[1], ix[0]), at(iy[1], ix[1]), wx[0], wx[1]);
+    return combine2(r0, r1, wy[0], wy[1]);
+}
+
 __global__ void __launch_bounds__(128)
 limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict__ det_index,
-                  const float *__restrict__ offs, const float *__restrict__ scales,
+                  const float *__restrict__ offs, OffsetSource src, const float *__restrict__ scales,
                   int C, int L, int K, int H, int W, SkeletonDev sk, float thre_hmp,
                   float min_len, float resize_factor, float *__restrict__ out_limbs) {
     __shared__ ToCand s_to[OG_MAX_TOPK];
@@ -70,9 +104,15 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
         candidate(jf, k, x1, y1, s1, idx1);
         float ox = 0.0f, oy = 0.0f, scale1 = 4.0f;
         if (idx1 >= 0) {
-            const float *o = offs + ((size_t)n * 2 * L + 2 * l) * HW + idx1;   // collect.py:143-147
-            ox = __ldg(o);
-            oy = __ldg(o + HW);
+            if (offs != nullptr) {
+                const float *o = offs + ((size_t)n * 2 * L + 2 * l) * HW + idx1;   // collect.py:143-147
+                ox = __ldg(o);
+                oy = __ldg(o + HW);
+            } else {
+                const int py = idx1 / W, px = idx1 - py * W;
+                ox = sample_offset(src, n, L, l, 0, px, py);
+                oy = sample_offset(src, n, L, l, 1, px, py);
+            }
             if (scales != nullptr) scale1 = __ldg(scales + ((size_t)n * C + jf) * HW + idx1);
         }
         const float gx = __fadd_rn(x1, __fmul_rn(ox, resize_factor));         // collect.py:152
@@ -113,14 +153,16 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
 }  // namespace
 
 int launch_limb_score(const float *det_score, const int32_t *det_index, const float *offs,
-                      const float *scales, int n, int c, int l, int k, int h, int w,
-                      const SkeletonDev &sk, float thre_hmp, float min_len, float resize_factor,
-                      float *out_limbs, cudaStream_t s) {
+                      const OffsetSource *lowres, const float *scales, int n, int c, int l, int k,
+                      int h, int w, const SkeletonDev &sk, float thre_hmp, float min_len,
+                      float resize_factor, float *out_limbs, cudaStream_t s) {
     if (n == 0) return OG_OK;
     const int threads = k <= 32 ? 32 : (k <= 64 ? 64 : 128);
     dim3 grid(l, n);
-    limb_score_kernel<<<grid, threads, 0, s>>>(det_score, det_index, offs, scales, c, l, k, h, w, sk,
-                                              thre_hmp, min_len, resize_factor, out_limbs);
+    OffsetSource src = {};
+    if (lowres) src = *lowres;
+    limb_score_kernel<<<grid, threads, 0, s>>>(det_score, det_index, offs, src, scales, c, l, k, h, w,
+                                              sk, thre_hmp, min_len, resize_factor, out_limbs);
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;
 }

@@ -26,7 +26,7 @@ namespace {
 
 // tuning knobs (profiles/k1_tuning.md records the sweep on B200)
 #ifndef OG_K1_ROWS
-#define OG_K1_ROWS 32
+#define OG_K1_ROWS 8
 #endif
 #ifndef OG_K1_UNROLL
 #define OG_K1_UNROLL 8
@@ -224,7 +224,7 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
                    const uint32_t *__restrict__ cand_count,
                    const uint64_t *__restrict__ cand_keys, float *__restrict__ out_score,
                    int32_t *__restrict__ out_index, int32_t *__restrict__ out_count,
-                   int force_radix, int apply_nms) {
+                   int force_radix, int apply_nms, int32_t *__restrict__ overflow_flag) {
     __shared__ uint64_t s_keys[kCandCap];
     __shared__ uint32_t s_hist[kRadixBins];
     __shared__ uint32_t s_part[kSelectThreads];
@@ -245,6 +245,14 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
         return;
     }
 
+    if (heat == nullptr) {      // fused path: no materialised plane to re-scan; the host re-runs
+        if (tid == 0) {         // the batch through the materialising path (og_fetch_poses)
+            atomicExch(overflow_flag, 1);
+            if (out_count) out_count[plane] = 0;
+        }
+        write_ranked(s_keys, 0, K, o_score, o_index);
+        return;
+    }
     // ---- exact radix selection over the plane (rare path) ----
     const float *__restrict__ p = heat + (size_t)plane * H * W;
     const int HW = H * W;
@@ -411,9 +419,21 @@ int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int
     if (after_pass1) OG_CUDA_TRY(cudaEventRecord(after_pass1, s));
     select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
                                                         out_score, out_index, out_count,
-                                                        force_radix ? 1 : 0, apply_nms ? 1 : 0);
+                                                        force_radix ? 1 : 0, apply_nms ? 1 : 0, nullptr);
     OG_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;
+    return OG_OK;
+}
+
+int launch_select_topk(const float *heat, int planes, int h, int w, float thre, int k,
+                       const uint32_t *cand_count, const uint64_t *cand_keys, float *out_score,
+                       int32_t *out_index, int32_t *out_count, int32_t *overflow_flag,
+                       cudaStream_t s) {
+    if (planes == 0) return OG_OK;
+    select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
+                                                        out_score, out_index, out_count, 0, 1,
+                                                        overflow_flag);
+    OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;
 }
 

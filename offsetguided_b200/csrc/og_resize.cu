@@ -9,47 +9,11 @@
 // along x and then along y (probed against torch 2.11, tests/golden/resize_small.npz).
 // Interpolation weights are exact for power-of-two strides (the reference uses 4).
 #include "og_common.cuh"
+#include "og_interp.cuh"
 
 namespace og {
 
 namespace {
-
-__device__ __forceinline__ void cubic_weights(float t, float w[4]) {
-    const float A = -0.75f;
-    const float x0 = t + 1.0f, x3 = 2.0f - t, x2 = 1.0f - t;
-    w[0] = ((A * x0 - 5.0f * A) * x0 + 8.0f * A) * x0 - 4.0f * A;
-    w[1] = ((A + 2.0f) * t - (A + 3.0f)) * t * t + 1.0f;
-    w[2] = ((A + 2.0f) * x2 - (A + 3.0f)) * x2 * x2 + 1.0f;
-    w[3] = ((A * x3 - 5.0f * A) * x3 + 8.0f * A) * x3 - 4.0f * A;
-}
-
-// taps of one axis; returns the tap count (2 or 4)
-__device__ __forceinline__ int axis_taps(int dst, int n_in, float inv_scale, bool cubic,
-                                         int idx[4], float w[4]) {
-    float real = inv_scale * ((float)dst + 0.5f) - 0.5f;
-    if (!cubic) real = fmaxf(real, 0.0f);
-    const float fl = floorf(real);
-    const int base = (int)fl;
-    const float t = fminf(fmaxf(real - fl, 0.0f), 1.0f);
-    if (cubic) {
-        cubic_weights(t, w);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) idx[j] = min(max(base + j - 1, 0), n_in - 1);
-        return 4;
-    }
-    idx[0] = min(base, n_in - 1);
-    idx[1] = min(base + 1, n_in - 1);
-    w[0] = 1.0f - t;
-    w[1] = t;
-    return 2;
-}
-
-__device__ __forceinline__ float combine(const float *v, const float *w, int taps) {
-    float acc = __fmul_rn(v[1], w[1]);
-    acc = __fmaf_rn(v[0], w[0], acc);
-    for (int j = 2; j < taps; ++j) acc = __fmaf_rn(v[j], w[j], acc);
-    return acc;
-}
 
 __global__ void resize_kernel(const float *__restrict__ in, float *__restrict__ out, int planes,
                               int h, int w, int scale, int cubic) {

@@ -207,6 +207,14 @@ class DecoderEngine(object):
         with torch.cuda.device(self.device):
             return self._fetch(n)
 
+    def set_fused(self, on=True):
+        """Enable / disable the fused network-resolution path of decode_features."""
+        _lib.check(self.lib.og_set_fused(self._h, 1 if on else 0))
+
+    @property
+    def fused_redo_count(self):
+        return int(self.lib.og_fused_redo_count(self._h))
+
     def enable_stage_timing(self, on=True):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.og_enable_stage_timing(self._h, 1 if on else 0))

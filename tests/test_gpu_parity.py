@@ -344,3 +344,72 @@ def test_decode_full_size_properties(cuda_device):
     for i in range(2):
         ref = ro.group_skeletons(ref_limbs[i], skel, 17, 0.04, 2, 40, True)
         gio.compare_poses(poses[i], ref, rtol=RTOL)
+
+
+# --------------------------------------------------------------------------- fused path
+@pytest.mark.parametrize('shape,stride,mode,flip', [
+    ((2, 40, 56), 4, 'bicubic', False), ((2, 45, 70), 4, 'bicubic', True),
+    ((1, 33, 31), 2, 'bicubic', False), ((2, 48, 64), 4, 'bilinear', True),
+    ((1, 20, 24), 8, 'bicubic', True), ((1, 17, 35), 4, 'bicubic', False)])
+def test_fused_path_equals_materialising_path(cuda_device, shape, stride, mode, flip):
+    """flip fusion + resize + NMS fused over network-resolution maps must give the very same
+    dets, limbs and poses as flip -> resize -> K1 on materialised maps (bit for bit)."""
+    n, h, w = shape
+    skel = cfg.COCO_PERSON_SKELETON
+    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel)
+    W, H = w * 4, h * 4                      # scenes are rendered for a stride-4 network
+    hs, os_ = [], []
+    for half in range(2 if flip else 1):
+        for i in range(n):
+            rng = np.random.RandomState(100 * h + i)
+            p = scenes.make_persons(rng, 3, W, H, scale_range=(W / 40.0, W / 24.0))
+            if half:
+                p = scenes.mirror_persons(p, W, kp)
+            hm = scenes.render_heatmaps(p, W, H) + rng.uniform(0, 0.02, size=(17, h, w)).astype(np.float32)
+            om = scenes.render_offsets(p, W, H, skel)
+            om[~np.isfinite(om)] = 0
+            hs.append(hm)
+            os_.append(om)
+    hmp = torch.from_numpy(np.stack(hs).astype(np.float32)).cuda()
+    omp = torch.from_numpy(np.stack(os_).astype(np.float32)).cuda()
+    tables = (kp, fl, rs) if flip else None
+    eng = DecoderEngine(17, skel, topk=16, thre_hmp=0.05, min_len=0.5, dist_max=40, use_scale=True,
+                        person_thre=0.05)
+    fused = eng.decode_features(hmp, omp, stride, stride, mode, tables)
+    f_int = [t.cpu().numpy() for t in eng.last_intermediates(n)]
+    assert eng.fused_redo_count == 0
+    eng.set_fused(False)
+    staged = eng.decode_features(hmp, omp, stride, stride, mode, tables)
+    s_int = [t.cpu().numpy() for t in eng.last_intermediates(n)]
+    assert sum(len(p) for p in staged) >= 1
+    for a, b in zip(f_int, s_int):
+        assert np.array_equal(a, b)
+    for a, b in zip(fused, staged):
+        assert np.array_equal(a, b)
+    # and against the oracle
+    ref = ro.generate_poses(np.stack(hs), np.stack(os_), skel, 17, topk=16, thre_hmp=0.05, min_len=0.5,
+                            person_thre=0.05, dist_max=40, use_scale=True, hmp_stride=stride,
+                            off_stride=stride, resize_mode=mode, flip_test=flip, kp_flips=kp,
+                            limb_flips=fl, limb_reserve=rs)
+    for p, r in zip(fused, ref):
+        gio.compare_poses(p, r, rtol=RTOL)
+
+
+def test_fused_path_overflow_reruns_exactly(cuda_device):
+    """Noise heat maps overflow the per-plane candidate lists; the batch is then re-run on the
+    GPU through the materialising path and must equal it."""
+    rng = np.random.RandomState(3)
+    hmp = torch.from_numpy(rng.uniform(0, 1, size=(1, 17, 64, 80)).astype(np.float32)).cuda()
+    omp = torch.from_numpy(rng.uniform(-8, 8, size=(1, 38, 64, 80)).astype(np.float32)).cuda()
+    eng = DecoderEngine(17, cfg.COCO_PERSON_SKELETON, topk=32, thre_hmp=0.04, dist_max=40,
+                        use_scale=True, person_thre=0.04)
+    fused = eng.decode_features(hmp, omp, 4, 4, 'bicubic', None)
+    assert eng.fused_redo_count == 1
+    f_int = [t.cpu().numpy() for t in eng.last_intermediates(1)]
+    eng.set_fused(False)
+    staged = eng.decode_features(hmp, omp, 4, 4, 'bicubic', None)
+    s_int = [t.cpu().numpy() for t in eng.last_intermediates(1)]
+    for a, b in zip(f_int, s_int):
+        assert np.array_equal(a, b)
+    assert np.array_equal(fused[0], staged[0]) and len(fused[0]) > 10
