@@ -96,31 +96,65 @@ fused_nms_candidates_kernel(const float *__restrict__ hmp, const int32_t *__rest
                                  s_yw[TAPS - 2][jy], s_yw[TAPS - 1][jy])
                       : combine2(s_hb[yb][jx], s_hb[yb + 1][jx], s_yw[0][jy], s_yw[1][jy]);
     };
-    // 4. full-resolution values, threshold first; the 3x3 test only for the few survivors
-    for (int i = tid; i < kTileH * S * kTileW; i += kFusedThreads) {
-        const int cy = i / (S * kTileW);
-        const int jx = i - cy * (S * kTileW) + 1;
-        const int X = S * cx0 + jx - 1;
-        if (X >= W) continue;
+    // 4. full-resolution values, threshold first; the 3x3 test only for the few survivors.
+    //    A warp owns whole cell rows: the S output rows of a cell row share TAPS + 1 rows of
+    //    s_hb and their tap tables stay in registers while the lanes sweep the columns.
+    constexpr int kWarps = kFusedThreads / 32;
+    constexpr int kRowsPerWarp = kTileH / kWarps;
+    static_assert(kTileH % kWarps == 0, "tile rows must split evenly over the warps");
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll 1
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int cy = warp * kRowsPerWarp + rr;
+        if (S * (cy0 + cy) >= H) break;
+        int yoff[S];
+        float wv[S][TAPS];
+        const int yb0 = s_yb[cy * S + 1];
 #pragma unroll
         for (int p = 0; p < S; ++p) {
             const int jy = cy * S + p + 1;
-            const int Y = S * cy0 + jy - 1;
-            if (Y >= H) break;
-            const float v = value_at(jy, jx);
-            if (v >= thre) {
-                float m = 0.0f;          // zero padding outside the image (heatmap.py:31)
-                for (int dy = -1; dy <= 1; ++dy)
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        if (dy == 0 && dx == 0) continue;
-                        const int yn = Y + dy, xn = X + dx;
-                        if (yn < 0 || yn >= H || xn < 0 || xn >= W) continue;
-                        m = fmaxf(m, value_at(jy + dy, jx + dx));
+            yoff[p] = s_yb[jy] - yb0;            // 0 or 1: floor(src) changes at most once per cell
+#pragma unroll
+            for (int t = 0; t < TAPS; ++t) wv[p][t] = s_yw[t][jy];
+        }
+#pragma unroll 1
+        for (int jx = lane + 1; jx <= S * kTileW; jx += 32) {
+            const int X = S * cx0 + jx - 1;
+            if (X >= W) break;
+            float r[TAPS + 1];
+#pragma unroll
+            for (int t = 0; t <= TAPS; ++t) r[t] = s_hb[min(yb0 + t, LH - 1)][jx];
+#pragma unroll
+            for (int p = 0; p < S; ++p) {
+                const int Y = S * (cy0 + cy) + p;
+                if (Y >= H) break;
+                const bool up = yoff[p] != 0;
+                float v;
+                if (kCubic)
+                    v = combine4(up ? r[1] : r[0], up ? r[2] : r[1], up ? r[TAPS - 1] : r[TAPS - 2],
+                                 up ? r[TAPS] : r[TAPS - 1], wv[p][0], wv[p][1], wv[p][TAPS - 2],
+                                 wv[p][TAPS - 1]);
+                else
+                    v = combine2(up ? r[1] : r[0], up ? r[2] : r[1], wv[p][0], wv[p][1]);
+                if (v >= thre) {
+                    const int jy = cy * S + p + 1;
+                    bool peak = true;      // zero padding outside the image: v >= thre > 0 wins
+                    for (int dy = -1; dy <= 1 && peak; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            if (dy == 0 && dx == 0) continue;
+                            const int yn = Y + dy, xn = X + dx;
+                            if (yn < 0 || yn >= H || xn < 0 || xn >= W) continue;
+                            if (value_at(jy + dy, jx + dx) > v) {
+                                peak = false;
+                                break;
+                            }
+                        }
+                    if (peak) {
+                        const uint32_t pos = atomicAdd(&cand_count[plane], 1u);
+                        if (pos < (uint32_t)kCandCap)
+                            cand_keys[(size_t)plane * kCandCap + pos] =
+                                make_key(v + 0.0f, (uint32_t)(Y * W + X));
                     }
-                if (v >= m) {
-                    const uint32_t pos = atomicAdd(&cand_count[plane], 1u);
-                    if (pos < (uint32_t)kCandCap)
-                        cand_keys[(size_t)plane * kCandCap + pos] = make_key(v + 0.0f, (uint32_t)(Y * W + X));
                 }
             }
         }

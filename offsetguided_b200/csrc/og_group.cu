@@ -59,7 +59,7 @@ __host__ __device__ inline Layout make_layout(int C, int L, int K, int smem_rows
     lo.xyvs = at;  at += (size_t)smem_rows * C * 16;
     lo.score = at; at += (size_t)smem_rows * C * 4;
     lo.ids = at;   at += (size_t)smem_rows * C * 4;
-    lo.conn = at;  at += align_up((size_t)K * OG_LIMB_COLS * 4, 16);
+    lo.conn = at;  at += 2 * align_up((size_t)K * OG_LIMB_COLS * 4, 16);     // double buffer
     lo.k_int = at; at += (size_t)10 * K * 4;
     at = align_up(at, 8);
     lo.p_f64 = at; at += pmax * 8;
@@ -133,7 +133,10 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, float *__restrict__ o
     const int tid = threadIdx.x, T = blockDim.x;
     const int img = blockIdx.x;
 
-    float *s_conn = reinterpret_cast<float *>(smem + lo.conn);
+    float *s_conn_buf[2];
+    s_conn_buf[0] = reinterpret_cast<float *>(smem + lo.conn);
+    s_conn_buf[1] = s_conn_buf[0] + align_up((size_t)K * OG_LIMB_COLS * 4, 16) / 4;
+    const int lane = tid & 31, wid = tid >> 5, nwarps = T >> 5;
     int *kbase = reinterpret_cast<int *>(smem + lo.k_int);
     int *s_valid = kbase + 0 * K;
     int *s_sorted = kbase + 1 * K;
@@ -183,10 +186,16 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, float *__restrict__ o
         bool overflow = false;
         __syncthreads();
 
+        // rows of limb type 0; the rows of type li + 1 are fetched while type li is processed
+        for (int i = tid; i < K * OG_LIMB_COLS; i += T) s_conn_buf[0][i] = limbs_img[i];
         for (int li = 0; li < L && !overflow; ++li) {
             const int jf = a.sk.from[li], jt = a.sk.to[li];
-            // ---- stage the K rows of this limb type
-            for (int i = tid; i < K * OG_LIMB_COLS; i += T) s_conn[i] = limbs_img[(size_t)li * K * OG_LIMB_COLS + i];
+            const float *s_conn = s_conn_buf[li & 1];
+            if (li + 1 < L) {
+                float *nxt = s_conn_buf[(li + 1) & 1];
+                const float *src = limbs_img + (size_t)(li + 1) * K * OG_LIMB_COLS;
+                for (int i = tid; i < K * OG_LIMB_COLS; i += T) nxt[i] = __ldg(src + i);
+            }
             if (tid < kNumFlags) s_flag[tid] = 0;
             __syncthreads();
             // ---- gate (group.py:64-76)
@@ -199,28 +208,39 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, float *__restrict__ o
                 s_valid[k] = v ? 1 : 0;
             }
             __syncthreads();
-            // ---- sort by limb score desc, ties by row asc (group.py:232, canonical stable)
-            for (int k = tid; k < K; k += T) {
-                if (!s_valid[k]) continue;
+            // ---- sort by limb score desc, ties by row asc (group.py:232, canonical stable):
+            //      rank of row k = number of valid rows that precede it; one warp per row,
+            //      lanes over the other rows, counted with ballots
+            for (int k = wid; k < K; k += nwarps) {
+                if (!s_valid[k]) continue;                         // warp-uniform
                 const float sc = s_conn[k * OG_LIMB_COLS + 10];
                 int rank = 0;
-                for (int j = 0; j < K; ++j) {
-                    if (!s_valid[j]) continue;
-                    const float sj = s_conn[j * OG_LIMB_COLS + 10];
-                    rank += (sj > sc || (sj == sc && j < k)) ? 1 : 0;
+                for (int j0 = 0; j0 < K; j0 += 32) {
+                    const int j = j0 + lane;
+                    bool before = false;
+                    if (j < K && s_valid[j]) {
+                        const float sj = s_conn[j * OG_LIMB_COLS + 10];
+                        before = sj > sc || (sj == sc && j < k);
+                    }
+                    rank += __popc(__ballot_sync(0xffffffffu, before));
                 }
-                s_sorted[rank] = k;
-                atomicAdd(const_cast<int *>(&s_flag[kNValid]), 1);
+                if (lane == 0) {
+                    s_sorted[rank] = k;
+                    atomicAdd(const_cast<int *>(&s_flag[kNValid]), 1);
+                }
             }
             __syncthreads();
             const int nvalid = s_flag[kNValid];
             // ---- keep the best row per to-joint id (group.py:233-239)
-            for (int r = tid; r < nvalid; r += T) {
+            for (int r = wid; r < nvalid; r += nwarps) {
                 const int t = (int)s_conn[s_sorted[r] * OG_LIMB_COLS + 7];
                 bool dup = false;
-                for (int r2 = 0; r2 < r && !dup; ++r2)
-                    dup = ((int)s_conn[s_sorted[r2] * OG_LIMB_COLS + 7] == t);
-                s_keep[r] = dup ? 0 : 1;
+                for (int r0 = 0; r0 < r && !dup; r0 += 32) {
+                    const int r2 = r0 + lane;
+                    const bool same = r2 < r && (int)s_conn[s_sorted[r2] * OG_LIMB_COLS + 7] == t;
+                    dup = __any_sync(0xffffffffu, same);
+                }
+                if (lane == 0) s_keep[r] = dup ? 0 : 1;
             }
             __syncthreads();
             const int kk = block_scan(nvalid, [&](int r) { return s_keep[r] != 0; }, s_pos, s_warp);
@@ -292,16 +312,25 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, float *__restrict__ o
                     s_del[p] = 0;
                 }
                 __syncthreads();
-                for (int p = tid; p < mm; p += T) {
+                for (int p = wid; p < mm; p += nwarps) {      // one warp per person, lanes over joints
                     const int rowa = s_order[p];
+                    int ida[(OG_MAX_KEYPOINTS + 31) / 32];
+#pragma unroll
+                    for (int cc = 0; cc < (OG_MAX_KEYPOINTS + 31) / 32; ++cc) {
+                        const int c = cc * 32 + lane;
+                        ida[cc] = c < C ? ids[rowa * C + c] : -1;
+                    }
                     for (int q = p + 1; q < mm; ++q) {
                         const int rowb = s_order[q];
                         int cnt = 0;
-                        for (int c = 0; c < C; ++c) {
-                            const int ia = ids[rowa * C + c];
-                            cnt += (ia != -1 && ia == ids[rowb * C + c]) ? 1 : 0;
+#pragma unroll
+                        for (int cc = 0; cc < (OG_MAX_KEYPOINTS + 31) / 32; ++cc) {
+                            const int c = cc * 32 + lane;
+                            if (cc * 32 >= C) break;
+                            const bool same = c < C && ida[cc] != -1 && ida[cc] == ids[rowb * C + c];
+                            cnt += __popc(__ballot_sync(0xffffffffu, same));
                         }
-                        if (cnt == 2) {
+                        if (cnt == 2 && lane == 0) {
                             s_blast[p] = (int16_t)q;     // ascending q: the last partner wins
                             s_del[q] = 1;
                             s_flag[kAnyMerge] = 1;

@@ -400,8 +400,8 @@ def test_fused_path_overflow_reruns_exactly(cuda_device):
     """Noise heat maps overflow the per-plane candidate lists; the batch is then re-run on the
     GPU through the materialising path and must equal it."""
     rng = np.random.RandomState(3)
-    hmp = torch.from_numpy(rng.uniform(0, 1, size=(1, 17, 64, 80)).astype(np.float32)).cuda()
-    omp = torch.from_numpy(rng.uniform(-8, 8, size=(1, 38, 64, 80)).astype(np.float32)).cuda()
+    hmp = torch.from_numpy(rng.uniform(0, 1, size=(1, 17, 160, 200)).astype(np.float32)).cuda()
+    omp = torch.from_numpy(rng.uniform(-8, 8, size=(1, 38, 160, 200)).astype(np.float32)).cuda()
     eng = DecoderEngine(17, cfg.COCO_PERSON_SKELETON, topk=32, thre_hmp=0.04, dist_max=40,
                         use_scale=True, person_thre=0.04)
     fused = eng.decode_features(hmp, omp, 4, 4, 'bicubic', None)
