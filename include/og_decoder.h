@@ -145,7 +145,7 @@ int og_resize_f32(const float *in_dev, float *out_dev, int planes, int hgt, int 
 
 /* generate_limbs + group_skeletons on full-resolution device maps:
  * K1 -> K2 -> K3 stream-ordered, then an asynchronous copy of the packed poses
- * into the handle's pinned staging buffer.  og_fetch_poses() synchronises. */
+ * into pinned memory of the handle.  Returns immediately; og_fetch_poses() synchronises. */
 int og_decode_maps(og_handle *h, const float *heat_dev, const float *offs_dev,
                    const float *scales_dev, int n, int hgt, int w, void *stream);
 
@@ -166,11 +166,15 @@ int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_
                            const int32_t *kp_flip, const int32_t *limb_flip,
                            const int32_t *limb_reserve, int n_reserve, void *stream);
 
-/* Wait for the last og_decode_* call and expose its result.  *poses_host points
- * into the handle's pinned buffer ([total, C, 6] float32, valid until the next
- * decode call); offsets / counts are [n] int32. */
+/* Up to two og_decode_* calls may be in flight on a handle (results are queued in order),
+ * so the launch of batch i + 1 can overlap the host-side consumption of batch i.
+ * og_fetch_poses waits for the OLDEST unfetched call and exposes its result: *poses_host
+ * points into pinned memory owned by the handle ([total, C, 6] float32), offsets / counts are
+ * [n] int32; the pointers stay valid until the second next og_decode_* call.
+ * og_pending returns the number of unfetched calls. */
 int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offset_host,
                    const int32_t **count_host, int32_t *total_rows);
+int og_pending(const og_handle *h);
 
 /* Copy the device-side intermediates of the last decode call (n images) into
  * caller-provided device buffers (any may be NULL): det scores [n, C, K],
@@ -192,7 +196,7 @@ int og_set_fused(og_handle *h, int enable);
 int64_t og_fused_redo_count(const og_handle *h);
 
 /* Per-stage device timing of og_decode_* calls with CUDA events recorded on the
- * launching stream.  og_last_stage_times_ms() waits for the last decode and fills
+ * launching stream.   og_last_stage_times_ms() reports the most recently FETCHED decode call:
  * out6 = { input copy + flip + resize, K1 pass 1 (NMS stream), K1 pass 2 (select),
  *          K2, K3, pose D2H } in milliseconds. */
 int og_enable_stage_timing(og_handle *h, int enable);

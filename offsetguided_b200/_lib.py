@@ -65,6 +65,7 @@ SIGNATURES = {
                                     c_int32_p, c_int32_p, c_int32_p, _i, _vp]),
     'og_fetch_poses': (_i, [_vp, ctypes.POINTER(c_float_p), ctypes.POINTER(c_int32_p),
                             ctypes.POINTER(c_int32_p), ctypes.POINTER(ctypes.c_int32)]),
+    'og_pending': (_i, [_vp]),
     'og_copy_intermediates': (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     'og_launch_count': (ctypes.c_int64, [_vp]),
     'og_set_fused': (_i, [_vp, _i]),

@@ -69,6 +69,33 @@ struct PinnedBuf {
 
 }  // namespace
 
+constexpr int kSlots = 2;          // decode calls that may be in flight before a fetch
+constexpr int kStageEvents = 7;    // start, after prep, K1 pass 1, K1 pass 2, K2, K3, D2H
+
+struct FeatureArgs {               // arguments of a features decode, kept for the exact redo
+    const float *hmp, *off;
+    int n, hgt, w, hmp_stride, off_stride, resize_mode, flip;
+};
+
+// Everything that belongs to ONE decode call until its result has been fetched.
+struct ResultSlot {
+    DevBuf<unsigned char> out;          // [meta int32][pose rows float]
+    PinnedBuf<unsigned char> out_host;
+    DevBuf<float> in_hmp, in_off;       // staged network-resolution inputs (host API)
+    cudaEvent_t done = nullptr;
+    cudaEvent_t ev[kStageEvents] = {nullptr};
+    cudaStream_t stream = nullptr;
+    int n = 0;
+    size_t meta_bytes = 0;
+    int rows_copied = 0;
+    int capacity_rows = 0;
+    bool pending = false;
+    bool fused = false;
+    bool timed = false;
+    bool prep_marked = false;
+    FeatureArgs args = {};
+};
+
 struct og_handle {
     og_config cfg;
     SkeletonDev sk;
@@ -77,52 +104,35 @@ struct og_handle {
     size_t group_smem;
     int64_t launches;
 
-    // K1
+    // intermediates, reused by consecutive calls in stream order
     DevBuf<uint32_t> cand_count;
     DevBuf<uint64_t> cand_keys;
     DevBuf<float> det_score;
     DevBuf<int32_t> det_index;
     DevBuf<int32_t> det_count;
-    // K2 / K3
     DevBuf<float> limbs;
     DevBuf<float> slab;
-    DevBuf<unsigned char> out;         // [meta int32 x meta_words][poses float]
-    PinnedBuf<unsigned char> out_host;
-    // feature path
-    DevBuf<float> in_hmp, in_off;      // staged network-resolution inputs (host path)
-    DevBuf<float> fused_hmp, fused_off;
+    DevBuf<float> fused_hmp, fused_off;     // materialising path only
     DevBuf<float> hr_hmp, hr_off;
     DevBuf<int32_t> kp_flip, limb_flip;
     DevBuf<uint8_t> limb_reserved;
 
-    // state of the last decode
-    cudaEvent_t done;
-    cudaStream_t last_stream;
-    int last_n;
-    size_t last_meta_bytes;
-    int last_rows_copied;
-    int last_capacity_rows;
+    ResultSlot slots[kSlots];
+    int head;                    // slot the next decode call uses
+    int tail;                    // oldest slot whose result has not been fetched
+    int pending;                 // decode calls in flight
+    int last_slot;               // slot of the most recent decode call (intermediates)
+    int fetched_slot;            // slot of the most recently fetched result (stage times)
     int rows_hint;
-    bool pending;
 
-    // fused network-resolution path (no materialised full-resolution maps)
     bool fused_enabled;
-    int64_t fused_redos;              // batches re-run through the materialising path
-    bool last_fused;                  // the pending decode used the fused path
-    bool tables_valid;                // device flip tables match the cached host copies
+    int64_t fused_redos;
+    bool tables_valid;           // device flip tables match the cached host copies
     int32_t kp_cache[OG_MAX_KEYPOINTS];
     int32_t limb_cache[OG_MAX_LIMBS];
     uint8_t reserved_cache[OG_MAX_LIMBS];
-    struct {                          // arguments of the pending features decode (for the redo)
-        const float *hmp, *off;
-        int n, hgt, w, hmp_stride, off_stride, resize_mode, flip;
-    } last_args;
 
-    // optional per-stage timing (og_enable_stage_timing)
     bool timing;
-    bool timing_valid;
-    bool prep_marked;
-    cudaEvent_t ev[7];      // start, after prep, after K1 pass 1, K1 pass 2, K2, K3, D2H
 };
 
 namespace {
@@ -148,8 +158,21 @@ int check_maps(int n, int hgt, int w, int c) {
     return OG_OK;
 }
 
-inline int mark(og_handle *h, int which, cudaStream_t s) {
-    if (h->timing) OG_CUDA_TRY(cudaEventRecord(h->ev[which], s));
+inline int mark(og_handle *h, ResultSlot *slot, int which, cudaStream_t s) {
+    if (h->timing) OG_CUDA_TRY(cudaEventRecord(slot->ev[which], s));
+    return OG_OK;
+}
+
+// Slot of a new decode call; `forced` re-uses a slot (the redo of a fetched-but-overflowed batch).
+int acquire_slot(og_handle *h, ResultSlot *forced, ResultSlot **out) {
+    if (forced) {
+        *out = forced;
+        return OG_OK;
+    }
+    ResultSlot *slot = &h->slots[h->head];
+    OG_REQUIRE(!slot->pending,
+               "%d decode calls are already in flight; call og_fetch_poses before the next decode", kSlots);
+    *out = slot;
     return OG_OK;
 }
 
@@ -192,17 +215,17 @@ int run_k3(og_handle *h, const float *limbs, int n, float *out_poses, int capaci
     return OG_OK;
 }
 
-// Shared body of every decode call.  K1 is either the full-resolution stream
-// (heat != nullptr) or the fused network-resolution kernel (lowres_hmp != nullptr).
 struct K1Fused {
     const float *hmp;       // network-resolution heat maps (n or 2n images)
     int h, w, scale;
     bool cubic, flip;
 };
 
-int decode_core(og_handle *h, const float *heat, const K1Fused *fused, const float *offs,
-                const OffsetSource *offs_lowres, const float *scales, int n, int hgt, int w,
-                cudaStream_t s) {
+// Shared body of every decode call: K1 (full-resolution stream, or the fused
+// network-resolution kernel) -> K2 -> K3 -> asynchronous D2H into the slot.
+int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused *fused,
+                const float *offs, const OffsetSource *offs_lowres, const float *scales, int n,
+                int hgt, int w, cudaStream_t s) {
     const og_config &c = h->cfg;
     OG_TRY(check_maps(n, hgt, w, c.n_keypoints));
     const size_t dets = (size_t)n * c.n_keypoints * c.topk;
@@ -212,66 +235,63 @@ int decode_core(og_handle *h, const float *heat, const K1Fused *fused, const flo
     OG_TRY(h->limbs.ensure((size_t)n * c.n_limbs * c.topk * OG_LIMB_COLS));
     const int capacity_rows = n * c.n_limbs * c.topk;
     const size_t mbytes = meta_bytes_for(n);
-    OG_TRY(h->out.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
-    OG_TRY(h->out_host.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
-    int32_t *meta = reinterpret_cast<int32_t *>(h->out.ptr);
-    float *poses = reinterpret_cast<float *>(h->out.ptr + mbytes);
+    OG_TRY(slot->out.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
+    OG_TRY(slot->out_host.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
+    int32_t *meta = reinterpret_cast<int32_t *>(slot->out.ptr);
+    float *poses = reinterpret_cast<float *>(slot->out.ptr + mbytes);
 
-    h->pending = false;
-    h->last_n = n;
-    h->last_meta_bytes = mbytes;
-    h->last_capacity_rows = capacity_rows;
-    h->last_stream = s;
-    h->last_fused = fused != nullptr;
-    h->timing_valid = false;
-    if (!h->prep_marked) OG_TRY(mark(h, 0, s));
-    OG_TRY(mark(h, 1, s));
-    h->prep_marked = false;
-    if (n == 0) {
-        h->last_rows_copied = 0;
-        return OG_OK;
+    slot->n = n;
+    slot->meta_bytes = mbytes;
+    slot->capacity_rows = capacity_rows;
+    slot->stream = s;
+    slot->fused = fused != nullptr;
+    slot->timed = false;
+    slot->rows_copied = 0;
+    if (!slot->prep_marked) OG_TRY(mark(h, slot, 0, s));
+    OG_TRY(mark(h, slot, 1, s));
+    slot->prep_marked = false;
+    if (n > 0) {
+        OG_CUDA_TRY(cudaMemsetAsync(meta + 2 * n, 0, 2 * sizeof(int32_t), s));     // total, overflow
+        if (fused) {
+            const int planes = n * c.n_keypoints;
+            OG_TRY(h->cand_count.ensure(planes));
+            OG_TRY(h->cand_keys.ensure((size_t)planes * kCandCap));
+            OG_TRY(launch_fused_candidates(fused->hmp, h->kp_flip.ptr, n, c.n_keypoints, fused->h,
+                                           fused->w, fused->scale, fused->cubic, fused->flip,
+                                           c.thre_hmp, h->cand_count.ptr, h->cand_keys.ptr, s));
+            OG_TRY(mark(h, slot, 2, s));
+            OG_TRY(launch_select_topk(nullptr, planes, hgt, w, c.thre_hmp, c.topk, h->cand_count.ptr,
+                                      h->cand_keys.ptr, h->det_score.ptr, h->det_index.ptr,
+                                      h->det_count.ptr, meta + 2 * n + 1, s));
+            h->launches += 2;
+        } else {
+            OG_TRY(run_k1(h, heat, n, hgt, w, c.thre_hmp, h->det_score.ptr, h->det_index.ptr,
+                          h->det_count.ptr, s, h->timing ? slot->ev[2] : nullptr));
+        }
+        OG_TRY(mark(h, slot, 3, s));
+        OG_TRY(launch_limb_score(h->det_score.ptr, h->det_index.ptr, offs, offs_lowres, scales, n,
+                                 c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp,
+                                 c.min_len, c.resize_factor, h->limbs.ptr, s));
+        h->launches += 1;
+        OG_TRY(mark(h, slot, 4, s));
+        OG_TRY(run_k3(h, h->limbs.ptr, n, poses, capacity_rows, meta, meta + n, meta + 2 * n, s, false));
+        OG_TRY(mark(h, slot, 5, s));
+        // one asynchronous copy: meta + the pose rows the previous batches suggest
+        const int rows = std::min(capacity_rows, h->rows_hint > 0 ? h->rows_hint : n * 32);
+        const size_t bytes = mbytes + (size_t)rows * pose_row_bytes(h);
+        OG_CUDA_TRY(cudaMemcpyAsync(slot->out_host.ptr, slot->out.ptr, bytes, cudaMemcpyDeviceToHost, s));
+        OG_TRY(mark(h, slot, 6, s));
+        slot->timed = h->timing;
+        slot->rows_copied = rows;
+        OG_CUDA_TRY(cudaEventRecord(slot->done, s));
     }
-    OG_CUDA_TRY(cudaMemsetAsync(meta + 2 * n, 0, 2 * sizeof(int32_t), s));     // total, overflow
-    if (fused) {
-        const int planes = n * c.n_keypoints;
-        OG_TRY(h->cand_count.ensure(planes));
-        OG_TRY(h->cand_keys.ensure((size_t)planes * kCandCap));
-        OG_TRY(launch_fused_candidates(fused->hmp, h->kp_flip.ptr, n, c.n_keypoints, fused->h,
-                                       fused->w, fused->scale, fused->cubic, fused->flip, c.thre_hmp,
-                                       h->cand_count.ptr, h->cand_keys.ptr, s));
-        OG_TRY(mark(h, 2, s));
-        OG_TRY(launch_select_topk(nullptr, planes, hgt, w, c.thre_hmp, c.topk, h->cand_count.ptr,
-                                  h->cand_keys.ptr, h->det_score.ptr, h->det_index.ptr,
-                                  h->det_count.ptr, meta + 2 * n + 1, s));
-        h->launches += 2;
-    } else {
-        OG_TRY(run_k1(h, heat, n, hgt, w, c.thre_hmp, h->det_score.ptr, h->det_index.ptr,
-                      h->det_count.ptr, s, h->timing ? h->ev[2] : nullptr));
+    if (!slot->pending) {           // a redo keeps its place in the queue
+        slot->pending = true;
+        h->pending += 1;
+        h->head = (h->head + 1) % kSlots;
     }
-    OG_TRY(mark(h, 3, s));
-    OG_TRY(launch_limb_score(h->det_score.ptr, h->det_index.ptr, offs, offs_lowres, scales, n,
-                             c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp, c.min_len,
-                             c.resize_factor, h->limbs.ptr, s));
-    h->launches += 1;
-    OG_TRY(mark(h, 4, s));
-    OG_TRY(run_k3(h, h->limbs.ptr, n, poses, capacity_rows, meta, meta + n, meta + 2 * n, s, false));
-    OG_TRY(mark(h, 5, s));
-
-    // one asynchronous copy: meta + the pose rows the previous batches suggest
-    const int rows = std::min(capacity_rows, h->rows_hint > 0 ? h->rows_hint : n * 32);
-    const size_t bytes = mbytes + (size_t)rows * pose_row_bytes(h);
-    OG_CUDA_TRY(cudaMemcpyAsync(h->out_host.ptr, h->out.ptr, bytes, cudaMemcpyDeviceToHost, s));
-    OG_TRY(mark(h, 6, s));
-    h->timing_valid = h->timing;
-    OG_CUDA_TRY(cudaEventRecord(h->done, s));
-    h->last_rows_copied = rows;
-    h->pending = true;
+    h->last_slot = (int)(slot - h->slots);
     return OG_OK;
-}
-
-int decode_maps_impl(og_handle *h, const float *heat, const float *offs, const float *scales, int n,
-                     int hgt, int w, cudaStream_t s) {
-    return decode_core(h, heat, nullptr, offs, nullptr, scales, n, hgt, w, s);
 }
 
 int upload_flip_tables(og_handle *h, const int32_t *kp_flip, const int32_t *limb_flip,
@@ -295,11 +315,13 @@ int upload_flip_tables(og_handle *h, const int32_t *kp_flip, const int32_t *limb
     OG_TRY(h->kp_flip.ensure(c.n_keypoints));
     OG_TRY(h->limb_flip.ensure(c.n_limbs));
     OG_TRY(h->limb_reserved.ensure(c.n_limbs));
-    // synchronous small copies from pageable memory: safe with respect to the caller's arrays
-    OG_CUDA_TRY(cudaMemcpyAsync(h->kp_flip.ptr, kp_flip, sizeof(int32_t) * c.n_keypoints, cudaMemcpyHostToDevice, s));
-    OG_CUDA_TRY(cudaMemcpyAsync(h->limb_flip.ptr, limb_flip, sizeof(int32_t) * c.n_limbs, cudaMemcpyHostToDevice, s));
-    OG_CUDA_TRY(cudaMemcpyAsync(h->limb_reserved.ptr, reserved, c.n_limbs, cudaMemcpyHostToDevice, s));
-    OG_CUDA_TRY(cudaStreamSynchronize(s));
+    // the tables may still be read by a decode in flight: drain the device first (rare: tables change
+    // only when the caller switches skeleton tables)
+    OG_CUDA_TRY(cudaDeviceSynchronize());
+    OG_CUDA_TRY(cudaMemcpy(h->kp_flip.ptr, kp_flip, sizeof(int32_t) * c.n_keypoints, cudaMemcpyHostToDevice));
+    OG_CUDA_TRY(cudaMemcpy(h->limb_flip.ptr, limb_flip, sizeof(int32_t) * c.n_limbs, cudaMemcpyHostToDevice));
+    OG_CUDA_TRY(cudaMemcpy(h->limb_reserved.ptr, reserved, c.n_limbs, cudaMemcpyHostToDevice));
+    (void)s;
     memcpy(h->kp_cache, kp_flip, sizeof(int32_t) * c.n_keypoints);
     memcpy(h->limb_cache, limb_flip, sizeof(int32_t) * c.n_limbs);
     memcpy(h->reserved_cache, reserved, c.n_limbs);
@@ -307,35 +329,17 @@ int upload_flip_tables(og_handle *h, const int32_t *kp_flip, const int32_t *limb
     return OG_OK;
 }
 
-int decode_features_impl(og_handle *h, const float *hmp, const float *off, int n, int hgt, int w,
-                         int hmp_stride, int off_stride, int resize_mode, int flip_test,
-                         const int32_t *kp_flip, const int32_t *limb_flip,
-                         const int32_t *limb_reserve, int n_reserve, cudaStream_t s,
-                         bool allow_fused = true) {
+int decode_features_impl(og_handle *h, ResultSlot *slot, const float *hmp, const float *off, int n,
+                         int hgt, int w, int hmp_stride, int off_stride, int resize_mode,
+                         int flip_test, cudaStream_t s, bool allow_fused) {
     const og_config &c = h->cfg;
-    OG_REQUIRE(hmp_stride >= 1 && off_stride >= 1, "strides must be >= 1");
-    OG_REQUIRE(hmp_stride == off_stride,
-               "heat and offset maps must reach the same resolution (collect.py:81): strides %d vs %d",
-               hmp_stride, off_stride);
-    OG_REQUIRE(resize_mode == 0 || resize_mode == 1, "resize_mode must be 0 (bilinear) or 1 (bicubic)");
     const float *cur_h = hmp, *cur_o = off;
     const size_t hw = (size_t)hgt * w;
-    if (!h->prep_marked) {
-        OG_TRY(mark(h, 0, s));
-        h->prep_marked = h->timing;
+    if (!slot->prep_marked) {
+        OG_TRY(mark(h, slot, 0, s));
+        slot->prep_marked = h->timing;
     }
-    h->last_args.hmp = hmp;
-    h->last_args.off = off;
-    h->last_args.n = n;
-    h->last_args.hgt = hgt;
-    h->last_args.w = w;
-    h->last_args.hmp_stride = hmp_stride;
-    h->last_args.off_stride = off_stride;
-    h->last_args.resize_mode = resize_mode;
-    h->last_args.flip = flip_test;
-    if (flip_test && kp_flip != nullptr)
-        OG_TRY(upload_flip_tables(h, kp_flip, limb_flip, limb_reserve, n_reserve, s));
-    OG_REQUIRE(!flip_test || h->tables_valid, "flip_test needs the keypoint / limb flip tables");
+    slot->args = FeatureArgs{hmp, off, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test};
 
     // Fused path: candidates straight from the network-resolution maps, offsets sampled at
     // the candidates; no full-resolution map is written.  thre_hmp <= 0 (every pixel is a
@@ -345,7 +349,7 @@ int decode_features_impl(og_handle *h, const float *hmp, const float *off, int n
         K1Fused k1 = {hmp, hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
         OffsetSource src = {off, hgt, w, off_stride, flip_test ? 1 : 0, n, h->limb_flip.ptr,
                             h->limb_reserved.ptr};
-        return decode_core(h, nullptr, &k1, nullptr, &src, nullptr, n, hgt * hmp_stride,
+        return decode_core(h, slot, nullptr, &k1, nullptr, &src, nullptr, n, hgt * hmp_stride,
                            w * hmp_stride, s);
     }
     if (flip_test) {
@@ -371,7 +375,22 @@ int decode_features_impl(og_handle *h, const float *hmp, const float *off, int n
         cur_h = h->hr_hmp.ptr;
         cur_o = h->hr_off.ptr;
     }
-    return decode_maps_impl(h, cur_h, cur_o, nullptr, n, H, W, s);
+    return decode_core(h, slot, cur_h, nullptr, cur_o, nullptr, nullptr, n, H, W, s);
+}
+
+int check_feature_args(og_handle *h, int n, int hgt, int w, int hmp_stride, int off_stride,
+                       int resize_mode, int flip_test, const int32_t *kp_flip,
+                       const int32_t *limb_flip, const int32_t *limb_reserve, int n_reserve,
+                       cudaStream_t s) {
+    OG_TRY(check_device(h));
+    OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
+    OG_REQUIRE(hmp_stride >= 1 && off_stride >= 1, "strides must be >= 1");
+    OG_REQUIRE(hmp_stride == off_stride,
+               "heat and offset maps must reach the same resolution (collect.py:81): strides %d vs %d",
+               hmp_stride, off_stride);
+    OG_REQUIRE(resize_mode == 0 || resize_mode == 1, "resize_mode must be 0 (bilinear) or 1 (bicubic)");
+    if (flip_test) OG_TRY(upload_flip_tables(h, kp_flip, limb_flip, limb_reserve, n_reserve, s));
+    return OG_OK;
 }
 
 }  // namespace
@@ -442,17 +461,13 @@ int og_create(const og_config *cfg, og_handle **out) {
     }
     h->device = device;
     h->launches = 0;
-    h->pending = false;
-    h->last_n = 0;
+    h->head = h->tail = h->pending = 0;
+    h->last_slot = 0;
+    h->fetched_slot = -1;
     h->rows_hint = 0;
-    h->last_stream = nullptr;
     h->timing = false;
-    h->timing_valid = false;
-    h->prep_marked = false;
-    for (int i = 0; i < 7; ++i) h->ev[i] = nullptr;
     h->fused_enabled = true;
     h->fused_redos = 0;
-    h->last_fused = false;
     h->tables_valid = false;
 
     // person-table rows held in shared memory: as many as fit beside the work arrays
@@ -479,11 +494,13 @@ int og_create(const og_config *cfg, og_handle **out) {
         delete h;
         return st;
     }
-    cudaError_t err = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
-    if (err != cudaSuccess) {
-        delete h;
-        set_error("cudaEventCreate failed: %s", cudaGetErrorString(err));
-        return OG_ERR_CUDA;
+    for (int i = 0; i < kSlots; ++i) {
+        cudaError_t err = cudaEventCreateWithFlags(&h->slots[i].done, cudaEventDisableTiming);
+        if (err != cudaSuccess) {
+            og_destroy(h);
+            set_error("cudaEventCreate failed: %s", cudaGetErrorString(err));
+            return OG_ERR_CUDA;
+        }
     }
     *out = h;
     return OG_OK;
@@ -499,10 +516,6 @@ int og_destroy(og_handle *h) {
     h->det_count.release();
     h->limbs.release();
     h->slab.release();
-    h->out.release();
-    h->out_host.release();
-    h->in_hmp.release();
-    h->in_off.release();
     h->fused_hmp.release();
     h->fused_off.release();
     h->hr_hmp.release();
@@ -510,9 +523,16 @@ int og_destroy(og_handle *h) {
     h->kp_flip.release();
     h->limb_flip.release();
     h->limb_reserved.release();
-    cudaEventDestroy(h->done);
-    for (int i = 0; i < 7; ++i)
-        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < kSlots; ++i) {
+        ResultSlot &sl = h->slots[i];
+        sl.out.release();
+        sl.out_host.release();
+        sl.in_hmp.release();
+        sl.in_off.release();
+        if (sl.done) cudaEventDestroy(sl.done);
+        for (int e = 0; e < kStageEvents; ++e)
+            if (sl.ev[e]) cudaEventDestroy(sl.ev[e]);
+    }
     delete h;
     return OG_OK;
 }
@@ -611,7 +631,11 @@ int og_decode_maps(og_handle *h, const float *heat_dev, const float *offs_dev,
                    const float *scales_dev, int n, int hgt, int w, void *stream) {
     OG_REQUIRE(h && heat_dev && offs_dev, "og_decode_maps: null pointer");
     OG_TRY(check_device(h));
-    return decode_maps_impl(h, heat_dev, offs_dev, scales_dev, n, hgt, w, static_cast<cudaStream_t>(stream));
+    ResultSlot *slot = nullptr;
+    OG_TRY(acquire_slot(h, nullptr, &slot));
+    slot->args = FeatureArgs{};
+    return decode_core(h, slot, heat_dev, nullptr, offs_dev, nullptr, scales_dev, n, hgt, w,
+                       static_cast<cudaStream_t>(stream));
 }
 
 int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_dev, int n, int hgt,
@@ -619,11 +643,13 @@ int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_
                            const int32_t *kp_flip, const int32_t *limb_flip,
                            const int32_t *limb_reserve, int n_reserve, void *stream) {
     OG_REQUIRE(h && hmp_dev && off_dev, "og_decode_features_dev: null pointer");
-    OG_TRY(check_device(h));
-    OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
-    return decode_features_impl(h, hmp_dev, off_dev, n, hgt, w, hmp_stride, off_stride, resize_mode,
-                                flip_test, kp_flip, limb_flip, limb_reserve, n_reserve,
-                                static_cast<cudaStream_t>(stream));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
+                              limb_flip, limb_reserve, n_reserve, s));
+    ResultSlot *slot = nullptr;
+    OG_TRY(acquire_slot(h, nullptr, &slot));
+    return decode_features_impl(h, slot, hmp_dev, off_dev, n, hgt, w, hmp_stride, off_stride,
+                                resize_mode, flip_test, s, true);
 }
 
 int og_decode_features_host(og_handle *h, const float *hmp_host, const float *off_host, int n,
@@ -631,22 +657,26 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
                             int flip_test, const int32_t *kp_flip, const int32_t *limb_flip,
                             const int32_t *limb_reserve, int n_reserve, void *stream) {
     OG_REQUIRE(h && hmp_host && off_host, "og_decode_features_host: null pointer");
-    OG_TRY(check_device(h));
-    OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
+                              limb_flip, limb_reserve, n_reserve, s));
+    ResultSlot *slot = nullptr;
+    OG_TRY(acquire_slot(h, nullptr, &slot));
     const og_config &c = h->cfg;
     const size_t n_in = (size_t)(flip_test ? 2 * n : n);
     const size_t hw = (size_t)hgt * w;
-    OG_TRY(h->in_hmp.ensure(n_in * c.n_keypoints * hw));
-    OG_TRY(h->in_off.ensure(n_in * 2 * c.n_limbs * hw));
-    OG_TRY(mark(h, 0, s));
-    h->prep_marked = h->timing;
-    OG_CUDA_TRY(cudaMemcpyAsync(h->in_hmp.ptr, hmp_host, n_in * c.n_keypoints * hw * sizeof(float),
-                                cudaMemcpyHostToDevice, s));
-    OG_CUDA_TRY(cudaMemcpyAsync(h->in_off.ptr, off_host, n_in * 2 * c.n_limbs * hw * sizeof(float),
-                                cudaMemcpyHostToDevice, s));
-    return decode_features_impl(h, h->in_hmp.ptr, h->in_off.ptr, n, hgt, w, hmp_stride, off_stride,
-                                resize_mode, flip_test, kp_flip, limb_flip, limb_reserve, n_reserve, s);
+    OG_TRY(slot->in_hmp.ensure(std::max<size_t>(1, n_in * c.n_keypoints * hw)));
+    OG_TRY(slot->in_off.ensure(std::max<size_t>(1, n_in * 2 * c.n_limbs * hw)));
+    OG_TRY(mark(h, slot, 0, s));
+    slot->prep_marked = h->timing;
+    if (n_in) {
+        OG_CUDA_TRY(cudaMemcpyAsync(slot->in_hmp.ptr, hmp_host, n_in * c.n_keypoints * hw * sizeof(float),
+                                    cudaMemcpyHostToDevice, s));
+        OG_CUDA_TRY(cudaMemcpyAsync(slot->in_off.ptr, off_host, n_in * 2 * c.n_limbs * hw * sizeof(float),
+                                    cudaMemcpyHostToDevice, s));
+    }
+    return decode_features_impl(h, slot, slot->in_hmp.ptr, slot->in_off.ptr, n, hgt, w, hmp_stride,
+                                off_stride, resize_mode, flip_test, s, true);
 }
 
 int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offset_host,
@@ -656,50 +686,60 @@ int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offse
     *offset_host = nullptr;
     *count_host = nullptr;
     *total_rows = 0;
-    if (h->last_n == 0) return OG_OK;
-    OG_REQUIRE(h->pending, "og_fetch_poses: no decode call is pending");
-    OG_CUDA_TRY(cudaEventSynchronize(h->done));
-    const int n = h->last_n;
-    const int32_t *meta = reinterpret_cast<const int32_t *>(h->out_host.ptr);
-    if (h->last_fused && meta[2 * n + 1] != 0) {
-        // Some plane produced more than kCandCap candidates (noise-like input): the fused
-        // kernel cannot re-scan a map it never materialised, so this batch is decoded again
-        // on the GPU through the materialising path, which selects exactly for any input.
-        h->fused_redos += 1;
-        OG_TRY(decode_features_impl(h, h->last_args.hmp, h->last_args.off, h->last_args.n,
-                                    h->last_args.hgt, h->last_args.w, h->last_args.hmp_stride,
-                                    h->last_args.off_stride, h->last_args.resize_mode,
-                                    h->last_args.flip, nullptr, nullptr, nullptr, 0, h->last_stream,
-                                    false));
-        OG_CUDA_TRY(cudaEventSynchronize(h->done));
+    OG_REQUIRE(h->pending > 0, "og_fetch_poses: no decode call is pending");
+    OG_TRY(check_device(h));
+    ResultSlot *slot = &h->slots[h->tail];
+    const int n = slot->n;
+    int total = 0;
+    const int32_t *meta = reinterpret_cast<const int32_t *>(slot->out_host.ptr);
+    if (n > 0) {
+        OG_CUDA_TRY(cudaEventSynchronize(slot->done));
+        if (slot->fused && meta[2 * n + 1] != 0) {
+            // Some plane produced more than kCandCap candidates (noise-like input): the fused
+            // kernel cannot re-scan a map it never materialised, so this batch is decoded again
+            // on the GPU through the materialising path, which selects exactly for any input.
+            h->fused_redos += 1;
+            const FeatureArgs a = slot->args;
+            OG_TRY(decode_features_impl(h, slot, a.hmp, a.off, a.n, a.hgt, a.w, a.hmp_stride,
+                                        a.off_stride, a.resize_mode, a.flip, slot->stream, false));
+            OG_CUDA_TRY(cudaEventSynchronize(slot->done));
+            meta = reinterpret_cast<const int32_t *>(slot->out_host.ptr);
+        }
+        total = meta[2 * n];
+        if (total > slot->capacity_rows) {
+            set_error("internal: %d pose rows exceed the worst-case capacity %d", total, slot->capacity_rows);
+            return OG_ERR_CAPACITY;
+        }
+        if (total > slot->rows_copied) {     // rare: more persons than the speculative copy covered
+            const size_t row = pose_row_bytes(h);
+            const size_t at = slot->meta_bytes + (size_t)slot->rows_copied * row;
+            OG_CUDA_TRY(cudaMemcpyAsync(slot->out_host.ptr + at, slot->out.ptr + at,
+                                        (size_t)(total - slot->rows_copied) * row,
+                                        cudaMemcpyDeviceToHost, slot->stream));
+            OG_CUDA_TRY(cudaStreamSynchronize(slot->stream));
+            slot->rows_copied = total;
+        }
+        h->rows_hint = total + total / 2 + 16;      // speculative D2H size of the next batch
+        *offset_host = meta;
+        *count_host = meta + n;
+        *poses_host = reinterpret_cast<const float *>(slot->out_host.ptr + slot->meta_bytes);
     }
-    const int total = meta[2 * n];
-    if (total > h->last_capacity_rows) {
-        set_error("internal: %d pose rows exceed the worst-case capacity %d", total, h->last_capacity_rows);
-        return OG_ERR_CAPACITY;
-    }
-    if (total > h->last_rows_copied) {       // rare: more persons than the speculative copy covered
-        const size_t row = pose_row_bytes(h);
-        const size_t at = h->last_meta_bytes + (size_t)h->last_rows_copied * row;
-        OG_CUDA_TRY(cudaMemcpyAsync(h->out_host.ptr + at, h->out.ptr + at,
-                                    (size_t)(total - h->last_rows_copied) * row,
-                                    cudaMemcpyDeviceToHost, h->last_stream));
-        OG_CUDA_TRY(cudaStreamSynchronize(h->last_stream));
-        h->last_rows_copied = total;
-    }
-    h->rows_hint = total + total / 2 + 16;      // speculative D2H size of the next batch
-    *offset_host = meta;
-    *count_host = meta + n;
     *total_rows = total;
-    *poses_host = reinterpret_cast<const float *>(h->out_host.ptr + h->last_meta_bytes);
+    slot->pending = false;
+    h->pending -= 1;
+    h->fetched_slot = h->tail;
+    h->tail = (h->tail + 1) % kSlots;
     return OG_OK;
 }
+
+int og_pending(const og_handle *h) { return h ? h->pending : 0; }
 
 int og_copy_intermediates(og_handle *h, int n, float *det_score_dev, int32_t *det_index_dev,
                           float *limbs_dev, void *stream) {
     OG_REQUIRE(h, "og_copy_intermediates: null handle");
-    OG_REQUIRE(n >= 0 && n <= h->last_n, "og_copy_intermediates: n = %d but the last decode had %d images",
-               n, h->last_n);
+    OG_REQUIRE(n >= 0 && n <= h->slots[h->last_slot].n,
+               "og_copy_intermediates: n = %d but the last decode had %d images", n,
+               h->slots[h->last_slot].n);
     OG_TRY(check_device(h));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const og_config &c = h->cfg;
@@ -728,20 +768,21 @@ int og_enable_stage_timing(og_handle *h, int enable) {
     OG_REQUIRE(h, "og_enable_stage_timing: null handle");
     OG_TRY(check_device(h));
     if (enable) {
-        for (int i = 0; i < 7; ++i)
-            if (!h->ev[i]) OG_CUDA_TRY(cudaEventCreate(&h->ev[i]));
+        for (int i = 0; i < kSlots; ++i)
+            for (int e = 0; e < kStageEvents; ++e)
+                if (!h->slots[i].ev[e]) OG_CUDA_TRY(cudaEventCreate(&h->slots[i].ev[e]));
     }
     h->timing = enable != 0;
-    h->timing_valid = false;
-    h->prep_marked = false;
     return OG_OK;
 }
 
 int og_last_stage_times_ms(og_handle *h, float *out6) {
     OG_REQUIRE(h && out6, "og_last_stage_times_ms: null pointer");
-    OG_REQUIRE(h->timing_valid, "og_last_stage_times_ms: enable stage timing and decode first");
-    OG_CUDA_TRY(cudaEventSynchronize(h->ev[6]));
-    for (int i = 0; i < 6; ++i) OG_CUDA_TRY(cudaEventElapsedTime(&out6[i], h->ev[i], h->ev[i + 1]));
+    OG_REQUIRE(h->fetched_slot >= 0 && h->slots[h->fetched_slot].timed,
+               "og_last_stage_times_ms: enable stage timing, decode and fetch first");
+    ResultSlot *slot = &h->slots[h->fetched_slot];
+    OG_CUDA_TRY(cudaEventSynchronize(slot->ev[6]));
+    for (int i = 0; i < 6; ++i) OG_CUDA_TRY(cudaEventElapsedTime(&out6[i], slot->ev[i], slot->ev[i + 1]));
     return OG_OK;
 }
 

@@ -160,8 +160,10 @@ class DecoderEngine(object):
         rows = np.ctypeslib.as_array(poses_p, shape=(total.value, c, _lib.OG_POSE_COLS))
         return [rows[offs[i]:offs[i] + cnts[i]].copy() for i in range(n)]
 
-    def decode_maps(self, heat, offs, scales=None):
-        """generate_limbs + group_skeletons on full-resolution maps (K1 -> K2 -> K3)."""
+    def decode_maps(self, heat, offs, scales=None, fetch=True):
+        """generate_limbs + group_skeletons on full-resolution maps (K1 -> K2 -> K3).
+        With ``fetch=False`` the call only launches (up to two calls may be in flight);
+        ``fetch(n)`` later returns the oldest pending result."""
         heat = as_cuda_f32(heat, self.device)
         offs = as_cuda_f32(offs, self.device)
         assert heat.shape[-2:] == offs.shape[-2:], 'spatial resolution should be equal'
@@ -171,6 +173,9 @@ class DecoderEngine(object):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.og_decode_maps(self._h, _ptr(heat), _ptr(offs), _ptr(scales),
                                                n, h, w, _stream_ptr(self.device)))
+            self._keep_maps = (heat, offs, scales)
+            if not fetch:
+                return n
             return self._fetch(n)
 
     def decode_features(self, hmp, off, hmp_stride, off_stride, resize_mode='bicubic',
@@ -198,14 +203,19 @@ class DecoderEngine(object):
         with torch.cuda.device(self.device):
             _lib.check(fn(self._h, _ptr(hmp), _ptr(off), n, h, w, int(hmp_stride), int(off_stride),
                           mode, 1 if flip else 0, *args, _stream_ptr(self.device)))
-            self._keepalive = (hmp, off)
+            self._keepalive = (getattr(self, '_keepalive', (None,))[-1], (hmp, off))
             if not fetch:
                 return n
             return self._fetch(n)
 
     def fetch(self, n):
+        """Result of the oldest decode call launched with ``fetch=False``."""
         with torch.cuda.device(self.device):
             return self._fetch(n)
+
+    @property
+    def pending(self):
+        return int(self.lib.og_pending(self._h))
 
     def set_fused(self, on=True):
         """Enable / disable the fused network-resolution path of decode_features."""

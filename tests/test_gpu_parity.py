@@ -413,3 +413,33 @@ def test_fused_path_overflow_reruns_exactly(cuda_device):
     for a, b in zip(f_int, s_int):
         assert np.array_equal(a, b)
     assert np.array_equal(fused[0], staged[0]) and len(fused[0]) > 10
+
+
+def test_two_decodes_in_flight(cuda_device):
+    """The handle queues up to two decode calls; results come back oldest first and equal
+    the synchronous results; a third un-fetched call is refused."""
+    from offsetguided_b200 import _lib
+    skel = cfg.COCO_PERSON_SKELETON
+    heat, offs = scenes.synth_hires_batch(321, 4, 4, 320, 256, skel)
+    th, to = torch.from_numpy(heat).cuda(), torch.from_numpy(offs).cuda()
+    eng = DecoderEngine(17, skel, topk=16, thre_hmp=0.05, dist_max=40, use_scale=True, person_thre=0.05)
+    eng.enable_stage_timing(True)
+    ref_a = eng.decode_maps(th[:3], to[:3])
+    ref_b = eng.decode_maps(th[3:], to[3:])
+    assert eng.pending == 0
+    na = eng.decode_maps(th[:3], to[:3], fetch=False)
+    nb = eng.decode_maps(th[3:], to[3:], fetch=False)
+    assert eng.pending == 2
+    with pytest.raises(_lib.OgError):
+        eng.decode_maps(th[:1], to[:1], fetch=False)
+    got_a = eng.fetch(na)
+    t_a = eng.last_stage_times_ms()
+    nc = eng.decode_maps(th[:0], to[:0], fetch=False)          # empty batch in the queue
+    got_b = eng.fetch(nb)
+    assert eng.fetch(nc) == [] and eng.pending == 0
+    assert len(got_a) == 3 and len(got_b) == 1
+    for g, r in zip(got_a + got_b, ref_a + ref_b):
+        assert np.array_equal(g, r)
+    assert t_a['k1_stream'] > 0 and t_a['k3'] > 0
+    with pytest.raises(_lib.OgError):
+        eng.fetch(1)
