@@ -353,10 +353,14 @@ def run_b200(args):
             traffic = json.load(open(os.path.join(ROOT, 'profiles', 'k1_traffic.json')))['dram_bytes_per_launch']
         except Exception:
             pass
-        cpu_n = args.cpu_sample or 0
-        run, cores, what = cpu_decode_fn()
-        cpu_n = cpu_n or (16 if cores > 1 else 1)
-        cpu_value, cores, what, cpu_times = time_cpu(args, cpu_n, 2 if cores > 1 else 1)
+        cpu_block = None          # timed on rank 0 at N = 1 only (bench contract)
+        if n_gpus == 1:
+            run, cores, what = cpu_decode_fn()
+            cpu_n = args.cpu_sample or (16 if cores > 1 else 1)
+            cpu_value, cores, what, cpu_times = time_cpu(args, cpu_n, 2 if cores > 1 else 1)
+            cpu_block = {'value': cpu_value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d images of the same workload (flip fusion + x4 resize + NMS/top-K '
+                                   '+ limbs + grouping), best of %d, %s' % (cpu_n, len(cpu_times), what)}
         line = {
             'metric': METRIC, 'value': n_gpus * B * args.steps / (hot_ms * 1e-3), 'unit': UNIT,
             'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -378,9 +382,7 @@ def run_b200(args):
                          'stream_pass_only_gbs': alg_bytes / (k1_stream_ms * 1e-3) / 1e9},
             'stage_ms': stage_mean,
             'persons_per_step': n_persons,
-            'cpu_baseline': {'value': cpu_value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                             'sample': '%d images of the same workload (flip fusion + x4 resize + NMS/top-K '
-                                       '+ limbs + grouping), best of %d, %s' % (cpu_n, len(cpu_times), what)},
+            'cpu_baseline': cpu_block,
             'clocks': clocks,
         }
         print(json.dumps(line))

@@ -629,7 +629,7 @@ int og_resize_f32(const float *in_dev, float *out_dev, int planes, int hgt, int 
 
 int og_decode_maps(og_handle *h, const float *heat_dev, const float *offs_dev,
                    const float *scales_dev, int n, int hgt, int w, void *stream) {
-    OG_REQUIRE(h && heat_dev && offs_dev, "og_decode_maps: null pointer");
+    OG_REQUIRE(h && (n == 0 || (heat_dev && offs_dev)), "og_decode_maps: null pointer");
     OG_TRY(check_device(h));
     ResultSlot *slot = nullptr;
     OG_TRY(acquire_slot(h, nullptr, &slot));
@@ -642,7 +642,7 @@ int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_
                            int w, int hmp_stride, int off_stride, int resize_mode, int flip_test,
                            const int32_t *kp_flip, const int32_t *limb_flip,
                            const int32_t *limb_reserve, int n_reserve, void *stream) {
-    OG_REQUIRE(h && hmp_dev && off_dev, "og_decode_features_dev: null pointer");
+    OG_REQUIRE(h && (n == 0 || (hmp_dev && off_dev)), "og_decode_features_dev: null pointer");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
                               limb_flip, limb_reserve, n_reserve, s));
@@ -656,7 +656,7 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
                             int hgt, int w, int hmp_stride, int off_stride, int resize_mode,
                             int flip_test, const int32_t *kp_flip, const int32_t *limb_flip,
                             const int32_t *limb_reserve, int n_reserve, void *stream) {
-    OG_REQUIRE(h && hmp_host && off_host, "og_decode_features_host: null pointer");
+    OG_REQUIRE(h && (n == 0 || (hmp_host && off_host)), "og_decode_features_host: null pointer");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
                               limb_flip, limb_reserve, n_reserve, s));
