@@ -29,9 +29,12 @@ namespace og {
 
 namespace {
 
-constexpr int kGroupThreads = 256;
+#ifndef OG_K3_THREADS
+#define OG_K3_THREADS 256
+#endif
+constexpr int kGroupThreads = OG_K3_THREADS;
 
-enum Flag { kNValid = 0, kAnyP1, kAnyP2, kAnyMerge, kOutOffset, kNumFlags = 8 };
+enum Flag { kNValid = 0, kAnyP1, kAnyP2, kAnyMerge, kOutOffset, kNKept, kNNew, kNumFlags = 8 };
 
 struct GroupArgs {
     int C, L, K;
@@ -138,16 +141,13 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, float *__restrict__ o
     s_conn_buf[1] = s_conn_buf[0] + align_up((size_t)K * OG_LIMB_COLS * 4, 16) / 4;
     const int lane = tid & 31, wid = tid >> 5, nwarps = T >> 5;
     int *kbase = reinterpret_cast<int *>(smem + lo.k_int);
-    int *s_valid = kbase + 0 * K;
     int *s_sorted = kbase + 1 * K;
-    int *s_keep = kbase + 2 * K;
     int *s_kept = kbase + 3 * K;
     int *s_kind1 = kbase + 4 * K;
     int *s_kind2 = kbase + 5 * K;
     float *s_kscore = reinterpret_cast<float *>(kbase + 6 * K);
     int *s_n1 = kbase + 7 * K;
     int *s_n2 = kbase + 8 * K;
-    int *s_isnew = kbase + 9 * K;
     int16_t *pbase = reinterpret_cast<int16_t *>(smem + lo.p_i16);
     int16_t *s_order = pbase + 0 * pmax;
     int16_t *s_order2 = pbase + 1 * pmax;
@@ -186,39 +186,43 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, float *__restrict__ o
         bool overflow = false;
         __syncthreads();
 
-        // rows of limb type 0; the rows of type li + 1 are fetched while type li is processed
-        for (int i = tid; i < K * OG_LIMB_COLS; i += T) s_conn_buf[0][i] = limbs_img[i];
+        // rows of limb type li + 1 are fetched with cp.async while type li is processed
+        auto fetch_rows = [&](int li_next) {
+            float *dst = s_conn_buf[li_next & 1];
+            const float *src = limbs_img + (size_t)li_next * K * OG_LIMB_COLS;
+            for (int i = tid; i < K * OG_LIMB_COLS; i += T) {
+                const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + i);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(src + i));
+            }
+            asm volatile("cp.async.commit_group;");
+        };
+        fetch_rows(0);
         for (int li = 0; li < L && !overflow; ++li) {
             const int jf = a.sk.from[li], jt = a.sk.to[li];
             const float *s_conn = s_conn_buf[li & 1];
-            if (li + 1 < L) {
-                float *nxt = s_conn_buf[(li + 1) & 1];
-                const float *src = limbs_img + (size_t)(li + 1) * K * OG_LIMB_COLS;
-                for (int i = tid; i < K * OG_LIMB_COLS; i += T) nxt[i] = __ldg(src + i);
-            }
+            asm volatile("cp.async.wait_all;" ::: "memory");        // rows of type li have landed
+            if (li + 1 < L) fetch_rows(li + 1);
             if (tid < kNumFlags) s_flag[tid] = 0;
             __syncthreads();
-            // ---- gate (group.py:64-76)
-            for (int k = tid; k < K; k += T) {
+
+            // gate (group.py:64-76): distance test and both endpoints strictly inside the image
+            auto row_valid = [&](int k) {
                 const float *r = s_conn + k * OG_LIMB_COLS;
                 float lim = a.dist_max;
                 if (a.use_scale) lim = (r[12] != r[12]) ? r[12] : fmaxf(a.dist_max, r[12]);
-                const bool v = (r[8] < lim) && (r[0] > 0.f) && (r[4] > 0.f) && (r[3] > 0.f) &&
-                               (r[1] > 0.f) && (r[10] == r[10]);
-                s_valid[k] = v ? 1 : 0;
-            }
-            __syncthreads();
-            // ---- sort by limb score desc, ties by row asc (group.py:232, canonical stable):
-            //      rank of row k = number of valid rows that precede it; one warp per row,
-            //      lanes over the other rows, counted with ballots
+                return (r[8] < lim) && (r[0] > 0.f) && (r[4] > 0.f) && (r[3] > 0.f) && (r[1] > 0.f) &&
+                       (r[10] == r[10]);
+            };
+            // ---- A. sort the valid rows by limb score desc, ties by row asc (group.py:232,
+            //         canonical stable): one warp per row, lanes over the other rows, ballots
             for (int k = wid; k < K; k += nwarps) {
-                if (!s_valid[k]) continue;                         // warp-uniform
+                if (!row_valid(k)) continue;                       // warp-uniform
                 const float sc = s_conn[k * OG_LIMB_COLS + 10];
                 int rank = 0;
                 for (int j0 = 0; j0 < K; j0 += 32) {
                     const int j = j0 + lane;
                     bool before = false;
-                    if (j < K && s_valid[j]) {
+                    if (j < K && row_valid(j)) {
                         const float sj = s_conn[j * OG_LIMB_COLS + 10];
                         before = sj > sc || (sj == sc && j < k);
                     }
@@ -230,34 +234,42 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, float *__restrict__ o
                 }
             }
             __syncthreads();
-            const int nvalid = s_flag[kNValid];
-            // ---- keep the best row per to-joint id (group.py:233-239)
-            for (int r = wid; r < nvalid; r += nwarps) {
-                const int t = (int)s_conn[s_sorted[r] * OG_LIMB_COLS + 7];
-                bool dup = false;
-                for (int r0 = 0; r0 < r && !dup; r0 += 32) {
-                    const int r2 = r0 + lane;
-                    const bool same = r2 < r && (int)s_conn[s_sorted[r2] * OG_LIMB_COLS + 7] == t;
-                    dup = __any_sync(0xffffffffu, same);
+            // ---- B. warp 0: keep the best row per to-joint id (group.py:233-239), compact,
+            //         stage the kept rows' ids / scores
+            if (wid == 0) {
+                const int nvalid = s_flag[kNValid];
+                int kept = 0;
+                for (int r0 = 0; r0 < nvalid; r0 += 32) {
+                    const int r = r0 + lane;
+                    const int k = r < nvalid ? s_sorted[r] : 0;
+                    const int t = r < nvalid ? (int)s_conn[k * OG_LIMB_COLS + 7] : -2;
+                    bool dup = false;
+                    for (int j = 0; j < kept && !dup; ++j) dup = (s_kind2[j] == t);     // earlier chunks
+                    for (int q = 0; q < 31; ++q) {                                      // this chunk
+                        const int tq = __shfl_sync(0xffffffffu, t, q);
+                        dup = dup || (q < lane && tq == t);
+                    }
+                    const bool keep = r < nvalid && !dup;
+                    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+                    if (keep) {
+                        const int j = kept + __popc(mask & ((1u << lane) - 1u));
+                        s_kept[j] = k;
+                        s_kind1[j] = (int)s_conn[k * OG_LIMB_COLS + 6];
+                        s_kind2[j] = t;
+                        s_kscore[j] = s_conn[k * OG_LIMB_COLS + 10];
+                        s_n1[j] = 0;
+                        s_n2[j] = 0;
+                    }
+                    kept += __popc(mask);
+                    __syncwarp();
                 }
-                if (lane == 0) s_keep[r] = dup ? 0 : 1;
+                if (lane == 0) s_flag[kNKept] = kept;
             }
             __syncthreads();
-            const int kk = block_scan(nvalid, [&](int r) { return s_keep[r] != 0; }, s_pos, s_warp);
-            for (int r = tid; r < nvalid; r += T) {
-                if (!s_keep[r]) continue;
-                const int j = s_pos[r], k = s_sorted[r];
-                s_kept[j] = k;
-                s_kind1[j] = (int)s_conn[k * OG_LIMB_COLS + 6];
-                s_kind2[j] = (int)s_conn[k * OG_LIMB_COLS + 7];
-                s_kscore[j] = s_conn[k * OG_LIMB_COLS + 10];
-                s_n1[j] = 0;
-                s_n2[j] = 0;
-            }
-            __syncthreads();
+            const int kk = s_flag[kNKept];
             if (kk == 0) continue;                                         // group.py:84-85
 
-            // ---- match persons x kept limbs on the pre-update snapshot (group.py:87-109)
+            // ---- C. match persons x kept limbs on the pre-update snapshot (group.py:87-109)
             for (int m = tid; m < mm; m += T) {
                 const int row = s_order[m];
                 const int idf = ids[row * C + jf], idt = ids[row * C + jt];
@@ -278,11 +290,13 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, float *__restrict__ o
                 }
                 s_pk1[m] = (int16_t)k1;
                 s_pk2[m] = (int16_t)k2;
+                s_blast[m] = -1;
+                s_del[m] = 0;
                 if (k1 >= 0) s_flag[kAnyP1] = 1;
                 if (k2 >= 0) s_flag[kAnyP2] = 1;
             }
             __syncthreads();
-            // ---- apply: both ends known (group.py:114-119), then one end known (:124-135)
+            // ---- D. apply: both ends known (group.py:114-119), then one end known (:124-135)
             for (int m = tid; m < mm; m += T) {
                 const int row = s_order[m];
                 const int k2 = s_pk2[m];
@@ -304,14 +318,9 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, float *__restrict__ o
                 }
             }
             __syncthreads();
-            // ---- merge persons sharing exactly two keypoint ids (group.py:140-155)
+            // ---- E. merge persons sharing exactly two keypoint ids (group.py:140-155)
             int mm_after = mm;
             if (mm >= 2) {
-                for (int p = tid; p < mm; p += T) {
-                    s_blast[p] = -1;
-                    s_del[p] = 0;
-                }
-                __syncthreads();
                 for (int p = wid; p < mm; p += nwarps) {      // one warp per person, lanes over joints
                     const int rowa = s_order[p];
                     int ida[(OG_MAX_KEYPOINTS + 31) / 32];
@@ -358,29 +367,33 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, float *__restrict__ o
                     s_order2 = tmp;
                 }
             }
-            // ---- unclaimed limbs start new persons (group.py:166-177)
-            {
+            // ---- F. warp 0: unclaimed limbs start new persons (group.py:166-177), column-sum
+            //         rule with its (-1) + (+1) cancellation
+            if (wid == 0) {
                 const int w2 = s_flag[kAnyP2] ? -1 : 2;
                 const int w1 = s_flag[kAnyP1] ? -1 : 1;
-                for (int j = tid; j < kk; j += T) s_isnew[j] = (s_n2[j] * w2 + s_n1[j] * w1 == 0) ? 1 : 0;
+                int nnew = 0;
+                for (int j0 = 0; j0 < kk; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool isnew = j < kk && (s_n2[j] * w2 + s_n1[j] * w1 == 0);
+                    const unsigned mask = __ballot_sync(0xffffffffu, isnew);
+                    if (isnew) s_sorted[nnew + __popc(mask & ((1u << lane) - 1u))] = j;   // new list
+                    nnew += __popc(mask);
+                }
+                if (lane == 0) s_flag[kNNew] = nnew;
             }
             __syncthreads();
-            const int nnew = block_scan(kk, [&](int j) { return s_isnew[j] != 0; }, s_pos, s_warp);
+            const int nnew = s_flag[kNNew];
             if (nalloc + nnew > pcap) {
                 overflow = true;          // uniform: restart this image on the global slab
                 continue;
             }
-            for (int j = tid; j < kk; j += T) {
-                if (!s_isnew[j]) continue;
-                s_sorted[s_pos[j]] = j;                        // s_sorted is free now: new list
-                s_order[mm_after + s_pos[j]] = (int16_t)(nalloc + s_pos[j]);
-            }
-            __syncthreads();
             for (int e = tid; e < nnew * C; e += T) {
                 const int q = e / C, c = e - q * C;
                 const int j = s_sorted[q];
                 const int at = (nalloc + q) * C + c;
                 const float *r = s_conn + s_kept[j] * OG_LIMB_COLS;
+                if (c == 0) s_order[mm_after + q] = (int16_t)(nalloc + q);
                 if (c == jt) {
                     ids[at] = s_kind2[j];
                     xyvs[at] = make_float4(r[3], r[4], r[5], r[12]);
@@ -399,6 +412,7 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, float *__restrict__ o
             mm = mm_after + nnew;
             __syncthreads();
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         if (!overflow) break;
     }
 

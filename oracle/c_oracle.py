@@ -18,6 +18,8 @@ def load():
         _lib = ctypes.CDLL(path)
         _lib.oc_num_threads.restype = ctypes.c_int
         _lib.oc_group_image.restype = ctypes.c_int
+        # torchrun exports OMP_NUM_THREADS=1; the CPU baseline uses every host core
+        _lib.oc_set_num_threads(ctypes.c_int(os.cpu_count() or 1))
     return _lib
 
 

@@ -31,6 +31,14 @@
 #define LIMB_COLS 13
 #define POSE_COLS 6
 
+void oc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
