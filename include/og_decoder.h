@@ -193,6 +193,10 @@ int64_t og_launch_count(const og_handle *h);
  * therefore stay valid until og_fetch_poses returns.  og_set_fused(h, 0) disables the fused
  * path; og_fused_redo_count reports how many batches were re-run. */
 int og_set_fused(og_handle *h, int enable);
+
+/* K3 runs a one-warp-per-image kernel first and the one-CTA-per-image kernel only for images
+ * with more than 64 partial persons; og_set_warp_grouping(h, 0) uses the CTA kernel for all. */
+int og_set_warp_grouping(og_handle *h, int enable);
 int64_t og_fused_redo_count(const og_handle *h);
 
 /* Per-stage device timing of og_decode_* calls with CUDA events recorded on the
