@@ -194,9 +194,9 @@ int64_t og_launch_count(const og_handle *h);
  * path; og_fused_redo_count reports how many batches were re-run. */
 int og_set_fused(og_handle *h, int enable);
 
-/* K3 runs a one-warp-per-image kernel first and the one-CTA-per-image kernel only for images
- * with more than 64 partial persons; og_set_warp_grouping(h, 0) uses the CTA kernel for all. */
-int og_set_warp_grouping(og_handle *h, int enable);
+/* Development aid: per-phase clock64() totals of the K3 CTA kernel; only in builds with
+ * -DOG_K3_PROFILE (returns OG_ERR_UNSUPPORTED otherwise). */
+int og_debug_k3_profile(uint64_t *out16, int reset);
 int64_t og_fused_redo_count(const og_handle *h);
 
 /* Per-stage device timing of og_decode_* calls with CUDA events recorded on the

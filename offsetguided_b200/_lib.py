@@ -69,7 +69,7 @@ SIGNATURES = {
     'og_copy_intermediates': (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     'og_launch_count': (ctypes.c_int64, [_vp]),
     'og_set_fused': (_i, [_vp, _i]),
-    'og_set_warp_grouping': (_i, [_vp, _i]),
+    'og_debug_k3_profile': (_i, [ctypes.POINTER(ctypes.c_uint64), _i]),
     'og_fused_redo_count': (ctypes.c_int64, [_vp]),
     'og_enable_stage_timing': (_i, [_vp, _i]),
     'og_last_stage_times_ms': (_i, [_vp, c_float_p]),

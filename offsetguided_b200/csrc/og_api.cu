@@ -112,7 +112,7 @@ struct og_handle {
     DevBuf<int32_t> det_count;
     DevBuf<float> limbs;
     DevBuf<float> slab;
-    DevBuf<int32_t> needs_cta;
+    DevBuf<int32_t> group_prep;
     DevBuf<float> fused_hmp, fused_off;     // materialising path only
     DevBuf<float> hr_hmp, hr_off;
     DevBuf<int32_t> kp_flip, limb_flip;
@@ -126,7 +126,6 @@ struct og_handle {
     int fetched_slot;            // slot of the most recently fetched result (stage times)
     int rows_hint;
 
-    bool warp_group;             // K3: one-warp-per-image kernel first, CTA kernel for the rest
     bool fused_enabled;
     int64_t fused_redos;
     bool tables_valid;           // device flip tables match the cached host copies
@@ -205,11 +204,8 @@ int run_k3(og_handle *h, const float *limbs, int n, float *out_poses, int capaci
     g.smem_rows = h->smem_rows;
     g.slab = nullptr;
     g.slab_stride = 0;
-    g.needs_cta = nullptr;
-    if (h->warp_group) {
-        OG_TRY(h->needs_cta.ensure(n));
-        g.needs_cta = h->needs_cta.ptr;
-    }
+    OG_TRY(h->group_prep.ensure(group_prep_ints(g)));
+    g.prep = h->group_prep.ptr;
     const int pmax = c.n_limbs * c.topk;
     if (h->smem_rows < pmax) {
         g.slab_stride = ((size_t)pmax * c.n_keypoints * 6 + 3) / 4 * 4;
@@ -218,7 +214,7 @@ int run_k3(og_handle *h, const float *limbs, int n, float *out_poses, int capaci
     }
     if (zero_total) OG_CUDA_TRY(cudaMemsetAsync(out_total, 0, sizeof(int32_t), s));
     OG_TRY(launch_group(g, limbs, out_poses, capacity_rows, out_offset, out_count, out_total, s));
-    h->launches += g.needs_cta ? 2 : 1;
+    h->launches += 2;       // prepare + grouping
     return OG_OK;
 }
 
@@ -496,9 +492,7 @@ int og_create(const og_config *cfg, og_handle **out) {
     g.smem_rows = rows;
     h->smem_rows = rows;
     h->group_smem = group_smem_bytes(g);
-    const size_t warp_smem = group_warp_smem_bytes(g);
-    h->warp_group = warp_smem <= budget;
-    int st = prepare_group_kernel(h->group_smem, h->warp_group ? warp_smem : 0);
+    int st = prepare_group_kernel(h->group_smem);
     if (st != OG_OK) {
         delete h;
         return st;
@@ -525,7 +519,7 @@ int og_destroy(og_handle *h) {
     h->det_count.release();
     h->limbs.release();
     h->slab.release();
-    h->needs_cta.release();
+    h->group_prep.release();
     h->fused_hmp.release();
     h->fused_off.release();
     h->hr_hmp.release();
@@ -774,10 +768,9 @@ int og_set_fused(og_handle *h, int enable) {
 
 int64_t og_fused_redo_count(const og_handle *h) { return h ? h->fused_redos : 0; }
 
-int og_set_warp_grouping(og_handle *h, int enable) {
-    OG_REQUIRE(h, "og_set_warp_grouping: null handle");
-    h->warp_group = enable != 0;
-    return OG_OK;
+int og_debug_k3_profile(uint64_t *out16, int reset) {
+    OG_REQUIRE(out16, "og_debug_k3_profile: null pointer");
+    return read_k3_profile(reinterpret_cast<unsigned long long *>(out16), reset != 0);
 }
 
 int og_enable_stage_timing(og_handle *h, int enable) {

@@ -114,11 +114,12 @@ struct GroupLaunch {
     int smem_rows;              // person-table rows kept in shared memory
     float *slab;                // global person tables, one per image (fallback)
     size_t slab_stride;         // floats between images, multiple of 4
-    int32_t *needs_cta;         // [n] scratch flags; nullptr = CTA kernel only
+    int32_t *prep;              // scratch of group_prep_ints() ints: kept limb rows per (image, limb)
 };
+int read_k3_profile(unsigned long long *out16, bool reset);
 size_t group_smem_bytes(const GroupLaunch &g);
-size_t group_warp_smem_bytes(const GroupLaunch &g);
-int prepare_group_kernel(size_t smem_bytes, size_t warp_smem_bytes);
+size_t group_prep_ints(const GroupLaunch &g);
+int prepare_group_kernel(size_t smem_bytes);
 int launch_group(const GroupLaunch &g, const float *limbs, float *out_poses, int capacity_rows,
                  int32_t *out_offset, int32_t *out_count, int32_t *out_total, cudaStream_t s);
 

@@ -221,10 +221,6 @@ class DecoderEngine(object):
         """Enable / disable the fused network-resolution path of decode_features."""
         _lib.check(self.lib.og_set_fused(self._h, 1 if on else 0))
 
-    def set_warp_grouping(self, on=True):
-        """K3: warp-per-image kernel first (default) or the CTA-per-image kernel for all."""
-        _lib.check(self.lib.og_set_warp_grouping(self._h, 1 if on else 0))
-
     @property
     def fused_redo_count(self):
         return int(self.lib.og_fused_redo_count(self._h))

@@ -46,7 +46,7 @@ def main():
     h2, o2 = scenes.synth_hires_batch(2000, 8, 20, 640, 640, skel)
     h2 = torch.from_numpy(h2).cuda().repeat(4, 1, 1, 1).contiguous()
     o2 = torch.from_numpy(o2).cuda().repeat(4, 1, 1, 1).contiguous()
-    for path in sorted(glob.glob(os.path.join(ROOT, 'build', 'k3_variants', '*.so'))):
+    for path in sorted(glob.glob(os.path.join(ROOT, 'build', 'k3_sweep', '*.so'))):
         print(json.dumps(run(path, '64 img x 6 persons K=32', h1, o1, skel, 17, 32)))
         print(json.dumps(run(path, '32 img x 20 persons K=64', h2, o2, skel, 17, 64)))
 

@@ -155,10 +155,6 @@ def test_k3_group_fuzz_bit_exact(cuda_device):
         assert got.dtype == np.float32
         assert got.shape == c['poses'].shape, f'case {ci}: person count {got.shape} vs {c["poses"].shape}'
         assert np.array_equal(got, c['poses']), f'case {ci}'
-        # the same through the one-CTA-per-image kernel alone
-        g._engine(c['limbs'].shape[1]).set_warp_grouping(False)
-        got = g.group_skeletons(c['limbs'])
-        assert got.shape == c['poses'].shape and np.array_equal(got, c['poses']), f'case {ci} (CTA kernel)'
 
 
 @pytest.mark.parametrize('name', ['limbs_coco_a', 'limbs_coco_noise', 'limbs_crowdpose'])
@@ -193,9 +189,6 @@ def test_k3_random_tables_against_oracle(cuda_device):
         got = g.group_skeletons(limbs)
         ref = ro.group_skeletons(limbs, skel, 17, 0.06, 2, 40, True)
         assert got.shape == ref.shape and np.array_equal(got, ref), f'case {case} k={k} pool={pool}'
-        g._engine(k).set_warp_grouping(False)
-        got = g.group_skeletons(limbs)
-        assert got.shape == ref.shape and np.array_equal(got, ref), f'case {case} k={k} pool={pool} (CTA)'
 
 
 def test_k3_empty_and_degenerate(cuda_device):
