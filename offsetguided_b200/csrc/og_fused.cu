@@ -36,6 +36,8 @@ fused_nms_candidates_kernel(const float *__restrict__ hmp, const int32_t *__rest
     __shared__ float s_yw[TAPS][YH];
     __shared__ int s_xb[XW];
     __shared__ int s_yb[YH];
+    __shared__ float s_am[LH][LW + 1];
+    __shared__ uint8_t s_act[kTileH][kTileW];
 
     const int tid = threadIdx.x;
     const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
@@ -53,6 +55,7 @@ fused_nms_candidates_kernel(const float *__restrict__ hmp, const int32_t *__rest
     const float *a = hmp + ((size_t)n * C + c) * h * w;
     const float *b = nullptr;
     if (kFlip) b = hmp + ((size_t)(N + n) * C + kp_flip[c]) * h * w;
+    float tile_amax = 0.0f;
     for (int i = tid; i < LH * LW; i += kFusedThreads) {
         const int ly = i / LW, lx = i - ly * LW;
         const int gy = min(max(cy0 - HALO + ly, 0), h - 1);
@@ -60,8 +63,17 @@ fused_nms_candidates_kernel(const float *__restrict__ hmp, const int32_t *__rest
         float v = __ldg(a + gy * w + gx);
         if (kFlip) v = __fmul_rn(__fadd_rn(v, __ldg(b + gy * w + (w - 1 - gx))), 0.5f);
         s_lo[ly][lx] = v;
+        tile_amax = fmaxf(tile_amax, fabsf(v));
     }
-    // 2. tap tables of the full-resolution columns / rows this tile produces
+    // Threshold first, at network resolution: an interpolated value is bounded by
+    // (sum |wx|)(sum |wy|) max|taps| <= 1.375^2 max|taps| for the A = -0.75 cubic (1 for
+    // bilinear), so a tile (or, below, a cell) whose taps are all < thre / kBound cannot hold
+    // a candidate and is skipped; kBound leaves 3 % for rounding.  Nothing else is skipped.
+    constexpr float kBound = kCubic ? 1.95f : 1.001f;
+    if (!__syncthreads_or(tile_amax * kBound >= thre)) return;
+
+    // 2. tap tables of the full-resolution columns / rows this tile produces, and the
+    //    (2 HALO + 1)^2 neighbourhood maximum of |cell| (the taps a cell's pixels can touch)
     const float inv = 1.0f / (float)S;
     for (int j = tid; j < XW + YH; j += kFusedThreads) {
         float wt[4];
@@ -78,14 +90,34 @@ fused_nms_candidates_kernel(const float *__restrict__ hmp, const int32_t *__rest
             for (int t = 0; t < TAPS; ++t) s_yw[t][jj] = wt[t];
         }
     }
+    for (int i = tid; i < LH * LW; i += kFusedThreads) {          // horizontal window maximum
+        const int ly = i / LW, lx = i - ly * LW;
+        float m = 0.0f;
+        for (int dx = -HALO; dx <= HALO; ++dx) {
+            const int xx = min(max(lx + dx, 0), LW - 1);
+            m = fmaxf(m, fabsf(s_lo[ly][xx]));
+        }
+        s_am[ly][lx] = m;
+    }
     __syncthreads();
-    // 3. interpolate every tile row along x
-    for (int i = tid; i < LH * XW; i += kFusedThreads) {
-        const int ly = i / XW, j = i - ly * XW;
-        const float *row = &s_lo[ly][s_xb[j]];
-        s_hb[ly][j] = kCubic ? combine4(row[0], row[1], row[2], row[3], s_xw[0][j], s_xw[1][j],
-                                        s_xw[TAPS - 2][j], s_xw[TAPS - 1][j])
-                             : combine2(row[0], row[1], s_xw[0][j], s_xw[1][j]);
+    // 3. interpolate every tile row along x: one thread per output column, taps in registers
+    for (int j = tid; j < XW; j += kFusedThreads / 2) {
+        if (tid >= kFusedThreads / 2) break;
+        const int xb = s_xb[j];
+        const float w0 = s_xw[0][j], w1 = s_xw[1][j], w2 = s_xw[TAPS - 2][j], w3 = s_xw[TAPS - 1][j];
+        for (int ly = 0; ly < LH; ++ly) {
+            const float *row = &s_lo[ly][xb];
+            s_hb[ly][j] = kCubic ? combine4(row[0], row[1], row[2], row[3], w0, w1, w2, w3)
+                                 : combine2(row[0], row[1], w0, w1);
+        }
+    }
+    if (tid >= kFusedThreads / 2) {                                // meanwhile: vertical window maximum
+        for (int i = tid - kFusedThreads / 2; i < kTileH * kTileW; i += kFusedThreads / 2) {
+            const int cy = i / kTileW, cx = i - cy * kTileW;
+            float m = 0.0f;
+            for (int dy = 0; dy <= 2 * HALO; ++dy) m = fmaxf(m, s_am[cy + dy][cx + HALO]);
+            s_act[cy][cx] = (m * kBound >= thre) ? 1 : 0;
+        }
     }
     __syncthreads();
 
@@ -96,9 +128,10 @@ fused_nms_candidates_kernel(const float *__restrict__ hmp, const int32_t *__rest
                                  s_yw[TAPS - 2][jy], s_yw[TAPS - 1][jy])
                       : combine2(s_hb[yb][jx], s_hb[yb + 1][jx], s_yw[0][jy], s_yw[1][jy]);
     };
-    // 4. full-resolution values, threshold first; the 3x3 test only for the few survivors.
-    //    A warp owns whole cell rows: the S output rows of a cell row share TAPS + 1 rows of
-    //    s_hb and their tap tables stay in registers while the lanes sweep the columns.
+    // 4. full-resolution values of the active cells, threshold first; the 3x3 test only for
+    //    the few survivors.  A warp owns whole cell rows: the S output rows of a cell row share
+    //    TAPS + 1 rows of s_hb and their tap tables stay in registers while the lanes sweep the
+    //    columns.
     constexpr int kWarps = kFusedThreads / 32;
     constexpr int kRowsPerWarp = kTileH / kWarps;
     static_assert(kTileH % kWarps == 0, "tile rows must split evenly over the warps");
@@ -120,7 +153,9 @@ fused_nms_candidates_kernel(const float *__restrict__ hmp, const int32_t *__rest
 #pragma unroll 1
         for (int jx = lane + 1; jx <= S * kTileW; jx += 32) {
             const int X = S * cx0 + jx - 1;
-            if (X >= W) break;
+            const bool active = X < W && s_act[cy][(jx - 1) / S] != 0;
+            if (!__any_sync(0xffffffffu, active)) continue;
+            if (!active) continue;
             float r[TAPS + 1];
 #pragma unroll
             for (int t = 0; t <= TAPS; ++t) r[t] = s_hb[min(yb0 + t, LH - 1)][jx];
@@ -128,14 +163,16 @@ fused_nms_candidates_kernel(const float *__restrict__ hmp, const int32_t *__rest
             for (int p = 0; p < S; ++p) {
                 const int Y = S * (cy0 + cy) + p;
                 if (Y >= H) break;
-                const bool up = yoff[p] != 0;
                 float v;
-                if (kCubic)
-                    v = combine4(up ? r[1] : r[0], up ? r[2] : r[1], up ? r[TAPS - 1] : r[TAPS - 2],
-                                 up ? r[TAPS] : r[TAPS - 1], wv[p][0], wv[p][1], wv[p][TAPS - 2],
-                                 wv[p][TAPS - 1]);
-                else
-                    v = combine2(up ? r[1] : r[0], up ? r[2] : r[1], wv[p][0], wv[p][1]);
+                if (yoff[p] != 0) {              // warp-uniform
+                    v = kCubic ? combine4(r[1], r[2], r[TAPS - 1], r[TAPS], wv[p][0], wv[p][1],
+                                          wv[p][TAPS - 2], wv[p][TAPS - 1])
+                               : combine2(r[1], r[2], wv[p][0], wv[p][1]);
+                } else {
+                    v = kCubic ? combine4(r[0], r[1], r[TAPS - 2], r[TAPS - 1], wv[p][0], wv[p][1],
+                                          wv[p][TAPS - 2], wv[p][TAPS - 1])
+                               : combine2(r[0], r[1], wv[p][0], wv[p][1]);
+                }
                 if (v >= thre) {
                     const int jy = cy * S + p + 1;
                     bool peak = true;      // zero padding outside the image: v >= thre > 0 wins
