@@ -18,7 +18,10 @@ namespace og {
 namespace {
 
 constexpr int kTileW = 32;       // low-resolution cells per tile
-constexpr int kTileH = 16;
+#ifndef OG_K1F_TILE_H
+#define OG_K1F_TILE_H 16
+#endif
+constexpr int kTileH = OG_K1F_TILE_H;
 constexpr int kFusedThreads = 256;
 
 template <int S, bool kCubic, bool kFlip>

@@ -443,3 +443,80 @@ def test_two_decodes_in_flight(cuda_device):
     assert t_a['k1_stream'] > 0 and t_a['k3'] > 0
     with pytest.raises(_lib.OgError):
         eng.fetch(1)
+
+
+# --------------------------------------------------------------------------- BASELINE sizes
+def _pose_lists_equal(got, ref):
+    assert len(got) == len(ref)
+    for p, r in zip(got, ref):
+        gio.compare_poses(p, r, rtol=RTOL)
+
+
+def test_bench_workload_batch64_matches_c_oracle(cuda_device):
+    """The bench workload itself (BASELINE configs[1] settings, batch 64, flip-test fusion,
+    160x160 -> 640x640) decoded through the reference-facing API from pinned host maps, every
+    image compared with the C oracle: person count / order, x, y, ids exact, scores 1e-5."""
+    import bench
+    from oracle import c_oracle as co
+    hmp, omp = bench.lowres_inputs(5000, 64, 640, True)
+    pp = decoder.decoder_factory(_args(topk=32, thre_hmp=0.04, person_thre=0.04, dist_max=40.0, batch_size=64))
+    feats = [[[torch.from_numpy(hmp).pin_memory()], [[]], [[]]], [[torch.from_numpy(omp).pin_memory()], [[]], [[]]]]
+    got = pp.generate_poses(feats, flip_test=True)
+    eng = pp._engine(torch.device('cuda', 0))
+    assert eng.fused_redo_count == 0
+    ds, di, lb = [t.cpu().numpy() for t in eng.last_intermediates(64)]
+    skel = cfg.COCO_PERSON_SKELETON
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel)
+    ref, ref_limbs = co.generate_poses(hmp, omp, skel, 17, topk=32, thre_hmp=0.04, min_len=0.5,
+                                       person_thre=0.04, dist_max=40.0, use_scale=True, flip_test=True,
+                                       kp_flips=cfg.heatmap_hflip(cfg.COCO_KEYPOINTS), limb_flips=fl,
+                                       limb_reserve=rs, return_limbs=True)
+    assert sum(len(p) for p in ref) >= 64 * 5
+    assert gio.compare_limbs(lb, ref_limbs, 0.04, rtol=RTOL) > 64 * 90
+    _pose_lists_equal(got, ref)
+    # the hot path on the materialised maps of the same batch gives the same persons
+    hm_f, om_f = co.flip_augment(hmp, omp, cfg.heatmap_hflip(cfg.COCO_KEYPOINTS), fl, rs)
+    heat = torch.from_numpy(co.resize(hm_f[:16], 4, 'bicubic')).cuda()
+    offs = torch.from_numpy(co.resize(om_f[:16], 4, 'bilinear')).cuda()
+    hot = DecoderEngine(17, skel, topk=32, thre_hmp=0.04, min_len=0.5, dist_max=40, use_scale=True,
+                        person_thre=0.04).decode_maps(heat, offs)
+    for p, r in zip(hot, got[:16]):
+        assert np.array_equal(p, r)
+
+
+def test_config4_1024_long_edge(cuda_device):
+    """BASELINE config 4 sizes: 256x256 maps -> 1024x1024, ids of the last channels exceed 2**24
+    and are stored as rounded float32 exactly like the reference (collect.py:227-228)."""
+    from oracle import c_oracle as co
+    skel = cfg.COCO_PERSON_SKELETON
+    n = 4
+    hmp, omp = scenes.render_batch(4242, n, 8, 1024, 1024, skel, noise=0.02, scale_range=(16.0, 38.0))
+    eng = DecoderEngine(17, skel, topk=32, thre_hmp=0.04, min_len=0.5, dist_max=40, use_scale=True,
+                        person_thre=0.04)
+    got = eng.decode_features(torch.from_numpy(hmp).cuda(), torch.from_numpy(omp).cuda(), 4, 4, 'bicubic')
+    _, _, lb = eng.last_intermediates(n)
+    ref, ref_limbs = co.generate_poses(hmp, omp, skel, 17, topk=32, thre_hmp=0.04, min_len=0.5,
+                                       person_thre=0.04, dist_max=40.0, use_scale=True, return_limbs=True)
+    assert gio.compare_limbs(lb.cpu().numpy(), ref_limbs, 0.04, rtol=RTOL) > n * 100
+    _pose_lists_equal(got, ref)
+    ids = np.concatenate([p[..., 5].ravel() for p in got])
+    assert ids.max() > 2 ** 24
+    eng.set_fused(False)
+    staged = eng.decode_features(torch.from_numpy(hmp).cuda(), torch.from_numpy(omp).cuda(), 4, 4, 'bicubic')
+    for a, b in zip(got, staged):
+        assert np.array_equal(a, b)
+
+
+def test_config3_crowdpose_batch32(cuda_device):
+    """BASELINE config 3: 14 keypoints, builder-supplied skeleton, 20 persons, K = 64, batch 32."""
+    from oracle import c_oracle as co
+    skel = cfg.CROWDPOSE_PERSON_SKELETON
+    hmp, omp = scenes.render_batch(777, 32, 20, 512, 512, skel, template=scenes.TEMPLATE_CROWDPOSE,
+                                   noise=0.02, scale_range=(7.0, 16.0))
+    eng = DecoderEngine(14, skel, topk=64, thre_hmp=0.06, min_len=0.5, dist_max=40, use_scale=True,
+                        person_thre=0.06)
+    got = eng.decode_features(torch.from_numpy(hmp).cuda(), torch.from_numpy(omp).cuda(), 4, 4, 'bicubic')
+    ref = co.generate_poses(hmp, omp, skel, 14, topk=64, thre_hmp=0.06, min_len=0.5, person_thre=0.06,
+                            dist_max=40.0, use_scale=True)
+    assert sum(len(p) for p in ref) > 32 * 15
+    _pose_lists_equal(got, ref)
