@@ -111,6 +111,14 @@ int og_limb_score_f32(og_handle *h, const float *det_score_dev, const int32_t *d
                       const float *offs_dev, const float *scales_dev,
                       int n, int hgt, int w, float *out_limbs_dev, void *stream);
 
+/* generate_limbs with the optional heads (collect.py:127-138, 158-165, 213-218):
+ * jomps_dev [n, 2, h, w] jitter-offset maps or NULL, use_jitter = --use-jitter-offset,
+ * vector_nd = 4 for the cat_flip_offs offsets ([n, 4L, h, w], factory.py:115-127). */
+int og_limb_score_ex_f32(og_handle *h, const float *det_score_dev, const int32_t *det_index_dev,
+                         const float *offs_dev, const float *scales_dev, const float *jomps_dev,
+                         int vector_nd, int use_jitter, int n, int hgt, int w, float *out_limbs_dev,
+                         void *stream);
+
 /* ---- decoder/group.py ---------------------------------------------------- */
 
 /* group_skeletons for n images (K3, one CTA per image).  limbs_dev [n, L, K, 13].
@@ -136,6 +144,18 @@ int og_flip_fuse_f32(og_handle *h, const float *hmp2n_dev, const float *off2n_de
                      const int32_t *limb_reserve, int n_reserve,
                      int n, int hgt, int w, float *out_hmp_dev, float *out_off_dev, void *stream);
 
+/* Flip fusion of a generic map stack (heat, scale, jitter maps; factory.py:101-113, 141-144):
+ * out[i, c] = (in[i, c] + sign * flip_W(in[n + i, perm[c]])) / 2, perm = NULL for identity,
+ * sign = -1 on even channels when negate_even (x components of jitter maps). */
+int og_flip_average_f32(const float *in2n_dev, const int32_t *perm, int negate_even, int n, int ch,
+                        int hgt, int w, float *out_dev, void *stream);
+
+/* flip_augment, cat_flip_offs branch (factory.py:115-127): out_dev [n, 4L, h, w] holds
+ * (x, y, x_flip, y_flip) per limb; reserved limbs repeat their original vector. */
+int og_flip_cat_offsets_f32(const float *off2n_dev, const int32_t *limb_flip,
+                            const int32_t *limb_reserve, int n_reserve, int n, int n_limbs, int hgt,
+                            int w, float *out_dev, void *stream);
+
 /* F.interpolate(scale_factor=scale, align_corners=False) (factory.py:74-78);
  * mode 0 = bilinear, 1 = bicubic (A = -0.75). in [planes, h, w] -> out [planes, h*s, w*s]. */
 int og_resize_f32(const float *in_dev, float *out_dev, int planes, int hgt, int w,
@@ -148,6 +168,11 @@ int og_resize_f32(const float *in_dev, float *out_dev, int planes, int hgt, int 
  * into pinned memory of the handle.  Returns immediately; og_fetch_poses() synchronises. */
 int og_decode_maps(og_handle *h, const float *heat_dev, const float *offs_dev,
                    const float *scales_dev, int n, int hgt, int w, void *stream);
+
+/* og_decode_maps with the optional heads of og_limb_score_ex_f32. */
+int og_decode_maps_ex(og_handle *h, const float *heat_dev, const float *offs_dev,
+                      const float *scales_dev, const float *jomps_dev, int vector_nd, int use_jitter,
+                      int n, int hgt, int w, void *stream);
 
 /* PostProcess.generate_poses on NETWORK-RESOLUTION maps held in HOST memory:
  * H2D copy, optional flip fusion (hmp_host has 2n images then), x stride resize

@@ -54,11 +54,15 @@ SIGNATURES = {
     'og_topk_channel_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'og_nms_topk_f32': (_i, [_vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _vp, _vp, _vp]),
     'og_limb_score_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    'og_limb_score_ex_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'og_group_f32': (_i, [_vp, _vp, _i, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp]),
     'og_scored_offset_f32': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     'og_flip_fuse_f32': (_i, [_vp, _vp, _vp, c_int32_p, c_int32_p, c_int32_p, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'og_flip_average_f32': (_i, [_vp, c_int32_p, _i, _i, _i, _i, _i, _vp, _vp]),
+    'og_flip_cat_offsets_f32': (_i, [_vp, c_int32_p, c_int32_p, _i, _i, _i, _i, _i, _vp, _vp]),
     'og_resize_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'og_decode_maps': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'og_decode_maps_ex': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'og_decode_features_host': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i,
                                      c_int32_p, c_int32_p, c_int32_p, _i, _vp]),
     'og_decode_features_dev': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i,

@@ -228,7 +228,7 @@ struct K1Fused {
 // network-resolution kernel) -> K2 -> K3 -> asynchronous D2H into the slot.
 int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused *fused,
                 const float *offs, const OffsetSource *offs_lowres, const float *scales, int n,
-                int hgt, int w, cudaStream_t s) {
+                int hgt, int w, cudaStream_t s, const LimbExtras *extras = nullptr) {
     const og_config &c = h->cfg;
     OG_TRY(check_maps(n, hgt, w, c.n_keypoints));
     const size_t dets = (size_t)n * c.n_keypoints * c.topk;
@@ -272,8 +272,8 @@ int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused
                           h->det_count.ptr, s, h->timing ? slot->ev[2] : nullptr));
         }
         OG_TRY(mark(h, slot, 3, s));
-        OG_TRY(launch_limb_score(h->det_score.ptr, h->det_index.ptr, offs, offs_lowres, scales, n,
-                                 c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp,
+        OG_TRY(launch_limb_score(h->det_score.ptr, h->det_index.ptr, offs, offs_lowres, scales, extras,
+                                 n, c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp,
                                  c.min_len, c.resize_factor, h->limbs.ptr, s));
         h->launches += 1;
         OG_TRY(mark(h, slot, 4, s));
@@ -577,11 +577,65 @@ int og_limb_score_f32(og_handle *h, const float *det_score_dev, const int32_t *d
     OG_TRY(check_device(h));
     OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
     const og_config &c = h->cfg;
-    OG_TRY(launch_limb_score(det_score_dev, det_index_dev, offs_dev, nullptr, scales_dev, n, c.n_keypoints,
-                             c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp, c.min_len, c.resize_factor,
-                             out_limbs_dev, static_cast<cudaStream_t>(stream)));
+    OG_TRY(launch_limb_score(det_score_dev, det_index_dev, offs_dev, nullptr, scales_dev, nullptr, n,
+                             c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp, c.min_len,
+                             c.resize_factor, out_limbs_dev, static_cast<cudaStream_t>(stream)));
     h->launches += 1;
     return OG_OK;
+}
+
+int og_limb_score_ex_f32(og_handle *h, const float *det_score_dev, const int32_t *det_index_dev,
+                         const float *offs_dev, const float *scales_dev, const float *jomps_dev,
+                         int vector_nd, int use_jitter, int n, int hgt, int w, float *out_limbs_dev,
+                         void *stream) {
+    OG_REQUIRE(h && det_score_dev && det_index_dev && offs_dev && out_limbs_dev,
+               "og_limb_score_ex_f32: null pointer");
+    OG_REQUIRE(vector_nd == 2 || vector_nd == 4, "vector_nd must be 2 or 4");
+    OG_REQUIRE(!(vector_nd == 4 && jomps_dev && use_jitter),
+               "jitter refinement of 4-D offset vectors is undefined (it raises in the reference too)");
+    OG_TRY(check_device(h));
+    OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
+    const og_config &c = h->cfg;
+    LimbExtras ex = {jomps_dev, vector_nd, use_jitter};
+    OG_TRY(launch_limb_score(det_score_dev, det_index_dev, offs_dev, nullptr, scales_dev, &ex, n,
+                             c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp, c.min_len,
+                             c.resize_factor, out_limbs_dev, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return OG_OK;
+}
+
+int og_flip_average_f32(const float *in2n_dev, const int32_t *perm, int negate_even, int n, int ch,
+                        int hgt, int w, float *out_dev, void *stream) {
+    OG_REQUIRE(in2n_dev && out_dev, "og_flip_average_f32: null pointer");
+    OG_REQUIRE(n >= 0 && ch >= 1 && ch <= 128 && hgt > 0 && w > 0, "og_flip_average_f32: bad shape");
+    ChannelPerm p;
+    for (int i = 0; i < ch; ++i) {
+        p.src[i] = perm ? perm[i] : i;
+        OG_REQUIRE(p.src[i] >= 0 && p.src[i] < ch, "og_flip_average_f32: perm[%d] out of range", i);
+    }
+    return launch_flip_average(in2n_dev, out_dev, n, ch, hgt, w, p, negate_even != 0,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int og_flip_cat_offsets_f32(const float *off2n_dev, const int32_t *limb_flip,
+                            const int32_t *limb_reserve, int n_reserve, int n, int n_limbs, int hgt,
+                            int w, float *out_dev, void *stream) {
+    OG_REQUIRE(off2n_dev && out_dev && limb_flip, "og_flip_cat_offsets_f32: null pointer");
+    OG_REQUIRE(n >= 0 && n_limbs >= 1 && n_limbs <= OG_MAX_LIMBS && hgt > 0 && w > 0,
+               "og_flip_cat_offsets_f32: bad shape");
+    ChannelPerm lf, rs;
+    for (int i = 0; i < 128; ++i) rs.src[i] = 0;
+    for (int i = 0; i < n_limbs; ++i) {
+        lf.src[i] = limb_flip[i];
+        OG_REQUIRE(lf.src[i] >= 0 && lf.src[i] < n_limbs, "limb_flip[%d] out of range", i);
+    }
+    for (int i = 0; i < n_reserve; ++i) {
+        OG_REQUIRE(limb_reserve && limb_reserve[i] >= 0 && limb_reserve[i] < n_limbs,
+                   "limb_reserve[%d] out of range", i);
+        rs.src[limb_reserve[i]] = 1;
+    }
+    return launch_flip_cat_offsets(off2n_dev, out_dev, n, n_limbs, hgt, w, lf, rs,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 int og_group_f32(og_handle *h, const float *limbs_dev, int n, float *out_poses_dev,
@@ -640,6 +694,22 @@ int og_decode_maps(og_handle *h, const float *heat_dev, const float *offs_dev,
     slot->args = FeatureArgs{};
     return decode_core(h, slot, heat_dev, nullptr, offs_dev, nullptr, scales_dev, n, hgt, w,
                        static_cast<cudaStream_t>(stream));
+}
+
+int og_decode_maps_ex(og_handle *h, const float *heat_dev, const float *offs_dev,
+                      const float *scales_dev, const float *jomps_dev, int vector_nd, int use_jitter,
+                      int n, int hgt, int w, void *stream) {
+    OG_REQUIRE(h && (n == 0 || (heat_dev && offs_dev)), "og_decode_maps_ex: null pointer");
+    OG_REQUIRE(vector_nd == 2 || vector_nd == 4, "vector_nd must be 2 or 4");
+    OG_REQUIRE(!(vector_nd == 4 && jomps_dev && use_jitter),
+               "jitter refinement of 4-D offset vectors is undefined (it raises in the reference too)");
+    OG_TRY(check_device(h));
+    ResultSlot *slot = nullptr;
+    OG_TRY(acquire_slot(h, nullptr, &slot));
+    slot->args = FeatureArgs{};
+    LimbExtras ex = {jomps_dev, vector_nd, use_jitter};
+    return decode_core(h, slot, heat_dev, nullptr, offs_dev, nullptr, scales_dev, n, hgt, w,
+                       static_cast<cudaStream_t>(stream), &ex);
 }
 
 int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_dev, int n, int hgt,

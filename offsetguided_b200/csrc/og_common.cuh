@@ -93,11 +93,29 @@ struct OffsetSource {
     const uint8_t *limb_reserved;
 };
 
+// Optional variants of generate_limbs (collect.py:127-138, 158-165, 213-218 and vector_nd = 4).
+struct LimbExtras {
+    const float *jomps;     // [n, 2, H, W] jitter-offset maps at decode resolution, or nullptr
+    int vector_nd;          // 2, or 4 for cat_flip_offs offsets ([n, 4L, H, W])
+    int use_jitter;         // --use-jitter-offset
+};
+
 // `offs` = materialised full-resolution offsets, or nullptr with `lowres` set.
 int launch_limb_score(const float *det_score, const int32_t *det_index, const float *offs,
-                      const OffsetSource *lowres, const float *scales, int n, int c, int l, int k,
-                      int h, int w, const SkeletonDev &sk, float thre_hmp, float min_len,
-                      float resize_factor, float *out_limbs, cudaStream_t s);
+                      const OffsetSource *lowres, const float *scales, const LimbExtras *extras,
+                      int n, int c, int l, int k, int h, int w, const SkeletonDev &sk, float thre_hmp,
+                      float min_len, float resize_factor, float *out_limbs, cudaStream_t s);
+
+struct ChannelPerm {
+    int32_t src[128];
+};
+// out[n, c] = (a[n, c] + sign * flip_W(b[N + n, perm[c]])) / 2, sign = -1 on even channels if
+// negate_even (flip fusion of heat / scale / jitter maps, factory.py:101-113, 141-144)
+int launch_flip_average(const float *in2n, float *out, int n, int ch, int h, int w,
+                        const ChannelPerm &perm, bool negate_even, cudaStream_t s);
+// cat_flip_offs branch (factory.py:115-127): out [n, 4L, h, w] = (x, y, x_flip, y_flip) per limb
+int launch_flip_cat_offsets(const float *off2n, float *out, int n, int l, int h, int w,
+                            const ChannelPerm &limb_flip, const ChannelPerm &reserved, cudaStream_t s);
 
 bool fused_scale_supported(int scale);
 int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n, int c, int h, int w,

@@ -57,10 +57,19 @@ __device__ __forceinline__ float sample_offset(const OffsetSource &src, int img,
     return combine2(r0, r1, wy[0], wy[1]);
 }
 
+// Tensor.norm over 4 components as ATen's CPU kernel evaluates it (probed): plain left-to-right
+// sum of squares, no fused multiply-add.
+__device__ __forceinline__ float norm4(float a, float b, float c, float d) {
+    float acc = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+    acc = __fadd_rn(acc, __fmul_rn(c, c));
+    acc = __fadd_rn(acc, __fmul_rn(d, d));
+    return __fsqrt_rn(acc);
+}
+
 __global__ void __launch_bounds__(128)
 limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict__ det_index,
                   const float *__restrict__ offs, OffsetSource src, const float *__restrict__ scales,
-                  int C, int L, int K, int H, int W, SkeletonDev sk, float thre_hmp,
+                  LimbExtras ex, int C, int L, int K, int H, int W, SkeletonDev sk, float thre_hmp,
                   float min_len, float resize_factor, float *__restrict__ out_limbs) {
     __shared__ ToCand s_to[OG_MAX_TOPK];
     const int l = blockIdx.x;
@@ -102,12 +111,18 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
         float x1, y1, s1;
         int32_t idx1;
         candidate(jf, k, x1, y1, s1, idx1);
-        float ox = 0.0f, oy = 0.0f, scale1 = 4.0f;
+        float ox = 0.0f, oy = 0.0f, ox2 = 0.0f, oy2 = 0.0f, scale1 = 4.0f;
+        const bool four = ex.vector_nd == 4;          // cat_flip_offs: (x, y, x_flip, y_flip)
         if (idx1 >= 0) {
             if (offs != nullptr) {
-                const float *o = offs + ((size_t)n * 2 * L + 2 * l) * HW + idx1;   // collect.py:143-147
+                const int nd = four ? 4 : 2;
+                const float *o = offs + ((size_t)n * nd * L + nd * l) * HW + idx1;   // collect.py:143-147
                 ox = __ldg(o);
                 oy = __ldg(o + HW);
+                if (four) {
+                    ox2 = __ldg(o + 2 * HW);
+                    oy2 = __ldg(o + 3 * HW);
+                }
             } else {
                 const int py = idx1 / W, px = idx1 - py * W;
                 ox = sample_offset(src, n, L, l, 0, px, py);
@@ -115,13 +130,30 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
             }
             if (scales != nullptr) scale1 = __ldg(scales + ((size_t)n * C + jf) * HW + idx1);
         }
-        const float gx = __fadd_rn(x1, __fmul_rn(ox, resize_factor));         // collect.py:152
-        const float gy = __fadd_rn(y1, __fmul_rn(oy, resize_factor));
-
-        float best = norm2(__fsub_rn(gx, s_to[0].x), __fsub_rn(gy, s_to[0].y));
+        float gx = __fadd_rn(x1, __fmul_rn(ox, resize_factor));               // collect.py:152
+        float gy = __fadd_rn(y1, __fmul_rn(oy, resize_factor));
+        const float gx2 = __fadd_rn(x1, __fmul_rn(ox2, resize_factor));
+        const float gy2 = __fadd_rn(y1, __fmul_rn(oy2, resize_factor));
+        if (ex.jomps != nullptr && ex.use_jitter && !four) {
+            // jitter refinement of the guided point (collect.py:158-165), including the
+            // reference's [x, y]-as-[row, col] indexing; .int() truncates toward zero.
+            // (The reference raises IndexError when x >= H; such points are left unrefined.)
+            const int xi = (int)gx, yi = (int)gy;
+            if (xi >= 0 && xi < W && yi >= 0 && yi < H && xi < H && yi < W) {
+                const float *jm = ex.jomps + (size_t)n * 2 * HW + (size_t)xi * W + yi;
+                gx = __fadd_rn(gx, __ldg(jm));
+                gy = __fadd_rn(gy, __ldg(jm + HW));
+            }
+        }
+        auto dist_to = [&](int m) {
+            const float dx = __fsub_rn(gx, s_to[m].x), dy = __fsub_rn(gy, s_to[m].y);
+            if (!four) return norm2(dx, dy);
+            return norm4(dx, dy, __fsub_rn(gx2, s_to[m].x), __fsub_rn(gy2, s_to[m].y));
+        };
+        float best = dist_to(0);
         int best_m = 0;
         for (int m = 1; m < K; ++m) {                                          // collect.py:171-177
-            const float d = norm2(__fsub_rn(gx, s_to[m].x), __fsub_rn(gy, s_to[m].y));
+            const float d = dist_to(m);
             if (d < best) {
                 best = d;
                 best_m = m;
@@ -133,12 +165,23 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
         const long long g1 = (long long)idx1 + (long long)jf * HW;             // collect.py:198-199
         const long long g2 = (long long)t.index + (long long)jt * HW;
 
+        float x1o = x1, y1o = y1, x2o = t.x, y2o = t.y;
+        if (ex.jomps != nullptr && ex.use_jitter) {        // collect.py:213-218
+            if (idx1 >= 0) {
+                x1o = __fadd_rn(x1o, __ldg(ex.jomps + (size_t)n * 2 * HW + idx1));
+                y1o = __fadd_rn(y1o, __ldg(ex.jomps + (size_t)n * 2 * HW + HW + idx1));
+            }
+            if (t.index >= 0) {
+                x2o = __fadd_rn(x2o, __ldg(ex.jomps + (size_t)n * 2 * HW + t.index));
+                y2o = __fadd_rn(y2o, __ldg(ex.jomps + (size_t)n * 2 * HW + HW + t.index));
+            }
+        }
         float *o = out_limbs + (((size_t)n * L + l) * K + k) * OG_LIMB_COLS;    // collect.py:223-233
-        o[0] = x1;
-        o[1] = y1;
+        o[0] = x1o;
+        o[1] = y1o;
         o[2] = s1;
-        o[3] = t.x;
-        o[4] = t.y;
+        o[3] = x2o;
+        o[4] = y2o;
         o[5] = t.score;
         o[6] = __ll2float_rn(g1);
         o[7] = __ll2float_rn(g2);
@@ -153,16 +196,18 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
 }  // namespace
 
 int launch_limb_score(const float *det_score, const int32_t *det_index, const float *offs,
-                      const OffsetSource *lowres, const float *scales, int n, int c, int l, int k,
-                      int h, int w, const SkeletonDev &sk, float thre_hmp, float min_len,
-                      float resize_factor, float *out_limbs, cudaStream_t s) {
+                      const OffsetSource *lowres, const float *scales, const LimbExtras *extras,
+                      int n, int c, int l, int k, int h, int w, const SkeletonDev &sk, float thre_hmp,
+                      float min_len, float resize_factor, float *out_limbs, cudaStream_t s) {
     if (n == 0) return OG_OK;
     const int threads = k <= 32 ? 32 : (k <= 64 ? 64 : 128);
     dim3 grid(l, n);
     OffsetSource src = {};
     if (lowres) src = *lowres;
-    limb_score_kernel<<<grid, threads, 0, s>>>(det_score, det_index, offs, src, scales, c, l, k, h, w,
-                                              sk, thre_hmp, min_len, resize_factor, out_limbs);
+    LimbExtras ex = {nullptr, 2, 0};
+    if (extras) ex = *extras;
+    limb_score_kernel<<<grid, threads, 0, s>>>(det_score, det_index, offs, src, scales, ex, c, l, k, h,
+                                              w, sk, thre_hmp, min_len, resize_factor, out_limbs);
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;
 }

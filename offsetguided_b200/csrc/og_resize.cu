@@ -104,6 +104,44 @@ __global__ void scored_offset_kernel(const float *__restrict__ hmp, const float 
     }
 }
 
+__global__ void flip_average_kernel(const float *__restrict__ in2n, float *__restrict__ out, int n,
+                                    int ch, int h, int w, ChannelPerm perm, int negate_even) {
+    const long long hw = (long long)h * w;
+    const long long total = (long long)n * ch * hw;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(g % w);
+        const int y = (int)((g / w) % h);
+        const int c = (int)((g / hw) % ch);
+        const int img = (int)(g / (hw * ch));
+        float b = in2n[(((long long)(n + img) * ch + perm.src[c]) * h + y) * w + (w - 1 - x)];
+        if (negate_even && (c & 1) == 0) b = -b;
+        out[g] = __fmul_rn(__fadd_rn(in2n[g], b), 0.5f);
+    }
+}
+
+__global__ void flip_cat_offsets_kernel(const float *__restrict__ off2n, float *__restrict__ out,
+                                        int n, int l, int h, int w, ChannelPerm limb_flip,
+                                        ChannelPerm reserved) {
+    const long long hw = (long long)h * w;
+    const long long total = (long long)n * 4 * l * hw;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(g % w);
+        const int y = (int)((g / w) % h);
+        const int ch = (int)((g / hw) % (4 * l));
+        const int img = (int)(g / (hw * 4 * l));
+        const int limb = ch >> 2, comp = ch & 3;
+        const float *orig = off2n + ((long long)img * 2 * l + 2 * limb + (comp & 1)) * hw;
+        float r = orig[y * w + x];                       // comps 0, 1 and reserved limbs (:127)
+        if (comp >= 2 && !reserved.src[limb]) {
+            r = off2n[(((long long)(n + img) * 2 * l + 2 * limb_flip.src[limb] + (comp & 1)) * h + y) * w + (w - 1 - x)];
+            if ((comp & 1) == 0) r = __fmul_rn(r, -1.0f);    // factory.py:124
+        }
+        out[g] = r;
+    }
+}
+
 inline int grid_for(long long total, int threads) {
     long long b = (total + threads - 1) / threads;
     return (int)(b < 1 ? 1 : (b > 148LL * 64 ? 148LL * 64 : b));
@@ -128,6 +166,25 @@ int launch_flip_fuse(const float *hmp2n, const float *off2n, const int32_t *kp_f
     flip_fuse_kernel<<<grid_for(total, 256), 256, 0, s>>>(hmp2n, off2n, kp_flip_dev, limb_flip_dev,
                                                          limb_reserved_dev, n, c, l, h, w, out_hmp,
                                                          out_off);
+    OG_CUDA_TRY(cudaGetLastError());
+    return OG_OK;
+}
+
+int launch_flip_average(const float *in2n, float *out, int n, int ch, int h, int w,
+                        const ChannelPerm &perm, bool negate_even, cudaStream_t s) {
+    const long long total = (long long)n * ch * h * w;
+    if (total == 0) return OG_OK;
+    flip_average_kernel<<<grid_for(total, 256), 256, 0, s>>>(in2n, out, n, ch, h, w, perm,
+                                                            negate_even ? 1 : 0);
+    OG_CUDA_TRY(cudaGetLastError());
+    return OG_OK;
+}
+
+int launch_flip_cat_offsets(const float *off2n, float *out, int n, int l, int h, int w,
+                            const ChannelPerm &limb_flip, const ChannelPerm &reserved, cudaStream_t s) {
+    const long long total = (long long)n * 4 * l * h * w;
+    if (total == 0) return OG_OK;
+    flip_cat_offsets_kernel<<<grid_for(total, 256), 256, 0, s>>>(off2n, out, n, l, h, w, limb_flip, reserved);
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;
 }

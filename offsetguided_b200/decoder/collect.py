@@ -53,10 +53,11 @@ class LimbsCollect(object):
 
         Args:
             hmps_hr (Tensor): (N, C, H, W) heat maps at decode resolution.
-            jomps_hr: jitter-offset maps; only ``None`` / ``[]`` is supported.
-            offs_hr (Tensor): (N, 2L, H, W) guiding offsets, (x, y) interleaved per limb.
+            jomps_hr: (N, 2, H, W) jitter-offset maps, used when ``include_jitter_offset``.
+            offs_hr (Tensor): (N, 2L, H, W) guiding offsets, (x, y) interleaved per limb
+                ((N, 4L, H, W) with ``vector_nd=4``).
             scmps_hr: (N, C, H, W) keypoint-scale maps, used when ``include_scale``.
-            vector_nd (int): 2 (the 4-D flip-concatenated variant is not implemented).
+            vector_nd (int): 2, or 4 for the flip-concatenated offsets of ``cat_flip_offs``.
 
         Returns:
             Tensor (N, L, K, 13) float32 on the device of ``hmps_hr``:
@@ -65,18 +66,16 @@ class LimbsCollect(object):
             (moved 100000 px off the image exactly as in the reference).
         """
         assert hmps_hr.shape[-2:] == offs_hr.shape[-2:], 'spatial resolution should be equal'
-        if vector_nd != 2:
-            raise NotImplementedError('generate_limbs: only vector_nd=2 is implemented '
-                                      '(cat_flip_offs builds 4-D vectors)')
-        if self.include_jitter_offset and isinstance(jomps_hr, torch.Tensor):
-            raise NotImplementedError('jitter-offset refinement is not implemented '
-                                      '(reference: "this trick does not help at all")')
+        if vector_nd not in (2, 4):
+            raise ValueError('vector_nd must be 2, or 4 for flip-concatenated offsets')
         src = hmps_hr.device
         heat = as_cuda_f32(hmps_hr)
         eng = self._engine(heat.device)
         scores, inds, _ = eng.nms_topk(heat)
         scales = scmps_hr if (self.include_scale and isinstance(scmps_hr, torch.Tensor)) else None
-        limbs = eng.limb_score(scores, inds, offs_hr, scales)
+        jomps = jomps_hr if (self.include_jitter_offset and isinstance(jomps_hr, torch.Tensor)) else None
+        limbs = eng.limb_score(scores, inds, offs_hr, scales, jomps, vector_nd,
+                               self.use_jitter_offset)
         return limbs.to(src)
 
     @staticmethod

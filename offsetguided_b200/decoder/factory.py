@@ -85,64 +85,87 @@ class PostProcess(torch.nn.Module):
         offs = out_offsets[self.feat_stage]
         scmps = out_scales[self.feat_stage]
 
-        if cat_flip_offs:
-            raise NotImplementedError('cat_flip_offs (4-D offset vectors) is not implemented')
-        if self.include_jitter_offset and isinstance(jomps, torch.Tensor):
-            raise NotImplementedError('jitter-offset refinement is not implemented')
-        use_scale_maps = self.include_scale and isinstance(scmps, torch.Tensor)
-
-        if scored_off or use_scale_maps:
-            return self._generate_poses_staged(hmps, offs, scmps if use_scale_maps else None,
-                                               flip_test, scored_off)
+        lc = self.limb_collect
+        use_scale_maps = self.include_scale and lc.include_scale and isinstance(scmps, torch.Tensor)
+        use_jitter_maps = (self.include_jitter_offset and lc.include_jitter_offset
+                           and isinstance(jomps, torch.Tensor))
+        if scored_off or use_scale_maps or use_jitter_maps or (flip_test and cat_flip_offs):
+            return self._generate_poses_staged(hmps, jomps if use_jitter_maps else None, offs,
+                                               scmps if use_scale_maps else None, flip_test,
+                                               cat_flip_offs, scored_off)
         device = hmps.device if hmps.is_cuda else torch.device('cuda', torch.cuda.current_device())
         eng = self._engine(device)
         tables = (self.keypoints_flips, self.limbs_flips[0], self.limbs_flips[1]) if flip_test else None
         return eng.decode_features(hmps, offs, self.hmp_stride, self.off_stride, self.inter_mode, tables)
 
-    def _generate_poses_staged(self, hmps, offs, scmps, flip_test, scored_off):
-        """Optional stages (scored_off, keypoint-scale maps): the same kernels, called
-        stage by stage through the C ABI."""
+    def _generate_poses_staged(self, hmps, jomps, offs, scmps, flip_test, cat_flip_offs, scored_off):
+        """The optional heads and flags (scored_off, keypoint-scale maps, jitter-offset maps,
+        cat_flip_offs): the same kernels, called stage by stage through the C ABI on
+        materialised maps (reference decoder/factory.py:67-91)."""
         from .. import _lib
         from ..engine import as_cuda_f32, _ptr, _stream_ptr
         lib = _lib.load()
         hmps = as_cuda_f32(hmps)
         device = hmps.device
         offs = as_cuda_f32(offs, device)
+        scmps = as_cuda_f32(scmps, device) if scmps is not None else None
+        jomps = as_cuda_f32(jomps, device) if jomps is not None else None
         eng = self._engine(device)
         mode = {'bilinear': 0, 'bicubic': 1}[self.inter_mode]
-        if scmps is not None:
-            scmps = as_cuda_f32(scmps, device)
+        vector_nd = 2
         with torch.cuda.device(device):
             s = _stream_ptr(device)
+
+            def flip_average(x, perm, negate_even):
+                n2, ch, h, w = x.shape
+                out = torch.empty((n2 // 2, ch, h, w), dtype=torch.float32, device=device)
+                _lib.check(lib.og_flip_average_f32(_ptr(x), _lib.int32_array(perm) if perm else None,
+                                                   1 if negate_even else 0, n2 // 2, ch, h, w,
+                                                   _ptr(out), s))
+                return out
+
             if flip_test:
-                n = hmps.shape[0] // 2
-                fh = torch.empty((n,) + tuple(hmps.shape[1:]), dtype=torch.float32, device=device)
-                fo = torch.empty((n,) + tuple(offs.shape[1:]), dtype=torch.float32, device=device)
-                kp = _lib.int32_array(self.keypoints_flips)
+                n2, _, h, w = hmps.shape
                 lf = _lib.int32_array(self.limbs_flips[0])
                 lr = _lib.int32_array(self.limbs_flips[1])
-                _lib.check(lib.og_flip_fuse_f32(eng._h, _ptr(hmps), _ptr(offs), kp, lf, lr,
-                                                len(self.limbs_flips[1]), n, hmps.shape[2],
-                                                hmps.shape[3], _ptr(fh), _ptr(fo), s))
-                if scmps is not None:        # factory.py:141-144
-                    flipped = torch.flip(scmps[n:], [-1])[:, self.keypoints_flips]
-                    scmps = (scmps[:n] + flipped) / 2
-                hmps, offs = fh, fo
+                if cat_flip_offs:                                       # factory.py:115-127
+                    out = torch.empty((n2 // 2, 4 * len(self.skeleton), h, w), dtype=torch.float32,
+                                      device=device)
+                    _lib.check(lib.og_flip_cat_offsets_f32(_ptr(offs), lf, lr, len(self.limbs_flips[1]),
+                                                           n2 // 2, len(self.skeleton), h, w, _ptr(out), s))
+                    offs, vector_nd = out, 4
+                    hmps = flip_average(hmps, self.keypoints_flips, False)
+                else:                                                   # factory.py:128-139
+                    fh = torch.empty((n2 // 2,) + tuple(hmps.shape[1:]), dtype=torch.float32, device=device)
+                    fo = torch.empty((n2 // 2,) + tuple(offs.shape[1:]), dtype=torch.float32, device=device)
+                    _lib.check(lib.og_flip_fuse_f32(eng._h, _ptr(hmps), _ptr(offs),
+                                                    _lib.int32_array(self.keypoints_flips), lf, lr,
+                                                    len(self.limbs_flips[1]), n2 // 2, h, w,
+                                                    _ptr(fh), _ptr(fo), s))
+                    hmps, offs = fh, fo
+                if jomps is not None:                                   # factory.py:109-113
+                    jomps = flip_average(jomps, None, True)
+                if scmps is not None:                                   # factory.py:141-144
+                    scmps = flip_average(scmps, self.keypoints_flips, False)
             if scored_off:
+                if vector_nd != 2:
+                    raise ValueError('scored_off cannot be combined with cat_flip_offs')
                 jf, jt = _offset.pack_jtypes(self.skeleton)
                 offs = _offset.scored_offset(hmps, offs, jf, jt, kernel_size=3)
 
             def up(x, stride, m):
-                if stride == 1:
+                if x is None or stride == 1:
                     return x
                 n, c, h, w = x.shape
                 out = torch.empty((n, c, h * stride, w * stride), dtype=torch.float32, device=device)
                 _lib.check(lib.og_resize_f32(_ptr(x.contiguous()), _ptr(out), n * c, h, w, stride, m, s))
                 return out
-            hmps_hr = up(hmps, self.hmp_stride, mode)
+            hmps_hr = up(hmps, self.hmp_stride, mode)                   # factory.py:74-88
             offs_hr = up(offs, self.off_stride, 0)
-            scmps_hr = up(scmps, self.off_stride, mode) if scmps is not None else None
-            return eng.decode_maps(hmps_hr, offs_hr, scmps_hr)
+            scmps_hr = up(scmps, self.off_stride, mode)
+            jomps_hr = up(jomps, self.hmp_stride, 0)
+            return eng.decode_maps(hmps_hr, offs_hr, scmps_hr, jomps=jomps_hr, vector_nd=vector_nd,
+                                   use_jitter=self.limb_collect.use_jitter_offset)
 
 
 def decoder_cli(parser):

@@ -106,21 +106,26 @@ class DecoderEngine(object):
                 _stream_ptr(self.device)))
         return scores, inds
 
-    def limb_score(self, det_scores, det_inds, offs, scales=None):
-        """K2.  -> limbs (N, L, K, 13) CUDA f32."""
+    def limb_score(self, det_scores, det_inds, offs, scales=None, jomps=None, vector_nd=2,
+                   use_jitter=False):
+        """K2.  -> limbs (N, L, K, 13) CUDA f32.  ``jomps`` (N, 2, H, W) jitter-offset maps and
+        ``vector_nd=4`` (cat_flip_offs offsets, 4L channels) are the optional variants."""
         offs = as_cuda_f32(offs, self.device)
         n, l2, h, w = offs.shape
-        assert l2 == 2 * self.n_limbs, 'offset map channel count differs from 2 * limbs'
+        assert l2 == vector_nd * self.n_limbs, 'offset map channel count differs from vector_nd * limbs'
         det_scores = as_cuda_f32(det_scores, self.device)
         det_inds = det_inds.to(self.device, torch.int32).contiguous()
         if scales is not None:
             scales = as_cuda_f32(scales, self.device)
+        if jomps is not None:
+            jomps = as_cuda_f32(jomps, self.device)
         limbs = torch.empty((n, self.n_limbs, self.topk, _lib.OG_LIMB_COLS),
                             dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.og_limb_score_f32(
-                self._h, _ptr(det_scores), _ptr(det_inds), _ptr(offs), _ptr(scales), n, h, w,
-                _ptr(limbs), _stream_ptr(self.device)))
+            _lib.check(self.lib.og_limb_score_ex_f32(
+                self._h, _ptr(det_scores), _ptr(det_inds), _ptr(offs), _ptr(scales), _ptr(jomps),
+                int(vector_nd), 1 if use_jitter else 0, n, h, w, _ptr(limbs),
+                _stream_ptr(self.device)))
         return limbs
 
     def group(self, limbs):
@@ -160,7 +165,8 @@ class DecoderEngine(object):
         rows = np.ctypeslib.as_array(poses_p, shape=(total.value, c, _lib.OG_POSE_COLS))
         return [rows[offs[i]:offs[i] + cnts[i]].copy() for i in range(n)]
 
-    def decode_maps(self, heat, offs, scales=None, fetch=True):
+    def decode_maps(self, heat, offs, scales=None, fetch=True, jomps=None, vector_nd=2,
+                    use_jitter=False):
         """generate_limbs + group_skeletons on full-resolution maps (K1 -> K2 -> K3).
         With ``fetch=False`` the call only launches (up to two calls may be in flight);
         ``fetch(n)`` later returns the oldest pending result."""
@@ -169,11 +175,14 @@ class DecoderEngine(object):
         assert heat.shape[-2:] == offs.shape[-2:], 'spatial resolution should be equal'
         if scales is not None:
             scales = as_cuda_f32(scales, self.device)
+        if jomps is not None:
+            jomps = as_cuda_f32(jomps, self.device)
         n, c, h, w = heat.shape
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.og_decode_maps(self._h, _ptr(heat), _ptr(offs), _ptr(scales),
-                                               n, h, w, _stream_ptr(self.device)))
-            self._keep_maps = (heat, offs, scales)
+            _lib.check(self.lib.og_decode_maps_ex(self._h, _ptr(heat), _ptr(offs), _ptr(scales),
+                                                  _ptr(jomps), int(vector_nd), 1 if use_jitter else 0,
+                                                  n, h, w, _stream_ptr(self.device)))
+            self._keep_maps = (heat, offs, scales, jomps)
             if not fetch:
                 return n
             return self._fetch(n)

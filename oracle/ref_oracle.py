@@ -135,10 +135,21 @@ def _norm2(dx, dy):
         return np.sqrt((dy.astype(np.float64) * dy.astype(np.float64) + xx).astype(F32))
 
 
+def _norm4(a, b, c, d):
+    """Tensor.norm over 4 components as ATen's CPU kernel evaluates it (probed): plain
+    left-to-right float32 sum of squares, no fused multiply-add."""
+    acc = (a * a + b * b).astype(F32)
+    acc = (acc + c * c).astype(F32)
+    acc = (acc + d * d).astype(F32)
+    return np.sqrt(acc)
+
+
 def generate_limbs(hmps_hr, offs_hr, skeleton, topk, thre_hmp, min_len,
-                   hmp_s=4, off_s=4, scmps_hr=None, return_dets=False):
+                   hmp_s=4, off_s=4, scmps_hr=None, return_dets=False, jomps_hr=None,
+                   use_jitter=True, vector_nd=2):
     """decoder/collect.py:62-236 with include_scale / include_jitter_offset off
-    unless ``scmps_hr`` is given (the scale gather of :111-116, 257-262).
+    unless ``scmps_hr`` (the scale gather of :111-116, 257-262) / ``jomps_hr`` (jitter offsets,
+    :127-138, 158-165, 213-218) are given; ``vector_nd = 4`` is the cat_flip_offs layout.
 
     Returns limbs (N, L, K, 13) float32 =
     [x1, y1, v1, x2, y2, v2, ind1, ind2, min_dist, len, limb_score, scale1, scale2].
@@ -161,13 +172,34 @@ def generate_limbs(hmps_hr, offs_hr, skeleton, topk, thre_hmp, min_len,
         scale_f = np.full(s_f.shape, 4, dtype=F32)
         scale_t = np.full(s_t.shape, 4, dtype=F32)
 
-    flat_off = offs_hr.reshape(n, nl, 2, h * w)                               # :143-144
-    off_f = np.take_along_axis(flat_off, ind_f[:, :, None, :], axis=-1)       # (N,L,2,K)
-    off_f = np.transpose(off_f, (0, 1, 3, 2))                                 # (N,L,K,2)
-    guid = xy_f + off_f * F32(off_s / hmp_s)                                  # :152
+    flat_off = offs_hr.reshape(n, nl, vector_nd, h * w)                       # :143-144
+    off_f = np.take_along_axis(flat_off, ind_f[:, :, None, :], axis=-1)       # (N,L,nd,K)
+    off_f = np.transpose(off_f, (0, 1, 3, 2))                                 # (N,L,K,nd)
+    guid = np.tile(xy_f, (1, 1, 1, vector_nd // 2)) + off_f * F32(off_s / hmp_s)   # :152
 
-    diff = guid[:, :, :, None, :] - xy_t[:, :, None, :, :]                    # (N,L,K,M,2)
-    dist = _norm2(diff[..., 0], diff[..., 1])                                 # :175
+    if jomps_hr is not None:                                                  # :127-138
+        jm = np.asarray(jomps_hr, dtype=F32)
+        jflat = jm.reshape(n, 2, h * w)
+        jit_f = np.stack([np.take_along_axis(jflat[:, None, c_], ind_f, axis=-1) for c_ in (0, 1)], -1)
+        jit_t = np.stack([np.take_along_axis(jflat[:, None, c_], ind_t, axis=-1) for c_ in (0, 1)], -1)
+        if use_jitter:                                                        # :158-165
+            assert vector_nd == 2, 'the reference cannot refine 4-D vectors'
+            gi = guid.astype(np.int32)                                        # .int(): toward zero
+            for i in range(n):
+                for j in range(nl):
+                    for k in range(topk):
+                        gx_, gy_ = int(gi[i, j, k, 0]), int(gi[i, j, k, 1])
+                        if 0 <= gx_ < w and 0 <= gy_ < h:
+                            guid[i, j, k] += jm[i, :, gx_, gy_]               # [x, y] as [row, col]
+    else:
+        jit_f = jit_t = None
+
+    xy_t_nd = np.tile(xy_t, (1, 1, 1, vector_nd // 2))
+    diff = guid[:, :, :, None, :] - xy_t_nd[:, :, None, :, :]                 # (N,L,K,M,nd)
+    if vector_nd == 2:
+        dist = _norm2(diff[..., 0], diff[..., 1])                             # :175
+    else:
+        dist = _norm4(diff[..., 0], diff[..., 1], diff[..., 2], diff[..., 3])
     min_ind = np.argmin(dist, axis=-1)                                        # :177 first index on ties
     min_dist = np.take_along_axis(dist, min_ind[..., None], axis=-1)[..., 0]
 
@@ -185,6 +217,10 @@ def generate_limbs(hmps_hr, offs_hr, skeleton, topk, thre_hmp, min_len,
     length = np.maximum(_norm2(d[..., 0], d[..., 1]), F32(min_len))
     limb_score = s_f * m_s_t * np.exp(-min_dist / length)                     # :208
 
+    if jit_f is not None and use_jitter:                                      # :211-218
+        m_jit_t = np.take_along_axis(jit_t, min_ind[..., None], axis=2)
+        xy_f = xy_f + jit_f
+        m_xy_t = m_xy_t + m_jit_t
     limbs = np.stack((xy_f[..., 0], xy_f[..., 1], s_f,
                       m_xy_t[..., 0], m_xy_t[..., 1], m_s_t,
                       g_ind_f.astype(F32), g_ind_t.astype(F32),
@@ -365,6 +401,34 @@ def delete_sort(subset, n_keypoints, thre, index):
 # --------------------------------------------------------------------------- #
 # decoder/factory.py
 # --------------------------------------------------------------------------- #
+def flip_average(x2n, perm=None, negate_even=False):
+    """(orig + sign * flip_W(flipped)[perm]) / 2 — heat / scale / jitter maps
+    (decoder/factory.py:101-113, 141-144)."""
+    x2n = np.asarray(x2n, dtype=F32)
+    n = x2n.shape[0] // 2
+    fl = x2n[n:, :, :, ::-1].copy()
+    if perm is not None:
+        fl = fl[:, perm]
+    if negate_even:
+        fl[:, ::2] *= F32(-1)
+    return ((x2n[:n] + fl) / F32(2)).astype(F32)
+
+
+def flip_cat_offsets(offs, limb_flips, limb_reserve):
+    """decoder/factory.py:115-127 — (2N, 2L, h, w) -> (N, 4L, h, w): per limb the original
+    vector followed by the mirrored limb's vector (x negated); reserved limbs repeat theirs."""
+    offs = np.asarray(offs, dtype=F32)
+    n2, l2, h, w = offs.shape
+    n = n2 // 2
+    o = offs.reshape(n2, -1, 2, h, w)
+    orig = o[:n]
+    fl = o[n:, :, :, :, ::-1].copy()
+    fl[:, :, 0] *= F32(-1.0)
+    out = np.concatenate((orig, fl[:, limb_flips]), axis=2)
+    out[:, limb_reserve, 2:] = orig[:, limb_reserve]
+    return out.reshape(n, -1, h, w).astype(F32)
+
+
 def flip_augment(hmps, offs, kp_flips, limb_flips, limb_reserve):
     """decoder/factory.py:98-146, default (vector addition) branch.
     hmps (2N, C, h, w), offs (2N, 2L, h, w): originals then W-flipped copies."""
@@ -455,15 +519,30 @@ def resize(x, scale, mode):
 def generate_poses(hmps, offs, skeleton, n_keypoints, *, topk, thre_hmp, min_len, person_thre,
                    sort_dim=2, dist_max=20, use_scale=True, hmp_stride=4, off_stride=4,
                    resize_mode='bicubic', flip_test=False, kp_flips=None, limb_flips=None,
-                   limb_reserve=None, return_limbs=False):
-    """decoder/factory.py:52-96 on network-resolution maps (no scale / jitter heads):
-    optional flip fusion, x stride resize, limb collection, greedy grouping."""
+                   limb_reserve=None, return_limbs=False, scmps=None, jomps=None, use_jitter=True,
+                   cat_flip_offs=False):
+    """decoder/factory.py:52-96 on network-resolution maps: optional flip fusion, x stride
+    resize, limb collection, greedy grouping; ``scmps`` / ``jomps`` are the optional
+    keypoint-scale and jitter-offset heads, ``cat_flip_offs`` the 4-D offset variant."""
+    vector_nd = 2
     if flip_test:
-        hmps, offs = flip_augment(hmps, offs, kp_flips, limb_flips, limb_reserve)
+        if cat_flip_offs:
+            offs = flip_cat_offsets(offs, limb_flips, limb_reserve)
+            hmps = flip_average(hmps, kp_flips)
+            vector_nd = 4
+        else:
+            hmps, offs = flip_augment(hmps, offs, kp_flips, limb_flips, limb_reserve)
+        if jomps is not None:
+            jomps = flip_average(jomps, None, True)
+        if scmps is not None:
+            scmps = flip_average(scmps, kp_flips)
     hmps_hr = resize(hmps, hmp_stride, resize_mode)
     offs_hr = resize(offs, off_stride, 'bilinear')
+    scmps_hr = resize(scmps, off_stride, resize_mode) if scmps is not None else None
+    jomps_hr = resize(jomps, hmp_stride, 'bilinear') if jomps is not None else None
     limbs = generate_limbs(hmps_hr, offs_hr, skeleton, topk, thre_hmp, min_len,
-                           hmp_stride, off_stride)
+                           hmp_stride, off_stride, scmps_hr=scmps_hr, jomps_hr=jomps_hr,
+                           use_jitter=use_jitter, vector_nd=vector_nd)
     poses = [group_skeletons(l, skeleton, n_keypoints, person_thre, sort_dim, dist_max, use_scale)
              for l in limbs]
     if return_limbs:

@@ -14,6 +14,8 @@ own output on identical inputs):
     reference's flip fusion and x4 bicubic / bilinear resize);
   * ``group_fuzz.npz`` — random (L, K, 13) limb tables with heavy id collisions ->
     reference ``group_skeletons`` (exercises merge / last-write-wins / cancellation);
+  * ``poses_optional_heads.npz`` — the optional heads / flags (keypoint-scale maps,
+    jitter-offset maps, cat_flip_offs) through the reference's generate_poses;
   * ``resize_*.npz`` — ATen ``F.interpolate`` bicubic / bilinear x4 on small maps;
   * ``encoder_check`` — asserts oracle/scenes.py renders bit-identically to the
     reference encoder.
@@ -307,6 +309,71 @@ def make_resize():
     print('resize_small: written')
 
 
+OPTIONAL_VARIANTS = {
+    # name: (include_scale, include_jitter_offset, use_jitter_offset, flip_test, cat_flip_offs)
+    'scale_jitter_flip': (True, True, True, True, False),
+    'jitter_noflip': (False, True, True, False, False),
+    'jitter_unused': (False, True, False, False, False),
+    'cat_flip': (False, False, True, True, True),
+    'scale_cat_flip': (True, False, True, True, True),
+}
+
+
+def make_optional_heads():
+    """The optional heads / flags of PostProcess.generate_poses through the reference:
+    keypoint-scale maps (include_scale), jitter-offset maps (include_jitter_offset, with and
+    without use_jitter_offset) and cat_flip_offs.  Scale / jitter maps are seeded noise
+    (regenerated by tests/golden_io.py from the stored seed)."""
+    from oracle import ref_oracle
+    kp = og_config.heatmap_hflip(COCO_KEYPOINTS)
+    fl, rs = og_config.offset_hflip(COCO_KEYPOINTS, COCO_PERSON_SKELETON)
+    w = h = 384
+    n = 2
+    hgen = HeatMapGenerator([w, h], 4, 3, 7, 0.01)
+    ogen = OffsetMapGenerator([w, h], 4, 7, 1.0, COCO_PERSON_SKELETON)
+    hs, os_, hf, of = [], [], [], []
+    for i in range(n):
+        rng = np.random.RandomState(6000 + i)
+        p = scenes.make_persons(rng, 4, w, h, scale_range=(8, 13))
+        hs.append(hgen.create_heatmaps(p, {'joint_num': 17}))
+        os_.append(ogen.create_offsetmaps(p, {'joint_num': 17})[0])
+        pf = scenes.mirror_persons(p, w, kp)
+        hf.append(hgen.create_heatmaps(pf, {'joint_num': 17}))
+        of.append(ogen.create_offsetmaps(pf, {'joint_num': 17})[0])
+    hmp = np.stack(hs + hf).astype(np.float32)
+    omp = np.stack(os_ + of).astype(np.float32)
+    omp[~np.isfinite(omp)] = 0
+    seed = 99
+    rng = np.random.RandomState(seed)
+    scm = rng.uniform(2, 60, size=(2 * n, 17, h // 4, w // 4)).astype(np.float32)
+    jom = rng.uniform(-1.5, 1.5, size=(2 * n, 2, h // 4, w // 4)).astype(np.float32)
+    out = {}
+    for name, (inc_scale, inc_jit, use_jit, flip, cat) in OPTIONAL_VARIANTS.items():
+        args = reference_args(topk=16, thre_hmp=0.06, person_thre=0.06, dist_max=40, batch_size=n,
+                              include_scale=inc_scale, include_jitter_offset=inc_jit,
+                              use_jitter_offset=use_jit)
+        proc = decoder.decoder_factory(args)
+        sel = slice(None) if flip else slice(0, n)
+        feats = [[[torch.from_numpy(hmp[sel])], [[]], [torch.from_numpy(jom[sel]) if inc_jit else []]],
+                 [[torch.from_numpy(omp[sel])], [[]], [torch.from_numpy(scm[sel]) if inc_scale else []]]]
+        poses = proc.generate_poses(feats, flip_test=flip, cat_flip_offs=cat)
+        proc.worker_pool.close()
+        proc.worker_pool.join()
+        mine = ref_oracle.generate_poses(
+            hmp[sel], omp[sel], COCO_PERSON_SKELETON, 17, topk=16, thre_hmp=0.06, min_len=0.5,
+            person_thre=0.06, dist_max=40, use_scale=True, flip_test=flip, kp_flips=kp, limb_flips=fl,
+            limb_reserve=rs, scmps=scm[sel] if inc_scale else None, jomps=jom[sel] if inc_jit else None,
+            use_jitter=use_jit, cat_flip_offs=cat)
+        for a, b in zip(poses, mine):
+            assert a.shape == b.shape and np.array_equal(a[..., 5], b[..., 5])
+            np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-6)
+        print(f'optional heads {name}: persons/img={[len(p) for p in poses]} oracle == reference')
+        out[name + '_counts'] = np.asarray([len(p) for p in poses])
+        out[name + '_poses'] = np.concatenate(poses, 0)
+    np.savez_compressed(os.path.join(HERE, 'poses_optional_heads.npz'), hmp=hmp, omp=omp,
+                        noise_seed=seed, **out)
+
+
 def main():
     torch.set_num_threads(8)
     encoder_check()
@@ -321,6 +388,7 @@ def main():
                     64, 0.06, 0.06, 40, 0.0, (4.0, 8.0))
     make_poses_case('poses_cfg1', 4000, 1, 5, 640, 640, 32, 0.06, 0.06, 40, False, 0.0)
     make_poses_case('poses_cfg2_flip', 5000, 2, 5, 640, 640, 32, 0.04, 0.04, 40, True, 0.0)
+    make_optional_heads()
 
 
 if __name__ == '__main__':

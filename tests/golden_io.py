@@ -40,6 +40,26 @@ def load_poses_case(name):
     return d
 
 
+OPTIONAL_VARIANTS = {
+    # name: (include_scale, include_jitter_offset, use_jitter_offset, flip_test, cat_flip_offs)
+    'scale_jitter_flip': (True, True, True, True, False),
+    'jitter_noflip': (False, True, True, False, False),
+    'jitter_unused': (False, True, False, False, False),
+    'cat_flip': (False, False, True, True, True),
+    'scale_cat_flip': (True, False, True, True, True),
+}
+
+
+def load_optional_heads():
+    """Inputs (incl. the seeded scale / jitter maps) and the reference's poses per variant."""
+    d = load('poses_optional_heads')
+    n2, _, h, w = d['hmp'].shape
+    rng = np.random.RandomState(int(d['noise_seed']))
+    d['scm'] = rng.uniform(2, 60, size=(n2, 17, h, w)).astype(np.float32)
+    d['jom'] = rng.uniform(-1.5, 1.5, size=(n2, 2, h, w)).astype(np.float32)
+    return d
+
+
 def load_group_fuzz():
     d = load('group_fuzz')
     cases = []

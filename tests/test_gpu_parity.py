@@ -520,3 +520,27 @@ def test_config3_crowdpose_batch32(cuda_device):
                             dist_max=40.0, use_scale=True)
     assert sum(len(p) for p in ref) > 32 * 15
     _pose_lists_equal(got, ref)
+
+
+@pytest.mark.parametrize('name', list(gio.OPTIONAL_VARIANTS))
+def test_optional_heads_match_reference(cuda_device, name):
+    """include_scale / include_jitter_offset / use_jitter_offset / cat_flip_offs through
+    decoder_factory(args).generate_poses against the reference's own output."""
+    d = gio.load_optional_heads()
+    inc_scale, inc_jit, use_jit, flip, cat = gio.OPTIONAL_VARIANTS[name]
+    n = d['hmp'].shape[0] // 2
+    sel = slice(None) if flip else slice(0, n)
+    pp = decoder.decoder_factory(_args(topk=16, thre_hmp=0.06, person_thre=0.06, dist_max=40, batch_size=n,
+                                       include_scale=inc_scale, include_jitter_offset=inc_jit,
+                                       use_jitter_offset=use_jit))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    feats = [[[dev(d['hmp'][sel])], [[]], [dev(d['jom'][sel]) if inc_jit else []]],
+             [[dev(d['omp'][sel])], [[]], [dev(d['scm'][sel]) if inc_scale else []]]]
+    got = pp.generate_poses(feats, flip_test=flip, cat_flip_offs=cat)
+    ref = gio.split_poses(d[name + '_poses'], d[name + '_counts'])
+    assert len(got) == len(ref)
+    for p, r in zip(got, ref):
+        assert p.shape == r.shape and np.array_equal(p[..., 5], r[..., 5])
+        np.testing.assert_allclose(p, r, rtol=RTOL, atol=1e-5)
+        if not (inc_jit and use_jit):
+            assert np.array_equal(p[..., :2], r[..., :2])

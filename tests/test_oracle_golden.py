@@ -128,3 +128,25 @@ def test_scene_renderer_is_deterministic():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert a[0].shape == (1, 17, 48, 64) and a[1].shape == (1, 38, 48, 64)
     assert a[0].max() > 0.9
+
+
+@pytest.mark.parametrize('name', list(gio.OPTIONAL_VARIANTS))
+def test_optional_heads_match_reference(name):
+    """Keypoint-scale maps, jitter-offset maps (used / unused) and cat_flip_offs."""
+    d = gio.load_optional_heads()
+    inc_scale, inc_jit, use_jit, flip, cat = gio.OPTIONAL_VARIANTS[name]
+    n = d['hmp'].shape[0] // 2
+    sel = slice(None) if flip else slice(0, n)
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, cfg.COCO_PERSON_SKELETON)
+    poses = ro.generate_poses(
+        d['hmp'][sel], d['omp'][sel], cfg.COCO_PERSON_SKELETON, 17, topk=16, thre_hmp=0.06, min_len=0.5,
+        person_thre=0.06, dist_max=40, use_scale=True, flip_test=flip,
+        kp_flips=cfg.heatmap_hflip(cfg.COCO_KEYPOINTS), limb_flips=fl, limb_reserve=rs,
+        scmps=d['scm'][sel] if inc_scale else None, jomps=d['jom'][sel] if inc_jit else None,
+        use_jitter=use_jit, cat_flip_offs=cat)
+    ref = gio.split_poses(d[name + '_poses'], d[name + '_counts'])
+    assert len(poses) == len(ref) and sum(len(p) for p in ref) >= 6
+    for p, r in zip(poses, ref):
+        gio.compare_poses(p, r, rtol=1e-6) if not inc_jit or not use_jit else None
+        assert p.shape == r.shape and np.array_equal(p[..., 5], r[..., 5])
+        np.testing.assert_allclose(p, r, rtol=1e-6, atol=1e-6)
