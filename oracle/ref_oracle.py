@@ -548,3 +548,39 @@ def generate_poses(hmps, offs, skeleton, n_keypoints, *, topk, thre_hmp, min_len
     if return_limbs:
         return poses, limbs
     return poses
+
+
+# --------------------------------------------------------------------------- #
+# caller side: transforms/preprocess.py, evaluate.py
+# --------------------------------------------------------------------------- #
+def annotations_inverse(keypoints, meta):
+    """transforms/preprocess.py:33-63 (hflip metas raise in the reference)."""
+    k = np.array(keypoints, copy=True)
+    k[:, :, 0] += meta['offset'][0]
+    k[:, :, 1] += meta['offset'][1]
+    k[:, :, 0] /= meta['scale'][0]
+    k[:, :, 1] /= meta['scale'][1]
+    k[:, :, 3] /= np.sqrt(np.prod(meta['scale']))
+    if meta['hflip']:
+        raise Exception('this should not happen. please have a check here, not implemented actually!')
+    return k
+
+
+def coco_result_rows(batch_poses, metas):
+    """evaluate.py:227-265 — explicit loops, as the reference writes them."""
+    rows, ids = [], []
+    for poses, meta in zip(batch_poses, metas):
+        subset = annotations_inverse(poses, meta)
+        ids.append(meta['image_id'])
+        subset[:, :, :2] = np.around(subset[:, :, :2], 2)
+        for person in subset.astype(float):
+            kps, v = [], []
+            for xyv in person[:, :3]:
+                v.append(xyv[2])
+                kps += [xyv[0], xyv[1], 1 if xyv[0] > 0 or xyv[1] > 0 else 0]
+            rows.append({'image_id': meta['image_id'], 'category_id': 1, 'keypoints': kps,
+                         'score': sum(v) / len(v)})
+        if not len(subset):
+            rows.append({'image_id': meta['image_id'], 'category_id': 1,
+                         'keypoints': np.zeros((subset.shape[1] * 3,)).tolist(), 'score': 0.01})
+    return rows, ids
