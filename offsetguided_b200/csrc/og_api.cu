@@ -113,6 +113,9 @@ struct og_handle {
     DevBuf<float> limbs;
     DevBuf<float> slab;
     DevBuf<int32_t> group_prep;
+    DevBuf<float> tile_amax;            // fused path scratch
+    DevBuf<int32_t> tile_list;          // [tiles] + the active-tile counter at the end
+    int sm_count;
     DevBuf<float> fused_hmp, fused_off;     // materialising path only
     DevBuf<float> hr_hmp, hr_off;
     DevBuf<int32_t> kp_flip, limb_flip;
@@ -259,14 +262,19 @@ int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused
             const int planes = n * c.n_keypoints;
             OG_TRY(h->cand_count.ensure(planes));
             OG_TRY(h->cand_keys.ensure((size_t)planes * kCandCap));
+            const size_t tiles = fused_tile_count(n, c.n_keypoints, fused->h, fused->w);
+            OG_TRY(h->tile_amax.ensure(tiles));
+            OG_TRY(h->tile_list.ensure(tiles + 1));
             OG_TRY(launch_fused_candidates(fused->hmp, h->kp_flip.ptr, n, c.n_keypoints, fused->h,
                                            fused->w, fused->scale, fused->cubic, fused->flip,
-                                           c.thre_hmp, h->cand_count.ptr, h->cand_keys.ptr, s));
+                                           c.thre_hmp, h->cand_count.ptr, h->cand_keys.ptr,
+                                           h->tile_amax.ptr, h->tile_list.ptr, h->tile_list.ptr + tiles,
+                                           h->sm_count, s, &h->launches));
             OG_TRY(mark(h, slot, 2, s));
             OG_TRY(launch_select_topk(nullptr, planes, hgt, w, c.thre_hmp, c.topk, h->cand_count.ptr,
                                       h->cand_keys.ptr, h->det_score.ptr, h->det_index.ptr,
                                       h->det_count.ptr, meta + 2 * n + 1, s));
-            h->launches += 2;
+            h->launches += 1;
         } else {
             OG_TRY(run_k1(h, heat, n, hgt, w, c.thre_hmp, h->det_score.ptr, h->det_index.ptr,
                           h->det_count.ptr, s, h->timing ? slot->ev[2] : nullptr));
@@ -347,7 +355,7 @@ int decode_features_impl(og_handle *h, ResultSlot *slot, const float *hmp, const
     // Fused path: candidates straight from the network-resolution maps, offsets sampled at
     // the candidates; no full-resolution map is written.  thre_hmp <= 0 (every pixel is a
     // candidate) and other strides use the materialising path below.
-    if (allow_fused && h->fused_enabled && c.thre_hmp > 0.0f && fused_scale_supported(hmp_stride)) {
+    if (allow_fused && h->fused_enabled && c.thre_hmp > 0.0f && fused_supported(hmp_stride, hgt, w)) {
         OG_TRY(check_maps(n, hgt * hmp_stride, w * hmp_stride, c.n_keypoints));
         K1Fused k1 = {hmp, hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
         OffsetSource src = {off, hgt, w, off_stride, flip_test ? 1 : 0, n, h->limb_flip.ptr,
@@ -463,6 +471,7 @@ int og_create(const og_config *cfg, og_handle **out) {
         h->sk.to[i] = cfg->limb_to[i];
     }
     h->device = device;
+    h->sm_count = prop.multiProcessorCount;
     h->launches = 0;
     h->head = h->tail = h->pending = 0;
     h->last_slot = 0;
@@ -520,6 +529,8 @@ int og_destroy(og_handle *h) {
     h->limbs.release();
     h->slab.release();
     h->group_prep.release();
+    h->tile_amax.release();
+    h->tile_list.release();
     h->fused_hmp.release();
     h->fused_off.release();
     h->hr_hmp.release();

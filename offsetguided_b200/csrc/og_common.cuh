@@ -117,10 +117,13 @@ int launch_flip_average(const float *in2n, float *out, int n, int ch, int h, int
 int launch_flip_cat_offsets(const float *off2n, float *out, int n, int l, int h, int w,
                             const ChannelPerm &limb_flip, const ChannelPerm &reserved, cudaStream_t s);
 
-bool fused_scale_supported(int scale);
+bool fused_supported(int scale, int h, int w);
+size_t fused_tile_count(int n, int c, int h, int w);
+// tile_amax: fused_tile_count floats, tile_list: as many ints, n_active: one int (scratch)
 int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n, int c, int h, int w,
                             int scale, bool cubic, bool flip, float thre, uint32_t *cand_count,
-                            uint64_t *cand_keys, cudaStream_t s);
+                            uint64_t *cand_keys, float *tile_amax, int32_t *tile_list,
+                            int32_t *n_active, int sm_count, cudaStream_t s, int64_t *launches);
 
 struct GroupLaunch {
     int n, c, l, k;
