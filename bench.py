@@ -327,8 +327,35 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop()
     e2e_launches = e2e_eng.launch_count - e2e_l0
-    h2d = hmp_h.numel() * 4 + omp_h.numel() * 4
     d2h = sum(p.nbytes for p in out) + (2 * B + 1) * 4
+    # host -> device bytes of one step: the heat maps are copied; the offset maps stay in pinned
+    # host memory and K2 reads its bilinear samples over PCIe (counted from the candidates:
+    # 2 components x 4 taps x 4 bytes per from-candidate of every limb, twice where the mirrored
+    # map is averaged in)
+    zero_copy = e2e_eng.zero_copy_count > 0
+    _, det_idx, _ = e2e_eng.last_intermediates(B)
+    per_joint = (det_idx >= 0).sum(dim=2).cpu().numpy()                     # (B, C)
+    _, reserved = cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel)
+    gathered = 0
+    for l, (jf, _jt) in enumerate(skel):
+        maps = 2 if (flip and l not in reserved) else 1
+        gathered += int(per_joint[:, jf].sum()) * 2 * 4 * 4 * maps
+    h2d_full = hmp_h.numel() * 4 + omp_h.numel() * 4
+    h2d = hmp_h.numel() * 4 + gathered if zero_copy else h2d_full
+
+    # the same call with the offset maps copied as a whole (zero-copy off), for comparison
+    e2e_eng.set_zero_copy(False)
+    for _ in range(2):
+        post.generate_poses(feats, flip_test=flip)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    full_steps = max(3, args.steps // 2)
+    for _ in range(full_steps):
+        post.generate_poses(feats, flip_test=flip)
+    torch.cuda.synchronize(dev)
+    full_copy_ms = (time.perf_counter() - t0) * 1e3 / full_steps
+    e2e_launches_all = e2e_eng.launch_count - e2e_l0
+    e2e_eng.set_zero_copy(True)
 
     # ---- max over ranks
     times = torch.tensor([hot_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -372,9 +399,19 @@ def run_b200(args):
                     'ms_per_step': e2e_ms / args.steps,
                     'stage_ms': {k: statistics.mean(s[k] for s in e2e_stages) for k in e2e_stages[0]},
                     'fused_redos': e2e_eng.fused_redo_count,
-                    'api': 'decoder_factory(args).generate_poses(features, flip_test=%s), pinned host maps' % flip},
-            'gpu_launches': hot_launches + e2e_launches,
-            'gpu_launches_detail': {'hot_path': hot_launches, 'e2e': e2e_launches},
+                    'api': 'decoder_factory(args).generate_poses(features, flip_test=%s), pinned host maps' % flip,
+                    'h2d_detail': {'heat_maps_copied': hmp_h.numel() * 4,
+                                   'offset_samples_read_over_pcie': gathered if zero_copy else 0,
+                                   'offset_maps_left_on_host': omp_h.numel() * 4 if zero_copy else 0,
+                                   'note': 'fused path: K2 needs 2*L*K bilinear samples per image, so pinned '
+                                           'offset maps are read in place (zero-copy) instead of copied'},
+                    'full_copy': {'value': n_gpus * B / (full_copy_ms * 1e-3), 'unit': UNIT,
+                                  'ms_per_step': full_copy_ms, 'h2d_bytes_per_step': h2d_full,
+                                  'note': 'same call with og_set_zero_copy(0): heat and offset maps both copied '
+                                          '(rank 0 time, %d steps)' % full_steps}},
+            'gpu_launches': hot_launches + e2e_launches_all,
+            'gpu_launches_detail': {'hot_path': hot_launches, 'e2e': e2e_launches,
+                                    'e2e_full_copy': e2e_launches_all - e2e_launches},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'kernel': 'K1 = nms_candidates_kernel + select_topk_kernel',

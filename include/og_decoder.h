@@ -224,6 +224,17 @@ int og_set_fused(og_handle *h, int enable);
 int og_debug_k3_profile(uint64_t *out16, int reset);
 int64_t og_fused_redo_count(const og_handle *h);
 
+/* og_decode_features_host, fused path: when `off_host` is pinned (device-accessible) host memory
+ * the offset maps are NOT copied to the device — K2 reads its 2 * L * K bilinear samples per image
+ * straight from the host buffer over PCIe (a few KB instead of 2L * h * w * 4 bytes per image).
+ * Pageable buffers are copied as a whole.  The host buffers must stay valid and unmodified until
+ * og_fetch_poses returns (this already holds for the asynchronous copies).  og_set_zero_copy(h, 0)
+ * forces the full copy; og_zero_copy_count reports how many calls left the offsets on the host.
+ * (replaces the reference's implicit "everything lives on the model's device",
+ * decoder/factory.py:59-63) */
+int og_set_zero_copy(og_handle *h, int enable);
+int64_t og_zero_copy_count(const og_handle *h);
+
 /* Per-stage device timing of og_decode_* calls with CUDA events recorded on the
  * launching stream.   og_last_stage_times_ms() reports the most recently FETCHED decode call:
  * out6 = { input copy + flip + resize, K1 pass 1 (NMS stream), K1 pass 2 (select),

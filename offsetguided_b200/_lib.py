@@ -75,6 +75,8 @@ SIGNATURES = {
     'og_set_fused': (_i, [_vp, _i]),
     'og_debug_k3_profile': (_i, [ctypes.POINTER(ctypes.c_uint64), _i]),
     'og_fused_redo_count': (ctypes.c_int64, [_vp]),
+    'og_set_zero_copy': (_i, [_vp, _i]),
+    'og_zero_copy_count': (ctypes.c_int64, [_vp]),
     'og_enable_stage_timing': (_i, [_vp, _i]),
     'og_last_stage_times_ms': (_i, [_vp, c_float_p]),
 }

@@ -75,6 +75,7 @@ constexpr int kStageEvents = 7;    // start, after prep, K1 pass 1, K1 pass 2, K
 struct FeatureArgs {               // arguments of a features decode, kept for the exact redo
     const float *hmp, *off;
     int n, hgt, w, hmp_stride, off_stride, resize_mode, flip;
+    const float *off_host;         // offsets left in pinned host memory (zero-copy), else nullptr
 };
 
 // Everything that belongs to ONE decode call until its result has been fetched.
@@ -113,8 +114,8 @@ struct og_handle {
     DevBuf<float> limbs;
     DevBuf<float> slab;
     DevBuf<int32_t> group_prep;
-    DevBuf<float> tile_amax;            // fused path scratch
-    DevBuf<int32_t> tile_list;          // [tiles] + the active-tile counter at the end
+    DevBuf<float> tile_amax;            // fused path scratch: activity map
+    DevBuf<int32_t> tile_list;          // [blocks] work list + the active-block counter at the end
     int sm_count;
     DevBuf<float> fused_hmp, fused_off;     // materialising path only
     DevBuf<float> hr_hmp, hr_off;
@@ -130,7 +131,9 @@ struct og_handle {
     int rows_hint;
 
     bool fused_enabled;
+    bool zero_copy_enabled;      // host API: K2 gathers offsets straight from pinned host memory
     int64_t fused_redos;
+    int64_t zero_copy_calls;
     bool tables_valid;           // device flip tables match the cached host copies
     int32_t kp_cache[OG_MAX_KEYPOINTS];
     int32_t limb_cache[OG_MAX_LIMBS];
@@ -262,8 +265,9 @@ int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused
             const int planes = n * c.n_keypoints;
             OG_TRY(h->cand_count.ensure(planes));
             OG_TRY(h->cand_keys.ensure((size_t)planes * kCandCap));
-            const size_t tiles = fused_tile_count(n, c.n_keypoints, fused->h, fused->w);
-            OG_TRY(h->tile_amax.ensure(tiles));
+            size_t amax_floats = 0, tiles = 0;
+            fused_scratch(n, c.n_keypoints, fused->h, fused->w, fused->scale, &amax_floats, &tiles);
+            OG_TRY(h->tile_amax.ensure(amax_floats));
             OG_TRY(h->tile_list.ensure(tiles + 1));
             OG_TRY(launch_fused_candidates(fused->hmp, h->kp_flip.ptr, n, c.n_keypoints, fused->h,
                                            fused->w, fused->scale, fused->cubic, fused->flip,
@@ -350,12 +354,13 @@ int decode_features_impl(og_handle *h, ResultSlot *slot, const float *hmp, const
         OG_TRY(mark(h, slot, 0, s));
         slot->prep_marked = h->timing;
     }
-    slot->args = FeatureArgs{hmp, off, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test};
+    slot->args = FeatureArgs{hmp, off, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, nullptr};
 
     // Fused path: candidates straight from the network-resolution maps, offsets sampled at
     // the candidates; no full-resolution map is written.  thre_hmp <= 0 (every pixel is a
     // candidate) and other strides use the materialising path below.
-    if (allow_fused && h->fused_enabled && c.thre_hmp > 0.0f && fused_supported(hmp_stride, hgt, w)) {
+    if (allow_fused && h->fused_enabled && c.thre_hmp > 0.0f &&
+        fused_supported(n, c.n_keypoints, hmp_stride, hgt, w)) {
         OG_TRY(check_maps(n, hgt * hmp_stride, w * hmp_stride, c.n_keypoints));
         K1Fused k1 = {hmp, hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
         OffsetSource src = {off, hgt, w, off_stride, flip_test ? 1 : 0, n, h->limb_flip.ptr,
@@ -479,7 +484,9 @@ int og_create(const og_config *cfg, og_handle **out) {
     h->rows_hint = 0;
     h->timing = false;
     h->fused_enabled = true;
+    h->zero_copy_enabled = true;
     h->fused_redos = 0;
+    h->zero_copy_calls = 0;
     h->tables_valid = false;
 
     // person-table rows held in shared memory: as many as fit beside the work arrays
@@ -750,18 +757,38 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
     const og_config &c = h->cfg;
     const size_t n_in = (size_t)(flip_test ? 2 * n : n);
     const size_t hw = (size_t)hgt * w;
+    // Zero-copy offsets: on the fused path K2 reads 2 * L * K bilinear samples per image, a few
+    // KB out of the 2L * h * w * 4 bytes of the offset maps.  When the caller's buffer is pinned
+    // (device-accessible) host memory the maps are not copied at all; K2 gathers its samples over
+    // PCIe.  Pageable buffers and the materialising path copy everything as before.
+    const float *off_alias = nullptr;
+    if (h->zero_copy_enabled && n_in && h->fused_enabled && c.thre_hmp > 0.0f &&
+        fused_supported(n, c.n_keypoints, hmp_stride, hgt, w)) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, off_host) == cudaSuccess &&
+            attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr)
+            off_alias = static_cast<const float *>(attr.devicePointer);
+        else
+            (void)cudaGetLastError();       // not registered: clear the sticky-free error state
+    }
     OG_TRY(slot->in_hmp.ensure(std::max<size_t>(1, n_in * c.n_keypoints * hw)));
-    OG_TRY(slot->in_off.ensure(std::max<size_t>(1, n_in * 2 * c.n_limbs * hw)));
+    if (!off_alias) OG_TRY(slot->in_off.ensure(std::max<size_t>(1, n_in * 2 * c.n_limbs * hw)));
     OG_TRY(mark(h, slot, 0, s));
     slot->prep_marked = h->timing;
     if (n_in) {
         OG_CUDA_TRY(cudaMemcpyAsync(slot->in_hmp.ptr, hmp_host, n_in * c.n_keypoints * hw * sizeof(float),
                                     cudaMemcpyHostToDevice, s));
-        OG_CUDA_TRY(cudaMemcpyAsync(slot->in_off.ptr, off_host, n_in * 2 * c.n_limbs * hw * sizeof(float),
-                                    cudaMemcpyHostToDevice, s));
+        if (!off_alias)
+            OG_CUDA_TRY(cudaMemcpyAsync(slot->in_off.ptr, off_host, n_in * 2 * c.n_limbs * hw * sizeof(float),
+                                        cudaMemcpyHostToDevice, s));
     }
-    return decode_features_impl(h, slot, slot->in_hmp.ptr, slot->in_off.ptr, n, hgt, w, hmp_stride,
-                                off_stride, resize_mode, flip_test, s, true);
+    const int st = decode_features_impl(h, slot, slot->in_hmp.ptr, off_alias ? off_alias : slot->in_off.ptr,
+                                        n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, s, true);
+    if (st == OG_OK && off_alias) {
+        slot->args.off_host = off_host;
+        h->zero_copy_calls += 1;
+    }
+    return st;
 }
 
 int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offset_host,
@@ -784,7 +811,14 @@ int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offse
             // kernel cannot re-scan a map it never materialised, so this batch is decoded again
             // on the GPU through the materialising path, which selects exactly for any input.
             h->fused_redos += 1;
-            const FeatureArgs a = slot->args;
+            FeatureArgs a = slot->args;
+            if (a.off_host) {           // the materialising path reads every offset: copy them now
+                const size_t elems = (size_t)(a.flip ? 2 * a.n : a.n) * 2 * h->cfg.n_limbs * a.hgt * a.w;
+                OG_TRY(slot->in_off.ensure(elems));
+                OG_CUDA_TRY(cudaMemcpyAsync(slot->in_off.ptr, a.off_host, elems * sizeof(float),
+                                            cudaMemcpyHostToDevice, slot->stream));
+                a.off = slot->in_off.ptr;
+            }
             OG_TRY(decode_features_impl(h, slot, a.hmp, a.off, a.n, a.hgt, a.w, a.hmp_stride,
                                         a.off_stride, a.resize_mode, a.flip, slot->stream, false));
             OG_CUDA_TRY(cudaEventSynchronize(slot->done));
@@ -848,6 +882,14 @@ int og_set_fused(og_handle *h, int enable) {
 }
 
 int64_t og_fused_redo_count(const og_handle *h) { return h ? h->fused_redos : 0; }
+
+int og_set_zero_copy(og_handle *h, int enable) {
+    OG_REQUIRE(h, "og_set_zero_copy: null handle");
+    h->zero_copy_enabled = enable != 0;
+    return OG_OK;
+}
+
+int64_t og_zero_copy_count(const og_handle *h) { return h ? h->zero_copy_calls : 0; }
 
 int og_debug_k3_profile(uint64_t *out16, int reset) {
     OG_REQUIRE(out16, "og_debug_k3_profile: null pointer");

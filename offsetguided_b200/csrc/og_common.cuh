@@ -117,12 +117,13 @@ int launch_flip_average(const float *in2n, float *out, int n, int ch, int h, int
 int launch_flip_cat_offsets(const float *off2n, float *out, int n, int l, int h, int w,
                             const ChannelPerm &limb_flip, const ChannelPerm &reserved, cudaStream_t s);
 
-bool fused_supported(int scale, int h, int w);
-size_t fused_tile_count(int n, int c, int h, int w);
-// tile_amax: fused_tile_count floats, tile_list: as many ints, n_active: one int (scratch)
+bool fused_supported(int n, int c, int scale, int h, int w);
+// scratch of the fused K1: floats of the 4 x 4-cell activity map, ints of the block work list
+void fused_scratch(int n, int c, int h, int w, int scale, size_t *amax_floats, size_t *list_ints);
+// sub_amax / block_list: fused_scratch() elements, n_active: one int
 int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n, int c, int h, int w,
                             int scale, bool cubic, bool flip, float thre, uint32_t *cand_count,
-                            uint64_t *cand_keys, float *tile_amax, int32_t *tile_list,
+                            uint64_t *cand_keys, float *sub_amax, int32_t *block_list,
                             int32_t *n_active, int sm_count, cudaStream_t s, int64_t *launches);
 
 struct GroupLaunch {

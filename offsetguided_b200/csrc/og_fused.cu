@@ -9,19 +9,23 @@
 // (sum |wx|)(sum |wy|) max|taps| <= 1.375^2 max|taps| for the A = -0.75 cubic (1 for bilinear),
 // so a region whose taps are all below thre / kBound cannot hold a candidate.  Three kernels:
 //
-//   tile_scan_kernel   streams the maps once (coalesced, one CTA per 16-row band of a plane)
-//                      and writes max |fused value| of every 16 x 32-cell tile;
-//   tile_list_kernel   a tile is ACTIVE if it or one of its 8 neighbours (they cover its 2-cell
-//                      halo) can reach thre; active tiles are appended to a work list;
-//   fused_nms_candidates_kernel   persistent CTAs walk the work list; the next tile's cells are
-//                      prefetched into registers while the current tile is processed.  A CTA
-//                      stages the tile (+halo, fused with the mirrored copy when flip-testing)
-//                      in shared memory, interpolates rows along x once, and every warp produces
-//                      the full-resolution values of its ACTIVE cells with one 4-tap (2-tap)
-//                      combine along y.  Values are bit-identical to the materialised map (same
-//                      taps, same accumulation order as ATen's CPU kernel), so the candidates
-//                      are too.  A value >= thre (rare) triggers the 3x3 test, which recomputes
-//                      the neighbours from the same shared rows.
+//   amax_scan_kernel    streams the maps once (128-bit loads, 8 rows in flight per thread) and
+//                       writes max |fused value| of every 4 x 4-cell sub-block — the only pass
+//                       that touches all of the input, HBM-bound;
+//   block_list_kernel   a BLOCK is (32 / S) x 8 cells = 32 x 8S full-resolution pixels; it is
+//                       active if a sub-block that overlaps the block or its tap halo can reach
+//                       thre.  Active blocks are compacted into a work list;
+//   fused_block_kernel  persistent warps walk the work list, ONE WARP PER BLOCK, one lane per
+//                       full-resolution column.  The block's cells (+halo, fused with the mirrored
+//                       copy when flip-testing, prefetched one block ahead into registers) go to
+//                       a per-warp shared tile; each lane interpolates its column along x once
+//                       (8 + 2 HALO values kept in registers), then walks down the 8S rows with one
+//                       4-tap (2-tap) combine per pixel in ATen's accumulation order, so values
+//                       are bit-identical to the materialised map.  Interpolation weights depend
+//                       on the phase (pixel mod S) only, so they live in registers for the
+//                       lifetime of the warp.  A row in which some lane reaches thre (rare) runs
+//                       the 3x3 test with lane shuffles; the pixel ring outside the block is
+//                       evaluated on demand.
 // Skipping is provably lossless (kBound leaves 3 % for rounding); nothing else is skipped.
 #include "og_common.cuh"
 #include "og_interp.cuh"
@@ -32,325 +36,421 @@ namespace og {
 
 namespace {
 
-constexpr int kTileW = 32;       // low-resolution cells per tile
-#ifndef OG_K1F_TILE_H
-#define OG_K1F_TILE_H 16
-#endif
-constexpr int kTileH = OG_K1F_TILE_H;
 constexpr int kFusedThreads = 256;
 constexpr int kScanThreads = 256;
+constexpr int kBlockCellsH = 8;       // cell rows of a block
+constexpr int kSub = 4;               // sub-block edge (cells) of the activity map
+constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ float bound_factor(bool cubic) { return cubic ? 1.95f : 1.001f; }
+__device__ __forceinline__ float4 ldg_stream4(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
 
-// ---- tile scan -------------------------------------------------------------
-template <bool kFlip>
+// |v| >= 0: the IEEE bit pattern orders like the value, and NaN sorts above everything,
+// which keeps such regions active
+__device__ __forceinline__ unsigned abs_bits(float v) { return __float_as_uint(fabsf(v)); }
+
+// ---- pass A: activity map ------------------------------------------------------
+// one thread per (plane, 8-row band, 4-cell column group): two sub-block maxima
+template <bool kFlip, bool kVec>
 __global__ void __launch_bounds__(kScanThreads)
-tile_scan_kernel(const float *__restrict__ hmp, const int32_t *__restrict__ kp_flip, int N, int C,
-                 int h, int w, float *__restrict__ tile_amax) {
-    __shared__ unsigned s_max[64];
-    const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
-    const int ty = blockIdx.x % tiles_y;
-    const int plane = blockIdx.x / tiles_y;
+amax_scan_kernel(const float *__restrict__ hmp, const int32_t *__restrict__ kp_flip, int N, int C,
+                 int h, int w, float *__restrict__ sub_amax, long long total) {
+    const long long idx = (long long)blockIdx.x * kScanThreads + threadIdx.x;
+    if (idx >= total) return;
+    const int sxs = (w + kSub - 1) / kSub, sys = (h + kSub - 1) / kSub;
+    const int bands = (h + 2 * kSub - 1) / (2 * kSub);
+    const int sx = (int)(idx % sxs);
+    const long long t = idx / sxs;
+    const int band = (int)(t % bands);
+    const int plane = (int)(t / bands);
     const int n = plane / C, c = plane - n * C;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < tiles_x && i < 64; i += kScanThreads) s_max[i] = 0u;
-    __syncthreads();
     const float *a = hmp + ((size_t)n * C + c) * h * w;
     const float *b = nullptr;
     if (kFlip) b = hmp + ((size_t)(N + n) * C + kp_flip[c]) * h * w;
-    const int y0 = ty * kTileH, y1 = min(h, y0 + kTileH);
-    const int cells = (y1 - y0) * w;
-    for (int i = tid; i < cells; i += kScanThreads) {
-        const int y = y0 + i / w, x = i - (i / w) * w;
-        float v = __ldg(a + y * w + x);
-        if (kFlip) v = __fmul_rn(__fadd_rn(v, __ldg(b + y * w + (w - 1 - x))), 0.5f);
-        // |v| >= 0: the IEEE bit pattern orders like the value (NaN sorts above everything,
-        // which keeps such tiles active)
-        atomicMax(&s_max[min(x / kTileW, 63)], __float_as_uint(fabsf(v)));
+    const int y0 = band * 2 * kSub, x0 = sx * kSub;
+    unsigned m[2] = {0u, 0u};
+    if (kVec) {
+        float4 va[2 * kSub], vb[2 * kSub];
+#pragma unroll
+        for (int r = 0; r < 2 * kSub; ++r) {
+            const int y = min(y0 + r, h - 1);          // a repeated row does not change a maximum
+            va[r] = ldg_stream4(a + (size_t)y * w + x0);
+            if (kFlip) vb[r] = ldg_stream4(b + (size_t)y * w + (w - kSub - x0));
+        }
+#pragma unroll
+        for (int r = 0; r < 2 * kSub; ++r) {
+            float4 f = va[r];
+            if (kFlip) {                     // (orig + flip_W(flipped)[kp_flip]) / 2, factory.py:101-106
+                f.x = __fmul_rn(__fadd_rn(f.x, vb[r].w), 0.5f);
+                f.y = __fmul_rn(__fadd_rn(f.y, vb[r].z), 0.5f);
+                f.z = __fmul_rn(__fadd_rn(f.z, vb[r].y), 0.5f);
+                f.w = __fmul_rn(__fadd_rn(f.w, vb[r].x), 0.5f);
+            }
+            const unsigned q = max(max(abs_bits(f.x), abs_bits(f.y)), max(abs_bits(f.z), abs_bits(f.w)));
+            m[r / kSub] = max(m[r / kSub], q);
+        }
+    } else {
+        for (int r = 0; r < 2 * kSub; ++r) {
+            const int y = y0 + r;
+            if (y >= h) break;
+            for (int j = 0; j < kSub; ++j) {
+                const int x = x0 + j;
+                if (x >= w) break;
+                float v = __ldg(a + (size_t)y * w + x);
+                if (kFlip) v = __fmul_rn(__fadd_rn(v, __ldg(b + (size_t)y * w + (w - 1 - x))), 0.5f);
+                m[r / kSub] = max(m[r / kSub], abs_bits(v));
+            }
+        }
+    }
+    float *o = sub_amax + ((size_t)plane * sys + 2 * band) * sxs + sx;
+    o[0] = __uint_as_float(m[0]);
+    if (2 * band + 1 < sys) o[sxs] = __uint_as_float(m[1]);
+}
+
+// ---- pass B: work list -----------------------------------------------------------
+// entry = {plane of the original map, plane of the mirrored map, block row << 16 | block column, 0}
+__global__ void __launch_bounds__(256)
+block_list_kernel(const float *__restrict__ sub_amax, const int32_t *__restrict__ kp_flip, int N, int C,
+                  int flip, int h, int w, int block_w, int halo, float limit, long long total,
+                  int4 *__restrict__ block_list, int32_t *__restrict__ n_active) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int sxs = (w + kSub - 1) / kSub, sys = (h + kSub - 1) / kSub;
+    const int bxs = (w + block_w - 1) / block_w, bys = (h + kBlockCellsH - 1) / kBlockCellsH;
+    bool active = false;
+    int bx = 0, by = 0, plane = 0;
+    if (g < total) {
+        bx = (int)(g % bxs);
+        by = (int)((g / bxs) % bys);
+        plane = (int)(g / ((long long)bxs * bys));
+        const float *p = sub_amax + (size_t)plane * sys * sxs;
+        const int sx0 = max(bx * block_w - halo, 0) / kSub;
+        const int sx1 = min(bx * block_w + block_w - 1 + halo, w - 1) / kSub;
+        const int sy0 = max(by * kBlockCellsH - halo, 0) / kSub;
+        const int sy1 = min(by * kBlockCellsH + kBlockCellsH - 1 + halo, h - 1) / kSub;
+        unsigned m = 0u;                   // independent loads, one compare (bit order = value order)
+        for (int sy = sy0; sy <= sy1; ++sy)
+            for (int sx = sx0; sx <= sx1; ++sx) m = max(m, __float_as_uint(p[sy * sxs + sx]));
+        active = !(__uint_as_float(m) < limit);       // NaN: active
+    }
+    // one global atomic per CTA
+    const unsigned ballot = __ballot_sync(kFull, active);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int sum = 0;
+        for (int i = 0; i < 8; ++i) {
+            const int cnt = s_warp[i];
+            s_warp[i] = sum;
+            sum += cnt;
+        }
+        s_base = sum ? atomicAdd(n_active, sum) : 0;
     }
     __syncthreads();
-    for (int i = tid; i < tiles_x; i += kScanThreads)
-        tile_amax[((size_t)plane * tiles_y + ty) * tiles_x + i] = __uint_as_float(s_max[min(i, 63)]);
+    if (active) {
+        const int n = plane / C, c = plane - n * C;
+        const int plane_b = flip ? (N + n) * C + kp_flip[c] : plane;
+        block_list[s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))] =
+            make_int4(plane, plane_b, (by << 16) | bx, 0);
+    }
 }
 
-__global__ void tile_list_kernel(const float *__restrict__ tile_amax, int planes, int tiles_y,
-                                 int tiles_x, float limit, int32_t *__restrict__ tile_list,
-                                 int32_t *__restrict__ n_active) {
-    const long long total = (long long)planes * tiles_y * tiles_x;
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total) return;
-    const int tx = (int)(g % tiles_x);
-    const int ty = (int)((g / tiles_x) % tiles_y);
-    const long long plane = g / ((long long)tiles_x * tiles_y);
-    const float *p = tile_amax + plane * tiles_y * tiles_x;
-    bool active = false;
-    for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int yy = ty + dy, xx = tx + dx;
-            if (yy < 0 || yy >= tiles_y || xx < 0 || xx >= tiles_x) continue;
-            const float m = p[yy * tiles_x + xx];
-            active = active || !(m < limit);          // NaN keeps the tile active
-        }
-    if (active) tile_list[atomicAdd(n_active, 1)] = (int32_t)g;
+// ---- pass C: interpolation + NMS over the active blocks -------------------------------
+// value of one full-resolution pixel from the warp's cell tile, generic taps (ring pixels only)
+template <int S, bool kCubic, int LW, int HALO>
+__device__ __noinline__ float tile_value(const float *lo, int cx0, int cy0, int X, int Y) {
+    constexpr int TAPS = kCubic ? 4 : 2;
+    const float inv = 1.0f / (float)S;
+    float wxs[4], wys[4];
+    const int fx = axis_first_tap(X, inv, kCubic, wxs) - (cx0 - HALO);
+    const int fy = axis_first_tap(Y, inv, kCubic, wys) - (cy0 - HALO);
+    float rows[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+        const float *row = lo + (fy + t) * LW + fx;
+        rows[t] = kCubic ? combine4(row[0], row[1], row[2], row[3], wxs[0], wxs[1], wxs[2], wxs[3])
+                         : combine2(row[0], row[1], wxs[0], wxs[1]);
+    }
+    return kCubic ? combine4(rows[0], rows[1], rows[TAPS - 2], rows[TAPS - 1], wys[0], wys[1], wys[2], wys[3])
+                  : combine2(rows[0], rows[1], wys[0], wys[1]);
 }
 
-// ---- interpolation + NMS over the active tiles ----------------------------------
 template <int S, bool kCubic, bool kFlip>
-__global__ void __launch_bounds__(kFusedThreads)
-fused_nms_candidates_kernel(const float *__restrict__ hmp, const int32_t *__restrict__ kp_flip,
-                            int N, int C, int h, int w, float thre,
-                            const int32_t *__restrict__ tile_list,
-                            const int32_t *__restrict__ n_active_ptr,
-                            uint32_t *__restrict__ cand_count, uint64_t *__restrict__ cand_keys) {
+__global__ void __launch_bounds__(kFusedThreads, S <= 4 ? 4 : 3)
+fused_block_kernel(const float *__restrict__ hmp, int h, int w, float thre,
+                   const int4 *__restrict__ block_list,
+                   const int32_t *__restrict__ n_active_ptr, uint32_t *__restrict__ cand_count,
+                   uint64_t *__restrict__ cand_keys) {
     constexpr int HALO = kCubic ? 2 : 1;
     constexpr int TAPS = kCubic ? 4 : 2;
-    constexpr int LW = kTileW + 2 * HALO, LH = kTileH + 2 * HALO;
-    constexpr int XW = S * kTileW + 2, YH = S * kTileH + 2;       // incl. the 1-pixel NMS ring
-    constexpr int kLoads = (LH * LW + kFusedThreads - 1) / kFusedThreads;
-    __shared__ float s_lo[LH][LW + 1];
-    __shared__ float s_hb[LH][XW];
-    __shared__ float s_xw[TAPS][XW];
-    __shared__ float s_yw[TAPS][YH];
-    __shared__ int s_xb[XW];
-    __shared__ int s_yb[YH];
-    __shared__ float s_am[LH][LW + 1];
-    __shared__ uint8_t s_act[kTileH][kTileW];
+    constexpr int BW = 32 / S, BH = kBlockCellsH;
+    constexpr int LW = BW + 2 * HALO, LH = BH + 2 * HALO;
+    constexpr int NL = (LW * LH + 31) / 32;
+    constexpr int kWarps = kFusedThreads / 32;
+    __shared__ float s_lo[kWarps][LH * LW];
 
-    const int tid = threadIdx.x;
-    const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *lo = s_lo[warp];
     const int W = w * S, H = h * S;
     const int n_active = *n_active_ptr;
-    const float kBound = bound_factor(kCubic);
+    const int stride = gridDim.x * kWarps;
     const float inv = 1.0f / (float)S;
 
-    // cells of a tile (+halo), border cells replicated (= ATen's tap clamping), fused with
-    // the mirrored copy: (orig + flip_W(flipped)[kp_flip]) / 2   (factory.py:101-106)
-    auto load_tile = [&](int tile, float (&vals)[kLoads]) {
-        const int tx = tile % tiles_x;
-        const int ty = (tile / tiles_x) % tiles_y;
-        const int plane = tile / (tiles_x * tiles_y);
-        const int n = plane / C, c = plane - n * C;
-        const float *a = hmp + ((size_t)n * C + c) * h * w;
-        const float *b = nullptr;
-        if (kFlip) b = hmp + ((size_t)(N + n) * C + kp_flip[c]) * h * w;
+    // Interpolation weights depend on the phase (pixel mod S) only: src = (dst + 0.5) / S - 0.5
+    // is exact in float for a power-of-two S.  The one exception is bilinear's clamp of src at 0
+    // (pixels < S / 2 from the top / left image border), handled where the taps are combined.
+    float wx[4];
+    axis_first_tap(lane + 2 * 32, inv, kCubic, wx);
+    const int xb_phase = lane / S + ((lane % S) >= S / 2 ? 1 : 0);     // first tap, tile-relative
+    float wy[S][TAPS];
 #pragma unroll
-        for (int u = 0; u < kLoads; ++u) {
-            const int i = tid + u * kFusedThreads;
-            float v = 0.0f;
-            if (i < LH * LW) {
-                const int ly = i / LW, lx = i - ly * LW;
-                const int gy = min(max(ty * kTileH - HALO + ly, 0), h - 1);
-                const int gx = min(max(tx * kTileW - HALO + lx, 0), w - 1);
-                v = __ldg(a + gy * w + gx);
-                if (kFlip) v = __fmul_rn(__fadd_rn(v, __ldg(b + gy * w + (w - 1 - gx))), 0.5f);
+    for (int p = 0; p < S; ++p) {
+        float t4[4];
+        axis_first_tap(p + 8 * S, inv, kCubic, t4);
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) wy[p][t] = t4[t];
+    }
+
+    // cells of a block (+halo), border cells replicated (= ATen's tap clamping), fused with
+    // the mirrored copy: (orig + flip_W(flipped)[kp_flip]) / 2   (factory.py:101-106)
+    const size_t hw = (size_t)h * w;
+    auto load_block = [&](const int4 e, float (&vals)[NL]) {
+        const int base_x = (e.z & 0xffff) * BW - HALO, base_y = (e.z >> 16) * BH - HALO;
+        const float *a = hmp + (size_t)e.x * hw;
+        const float *b = hmp + (size_t)e.y * hw;
+        const bool interior = base_x >= 0 && base_y >= 0 && base_x + LW <= w && base_y + LH <= h;
+        if (interior) {                     // warp-uniform: no clamping
+            a += base_y * w + base_x;
+            b += base_y * w + (w - 1 - base_x);
+#pragma unroll
+            for (int u = 0; u < NL; ++u) {
+                const int i = lane + 32 * u;
+                float v = 0.0f;
+                if (i < LH * LW) {
+                    const int ly = i / LW, lx = i - ly * LW;
+                    v = __ldg(a + ly * w + lx);
+                    if (kFlip) v = __fmul_rn(__fadd_rn(v, __ldg(b + ly * w - lx)), 0.5f);
+                }
+                vals[u] = v;
             }
-            vals[u] = v;
+        } else {
+#pragma unroll
+            for (int u = 0; u < NL; ++u) {
+                const int i = lane + 32 * u;
+                float v = 0.0f;
+                if (i < LH * LW) {
+                    const int ly = i / LW, lx = i - ly * LW;
+                    const int gy = min(max(base_y + ly, 0), h - 1);
+                    const int gx = min(max(base_x + lx, 0), w - 1);
+                    v = __ldg(a + gy * w + gx);
+                    if (kFlip) v = __fmul_rn(__fadd_rn(v, __ldg(b + gy * w + (w - 1 - gx))), 0.5f);
+                }
+                vals[u] = v;
+            }
         }
     };
 
-    float vals[kLoads];
-    int item = blockIdx.x;
-    if (item < n_active) load_tile(tile_list[item], vals);
-    for (; item < n_active; item += gridDim.x) {
-        const int tile = tile_list[item];
-        const int tx = tile % tiles_x;
-        const int ty = (tile / tiles_x) % tiles_y;
-        const int plane = tile / (tiles_x * tiles_y);
-        const int cx0 = tx * kTileW, cy0 = ty * kTileH;
+    float vals[NL];
+    int item = blockIdx.x * kWarps + warp;
+    int4 blk = make_int4(0, 0, 0, 0), blk_next = blk;
+    if (item < n_active) {
+        blk = block_list[item];
+        load_block(blk, vals);
+    }
+    for (; item < n_active; item += stride, blk = blk_next) {
+        const int plane = blk.x;
+        const int cx0 = (blk.z & 0xffff) * BW, cy0 = (blk.z >> 16) * BH;
+        const int X0 = cx0 * S, Y0 = cy0 * S;
+        const int X = X0 + lane;
 
-        // 1. registers -> shared; start fetching the next tile of this CTA
+        __syncwarp();                       // the previous block's reads of the tile are done
 #pragma unroll
-        for (int u = 0; u < kLoads; ++u) {
-            const int i = tid + u * kFusedThreads;
-            if (i < LH * LW) s_lo[i / LW][i % LW] = vals[u];
+        for (int u = 0; u < NL; ++u) {
+            const int i = lane + 32 * u;
+            if (i < LH * LW) lo[i] = vals[u];
         }
-        if (item + (int)gridDim.x < n_active) load_tile(tile_list[item + gridDim.x], vals);
-        // 2. tap tables of the full-resolution columns / rows this tile produces
-        for (int j = tid; j < XW + YH; j += kFusedThreads) {
-            float wt[4];
-            if (j < XW) {
-                const int first = axis_first_tap(S * cx0 - 1 + j, inv, kCubic, wt);
-                s_xb[j] = first - (cx0 - HALO);
-#pragma unroll
-                for (int t = 0; t < TAPS; ++t) s_xw[t][j] = wt[t];
-            } else {
-                const int jj = j - XW;
-                const int first = axis_first_tap(S * cy0 - 1 + jj, inv, kCubic, wt);
-                s_yb[jj] = first - (cy0 - HALO);
-#pragma unroll
-                for (int t = 0; t < TAPS; ++t) s_yw[t][jj] = wt[t];
-            }
+        if (item + stride < n_active) {     // prefetch the next block of this warp into registers
+            blk_next = block_list[item + stride];
+            load_block(blk_next, vals);
         }
-        __syncthreads();
-        //    horizontal (2 HALO + 1)-window maximum of |cell| (the taps a cell's pixels can touch)
-        for (int i = tid; i < LH * LW; i += kFusedThreads) {
-            const int ly = i / LW, lx = i - ly * LW;
-            float m = 0.0f;
-            for (int dx = -HALO; dx <= HALO; ++dx) {
-                const int xx = min(max(lx + dx, 0), LW - 1);
-                m = fmaxf(m, fabsf(s_lo[ly][xx]));
-            }
-            s_am[ly][lx] = m;
-        }
-        __syncthreads();
-        // 3. interpolate every tile row along x: one thread per output column, taps in
-        //    registers; the other half of the CTA finishes the cell activity map meanwhile
-        if (tid < kFusedThreads / 2) {
-            for (int j = tid; j < XW; j += kFusedThreads / 2) {
-                const int xb = s_xb[j];
-                const float w0 = s_xw[0][j], w1 = s_xw[1][j], w2 = s_xw[TAPS - 2][j],
-                            w3 = s_xw[TAPS - 1][j];
-                for (int ly = 0; ly < LH; ++ly) {
-                    const float *row = &s_lo[ly][xb];
-                    s_hb[ly][j] = kCubic ? combine4(row[0], row[1], row[2], row[3], w0, w1, w2, w3)
-                                         : combine2(row[0], row[1], w0, w1);
-                }
-            }
-        } else {
-            for (int i = tid - kFusedThreads / 2; i < kTileH * kTileW; i += kFusedThreads / 2) {
-                const int cy = i / kTileW, cx = i - cy * kTileW;
-                float m = 0.0f;
-                for (int dy = 0; dy <= 2 * HALO; ++dy) m = fmaxf(m, s_am[cy + dy][cx + HALO]);
-                s_act[cy][cx] = !(m * kBound < thre) ? 1 : 0;
-            }
-        }
-        __syncthreads();
+        __syncwarp();
 
-        auto value_at = [&](int jy, int jx) {
-            const int yb = s_yb[jy];
-            return kCubic ? combine4(s_hb[yb][jx], s_hb[yb + 1][jx], s_hb[yb + TAPS - 2][jx],
-                                     s_hb[yb + TAPS - 1][jx], s_yw[0][jy], s_yw[1][jy],
-                                     s_yw[TAPS - 2][jy], s_yw[TAPS - 1][jy])
-                          : combine2(s_hb[yb][jx], s_hb[yb + 1][jx], s_yw[0][jy], s_yw[1][jy]);
+        // This lane's column: tile rows are interpolated along x one at a time (xrow) into a
+        // sliding window win[k] = row q + k of the column, k = 0 .. TAPS; the S pixels of cell row q
+        // combine win[0 .. TAPS-1] (phase < S / 2) or win[1 .. TAPS] along y.
+        const bool clamp_l = !kCubic && X < S / 2;
+        const int xb = clamp_l ? 1 : xb_phase;
+        const float wx0 = clamp_l ? 1.0f : wx[0], wx1 = clamp_l ? 0.0f : wx[1];
+        const bool inside = X < W;             // outside the image: zero padding of the NMS window
+        auto xrow = [&](int ly) {
+            const float *row = lo + ly * LW + xb;
+            const float v = kCubic ? combine4(row[0], row[1], row[2], row[3], wx0, wx1, wx[2], wx[3])
+                                   : combine2(row[0], row[1], wx0, wx1);
+            return inside ? v : 0.0f;
         };
-        // 4. full-resolution values of the active cells, threshold first; the 3x3 test only for
-        //    the few survivors.  A warp owns whole cell rows: the S output rows of a cell row
-        //    share TAPS + 1 rows of s_hb and their tap tables stay in registers while the lanes
-        //    sweep the columns.
-        constexpr int kWarps = kFusedThreads / 32;
-        constexpr int kRowsPerWarp = kTileH / kWarps;
-        static_assert(kTileH % kWarps == 0, "tile rows must split evenly over the warps");
-        const int warp = tid >> 5, lane = tid & 31;
+        float win[TAPS + 1];
+        win[0] = 0.0f;
+#pragma unroll
+        for (int k = 1; k <= TAPS; ++k) win[k] = xrow(k - 1);
+        auto ycombine = [&](int first, int p) {        // taps win[first ..], weights of phase p
+            return kCubic ? combine4(win[first], win[first + 1], win[first + TAPS - 2], win[first + TAPS - 1],
+                                     wy[p][0], wy[p][1], wy[p][TAPS - 2], wy[p][TAPS - 1])
+                          : combine2(win[first], win[first + 1], wy[p][0], wy[p][1]);
+        };
+        const bool clamp_t = !kCubic && Y0 == 0;
+
+        float vp = 0.0f, vc, vn = 0.0f;       // rows r - 1, r, r + 1 of this lane's column
+        if (Y0 > 0) vp = ycombine(1, S - 1);  // last pixel row of the cell row above the block
+        const int valid_q = min(h - cy0, BH + 1);     // cell rows of the image below the block's top
 #pragma unroll 1
-        for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-            const int cy = warp * kRowsPerWarp + rr;
-            if (S * (cy0 + cy) >= H) break;
-            int yoff[S];
-            float wv[S][TAPS];
-            const int yb0 = s_yb[cy * S + 1];
+        for (int q = 0; q < BH && q < valid_q; ++q) {
+#pragma unroll
+            for (int k = 0; k < TAPS; ++k) win[k] = win[k + 1];
+            win[TAPS] = xrow(q + TAPS);
+            const bool top = clamp_t && q == 0;    // bilinear rows above src = 0: value = first cell row
+            if (q == 0) vc = top ? combine2(win[1], win[2], 1.0f, 0.0f) : ycombine(0, 0);
 #pragma unroll
             for (int p = 0; p < S; ++p) {
-                const int jy = cy * S + p + 1;
-                yoff[p] = s_yb[jy] - yb0;        // 0 or 1: floor(src) changes at most once per cell
-#pragma unroll
-                for (int t = 0; t < TAPS; ++t) wv[p][t] = s_yw[t][jy];
-            }
-#pragma unroll 1
-            for (int jx = lane + 1; jx <= S * kTileW; jx += 32) {
-                const int X = S * cx0 + jx - 1;
-                const bool active = X < W && s_act[cy][(jx - 1) / S] != 0;
-                if (!__any_sync(0xffffffffu, active)) continue;
-                if (!active) continue;
-                float r[TAPS + 1];
-#pragma unroll
-                for (int t = 0; t <= TAPS; ++t) r[t] = s_hb[min(yb0 + t, LH - 1)][jx];
-#pragma unroll
-                for (int p = 0; p < S; ++p) {
-                    const int Y = S * (cy0 + cy) + p;
-                    if (Y >= H) break;
-                    float v;
-                    if (yoff[p] != 0) {              // warp-uniform
-                        v = kCubic ? combine4(r[1], r[2], r[TAPS - 1], r[TAPS], wv[p][0], wv[p][1],
-                                              wv[p][TAPS - 2], wv[p][TAPS - 1])
-                                   : combine2(r[1], r[2], wv[p][0], wv[p][1]);
-                    } else {
-                        v = kCubic ? combine4(r[0], r[1], r[TAPS - 2], r[TAPS - 1], wv[p][0],
-                                              wv[p][1], wv[p][TAPS - 2], wv[p][TAPS - 1])
-                                   : combine2(r[0], r[1], wv[p][0], wv[p][1]);
-                    }
-                    if (v >= thre) {
-                        const int jy = cy * S + p + 1;
-                        bool peak = true;      // zero padding outside the image: v >= thre > 0 wins
-                        for (int dy = -1; dy <= 1 && peak; ++dy)
-                            for (int dx = -1; dx <= 1; ++dx) {
-                                if (dy == 0 && dx == 0) continue;
-                                const int yn = Y + dy, xn = X + dx;
-                                if (yn < 0 || yn >= H || xn < 0 || xn >= W) continue;
-                                if (value_at(jy + dy, jx + dx) > v) {
-                                    peak = false;
-                                    break;
-                                }
+                const int r = q * S + p;
+                if (p + 1 < S) {
+                    vn = ycombine(p + 1 >= S / 2 ? 1 : 0, p + 1);
+                    if (top && p + 1 < S / 2) vn = combine2(win[1], win[2], 1.0f, 0.0f);
+                } else {
+                    // first pixel row of the next cell row; zero padding below the image
+                    vn = q + 1 < valid_q ? ycombine(1, 0) : 0.0f;
+                }
+                const bool pass = vc >= thre;         // thre > 0: padding never passes
+                if (__any_sync(kFull, pass)) {
+                    const float lp = __shfl_up_sync(kFull, vp, 1), lc = __shfl_up_sync(kFull, vc, 1),
+                                ln = __shfl_up_sync(kFull, vn, 1);
+                    const float rp = __shfl_down_sync(kFull, vp, 1), rc = __shfl_down_sync(kFull, vc, 1),
+                                rn = __shfl_down_sync(kFull, vn, 1);
+                    if (pass) {
+                        const int Y = Y0 + r;
+                        bool peak = !(vp > vc) && !(vn > vc);
+                        if (lane > 0) peak = peak && !(lp > vc) && !(lc > vc) && !(ln > vc);
+                        if (lane < 31) peak = peak && !(rp > vc) && !(rc > vc) && !(rn > vc);
+                        // ring columns outside the block: evaluated only for a pixel that survived
+                        // everything else
+                        if (peak && ((lane == 0 && X0 > 0) || (lane == 31 && X + 1 < W))) {
+                            const int Xn = lane == 0 ? X - 1 : X + 1;
+                            for (int dy = -1; dy <= 1 && peak; ++dy) {
+                                if (Y + dy < 0 || Y + dy >= H) continue;
+                                peak = !(tile_value<S, kCubic, LW, HALO>(lo, cx0, cy0, Xn, Y + dy) > vc);
                             }
+                        }
                         if (peak) {
                             const uint32_t pos = atomicAdd(&cand_count[plane], 1u);
                             if (pos < (uint32_t)kCandCap)
                                 cand_keys[(size_t)plane * kCandCap + pos] =
-                                    make_key(v + 0.0f, (uint32_t)(Y * W + X));
+                                    make_key(vc + 0.0f, (uint32_t)(Y * W + X));
                         }
                     }
                 }
+                vp = vc;
+                vc = vn;
             }
         }
-        __syncthreads();          // the next tile overwrites the shared arrays
     }
 }
 
-template <int S>
-int launch_main(const float *hmp, const int32_t *kp_flip, int n, int c, int h, int w, bool cubic,
-                bool flip, float thre, const int32_t *tile_list, const int32_t *n_active,
-                uint32_t *cand_count, uint64_t *cand_keys, int grid, cudaStream_t s) {
-    if (cubic) {
-        if (flip) fused_nms_candidates_kernel<S, true, true><<<grid, kFusedThreads, 0, s>>>(hmp, kp_flip, n, c, h, w, thre, tile_list, n_active, cand_count, cand_keys);
-        else fused_nms_candidates_kernel<S, true, false><<<grid, kFusedThreads, 0, s>>>(hmp, kp_flip, n, c, h, w, thre, tile_list, n_active, cand_count, cand_keys);
-    } else {
-        if (flip) fused_nms_candidates_kernel<S, false, true><<<grid, kFusedThreads, 0, s>>>(hmp, kp_flip, n, c, h, w, thre, tile_list, n_active, cand_count, cand_keys);
-        else fused_nms_candidates_kernel<S, false, false><<<grid, kFusedThreads, 0, s>>>(hmp, kp_flip, n, c, h, w, thre, tile_list, n_active, cand_count, cand_keys);
-    }
+template <typename Kernel>
+int resident_grid(Kernel kernel, int sm_count) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFusedThreads, 0) != cudaSuccess ||
+        per_sm < 1)
+        per_sm = 1;
+    return sm_count * per_sm;
+}
+
+template <int S, bool kCubic, bool kFlip>
+int launch_blocks_t(const float *hmp, int h, int w, float thre, const int4 *block_list,
+                    const int32_t *n_active, uint32_t *cand_count, uint64_t *cand_keys, int sm_count,
+                    size_t blocks, cudaStream_t s) {
+    auto kernel = fused_block_kernel<S, kCubic, kFlip>;
+    // every CTA resident, warps stride over the work list
+    const int grid = (int)std::min<size_t>((blocks + kFusedThreads / 32 - 1) / (kFusedThreads / 32),
+                                           (size_t)resident_grid(kernel, sm_count));
+    kernel<<<grid, kFusedThreads, 0, s>>>(hmp, h, w, thre, block_list, n_active, cand_count, cand_keys);
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;
 }
 
-}  // namespace
-
-bool fused_supported(int scale, int h, int w) {
-    (void)h;
-    return (scale == 2 || scale == 4 || scale == 8) && (w + kTileW - 1) / kTileW <= 64;
+template <int S>
+int launch_blocks_s(const float *hmp, int h, int w, bool cubic, bool flip, float thre,
+                    const int4 *block_list, const int32_t *n_active, uint32_t *cand_count,
+                    uint64_t *cand_keys, int sm_count, size_t blocks, cudaStream_t s) {
+    if (cubic)
+        return flip ? launch_blocks_t<S, true, true>(hmp, h, w, thre, block_list, n_active, cand_count, cand_keys, sm_count, blocks, s)
+                    : launch_blocks_t<S, true, false>(hmp, h, w, thre, block_list, n_active, cand_count, cand_keys, sm_count, blocks, s);
+    return flip ? launch_blocks_t<S, false, true>(hmp, h, w, thre, block_list, n_active, cand_count, cand_keys, sm_count, blocks, s)
+                : launch_blocks_t<S, false, false>(hmp, h, w, thre, block_list, n_active, cand_count, cand_keys, sm_count, blocks, s);
 }
 
-size_t fused_tile_count(int n, int c, int h, int w) {
-    return (size_t)n * c * ((w + kTileW - 1) / kTileW) * ((h + kTileH - 1) / kTileH);
+inline size_t block_count(int n, int c, int h, int w, int scale) {
+    const int bw = 32 / scale;
+    return (size_t)n * c * ((w + bw - 1) / bw) * ((h + kBlockCellsH - 1) / kBlockCellsH);
+}
+
+}  // namespace
+
+bool fused_supported(int n, int c, int scale, int h, int w) {
+    if (!(scale == 2 || scale == 4 || scale == 8)) return false;
+    return block_count(n, c, h, w, scale) < 0x1fffffffULL && h < 65536 * kBlockCellsH && w < 65536 &&
+           (unsigned long long)h * scale * w * scale < 0xffffffffULL;
+}
+
+void fused_scratch(int n, int c, int h, int w, int scale, size_t *amax_floats, size_t *list_ints) {
+    *amax_floats = (size_t)n * c * ((w + kSub - 1) / kSub) * ((h + kSub - 1) / kSub);
+    *list_ints = 4 * block_count(n, c, h, w, scale);          // int4 entries
 }
 
 int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n, int c, int h, int w,
                             int scale, bool cubic, bool flip, float thre, uint32_t *cand_count,
-                            uint64_t *cand_keys, float *tile_amax, int32_t *tile_list,
+                            uint64_t *cand_keys, float *sub_amax, int32_t *block_list,
                             int32_t *n_active, int sm_count, cudaStream_t s, int64_t *launches) {
     if (n == 0) return OG_OK;
-    const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
-    const size_t tiles = fused_tile_count(n, c, h, w);
-    if (tiles > 0x7fffffffULL || tiles_x > 64) {
-        set_error("fused K1: %zu tiles (%d per row) exceed the supported range", tiles, tiles_x);
+    if (!fused_supported(n, c, scale, h, w)) {
+        set_error("fused K1: scale %d / %d x %d maps are outside the supported range", scale, h, w);
         return OG_ERR_UNSUPPORTED;
     }
     OG_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t) * (size_t)n * c, s));
     OG_CUDA_TRY(cudaMemsetAsync(n_active, 0, sizeof(int32_t), s));
-    const int bands = n * c * tiles_y;
-    if (flip) tile_scan_kernel<true><<<bands, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n, c, h, w, tile_amax);
-    else tile_scan_kernel<false><<<bands, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n, c, h, w, tile_amax);
+
+    const int sxs = (w + kSub - 1) / kSub, bands = (h + 2 * kSub - 1) / (2 * kSub);
+    const long long scan_threads = (long long)n * c * bands * sxs;
+    const unsigned scan_grid = (unsigned)((scan_threads + kScanThreads - 1) / kScanThreads);
+    // 128-bit loads need whole 4-cell groups and 16-byte aligned rows (also of the mirrored read)
+    const bool vec = (w % kSub) == 0 && (reinterpret_cast<uintptr_t>(hmp) & 15) == 0;
+    if (flip) {
+        if (vec) amax_scan_kernel<true, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n, c, h, w, sub_amax, scan_threads);
+        else amax_scan_kernel<true, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n, c, h, w, sub_amax, scan_threads);
+    } else {
+        if (vec) amax_scan_kernel<false, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n, c, h, w, sub_amax, scan_threads);
+        else amax_scan_kernel<false, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n, c, h, w, sub_amax, scan_threads);
+    }
     OG_CUDA_TRY(cudaGetLastError());
+
+    const size_t blocks = block_count(n, c, h, w, scale);
     const float limit = thre / (cubic ? 1.95f : 1.001f);
-    tile_list_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, s>>>(tile_amax, n * c, tiles_y, tiles_x,
-                                                                    limit, tile_list, n_active);
+    int4 *list4 = reinterpret_cast<int4 *>(block_list);
+    block_list_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, s>>>(
+        sub_amax, kp_flip_dev, n, c, flip ? 1 : 0, h, w, 32 / scale, cubic ? 2 : 1, limit,
+        (long long)blocks, list4, n_active);
     OG_CUDA_TRY(cudaGetLastError());
-    const int grid = (int)std::min<size_t>(tiles, (size_t)sm_count * 4);
+
     int st;
     switch (scale) {
-        case 2: st = launch_main<2>(hmp, kp_flip_dev, n, c, h, w, cubic, flip, thre, tile_list, n_active, cand_count, cand_keys, grid, s); break;
-        case 4: st = launch_main<4>(hmp, kp_flip_dev, n, c, h, w, cubic, flip, thre, tile_list, n_active, cand_count, cand_keys, grid, s); break;
-        case 8: st = launch_main<8>(hmp, kp_flip_dev, n, c, h, w, cubic, flip, thre, tile_list, n_active, cand_count, cand_keys, grid, s); break;
-        default:
-            set_error("fused K1: scale %d is not instantiated", scale);
-            return OG_ERR_UNSUPPORTED;
+        case 2: st = launch_blocks_s<2>(hmp, h, w, cubic, flip, thre, list4, n_active, cand_count, cand_keys, sm_count, blocks, s); break;
+        case 4: st = launch_blocks_s<4>(hmp, h, w, cubic, flip, thre, list4, n_active, cand_count, cand_keys, sm_count, blocks, s); break;
+        default: st = launch_blocks_s<8>(hmp, h, w, cubic, flip, thre, list4, n_active, cand_count, cand_keys, sm_count, blocks, s); break;
     }
     if (st == OG_OK && launches) *launches += 3;
     return st;

@@ -31,6 +31,8 @@
 // overflow (every new person consumes one limb row).
 #include "og_common.cuh"
 
+#include <mutex>
+
 namespace og {
 
 namespace {
@@ -575,9 +577,18 @@ size_t group_smem_bytes(const GroupLaunch &g) { return make_layout(g.c, g.l, g.k
 
 size_t group_prep_ints(const GroupLaunch &g) { return (size_t)g.n * g.l * (g.k + 1); }
 
+// The attribute belongs to the kernel (per device), not to a handle: handles with different
+// table sizes coexist, so it is only ever raised.
 int prepare_group_kernel(size_t smem_bytes) {
+    static std::mutex mu;
+    static size_t granted[64] = {0};
+    int dev = 0;
+    OG_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && smem_bytes <= granted[dev]) return OG_OK;
     OG_CUDA_TRY(cudaFuncSetAttribute(group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_bytes));
+    if (dev >= 0 && dev < 64) granted[dev] = smem_bytes;
     return OG_OK;
 }
 

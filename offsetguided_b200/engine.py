@@ -234,6 +234,15 @@ class DecoderEngine(object):
     def fused_redo_count(self):
         return int(self.lib.og_fused_redo_count(self._h))
 
+    def set_zero_copy(self, on=True):
+        """Host inputs on the fused path: leave the offset maps in pinned host memory and let K2
+        gather its samples over PCIe (default), or copy them as a whole."""
+        _lib.check(self.lib.og_set_zero_copy(self._h, 1 if on else 0))
+
+    @property
+    def zero_copy_count(self):
+        return int(self.lib.og_zero_copy_count(self._h))
+
     def enable_stage_timing(self, on=True):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.og_enable_stage_timing(self._h, 1 if on else 0))

@@ -415,6 +415,59 @@ def test_fused_path_overflow_reruns_exactly(cuda_device):
     assert np.array_equal(fused[0], staged[0]) and len(fused[0]) > 10
 
 
+def test_host_offsets_stay_on_the_host(cuda_device):
+    """Host API, fused path: pinned offset maps are not copied (K2 gathers its samples over
+    PCIe); pageable maps are copied as a whole; a candidate overflow re-runs the batch exactly
+    after copying them.  All three give the results of the device-resident call."""
+    import bench
+    skel = cfg.COCO_PERSON_SKELETON
+    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel)
+    hmp, omp = bench.lowres_inputs(777, 3, 320, True)
+    th, to = torch.from_numpy(hmp), torch.from_numpy(omp)
+    eng = DecoderEngine(17, skel, topk=32, thre_hmp=0.04, dist_max=40, use_scale=True, person_thre=0.04)
+    ref = eng.decode_features(th.cuda(), to.cuda(), 4, 4, 'bicubic', (kp, fl, rs))
+    ref_int = [t.cpu().numpy() for t in eng.last_intermediates(3)]
+    assert sum(len(p) for p in ref) >= 12 and eng.zero_copy_count == 0
+    pinned = eng.decode_features(th.pin_memory(), to.pin_memory(), 4, 4, 'bicubic', (kp, fl, rs))
+    pin_int = [t.cpu().numpy() for t in eng.last_intermediates(3)]
+    assert eng.zero_copy_count == 1
+    pageable = eng.decode_features(th, to, 4, 4, 'bicubic', (kp, fl, rs))
+    assert eng.zero_copy_count == 1
+    eng.set_zero_copy(False)
+    copied = eng.decode_features(th.pin_memory(), to.pin_memory(), 4, 4, 'bicubic', (kp, fl, rs))
+    assert eng.zero_copy_count == 1 and eng.fused_redo_count == 0
+    for a, b in zip(ref_int, pin_int):
+        assert np.array_equal(a, b)
+    for r, a, b, c in zip(ref, pinned, pageable, copied):
+        assert np.array_equal(r, a) and np.array_equal(r, b) and np.array_equal(r, c)
+    # overflow of the candidate lists with the offsets still on the host
+    eng.set_zero_copy(True)
+    rng = np.random.RandomState(5)
+    nh = torch.from_numpy(rng.uniform(0, 1, size=(1, 17, 160, 200)).astype(np.float32))
+    no = torch.from_numpy(rng.uniform(-8, 8, size=(1, 38, 160, 200)).astype(np.float32))
+    over = eng.decode_features(nh.pin_memory(), no.pin_memory(), 4, 4, 'bicubic', None)
+    assert eng.fused_redo_count == 1 and eng.zero_copy_count == 2
+    eng.set_fused(False)
+    staged = eng.decode_features(nh.cuda(), no.cuda(), 4, 4, 'bicubic', None)
+    assert np.array_equal(over[0], staged[0]) and len(over[0]) > 5
+
+
+def test_handles_with_different_table_sizes_coexist(cuda_device):
+    """K3's dynamic shared memory attribute is per kernel, not per handle: a handle with a small
+    person table created later must not shrink it for an earlier, larger one."""
+    skel = cfg.COCO_PERSON_SKELETON
+    heat, offs = scenes.synth_hires_batch(99, 2, 4, 320, 256, skel)
+    th, to = torch.from_numpy(heat).cuda(), torch.from_numpy(offs).cuda()
+    big = DecoderEngine(17, skel, topk=32, thre_hmp=0.05, dist_max=40, use_scale=True, person_thre=0.05)
+    first = big.decode_maps(th, to)
+    small = DecoderEngine(17, skel[:4], topk=2, thre_hmp=0.05, dist_max=40, use_scale=True, person_thre=0.05)
+    small.decode_maps(th, to[:, :8].contiguous())
+    again = big.decode_maps(th, to)
+    for a, b in zip(first, again):
+        assert np.array_equal(a, b)
+
+
 def test_two_decodes_in_flight(cuda_device):
     """The handle queues up to two decode calls; results come back oldest first and equal
     the synchronous results; a third un-fetched call is refused."""
