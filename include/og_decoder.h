@@ -163,9 +163,14 @@ int og_resize_f32(const float *in_dev, float *out_dev, int planes, int hgt, int 
 
 /* ---- whole path ----------------------------------------------------------- */
 
-/* generate_limbs + group_skeletons on full-resolution device maps:
- * K1 -> K2 -> K3 stream-ordered, then an asynchronous copy of the packed poses
- * into pinned memory of the handle.  Returns immediately; og_fetch_poses() synchronises. */
+/* generate_limbs + group_skeletons on full-resolution device maps: K1 on `stream`
+ * (after whatever produced the maps there), then K2 -> K3 -> an asynchronous copy of the
+ * packed poses into pinned memory of the handle on a high-priority stream OWNED BY THE
+ * HANDLE, ordered after K1 by an event.  K2 / K3 are latency-bound and fill a fraction of
+ * the SMs, so the next call's K1 (HBM-bound) runs beside them instead of behind them.
+ * Returns immediately; og_fetch_poses() synchronises.  Every input buffer of an og_decode_*
+ * call must stay valid and unmodified until its og_fetch_poses returns (K2 reads the offset
+ * maps after the call has returned, not in `stream` order). */
 int og_decode_maps(og_handle *h, const float *heat_dev, const float *offs_dev,
                    const float *scales_dev, int n, int hgt, int w, void *stream);
 
@@ -235,8 +240,9 @@ int64_t og_fused_redo_count(const og_handle *h);
 int og_set_zero_copy(og_handle *h, int enable);
 int64_t og_zero_copy_count(const og_handle *h);
 
-/* Per-stage device timing of og_decode_* calls with CUDA events recorded on the
- * launching stream.   og_last_stage_times_ms() reports the most recently FETCHED decode call:
+/* Per-stage device timing of og_decode_* calls with CUDA events recorded on the stream
+ * each stage is launched on (input staging and K1: the caller's stream; K2, K3, D2H: the
+ * handle's stream).  og_last_stage_times_ms() reports the most recently FETCHED decode call:
  * out6 = { input copy + flip + resize, K1 pass 1 (NMS stream), K1 pass 2 (select),
  *          K2, K3, pose D2H } in milliseconds. */
 int og_enable_stage_timing(og_handle *h, int enable);

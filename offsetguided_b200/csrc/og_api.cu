@@ -70,7 +70,8 @@ struct PinnedBuf {
 }  // namespace
 
 constexpr int kSlots = 2;          // decode calls that may be in flight before a fetch
-constexpr int kStageEvents = 7;    // start, after prep, K1 pass 1, K1 pass 2, K2, K3, D2H
+// start, after prep, K1 pass 1, K1 pass 2 (caller's stream) | K2 start, K2, K3, D2H (handle's stream)
+constexpr int kStageEvents = 8;
 
 struct FeatureArgs {               // arguments of a features decode, kept for the exact redo
     const float *hmp, *off;
@@ -83,6 +84,10 @@ struct ResultSlot {
     DevBuf<unsigned char> out;          // [meta int32][pose rows float]
     PinnedBuf<unsigned char> out_host;
     DevBuf<float> in_hmp, in_off;       // staged network-resolution inputs (host API)
+    DevBuf<float> det_score;            // K1 output of this call (written on the caller's stream,
+    DevBuf<int32_t> det_index;          //  read by K2 on the handle's stream while the next
+    DevBuf<int32_t> det_count;          //  call's K1 already runs)
+    cudaEvent_t k1_done = nullptr;
     cudaEvent_t done = nullptr;
     cudaEvent_t ev[kStageEvents] = {nullptr};
     cudaStream_t stream = nullptr;
@@ -108,9 +113,7 @@ struct og_handle {
     // intermediates, reused by consecutive calls in stream order
     DevBuf<uint32_t> cand_count;
     DevBuf<uint64_t> cand_keys;
-    DevBuf<float> det_score;
-    DevBuf<int32_t> det_index;
-    DevBuf<int32_t> det_count;
+    cudaStream_t aux;                   // K2 -> K3 -> D2H of every call, high priority
     DevBuf<float> limbs;
     DevBuf<float> slab;
     DevBuf<int32_t> group_prep;
@@ -238,9 +241,9 @@ int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused
     const og_config &c = h->cfg;
     OG_TRY(check_maps(n, hgt, w, c.n_keypoints));
     const size_t dets = (size_t)n * c.n_keypoints * c.topk;
-    OG_TRY(h->det_score.ensure(dets));
-    OG_TRY(h->det_index.ensure(dets));
-    OG_TRY(h->det_count.ensure((size_t)n * c.n_keypoints));
+    OG_TRY(slot->det_score.ensure(dets));
+    OG_TRY(slot->det_index.ensure(dets));
+    OG_TRY(slot->det_count.ensure((size_t)n * c.n_keypoints));
     OG_TRY(h->limbs.ensure((size_t)n * c.n_limbs * c.topk * OG_LIMB_COLS));
     const int capacity_rows = n * c.n_limbs * c.topk;
     const size_t mbytes = meta_bytes_for(n);
@@ -276,29 +279,36 @@ int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused
                                            h->sm_count, s, &h->launches));
             OG_TRY(mark(h, slot, 2, s));
             OG_TRY(launch_select_topk(nullptr, planes, hgt, w, c.thre_hmp, c.topk, h->cand_count.ptr,
-                                      h->cand_keys.ptr, h->det_score.ptr, h->det_index.ptr,
-                                      h->det_count.ptr, meta + 2 * n + 1, s));
+                                      h->cand_keys.ptr, slot->det_score.ptr, slot->det_index.ptr,
+                                      slot->det_count.ptr, meta + 2 * n + 1, s));
             h->launches += 1;
         } else {
-            OG_TRY(run_k1(h, heat, n, hgt, w, c.thre_hmp, h->det_score.ptr, h->det_index.ptr,
-                          h->det_count.ptr, s, h->timing ? slot->ev[2] : nullptr));
+            OG_TRY(run_k1(h, heat, n, hgt, w, c.thre_hmp, slot->det_score.ptr, slot->det_index.ptr,
+                          slot->det_count.ptr, s, h->timing ? slot->ev[2] : nullptr));
         }
         OG_TRY(mark(h, slot, 3, s));
-        OG_TRY(launch_limb_score(h->det_score.ptr, h->det_index.ptr, offs, offs_lowres, scales, extras,
-                                 n, c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp,
-                                 c.min_len, c.resize_factor, h->limbs.ptr, s));
+        // K2 -> K3 -> D2H run on the handle's own high-priority stream: they are latency-bound
+        // and occupy a fraction of the SMs, so the next call's K1 (HBM-bound, on the caller's
+        // stream) overlaps them instead of queueing behind them.
+        cudaStream_t a = h->aux;
+        OG_CUDA_TRY(cudaEventRecord(slot->k1_done, s));
+        OG_CUDA_TRY(cudaStreamWaitEvent(a, slot->k1_done, 0));
+        OG_TRY(mark(h, slot, 4, a));
+        OG_TRY(launch_limb_score(slot->det_score.ptr, slot->det_index.ptr, offs, offs_lowres, scales,
+                                 extras, n, c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp,
+                                 c.min_len, c.resize_factor, h->limbs.ptr, a));
         h->launches += 1;
-        OG_TRY(mark(h, slot, 4, s));
-        OG_TRY(run_k3(h, h->limbs.ptr, n, poses, capacity_rows, meta, meta + n, meta + 2 * n, s, false));
-        OG_TRY(mark(h, slot, 5, s));
+        OG_TRY(mark(h, slot, 5, a));
+        OG_TRY(run_k3(h, h->limbs.ptr, n, poses, capacity_rows, meta, meta + n, meta + 2 * n, a, false));
+        OG_TRY(mark(h, slot, 6, a));
         // one asynchronous copy: meta + the pose rows the previous batches suggest
         const int rows = std::min(capacity_rows, h->rows_hint > 0 ? h->rows_hint : n * 32);
         const size_t bytes = mbytes + (size_t)rows * pose_row_bytes(h);
-        OG_CUDA_TRY(cudaMemcpyAsync(slot->out_host.ptr, slot->out.ptr, bytes, cudaMemcpyDeviceToHost, s));
-        OG_TRY(mark(h, slot, 6, s));
+        OG_CUDA_TRY(cudaMemcpyAsync(slot->out_host.ptr, slot->out.ptr, bytes, cudaMemcpyDeviceToHost, a));
+        OG_TRY(mark(h, slot, 7, a));
         slot->timed = h->timing;
         slot->rows_copied = rows;
-        OG_CUDA_TRY(cudaEventRecord(slot->done, s));
+        OG_CUDA_TRY(cudaEventRecord(slot->done, a));
     }
     if (!slot->pending) {           // a redo keeps its place in the queue
         slot->pending = true;
@@ -368,6 +378,11 @@ int decode_features_impl(og_handle *h, ResultSlot *slot, const float *hmp, const
         return decode_core(h, slot, nullptr, &k1, nullptr, &src, nullptr, n, hgt * hmp_stride,
                            w * hmp_stride, s);
     }
+    // Materialising path: the flip / resize outputs below are handle-owned and still read by
+    // K2 of an earlier call on the handle's stream, so this call's writes wait for those calls.
+    for (int i = 0; i < kSlots; ++i)
+        if (&h->slots[i] != slot && h->slots[i].pending && h->slots[i].n > 0)
+            OG_CUDA_TRY(cudaStreamWaitEvent(s, h->slots[i].done, 0));
     if (flip_test) {
         OG_TRY(h->fused_hmp.ensure((size_t)n * c.n_keypoints * hw));
         OG_TRY(h->fused_off.ensure((size_t)n * 2 * c.n_limbs * hw));
@@ -513,8 +528,20 @@ int og_create(const og_config *cfg, og_handle **out) {
         delete h;
         return st;
     }
+    {
+        int least = 0, greatest = 0;
+        cudaError_t err = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (err == cudaSuccess) err = cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, greatest);
+        if (err != cudaSuccess) {
+            h->aux = nullptr;
+            og_destroy(h);
+            set_error("cudaStreamCreateWithPriority failed: %s", cudaGetErrorString(err));
+            return OG_ERR_CUDA;
+        }
+    }
     for (int i = 0; i < kSlots; ++i) {
         cudaError_t err = cudaEventCreateWithFlags(&h->slots[i].done, cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->slots[i].k1_done, cudaEventDisableTiming);
         if (err != cudaSuccess) {
             og_destroy(h);
             set_error("cudaEventCreate failed: %s", cudaGetErrorString(err));
@@ -530,9 +557,6 @@ int og_destroy(og_handle *h) {
     cudaDeviceSynchronize();
     h->cand_count.release();
     h->cand_keys.release();
-    h->det_score.release();
-    h->det_index.release();
-    h->det_count.release();
     h->limbs.release();
     h->slab.release();
     h->group_prep.release();
@@ -551,10 +575,15 @@ int og_destroy(og_handle *h) {
         sl.out_host.release();
         sl.in_hmp.release();
         sl.in_off.release();
+        sl.det_score.release();
+        sl.det_index.release();
+        sl.det_count.release();
         if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.k1_done) cudaEventDestroy(sl.k1_done);
         for (int e = 0; e < kStageEvents; ++e)
             if (sl.ev[e]) cudaEventDestroy(sl.ev[e]);
     }
+    if (h->aux) cudaStreamDestroy(h->aux);
     delete h;
     return OG_OK;
 }
@@ -662,6 +691,7 @@ int og_group_f32(og_handle *h, const float *limbs_dev, int n, float *out_poses_d
     OG_REQUIRE(h && limbs_dev && out_poses_dev && out_offset_dev && out_count_dev && out_total_dev,
                "og_group_f32: null pointer");
     OG_REQUIRE(n >= 0 && capacity_rows >= 0, "og_group_f32: negative size");
+    OG_REQUIRE(h->pending == 0, "og_group_f32: fetch the pending decode calls first (shared scratch)");
     OG_TRY(check_device(h));
     return run_k3(h, limbs_dev, n, out_poses_dev, capacity_rows, out_offset_dev, out_count_dev,
                   out_total_dev, static_cast<cudaStream_t>(stream));
@@ -834,8 +864,8 @@ int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offse
             const size_t at = slot->meta_bytes + (size_t)slot->rows_copied * row;
             OG_CUDA_TRY(cudaMemcpyAsync(slot->out_host.ptr + at, slot->out.ptr + at,
                                         (size_t)(total - slot->rows_copied) * row,
-                                        cudaMemcpyDeviceToHost, slot->stream));
-            OG_CUDA_TRY(cudaStreamSynchronize(slot->stream));
+                                        cudaMemcpyDeviceToHost, h->aux));
+            OG_CUDA_TRY(cudaStreamSynchronize(h->aux));
             slot->rows_copied = total;
         }
         h->rows_hint = total + total / 2 + 16;      // speculative D2H size of the next batch
@@ -862,11 +892,13 @@ int og_copy_intermediates(og_handle *h, int n, float *det_score_dev, int32_t *de
     OG_TRY(check_device(h));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const og_config &c = h->cfg;
+    ResultSlot *slot = &h->slots[h->last_slot];
+    if (slot->n > 0) OG_CUDA_TRY(cudaStreamWaitEvent(s, slot->done, 0));     // K2 ran on the handle's stream
     const size_t dets = (size_t)n * c.n_keypoints * c.topk;
     if (det_score_dev && dets)
-        OG_CUDA_TRY(cudaMemcpyAsync(det_score_dev, h->det_score.ptr, dets * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        OG_CUDA_TRY(cudaMemcpyAsync(det_score_dev, slot->det_score.ptr, dets * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (det_index_dev && dets)
-        OG_CUDA_TRY(cudaMemcpyAsync(det_index_dev, h->det_index.ptr, dets * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        OG_CUDA_TRY(cudaMemcpyAsync(det_index_dev, slot->det_index.ptr, dets * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
     const size_t lim = (size_t)n * c.n_limbs * c.topk * OG_LIMB_COLS;
     if (limbs_dev && lim)
         OG_CUDA_TRY(cudaMemcpyAsync(limbs_dev, h->limbs.ptr, lim * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -913,8 +945,10 @@ int og_last_stage_times_ms(og_handle *h, float *out6) {
     OG_REQUIRE(h->fetched_slot >= 0 && h->slots[h->fetched_slot].timed,
                "og_last_stage_times_ms: enable stage timing, decode and fetch first");
     ResultSlot *slot = &h->slots[h->fetched_slot];
-    OG_CUDA_TRY(cudaEventSynchronize(slot->ev[6]));
-    for (int i = 0; i < 6; ++i) OG_CUDA_TRY(cudaEventElapsedTime(&out6[i], slot->ev[i], slot->ev[i + 1]));
+    OG_CUDA_TRY(cudaEventSynchronize(slot->ev[kStageEvents - 1]));
+    static const int first[6] = {0, 1, 2, 4, 5, 6};     // ev[3] -> ev[4] is the hand-over between streams
+    for (int i = 0; i < 6; ++i)
+        OG_CUDA_TRY(cudaEventElapsedTime(&out6[i], slot->ev[first[i]], slot->ev[first[i] + 1]));
     return OG_OK;
 }
 

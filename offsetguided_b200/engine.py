@@ -3,6 +3,7 @@
 PyTorch is used for device memory, streams and the numpy bridge only; every
 computation is a call into libogdecoder.so through ``_lib``.
 """
+import collections
 import ctypes
 
 import numpy as np
@@ -62,6 +63,9 @@ class DecoderEngine(object):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.og_create(ctypes.byref(cfg), ctypes.byref(handle)))
         self._h = handle
+        # input tensors of the decode calls in flight: K2 reads the offset maps on the handle's
+        # stream after the call has returned, so they must outlive the call (until its fetch)
+        self._inflight = collections.deque()
 
     def close(self):
         if getattr(self, '_h', None):
@@ -155,6 +159,8 @@ class DecoderEngine(object):
         total = ctypes.c_int32(0)
         _lib.check(self.lib.og_fetch_poses(self._h, ctypes.byref(poses_p), ctypes.byref(off_p),
                                            ctypes.byref(cnt_p), ctypes.byref(total)))
+        if self._inflight:
+            self._inflight.popleft()
         if n == 0:
             return []
         c = self.n_keypoints
@@ -182,7 +188,7 @@ class DecoderEngine(object):
             _lib.check(self.lib.og_decode_maps_ex(self._h, _ptr(heat), _ptr(offs), _ptr(scales),
                                                   _ptr(jomps), int(vector_nd), 1 if use_jitter else 0,
                                                   n, h, w, _stream_ptr(self.device)))
-            self._keep_maps = (heat, offs, scales, jomps)
+            self._inflight.append((heat, offs, scales, jomps))
             if not fetch:
                 return n
             return self._fetch(n)
@@ -212,7 +218,7 @@ class DecoderEngine(object):
         with torch.cuda.device(self.device):
             _lib.check(fn(self._h, _ptr(hmp), _ptr(off), n, h, w, int(hmp_stride), int(off_stride),
                           mode, 1 if flip else 0, *args, _stream_ptr(self.device)))
-            self._keepalive = (getattr(self, '_keepalive', (None,))[-1], (hmp, off))
+            self._inflight.append((hmp, off))
             if not fetch:
                 return n
             return self._fetch(n)
