@@ -1,6 +1,7 @@
 // C ABI of the decoder library (include/og_decoder.h): handle, buffer management,
 // stream-ordered composition of the kernels, host staging.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -70,6 +71,7 @@ struct PinnedBuf {
 }  // namespace
 
 constexpr int kSlots = 2;          // decode calls that may be in flight before a fetch
+constexpr int kMaxChunks = 8;      // image ranges of one host-API call (copy / decode pipeline)
 // start, after prep, K1 pass 1, K1 pass 2 (caller's stream) | K2 start, K2, K3, D2H (handle's stream)
 constexpr int kStageEvents = 8;
 
@@ -87,7 +89,9 @@ struct ResultSlot {
     DevBuf<float> det_score;            // K1 output of this call (written on the caller's stream,
     DevBuf<int32_t> det_index;          //  read by K2 on the handle's stream while the next
     DevBuf<int32_t> det_count;          //  call's K1 already runs)
-    cudaEvent_t k1_done = nullptr;
+    cudaEvent_t k1_done[kMaxChunks] = {nullptr};
+    cudaEvent_t copied[kMaxChunks] = {nullptr};
+    cudaEvent_t call_start = nullptr;
     cudaEvent_t done = nullptr;
     cudaEvent_t ev[kStageEvents] = {nullptr};
     cudaStream_t stream = nullptr;
@@ -114,6 +118,7 @@ struct og_handle {
     DevBuf<uint32_t> cand_count;
     DevBuf<uint64_t> cand_keys;
     cudaStream_t aux;                   // K2 -> K3 -> D2H of every call, high priority
+    cudaStream_t cp;                    // host API: input copies, one image range ahead of the kernels
     DevBuf<float> limbs;
     DevBuf<float> slab;
     DevBuf<int32_t> group_prep;
@@ -135,6 +140,7 @@ struct og_handle {
 
     bool fused_enabled;
     bool zero_copy_enabled;      // host API: K2 gathers offsets straight from pinned host memory
+    int host_chunks;             // host API: image ranges of the copy / decode pipeline
     int64_t fused_redos;
     int64_t zero_copy_calls;
     bool tables_valid;           // device flip tables match the cached host copies
@@ -233,11 +239,9 @@ struct K1Fused {
     bool cubic, flip;
 };
 
-// Shared body of every decode call: K1 (full-resolution stream, or the fused
-// network-resolution kernel) -> K2 -> K3 -> asynchronous D2H into the slot.
-int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused *fused,
-                const float *offs, const OffsetSource *offs_lowres, const float *scales, int n,
-                int hgt, int w, cudaStream_t s, const LimbExtras *extras = nullptr) {
+// One decode call = begin_call, decode_range over one or more image ranges, finish_call.
+// begin_call: buffers of the slot, meta words cleared, first stage marks.
+int begin_call(og_handle *h, ResultSlot *slot, bool fused, int n, int hgt, int w, cudaStream_t s) {
     const og_config &c = h->cfg;
     OG_TRY(check_maps(n, hgt, w, c.n_keypoints));
     const size_t dets = (size_t)n * c.n_keypoints * c.topk;
@@ -249,61 +253,106 @@ int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused
     const size_t mbytes = meta_bytes_for(n);
     OG_TRY(slot->out.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
     OG_TRY(slot->out_host.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
-    int32_t *meta = reinterpret_cast<int32_t *>(slot->out.ptr);
-    float *poses = reinterpret_cast<float *>(slot->out.ptr + mbytes);
-
+    if (n > 0) {
+        const int planes = n * c.n_keypoints;
+        OG_TRY(h->cand_count.ensure(planes));
+        OG_TRY(h->cand_keys.ensure((size_t)planes * kCandCap));
+    }
     slot->n = n;
     slot->meta_bytes = mbytes;
     slot->capacity_rows = capacity_rows;
     slot->stream = s;
-    slot->fused = fused != nullptr;
+    slot->fused = fused;
     slot->timed = false;
     slot->rows_copied = 0;
     if (!slot->prep_marked) OG_TRY(mark(h, slot, 0, s));
-    OG_TRY(mark(h, slot, 1, s));
     slot->prep_marked = false;
     if (n > 0) {
+        int32_t *meta = reinterpret_cast<int32_t *>(slot->out.ptr);
         OG_CUDA_TRY(cudaMemsetAsync(meta + 2 * n, 0, 2 * sizeof(int32_t), s));     // total, overflow
-        if (fused) {
-            const int planes = n * c.n_keypoints;
-            OG_TRY(h->cand_count.ensure(planes));
-            OG_TRY(h->cand_keys.ensure((size_t)planes * kCandCap));
-            size_t amax_floats = 0, tiles = 0;
-            fused_scratch(n, c.n_keypoints, fused->h, fused->w, fused->scale, &amax_floats, &tiles);
-            OG_TRY(h->tile_amax.ensure(amax_floats));
-            OG_TRY(h->tile_list.ensure(tiles + 1));
-            OG_TRY(launch_fused_candidates(fused->hmp, h->kp_flip.ptr, n, c.n_keypoints, fused->h,
-                                           fused->w, fused->scale, fused->cubic, fused->flip,
-                                           c.thre_hmp, h->cand_count.ptr, h->cand_keys.ptr,
-                                           h->tile_amax.ptr, h->tile_list.ptr, h->tile_list.ptr + tiles,
-                                           h->sm_count, s, &h->launches));
-            OG_TRY(mark(h, slot, 2, s));
-            OG_TRY(launch_select_topk(nullptr, planes, hgt, w, c.thre_hmp, c.topk, h->cand_count.ptr,
-                                      h->cand_keys.ptr, slot->det_score.ptr, slot->det_index.ptr,
-                                      slot->det_count.ptr, meta + 2 * n + 1, s));
-            h->launches += 1;
-        } else {
-            OG_TRY(run_k1(h, heat, n, hgt, w, c.thre_hmp, slot->det_score.ptr, slot->det_index.ptr,
-                          slot->det_count.ptr, s, h->timing ? slot->ev[2] : nullptr));
-        }
-        OG_TRY(mark(h, slot, 3, s));
-        // K2 -> K3 -> D2H run on the handle's own high-priority stream: they are latency-bound
-        // and occupy a fraction of the SMs, so the next call's K1 (HBM-bound, on the caller's
-        // stream) overlaps them instead of queueing behind them.
-        cudaStream_t a = h->aux;
-        OG_CUDA_TRY(cudaEventRecord(slot->k1_done, s));
-        OG_CUDA_TRY(cudaStreamWaitEvent(a, slot->k1_done, 0));
-        OG_TRY(mark(h, slot, 4, a));
-        OG_TRY(launch_limb_score(slot->det_score.ptr, slot->det_index.ptr, offs, offs_lowres, scales,
-                                 extras, n, c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp,
-                                 c.min_len, c.resize_factor, h->limbs.ptr, a));
+    }
+    return OG_OK;
+}
+
+// Images [i0, i0 + cn) of the call: K1 (full-resolution stream, or the fused network-resolution
+// kernels) on the caller's stream, then K2 -> K3 on the handle's stream.  `timed` ranges record
+// the stage events (the last range of a call).  All map pointers address image 0 of the call.
+int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, const float *heat,
+                 const K1Fused *fused, const float *offs, const OffsetSource *offs_lowres,
+                 const float *scales, int hgt, int w, cudaStream_t s, const LimbExtras *extras,
+                 bool timed) {
+    const og_config &c = h->cfg;
+    const int n = slot->n;
+    int32_t *meta = reinterpret_cast<int32_t *>(slot->out.ptr);
+    float *poses = reinterpret_cast<float *>(slot->out.ptr + slot->meta_bytes);
+    const size_t HW = (size_t)hgt * w;
+    const size_t det0 = (size_t)i0 * c.n_keypoints * c.topk;
+    const size_t plane0 = (size_t)i0 * c.n_keypoints;
+    float *det_score = slot->det_score.ptr + det0;
+    int32_t *det_index = slot->det_index.ptr + det0;
+    int32_t *det_count = slot->det_count.ptr + plane0;
+    uint32_t *cand_count = h->cand_count.ptr + plane0;
+    uint64_t *cand_keys = h->cand_keys.ptr + plane0 * kCandCap;
+    const int planes = cn * c.n_keypoints;
+    if (timed) OG_TRY(mark(h, slot, 1, s));
+    if (fused) {
+        size_t amax_floats = 0, tiles = 0;
+        fused_scratch(cn, c.n_keypoints, fused->h, fused->w, fused->scale, &amax_floats, &tiles);
+        OG_TRY(h->tile_amax.ensure(amax_floats));
+        OG_TRY(h->tile_list.ensure(tiles + 1));
+        // the mirrored copy of image i sits n images behind it: shifting the base keeps that offset
+        OG_TRY(launch_fused_candidates(fused->hmp + plane0 * fused->h * fused->w, h->kp_flip.ptr, cn, n,
+                                       c.n_keypoints, fused->h, fused->w, fused->scale, fused->cubic,
+                                       fused->flip, c.thre_hmp, cand_count, cand_keys, h->tile_amax.ptr,
+                                       h->tile_list.ptr, h->tile_list.ptr + tiles, h->sm_count, s,
+                                       &h->launches));
+        if (timed) OG_TRY(mark(h, slot, 2, s));
+        OG_TRY(launch_select_topk(nullptr, planes, hgt, w, c.thre_hmp, c.topk, cand_count, cand_keys,
+                                  det_score, det_index, det_count, meta + 2 * n + 1, s));
         h->launches += 1;
-        OG_TRY(mark(h, slot, 5, a));
-        OG_TRY(run_k3(h, h->limbs.ptr, n, poses, capacity_rows, meta, meta + n, meta + 2 * n, a, false));
-        OG_TRY(mark(h, slot, 6, a));
-        // one asynchronous copy: meta + the pose rows the previous batches suggest
-        const int rows = std::min(capacity_rows, h->rows_hint > 0 ? h->rows_hint : n * 32);
-        const size_t bytes = mbytes + (size_t)rows * pose_row_bytes(h);
+    } else {
+        OG_TRY(launch_nms_topk(heat + plane0 * HW, planes, hgt, w, c.thre_hmp, c.topk, cand_count,
+                               cand_keys, det_score, det_index, det_count, false, true, s, &h->launches,
+                               timed && h->timing ? slot->ev[2] : nullptr));
+    }
+    if (timed) OG_TRY(mark(h, slot, 3, s));
+    // K2 -> K3 -> D2H run on the handle's own high-priority stream: they are latency-bound
+    // and occupy a fraction of the SMs, so the next K1 (HBM-bound, on the caller's stream)
+    // overlaps them instead of queueing behind them.
+    cudaStream_t a = h->aux;
+    OG_CUDA_TRY(cudaEventRecord(slot->k1_done[chunk], s));
+    OG_CUDA_TRY(cudaStreamWaitEvent(a, slot->k1_done[chunk], 0));
+    if (timed) OG_TRY(mark(h, slot, 4, a));
+    const int nd = extras ? extras->vector_nd : 2;
+    OffsetSource src = {};
+    if (offs_lowres) {
+        src = *offs_lowres;
+        src.maps += (size_t)i0 * 2 * c.n_limbs * src.h * src.w;
+    }
+    LimbExtras ex = {nullptr, 2, 0};
+    if (extras) {
+        ex = *extras;
+        if (ex.jomps) ex.jomps += (size_t)i0 * 2 * HW;
+    }
+    float *limbs = h->limbs.ptr + (size_t)i0 * c.n_limbs * c.topk * OG_LIMB_COLS;
+    OG_TRY(launch_limb_score(det_score, det_index, offs ? offs + (size_t)i0 * nd * c.n_limbs * HW : nullptr,
+                             offs_lowres ? &src : nullptr, scales ? scales + plane0 * HW : nullptr,
+                             extras ? &ex : nullptr, cn, c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk,
+                             c.thre_hmp, c.min_len, c.resize_factor, limbs, a));
+    h->launches += 1;
+    if (timed) OG_TRY(mark(h, slot, 5, a));
+    OG_TRY(run_k3(h, limbs, cn, poses, slot->capacity_rows, meta + i0, meta + n + i0, meta + 2 * n, a, false));
+    if (timed) OG_TRY(mark(h, slot, 6, a));
+    return OG_OK;
+}
+
+// finish_call: one asynchronous copy of meta + the pose rows the previous batches suggest
+int finish_call(og_handle *h, ResultSlot *slot) {
+    const int n = slot->n;
+    if (n > 0) {
+        cudaStream_t a = h->aux;
+        const int rows = std::min(slot->capacity_rows, h->rows_hint > 0 ? h->rows_hint : n * 32);
+        const size_t bytes = slot->meta_bytes + (size_t)rows * pose_row_bytes(h);
         OG_CUDA_TRY(cudaMemcpyAsync(slot->out_host.ptr, slot->out.ptr, bytes, cudaMemcpyDeviceToHost, a));
         OG_TRY(mark(h, slot, 7, a));
         slot->timed = h->timing;
@@ -317,6 +366,18 @@ int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused
     }
     h->last_slot = (int)(slot - h->slots);
     return OG_OK;
+}
+
+// The whole batch as one range.
+int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused *fused,
+                const float *offs, const OffsetSource *offs_lowres, const float *scales, int n,
+                int hgt, int w, cudaStream_t s, const LimbExtras *extras = nullptr) {
+    OG_TRY(begin_call(h, slot, fused != nullptr, n, hgt, w, s));
+    if (n > 0)
+        OG_TRY(decode_range(h, slot, 0, 0, n, heat, fused, offs, offs_lowres, scales, hgt, w, s, extras, true));
+    else
+        OG_TRY(mark(h, slot, 1, s));
+    return finish_call(h, slot);
 }
 
 int upload_flip_tables(og_handle *h, const int32_t *kp_flip, const int32_t *limb_flip,
@@ -498,8 +559,15 @@ int og_create(const og_config *cfg, og_handle **out) {
     h->fetched_slot = -1;
     h->rows_hint = 0;
     h->timing = false;
+    h->aux = nullptr;
+    h->cp = nullptr;
     h->fused_enabled = true;
     h->zero_copy_enabled = true;
+    h->host_chunks = 4;
+    if (const char *env = getenv("OG_HOST_CHUNKS")) {          // tuning aid
+        const int v = atoi(env);
+        if (v >= 1 && v <= kMaxChunks) h->host_chunks = v;
+    }
     h->fused_redos = 0;
     h->zero_copy_calls = 0;
     h->tables_valid = false;
@@ -539,9 +607,19 @@ int og_create(const og_config *cfg, og_handle **out) {
             return OG_ERR_CUDA;
         }
     }
+    if (cudaStreamCreateWithFlags(&h->cp, cudaStreamNonBlocking) != cudaSuccess) {
+        h->cp = nullptr;
+        og_destroy(h);
+        set_error("cudaStreamCreateWithFlags failed");
+        return OG_ERR_CUDA;
+    }
     for (int i = 0; i < kSlots; ++i) {
         cudaError_t err = cudaEventCreateWithFlags(&h->slots[i].done, cudaEventDisableTiming);
-        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->slots[i].k1_done, cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->slots[i].call_start, cudaEventDisableTiming);
+        for (int j = 0; j < kMaxChunks && err == cudaSuccess; ++j) {
+            err = cudaEventCreateWithFlags(&h->slots[i].k1_done[j], cudaEventDisableTiming);
+            if (err == cudaSuccess) err = cudaEventCreateWithFlags(&h->slots[i].copied[j], cudaEventDisableTiming);
+        }
         if (err != cudaSuccess) {
             og_destroy(h);
             set_error("cudaEventCreate failed: %s", cudaGetErrorString(err));
@@ -579,11 +657,16 @@ int og_destroy(og_handle *h) {
         sl.det_index.release();
         sl.det_count.release();
         if (sl.done) cudaEventDestroy(sl.done);
-        if (sl.k1_done) cudaEventDestroy(sl.k1_done);
+        if (sl.call_start) cudaEventDestroy(sl.call_start);
+        for (int j = 0; j < kMaxChunks; ++j) {
+            if (sl.k1_done[j]) cudaEventDestroy(sl.k1_done[j]);
+            if (sl.copied[j]) cudaEventDestroy(sl.copied[j]);
+        }
         for (int e = 0; e < kStageEvents; ++e)
             if (sl.ev[e]) cudaEventDestroy(sl.ev[e]);
     }
     if (h->aux) cudaStreamDestroy(h->aux);
+    if (h->cp) cudaStreamDestroy(h->cp);
     delete h;
     return OG_OK;
 }
@@ -787,38 +870,73 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
     const og_config &c = h->cfg;
     const size_t n_in = (size_t)(flip_test ? 2 * n : n);
     const size_t hw = (size_t)hgt * w;
+    const bool fuse = h->fused_enabled && c.thre_hmp > 0.0f &&
+                      fused_supported(n, c.n_keypoints, hmp_stride, hgt, w);
     // Zero-copy offsets: on the fused path K2 reads 2 * L * K bilinear samples per image, a few
     // KB out of the 2L * h * w * 4 bytes of the offset maps.  When the caller's buffer is pinned
     // (device-accessible) host memory the maps are not copied at all; K2 gathers its samples over
     // PCIe.  Pageable buffers and the materialising path copy everything as before.
     const float *off_alias = nullptr;
-    if (h->zero_copy_enabled && n_in && h->fused_enabled && c.thre_hmp > 0.0f &&
-        fused_supported(n, c.n_keypoints, hmp_stride, hgt, w)) {
+    if (h->zero_copy_enabled && n_in && fuse) {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, off_host) == cudaSuccess &&
             attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr)
             off_alias = static_cast<const float *>(attr.devicePointer);
         else
-            (void)cudaGetLastError();       // not registered: clear the sticky-free error state
+            (void)cudaGetLastError();       // not registered: clear the error state
     }
-    OG_TRY(slot->in_hmp.ensure(std::max<size_t>(1, n_in * c.n_keypoints * hw)));
-    if (!off_alias) OG_TRY(slot->in_off.ensure(std::max<size_t>(1, n_in * 2 * c.n_limbs * hw)));
+    const size_t hmp_img = (size_t)c.n_keypoints * hw, off_img = (size_t)2 * c.n_limbs * hw;
+    OG_TRY(slot->in_hmp.ensure(std::max<size_t>(1, n_in * hmp_img)));
+    if (!off_alias) OG_TRY(slot->in_off.ensure(std::max<size_t>(1, n_in * off_img)));
     OG_TRY(mark(h, slot, 0, s));
     slot->prep_marked = h->timing;
-    if (n_in) {
-        OG_CUDA_TRY(cudaMemcpyAsync(slot->in_hmp.ptr, hmp_host, n_in * c.n_keypoints * hw * sizeof(float),
-                                    cudaMemcpyHostToDevice, s));
+
+    // The copies run on the handle's copy stream, one image range ahead of the kernels: while
+    // range j is decoded (K1f on `stream`, K2 / K3 on the handle's stream) range j + 1 crosses
+    // PCIe.  The buffers are ready in `stream` order, so the copy stream starts behind it.
+    OG_CUDA_TRY(cudaEventRecord(slot->call_start, s));
+    OG_CUDA_TRY(cudaStreamWaitEvent(h->cp, slot->call_start, 0));
+    // images [i0, i0 + cn) and, when flip-testing, their mirrored copies n images further on: one
+    // 2-row strided copy (row pitch = n images) instead of two transfers
+    auto copy_range = [&](int i0, int cn) -> int {
+        const size_t rows = flip_test ? 2 : 1;
+        OG_CUDA_TRY(cudaMemcpy2DAsync(slot->in_hmp.ptr + (size_t)i0 * hmp_img, (size_t)n * hmp_img * sizeof(float),
+                                      hmp_host + (size_t)i0 * hmp_img, (size_t)n * hmp_img * sizeof(float),
+                                      (size_t)cn * hmp_img * sizeof(float), rows, cudaMemcpyHostToDevice, h->cp));
         if (!off_alias)
-            OG_CUDA_TRY(cudaMemcpyAsync(slot->in_off.ptr, off_host, n_in * 2 * c.n_limbs * hw * sizeof(float),
-                                        cudaMemcpyHostToDevice, s));
+            OG_CUDA_TRY(cudaMemcpy2DAsync(slot->in_off.ptr + (size_t)i0 * off_img, (size_t)n * off_img * sizeof(float),
+                                          off_host + (size_t)i0 * off_img, (size_t)n * off_img * sizeof(float),
+                                          (size_t)cn * off_img * sizeof(float), rows, cudaMemcpyHostToDevice, h->cp));
+        return OG_OK;
+    };
+    const float *off_src = off_alias ? off_alias : slot->in_off.ptr;
+    if (!fuse || n == 0) {                  // materialising path: one range
+        if (n) OG_TRY(copy_range(0, n));
+        OG_CUDA_TRY(cudaEventRecord(slot->copied[0], h->cp));
+        OG_CUDA_TRY(cudaStreamWaitEvent(s, slot->copied[0], 0));
+        return decode_features_impl(h, slot, slot->in_hmp.ptr, off_src, n, hgt, w, hmp_stride,
+                                    off_stride, resize_mode, flip_test, s, true);
     }
-    const int st = decode_features_impl(h, slot, slot->in_hmp.ptr, off_alias ? off_alias : slot->in_off.ptr,
-                                        n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, s, true);
-    if (st == OG_OK && off_alias) {
-        slot->args.off_host = off_host;
-        h->zero_copy_calls += 1;
+    const int H = hgt * hmp_stride, W = w * hmp_stride;
+    OG_TRY(check_maps(n, H, W, c.n_keypoints));
+    slot->args = FeatureArgs{slot->in_hmp.ptr, off_alias ? nullptr : slot->in_off.ptr, n, hgt, w,
+                             hmp_stride, off_stride, resize_mode, flip_test, off_alias ? off_host : nullptr};
+    K1Fused k1 = {slot->in_hmp.ptr, hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
+    OffsetSource src = {off_src, hgt, w, off_stride, flip_test ? 1 : 0, n, h->limb_flip.ptr,
+                        h->limb_reserved.ptr};
+    OG_TRY(begin_call(h, slot, true, n, H, W, s));
+    const int per = std::max((n + h->host_chunks - 1) / h->host_chunks, std::min(n, 4));
+    int chunk = 0;
+    for (int i0 = 0; i0 < n; i0 += per, ++chunk) {
+        const int cn = std::min(per, n - i0);
+        const bool last = i0 + cn >= n;
+        OG_TRY(copy_range(i0, cn));
+        OG_CUDA_TRY(cudaEventRecord(slot->copied[chunk], h->cp));
+        OG_CUDA_TRY(cudaStreamWaitEvent(s, slot->copied[chunk], 0));
+        OG_TRY(decode_range(h, slot, chunk, i0, cn, nullptr, &k1, nullptr, &src, nullptr, H, W, s, nullptr, last));
     }
-    return st;
+    if (off_alias) h->zero_copy_calls += 1;
+    return finish_call(h, slot);
 }
 
 int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offset_host,

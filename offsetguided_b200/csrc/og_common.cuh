@@ -121,7 +121,8 @@ bool fused_supported(int n, int c, int scale, int h, int w);
 // scratch of the fused K1: floats of the 4 x 4-cell activity map, ints of the block work list
 void fused_scratch(int n, int c, int h, int w, int scale, size_t *amax_floats, size_t *list_ints);
 // sub_amax / block_list: fused_scratch() elements, n_active: one int
-int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n, int c, int h, int w,
+// `n` images starting at hmp; the mirrored copy of image i is image n_total + i (flip only)
+int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n, int n_total, int c, int h, int w,
                             int scale, bool cubic, bool flip, float thre, uint32_t *cand_count,
                             uint64_t *cand_keys, float *sub_amax, int32_t *block_list,
                             int32_t *n_active, int sm_count, cudaStream_t s, int64_t *launches);

@@ -412,7 +412,7 @@ void fused_scratch(int n, int c, int h, int w, int scale, size_t *amax_floats, s
     *list_ints = 4 * block_count(n, c, h, w, scale);          // int4 entries
 }
 
-int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n, int c, int h, int w,
+int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n, int n_total, int c, int h, int w,
                             int scale, bool cubic, bool flip, float thre, uint32_t *cand_count,
                             uint64_t *cand_keys, float *sub_amax, int32_t *block_list,
                             int32_t *n_active, int sm_count, cudaStream_t s, int64_t *launches) {
@@ -430,11 +430,11 @@ int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n,
     // 128-bit loads need whole 4-cell groups and 16-byte aligned rows (also of the mirrored read)
     const bool vec = (w % kSub) == 0 && (reinterpret_cast<uintptr_t>(hmp) & 15) == 0;
     if (flip) {
-        if (vec) amax_scan_kernel<true, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n, c, h, w, sub_amax, scan_threads);
-        else amax_scan_kernel<true, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n, c, h, w, sub_amax, scan_threads);
+        if (vec) amax_scan_kernel<true, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
+        else amax_scan_kernel<true, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
     } else {
-        if (vec) amax_scan_kernel<false, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n, c, h, w, sub_amax, scan_threads);
-        else amax_scan_kernel<false, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n, c, h, w, sub_amax, scan_threads);
+        if (vec) amax_scan_kernel<false, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
+        else amax_scan_kernel<false, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
     }
     OG_CUDA_TRY(cudaGetLastError());
 
@@ -442,7 +442,7 @@ int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n,
     const float limit = thre / (cubic ? 1.95f : 1.001f);
     int4 *list4 = reinterpret_cast<int4 *>(block_list);
     block_list_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, s>>>(
-        sub_amax, kp_flip_dev, n, c, flip ? 1 : 0, h, w, 32 / scale, cubic ? 2 : 1, limit,
+        sub_amax, kp_flip_dev, n_total, c, flip ? 1 : 0, h, w, 32 / scale, cubic ? 2 : 1, limit,
         (long long)blocks, list4, n_active);
     OG_CUDA_TRY(cudaGetLastError());
 
