@@ -13,6 +13,8 @@ person-thre 0.04, dist-max 40) at the north-star batch of 64 images per GPU.
   e2e       images/s through the reference-facing API PostProcess.generate_poses with
             HOST (pinned) network-resolution maps: H2D copy, flip fusion, x4 resize,
             K1..K3 and the D2H read of the poses are all inside the timed region;
+  features_dev  the same decode from DEVICE-resident network-resolution maps (the call
+            evaluate.py makes right after model(images)), extra key;
   roofline  K1 (both passes) algorithmic bytes N*C*H*W*4 over its CUDA-event duration,
             against the measured HBM copy peak (MEASURED_PEAKS.json);
   cpu_baseline  the oracle port of the reference decoder (oracle/) on the host cores, on
@@ -310,6 +312,31 @@ def run_b200(args):
     hmp_np, omp_np = lowres_inputs(5000 * (rank + 1), B, E, flip)
     hmp_h = torch.from_numpy(hmp_np).pin_memory()
     omp_h = torch.from_numpy(omp_np).pin_memory()
+
+    # ---- the call evaluate.py makes: DEVICE-resident network-resolution maps (right after
+    #      model(images)), fused flip + x4 resize + NMS, two batches in flight
+    hmp_d, omp_d = hmp_h.to(dev), omp_h.to(dev)
+    tables = (cfg.heatmap_hflip(cfg.COCO_KEYPOINTS),) + tuple(cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel))
+    tables = tables if flip else None
+    for _ in range(args.warmup):
+        eng.decode_features(hmp_d, omp_d, 4, 4, 'bicubic', tables)
+    barrier()
+    dev_l0 = eng.launch_count
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_stages = []
+    f0.record()
+    eng.decode_features(hmp_d, omp_d, 4, 4, 'bicubic', tables, fetch=False)
+    for _ in range(args.steps - 1):
+        eng.decode_features(hmp_d, omp_d, 4, 4, 'bicubic', tables, fetch=False)
+        eng.fetch(B)
+        dev_stages.append(eng.last_stage_times_ms())
+    eng.fetch(B)
+    dev_stages.append(eng.last_stage_times_ms())
+    f1.record()
+    barrier()
+    dev_ms = f0.elapsed_time(f1)
+    dev_launches = eng.launch_count - dev_l0
+    del hmp_d, omp_d
     feats = [[[hmp_h], [[]], [[]]], [[omp_h], [[]], [[]]]]
     e2e_eng = post._engine(dev)
     e2e_eng.enable_stage_timing(True)
@@ -358,10 +385,10 @@ def run_b200(args):
     e2e_eng.set_zero_copy(True)
 
     # ---- max over ranks
-    times = torch.tensor([hot_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([hot_ms, e2e_s * 1e3, dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    hot_ms, e2e_ms = [float(v) for v in times.cpu()]
+    hot_ms, e2e_ms, dev_ms = [float(v) for v in times.cpu()]
 
     if rank == 0:
         k1_ms = statistics.mean(s['k1_stream'] + s['k1_select'] for s in stages)
@@ -409,9 +436,17 @@ def run_b200(args):
                                   'ms_per_step': full_copy_ms, 'h2d_bytes_per_step': h2d_full,
                                   'note': 'same call with og_set_zero_copy(0): heat and offset maps both copied '
                                           '(rank 0 time, %d steps)' % full_steps}},
-            'gpu_launches': hot_launches + e2e_launches_all,
+            'features_dev': {'value': n_gpus * B * args.steps / (dev_ms * 1e-3), 'unit': UNIT,
+                             'ms_per_step': dev_ms / args.steps,
+                             'stage_ms': {k: statistics.mean(s[k] for s in dev_stages) for k in dev_stages[0]},
+                             'note': 'same API on DEVICE-resident network-resolution maps (what evaluate.py '
+                                     'hands over after model(images)): fused flip + x4 bicubic + NMS (K1f), '
+                                     'offsets sampled at the candidates; 223 MB of heat maps read per step, '
+                                     'no full-resolution map written; two batches in flight'},
+            'gpu_launches': hot_launches + e2e_launches_all + dev_launches,
             'gpu_launches_detail': {'hot_path': hot_launches, 'e2e': e2e_launches,
-                                    'e2e_full_copy': e2e_launches_all - e2e_launches},
+                                    'e2e_full_copy': e2e_launches_all - e2e_launches,
+                                    'features_dev': dev_launches},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'kernel': 'K1 = nms_candidates_kernel + select_topk_kernel',

@@ -134,9 +134,16 @@ block_list_kernel(const float *__restrict__ sub_amax, const int32_t *__restrict_
         const int sx1 = min(bx * block_w + block_w - 1 + halo, w - 1) / kSub;
         const int sy0 = max(by * kBlockCellsH - halo, 0) / kSub;
         const int sy1 = min(by * kBlockCellsH + kBlockCellsH - 1 + halo, h - 1) / kSub;
-        unsigned m = 0u;                   // independent loads, one compare (bit order = value order)
-        for (int sy = sy0; sy <= sy1; ++sy)
-            for (int sx = sx0; sx <= sx1; ++sx) m = max(m, __float_as_uint(p[sy * sxs + sx]));
+        // The window is at most 4 x 6 sub-blocks (8 + 2 halo rows, 16 + 2 halo columns): a fixed,
+        // fully unrolled trip count with clamped coordinates keeps all loads independent and in
+        // flight together (a repeated sub-block does not change the maximum); one compare at the
+        // end (bit order = value order for |v|).
+        unsigned m = 0u;
+#pragma unroll
+        for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 6; ++dx)
+                m = max(m, __float_as_uint(__ldg(p + min(sy0 + dy, sy1) * sxs + min(sx0 + dx, sx1))));
         active = !(__uint_as_float(m) < limit);       // NaN: active
     }
     // one global atomic per CTA
@@ -375,9 +382,13 @@ int launch_blocks_t(const float *hmp, int h, int w, float thre, const int4 *bloc
                     const int32_t *n_active, uint32_t *cand_count, uint64_t *cand_keys, int sm_count,
                     size_t blocks, cudaStream_t s) {
     auto kernel = fused_block_kernel<S, kCubic, kFlip>;
-    // every CTA resident, warps stride over the work list
+    // Warps stride over the work list.  kCtaWaves x the resident CTA count: the per-warp setup
+    // (weights) is still amortised over several blocks, but CTAs retire during the kernel, so the
+    // high-priority K3 CTAs of the previous call (one per image, 200 KB of shared memory) find
+    // room instead of waiting for a fully persistent grid to drain.
+    constexpr int kCtaWaves = 4;
     const int grid = (int)std::min<size_t>((blocks + kFusedThreads / 32 - 1) / (kFusedThreads / 32),
-                                           (size_t)resident_grid(kernel, sm_count));
+                                           (size_t)resident_grid(kernel, sm_count) * kCtaWaves);
     kernel<<<grid, kFusedThreads, 0, s>>>(hmp, h, w, thre, block_list, n_active, cand_count, cand_keys);
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;

@@ -306,9 +306,11 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, const int32_t *__rest
             const float *s_conn = s_conn_buf[li & 1];
             const int *s_rows = s_rows_buf[li & 1];
             asm volatile("cp.async.wait_all;" ::: "memory");        // data of type li has landed
-            if (li + 1 < L) fetch_rows(li + 1);
             if (tid < kNumFlags) s_flag[tid] = 0;
             __syncthreads();
+            // The buffers of type li + 1 are those of type li - 1: only after the barrier has every
+            // thread finished reading them (a type with kk == 0 leaves its iteration without one).
+            if (li + 1 < L) fetch_rows(li + 1);
             OG_K3_PROF(0);
             const int kk = s_rows[K];
             if (kk == 0) continue;                                         // group.py:84-85
