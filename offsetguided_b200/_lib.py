@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(_PKG_DIR, 'libogdecoder.so')
 OG_LIMB_COLS = 13
 OG_POSE_COLS = 6
 OG_MAX_TOPK = 128
+OG_DTYPE_F32 = 0
+OG_DTYPE_BF16 = 1
 
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -67,6 +69,8 @@ SIGNATURES = {
                                      c_int32_p, c_int32_p, c_int32_p, _i, _vp]),
     'og_decode_features_dev': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i,
                                     c_int32_p, c_int32_p, c_int32_p, _i, _vp]),
+    'og_decode_features_dev_ex': (_i, [_vp, _vp, _vp, _i, ctypes.c_int64, ctypes.c_int64, _i, _i, _i, _i, _i,
+                                       _i, _i, c_int32_p, c_int32_p, c_int32_p, _i, _vp]),
     'og_fetch_poses': (_i, [_vp, ctypes.POINTER(c_float_p), ctypes.POINTER(c_int32_p),
                             ctypes.POINTER(c_int32_p), ctypes.POINTER(ctypes.c_int32)]),
     'og_pending': (_i, [_vp]),

@@ -79,6 +79,7 @@ struct FeatureArgs {               // arguments of a features decode, kept for t
     const float *hmp, *off;
     int n, hgt, w, hmp_stride, off_stride, resize_mode, flip;
     const float *off_host;         // offsets left in pinned host memory (zero-copy), else nullptr
+    MapView hmp_view, off_view;    // og_decode_features_dev_ex: bf16 / strided maps (ptr != nullptr)
 };
 
 // Everything that belongs to ONE decode call until its result has been fetched.
@@ -234,10 +235,17 @@ int run_k3(og_handle *h, const float *limbs, int n, float *out_poses, int capaci
 }
 
 struct K1Fused {
-    const float *hmp;       // network-resolution heat maps (n or 2n images)
+    MapView hmp;            // network-resolution heat maps (n or 2n images)
     int h, w, scale;
     bool cubic, flip;
 };
+
+inline MapView dense_f32(const float *p, size_t per_image) { return MapView{p, OG_DTYPE_F32, per_image}; }
+inline size_t elem_size(int dtype) { return dtype == OG_DTYPE_BF16 ? 2 : 4; }
+inline MapView shift_images(MapView v, size_t images) {
+    v.ptr = static_cast<const char *>(v.ptr) + images * v.image_stride * elem_size(v.dtype);
+    return v;
+}
 
 // One decode call = begin_call, decode_range over one or more image ranges, finish_call.
 // begin_call: buffers of the slot, meta words cleared, first stage marks.
@@ -301,7 +309,7 @@ int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, cons
         OG_TRY(h->tile_amax.ensure(amax_floats));
         OG_TRY(h->tile_list.ensure(tiles + 1));
         // the mirrored copy of image i sits n images behind it: shifting the base keeps that offset
-        OG_TRY(launch_fused_candidates(fused->hmp + plane0 * fused->h * fused->w, h->kp_flip.ptr, cn, n,
+        OG_TRY(launch_fused_candidates(shift_images(fused->hmp, i0), h->kp_flip.ptr, cn, n,
                                        c.n_keypoints, fused->h, fused->w, fused->scale, fused->cubic,
                                        fused->flip, c.thre_hmp, cand_count, cand_keys, h->tile_amax.ptr,
                                        h->tile_list.ptr, h->tile_list.ptr + tiles, h->sm_count, s,
@@ -327,7 +335,7 @@ int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, cons
     OffsetSource src = {};
     if (offs_lowres) {
         src = *offs_lowres;
-        src.maps += (size_t)i0 * 2 * c.n_limbs * src.h * src.w;
+        src.maps = shift_images(src.maps, i0);
     }
     LimbExtras ex = {nullptr, 2, 0};
     if (extras) {
@@ -425,7 +433,8 @@ int decode_features_impl(og_handle *h, ResultSlot *slot, const float *hmp, const
         OG_TRY(mark(h, slot, 0, s));
         slot->prep_marked = h->timing;
     }
-    slot->args = FeatureArgs{hmp, off, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, nullptr};
+    slot->args = FeatureArgs{hmp, off, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, nullptr,
+                             MapView{nullptr, 0, 0}, MapView{nullptr, 0, 0}};
 
     // Fused path: candidates straight from the network-resolution maps, offsets sampled at
     // the candidates; no full-resolution map is written.  thre_hmp <= 0 (every pixel is a
@@ -433,9 +442,10 @@ int decode_features_impl(og_handle *h, ResultSlot *slot, const float *hmp, const
     if (allow_fused && h->fused_enabled && c.thre_hmp > 0.0f &&
         fused_supported(n, c.n_keypoints, hmp_stride, hgt, w)) {
         OG_TRY(check_maps(n, hgt * hmp_stride, w * hmp_stride, c.n_keypoints));
-        K1Fused k1 = {hmp, hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
-        OffsetSource src = {off, hgt, w, off_stride, flip_test ? 1 : 0, n, h->limb_flip.ptr,
-                            h->limb_reserved.ptr};
+        K1Fused k1 = {dense_f32(hmp, (size_t)c.n_keypoints * hw), hgt, w, hmp_stride, resize_mode == 1,
+                      flip_test != 0};
+        OffsetSource src = {dense_f32(off, (size_t)2 * c.n_limbs * hw), hgt, w, off_stride,
+                            flip_test ? 1 : 0, n, h->limb_flip.ptr, h->limb_reserved.ptr};
         return decode_core(h, slot, nullptr, &k1, nullptr, &src, nullptr, n, hgt * hmp_stride,
                            w * hmp_stride, s);
     }
@@ -857,6 +867,45 @@ int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_
                                 resize_mode, flip_test, s, true);
 }
 
+int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off_dev, int dtype,
+                              int64_t hmp_image_stride, int64_t off_image_stride, int n, int hgt,
+                              int w, int hmp_stride, int off_stride, int resize_mode, int flip_test,
+                              const int32_t *kp_flip, const int32_t *limb_flip,
+                              const int32_t *limb_reserve, int n_reserve, void *stream) {
+    OG_REQUIRE(h && (n == 0 || (hmp_dev && off_dev)), "og_decode_features_dev_ex: null pointer");
+    OG_REQUIRE(dtype == OG_DTYPE_F32 || dtype == OG_DTYPE_BF16, "dtype must be OG_DTYPE_F32 or OG_DTYPE_BF16");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
+                              limb_flip, limb_reserve, n_reserve, s));
+    const og_config &c = h->cfg;
+    const size_t hw = (size_t)hgt * w;
+    const size_t hmp_img = (size_t)c.n_keypoints * hw, off_img = (size_t)2 * c.n_limbs * hw;
+    OG_REQUIRE(hmp_image_stride == 0 || (size_t)hmp_image_stride >= hmp_img,
+               "hmp_image_stride %lld is smaller than one image (%zu elements)", (long long)hmp_image_stride, hmp_img);
+    OG_REQUIRE(off_image_stride == 0 || (size_t)off_image_stride >= off_img,
+               "off_image_stride %lld is smaller than one image (%zu elements)", (long long)off_image_stride, off_img);
+    MapView hv = {hmp_dev, dtype, hmp_image_stride ? (size_t)hmp_image_stride : hmp_img};
+    MapView ov = {off_dev, dtype, off_image_stride ? (size_t)off_image_stride : off_img};
+    if (dtype == OG_DTYPE_F32 && hv.image_stride == hmp_img && ov.image_stride == off_img)
+        return og_decode_features_dev(h, static_cast<const float *>(hmp_dev), static_cast<const float *>(off_dev),
+                                      n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
+                                      limb_flip, limb_reserve, n_reserve, stream);
+    if (!(h->fused_enabled && c.thre_hmp > 0.0f && fused_supported(n, c.n_keypoints, hmp_stride, hgt, w))) {
+        set_error("og_decode_features_dev_ex: bf16 / strided maps need the fused path (stride 2, 4 or 8, "
+                  "thre_hmp > 0, fused enabled); convert to dense float32 and call og_decode_features_dev");
+        return OG_ERR_UNSUPPORTED;
+    }
+    ResultSlot *slot = nullptr;
+    OG_TRY(acquire_slot(h, nullptr, &slot));
+    const int H = hgt * hmp_stride, W = w * hmp_stride;
+    OG_TRY(check_maps(n, H, W, c.n_keypoints));
+    slot->args = FeatureArgs{nullptr, nullptr, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test,
+                             nullptr, hv, ov};
+    K1Fused k1 = {hv, hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
+    OffsetSource src = {ov, hgt, w, off_stride, flip_test ? 1 : 0, n, h->limb_flip.ptr, h->limb_reserved.ptr};
+    return decode_core(h, slot, nullptr, &k1, nullptr, &src, nullptr, n, H, W, s);
+}
+
 int og_decode_features_host(og_handle *h, const float *hmp_host, const float *off_host, int n,
                             int hgt, int w, int hmp_stride, int off_stride, int resize_mode,
                             int flip_test, const int32_t *kp_flip, const int32_t *limb_flip,
@@ -920,10 +969,11 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
     const int H = hgt * hmp_stride, W = w * hmp_stride;
     OG_TRY(check_maps(n, H, W, c.n_keypoints));
     slot->args = FeatureArgs{slot->in_hmp.ptr, off_alias ? nullptr : slot->in_off.ptr, n, hgt, w,
-                             hmp_stride, off_stride, resize_mode, flip_test, off_alias ? off_host : nullptr};
-    K1Fused k1 = {slot->in_hmp.ptr, hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
-    OffsetSource src = {off_src, hgt, w, off_stride, flip_test ? 1 : 0, n, h->limb_flip.ptr,
-                        h->limb_reserved.ptr};
+                             hmp_stride, off_stride, resize_mode, flip_test, off_alias ? off_host : nullptr,
+                             MapView{nullptr, 0, 0}, MapView{nullptr, 0, 0}};
+    K1Fused k1 = {dense_f32(slot->in_hmp.ptr, hmp_img), hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
+    OffsetSource src = {dense_f32(off_src, off_img), hgt, w, off_stride, flip_test ? 1 : 0, n,
+                        h->limb_flip.ptr, h->limb_reserved.ptr};
     OG_TRY(begin_call(h, slot, true, n, H, W, s));
     const int per = std::max((n + h->host_chunks - 1) / h->host_chunks, std::min(n, 4));
     int chunk = 0;
@@ -960,6 +1010,18 @@ int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offse
             // on the GPU through the materialising path, which selects exactly for any input.
             h->fused_redos += 1;
             FeatureArgs a = slot->args;
+            if (a.hmp_view.ptr) {       // bf16 / strided maps: dense float32 copies for the exact path
+                const int n_in = a.flip ? 2 * a.n : a.n;
+                const size_t hmp_img = (size_t)h->cfg.n_keypoints * a.hgt * a.w;
+                const size_t off_img = (size_t)2 * h->cfg.n_limbs * a.hgt * a.w;
+                OG_TRY(slot->in_hmp.ensure((size_t)n_in * hmp_img));
+                OG_TRY(slot->in_off.ensure((size_t)n_in * off_img));
+                OG_TRY(launch_densify(a.hmp_view, slot->in_hmp.ptr, n_in, hmp_img, slot->stream));
+                OG_TRY(launch_densify(a.off_view, slot->in_off.ptr, n_in, off_img, slot->stream));
+                h->launches += 2;
+                a.hmp = slot->in_hmp.ptr;
+                a.off = slot->in_off.ptr;
+            }
             if (a.off_host) {           // the materialising path reads every offset: copy them now
                 const size_t elems = (size_t)(a.flip ? 2 * a.n : a.n) * 2 * h->cfg.n_limbs * a.hgt * a.w;
                 OG_TRY(slot->in_off.ensure(elems));

@@ -2,6 +2,7 @@
 // include/og_decoder.h).
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -83,10 +84,28 @@ int launch_select_topk(const float *heat, int planes, int h, int w, float thre, 
                        int32_t *out_index, int32_t *out_count, int32_t *overflow_flag,
                        cudaStream_t s);
 
+// ---- network-resolution maps as the caller holds them ------------------------------
+// Element types: float32 (what the reference decodes, factory.py:59) or bfloat16 straight from
+// a bf16 head.  A bf16 value widens exactly to float32, so everything after the
+// load is the float32 path bit for bit.  Images may be `image_stride` elements apart (channel
+// slices of one packed [N, 55, h, w] network output); the planes of an image are contiguous.
+struct MapView {
+    const void *ptr;
+    int dtype;                      // OG_DTYPE_F32 / OG_DTYPE_BF16
+    size_t image_stride;            // elements between consecutive images
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ float load_cell(const float *p) { return __ldg(p); }
+__device__ __forceinline__ float load_cell(const __nv_bfloat16 *p) {
+    return __uint_as_float((unsigned)__ldg(reinterpret_cast<const unsigned short *>(p)) << 16);
+}
+#endif
+int launch_densify(const MapView &src, float *dst, int images, size_t per_image, cudaStream_t s);
+
 // Offsets still at network resolution (fused path): K2 samples them bilinearly at the
 // candidate pixels instead of gathering from a materialised full-resolution map.
 struct OffsetSource {
-    const float *maps;              // [n or 2n][2L][h][w]
+    MapView maps;                   // [n or 2n][2L][h][w]
     int h, w, scale;                // network resolution and the x scale to decode resolution
     int flip, n;                    // flip: maps = n originals then n mirrored copies
     const int32_t *limb_flip;       // device tables (flip only)
@@ -122,7 +141,7 @@ bool fused_supported(int n, int c, int scale, int h, int w);
 void fused_scratch(int n, int c, int h, int w, int scale, size_t *amax_floats, size_t *list_ints);
 // sub_amax / block_list: fused_scratch() elements, n_active: one int
 // `n` images starting at hmp; the mirrored copy of image i is image n_total + i (flip only)
-int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n, int n_total, int c, int h, int w,
+int launch_fused_candidates(const MapView &hmp, const int32_t *kp_flip_dev, int n, int n_total, int c, int h, int w,
                             int scale, bool cubic, bool flip, float thre, uint32_t *cand_count,
                             uint64_t *cand_keys, float *sub_amax, int32_t *block_list,
                             int32_t *n_active, int sm_count, cudaStream_t s, int64_t *launches);

@@ -50,16 +50,25 @@ __device__ __forceinline__ float4 ldg_stream4(const float *p) {
     return v;
 }
 
+// four consecutive cells with one streaming load (16 / 8 bytes)
+__device__ __forceinline__ float4 load_cells4(const float *p) { return ldg_stream4(p); }
+__device__ __forceinline__ float4 load_cells4(const __nv_bfloat16 *p) {
+    unsigned lo, hi;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(p));
+    return make_float4(__uint_as_float(lo << 16), __uint_as_float(lo & 0xffff0000u),
+                       __uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+}
+
 // |v| >= 0: the IEEE bit pattern orders like the value, and NaN sorts above everything,
 // which keeps such regions active
 __device__ __forceinline__ unsigned abs_bits(float v) { return __float_as_uint(fabsf(v)); }
 
 // ---- pass A: activity map ------------------------------------------------------
 // one thread per (plane, 8-row band, 4-cell column group): two sub-block maxima
-template <bool kFlip, bool kVec>
+template <typename T, bool kFlip, bool kVec>
 __global__ void __launch_bounds__(kScanThreads)
-amax_scan_kernel(const float *__restrict__ hmp, const int32_t *__restrict__ kp_flip, int N, int C,
-                 int h, int w, float *__restrict__ sub_amax, long long total) {
+amax_scan_kernel(const T *__restrict__ hmp, size_t img_stride, const int32_t *__restrict__ kp_flip,
+                 int N, int C, int h, int w, float *__restrict__ sub_amax, long long total) {
     const long long idx = (long long)blockIdx.x * kScanThreads + threadIdx.x;
     if (idx >= total) return;
     const int sxs = (w + kSub - 1) / kSub, sys = (h + kSub - 1) / kSub;
@@ -69,9 +78,9 @@ amax_scan_kernel(const float *__restrict__ hmp, const int32_t *__restrict__ kp_f
     const int band = (int)(t % bands);
     const int plane = (int)(t / bands);
     const int n = plane / C, c = plane - n * C;
-    const float *a = hmp + ((size_t)n * C + c) * h * w;
-    const float *b = nullptr;
-    if (kFlip) b = hmp + ((size_t)(N + n) * C + kp_flip[c]) * h * w;
+    const T *a = hmp + (size_t)n * img_stride + (size_t)c * h * w;
+    const T *b = nullptr;
+    if (kFlip) b = hmp + (size_t)(N + n) * img_stride + (size_t)kp_flip[c] * h * w;
     const int y0 = band * 2 * kSub, x0 = sx * kSub;
     unsigned m[2] = {0u, 0u};
     if (kVec) {
@@ -79,8 +88,8 @@ amax_scan_kernel(const float *__restrict__ hmp, const int32_t *__restrict__ kp_f
 #pragma unroll
         for (int r = 0; r < 2 * kSub; ++r) {
             const int y = min(y0 + r, h - 1);          // a repeated row does not change a maximum
-            va[r] = ldg_stream4(a + (size_t)y * w + x0);
-            if (kFlip) vb[r] = ldg_stream4(b + (size_t)y * w + (w - kSub - x0));
+            va[r] = load_cells4(a + (size_t)y * w + x0);
+            if (kFlip) vb[r] = load_cells4(b + (size_t)y * w + (w - kSub - x0));
         }
 #pragma unroll
         for (int r = 0; r < 2 * kSub; ++r) {
@@ -101,8 +110,8 @@ amax_scan_kernel(const float *__restrict__ hmp, const int32_t *__restrict__ kp_f
             for (int j = 0; j < kSub; ++j) {
                 const int x = x0 + j;
                 if (x >= w) break;
-                float v = __ldg(a + (size_t)y * w + x);
-                if (kFlip) v = __fmul_rn(__fadd_rn(v, __ldg(b + (size_t)y * w + (w - 1 - x))), 0.5f);
+                float v = load_cell(a + (size_t)y * w + x);
+                if (kFlip) v = __fmul_rn(__fadd_rn(v, load_cell(b + (size_t)y * w + (w - 1 - x))), 0.5f);
                 m[r / kSub] = max(m[r / kSub], abs_bits(v));
             }
         }
@@ -113,9 +122,10 @@ amax_scan_kernel(const float *__restrict__ hmp, const int32_t *__restrict__ kp_f
 }
 
 // ---- pass B: work list -----------------------------------------------------------
-// entry = {plane of the original map, plane of the mirrored map, block row << 16 | block column, 0}
+// entry = {plane (image * C + channel), image, block row << 16 | block column,
+//          channel | channel of the mirrored map << 16}
 __global__ void __launch_bounds__(256)
-block_list_kernel(const float *__restrict__ sub_amax, const int32_t *__restrict__ kp_flip, int N, int C,
+block_list_kernel(const float *__restrict__ sub_amax, const int32_t *__restrict__ kp_flip, int C,
                   int flip, int h, int w, int block_w, int halo, float limit, long long total,
                   int4 *__restrict__ block_list, int32_t *__restrict__ n_active) {
     __shared__ int s_warp[8];
@@ -163,9 +173,9 @@ block_list_kernel(const float *__restrict__ sub_amax, const int32_t *__restrict_
     __syncthreads();
     if (active) {
         const int n = plane / C, c = plane - n * C;
-        const int plane_b = flip ? (N + n) * C + kp_flip[c] : plane;
+        const int cb = flip ? kp_flip[c] : c;
         block_list[s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))] =
-            make_int4(plane, plane_b, (by << 16) | bx, 0);
+            make_int4(plane, n, (by << 16) | bx, c | (cb << 16));
     }
 }
 
@@ -189,9 +199,9 @@ __device__ __noinline__ float tile_value(const float *lo, int cx0, int cy0, int 
                   : combine2(rows[0], rows[1], wys[0], wys[1]);
 }
 
-template <int S, bool kCubic, bool kFlip>
+template <typename T, int S, bool kCubic, bool kFlip>
 __global__ void __launch_bounds__(kFusedThreads, S <= 4 ? 4 : 3)
-fused_block_kernel(const float *__restrict__ hmp, int h, int w, float thre,
+fused_block_kernel(const T *__restrict__ hmp, size_t img_stride, int N, int h, int w, float thre,
                    const int4 *__restrict__ block_list,
                    const int32_t *__restrict__ n_active_ptr, uint32_t *__restrict__ cand_count,
                    uint64_t *__restrict__ cand_keys) {
@@ -230,8 +240,8 @@ fused_block_kernel(const float *__restrict__ hmp, int h, int w, float thre,
     const size_t hw = (size_t)h * w;
     auto load_block = [&](const int4 e, float (&vals)[NL]) {
         const int base_x = (e.z & 0xffff) * BW - HALO, base_y = (e.z >> 16) * BH - HALO;
-        const float *a = hmp + (size_t)e.x * hw;
-        const float *b = hmp + (size_t)e.y * hw;
+        const T *a = hmp + (size_t)e.y * img_stride + (size_t)(e.w & 0xffff) * hw;
+        const T *b = hmp + (size_t)(N + e.y) * img_stride + (size_t)(e.w >> 16) * hw;
         const bool interior = base_x >= 0 && base_y >= 0 && base_x + LW <= w && base_y + LH <= h;
         if (interior) {                     // warp-uniform: no clamping
             a += base_y * w + base_x;
@@ -242,8 +252,8 @@ fused_block_kernel(const float *__restrict__ hmp, int h, int w, float thre,
                 float v = 0.0f;
                 if (i < LH * LW) {
                     const int ly = i / LW, lx = i - ly * LW;
-                    v = __ldg(a + ly * w + lx);
-                    if (kFlip) v = __fmul_rn(__fadd_rn(v, __ldg(b + ly * w - lx)), 0.5f);
+                    v = load_cell(a + ly * w + lx);
+                    if (kFlip) v = __fmul_rn(__fadd_rn(v, load_cell(b + ly * w - lx)), 0.5f);
                 }
                 vals[u] = v;
             }
@@ -256,8 +266,8 @@ fused_block_kernel(const float *__restrict__ hmp, int h, int w, float thre,
                     const int ly = i / LW, lx = i - ly * LW;
                     const int gy = min(max(base_y + ly, 0), h - 1);
                     const int gx = min(max(base_x + lx, 0), w - 1);
-                    v = __ldg(a + gy * w + gx);
-                    if (kFlip) v = __fmul_rn(__fadd_rn(v, __ldg(b + gy * w + (w - 1 - gx))), 0.5f);
+                    v = load_cell(a + gy * w + gx);
+                    if (kFlip) v = __fmul_rn(__fadd_rn(v, load_cell(b + gy * w + (w - 1 - gx))), 0.5f);
                 }
                 vals[u] = v;
             }
@@ -377,11 +387,11 @@ int resident_grid(Kernel kernel, int sm_count) {
     return sm_count * per_sm;
 }
 
-template <int S, bool kCubic, bool kFlip>
-int launch_blocks_t(const float *hmp, int h, int w, float thre, const int4 *block_list,
-                    const int32_t *n_active, uint32_t *cand_count, uint64_t *cand_keys, int sm_count,
-                    size_t blocks, cudaStream_t s) {
-    auto kernel = fused_block_kernel<S, kCubic, kFlip>;
+template <typename T, int S, bool kCubic, bool kFlip>
+int launch_blocks_t(const T *hmp, size_t img_stride, int n_total, int h, int w, float thre,
+                    const int4 *block_list, const int32_t *n_active, uint32_t *cand_count,
+                    uint64_t *cand_keys, int sm_count, size_t blocks, cudaStream_t s) {
+    auto kernel = fused_block_kernel<T, S, kCubic, kFlip>;
     // Warps stride over the work list.  kCtaWaves x the resident CTA count: the per-warp setup
     // (weights) is still amortised over several blocks, but CTAs retire during the kernel, so the
     // high-priority K3 CTAs of the previous call (one per image, 200 KB of shared memory) find
@@ -389,20 +399,21 @@ int launch_blocks_t(const float *hmp, int h, int w, float thre, const int4 *bloc
     constexpr int kCtaWaves = 4;
     const int grid = (int)std::min<size_t>((blocks + kFusedThreads / 32 - 1) / (kFusedThreads / 32),
                                            (size_t)resident_grid(kernel, sm_count) * kCtaWaves);
-    kernel<<<grid, kFusedThreads, 0, s>>>(hmp, h, w, thre, block_list, n_active, cand_count, cand_keys);
+    kernel<<<grid, kFusedThreads, 0, s>>>(hmp, img_stride, n_total, h, w, thre, block_list, n_active,
+                                          cand_count, cand_keys);
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;
 }
 
-template <int S>
-int launch_blocks_s(const float *hmp, int h, int w, bool cubic, bool flip, float thre,
-                    const int4 *block_list, const int32_t *n_active, uint32_t *cand_count,
+template <typename T, int S>
+int launch_blocks_s(const T *hmp, size_t img_stride, int n_total, int h, int w, bool cubic, bool flip,
+                    float thre, const int4 *block_list, const int32_t *n_active, uint32_t *cand_count,
                     uint64_t *cand_keys, int sm_count, size_t blocks, cudaStream_t s) {
     if (cubic)
-        return flip ? launch_blocks_t<S, true, true>(hmp, h, w, thre, block_list, n_active, cand_count, cand_keys, sm_count, blocks, s)
-                    : launch_blocks_t<S, true, false>(hmp, h, w, thre, block_list, n_active, cand_count, cand_keys, sm_count, blocks, s);
-    return flip ? launch_blocks_t<S, false, true>(hmp, h, w, thre, block_list, n_active, cand_count, cand_keys, sm_count, blocks, s)
-                : launch_blocks_t<S, false, false>(hmp, h, w, thre, block_list, n_active, cand_count, cand_keys, sm_count, blocks, s);
+        return flip ? launch_blocks_t<T, S, true, true>(hmp, img_stride, n_total, h, w, thre, block_list, n_active, cand_count, cand_keys, sm_count, blocks, s)
+                    : launch_blocks_t<T, S, true, false>(hmp, img_stride, n_total, h, w, thre, block_list, n_active, cand_count, cand_keys, sm_count, blocks, s);
+    return flip ? launch_blocks_t<T, S, false, true>(hmp, img_stride, n_total, h, w, thre, block_list, n_active, cand_count, cand_keys, sm_count, blocks, s)
+                : launch_blocks_t<T, S, false, false>(hmp, img_stride, n_total, h, w, thre, block_list, n_active, cand_count, cand_keys, sm_count, blocks, s);
 }
 
 inline size_t block_count(int n, int c, int h, int w, int scale) {
@@ -423,29 +434,29 @@ void fused_scratch(int n, int c, int h, int w, int scale, size_t *amax_floats, s
     *list_ints = 4 * block_count(n, c, h, w, scale);          // int4 entries
 }
 
-int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n, int n_total, int c, int h, int w,
-                            int scale, bool cubic, bool flip, float thre, uint32_t *cand_count,
-                            uint64_t *cand_keys, float *sub_amax, int32_t *block_list,
-                            int32_t *n_active, int sm_count, cudaStream_t s, int64_t *launches) {
-    if (n == 0) return OG_OK;
-    if (!fused_supported(n, c, scale, h, w)) {
-        set_error("fused K1: scale %d / %d x %d maps are outside the supported range", scale, h, w);
-        return OG_ERR_UNSUPPORTED;
-    }
+namespace {
+template <typename T>
+int launch_fused_t(const T *hmp, size_t img_stride, const int32_t *kp_flip_dev, int n, int n_total,
+                   int c, int h, int w, int scale, bool cubic, bool flip, float thre,
+                   uint32_t *cand_count, uint64_t *cand_keys, float *sub_amax, int32_t *block_list,
+                   int32_t *n_active, int sm_count, cudaStream_t s, int64_t *launches) {
     OG_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t) * (size_t)n * c, s));
     OG_CUDA_TRY(cudaMemsetAsync(n_active, 0, sizeof(int32_t), s));
 
     const int sxs = (w + kSub - 1) / kSub, bands = (h + 2 * kSub - 1) / (2 * kSub);
     const long long scan_threads = (long long)n * c * bands * sxs;
     const unsigned scan_grid = (unsigned)((scan_threads + kScanThreads - 1) / kScanThreads);
-    // 128-bit loads need whole 4-cell groups and 16-byte aligned rows (also of the mirrored read)
-    const bool vec = (w % kSub) == 0 && (reinterpret_cast<uintptr_t>(hmp) & 15) == 0;
+    // vector loads need whole 4-cell groups and rows aligned to the 4-cell load size (also the
+    // rows of the mirrored read and of every image)
+    const size_t vec_bytes = 4 * sizeof(T);
+    const bool vec = (w % kSub) == 0 && (reinterpret_cast<uintptr_t>(hmp) % vec_bytes) == 0 &&
+                     (img_stride * sizeof(T)) % vec_bytes == 0;
     if (flip) {
-        if (vec) amax_scan_kernel<true, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
-        else amax_scan_kernel<true, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
+        if (vec) amax_scan_kernel<T, true, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
+        else amax_scan_kernel<T, true, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
     } else {
-        if (vec) amax_scan_kernel<false, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
-        else amax_scan_kernel<false, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
+        if (vec) amax_scan_kernel<T, false, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
+        else amax_scan_kernel<T, false, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
     }
     OG_CUDA_TRY(cudaGetLastError());
 
@@ -453,18 +464,63 @@ int launch_fused_candidates(const float *hmp, const int32_t *kp_flip_dev, int n,
     const float limit = thre / (cubic ? 1.95f : 1.001f);
     int4 *list4 = reinterpret_cast<int4 *>(block_list);
     block_list_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, s>>>(
-        sub_amax, kp_flip_dev, n_total, c, flip ? 1 : 0, h, w, 32 / scale, cubic ? 2 : 1, limit,
+        sub_amax, kp_flip_dev, c, flip ? 1 : 0, h, w, 32 / scale, cubic ? 2 : 1, limit,
         (long long)blocks, list4, n_active);
     OG_CUDA_TRY(cudaGetLastError());
 
     int st;
     switch (scale) {
-        case 2: st = launch_blocks_s<2>(hmp, h, w, cubic, flip, thre, list4, n_active, cand_count, cand_keys, sm_count, blocks, s); break;
-        case 4: st = launch_blocks_s<4>(hmp, h, w, cubic, flip, thre, list4, n_active, cand_count, cand_keys, sm_count, blocks, s); break;
-        default: st = launch_blocks_s<8>(hmp, h, w, cubic, flip, thre, list4, n_active, cand_count, cand_keys, sm_count, blocks, s); break;
+        case 2: st = launch_blocks_s<T, 2>(hmp, img_stride, n_total, h, w, cubic, flip, thre, list4, n_active, cand_count, cand_keys, sm_count, blocks, s); break;
+        case 4: st = launch_blocks_s<T, 4>(hmp, img_stride, n_total, h, w, cubic, flip, thre, list4, n_active, cand_count, cand_keys, sm_count, blocks, s); break;
+        default: st = launch_blocks_s<T, 8>(hmp, img_stride, n_total, h, w, cubic, flip, thre, list4, n_active, cand_count, cand_keys, sm_count, blocks, s); break;
     }
     if (st == OG_OK && launches) *launches += 3;
     return st;
+}
+}  // namespace
+
+int launch_fused_candidates(const MapView &hmp, const int32_t *kp_flip_dev, int n, int n_total, int c,
+                            int h, int w, int scale, bool cubic, bool flip, float thre,
+                            uint32_t *cand_count, uint64_t *cand_keys, float *sub_amax,
+                            int32_t *block_list, int32_t *n_active, int sm_count, cudaStream_t s,
+                            int64_t *launches) {
+    if (n == 0) return OG_OK;
+    if (!fused_supported(n, c, scale, h, w)) {
+        set_error("fused K1: scale %d / %d x %d maps are outside the supported range", scale, h, w);
+        return OG_ERR_UNSUPPORTED;
+    }
+    if (hmp.dtype == OG_DTYPE_BF16)
+        return launch_fused_t(static_cast<const __nv_bfloat16 *>(hmp.ptr), hmp.image_stride, kp_flip_dev, n,
+                              n_total, c, h, w, scale, cubic, flip, thre, cand_count, cand_keys, sub_amax,
+                              block_list, n_active, sm_count, s, launches);
+    return launch_fused_t(static_cast<const float *>(hmp.ptr), hmp.image_stride, kp_flip_dev, n, n_total, c,
+                          h, w, scale, cubic, flip, thre, cand_count, cand_keys, sub_amax, block_list,
+                          n_active, sm_count, s, launches);
+}
+
+// dense float32 copy of strided / bf16 maps (only the exact redo of an overflowed batch needs it)
+namespace {
+template <typename T>
+__global__ void densify_kernel(const T *__restrict__ src, size_t img_stride, float *__restrict__ dst,
+                               size_t per_image, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const size_t img = i / per_image, r = i - img * per_image;
+        dst[i] = load_cell(src + img * img_stride + r);
+    }
+}
+}  // namespace
+
+int launch_densify(const MapView &src, float *dst, int images, size_t per_image, cudaStream_t s) {
+    const size_t total = (size_t)images * per_image;
+    if (total == 0) return OG_OK;
+    const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+    if (src.dtype == OG_DTYPE_BF16)
+        densify_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(src.ptr), src.image_stride, dst, per_image, total);
+    else
+        densify_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(src.ptr), src.image_stride, dst, per_image, total);
+    OG_CUDA_TRY(cudaGetLastError());
+    return OG_OK;
 }
 
 }  // namespace og

@@ -28,19 +28,21 @@ __device__ __forceinline__ float norm2(float dx, float dy) {
 // maps are still at network resolution: bilinear x S sampling on the fly, optionally fused
 // with the flip-test average (factory.py:128-139) — bit-identical to gathering from the
 // materialised F.interpolate(offs, scale_factor=S, mode='bilinear') map.
-__device__ __forceinline__ float sample_offset(const OffsetSource &src, int img, int L, int l,
-                                               int comp, int X, int Y) {
+template <typename T>
+__device__ __forceinline__ float sample_offset_t(const OffsetSource &src, int img, int L, int l,
+                                                 int comp, int X, int Y) {
     const int h = src.h, w = src.w;
     const size_t hw = (size_t)h * w;
-    const float *a = src.maps + ((size_t)img * 2 * L + 2 * l + comp) * hw;
+    const T *base = static_cast<const T *>(src.maps.ptr);
+    const T *a = base + (size_t)img * src.maps.image_stride + (size_t)(2 * l + comp) * hw;
     const bool mirrored = src.flip && !src.limb_reserved[l];
-    const float *b = mirrored
-                         ? src.maps + ((size_t)(src.n + img) * 2 * L + 2 * src.limb_flip[l] + comp) * hw
-                         : nullptr;
+    const T *b = mirrored ? base + (size_t)(src.n + img) * src.maps.image_stride +
+                                (size_t)(2 * src.limb_flip[l] + comp) * hw
+                          : nullptr;
     auto at = [&](int yy, int xx) {
-        float v = __ldg(a + yy * w + xx);
+        float v = load_cell(a + yy * w + xx);
         if (mirrored) {
-            float m = __ldg(b + yy * w + (w - 1 - xx));
+            float m = load_cell(b + yy * w + (w - 1 - xx));
             if (comp == 0) m = -m;
             v = __fmul_rn(__fadd_rn(v, m), 0.5f);
         }
@@ -55,6 +57,12 @@ __device__ __forceinline__ float sample_offset(const OffsetSource &src, int img,
     const float r0 = combine2(at(iy[0], ix[0]), at(iy[0], ix[1]), wx[0], wx[1]);
     const float r1 = combine2(at(iy[1], ix[0]), at(iy[1], ix[1]), wx[0], wx[1]);
     return combine2(r0, r1, wy[0], wy[1]);
+}
+
+__device__ __forceinline__ float sample_offset(const OffsetSource &src, int img, int L, int l,
+                                               int comp, int X, int Y) {
+    if (src.maps.dtype == OG_DTYPE_BF16) return sample_offset_t<__nv_bfloat16>(src, img, L, l, comp, X, Y);
+    return sample_offset_t<float>(src, img, L, l, comp, X, Y);
 }
 
 // Tensor.norm over 4 components as ATen's CPU kernel evaluates it (probed): plain left-to-right

@@ -31,6 +31,17 @@ def as_cuda_f32(t, device=None):
     return t.contiguous().float()
 
 
+def _image_strided(t):
+    """(tensor, elements between images) for an NCHW tensor whose planes are dense and contiguous
+    within an image (a channel slice of a packed head output qualifies); other layouts are
+    made contiguous first."""
+    n, c, h, w = t.shape
+    st = t.stride()
+    if st[3] == 1 and st[2] == w and st[1] == h * w and (n <= 1 or st[0] >= c * h * w):
+        return t, (st[0] if n > 1 else c * h * w)
+    return t.contiguous(), c * h * w
+
+
 class DecoderEngine(object):
     """One configured decoder bound to one CUDA device."""
 
@@ -66,6 +77,8 @@ class DecoderEngine(object):
         # input tensors of the decode calls in flight: K2 reads the offset maps on the handle's
         # stream after the call has returned, so they must outlive the call (until its fetch)
         self._inflight = collections.deque()
+        self._fused = True
+        self._flip_cache = {}
 
     def close(self):
         if getattr(self, '_h', None):
@@ -168,8 +181,9 @@ class DecoderEngine(object):
         cnts = np.ctypeslib.as_array(cnt_p, shape=(n,))
         if total.value == 0:
             return [np.zeros((0, c, _lib.OG_POSE_COLS), dtype=np.float32) for _ in range(n)]
-        rows = np.ctypeslib.as_array(poses_p, shape=(total.value, c, _lib.OG_POSE_COLS))
-        return [rows[offs[i]:offs[i] + cnts[i]].copy() for i in range(n)]
+        # one copy out of the handle's pinned buffer; the per-image arrays are views of it
+        rows = np.ctypeslib.as_array(poses_p, shape=(total.value, c, _lib.OG_POSE_COLS)).copy()
+        return [rows[o:o + k] for o, k in zip(offs.tolist(), cnts.tolist())]
 
     def decode_maps(self, heat, offs, scales=None, fetch=True, jomps=None, vector_nd=2,
                     use_jitter=False):
@@ -202,26 +216,48 @@ class DecoderEngine(object):
         mode = {'bilinear': 0, 'bicubic': 1}[resize_mode]
         on_host = not hmp.is_cuda
         assert hmp.is_cuda == off.is_cuda, 'heat and offset maps must live on the same side'
-        hmp = hmp.contiguous().float()
-        off = off.contiguous().float()
-        n_in, c, h, w = hmp.shape
         flip = flip_tables is not None
+        args = self._flip_args(flip_tables) if flip else (None, None, None, 0)
+        # Device maps as a bf16 network leaves them (bf16, or channel slices of one packed head
+        # output) are decoded in place on the fused path; anything else becomes dense float32.
+        in_place = (not on_host and self._fused and self.thre_hmp > 0 and int(hmp_stride) in (2, 4, 8)
+                    and hmp.shape[0] > 0 and hmp.dtype == off.dtype
+                    and hmp.dtype in (torch.float32, torch.bfloat16))
+        if in_place:
+            hmp, hmp_is = _image_strided(hmp)
+            off, off_is = _image_strided(off)
+            in_place = (hmp.dtype == torch.bfloat16 or hmp_is != hmp.shape[1] * hmp.shape[2] * hmp.shape[3]
+                        or off_is != off.shape[1] * off.shape[2] * off.shape[3])
+        if not in_place:
+            hmp = hmp.contiguous().float()
+            off = off.contiguous().float()
+        n_in, c, h, w = hmp.shape
         n = n_in // 2 if flip else n_in
-        if flip:
-            kp, lf, lr = flip_tables
-            kp_a, lf_a, lr_a = _lib.int32_array(kp), _lib.int32_array(lf), _lib.int32_array(lr)
-            args = (ctypes.cast(kp_a, _lib.c_int32_p), ctypes.cast(lf_a, _lib.c_int32_p),
-                    ctypes.cast(lr_a, _lib.c_int32_p), len(lr))
-        else:
-            args = (None, None, None, 0)
-        fn = self.lib.og_decode_features_host if on_host else self.lib.og_decode_features_dev
         with torch.cuda.device(self.device):
-            _lib.check(fn(self._h, _ptr(hmp), _ptr(off), n, h, w, int(hmp_stride), int(off_stride),
-                          mode, 1 if flip else 0, *args, _stream_ptr(self.device)))
+            if in_place:
+                dtype = _lib.OG_DTYPE_BF16 if hmp.dtype == torch.bfloat16 else _lib.OG_DTYPE_F32
+                _lib.check(self.lib.og_decode_features_dev_ex(
+                    self._h, _ptr(hmp), _ptr(off), dtype, hmp_is, off_is, n, h, w, int(hmp_stride),
+                    int(off_stride), mode, 1 if flip else 0, *args, _stream_ptr(self.device)))
+            else:
+                fn = self.lib.og_decode_features_host if on_host else self.lib.og_decode_features_dev
+                _lib.check(fn(self._h, _ptr(hmp), _ptr(off), n, h, w, int(hmp_stride), int(off_stride),
+                              mode, 1 if flip else 0, *args, _stream_ptr(self.device)))
             self._inflight.append((hmp, off))
             if not fetch:
                 return n
             return self._fetch(n)
+
+    def _flip_args(self, flip_tables):
+        """ctypes views of (kp_flips, limb_flips, limb_reserve), built once per table set."""
+        key = tuple(id(t) for t in flip_tables)          # the tables are long-lived config lists
+        hit = self._flip_cache.get(key)
+        if hit is None or any(a is not b for a, b in zip(hit[0], flip_tables)):
+            arrays = tuple(_lib.int32_array(t) for t in flip_tables)
+            hit = (tuple(flip_tables), arrays,
+                   tuple(ctypes.cast(a, _lib.c_int32_p) for a in arrays) + (len(flip_tables[2]),))
+            self._flip_cache[key] = hit
+        return hit[2]
 
     def fetch(self, n):
         """Result of the oldest decode call launched with ``fetch=False``."""
@@ -235,6 +271,7 @@ class DecoderEngine(object):
     def set_fused(self, on=True):
         """Enable / disable the fused network-resolution path of decode_features."""
         _lib.check(self.lib.og_set_fused(self._h, 1 if on else 0))
+        self._fused = bool(on)
 
     @property
     def fused_redo_count(self):

@@ -453,6 +453,69 @@ def test_host_offsets_stay_on_the_host(cuda_device):
     assert np.array_equal(over[0], staged[0]) and len(over[0]) > 5
 
 
+@pytest.mark.parametrize('dtype,flip', [('bf16', True), ('bf16', False), ('f32', True)])
+def test_packed_head_output_decoded_in_place(cuda_device, dtype, flip):
+    """SURVEY 8f-4 / BASELINE config 5 hand-over: one packed [2N, 17 + 38, h, w] head output, bf16 or
+    float32, its two channel slices decoded in place (no split, no float32 copy).  A bf16 value
+    widens exactly, so dets / limbs / poses equal those of the dense float32 copies bit for bit,
+    and the oracle on the converted maps agrees."""
+    import bench
+    skel = cfg.COCO_PERSON_SKELETON
+    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel)
+    n = 3
+    hmp, omp = bench.lowres_inputs(4321, n, 384, flip)
+    packed = torch.from_numpy(np.concatenate((hmp, omp), axis=1)).cuda()
+    if dtype == 'bf16':
+        packed = packed.to(torch.bfloat16)
+    h_view, o_view = packed[:, :17], packed[:, 17:]
+    assert not h_view.is_contiguous()
+    pp = decoder.decoder_factory(_args(topk=32, thre_hmp=0.04, person_thre=0.04, dist_max=40))
+    eng = pp._engine(torch.device('cuda', 0))
+    feats = [[[h_view], [[]], [[]]], [[o_view], [[]], [[]]]]
+    l0 = eng.launch_count
+    got = pp.generate_poses(feats, flip_test=flip)
+    assert eng.launch_count - l0 == 7          # K1f x3, select, K2, K3 x2: no conversion kernel of ours
+    got_int = [t.cpu().numpy() for t in eng.last_intermediates(n)]
+    h32, o32 = h_view.float().contiguous(), o_view.float().contiguous()
+    ref = pp.generate_poses([[[h32], [[]], [[]]], [[o32], [[]], [[]]]], flip_test=flip)
+    ref_int = [t.cpu().numpy() for t in eng.last_intermediates(n)]
+    assert sum(len(p) for p in ref) >= 3 * 4
+    for a, b in zip(got_int, ref_int):
+        assert np.array_equal(a, b)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    orc = ro.generate_poses(h32.cpu().numpy(), o32.cpu().numpy(), skel, 17, topk=32, thre_hmp=0.04,
+                            min_len=0.5, person_thre=0.04, dist_max=40, use_scale=True, hmp_stride=4,
+                            off_stride=4, resize_mode='bicubic', flip_test=flip, kp_flips=kp,
+                            limb_flips=fl, limb_reserve=rs)
+    for p, r in zip(got, orc):
+        gio.compare_poses(p, r, rtol=RTOL)
+
+
+def test_bf16_overflow_redo_and_odd_shapes(cuda_device):
+    """bf16 maps with an odd width (scalar loads) and a noise batch whose candidate lists overflow
+    (exact redo after an on-device conversion to dense float32)."""
+    skel = cfg.COCO_PERSON_SKELETON
+    eng = DecoderEngine(17, skel, topk=32, thre_hmp=0.04, dist_max=40, use_scale=True, person_thre=0.04)
+    rng = np.random.RandomState(11)
+    for shape, redo in (((2, 55, 37, 45), 0), ((1, 55, 160, 200), 1)):
+        packed = torch.from_numpy(rng.uniform(0, 1, size=shape).astype(np.float32))
+        packed[:, 17:] = packed[:, 17:] * 16 - 8
+        if not redo:
+            packed[:, :17] *= (rng.uniform(0, 1, size=(shape[0], 17) + shape[2:]) > 0.97)
+        packed = packed.cuda().to(torch.bfloat16)
+        r0 = eng.fused_redo_count
+        got = eng.decode_features(packed[:, :17], packed[:, 17:], 4, 4, 'bicubic', None)
+        assert eng.fused_redo_count - r0 == redo
+        eng.set_fused(False)
+        ref = eng.decode_features(packed[:, :17].float(), packed[:, 17:].float(), 4, 4, 'bicubic', None)
+        eng.set_fused(True)
+        assert sum(len(p) for p in ref) > 3
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b)
+
+
 def test_handles_with_different_table_sizes_coexist(cuda_device):
     """K3's dynamic shared memory attribute is per kernel, not per handle: a handle with a small
     person table created later must not shrink it for an earlier, larger one."""
