@@ -72,7 +72,8 @@ struct PinnedBuf {
 
 constexpr int kSlots = 2;          // decode calls that may be in flight before a fetch
 constexpr int kMaxChunks = 8;      // image ranges of one host-API call (copy / decode pipeline)
-// start, after prep, K1 pass 1, K1 pass 2 (caller's stream) | K2 start, K2, K3, D2H (handle's stream)
+// start, after prep, K1 pass 1 (caller's stream) | select start, select = K2 start, K2, K3, D2H
+// (handle's stream)
 constexpr int kStageEvents = 8;
 
 struct FeatureArgs {               // arguments of a features decode, kept for the exact redo
@@ -90,6 +91,8 @@ struct ResultSlot {
     DevBuf<float> det_score;            // K1 output of this call (written on the caller's stream,
     DevBuf<int32_t> det_index;          //  read by K2 on the handle's stream while the next
     DevBuf<int32_t> det_count;          //  call's K1 already runs)
+    DevBuf<uint32_t> cand_count;        // K1 pass 1 -> pass 2 hand-over, same reason
+    DevBuf<uint64_t> cand_keys;
     cudaEvent_t k1_done[kMaxChunks] = {nullptr};
     cudaEvent_t copied[kMaxChunks] = {nullptr};
     cudaEvent_t call_start = nullptr;
@@ -142,6 +145,7 @@ struct og_handle {
     bool fused_enabled;
     bool zero_copy_enabled;      // host API: K2 gathers offsets straight from pinned host memory
     int host_chunks;             // host API: image ranges of the copy / decode pipeline
+    int select_on_aux;           // 0: never, 1: fused path only, 2: always (tuning aid)
     int64_t fused_redos;
     int64_t zero_copy_calls;
     bool tables_valid;           // device flip tables match the cached host copies
@@ -263,8 +267,8 @@ int begin_call(og_handle *h, ResultSlot *slot, bool fused, int n, int hgt, int w
     OG_TRY(slot->out_host.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
     if (n > 0) {
         const int planes = n * c.n_keypoints;
-        OG_TRY(h->cand_count.ensure(planes));
-        OG_TRY(h->cand_keys.ensure((size_t)planes * kCandCap));
+        OG_TRY(slot->cand_count.ensure(planes));
+        OG_TRY(slot->cand_keys.ensure((size_t)planes * kCandCap));
     }
     slot->n = n;
     slot->meta_bytes = mbytes;
@@ -276,8 +280,10 @@ int begin_call(og_handle *h, ResultSlot *slot, bool fused, int n, int hgt, int w
     if (!slot->prep_marked) OG_TRY(mark(h, slot, 0, s));
     slot->prep_marked = false;
     if (n > 0) {
+        // total, overflow: first written by pass 2 / K3 of this call, which follow on the same stream
         int32_t *meta = reinterpret_cast<int32_t *>(slot->out.ptr);
-        OG_CUDA_TRY(cudaMemsetAsync(meta + 2 * n, 0, 2 * sizeof(int32_t), s));     // total, overflow
+        const bool on_aux = h->select_on_aux == 2 || (h->select_on_aux == 1 && fused);
+        OG_CUDA_TRY(cudaMemsetAsync(meta + 2 * n, 0, 2 * sizeof(int32_t), on_aux ? h->aux : s));
     }
     return OG_OK;
 }
@@ -299,8 +305,8 @@ int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, cons
     float *det_score = slot->det_score.ptr + det0;
     int32_t *det_index = slot->det_index.ptr + det0;
     int32_t *det_count = slot->det_count.ptr + plane0;
-    uint32_t *cand_count = h->cand_count.ptr + plane0;
-    uint64_t *cand_keys = h->cand_keys.ptr + plane0 * kCandCap;
+    uint32_t *cand_count = slot->cand_count.ptr + plane0;
+    uint64_t *cand_keys = slot->cand_keys.ptr + plane0 * kCandCap;
     const int planes = cn * c.n_keypoints;
     if (timed) OG_TRY(mark(h, slot, 1, s));
     if (fused) {
@@ -314,22 +320,31 @@ int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, cons
                                        fused->flip, c.thre_hmp, cand_count, cand_keys, h->tile_amax.ptr,
                                        h->tile_list.ptr, h->tile_list.ptr + tiles, h->sm_count, s,
                                        &h->launches));
-        if (timed) OG_TRY(mark(h, slot, 2, s));
-        OG_TRY(launch_select_topk(nullptr, planes, hgt, w, c.thre_hmp, c.topk, cand_count, cand_keys,
-                                  det_score, det_index, det_count, meta + 2 * n + 1, s));
-        h->launches += 1;
     } else {
-        OG_TRY(launch_nms_topk(heat + plane0 * HW, planes, hgt, w, c.thre_hmp, c.topk, cand_count,
-                               cand_keys, det_score, det_index, det_count, false, true, s, &h->launches,
-                               timed && h->timing ? slot->ev[2] : nullptr));
+        OG_TRY(launch_nms_candidates(heat + plane0 * HW, planes, hgt, w, c.thre_hmp, cand_count, cand_keys,
+                                     s, &h->launches));
     }
-    if (timed) OG_TRY(mark(h, slot, 3, s));
-    // K2 -> K3 -> D2H run on the handle's own high-priority stream: they are latency-bound
-    // and occupy a fraction of the SMs, so the next K1 (HBM-bound, on the caller's stream)
-    // overlaps them instead of queueing behind them.
+    if (timed) OG_TRY(mark(h, slot, 2, s));
+    // Everything after the streaming pass runs on the handle's own high-priority stream: the
+    // per-plane selection, K2, K3 and the D2H are latency-bound and occupy a fraction of the
+    // SMs, so the next K1 pass (HBM-bound, on the caller's stream) overlaps them instead of
+    // queueing behind them.
     cudaStream_t a = h->aux;
-    OG_CUDA_TRY(cudaEventRecord(slot->k1_done[chunk], s));
-    OG_CUDA_TRY(cudaStreamWaitEvent(a, slot->k1_done[chunk], 0));
+    const bool sel_on_aux = h->select_on_aux == 2 || (h->select_on_aux == 1 && fused != nullptr);
+    if (sel_on_aux) {
+        OG_CUDA_TRY(cudaEventRecord(slot->k1_done[chunk], s));
+        OG_CUDA_TRY(cudaStreamWaitEvent(a, slot->k1_done[chunk], 0));
+    }
+    cudaStream_t sel = sel_on_aux ? a : s;
+    if (timed) OG_TRY(mark(h, slot, 3, sel));
+    OG_TRY(launch_select_topk(fused ? nullptr : heat + plane0 * HW, planes, hgt, w, c.thre_hmp, c.topk,
+                              cand_count, cand_keys, det_score, det_index, det_count,
+                              fused ? meta + 2 * n + 1 : nullptr, sel));
+    h->launches += 1;
+    if (!sel_on_aux) {
+        OG_CUDA_TRY(cudaEventRecord(slot->k1_done[chunk], s));
+        OG_CUDA_TRY(cudaStreamWaitEvent(a, slot->k1_done[chunk], 0));
+    }
     if (timed) OG_TRY(mark(h, slot, 4, a));
     const int nd = extras ? extras->vector_nd : 2;
     OffsetSource src = {};
@@ -578,6 +593,8 @@ int og_create(const og_config *cfg, og_handle **out) {
         const int v = atoi(env);
         if (v >= 1 && v <= kMaxChunks) h->host_chunks = v;
     }
+    h->select_on_aux = 1;
+    if (const char *env = getenv("OG_SELECT_ON_AUX")) h->select_on_aux = atoi(env);
     h->fused_redos = 0;
     h->zero_copy_calls = 0;
     h->tables_valid = false;
@@ -609,6 +626,7 @@ int og_create(const og_config *cfg, og_handle **out) {
     {
         int least = 0, greatest = 0;
         cudaError_t err = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (const char *env = getenv("OG_AUX_PRIORITY")) if (atoi(env) == 0) greatest = least;   // tuning aid
         if (err == cudaSuccess) err = cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, greatest);
         if (err != cudaSuccess) {
             h->aux = nullptr;
@@ -666,6 +684,8 @@ int og_destroy(og_handle *h) {
         sl.det_score.release();
         sl.det_index.release();
         sl.det_count.release();
+        sl.cand_count.release();
+        sl.cand_keys.release();
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.call_start) cudaEventDestroy(sl.call_start);
         for (int j = 0; j < kMaxChunks; ++j) {
@@ -1126,7 +1146,7 @@ int og_last_stage_times_ms(og_handle *h, float *out6) {
                "og_last_stage_times_ms: enable stage timing, decode and fetch first");
     ResultSlot *slot = &h->slots[h->fetched_slot];
     OG_CUDA_TRY(cudaEventSynchronize(slot->ev[kStageEvents - 1]));
-    static const int first[6] = {0, 1, 2, 4, 5, 6};     // ev[3] -> ev[4] is the hand-over between streams
+    static const int first[6] = {0, 1, 3, 4, 5, 6};     // ev[2] -> ev[3] is the hand-over between streams
     for (int i = 0; i < 6; ++i)
         OG_CUDA_TRY(cudaEventElapsedTime(&out6[i], slot->ev[first[i]], slot->ev[first[i] + 1]));
     return OG_OK;

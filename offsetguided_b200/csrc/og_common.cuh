@@ -77,6 +77,10 @@ int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int
                     float *out_score, int32_t *out_index, int32_t *out_count,
                     bool force_radix, bool apply_nms, cudaStream_t s, int64_t *launches,
                     cudaEvent_t after_pass1 = nullptr);
+// pass 1 alone (counters cleared, survivors appended)
+int launch_nms_candidates(const float *heat, int planes, int h, int w, float thre,
+                          uint32_t *cand_count, uint64_t *cand_keys, cudaStream_t s,
+                          int64_t *launches);
 // pass 2 alone on candidate lists some other kernel filled; with heat == nullptr a plane
 // with more than kCandCap candidates cannot be re-scanned and raises *overflow_flag.
 int launch_select_topk(const float *heat, int planes, int h, int w, float thre, int k,

@@ -401,25 +401,32 @@ int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int
                     int32_t *out_index, int32_t *out_count, bool force_radix, bool apply_nms,
                     cudaStream_t s, int64_t *launches, cudaEvent_t after_pass1) {
     if (planes == 0) return OG_OK;
-    if (!force_radix) {
-        OG_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t) * planes, s));
-        const int strips = (w + 127) / 128;
-        const int chunks = (h + kRowsPerWarp - 1) / kRowsPerWarp;
-        const long long warps = (long long)planes * strips * chunks;
-        const int threads = kK1Threads;
-        const long long blocks = (warps + (threads / 32) - 1) / (threads / 32);
-        const bool vec4 = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
-        const bool pos = thre > 0.0f;
-        auto kern = pos ? (vec4 ? nms_candidates_kernel<true, true> : nms_candidates_kernel<true, false>)
-                        : (vec4 ? nms_candidates_kernel<false, true> : nms_candidates_kernel<false, false>);
-        kern<<<(unsigned)blocks, threads, 0, s>>>(heat, planes, h, w, thre, cand_count, cand_keys);
-        OG_CUDA_TRY(cudaGetLastError());
-        if (launches) *launches += 1;
-    }
+    if (!force_radix) OG_TRY(launch_nms_candidates(heat, planes, h, w, thre, cand_count, cand_keys, s, launches));
     if (after_pass1) OG_CUDA_TRY(cudaEventRecord(after_pass1, s));
     select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
                                                         out_score, out_index, out_count,
                                                         force_radix ? 1 : 0, apply_nms ? 1 : 0, nullptr);
+    OG_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += 1;
+    return OG_OK;
+}
+
+// pass 1 alone: clear the counters, stream the maps, append the survivors
+int launch_nms_candidates(const float *heat, int planes, int h, int w, float thre,
+                          uint32_t *cand_count, uint64_t *cand_keys, cudaStream_t s,
+                          int64_t *launches) {
+    if (planes == 0) return OG_OK;
+    OG_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t) * planes, s));
+    const int strips = (w + 127) / 128;
+    const int chunks = (h + kRowsPerWarp - 1) / kRowsPerWarp;
+    const long long warps = (long long)planes * strips * chunks;
+    const int threads = kK1Threads;
+    const long long blocks = (warps + (threads / 32) - 1) / (threads / 32);
+    const bool vec4 = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
+    const bool pos = thre > 0.0f;
+    auto kern = pos ? (vec4 ? nms_candidates_kernel<true, true> : nms_candidates_kernel<true, false>)
+                    : (vec4 ? nms_candidates_kernel<false, true> : nms_candidates_kernel<false, false>);
+    kern<<<(unsigned)blocks, threads, 0, s>>>(heat, planes, h, w, thre, cand_count, cand_keys);
     OG_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;
     return OG_OK;
