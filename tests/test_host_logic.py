@@ -119,3 +119,26 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'oracle' not in src.replace('no oracle', ''), f'{f} mentions the oracle'
+
+
+def test_image_strided_views_are_passed_through():
+    """Channel slices of one packed [N, 55, h, w] head output keep their memory (decoded in
+    place by og_decode_features_dev_ex); other layouts are made contiguous."""
+    import torch
+    from offsetguided_b200.engine import _image_strided
+    packed = torch.zeros(4, 55, 6, 8)
+    h_view, o_view = packed[:, :17], packed[:, 17:]
+    t, stride = _image_strided(h_view)
+    assert t.data_ptr() == h_view.data_ptr() and stride == 55 * 48
+    t, stride = _image_strided(o_view)
+    assert t.data_ptr() == o_view.data_ptr() and stride == 55 * 48
+    t, stride = _image_strided(packed)
+    assert t.data_ptr() == packed.data_ptr() and stride == 55 * 48
+    one = packed[:1, :17]
+    assert _image_strided(one)[1] == 17 * 48
+    transposed = packed.permute(0, 1, 3, 2)[:, :17]              # W-major planes: not passable
+    t, stride = _image_strided(transposed)
+    assert t.is_contiguous() and stride == 17 * 48 and t.data_ptr() != packed.data_ptr()
+    every_other = packed[:, ::2]                                  # plane stride != h * w
+    t, stride = _image_strided(every_other)
+    assert t.is_contiguous() and stride == every_other.shape[1] * 48
