@@ -396,6 +396,69 @@ def test_fused_path_equals_materialising_path(cuda_device, shape, stride, mode, 
         gio.compare_poses(p, r, rtol=RTOL)
 
 
+@pytest.mark.parametrize('stride,mode,flip', [(4, 'bicubic', False), (4, 'bicubic', True), (2, 'bicubic', False),
+                                              (8, 'bicubic', True), (4, 'bilinear', False), (2, 'bilinear', True),
+                                              (8, 'bilinear', False)])
+def test_fused_candidates_at_block_and_image_borders(cuda_device, stride, mode, flip):
+    """K1f corner cases, compared with flip -> resize -> K1 on the materialised map: spikes on both
+    sides of every work-block boundary (the 3 x 3 test then needs the pixel ring outside the block,
+    lanes 0 / 31 and the rows above / below), in the image corners and on the borders (tap clamping,
+    bilinear's src < 0 clamp, zero padding of the NMS window), 2-cell plateaus straddling a boundary
+    (tied peaks in two blocks), values that land exactly on the threshold, and negative lobes."""
+    h, w = 37, 70
+    bw = 32 // stride                       # cells per work block along x; 8 cell rows per block
+    rng = np.random.RandomState(stride * 7 + len(mode))
+    n_in = 4 if flip else 2
+    hmp = np.zeros((n_in, 17, h, w), np.float32)
+    for img in range(n_in):
+        for c in range(17):
+            pts = [(0, 0), (0, w - 1), (h - 1, 0), (h - 1, w - 1), (0, w // 2), (h // 2, 0), (h - 1, 5), (9, w - 1)]
+            for by in (8, 16, 24, 32):
+                for bx in range(bw, w, bw):
+                    pts.append((by - 1 if rng.rand() < 0.5 else by, bx - 1 if rng.rand() < 0.5 else bx))
+            picks = [pts[i] for i in rng.choice(len(pts), size=10, replace=False)]
+            for (y, x) in picks:
+                hmp[img, c, y, x] = rng.uniform(0.3, 1.0)
+            # plateaus across a vertical and a horizontal block boundary
+            hmp[img, c, 20, bw - 1:bw + 1] = 0.625
+            hmp[img, c, 15:17, 3 * bw // 2] = 0.75
+            hmp[img, c, 28, 40] = -0.5                       # negative lobe next to positives
+            hmp[img, c, 28, 41] = 0.5
+    hmp[0, 0] = 0
+    hmp[0, 0, 12, 12] = 0.05                                 # an exact-threshold plane (see thre below)
+    omp = np.zeros((n_in, 38, h, w), np.float32)
+    skel = cfg.COCO_PERSON_SKELETON
+    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel)
+    tables = (kp, fl, rs) if flip else None
+    # threshold = the exact interpolated peak value of plane (0, 0), so ">= thre" is hit with equality
+    up = co_resize_plane(hmp, kp, flip, stride, mode)
+    thre = float(up.max())
+    assert 0.01 < thre < 0.6
+    eng = DecoderEngine(17, skel, topk=64, thre_hmp=thre, min_len=0.5, dist_max=40, use_scale=True,
+                        person_thre=0.05)
+    th, to = torch.from_numpy(hmp).cuda(), torch.from_numpy(omp).cuda()
+    eng.decode_features(th, to, stride, stride, mode, tables)
+    assert eng.fused_redo_count == 0
+    f_s, f_i, _ = [t.cpu().numpy() for t in eng.last_intermediates(n_in // 2 if flip else n_in)]
+    eng.set_fused(False)
+    eng.decode_features(th, to, stride, stride, mode, tables)
+    s_s, s_i, _ = [t.cpu().numpy() for t in eng.last_intermediates(n_in // 2 if flip else n_in)]
+    assert (s_i >= 0).sum() > 17 * 4
+    assert np.array_equal(f_i, s_i) and np.array_equal(f_s, s_s)
+    assert (f_s[0, 0] == np.float32(thre)).any()              # the equality case was really exercised
+
+
+def co_resize_plane(hmp, kp, flip, stride, mode):
+    """Full-resolution values of plane (image 0, channel 0) as the reference computes them."""
+    from oracle import c_oracle as co
+    n = hmp.shape[0] // 2 if flip else hmp.shape[0]
+    plane = hmp[:1, :1].copy()
+    if flip:
+        plane = ((hmp[:1, :1] + hmp[n:n + 1, kp[0]:kp[0] + 1, :, ::-1]) * np.float32(0.5)).astype(np.float32)
+    return co.resize(np.ascontiguousarray(plane), stride, mode)[0, 0]
+
+
 def test_fused_path_overflow_reruns_exactly(cuda_device):
     """Noise heat maps overflow the per-plane candidate lists; the batch is then re-run on the
     GPU through the materialising path and must equal it."""
