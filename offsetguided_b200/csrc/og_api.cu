@@ -114,7 +114,8 @@ struct og_handle {
     og_config cfg;
     SkeletonDev sk;
     int device;
-    int smem_rows;
+    int smem_rows;               // person-table rows in shared memory, batches up to one image per SM
+    int smem_rows_dense;         // ... larger batches (several K3 CTAs per SM)
     size_t group_smem;
     int64_t launches;
 
@@ -126,7 +127,7 @@ struct og_handle {
     DevBuf<float> limbs;
     DevBuf<float> slab;
     DevBuf<int32_t> group_prep;
-    DevBuf<float> tile_amax;            // fused path scratch: activity map
+    DevBuf<uint8_t> tile_flag;          // fused path scratch: one flag per work block, zero between calls
     DevBuf<int32_t> tile_list;          // [blocks] work list + the active-block counter at the end
     int sm_count;
     DevBuf<float> fused_hmp, fused_off;     // materialising path only
@@ -221,13 +222,13 @@ int run_k3(og_handle *h, const float *limbs, int n, float *out_poses, int capaci
     g.use_scale = c.use_scale;
     g.person_thre = c.person_thre;
     g.sort_dim = c.sort_dim;
-    g.smem_rows = h->smem_rows;
+    g.smem_rows = n > h->sm_count ? h->smem_rows_dense : h->smem_rows;
     g.slab = nullptr;
     g.slab_stride = 0;
     OG_TRY(h->group_prep.ensure(group_prep_ints(g)));
     g.prep = h->group_prep.ptr;
     const int pmax = c.n_limbs * c.topk;
-    if (h->smem_rows < pmax) {
+    if (g.smem_rows < pmax) {
         g.slab_stride = ((size_t)pmax * c.n_keypoints * 6 + 3) / 4 * 4;
         OG_TRY(h->slab.ensure(g.slab_stride * (size_t)n));
         g.slab = h->slab.ptr;
@@ -310,14 +311,17 @@ int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, cons
     const int planes = cn * c.n_keypoints;
     if (timed) OG_TRY(mark(h, slot, 1, s));
     if (fused) {
-        size_t amax_floats = 0, tiles = 0;
-        fused_scratch(cn, c.n_keypoints, fused->h, fused->w, fused->scale, &amax_floats, &tiles);
-        OG_TRY(h->tile_amax.ensure(amax_floats));
+        size_t flag_bytes = 0, tiles = 0;
+        fused_scratch(cn, c.n_keypoints, fused->h, fused->w, fused->scale, &flag_bytes, &tiles);
+        if (flag_bytes > h->tile_flag.cap) {        // a fresh buffer starts out clear; the kernels keep it so
+            OG_TRY(h->tile_flag.ensure(flag_bytes));
+            OG_CUDA_TRY(cudaMemsetAsync(h->tile_flag.ptr, 0, h->tile_flag.cap, s));
+        }
         OG_TRY(h->tile_list.ensure(tiles + 1));
         // the mirrored copy of image i sits n images behind it: shifting the base keeps that offset
         OG_TRY(launch_fused_candidates(shift_images(fused->hmp, i0), h->kp_flip.ptr, cn, n,
                                        c.n_keypoints, fused->h, fused->w, fused->scale, fused->cubic,
-                                       fused->flip, c.thre_hmp, cand_count, cand_keys, h->tile_amax.ptr,
+                                       fused->flip, c.thre_hmp, cand_count, cand_keys, h->tile_flag.ptr,
                                        h->tile_list.ptr, h->tile_list.ptr + tiles, h->sm_count, s,
                                        &h->launches));
     } else {
@@ -615,6 +619,27 @@ int og_create(const og_config *cfg, og_handle **out) {
     }
     int rows = (int)((budget - fixed) / ((size_t)cfg->n_keypoints * 24));
     rows = std::min(rows, std::min(pmax, 256));
+    // K3 is latency-bound (one CTA per image, issue slots ~4 % busy).  Up to one image per SM
+    // the large table is used: one CTA fills an SM's shared memory, which also spreads the CTAs
+    // over the SMs when they run beside the next call's K1.  Beyond that, several CTAs per SM
+    // multiply what an SM groups per second (profiles/r1_k3_occupancy_sweep.txt): the dense
+    // table keeps as many person rows as three (else two) CTAs per SM allow while ~40 KB of the
+    // SM stay L1 — but at least 64 rows: real scenes hold tens of persons, and a larger table
+    // restarts the image on the global slab.
+    int dense = rows;
+    for (const size_t share : {(size_t)62 * 1024, (size_t)94 * 1024}) {
+        if (fixed >= share) continue;
+        const int fit = (int)((share - fixed) / ((size_t)cfg->n_keypoints * 24));
+        if (fit >= 64) {
+            dense = std::min(rows, fit);
+            break;
+        }
+    }
+    if (const char *env = getenv("OG_K3_ROWS")) {              // tuning aid: person-table rows in shared memory
+        const int v = atoi(env);
+        if (v >= 16) rows = dense = std::min(rows, v);
+    }
+    h->smem_rows_dense = dense;
     g.smem_rows = rows;
     h->smem_rows = rows;
     h->group_smem = group_smem_bytes(g);
@@ -666,7 +691,7 @@ int og_destroy(og_handle *h) {
     h->limbs.release();
     h->slab.release();
     h->group_prep.release();
-    h->tile_amax.release();
+    h->tile_flag.release();
     h->tile_list.release();
     h->fused_hmp.release();
     h->fused_off.release();

@@ -142,12 +142,13 @@ int launch_flip_cat_offsets(const float *off2n, float *out, int n, int l, int h,
 
 bool fused_supported(int n, int c, int scale, int h, int w);
 // scratch of the fused K1: floats of the 4 x 4-cell activity map, ints of the block work list
-void fused_scratch(int n, int c, int h, int w, int scale, size_t *amax_floats, size_t *list_ints);
-// sub_amax / block_list: fused_scratch() elements, n_active: one int
+void fused_scratch(int n, int c, int h, int w, int scale, size_t *flag_bytes, size_t *list_ints);
+// block_flag: fused_scratch() bytes, ALL ZERO on entry (the kernels leave them zero again);
+// block_list: fused_scratch() ints, n_active: one int
 // `n` images starting at hmp; the mirrored copy of image i is image n_total + i (flip only)
 int launch_fused_candidates(const MapView &hmp, const int32_t *kp_flip_dev, int n, int n_total, int c, int h, int w,
                             int scale, bool cubic, bool flip, float thre, uint32_t *cand_count,
-                            uint64_t *cand_keys, float *sub_amax, int32_t *block_list,
+                            uint64_t *cand_keys, uint8_t *block_flag, int32_t *block_list,
                             int32_t *n_active, int sm_count, cudaStream_t s, int64_t *launches);
 
 struct GroupLaunch {

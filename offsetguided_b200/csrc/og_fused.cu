@@ -9,12 +9,12 @@
 // (sum |wx|)(sum |wy|) max|taps| <= 1.375^2 max|taps| for the A = -0.75 cubic (1 for bilinear),
 // so a region whose taps are all below thre / kBound cannot hold a candidate.  Three kernels:
 //
-//   amax_scan_kernel    streams the maps once (128-bit loads, 8 rows in flight per thread) and
-//                       writes max |fused value| of every 4 x 4-cell sub-block — the only pass
-//                       that touches all of the input, HBM-bound;
-//   block_list_kernel   a BLOCK is (32 / S) x 8 cells = 32 x 8S full-resolution pixels; it is
-//                       active if a sub-block that overlaps the block or its tap halo can reach
-//                       thre.  Active blocks are compacted into a work list;
+//   amax_scan_kernel    streams the maps once (128-bit loads, 8 rows in flight per thread): max
+//                       |fused value| of every 4 x 4-cell sub-block — the only pass that touches
+//                       all of the input, HBM-bound.  A BLOCK is (32 / S) x 8 cells = 32 x 8S
+//                       full-resolution pixels; a sub-block that can reach thre (rare) flags the
+//                       blocks whose cells or tap halo it overlaps;
+//   block_list_kernel   compacts the flagged blocks into a work list (and clears the flags);
 //   fused_block_kernel  persistent warps walk the work list, ONE WARP PER BLOCK, one lane per
 //                       full-resolution column.  The block's cells (+halo, fused with the mirrored
 //                       copy when flip-testing, prefetched one block ahead into registers) go to
@@ -68,10 +68,11 @@ __device__ __forceinline__ unsigned abs_bits(float v) { return __float_as_uint(f
 template <typename T, bool kFlip, bool kVec>
 __global__ void __launch_bounds__(kScanThreads)
 amax_scan_kernel(const T *__restrict__ hmp, size_t img_stride, const int32_t *__restrict__ kp_flip,
-                 int N, int C, int h, int w, float *__restrict__ sub_amax, long long total) {
+                 int N, int C, int h, int w, int block_w, int halo, float limit,
+                 uint8_t *__restrict__ block_flag, long long total) {
     const long long idx = (long long)blockIdx.x * kScanThreads + threadIdx.x;
     if (idx >= total) return;
-    const int sxs = (w + kSub - 1) / kSub, sys = (h + kSub - 1) / kSub;
+    const int sxs = (w + kSub - 1) / kSub;
     const int bands = (h + 2 * kSub - 1) / (2 * kSub);
     const int sx = (int)(idx % sxs);
     const long long t = idx / sxs;
@@ -116,45 +117,38 @@ amax_scan_kernel(const T *__restrict__ hmp, size_t img_stride, const int32_t *__
             }
         }
     }
-    float *o = sub_amax + ((size_t)plane * sys + 2 * band) * sxs + sx;
-    o[0] = __uint_as_float(m[0]);
-    if (2 * band + 1 < sys) o[sxs] = __uint_as_float(m[1]);
+    // A sub-block that can reach the threshold (rare) flags every work block whose cells or tap
+    // halo it overlaps; plain byte stores of the same value from many threads are benign.
+    const int bxs = (w + block_w - 1) / block_w, bys = (h + kBlockCellsH - 1) / kBlockCellsH;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (__uint_as_float(m[j]) < limit) continue;               // NaN: not below, stays active
+        const int ys = y0 + j * kSub;
+        if (ys >= h) continue;
+        const int bx_lo = max(x0 - halo, 0) / block_w, bx_hi = min((x0 + kSub - 1 + halo) / block_w, bxs - 1);
+        const int by_lo = max(ys - halo, 0) / kBlockCellsH,
+                  by_hi = min((ys + kSub - 1 + halo) / kBlockCellsH, bys - 1);
+        for (int by = by_lo; by <= by_hi; ++by)
+            for (int bx = bx_lo; bx <= bx_hi; ++bx)
+                block_flag[((size_t)plane * bys + by) * bxs + bx] = 1;
+    }
 }
 
 // ---- pass B: work list -----------------------------------------------------------
+// Compacts the flagged blocks and clears the flags for the next call.
 // entry = {plane (image * C + channel), image, block row << 16 | block column,
 //          channel | channel of the mirrored map << 16}
 __global__ void __launch_bounds__(256)
-block_list_kernel(const float *__restrict__ sub_amax, const int32_t *__restrict__ kp_flip, int C,
-                  int flip, int h, int w, int block_w, int halo, float limit, long long total,
-                  int4 *__restrict__ block_list, int32_t *__restrict__ n_active) {
+block_list_kernel(uint8_t *__restrict__ block_flag, const int32_t *__restrict__ kp_flip, int C,
+                  int flip, int bxs, int bys, long long total, int4 *__restrict__ block_list,
+                  int32_t *__restrict__ n_active) {
     __shared__ int s_warp[8];
     __shared__ int s_base;
     const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
-    const int sxs = (w + kSub - 1) / kSub, sys = (h + kSub - 1) / kSub;
-    const int bxs = (w + block_w - 1) / block_w, bys = (h + kBlockCellsH - 1) / kBlockCellsH;
     bool active = false;
-    int bx = 0, by = 0, plane = 0;
     if (g < total) {
-        bx = (int)(g % bxs);
-        by = (int)((g / bxs) % bys);
-        plane = (int)(g / ((long long)bxs * bys));
-        const float *p = sub_amax + (size_t)plane * sys * sxs;
-        const int sx0 = max(bx * block_w - halo, 0) / kSub;
-        const int sx1 = min(bx * block_w + block_w - 1 + halo, w - 1) / kSub;
-        const int sy0 = max(by * kBlockCellsH - halo, 0) / kSub;
-        const int sy1 = min(by * kBlockCellsH + kBlockCellsH - 1 + halo, h - 1) / kSub;
-        // The window is at most 4 x 6 sub-blocks (8 + 2 halo rows, 16 + 2 halo columns): a fixed,
-        // fully unrolled trip count with clamped coordinates keeps all loads independent and in
-        // flight together (a repeated sub-block does not change the maximum); one compare at the
-        // end (bit order = value order for |v|).
-        unsigned m = 0u;
-#pragma unroll
-        for (int dy = 0; dy < 4; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 6; ++dx)
-                m = max(m, __float_as_uint(__ldg(p + min(sy0 + dy, sy1) * sxs + min(sx0 + dx, sx1))));
-        active = !(__uint_as_float(m) < limit);       // NaN: active
+        active = block_flag[g] != 0;
+        if (active) block_flag[g] = 0;
     }
     // one global atomic per CTA
     const unsigned ballot = __ballot_sync(kFull, active);
@@ -172,6 +166,9 @@ block_list_kernel(const float *__restrict__ sub_amax, const int32_t *__restrict_
     }
     __syncthreads();
     if (active) {
+        const int bx = (int)(g % bxs);
+        const int by = (int)((g / bxs) % bys);
+        const int plane = (int)(g / ((long long)bxs * bys));
         const int n = plane / C, c = plane - n * C;
         const int cb = flip ? kp_flip[c] : c;
         block_list[s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))] =
@@ -429,8 +426,8 @@ bool fused_supported(int n, int c, int scale, int h, int w) {
            (unsigned long long)h * scale * w * scale < 0xffffffffULL;
 }
 
-void fused_scratch(int n, int c, int h, int w, int scale, size_t *amax_floats, size_t *list_ints) {
-    *amax_floats = (size_t)n * c * ((w + kSub - 1) / kSub) * ((h + kSub - 1) / kSub);
+void fused_scratch(int n, int c, int h, int w, int scale, size_t *flag_bytes, size_t *list_ints) {
+    *flag_bytes = block_count(n, c, h, w, scale);               // one byte per work block
     *list_ints = 4 * block_count(n, c, h, w, scale);          // int4 entries
 }
 
@@ -438,7 +435,7 @@ namespace {
 template <typename T>
 int launch_fused_t(const T *hmp, size_t img_stride, const int32_t *kp_flip_dev, int n, int n_total,
                    int c, int h, int w, int scale, bool cubic, bool flip, float thre,
-                   uint32_t *cand_count, uint64_t *cand_keys, float *sub_amax, int32_t *block_list,
+                   uint32_t *cand_count, uint64_t *cand_keys, uint8_t *block_flag, int32_t *block_list,
                    int32_t *n_active, int sm_count, cudaStream_t s, int64_t *launches) {
     OG_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t) * (size_t)n * c, s));
     OG_CUDA_TRY(cudaMemsetAsync(n_active, 0, sizeof(int32_t), s));
@@ -446,26 +443,27 @@ int launch_fused_t(const T *hmp, size_t img_stride, const int32_t *kp_flip_dev, 
     const int sxs = (w + kSub - 1) / kSub, bands = (h + 2 * kSub - 1) / (2 * kSub);
     const long long scan_threads = (long long)n * c * bands * sxs;
     const unsigned scan_grid = (unsigned)((scan_threads + kScanThreads - 1) / kScanThreads);
+    const int block_w = 32 / scale, halo = cubic ? 2 : 1;
+    const float limit = thre / (cubic ? 1.95f : 1.001f);
     // vector loads need whole 4-cell groups and rows aligned to the 4-cell load size (also the
     // rows of the mirrored read and of every image)
     const size_t vec_bytes = 4 * sizeof(T);
     const bool vec = (w % kSub) == 0 && (reinterpret_cast<uintptr_t>(hmp) % vec_bytes) == 0 &&
                      (img_stride * sizeof(T)) % vec_bytes == 0;
     if (flip) {
-        if (vec) amax_scan_kernel<T, true, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
-        else amax_scan_kernel<T, true, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
+        if (vec) amax_scan_kernel<T, true, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
+        else amax_scan_kernel<T, true, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
     } else {
-        if (vec) amax_scan_kernel<T, false, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
-        else amax_scan_kernel<T, false, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, sub_amax, scan_threads);
+        if (vec) amax_scan_kernel<T, false, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
+        else amax_scan_kernel<T, false, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
     }
     OG_CUDA_TRY(cudaGetLastError());
 
     const size_t blocks = block_count(n, c, h, w, scale);
-    const float limit = thre / (cubic ? 1.95f : 1.001f);
     int4 *list4 = reinterpret_cast<int4 *>(block_list);
     block_list_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, s>>>(
-        sub_amax, kp_flip_dev, c, flip ? 1 : 0, h, w, 32 / scale, cubic ? 2 : 1, limit,
-        (long long)blocks, list4, n_active);
+        block_flag, kp_flip_dev, c, flip ? 1 : 0, (w + block_w - 1) / block_w,
+        (h + kBlockCellsH - 1) / kBlockCellsH, (long long)blocks, list4, n_active);
     OG_CUDA_TRY(cudaGetLastError());
 
     int st;
@@ -481,7 +479,7 @@ int launch_fused_t(const T *hmp, size_t img_stride, const int32_t *kp_flip_dev, 
 
 int launch_fused_candidates(const MapView &hmp, const int32_t *kp_flip_dev, int n, int n_total, int c,
                             int h, int w, int scale, bool cubic, bool flip, float thre,
-                            uint32_t *cand_count, uint64_t *cand_keys, float *sub_amax,
+                            uint32_t *cand_count, uint64_t *cand_keys, uint8_t *block_flag,
                             int32_t *block_list, int32_t *n_active, int sm_count, cudaStream_t s,
                             int64_t *launches) {
     if (n == 0) return OG_OK;
@@ -491,10 +489,10 @@ int launch_fused_candidates(const MapView &hmp, const int32_t *kp_flip_dev, int 
     }
     if (hmp.dtype == OG_DTYPE_BF16)
         return launch_fused_t(static_cast<const __nv_bfloat16 *>(hmp.ptr), hmp.image_stride, kp_flip_dev, n,
-                              n_total, c, h, w, scale, cubic, flip, thre, cand_count, cand_keys, sub_amax,
+                              n_total, c, h, w, scale, cubic, flip, thre, cand_count, cand_keys, block_flag,
                               block_list, n_active, sm_count, s, launches);
     return launch_fused_t(static_cast<const float *>(hmp.ptr), hmp.image_stride, kp_flip_dev, n, n_total, c,
-                          h, w, scale, cubic, flip, thre, cand_count, cand_keys, sub_amax, block_list,
+                          h, w, scale, cubic, flip, thre, cand_count, cand_keys, block_flag, block_list,
                           n_active, sm_count, s, launches);
 }
 

@@ -191,6 +191,39 @@ def test_k3_random_tables_against_oracle(cuda_device):
         assert got.shape == ref.shape and np.array_equal(got, ref), f'case {case} k={k} pool={pool}'
 
 
+def test_k3_large_batch_uses_dense_tables(cuda_device):
+    """Beyond one image per SM K3 keeps a smaller person table in shared memory (three CTAs per
+    SM); every image — also the ones whose table overflows it and restarts on the global slab —
+    must come out as in a small batch."""
+    rng = np.random.RandomState(123)
+    skel = cfg.COCO_PERSON_SKELETON
+    tables = []
+    for case in range(12):
+        k, pool = 32, int(rng.choice([4, 10, 400]))         # pool 400: ~100+ persons, overflows 100 rows
+        limbs = np.zeros((19, k, 13), np.float32)
+        xy = rng.randint(1, 600, size=(17, pool, 2)).astype(np.float32)
+        ids = rng.randint(0, 640 * 640, size=(17, pool))
+        for l, (jf, jt) in enumerate(skel):
+            sc = (rng.permutation(k) + rng.uniform(0.1, 0.9, size=k)).astype(np.float32) / k
+            for r in range(k):
+                a, b = rng.randint(pool), rng.randint(pool)
+                limbs[l, r] = (xy[jf, a, 0], xy[jf, a, 1], 0.5, xy[jt, b, 0], xy[jt, b, 1], 0.6,
+                               ids[jf, a] + jf * 409600, ids[jt, b] + jt * 409600,
+                               rng.uniform(0, 50), 10, sc[r], 4, 4)
+        tables.append(limbs)
+    g = decoder.GreedyGroup(0.06, sort_dim=2, dist_max=40, use_scale=True)
+    small = g.group_batch(np.stack(tables))
+    ref = [ro.group_skeletons(t, skel, 17, 0.06, 2, 40, True) for t in tables]
+    assert max(len(r) for r in ref) > 100
+    for a, r in zip(small, ref):
+        assert a.shape == r.shape and np.array_equal(a, r)
+    order = rng.randint(0, len(tables), size=400)
+    big = g.group_batch(np.stack([tables[i] for i in order]))
+    assert len(big) == 400
+    for got, i in zip(big, order):
+        assert got.shape == ref[i].shape and np.array_equal(got, ref[i])
+
+
 def test_k3_empty_and_degenerate(cuda_device):
     g = decoder.GreedyGroup(0.06, sort_dim=2, dist_max=40, use_scale=False)
     out = g.group_skeletons(np.zeros((19, 4, 13), np.float32))
