@@ -69,7 +69,11 @@ def workload_config(args, n_gpus):
         'images_per_gpu_per_step': args.batch,
         'global_batch': args.batch * n_gpus,
         'parallelism': 'image-sharded x%d, no collective' % n_gpus,
-        'l2_policy': 'hot-path inputs are 5.8 GB per step (heat 1.78 GB + offsets 3.98 GB) >> 126 MB L2',
+        'l2_policy': 'hot-path inputs are %.1f GB per step (heat %.2f GB + offsets %.2f GB) >> 126 MB L2; '
+                     'e2e / features_dev read %.0f MB of network-resolution heat maps per step'
+                     % (args.batch * 55 * args.long_edge ** 2 * 4 / 1e9, args.batch * 17 * args.long_edge ** 2 * 4 / 1e9,
+                        args.batch * 38 * args.long_edge ** 2 * 4 / 1e9,
+                        args.batch * (1 if args.no_flip else 2) * 17 * (args.long_edge // 4) ** 2 * 4 / 1e6),
         'persons_per_image': PERSONS,
     }
 

@@ -283,8 +283,8 @@ int begin_call(og_handle *h, ResultSlot *slot, bool fused, int n, int hgt, int w
     if (n > 0) {
         // total, overflow: first written by pass 2 / K3 of this call, which follow on the same stream
         int32_t *meta = reinterpret_cast<int32_t *>(slot->out.ptr);
-        const bool on_aux = h->select_on_aux == 2 || (h->select_on_aux == 1 && fused);
-        OG_CUDA_TRY(cudaMemsetAsync(meta + 2 * n, 0, 2 * sizeof(int32_t), on_aux ? h->aux : s));
+        (void)s;
+        OG_CUDA_TRY(cudaMemsetAsync(meta + 2 * n, 0, 2 * sizeof(int32_t), h->aux));
     }
     return OG_OK;
 }
@@ -992,15 +992,22 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
     OG_CUDA_TRY(cudaStreamWaitEvent(h->cp, slot->call_start, 0));
     // images [i0, i0 + cn) and, when flip-testing, their mirrored copies n images further on: one
     // 2-row strided copy (row pitch = n images) instead of two transfers
+    auto copy_images = [&](float *dst, const float *src, size_t per_image, int i0, int cn) -> int {
+        const size_t pitch = (size_t)n * per_image * sizeof(float), width = (size_t)cn * per_image * sizeof(float);
+        if (flip_test && pitch <= 0x7fffffffULL) {          // within cudaMemcpy2D's pitch limit
+            OG_CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)i0 * per_image, pitch, src + (size_t)i0 * per_image, pitch,
+                                          width, 2, cudaMemcpyHostToDevice, h->cp));
+            return OG_OK;
+        }
+        for (int half = 0; half < (flip_test ? 2 : 1); ++half) {
+            const size_t at = ((size_t)half * n + i0) * per_image;
+            OG_CUDA_TRY(cudaMemcpyAsync(dst + at, src + at, width, cudaMemcpyHostToDevice, h->cp));
+        }
+        return OG_OK;
+    };
     auto copy_range = [&](int i0, int cn) -> int {
-        const size_t rows = flip_test ? 2 : 1;
-        OG_CUDA_TRY(cudaMemcpy2DAsync(slot->in_hmp.ptr + (size_t)i0 * hmp_img, (size_t)n * hmp_img * sizeof(float),
-                                      hmp_host + (size_t)i0 * hmp_img, (size_t)n * hmp_img * sizeof(float),
-                                      (size_t)cn * hmp_img * sizeof(float), rows, cudaMemcpyHostToDevice, h->cp));
-        if (!off_alias)
-            OG_CUDA_TRY(cudaMemcpy2DAsync(slot->in_off.ptr + (size_t)i0 * off_img, (size_t)n * off_img * sizeof(float),
-                                          off_host + (size_t)i0 * off_img, (size_t)n * off_img * sizeof(float),
-                                          (size_t)cn * off_img * sizeof(float), rows, cudaMemcpyHostToDevice, h->cp));
+        OG_TRY(copy_images(slot->in_hmp.ptr, hmp_host, hmp_img, i0, cn));
+        if (!off_alias) OG_TRY(copy_images(slot->in_off.ptr, off_host, off_img, i0, cn));
         return OG_OK;
     };
     const float *off_src = off_alias ? off_alias : slot->in_off.ptr;

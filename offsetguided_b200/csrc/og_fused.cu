@@ -15,17 +15,19 @@
 //                       full-resolution pixels; a sub-block that can reach thre (rare) flags the
 //                       blocks whose cells or tap halo it overlaps;
 //   block_list_kernel   compacts the flagged blocks into a work list (and clears the flags);
-//   fused_block_kernel  persistent warps walk the work list, ONE WARP PER BLOCK, one lane per
-//                       full-resolution column.  The block's cells (+halo, fused with the mirrored
-//                       copy when flip-testing, prefetched one block ahead into registers) go to
-//                       a per-warp shared tile; each lane interpolates its column along x once
-//                       (8 + 2 HALO values kept in registers), then walks down the 8S rows with one
-//                       4-tap (2-tap) combine per pixel in ATen's accumulation order, so values
-//                       are bit-identical to the materialised map.  Interpolation weights depend
-//                       on the phase (pixel mod S) only, so they live in registers for the
-//                       lifetime of the warp.  A row in which some lane reaches thre (rare) runs
-//                       the 3x3 test with lane shuffles; the pixel ring outside the block is
-//                       evaluated on demand.
+//   fused_block_kernel  warps stride over the work list, ONE WARP PER BLOCK, one lane per
+//                       full-resolution column.  The block's cells (+halo, averaged with the
+//                       mirrored copy when flip-testing, prefetched one block ahead into registers)
+//                       go to a per-warp shared tile; each lane interpolates its column along x
+//                       one tile row at a time into a sliding (TAPS + 1)-row register window and
+//                       walks down the 8S rows with one 4-tap (2-tap) combine per pixel in ATen's
+//                       accumulation order, so values are bit-identical to the materialised map.
+//                       Interpolation weights depend on the phase (pixel mod S) only, so they
+//                       live in registers for the lifetime of the warp.  A row in which some lane
+//                       reaches thre runs the 3x3 test with lane shuffles; the pixel ring outside
+//                       the block is evaluated on demand.  The cell-row loop is deliberately NOT
+//                       unrolled: 8S rows of straight-line code (64 KB) thrash the instruction
+//                       cache and run 3x slower.
 // Skipping is provably lossless (kBound leaves 3 % for rounding); nothing else is skipped.
 #include "og_common.cuh"
 #include "og_interp.cuh"

@@ -589,6 +589,34 @@ def test_packed_head_output_decoded_in_place(cuda_device, dtype, flip):
         gio.compare_poses(p, r, rtol=RTOL)
 
 
+def test_config5_handover_batch32_bf16(cuda_device):
+    """BASELINE config 5 per-GPU share (batch 256 over 8 GPUs = 32 images, flip-test: 64 network
+    outputs): the hourglass head hands over one packed bf16 [64, 55, 160, 160] tensor.  With
+    random-init weights (normal(0, 0.001), models/networks.py:147-173) the heat maps are ~0 and no
+    person may come out; with persons rendered into the same tensor every image must decode as the
+    float32 copies do (C oracle)."""
+    import bench
+    from oracle import c_oracle as co
+    skel = cfg.COCO_PERSON_SKELETON
+    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel)
+    n = 32
+    pp = decoder.decoder_factory(_args(topk=32, thre_hmp=0.04, person_thre=0.04, dist_max=40, batch_size=n))
+    g = torch.Generator(device='cuda').manual_seed(5)
+    empty = (torch.randn((2 * n, 55, 160, 160), generator=g, device='cuda') * 0.001).to(torch.bfloat16)
+    out = pp.generate_poses([[[empty[:, :17]], [[]], [[]]], [[empty[:, 17:]], [[]], [[]]]], flip_test=True)
+    assert len(out) == n and all(p.shape == (0, 17, 6) and p.dtype == np.float32 for p in out)
+    hmp, omp = bench.lowres_inputs(31337, n, 640, True)
+    packed = torch.from_numpy(np.concatenate((hmp, omp), axis=1)).cuda().to(torch.bfloat16)
+    got = pp.generate_poses([[[packed[:, :17]], [[]], [[]]], [[packed[:, 17:]], [[]], [[]]]], flip_test=True)
+    wide = packed.float().cpu().numpy()
+    ref = co.generate_poses(np.ascontiguousarray(wide[:, :17]), np.ascontiguousarray(wide[:, 17:]), skel, 17,
+                            topk=32, thre_hmp=0.04, min_len=0.5, person_thre=0.04, dist_max=40.0,
+                            use_scale=True, flip_test=True, kp_flips=kp, limb_flips=fl, limb_reserve=rs)
+    assert sum(len(p) for p in ref) >= n * 4
+    _pose_lists_equal(got, ref)
+
+
 def test_bf16_overflow_redo_and_odd_shapes(cuda_device):
     """bf16 maps with an odd width (scalar loads) and a noise batch whose candidate lists overflow
     (exact redo after an on-device conversion to dense float32)."""
