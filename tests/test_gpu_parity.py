@@ -747,6 +747,50 @@ def test_config4_1024_long_edge(cuda_device):
         assert np.array_equal(a, b)
 
 
+def test_maximum_sizes(cuda_device):
+    """The ABI's upper bounds: topk = OG_MAX_TOPK (128) on crowded scenes, and a skeleton with
+    OG_MAX_KEYPOINTS = 64 keypoints and OG_MAX_LIMBS = 64 limbs (a ring), both against the oracle."""
+    skel = cfg.COCO_PERSON_SKELETON
+    heat, offs = scenes.synth_hires_batch(909, 2, 20, 320, 256, skel)
+    eng = DecoderEngine(17, skel, topk=128, thre_hmp=0.04, min_len=0.5, dist_max=40, use_scale=True,
+                        person_thre=0.04)
+    got = eng.decode_maps(torch.from_numpy(heat).cuda(), torch.from_numpy(offs).cuda())
+    ref_limbs = ro.generate_limbs(heat, offs, skel, 128, 0.04, 0.5, 1, 1)
+    _, _, lb = eng.last_intermediates(2)
+    assert gio.compare_limbs(lb.cpu().numpy(), ref_limbs, 0.04, rtol=RTOL) > 300
+    for i in range(2):
+        gio.compare_poses(got[i], ro.group_skeletons(ref_limbs[i], skel, 17, 0.04, 2, 40, True), rtol=RTOL)
+        assert len(got[i]) >= 15
+    # 64 keypoints / 64 limbs: joint j sits at a fixed offset from joint j - 1
+    c = 64
+    ring = [(j, (j + 1) % c) for j in range(c)]
+    rng = np.random.RandomState(64)
+    h, w = 96, 128
+    heat = rng.uniform(0, 0.02, size=(1, c, h, w)).astype(np.float32)
+    offs = np.zeros((1, 2 * c, h, w), np.float32)
+    for person in range(3):
+        x0, y0 = rng.randint(10, 40), rng.randint(10, 30) + 25 * person
+        pts = [(x0 + (j % 16) * 5 + rng.randint(0, 2), y0 + (j // 16) * 5) for j in range(c)]
+        for j, (x, y) in enumerate(pts):
+            heat[0, j, y, x] = 0.9 - 0.1 * person + 0.001 * j
+        for l, (a, b) in enumerate(ring):
+            (xa, ya), (xb, yb) = pts[a], pts[b]
+            offs[0, 2 * l, ya, xa] = xb - xa
+            offs[0, 2 * l + 1, ya, xa] = yb - ya
+    eng = DecoderEngine(c, ring, topk=8, thre_hmp=0.05, min_len=0.5, dist_max=40, use_scale=True,
+                        person_thre=0.05)
+    got = eng.decode_maps(torch.from_numpy(heat).cuda(), torch.from_numpy(offs).cuda())
+    ref_limbs = ro.generate_limbs(heat, offs, ring, 8, 0.05, 0.5, 1, 1)
+    ref = ro.group_skeletons(ref_limbs[0], ring, c, 0.05, 2, 40, True)
+    assert len(ref) == 3 and (ref[:, :, 2] > 0).all()
+    gio.compare_poses(got[0], ref, rtol=RTOL)
+    from offsetguided_b200 import _lib
+    with pytest.raises(_lib.OgError):
+        DecoderEngine(17, skel, topk=129, thre_hmp=0.05)
+    with pytest.raises(_lib.OgError):
+        DecoderEngine(65, [(0, 1)], topk=8, thre_hmp=0.05)
+
+
 def test_config3_crowdpose_batch32(cuda_device):
     """BASELINE config 3: 14 keypoints, builder-supplied skeleton, 20 persons, K = 64, batch 32."""
     from oracle import c_oracle as co
