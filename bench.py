@@ -180,16 +180,16 @@ def cpu_decode_fn():
         c_oracle.load()
         cores = c_oracle.num_threads()
 
-        def run(hmp, omp, flip):
+        def run(hmp, omp, flip, stage_seconds=None):
             return c_oracle.generate_poses(hmp, omp, skel, 17, topk=TOPK, thre_hmp=THRE_HMP,
                                            min_len=MIN_LEN, person_thre=PERSON_THRE, dist_max=DIST_MAX,
                                            use_scale=True, flip_test=flip, kp_flips=kp, limb_flips=fl,
-                                           limb_reserve=rs)
+                                           limb_reserve=rs, stage_seconds=stage_seconds)
         return run, cores, 'oracle/og_oracle.c (C + OpenMP restatement of the reference decoder)'
     except Exception:
         from oracle import ref_oracle as ro
 
-        def run(hmp, omp, flip):
+        def run(hmp, omp, flip, stage_seconds=None):
             return ro.generate_poses(hmp, omp, skel, 17, topk=TOPK, thre_hmp=THRE_HMP, min_len=MIN_LEN,
                                      person_thre=PERSON_THRE, dist_max=DIST_MAX, use_scale=True,
                                      flip_test=flip, kp_flips=kp, limb_flips=fl, limb_reserve=rs)
@@ -202,14 +202,17 @@ def time_cpu(args, n_images, repeats):
     hmp, omp = lowres_inputs(9000, n_images, args.long_edge, flip)
     run(hmp[:1] if not flip else np.concatenate((hmp[:1], hmp[n_images:n_images + 1])),
         omp[:1] if not flip else np.concatenate((omp[:1], omp[n_images:n_images + 1])), flip)   # warm
-    times = []
+    times, stage_runs = [], []
     for _ in range(repeats):
+        stage = {}
         t0 = time.perf_counter()
-        poses = run(hmp, omp, flip)
+        poses = run(hmp, omp, flip, stage)
         times.append(time.perf_counter() - t0)
+        stage_runs.append(stage)
         assert len(poses) == n_images
     best = min(times)
-    return n_images / best, cores, what, times
+    stage_ms = {k: 1e3 * v / n_images for k, v in stage_runs[times.index(best)].items()}
+    return n_images / best, cores, what, times, stage_ms
 
 
 def run_reference(args):
@@ -420,10 +423,11 @@ def run_b200(args):
         if n_gpus == 1:
             run, cores, what = cpu_decode_fn()
             cpu_n = args.cpu_sample or (16 if cores > 1 else 1)
-            cpu_value, cores, what, cpu_times = time_cpu(args, cpu_n, 2 if cores > 1 else 1)
+            cpu_value, cores, what, cpu_times, cpu_stage = time_cpu(args, cpu_n, 2 if cores > 1 else 1)
             cpu_block = {'value': cpu_value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d images of the same workload (flip fusion + x4 resize + NMS/top-K '
-                                   '+ limbs + grouping), best of %d, %s' % (cpu_n, len(cpu_times), what)}
+                                   '+ limbs + grouping), best of %d, %s' % (cpu_n, len(cpu_times), what),
+                         'stage_ms_per_image': cpu_stage}
         line = {
             'metric': METRIC, 'value': n_gpus * B * args.steps / (hot_ms * 1e-3), 'unit': UNIT,
             'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup,

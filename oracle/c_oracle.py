@@ -113,13 +113,26 @@ def group_skeletons(limbs, skeleton, n_keypoints, person_thre, sort_dim=2, dist_
 def generate_poses(hmps, offs, skeleton, n_keypoints, *, topk, thre_hmp, min_len, person_thre,
                    sort_dim=2, dist_max=20, use_scale=True, hmp_stride=4, off_stride=4,
                    resize_mode='bicubic', flip_test=False, kp_flips=None, limb_flips=None,
-                   limb_reserve=None, return_limbs=False):
+                   limb_reserve=None, return_limbs=False, stage_seconds=None):
+    """``stage_seconds`` (a dict) accumulates the wall time of every stage, for the CPU baseline
+    of bench.py: flip fusion / resize / NMS + top-K + limbs / grouping."""
+    import time
+    t = [time.perf_counter()]
+
+    def lap(name):
+        t.append(time.perf_counter())
+        if stage_seconds is not None:
+            stage_seconds[name] = stage_seconds.get(name, 0.0) + t[-1] - t[-2]
     if flip_test:
         hmps, offs = flip_augment(hmps, offs, kp_flips, limb_flips, limb_reserve)
+    lap('flip_fusion')
     hmps_hr = resize(hmps, hmp_stride, resize_mode) if hmp_stride > 1 else hmps
     offs_hr = resize(offs, off_stride, 'bilinear') if off_stride > 1 else offs
+    lap('resize')
     limbs = generate_limbs(hmps_hr, offs_hr, skeleton, topk, thre_hmp, min_len, hmp_stride, off_stride)
+    lap('nms_topk_limbs')
     poses = group_batch(limbs, skeleton, n_keypoints, person_thre, sort_dim, dist_max, use_scale)
+    lap('grouping')
     if return_limbs:
         return poses, limbs
     return poses
