@@ -43,6 +43,7 @@ extern "C" {
 #define OG_MAX_TOPK 128
 #define OG_DTYPE_F32 0       /* element types of og_decode_features_dev_ex */
 #define OG_DTYPE_BF16 1
+#define OG_DTYPE_F16 2       /* what the reference's apex AMP evaluation produces (evaluate.py:139-150) */
 
 typedef enum og_status {
     OG_OK = 0,
@@ -198,13 +199,13 @@ int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_
                            const int32_t *kp_flip, const int32_t *limb_flip,
                            const int32_t *limb_reserve, int n_reserve, void *stream);
 
-/* og_decode_features_dev on maps as a bf16 network leaves them (the reference
- * converts everything to float32 first, decoder/factory.py:59): `dtype` OG_DTYPE_F32 or
- * OG_DTYPE_BF16; consecutive images are `hmp_image_stride` / `off_image_stride` ELEMENTS apart
+/* og_decode_features_dev on maps as a reduced-precision network leaves them (the
+ * reference converts everything to float32 first, decoder/factory.py:59): `dtype` OG_DTYPE_F32,
+ * OG_DTYPE_BF16 or OG_DTYPE_F16; consecutive images are `hmp_image_stride` / `off_image_stride` ELEMENTS apart
  * (0 = dense), the C (resp. 2L) planes of one image are contiguous — so the two channel slices
  * of one packed [n, C + 2L, h, w] head output are decoded in place, without a split or a
- * float32 copy.  bf16 values widen exactly to float32: results are bit-identical to decoding
- * the converted maps.  Fused path only (strides 2 / 4 / 8, thre_hmp > 0); the exact redo of a
+ * float32 copy.  bf16 / f16 values widen exactly to float32: results are bit-identical to
+ * decoding the converted maps.  Fused path only (strides 2 / 4 / 8, thre_hmp > 0); the exact redo of a
  * candidate overflow converts the maps to dense float32 on the device first. */
 int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off_dev, int dtype,
                               int64_t hmp_image_stride, int64_t off_image_stride,

@@ -15,6 +15,7 @@ OG_POSE_COLS = 6
 OG_MAX_TOPK = 128
 OG_DTYPE_F32 = 0
 OG_DTYPE_BF16 = 1
+OG_DTYPE_F16 = 2
 
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 c_float_p = ctypes.POINTER(ctypes.c_float)

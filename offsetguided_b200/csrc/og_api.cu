@@ -246,7 +246,7 @@ struct K1Fused {
 };
 
 inline MapView dense_f32(const float *p, size_t per_image) { return MapView{p, OG_DTYPE_F32, per_image}; }
-inline size_t elem_size(int dtype) { return dtype == OG_DTYPE_BF16 ? 2 : 4; }
+inline size_t elem_size(int dtype) { return dtype == OG_DTYPE_F32 ? 4 : 2; }
 inline MapView shift_images(MapView v, size_t images) {
     v.ptr = static_cast<const char *>(v.ptr) + images * v.image_stride * elem_size(v.dtype);
     return v;
@@ -918,7 +918,8 @@ int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off
                               const int32_t *kp_flip, const int32_t *limb_flip,
                               const int32_t *limb_reserve, int n_reserve, void *stream) {
     OG_REQUIRE(h && (n == 0 || (hmp_dev && off_dev)), "og_decode_features_dev_ex: null pointer");
-    OG_REQUIRE(dtype == OG_DTYPE_F32 || dtype == OG_DTYPE_BF16, "dtype must be OG_DTYPE_F32 or OG_DTYPE_BF16");
+    OG_REQUIRE(dtype == OG_DTYPE_F32 || dtype == OG_DTYPE_BF16 || dtype == OG_DTYPE_F16,
+               "dtype must be OG_DTYPE_F32, OG_DTYPE_BF16 or OG_DTYPE_F16");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
                               limb_flip, limb_reserve, n_reserve, s));

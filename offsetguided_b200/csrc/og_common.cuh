@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -89,19 +90,22 @@ int launch_select_topk(const float *heat, int planes, int h, int w, float thre, 
                        cudaStream_t s);
 
 // ---- network-resolution maps as the caller holds them ------------------------------
-// Element types: float32 (what the reference decodes, factory.py:59) or bfloat16 straight from
-// a bf16 head.  A bf16 value widens exactly to float32, so everything after the
+// Element types: float32 (what the reference decodes, factory.py:59), or bfloat16 / float16
+// straight from a reduced-precision head.  Such a value widens exactly to float32, so everything after the
 // load is the float32 path bit for bit.  Images may be `image_stride` elements apart (channel
 // slices of one packed [N, 55, h, w] network output); the planes of an image are contiguous.
 struct MapView {
     const void *ptr;
-    int dtype;                      // OG_DTYPE_F32 / OG_DTYPE_BF16
+    int dtype;                      // OG_DTYPE_F32 / OG_DTYPE_BF16 / OG_DTYPE_F16
     size_t image_stride;            // elements between consecutive images
 };
 #ifdef __CUDACC__
 __device__ __forceinline__ float load_cell(const float *p) { return __ldg(p); }
 __device__ __forceinline__ float load_cell(const __nv_bfloat16 *p) {
     return __uint_as_float((unsigned)__ldg(reinterpret_cast<const unsigned short *>(p)) << 16);
+}
+__device__ __forceinline__ float load_cell(const __half *p) {
+    return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short *>(p))));
 }
 #endif
 int launch_densify(const MapView &src, float *dst, int images, size_t per_image, cudaStream_t s);

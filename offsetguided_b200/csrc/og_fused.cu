@@ -61,6 +61,14 @@ __device__ __forceinline__ float4 load_cells4(const __nv_bfloat16 *p) {
                        __uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
 }
 
+__device__ __forceinline__ float4 load_cells4(const __half *p) {
+    unsigned lo, hi;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&lo));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
 // |v| >= 0: the IEEE bit pattern orders like the value, and NaN sorts above everything,
 // which keeps such regions active
 __device__ __forceinline__ unsigned abs_bits(float v) { return __float_as_uint(fabsf(v)); }
@@ -493,6 +501,10 @@ int launch_fused_candidates(const MapView &hmp, const int32_t *kp_flip_dev, int 
         return launch_fused_t(static_cast<const __nv_bfloat16 *>(hmp.ptr), hmp.image_stride, kp_flip_dev, n,
                               n_total, c, h, w, scale, cubic, flip, thre, cand_count, cand_keys, block_flag,
                               block_list, n_active, sm_count, s, launches);
+    if (hmp.dtype == OG_DTYPE_F16)
+        return launch_fused_t(static_cast<const __half *>(hmp.ptr), hmp.image_stride, kp_flip_dev, n,
+                              n_total, c, h, w, scale, cubic, flip, thre, cand_count, cand_keys, block_flag,
+                              block_list, n_active, sm_count, s, launches);
     return launch_fused_t(static_cast<const float *>(hmp.ptr), hmp.image_stride, kp_flip_dev, n, n_total, c,
                           h, w, scale, cubic, flip, thre, cand_count, cand_keys, block_flag, block_list,
                           n_active, sm_count, s, launches);
@@ -517,6 +529,8 @@ int launch_densify(const MapView &src, float *dst, int images, size_t per_image,
     const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
     if (src.dtype == OG_DTYPE_BF16)
         densify_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(src.ptr), src.image_stride, dst, per_image, total);
+    else if (src.dtype == OG_DTYPE_F16)
+        densify_kernel<<<grid, 256, 0, s>>>(static_cast<const __half *>(src.ptr), src.image_stride, dst, per_image, total);
     else
         densify_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(src.ptr), src.image_stride, dst, per_image, total);
     OG_CUDA_TRY(cudaGetLastError());

@@ -62,6 +62,7 @@ __device__ __forceinline__ float sample_offset_t(const OffsetSource &src, int im
 __device__ __forceinline__ float sample_offset(const OffsetSource &src, int img, int L, int l,
                                                int comp, int X, int Y) {
     if (src.maps.dtype == OG_DTYPE_BF16) return sample_offset_t<__nv_bfloat16>(src, img, L, l, comp, X, Y);
+    if (src.maps.dtype == OG_DTYPE_F16) return sample_offset_t<__half>(src, img, L, l, comp, X, Y);
     return sample_offset_t<float>(src, img, L, l, comp, X, Y);
 }
 

@@ -31,6 +31,10 @@ def as_cuda_f32(t, device=None):
     return t.contiguous().float()
 
 
+_DTYPES = {torch.float32: _lib.OG_DTYPE_F32, torch.bfloat16: _lib.OG_DTYPE_BF16,
+           torch.float16: _lib.OG_DTYPE_F16}
+
+
 def _image_strided(t):
     """(tensor, elements between images) for an NCHW tensor whose planes are dense and contiguous
     within an image (a channel slice of a packed head output qualifies); other layouts are
@@ -218,15 +222,16 @@ class DecoderEngine(object):
         assert hmp.is_cuda == off.is_cuda, 'heat and offset maps must live on the same side'
         flip = flip_tables is not None
         args = self._flip_args(flip_tables) if flip else (None, None, None, 0)
-        # Device maps as a bf16 network leaves them (bf16, or channel slices of one packed head
-        # output) are decoded in place on the fused path; anything else becomes dense float32.
+        # Device maps as a reduced-precision network leaves them (bf16 / f16, or channel slices of
+        # one packed head output) are decoded in place on the fused path; anything else becomes
+        # dense float32.
         in_place = (not on_host and self._fused and self.thre_hmp > 0 and int(hmp_stride) in (2, 4, 8)
                     and hmp.shape[0] > 0 and hmp.dtype == off.dtype
-                    and hmp.dtype in (torch.float32, torch.bfloat16))
+                    and hmp.dtype in _DTYPES)
         if in_place:
             hmp, hmp_is = _image_strided(hmp)
             off, off_is = _image_strided(off)
-            in_place = (hmp.dtype == torch.bfloat16 or hmp_is != hmp.shape[1] * hmp.shape[2] * hmp.shape[3]
+            in_place = (hmp.dtype != torch.float32 or hmp_is != hmp.shape[1] * hmp.shape[2] * hmp.shape[3]
                         or off_is != off.shape[1] * off.shape[2] * off.shape[3])
         if not in_place:
             hmp = hmp.contiguous().float()
@@ -235,7 +240,7 @@ class DecoderEngine(object):
         n = n_in // 2 if flip else n_in
         with torch.cuda.device(self.device):
             if in_place:
-                dtype = _lib.OG_DTYPE_BF16 if hmp.dtype == torch.bfloat16 else _lib.OG_DTYPE_F32
+                dtype = _DTYPES[hmp.dtype]
                 _lib.check(self.lib.og_decode_features_dev_ex(
                     self._h, _ptr(hmp), _ptr(off), dtype, hmp_is, off_is, n, h, w, int(hmp_stride),
                     int(off_stride), mode, 1 if flip else 0, *args, _stream_ptr(self.device)))

@@ -549,7 +549,7 @@ def test_host_offsets_stay_on_the_host(cuda_device):
     assert np.array_equal(over[0], staged[0]) and len(over[0]) > 5
 
 
-@pytest.mark.parametrize('dtype,flip', [('bf16', True), ('bf16', False), ('f32', True)])
+@pytest.mark.parametrize('dtype,flip', [('bf16', True), ('bf16', False), ('f32', True), ('f16', True)])
 def test_packed_head_output_decoded_in_place(cuda_device, dtype, flip):
     """SURVEY 8f-4 / BASELINE config 5 hand-over: one packed [2N, 17 + 38, h, w] head output, bf16 or
     float32, its two channel slices decoded in place (no split, no float32 copy).  A bf16 value
@@ -562,8 +562,8 @@ def test_packed_head_output_decoded_in_place(cuda_device, dtype, flip):
     n = 3
     hmp, omp = bench.lowres_inputs(4321, n, 384, flip)
     packed = torch.from_numpy(np.concatenate((hmp, omp), axis=1)).cuda()
-    if dtype == 'bf16':
-        packed = packed.to(torch.bfloat16)
+    if dtype != 'f32':
+        packed = packed.to(torch.bfloat16 if dtype == 'bf16' else torch.float16)
     h_view, o_view = packed[:, :17], packed[:, 17:]
     assert not h_view.is_contiguous()
     pp = decoder.decoder_factory(_args(topk=32, thre_hmp=0.04, person_thre=0.04, dist_max=40))
