@@ -98,6 +98,58 @@ class PostProcess(torch.nn.Module):
         tables = (self.keypoints_flips, self.limbs_flips[0], self.limbs_flips[1]) if flip_test else None
         return eng.decode_features(hmps, offs, self.hmp_stride, self.off_stride, self.inter_mode, tables)
 
+    def flip_augment(self, hmps, jomps, offs, scmps, cat_flip_offs, vector_nd):
+        """Fuse the outputs of the original and the W-flipped images (reference
+        decoder/factory.py:98-146; same arguments and return tuple).  ``hmps`` (2N, C, h, w) and
+        ``offs`` (2N, 2L, h, w) hold the originals followed by the flipped copies; ``jomps`` /
+        ``scmps`` are tensors only when the matching optional head is enabled.  Returns
+        ``(hmps, jomps, offs, scmps, vector_nd)`` for N images; ``cat_flip_offs`` builds the 4-D
+        offset vectors (vector_nd = 4) instead of averaging."""
+        from .. import _lib
+        from ..engine import as_cuda_f32, _ptr, _stream_ptr
+        lib = _lib.load()
+        hmps = as_cuda_f32(hmps)
+        device = hmps.device
+        offs = as_cuda_f32(offs, device)
+        use_jomps = self.include_jitter_offset and isinstance(jomps, torch.Tensor)
+        use_scmps = self.include_scale and isinstance(scmps, torch.Tensor)
+        eng = self._engine(device)
+        with torch.cuda.device(device):
+            s = _stream_ptr(device)
+
+            def flip_average(x, perm, negate_even):
+                x = as_cuda_f32(x, device)
+                n2, ch, h, w = x.shape
+                out = torch.empty((n2 // 2, ch, h, w), dtype=torch.float32, device=device)
+                _lib.check(lib.og_flip_average_f32(_ptr(x), _lib.int32_array(perm) if perm else None,
+                                                   1 if negate_even else 0, n2 // 2, ch, h, w,
+                                                   _ptr(out), s))
+                return out
+
+            n2, _, h, w = hmps.shape
+            lf = _lib.int32_array(self.limbs_flips[0])
+            lr = _lib.int32_array(self.limbs_flips[1])
+            if cat_flip_offs:                                       # factory.py:115-127
+                out = torch.empty((n2 // 2, 4 * len(self.skeleton), h, w), dtype=torch.float32,
+                                  device=device)
+                _lib.check(lib.og_flip_cat_offsets_f32(_ptr(offs), lf, lr, len(self.limbs_flips[1]),
+                                                       n2 // 2, len(self.skeleton), h, w, _ptr(out), s))
+                offs, vector_nd = out, 4
+                hmps = flip_average(hmps, self.keypoints_flips, False)
+            else:                                                   # factory.py:128-139
+                fh = torch.empty((n2 // 2,) + tuple(hmps.shape[1:]), dtype=torch.float32, device=device)
+                fo = torch.empty((n2 // 2,) + tuple(offs.shape[1:]), dtype=torch.float32, device=device)
+                _lib.check(lib.og_flip_fuse_f32(eng._h, _ptr(hmps), _ptr(offs),
+                                                _lib.int32_array(self.keypoints_flips), lf, lr,
+                                                len(self.limbs_flips[1]), n2 // 2, h, w,
+                                                _ptr(fh), _ptr(fo), s))
+                hmps, offs = fh, fo
+            if use_jomps:                                           # factory.py:109-113
+                jomps = flip_average(jomps, None, True)
+            if use_scmps:                                           # factory.py:141-144
+                scmps = flip_average(scmps, self.keypoints_flips, False)
+        return hmps, jomps, offs, scmps, vector_nd
+
     def _generate_poses_staged(self, hmps, jomps, offs, scmps, flip_test, cat_flip_offs, scored_off):
         """The optional heads and flags (scored_off, keypoint-scale maps, jitter-offset maps,
         cat_flip_offs): the same kernels, called stage by stage through the C ABI on
@@ -113,40 +165,11 @@ class PostProcess(torch.nn.Module):
         eng = self._engine(device)
         mode = {'bilinear': 0, 'bicubic': 1}[self.inter_mode]
         vector_nd = 2
+        if flip_test:
+            hmps, jomps, offs, scmps, vector_nd = self.flip_augment(hmps, jomps, offs, scmps,
+                                                                    cat_flip_offs, vector_nd)
         with torch.cuda.device(device):
             s = _stream_ptr(device)
-
-            def flip_average(x, perm, negate_even):
-                n2, ch, h, w = x.shape
-                out = torch.empty((n2 // 2, ch, h, w), dtype=torch.float32, device=device)
-                _lib.check(lib.og_flip_average_f32(_ptr(x), _lib.int32_array(perm) if perm else None,
-                                                   1 if negate_even else 0, n2 // 2, ch, h, w,
-                                                   _ptr(out), s))
-                return out
-
-            if flip_test:
-                n2, _, h, w = hmps.shape
-                lf = _lib.int32_array(self.limbs_flips[0])
-                lr = _lib.int32_array(self.limbs_flips[1])
-                if cat_flip_offs:                                       # factory.py:115-127
-                    out = torch.empty((n2 // 2, 4 * len(self.skeleton), h, w), dtype=torch.float32,
-                                      device=device)
-                    _lib.check(lib.og_flip_cat_offsets_f32(_ptr(offs), lf, lr, len(self.limbs_flips[1]),
-                                                           n2 // 2, len(self.skeleton), h, w, _ptr(out), s))
-                    offs, vector_nd = out, 4
-                    hmps = flip_average(hmps, self.keypoints_flips, False)
-                else:                                                   # factory.py:128-139
-                    fh = torch.empty((n2 // 2,) + tuple(hmps.shape[1:]), dtype=torch.float32, device=device)
-                    fo = torch.empty((n2 // 2,) + tuple(offs.shape[1:]), dtype=torch.float32, device=device)
-                    _lib.check(lib.og_flip_fuse_f32(eng._h, _ptr(hmps), _ptr(offs),
-                                                    _lib.int32_array(self.keypoints_flips), lf, lr,
-                                                    len(self.limbs_flips[1]), n2 // 2, h, w,
-                                                    _ptr(fh), _ptr(fo), s))
-                    hmps, offs = fh, fo
-                if jomps is not None:                                   # factory.py:109-113
-                    jomps = flip_average(jomps, None, True)
-                if scmps is not None:                                   # factory.py:141-144
-                    scmps = flip_average(scmps, self.keypoints_flips, False)
             if scored_off:
                 if vector_nd != 2:
                     raise ValueError('scored_off cannot be combined with cat_flip_offs')

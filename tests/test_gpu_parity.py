@@ -262,6 +262,35 @@ def test_resize_and_flip_bit_exact(cuda_device):
     assert np.array_equal(fh.cpu().numpy(), rh) and np.array_equal(fo.cpu().numpy(), rr)
 
 
+def test_flip_augment_method_matches_reference_semantics(cuda_device):
+    """PostProcess.flip_augment keeps the reference's signature and return tuple
+    (decoder/factory.py:98-146): default branch against the oracle, cat_flip_offs branch against
+    the reference's own tensor expressions."""
+    rng = np.random.RandomState(8)
+    n, h, w = 2, 12, 20
+    hm = rng.uniform(0, 1, size=(2 * n, 17, h, w)).astype(np.float32)
+    om = rng.uniform(-9, 9, size=(2 * n, 38, h, w)).astype(np.float32)
+    pp = decoder.decoder_factory(_args())
+    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, cfg.COCO_PERSON_SKELETON)
+    th, to = torch.from_numpy(hm).cuda(), torch.from_numpy(om).cuda()
+    fh, fj, fo, fs, nd = pp.flip_augment(th, [], to, [], False, 2)
+    rh, ro_ = ro.flip_augment(hm, om, kp, fl, rs)
+    assert nd == 2 and fj == [] and fs == []
+    assert np.array_equal(fh.cpu().numpy(), rh) and np.array_equal(fo.cpu().numpy(), ro_)
+    ch, _, co_, _, nd = pp.flip_augment(th, [], to, [], True, 2)
+    o5 = torch.from_numpy(om).view(2 * n, -1, 2, h, w)
+    orig = o5[:n]
+    reserve = o5[:n, rs].clone()
+    flip = torch.flip(o5[n:], [-1]).clone()
+    flip[:, :, ::2] *= -1.0
+    cat = torch.cat((orig, flip[:, fl]), dim=2)
+    cat[:, rs, 2:] = reserve
+    assert nd == 4 and np.array_equal(co_.cpu().numpy(), cat.reshape(n, -1, h, w).numpy())
+    assert np.array_equal(ch.cpu().numpy(), rh)
+    assert th.shape[0] == 2 * n and np.array_equal(th.cpu().numpy(), hm)          # inputs untouched
+
+
 def test_scored_offset_matches_oracle(cuda_device):
     rng = np.random.RandomState(4)
     hm = rng.uniform(0, 1, size=(2, 17, 20, 24)).astype(np.float32)
