@@ -1,5 +1,6 @@
 """Post-processing entry point (reference decoder/factory.py): ``decoder_cli``,
 ``decoder_factory(args)`` -> ``PostProcess``, ``PostProcess.generate_poses``."""
+import argparse
 import logging
 import re
 
@@ -276,3 +277,12 @@ def decoder_factory(args):
                        limb_grouper=skeleton_grouper, include_scale=args.include_scale,
                        include_jitter_offset=args.include_jitter_offset,
                        feat_stage=args.feat_stage)
+
+
+def debug_parse_args():
+    """Decoder flags at their defaults plus ``--for-debug`` (reference decoder/factory.py:270-280)."""
+    parser = argparse.ArgumentParser(description='Test decoder')
+    parser.add_argument('--for-debug', default=False, action='store_true',
+                        help='this parse is only for debug the code')
+    decoder_cli(parser)
+    return parser.parse_args(['--for-debug'])

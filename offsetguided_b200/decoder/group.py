@@ -89,9 +89,15 @@ def soft_nms(subset, suppressed_v=0):
             if occ[y, x]:
                 xyv[2] = suppressed_v
             else:
-                x0 = max(0, int(xyv[0] - jw))
-                y0 = max(0, int(xyv[1] - jw))
-                x1 = max(x0 + 1, min(occ.shape[1], int(xyv[0] + jw) + 1))
-                y1 = max(y0 + 1, min(occ.shape[0], int(xyv[1] + jw) + 1))
-                occ[y0:y1, x0:x1] += 1
+                scalar_square_add_single(occ, xyv[0], xyv[1], jw, 1)
     return subset
+
+
+def scalar_square_add_single(field, x, y, width, value):
+    """Add ``value`` to the square of half-width ``width`` round (x, y), clipped to the field and
+    at least one pixel large (reference decoder/group.py:278-283; used by soft_nms)."""
+    x0 = max(0, int(x - width))
+    y0 = max(0, int(y - width))
+    x1 = max(x0 + 1, min(field.shape[1], int(x + width) + 1))
+    y1 = max(y0 + 1, min(field.shape[0], int(y + width) + 1))
+    field[y0:y1, x0:x1] += value

@@ -26,6 +26,12 @@ def _on_cuda(t):
     return out, src
 
 
+def normalize_hmps():
+    """Placeholder of the reference (decoder/heatmap.py:10-12: "todo: filter and smooth the
+    heatmaps", never implemented there); kept so that the module exports the same names."""
+    return None
+
+
 def hmp_NMS(heat, kernel=3):
     """3x3 max-pool NMS (reference decoder/heatmap.py:15-35): peaks keep their value,
     every other response becomes 0.  The border is zero padded, plateaus survive.
