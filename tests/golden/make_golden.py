@@ -374,6 +374,30 @@ def make_optional_heads():
                         noise_seed=seed, **out)
 
 
+def make_soft_nms():
+    """decoder.soft_nms (group.py:249-283) on random pose sets: overlapping duplicates, unset (-1)
+    keypoints, points outside the occupancy field."""
+    from decoder import soft_nms
+    rng = np.random.RandomState(4242)
+    inputs, outputs = [], []
+    for case in range(12):
+        persons = int(rng.randint(1, 7))
+        sub = np.zeros((persons, 17, 6), np.float32)
+        sub[..., 0] = rng.uniform(0, 60, size=(persons, 17))
+        sub[..., 1] = rng.uniform(0, 40, size=(persons, 17))
+        sub[..., 2] = np.where(rng.uniform(size=(persons, 17)) < 0.2, -1, rng.uniform(0.1, 1, size=(persons, 17)))
+        sub[..., 3] = rng.choice([0.0, 4.0, 12.0, 25.0], size=(persons, 17))
+        if persons > 1:
+            sub[1, :8, :2] = sub[0, :8, :2] + rng.uniform(-2, 2, size=(8, 2))      # near-duplicates
+        inputs.append(sub.copy())
+        outputs.append(soft_nms(sub.copy(), suppressed_v=0 if case % 2 == 0 else -3).copy())
+    np.savez_compressed(os.path.join(HERE, 'soft_nms.npz'),
+                        counts=np.array([len(x) for x in inputs], np.int32),
+                        inputs=np.concatenate(inputs), outputs=np.concatenate(outputs))
+    print('soft_nms: %d cases, %d keypoints suppressed' % (
+        len(inputs), int(sum((a[..., 2] != b[..., 2]).sum() for a, b in zip(inputs, outputs)))))
+
+
 def main():
     torch.set_num_threads(8)
     encoder_check()
@@ -389,6 +413,7 @@ def main():
     make_poses_case('poses_cfg1', 4000, 1, 5, 640, 640, 32, 0.06, 0.06, 40, False, 0.0)
     make_poses_case('poses_cfg2_flip', 5000, 2, 5, 640, 640, 32, 0.04, 0.04, 40, True, 0.0)
     make_optional_heads()
+    make_soft_nms()
 
 
 if __name__ == '__main__':

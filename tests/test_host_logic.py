@@ -142,3 +142,21 @@ def test_image_strided_views_are_passed_through():
     every_other = packed[:, ::2]                                  # plane stride != h * w
     t, stride = _image_strided(every_other)
     assert t.is_contiguous() and stride == every_other.shape[1] * 48
+
+
+def test_soft_nms_matches_reference_fixture():
+    """decoder.soft_nms against outputs of the reference's own soft_nms (tests/golden/soft_nms.npz,
+    written by make_golden.make_soft_nms)."""
+    from offsetguided_b200 import decoder
+    d = np.load(os.path.join(ROOT, 'tests', 'golden', 'soft_nms.npz'))
+    at = 0
+    changed = 0
+    for case, n in enumerate(d['counts']):
+        sub = d['inputs'][at:at + n].copy()
+        ref = d['outputs'][at:at + n]
+        got = decoder.soft_nms(sub, suppressed_v=0 if case % 2 == 0 else -3)
+        assert got is sub and np.array_equal(got, ref), f'case {case}'
+        changed += int((d['inputs'][at:at + n][..., 2] != ref[..., 2]).sum())
+        at += n
+    assert changed > 20
+    assert decoder.soft_nms([]) == []
