@@ -12,16 +12,20 @@ import numpy as np
 def annotations_inverse(keypoints, meta):
     """Back-project the poses of one image into the original image space
     (reference transforms/preprocess.py:33-63): undo the padding shift, then the resize;
-    keypoint scales are divided by sqrt(sx * sy).  Returns a new array."""
-    keypoints = np.array(keypoints, copy=True)
-    keypoints[:, :, 0] += meta['offset'][0]
-    keypoints[:, :, 1] += meta['offset'][1]
-    keypoints[:, :, 0] /= meta['scale'][0]
-    keypoints[:, :, 1] /= meta['scale'][1]
-    keypoints[:, :, 3] /= np.sqrt(np.prod(meta['scale']))
+    keypoint scales are divided by sqrt(sx * sy).  Returns a new array.
+
+    x and y are handled together; each step is evaluated in float64 and rounded back to the
+    array's dtype, exactly like the reference's four in-place updates."""
     if meta['hflip']:
-        raise Exception('this should not happen. please have a check here, not implemented actually!')
-    return keypoints
+        raise NotImplementedError('horizontally flipped inputs are not back-projected '
+                                  '(the reference raises here as well)')
+    out = np.array(keypoints, copy=True)
+    shift = np.asarray(meta['offset'], dtype=np.float64)[:2]
+    zoom = np.asarray(meta['scale'], dtype=np.float64)[:2]
+    shifted = (out[:, :, :2] + shift).astype(out.dtype)
+    out[:, :, :2] = shifted / zoom
+    out[:, :, 3] = out[:, :, 3] / np.sqrt(np.prod(meta['scale']))
+    return out
 
 
 def coco_results(batch_poses, metas):
