@@ -193,37 +193,35 @@ class PostProcess(torch.nn.Module):
 
 
 def decoder_cli(parser):
-    """Command-line flags of the decoder (reference decoder/factory.py:149-188)."""
-    group = parser.add_argument_group('limb collections in post-processing')
-    group.add_argument('--resize-mode', default='bicubic', choices=['bilinear', 'bicubic'], type=str,
-                       help='interpolation mode for resizing the keypoint heatmaps.')
-    group.add_argument('--topk', default=48, type=int,
-                       help='select the top K responses on each heatmaps, and hence leads to top K '
-                            'limbs of each type. A bigger topk may not leads to better performance')
-    group.add_argument('--thre-hmp', default=0.06, type=float,
-                       help='candidate kepoints below this response value are moved outside the '
-                            'image boarder')
-    group.add_argument('--min-len', default=0.5, type=float,
-                       help='length in pixels, clamp the candidate limbs of zero length to min_len')
-    group.add_argument('--feat-stage', default=-1, type=int,
-                       help='use the inferred feature maps at this stage to generate results')
+    """Command-line flags of the decoder: the flag names, types, choices and defaults of the
+    reference (decoder/factory.py:149-188), so that its launch commands keep working."""
+    collect_flags = parser.add_argument_group('limb collections in post-processing')
+    add = collect_flags.add_argument
+    add('--resize-mode', default='bicubic', choices=['bilinear', 'bicubic'], type=str,
+        help='how the heat maps are brought to decode resolution (offset maps are always bilinear)')
+    add('--topk', default=48, type=int,
+        help='peaks kept per heat-map channel = limb candidates per limb type (at most 128)')
+    add('--thre-hmp', default=0.06, type=float,
+        help='peaks scoring less than this are parked off-image and never form a limb')
+    add('--min-len', default=0.5, type=float,
+        help='lower clamp (pixels) of a limb length, guards the score of zero-length limbs')
+    add('--feat-stage', default=-1, type=int,
+        help='index of the network stack whose output maps are decoded')
 
-    group = parser.add_argument_group('greedy grouping in post-processing')
-    group.add_argument('--person-thre', default=0.06, type=float,
-                       help='threshold for pose instance scores, but COCO evaluates the top k instances')
-    group.add_argument('--sort-dim', default=2, choices=[2, 4], type=int,
-                       help='sort the person poses by the values at the this axis. 2th dim means '
-                            'keypoints score, 4th dim means limb score.')
-    group.add_argument('--dist-max', default=20, type=float,
-                       help='abandon limbs with delta offsets bigger than dist_max, only useful when '
-                            'keypoint scales are not used because use-scale will overlap the smaller '
-                            'dist-max')
-    group.add_argument('--use-scale', default=True, type=boolean_string,
-                       help='only effective when we set --include-scale in the network; use the '
-                            'inferred keypoint scales as the criterion to keep limbs (keypoint pairs)')
-    group.add_argument('--use-jitter-offset', default=True, type=boolean_string,
-                       help='only effective when we set --include-jitter-offset in the network; use '
-                            'the inferred jitter offset to refine the keypoint localization')
+    group_flags = parser.add_argument_group('greedy grouping in post-processing')
+    add = group_flags.add_argument
+    add('--person-thre', default=0.06, type=float,
+        help='persons whose mean score falls below this are dropped')
+    add('--sort-dim', default=2, choices=[2, 4], type=int,
+        help='pose column the person score averages: 2 = keypoint score, 4 = limb score')
+    add('--dist-max', default=20, type=float,
+        help='largest distance (pixels) between a guided limb end and its matched keypoint; with '
+             '--use-scale the keypoint scale takes over whenever it is larger')
+    add('--use-scale', default=True, type=boolean_string,
+        help='gate limbs by the regressed keypoint scale (needs a network built with --include-scale)')
+    add('--use-jitter-offset', default=True, type=boolean_string,
+        help='refine keypoint positions with the regressed jitter offsets (needs '
+             '--include-jitter-offset)')
 
 
 _OMP_SKELETONS = {
