@@ -9,11 +9,10 @@
 // (sum |wx|)(sum |wy|) max|taps| <= 1.375^2 max|taps| for the A = -0.75 cubic (1 for bilinear),
 // so a region whose taps are all below thre / kBound cannot hold a candidate.  Three kernels:
 //
-//   amax_scan_kernel    streams the maps once (128-bit loads, 8 rows in flight per thread): max
-//                       |fused value| of every 4 x 4-cell sub-block — the only pass that touches
-//                       all of the input, HBM-bound.  A BLOCK is (32 / S) x 8 cells = 32 x 8S
-//                       full-resolution pixels; a sub-block that can reach thre (rare) flags the
-//                       blocks whose cells or tap halo it overlaps;
+//   amax_scan_kernel    streams the maps once (128-bit loads, 8 rows in flight per thread) — the
+//                       only pass that touches all of the input, HBM-bound.  A BLOCK is
+//                       (32 / S) x 8 cells = 32 x 8S full-resolution pixels; a cell that can reach
+//                       thre (2 % of them) flags the blocks whose cells or tap halo it overlaps;
 //   block_list_kernel   compacts the flagged blocks into a work list (and clears the flags);
 //   fused_block_kernel  warps stride over the work list, ONE WARP PER BLOCK, one lane per
 //                       full-resolution column.  The block's cells (+halo, averaged with the
@@ -41,7 +40,7 @@ namespace {
 constexpr int kFusedThreads = 256;
 constexpr int kScanThreads = 256;
 constexpr int kBlockCellsH = 8;       // cell rows of a block
-constexpr int kSub = 4;               // sub-block edge (cells) of the activity map
+constexpr int kSub = 4;               // cells per scan thread along x (one vector load); 2 x kSub rows
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ float4 ldg_stream4(const float *p) {
@@ -73,8 +72,8 @@ __device__ __forceinline__ float4 load_cells4(const __half *p) {
 // which keeps such regions active
 __device__ __forceinline__ unsigned abs_bits(float v) { return __float_as_uint(fabsf(v)); }
 
-// ---- pass A: activity map ------------------------------------------------------
-// one thread per (plane, 8-row band, 4-cell column group): two sub-block maxima
+// ---- pass A: activity flags ----------------------------------------------------
+// one thread per (plane, 8-row band, 4-cell column group)
 template <typename T, bool kFlip, bool kVec>
 __global__ void __launch_bounds__(kScanThreads)
 amax_scan_kernel(const T *__restrict__ hmp, size_t img_stride, const int32_t *__restrict__ kp_flip,
@@ -93,26 +92,45 @@ amax_scan_kernel(const T *__restrict__ hmp, size_t img_stride, const int32_t *__
     const T *b = nullptr;
     if (kFlip) b = hmp + (size_t)(N + n) * img_stride + (size_t)kp_flip[c] * h * w;
     const int y0 = band * 2 * kSub, x0 = sx * kSub;
-    unsigned m[2] = {0u, 0u};
+    const int bxs = (w + block_w - 1) / block_w, bys = (h + kBlockCellsH - 1) / kBlockCellsH;
+    uint8_t *flags = block_flag + (size_t)plane * bys * bxs;
+    // Cells [xa, xb] of row y can reach the threshold (rare): flag every work block whose cells or
+    // tap halo they overlap.  Plain byte stores of the same value from many threads are benign.
+    auto flag_blocks = [&](int xa, int xb, int y) {
+        const int bx_lo = max(xa - halo, 0) / block_w, bx_hi = min((xb + halo) / block_w, bxs - 1);
+        const int by_lo = max(y - halo, 0) / kBlockCellsH, by_hi = min((y + halo) / kBlockCellsH, bys - 1);
+        for (int by = by_lo; by <= by_hi; ++by)
+            for (int bx = bx_lo; bx <= bx_hi; ++bx) flags[by * bxs + bx] = 1;
+    };
     if (kVec) {
-        float4 va[2 * kSub], vb[2 * kSub];
+        // two batches of kSub rows: 4 (8 with the mirrored copy) independent 128-bit loads in
+        // flight per thread keep the register count low enough for full occupancy
+#pragma unroll 1
+        for (int r0 = 0; r0 < 2 * kSub; r0 += kSub) {
+            float4 va[kSub], vb[kSub];
 #pragma unroll
-        for (int r = 0; r < 2 * kSub; ++r) {
-            const int y = min(y0 + r, h - 1);          // a repeated row does not change a maximum
-            va[r] = load_cells4(a + (size_t)y * w + x0);
-            if (kFlip) vb[r] = load_cells4(b + (size_t)y * w + (w - kSub - x0));
-        }
-#pragma unroll
-        for (int r = 0; r < 2 * kSub; ++r) {
-            float4 f = va[r];
-            if (kFlip) {                     // (orig + flip_W(flipped)[kp_flip]) / 2, factory.py:101-106
-                f.x = __fmul_rn(__fadd_rn(f.x, vb[r].w), 0.5f);
-                f.y = __fmul_rn(__fadd_rn(f.y, vb[r].z), 0.5f);
-                f.z = __fmul_rn(__fadd_rn(f.z, vb[r].y), 0.5f);
-                f.w = __fmul_rn(__fadd_rn(f.w, vb[r].x), 0.5f);
+            for (int r = 0; r < kSub; ++r) {
+                const int y = min(y0 + r0 + r, h - 1);     // rows below the image repeat the last one
+                va[r] = load_cells4(a + (size_t)y * w + x0);
+                if (kFlip) vb[r] = load_cells4(b + (size_t)y * w + (w - kSub - x0));
             }
-            const unsigned q = max(max(abs_bits(f.x), abs_bits(f.y)), max(abs_bits(f.z), abs_bits(f.w)));
-            m[r / kSub] = max(m[r / kSub], q);
+#pragma unroll
+            for (int r = 0; r < kSub; ++r) {
+                float4 f = va[r];
+                if (kFlip) {                 // (orig + flip_W(flipped)[kp_flip]) / 2, factory.py:101-106
+                    f.x = __fmul_rn(__fadd_rn(f.x, vb[r].w), 0.5f);
+                    f.y = __fmul_rn(__fadd_rn(f.y, vb[r].z), 0.5f);
+                    f.z = __fmul_rn(__fadd_rn(f.z, vb[r].y), 0.5f);
+                    f.w = __fmul_rn(__fadd_rn(f.w, vb[r].x), 0.5f);
+                }
+                const unsigned q = max(max(abs_bits(f.x), abs_bits(f.y)), max(abs_bits(f.z), abs_bits(f.w)));
+                if (__uint_as_float(q) < limit || y0 + r0 + r >= h) continue;   // NaN is not below: stays active
+                const bool c0 = !(fabsf(f.x) < limit), c1 = !(fabsf(f.y) < limit), c2 = !(fabsf(f.z) < limit),
+                           c3 = !(fabsf(f.w) < limit);
+                const int first = c0 ? 0 : (c1 ? 1 : (c2 ? 2 : 3));
+                const int last = c3 ? 3 : (c2 ? 2 : (c1 ? 1 : 0));
+                flag_blocks(x0 + first, x0 + last, y0 + r0 + r);
+            }
         }
     } else {
         for (int r = 0; r < 2 * kSub; ++r) {
@@ -123,24 +141,9 @@ amax_scan_kernel(const T *__restrict__ hmp, size_t img_stride, const int32_t *__
                 if (x >= w) break;
                 float v = load_cell(a + (size_t)y * w + x);
                 if (kFlip) v = __fmul_rn(__fadd_rn(v, load_cell(b + (size_t)y * w + (w - 1 - x))), 0.5f);
-                m[r / kSub] = max(m[r / kSub], abs_bits(v));
+                if (!(fabsf(v) < limit)) flag_blocks(x, x, y);
             }
         }
-    }
-    // A sub-block that can reach the threshold (rare) flags every work block whose cells or tap
-    // halo it overlaps; plain byte stores of the same value from many threads are benign.
-    const int bxs = (w + block_w - 1) / block_w, bys = (h + kBlockCellsH - 1) / kBlockCellsH;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        if (__uint_as_float(m[j]) < limit) continue;               // NaN: not below, stays active
-        const int ys = y0 + j * kSub;
-        if (ys >= h) continue;
-        const int bx_lo = max(x0 - halo, 0) / block_w, bx_hi = min((x0 + kSub - 1 + halo) / block_w, bxs - 1);
-        const int by_lo = max(ys - halo, 0) / kBlockCellsH,
-                  by_hi = min((ys + kSub - 1 + halo) / kBlockCellsH, bys - 1);
-        for (int by = by_lo; by <= by_hi; ++by)
-            for (int bx = bx_lo; bx <= bx_hi; ++bx)
-                block_flag[((size_t)plane * bys + by) * bxs + bx] = 1;
     }
 }
 
