@@ -253,17 +253,18 @@ fused_block_kernel(const T *__restrict__ hmp, size_t img_stride, int N, int h, i
         const T *a = hmp + (size_t)e.y * img_stride + (size_t)(e.w & 0xffff) * hw;
         const T *b = hmp + (size_t)(N + e.y) * img_stride + (size_t)(e.w >> 16) * hw;
         const bool interior = base_x >= 0 && base_y >= 0 && base_x + LW <= w && base_y + LH <= h;
-        if (interior) {                     // warp-uniform: no clamping
-            a += base_y * w + base_x;
-            b += base_y * w + (w - 1 - base_x);
+        if (interior) {                     // warp-uniform: no clamping; 32-bit indices off two bases
+            const int ao = base_y * w + base_x;
+            const int bo = base_y * w + (w - 1 - base_x);
 #pragma unroll
             for (int u = 0; u < NL; ++u) {
                 const int i = lane + 32 * u;
                 float v = 0.0f;
                 if (i < LH * LW) {
                     const int ly = i / LW, lx = i - ly * LW;
-                    v = load_cell(a + ly * w + lx);
-                    if (kFlip) v = __fmul_rn(__fadd_rn(v, load_cell(b + ly * w - lx)), 0.5f);
+                    const int row = ly * w;
+                    v = load_cell(a + (ao + row + lx));
+                    if (kFlip) v = __fmul_rn(__fadd_rn(v, load_cell(b + (bo + row - lx))), 0.5f);
                 }
                 vals[u] = v;
             }
@@ -276,8 +277,8 @@ fused_block_kernel(const T *__restrict__ hmp, size_t img_stride, int N, int h, i
                     const int ly = i / LW, lx = i - ly * LW;
                     const int gy = min(max(base_y + ly, 0), h - 1);
                     const int gx = min(max(base_x + lx, 0), w - 1);
-                    v = load_cell(a + gy * w + gx);
-                    if (kFlip) v = __fmul_rn(__fadd_rn(v, load_cell(b + gy * w + (w - 1 - gx))), 0.5f);
+                    v = load_cell(a + (gy * w + gx));
+                    if (kFlip) v = __fmul_rn(__fadd_rn(v, load_cell(b + (gy * w + (w - 1 - gx)))), 0.5f);
                 }
                 vals[u] = v;
             }
