@@ -146,6 +146,7 @@ struct og_handle {
     bool fused_enabled;
     bool zero_copy_enabled;      // host API: K2 gathers offsets straight from pinned host memory
     int host_chunks;             // host API: image ranges of the copy / decode pipeline
+    int host_tail;               // ... with a short last range (tuning aid: OG_HOST_TAIL=0 disables)
     int select_on_aux;           // 0: never, 1: fused path only, 2: always (tuning aid)
     int64_t fused_redos;
     int64_t zero_copy_calls;
@@ -597,6 +598,8 @@ int og_create(const og_config *cfg, og_handle **out) {
         const int v = atoi(env);
         if (v >= 1 && v <= kMaxChunks) h->host_chunks = v;
     }
+    h->host_tail = 1;
+    if (const char *env = getenv("OG_HOST_TAIL")) h->host_tail = atoi(env) != 0;
     h->select_on_aux = 1;
     if (const char *env = getenv("OG_SELECT_ON_AUX")) h->select_on_aux = atoi(env);
     h->fused_redos = 0;
@@ -1028,11 +1031,23 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
     OffsetSource src = {dense_f32(off_src, off_img), hgt, w, off_stride, flip_test ? 1 : 0, n,
                         h->limb_flip.ptr, h->limb_reserved.ptr};
     OG_TRY(begin_call(h, slot, true, n, H, W, s));
-    const int per = std::max((n + h->host_chunks - 1) / h->host_chunks, std::min(n, 4));
-    int chunk = 0;
-    for (int i0 = 0; i0 < n; i0 += per, ++chunk) {
-        const int cn = std::min(per, n - i0);
-        const bool last = i0 + cn >= n;
+    // Image ranges: only the kernels of the LAST range run after the last byte has arrived, so
+    // that range is kept small (n / 16, at least 4 images); the others share the rest evenly.
+    int bounds[kMaxChunks + 1];
+    int ranges = 0;
+    {
+        const int chunks = std::max(1, std::min(h->host_chunks, kMaxChunks));
+        int tail = 0;
+        if (chunks >= 2 && n >= 16 && h->host_tail) tail = std::max(4, n / 16);
+        const int body = n - tail, body_ranges = tail ? chunks - 1 : chunks;
+        const int per = std::max((body + body_ranges - 1) / body_ranges, std::min(body, 4));
+        bounds[0] = 0;
+        for (int at = 0; at < body; at += per) bounds[++ranges] = std::min(at + per, body);
+        if (tail) bounds[++ranges] = n;
+    }
+    for (int chunk = 0; chunk < ranges; ++chunk) {
+        const int i0 = bounds[chunk], cn = bounds[chunk + 1] - i0;
+        const bool last = chunk + 1 == ranges;
         OG_TRY(copy_range(i0, cn));
         OG_CUDA_TRY(cudaEventRecord(slot->copied[chunk], h->cp));
         OG_CUDA_TRY(cudaStreamWaitEvent(s, slot->copied[chunk], 0));
