@@ -35,6 +35,11 @@ _DTYPES = {torch.float32: _lib.OG_DTYPE_F32, torch.bfloat16: _lib.OG_DTYPE_BF16,
            torch.float16: _lib.OG_DTYPE_F16}
 
 
+def _view(pointer, ctype, count, dtype):
+    """numpy view of `count` elements behind a ctypes pointer (cheaper than np.ctypeslib.as_array)."""
+    return np.frombuffer((ctype * count).from_address(ctypes.addressof(pointer.contents)), dtype=dtype)
+
+
 def _image_strided(t):
     """(tensor, elements between images) for an NCHW tensor whose planes are dense and contiguous
     within an image (a channel slice of a packed head output qualifies); other layouts are
@@ -181,13 +186,14 @@ class DecoderEngine(object):
         if n == 0:
             return []
         c = self.n_keypoints
-        offs = np.ctypeslib.as_array(off_p, shape=(n,))
-        cnts = np.ctypeslib.as_array(cnt_p, shape=(n,))
         if total.value == 0:
             return [np.zeros((0, c, _lib.OG_POSE_COLS), dtype=np.float32) for _ in range(n)]
+        offs = _view(off_p, ctypes.c_int32, n, np.int32).tolist()
+        cnts = _view(cnt_p, ctypes.c_int32, n, np.int32).tolist()
         # one copy out of the handle's pinned buffer; the per-image arrays are views of it
-        rows = np.ctypeslib.as_array(poses_p, shape=(total.value, c, _lib.OG_POSE_COLS)).copy()
-        return [rows[o:o + k] for o, k in zip(offs.tolist(), cnts.tolist())]
+        rows = _view(poses_p, ctypes.c_float, total.value * c * _lib.OG_POSE_COLS, np.float32).copy()
+        rows = rows.reshape(total.value, c, _lib.OG_POSE_COLS)
+        return [rows[o:o + k] for o, k in zip(offs, cnts)]
 
     def decode_maps(self, heat, offs, scales=None, fetch=True, jomps=None, vector_nd=2,
                     use_jitter=False):
