@@ -258,10 +258,11 @@ def run_b200(args):
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        # NCCL prints its version banner on STDOUT at the VERSION level; stdout carries the one
-        # JSON line only.  An explicit INFO / TRACE setting of the caller is left alone.
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
+        # This image exports NCCL_DEBUG=VERSION, which makes NCCL print its version banner on
+        # STDOUT (also at WARN; probed) — stdout carries the one JSON line only.  Any other explicit
+        # setting of the caller (INFO, TRACE) is left alone.
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+            os.environ.pop('NCCL_DEBUG')
         dist.init_process_group('nccl', device_id=dev)
     n_gpus = world
 
