@@ -16,9 +16,13 @@
  *     CUDA stream passed as void* (cudaStream_t); no C++ exceptions cross the ABI;
  *   - every function returns an og_status (0 = OG_OK); og_last_error() gives the
  *     text of the last failure on the calling thread;
- *   - all maps are float32, NCHW, contiguous; "dev" pointers are device memory of
- *     the handle's GPU, "host" pointers are host memory (pinned memory makes the
- *     copies asynchronous);
+ *   - all maps are float32, NCHW, contiguous (og_decode_features_dev_ex also takes
+ *     bfloat16 / float16 maps and image-strided views); "dev" pointers are device
+ *     memory of the handle's GPU, "host" pointers are host memory (pinned memory makes
+ *     the copies asynchronous and lets the offset maps stay on the host);
+ *   - `stream` is the caller's stream: inputs are consumed in its order.  A handle owns
+ *     two more streams (grouping / result copy, host-input copies); og_fetch_poses is the
+ *     synchronisation point, and inputs must stay valid until it returns;
  *   - a handle is bound to one GPU and one configuration and is not thread-safe;
  *     distinct handles are independent (the image-sharding driver keeps one per GPU);
  *   - there is no CPU fallback: every entry point launches sm_100a kernels.
