@@ -669,6 +669,33 @@ def test_bf16_overflow_redo_and_odd_shapes(cuda_device):
             assert np.array_equal(a, b)
 
 
+def test_dev_ex_argument_errors(cuda_device):
+    """og_decode_features_dev_ex refuses what it cannot decode in place (loudly, no fallback):
+    reduced-precision maps without the fused path, image strides shorter than an image, unknown
+    element types; the Python mirror converts to dense float32 itself in the first case."""
+    import ctypes
+    from offsetguided_b200 import _lib
+    from offsetguided_b200.engine import _ptr, _stream_ptr
+    skel = cfg.COCO_PERSON_SKELETON
+    eng = DecoderEngine(17, skel, topk=8, thre_hmp=0.05, dist_max=40, use_scale=True, person_thre=0.05)
+    packed = torch.zeros((2, 55, 16, 24), dtype=torch.bfloat16, device='cuda')
+    hv, ov = packed[:, :17], packed[:, 17:]
+
+    def call(dtype, hs, os_, stride=4):
+        return eng.lib.og_decode_features_dev_ex(eng._h, _ptr(hv), _ptr(ov), dtype, hs, os_, 2, 16, 24, stride,
+                                                 stride, 1, 0, None, None, None, 0, _stream_ptr(eng.device))
+    per = 55 * 16 * 24
+    assert call(_lib.OG_DTYPE_BF16, per, per) == 0 and eng.fetch(2)[0].shape == (0, 17, 6)
+    assert call(7, per, per) != 0 and b'dtype' in eng.lib.og_last_error()
+    assert call(_lib.OG_DTYPE_BF16, 100, per) != 0 and b'hmp_image_stride' in eng.lib.og_last_error()
+    assert call(_lib.OG_DTYPE_BF16, per, per, stride=3) != 0          # stride 3: no fused kernel
+    eng.set_fused(False)
+    assert call(_lib.OG_DTYPE_BF16, per, per) != 0 and b'fused path' in eng.lib.og_last_error()
+    assert eng.pending == 0
+    out = eng.decode_features(hv, ov, 4, 4, 'bicubic', None)           # mirror: dense float32 copy
+    assert len(out) == 2 and out[0].shape == (0, 17, 6)
+
+
 def test_handles_with_different_table_sizes_coexist(cuda_device):
     """K3's dynamic shared memory attribute is per kernel, not per handle: a handle with a small
     person table created later must not shrink it for an earlier, larger one."""
