@@ -34,6 +34,13 @@ class GreedyGroup(object):
         self.n_keypoints = len(keypoints)
         self._engines = {}
 
+    def __getstate__(self):
+        # The reference hands bound methods of this class to a multiprocessing pool
+        # (demo_batch.py:284); handles of the CUDA library do not travel, a copy re-creates its own.
+        state = dict(self.__dict__)
+        state['_engines'] = {}
+        return state
+
     def _engine(self, topk, device=None):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())

@@ -160,3 +160,16 @@ def test_soft_nms_matches_reference_fixture():
         at += n
     assert changed > 20
     assert decoder.soft_nms([]) == []
+
+
+def test_greedy_group_pickles_without_its_handles():
+    """demo_batch.py:284 passes a bound method of GreedyGroup to a process pool: the object must
+    pickle; CUDA handles stay behind and are re-created by whoever uses the copy."""
+    import pickle
+    from offsetguided_b200 import decoder
+    g = decoder.GreedyGroup(0.06, dist_max=40, use_scale=True)
+    g._engines[(0, 32)] = object()                       # stands in for a live handle
+    method = pickle.loads(pickle.dumps(g.group_skeletons))
+    clone = method.__self__
+    assert clone._engines == {} and clone.dist_max == 40 and clone.use_scale is True
+    assert clone.skeleton == g.skeleton and len(g._engines) == 1
