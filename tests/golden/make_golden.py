@@ -157,7 +157,7 @@ def make_limbs_case(name, seed, n, persons, w, h, keypoints, skeleton, template,
 
 
 def make_poses_case(name, seed, n, persons, w, h, topk, thre_hmp, person_thre, dist_max,
-                    flip_test, noise_amp):
+                    flip_test, noise_amp, keep_inf=False):
     """Network-resolution maps from the reference encoder, decoded through the
     reference's PostProcess.generate_poses."""
     kp_flips = og_config.heatmap_hflip(COCO_KEYPOINTS)
@@ -176,7 +176,8 @@ def make_poses_case(name, seed, n, persons, w, h, topk, thre_hmp, person_thre, d
             os_f.append(ogen.create_offsetmaps(pf, {'joint_num': 17})[0])
     hmp = np.stack(hs + hs_f).astype(np.float32)
     omp = np.stack(os_ + os_f).astype(np.float32)
-    omp[~np.isfinite(omp)] = 0
+    if not keep_inf:        # keep_inf: the encoder's +inf background as utils/simulate.py:131 feeds it
+        omp[~np.isfinite(omp)] = 0
     noise_seed = seed + 777
     hmp_in = add_noise(hmp, noise_seed, noise_amp)
 
@@ -412,6 +413,8 @@ def main():
                     64, 0.06, 0.06, 40, 0.0, (4.0, 8.0))
     make_poses_case('poses_cfg1', 4000, 1, 5, 640, 640, 32, 0.06, 0.06, 40, False, 0.0)
     make_poses_case('poses_cfg2_flip', 5000, 2, 5, 640, 640, 32, 0.04, 0.04, 40, True, 0.0)
+    make_poses_case('poses_inf_background', 6000, 2, 5, 640, 640, 32, 0.06, 0.06, 40, False, 0.0, keep_inf=True)
+    make_poses_case('poses_inf_background_flip', 6100, 2, 5, 640, 640, 32, 0.06, 0.06, 40, True, 0.0, keep_inf=True)
     make_optional_heads()
     make_soft_nms()
 

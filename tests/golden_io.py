@@ -80,7 +80,19 @@ def split_poses(poses, counts):
     return out
 
 
-def compare_limbs(got, ref, thre_hmp, rtol=1e-5):
+def tolerances(name, rtol):
+    """(limb rtol, min_dist atol, pose rtol) of a poses fixture.  The 'poses_inf_*' fixtures keep the
+    encoder's +inf offset background (what utils/simulate.py feeds): on them ATen's bilinear resize
+    is itself reproducible only to 1 ulp of an offset value from one process to the next (probed:
+    the same reference calls on the same arrays give limbs that differ in 3 rows), and 1 ulp of a
+    ~64-pixel offset is 8e-6 pixels of min_dist.  Those fixtures are therefore compared at the
+    north-star tolerance (scores 1e-5 relative) instead of bit-for-bit."""
+    if name.startswith('poses_inf'):
+        return 1e-5, 1e-4, 1e-5
+    return rtol, 1e-6, rtol
+
+
+def compare_limbs(got, ref, thre_hmp, rtol=1e-5, dist_atol=1e-6):
     """Compare two (N, L, K, 13) limb tables on the rows that can influence
     grouping: rows whose from-candidate is above threshold.  Integer-valued
     columns (x, y, ids) must be equal; float columns agree within rtol.
@@ -96,7 +108,7 @@ def compare_limbs(got, ref, thre_hmp, rtol=1e-5):
     for col in (0, 1, 3, 4, 6, 7, 11, 12):
         assert np.array_equal(g[:, col], r[:, col]), f'limb column {col} differs'
     for col in (2, 5, 8, 9, 10):
-        np.testing.assert_allclose(g[:, col], r[:, col], rtol=rtol, atol=1e-6,
+        np.testing.assert_allclose(g[:, col], r[:, col], rtol=rtol, atol=dist_atol if col == 8 else 1e-6,
                                    err_msg=f'limb column {col}')
     return int(to_live.sum())
 
