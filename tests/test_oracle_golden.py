@@ -149,6 +149,6 @@ def test_optional_heads_match_reference(name):
     ref = gio.split_poses(d[name + '_poses'], d[name + '_counts'])
     assert len(poses) == len(ref) and sum(len(p) for p in ref) >= 6
     for p, r in zip(poses, ref):
-        gio.compare_poses(p, r, rtol=pr) if not inc_jit or not use_jit else None
+        gio.compare_poses(p, r, rtol=1e-6) if not inc_jit or not use_jit else None
         assert p.shape == r.shape and np.array_equal(p[..., 5], r[..., 5])
         np.testing.assert_allclose(p, r, rtol=1e-6, atol=1e-6)
