@@ -660,7 +660,7 @@ def test_bf16_overflow_redo_and_odd_shapes(cuda_device):
         packed = torch.from_numpy(rng.uniform(0, 1, size=shape).astype(np.float32))
         packed[:, 17:] = packed[:, 17:] * 16 - 8
         if not redo:
-            packed[:, :17] *= (rng.uniform(0, 1, size=(shape[0], 17) + shape[2:]) > 0.97)
+            packed[:, :17] *= torch.from_numpy(rng.uniform(0, 1, size=(shape[0], 17) + shape[2:]) > 0.97)
         packed = packed.cuda().to(torch.bfloat16)
         r0 = eng.fused_redo_count
         got = eng.decode_features(packed[:, :17], packed[:, 17:], 4, 4, 'bicubic', None)
