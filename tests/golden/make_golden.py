@@ -129,8 +129,8 @@ def make_limbs_case(name, seed, n, persons, w, h, keypoints, skeleton, template,
         om[~np.isfinite(om)] = 0
         hs.append(hm)
         os_.append(om)
-    heat_clean = np.stack(hs).astype(np.float32)
-    offs = np.stack(os_).astype(np.float32)
+    heat_clean = np.ascontiguousarray(np.stack(hs), dtype=np.float32)
+    offs = np.ascontiguousarray(np.stack(os_), dtype=np.float32)
     heat = add_noise(heat_clean, seed + 500, noise)
 
     collect = decoder.LimbsCollect(1, 1, topk=topk, thre_hmp=thre_hmp, min_len=0.5,
@@ -157,7 +157,7 @@ def make_limbs_case(name, seed, n, persons, w, h, keypoints, skeleton, template,
 
 
 def make_poses_case(name, seed, n, persons, w, h, topk, thre_hmp, person_thre, dist_max,
-                    flip_test, noise_amp, keep_inf=False):
+                    flip_test, noise_amp, keep_inf=False, resize_mode='bicubic'):
     """Network-resolution maps from the reference encoder, decoded through the
     reference's PostProcess.generate_poses."""
     kp_flips = og_config.heatmap_hflip(COCO_KEYPOINTS)
@@ -174,15 +174,18 @@ def make_poses_case(name, seed, n, persons, w, h, topk, thre_hmp, person_thre, d
             pf = scenes.mirror_persons(p, w, kp_flips)
             hs_f.append(hgen.create_heatmaps(pf, {'joint_num': 17}))
             os_f.append(ogen.create_offsetmaps(pf, {'joint_num': 17})[0])
-    hmp = np.stack(hs + hs_f).astype(np.float32)
-    omp = np.stack(os_ + os_f).astype(np.float32)
+    # C-contiguous NCHW, the layout a network emits: np.stack keeps the (H, W, C) memory order of
+    # the encoder's arrays, and ATen's bilinear resize has a separate channels-last kernel whose
+    # results differ from the contiguous one by 1 ulp (the saved .npz is C-ordered either way)
+    hmp = np.ascontiguousarray(np.stack(hs + hs_f), dtype=np.float32)
+    omp = np.ascontiguousarray(np.stack(os_ + os_f), dtype=np.float32)
     if not keep_inf:        # keep_inf: the encoder's +inf background as utils/simulate.py:131 feeds it
         omp[~np.isfinite(omp)] = 0
     noise_seed = seed + 777
     hmp_in = add_noise(hmp, noise_seed, noise_amp)
 
     args = reference_args(topk=topk, thre_hmp=thre_hmp, person_thre=person_thre,
-                          dist_max=dist_max, batch_size=n)
+                          dist_max=dist_max, batch_size=n, resize_mode=resize_mode)
     proc = decoder.decoder_factory(args)
     feats = [[[torch.from_numpy(hmp_in)], [[]], [[]]], [[torch.from_numpy(omp)], [[]], [[]]]]
     poses = proc.generate_poses(feats, flip_test=flip_test)
@@ -194,7 +197,7 @@ def make_poses_case(name, seed, n, persons, w, h, topk, thre_hmp, person_thre, d
     if flip_test:
         th, _, to, _, _ = proc.flip_augment(th, [], to, [], False, 2)
     fused_h, fused_o = th.numpy().copy(), to.numpy().copy()
-    th = torch.nn.functional.interpolate(th, scale_factor=4, mode='bicubic')
+    th = torch.nn.functional.interpolate(th, scale_factor=4, mode=resize_mode)
     to = torch.nn.functional.interpolate(to, scale_factor=4, mode='bilinear')
     nms = decoder.hmp_NMS(th)
     ties = tie_report(nms.numpy(), thre_hmp, topk)
@@ -207,6 +210,7 @@ def make_poses_case(name, seed, n, persons, w, h, topk, thre_hmp, person_thre, d
         os.path.join(HERE, name + '.npz'),
         hmp=hmp, omp=omp, noise_seed=noise_seed, noise_amp=noise_amp, flip_test=flip_test,
         topk=topk, thre_hmp=thre_hmp, person_thre=person_thre, dist_max=dist_max, min_len=0.5,
+        resize_mode=np.array(resize_mode),
         fused_h_sum=np.float64(fused_h.astype(np.float64).sum()),
         fused_o_sum=np.float64(fused_o.astype(np.float64).sum()),
         heat_hr_probe=th.numpy()[:, :, ::37, ::41].copy(),
@@ -341,8 +345,8 @@ def make_optional_heads():
         pf = scenes.mirror_persons(p, w, kp)
         hf.append(hgen.create_heatmaps(pf, {'joint_num': 17}))
         of.append(ogen.create_offsetmaps(pf, {'joint_num': 17})[0])
-    hmp = np.stack(hs + hf).astype(np.float32)
-    omp = np.stack(os_ + of).astype(np.float32)
+    hmp = np.ascontiguousarray(np.stack(hs + hf), dtype=np.float32)          # see make_poses_case
+    omp = np.ascontiguousarray(np.stack(os_ + of), dtype=np.float32)
     omp[~np.isfinite(omp)] = 0
     seed = 99
     rng = np.random.RandomState(seed)
@@ -413,6 +417,8 @@ def main():
                     64, 0.06, 0.06, 40, 0.0, (4.0, 8.0))
     make_poses_case('poses_cfg1', 4000, 1, 5, 640, 640, 32, 0.06, 0.06, 40, False, 0.0)
     make_poses_case('poses_cfg2_flip', 5000, 2, 5, 640, 640, 32, 0.04, 0.04, 40, True, 0.0)
+    make_poses_case('poses_bilinear_flip', 7000, 2, 6, 640, 640, 32, 0.05, 0.05, 40, True, 0.0,
+                    resize_mode='bilinear')
     make_poses_case('poses_inf_background', 6000, 2, 5, 640, 640, 32, 0.06, 0.06, 40, False, 0.0, keep_inf=True)
     make_poses_case('poses_inf_background_flip', 6100, 2, 5, 640, 640, 32, 0.06, 0.06, 40, True, 0.0, keep_inf=True)
     make_optional_heads()

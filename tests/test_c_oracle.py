@@ -38,7 +38,7 @@ def test_c_group_fuzz_bit_exact():
 
 
 @pytest.mark.parametrize('name', ['poses_cfg1', 'poses_cfg2_flip', 'poses_inf_background',
-                                  'poses_inf_background_flip'])
+                                  'poses_inf_background_flip', 'poses_bilinear_flip'])
 def test_c_generate_poses_matches_reference(name):
     d = gio.load_poses_case(name)
     fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, cfg.COCO_PERSON_SKELETON)
@@ -46,7 +46,7 @@ def test_c_generate_poses_matches_reference(name):
         d['hmp'], d['omp'], cfg.COCO_PERSON_SKELETON, 17, topk=d['topk'], thre_hmp=d['thre_hmp'],
         min_len=d['min_len'], person_thre=d['person_thre'], dist_max=d['dist_max'], use_scale=True,
         flip_test=d['flip_test'], kp_flips=cfg.heatmap_hflip(cfg.COCO_KEYPOINTS), limb_flips=fl,
-        limb_reserve=rs, return_limbs=True)
+        limb_reserve=rs, return_limbs=True, resize_mode=d['resize_mode'])
     lr, da, pr = gio.tolerances(name, 1e-6)
     assert gio.compare_limbs(limbs, d['limbs'], d['thre_hmp'], rtol=lr, dist_atol=da) > 50
     for p, r in zip(poses, gio.split_poses(d['poses'], d['pose_counts'])):
@@ -55,7 +55,7 @@ def test_c_generate_poses_matches_reference(name):
     live = d['det_scores'] >= np.float32(d['thre_hmp'])
     hm, om = (co.flip_augment(d['hmp'], d['omp'], cfg.heatmap_hflip(cfg.COCO_KEYPOINTS), fl, rs)
               if d['flip_test'] else (d['hmp'], d['omp']))
-    dets = co.joint_dets(co.resize(hm, 4, 'bicubic'), d['topk'])
+    dets = co.joint_dets(co.resize(hm, 4, d['resize_mode']), d['topk'])
     assert np.array_equal(dets[0][live], d['det_scores'][live])
     assert np.array_equal(dets[1][live], d['det_inds'][live])
 

@@ -330,12 +330,13 @@ def _args(**over):
                                        ('poses_cfg1', True), ('poses_cfg2_flip', True),
                                        ('poses_inf_background', False), ('poses_inf_background', True),
                                        ('poses_inf_background_flip', False),
-                                       ('poses_inf_background_flip', True)])
+                                       ('poses_inf_background_flip', True),
+                                       ('poses_bilinear_flip', False), ('poses_bilinear_flip', True)])
 def test_generate_poses_matches_reference(cuda_device, name, host):
     """BASELINE configs 1 and 2 through the reference-facing API, device and host inputs."""
     d = gio.load_poses_case(name)
     pp = decoder.decoder_factory(_args(topk=d['topk'], thre_hmp=d['thre_hmp'], person_thre=d['person_thre'],
-                                       dist_max=d['dist_max']))
+                                       dist_max=d['dist_max'], resize_mode=d['resize_mode']))
     hmp, omp = torch.from_numpy(d['hmp']), torch.from_numpy(d['omp'])
     if host:
         hmp, omp = hmp.pin_memory(), omp.pin_memory()

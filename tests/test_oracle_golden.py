@@ -49,7 +49,7 @@ def test_group_fuzz_bit_exact():
 
 
 @pytest.mark.parametrize('name', ['poses_cfg1', 'poses_cfg2_flip', 'poses_inf_background',
-                                  'poses_inf_background_flip'])
+                                  'poses_inf_background_flip', 'poses_bilinear_flip'])
 def test_generate_poses_matches_reference(name):
     d = gio.load_poses_case(name)
     fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, cfg.COCO_PERSON_SKELETON)
@@ -57,7 +57,7 @@ def test_generate_poses_matches_reference(name):
         d['hmp'], d['omp'], cfg.COCO_PERSON_SKELETON, 17, topk=d['topk'], thre_hmp=d['thre_hmp'],
         min_len=d['min_len'], person_thre=d['person_thre'], dist_max=d['dist_max'], use_scale=True,
         flip_test=d['flip_test'], kp_flips=cfg.heatmap_hflip(cfg.COCO_KEYPOINTS), limb_flips=fl,
-        limb_reserve=rs, return_limbs=True)
+        limb_reserve=rs, return_limbs=True, resize_mode=d['resize_mode'])
     lr, da, pr = gio.tolerances(name, 1e-6)
     assert gio.compare_limbs(limbs, d['limbs'], d['thre_hmp'], rtol=lr, dist_atol=da) > 50
     ref = gio.split_poses(d['poses'], d['pose_counts'])
