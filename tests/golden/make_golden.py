@@ -309,8 +309,12 @@ def make_resize():
     t2 = torch.from_numpy(x2)
     bic2 = torch.nn.functional.interpolate(t2, scale_factor=2, mode='bicubic').numpy()
     bil2 = torch.nn.functional.interpolate(t2, scale_factor=2, mode='bilinear').numpy()
+    x8 = rng.uniform(-1, 1, size=(1, 2, 11, 13)).astype(np.float32)
+    t8 = torch.from_numpy(x8)
+    bic8 = torch.nn.functional.interpolate(t8, scale_factor=8, mode='bicubic').numpy()
+    bil8 = torch.nn.functional.interpolate(t8, scale_factor=8, mode='bilinear').numpy()
     np.savez_compressed(os.path.join(HERE, 'resize_small.npz'), x=x, bicubic4=bic, bilinear4=bil,
-                        x2=x2, bicubic2=bic2, bilinear2=bil2)
+                        x2=x2, bicubic2=bic2, bilinear2=bil2, x8=x8, bicubic8=bic8, bilinear8=bil8)
     print('resize_small: written')
 
 

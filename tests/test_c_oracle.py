@@ -12,7 +12,8 @@ from offsetguided_b200 import config as cfg
 def test_c_resize_bit_exact_against_aten():
     d = gio.load('resize_small')
     for key, xk, scale, mode in (('bicubic4', 'x', 4, 'bicubic'), ('bilinear4', 'x', 4, 'bilinear'),
-                                 ('bicubic2', 'x2', 2, 'bicubic'), ('bilinear2', 'x2', 2, 'bilinear')):
+                                 ('bicubic2', 'x2', 2, 'bicubic'), ('bilinear2', 'x2', 2, 'bilinear'),
+                                 ('bicubic8', 'x8', 8, 'bicubic'), ('bilinear8', 'x8', 8, 'bilinear')):
         assert np.array_equal(co.resize(d[xk], scale, mode), d[key]), key
 
 

@@ -239,7 +239,8 @@ def test_resize_and_flip_bit_exact(cuda_device):
     lib = _lib.load()
     d = gio.load('resize_small')
     for key, xk, scale, mode in (('bicubic4', 'x', 4, 1), ('bilinear4', 'x', 4, 0),
-                                 ('bicubic2', 'x2', 2, 1), ('bilinear2', 'x2', 2, 0)):
+                                 ('bicubic2', 'x2', 2, 1), ('bilinear2', 'x2', 2, 0),
+                                 ('bicubic8', 'x8', 8, 1), ('bilinear8', 'x8', 8, 0)):
         x = torch.from_numpy(d[xk]).cuda()
         n, c, h, w = x.shape
         out = torch.empty((n, c, h * scale, w * scale), device='cuda')

@@ -72,6 +72,8 @@ def test_resize_bit_exact_against_aten():
     assert np.array_equal(ro.resize(d['x'], 4, 'bilinear'), d['bilinear4'])
     assert np.array_equal(ro.resize(d['x2'], 2, 'bicubic'), d['bicubic2'])
     assert np.array_equal(ro.resize(d['x2'], 2, 'bilinear'), d['bilinear2'])
+    assert np.array_equal(ro.resize(d['x8'], 8, 'bicubic'), d['bicubic8'])
+    assert np.array_equal(ro.resize(d['x8'], 8, 'bilinear'), d['bilinear8'])
 
 
 def test_resize_probes_of_pose_fixtures():
