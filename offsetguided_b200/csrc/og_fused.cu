@@ -334,8 +334,11 @@ fused_block_kernel(const T *__restrict__ hmp, size_t img_stride, int N, int h, i
         };
         const bool clamp_t = !kCubic && Y0 == 0;
 
-        float vp = 0.0f, vc, vn = 0.0f;       // rows r - 1, r, r + 1 of this lane's column
-        if (Y0 > 0) vp = ycombine(1, S - 1);  // last pixel row of the cell row above the block
+        // v[0] = pixel row above cell row q, v[1 .. S] = its S rows, v[S + 1] = the row below
+        float v[S + 2];
+        v[S] = 0.0f;
+        if (Y0 > 0) v[S] = ycombine(1, S - 1);        // last pixel row of the cell row above the block
+        v[S + 1] = 0.0f;
         const int valid_q = min(h - cy0, BH + 1);     // cell rows of the image below the block's top
 #pragma unroll 1
         for (int q = 0; q < BH && q < valid_q; ++q) {
@@ -343,47 +346,54 @@ fused_block_kernel(const T *__restrict__ hmp, size_t img_stride, int N, int h, i
             for (int k = 0; k < TAPS; ++k) win[k] = win[k + 1];
             win[TAPS] = xrow(q + TAPS);
             const bool top = clamp_t && q == 0;    // bilinear rows above src = 0: value = first cell row
-            if (q == 0) vc = top ? combine2(win[1], win[2], 1.0f, 0.0f) : ycombine(0, 0);
+            v[0] = v[S];
+            v[1] = q == 0 ? (top ? combine2(win[1], win[2], 1.0f, 0.0f) : ycombine(0, 0)) : v[S + 1];
+#pragma unroll
+            for (int p = 1; p < S; ++p) {
+                v[p + 1] = ycombine(p >= S / 2 ? 1 : 0, p);
+                if (top && p < S / 2) v[p + 1] = combine2(win[1], win[2], 1.0f, 0.0f);
+            }
+            // first pixel row of the next cell row; zero padding below the image
+            v[S + 1] = q + 1 < valid_q ? ycombine(1, 0) : 0.0f;
+            // Threshold and the two vertical neighbours first (this lane's own registers): only a
+            // row that holds a vertical maximum above thre — about one row per blob and column —
+            // pays for the shuffles, and a cell row without any costs one vote.  fmaxf drops a NaN
+            // neighbour like !(neighbour > v) does; thre > 0, so zero padding never passes.
+            unsigned mask = 0u;
+#pragma unroll
+            for (int p = 0; p < S; ++p)
+                if (v[p + 1] >= fmaxf(thre, fmaxf(v[p], v[p + 2]))) mask |= 1u << p;
+            if (!__any_sync(kFull, mask != 0u)) continue;
 #pragma unroll
             for (int p = 0; p < S; ++p) {
-                const int r = q * S + p;
-                if (p + 1 < S) {
-                    vn = ycombine(p + 1 >= S / 2 ? 1 : 0, p + 1);
-                    if (top && p + 1 < S / 2) vn = combine2(win[1], win[2], 1.0f, 0.0f);
-                } else {
-                    // first pixel row of the next cell row; zero padding below the image
-                    vn = q + 1 < valid_q ? ycombine(1, 0) : 0.0f;
-                }
-                const bool pass = vc >= thre;         // thre > 0: padding never passes
-                if (__any_sync(kFull, pass)) {
-                    const float lp = __shfl_up_sync(kFull, vp, 1), lc = __shfl_up_sync(kFull, vc, 1),
-                                ln = __shfl_up_sync(kFull, vn, 1);
-                    const float rp = __shfl_down_sync(kFull, vp, 1), rc = __shfl_down_sync(kFull, vc, 1),
-                                rn = __shfl_down_sync(kFull, vn, 1);
-                    if (pass) {
-                        const int Y = Y0 + r;
-                        bool peak = !(vp > vc) && !(vn > vc);
-                        if (lane > 0) peak = peak && !(lp > vc) && !(lc > vc) && !(ln > vc);
-                        if (lane < 31) peak = peak && !(rp > vc) && !(rc > vc) && !(rn > vc);
-                        // ring columns outside the block: evaluated only for a pixel that survived
-                        // everything else
-                        if (peak && ((lane == 0 && X0 > 0) || (lane == 31 && X + 1 < W))) {
-                            const int Xn = lane == 0 ? X - 1 : X + 1;
-                            for (int dy = -1; dy <= 1 && peak; ++dy) {
-                                if (Y + dy < 0 || Y + dy >= H) continue;
-                                peak = !(tile_value<S, kCubic, LW, HALO>(lo, cx0, cy0, Xn, Y + dy) > vc);
-                            }
-                        }
-                        if (peak) {
-                            const uint32_t pos = atomicAdd(&cand_count[plane], 1u);
-                            if (pos < (uint32_t)kCandCap)
-                                cand_keys[(size_t)plane * kCandCap + pos] =
-                                    make_key(vc + 0.0f, (uint32_t)(Y * W + X));
+                const bool pass = (mask >> p) & 1u;
+                if (!__any_sync(kFull, pass)) continue;
+                const float vp = v[p], vc = v[p + 1], vn = v[p + 2];
+                const float lp = __shfl_up_sync(kFull, vp, 1), lc = __shfl_up_sync(kFull, vc, 1),
+                            ln = __shfl_up_sync(kFull, vn, 1);
+                const float rp = __shfl_down_sync(kFull, vp, 1), rc = __shfl_down_sync(kFull, vc, 1),
+                            rn = __shfl_down_sync(kFull, vn, 1);
+                if (pass) {
+                    const int Y = Y0 + q * S + p;
+                    bool peak = true;
+                    if (lane > 0) peak = peak && !(lp > vc) && !(lc > vc) && !(ln > vc);
+                    if (lane < 31) peak = peak && !(rp > vc) && !(rc > vc) && !(rn > vc);
+                    // ring columns outside the block: evaluated only for a pixel that survived
+                    // everything else
+                    if (peak && ((lane == 0 && X0 > 0) || (lane == 31 && X + 1 < W))) {
+                        const int Xn = lane == 0 ? X - 1 : X + 1;
+                        for (int dy = -1; dy <= 1 && peak; ++dy) {
+                            if (Y + dy < 0 || Y + dy >= H) continue;
+                            peak = !(tile_value<S, kCubic, LW, HALO>(lo, cx0, cy0, Xn, Y + dy) > vc);
                         }
                     }
+                    if (peak) {
+                        const uint32_t pos = atomicAdd(&cand_count[plane], 1u);
+                        if (pos < (uint32_t)kCandCap)
+                            cand_keys[(size_t)plane * kCandCap + pos] =
+                                make_key(vc + 0.0f, (uint32_t)(Y * W + X));
+                    }
                 }
-                vp = vc;
-                vc = vn;
             }
         }
     }
