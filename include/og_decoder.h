@@ -218,11 +218,13 @@ int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off
                               const int32_t *kp_flip, const int32_t *limb_flip,
                               const int32_t *limb_reserve, int n_reserve, void *stream);
 
-/* Up to two og_decode_* calls may be in flight on a handle (results are queued in order),
- * so the launch of batch i + 1 can overlap the host-side consumption of batch i.
+/* Up to three og_decode_* calls may be in flight on a handle (results are queued in order),
+ * so the launches of the next batches overlap the kernels and the host-side consumption of
+ * batch i (two in flight hide the host round trip when K1 is long; a third also hides the
+ * launch calls themselves when the kernels take ~0.1 ms).
  * og_fetch_poses waits for the OLDEST unfetched call and exposes its result: *poses_host
  * points into pinned memory owned by the handle ([total, C, 6] float32), offsets / counts are
- * [n] int32; the pointers stay valid until the second next og_decode_* call.
+ * [n] int32; the pointers stay valid until the third next og_decode_* call.
  * og_pending returns the number of unfetched calls. */
 int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offset_host,
                    const int32_t **count_host, int32_t *total_rows);

@@ -70,7 +70,7 @@ struct PinnedBuf {
 
 }  // namespace
 
-constexpr int kSlots = 2;          // decode calls that may be in flight before a fetch
+constexpr int kSlots = 3;          // decode calls that may be in flight before a fetch
 constexpr int kMaxChunks = 8;      // image ranges of one host-API call (copy / decode pipeline)
 // start, after prep, K1 pass 1 (caller's stream) | select start, select = K2 start, K2, K3, D2H
 // (handle's stream)

@@ -198,7 +198,7 @@ class DecoderEngine(object):
     def decode_maps(self, heat, offs, scales=None, fetch=True, jomps=None, vector_nd=2,
                     use_jitter=False):
         """generate_limbs + group_skeletons on full-resolution maps (K1 -> K2 -> K3).
-        With ``fetch=False`` the call only launches (up to two calls may be in flight);
+        With ``fetch=False`` the call only launches (up to three calls may be in flight);
         ``fetch(n)`` later returns the oldest pending result."""
         heat = as_cuda_f32(heat, self.device)
         offs = as_cuda_f32(offs, self.device)

@@ -29,8 +29,10 @@ def main():
         t_launch, t_fetch = [], []
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        eng.decode_features(th, to, 4, 4, 'bicubic', tables, fetch=False)
-        for _ in range(steps - 1):
+        depth = int(os.environ.get('PIPE_DEPTH', '2'))           # decode calls in flight
+        for _ in range(depth - 1):
+            eng.decode_features(th, to, 4, 4, 'bicubic', tables, fetch=False)
+        for _ in range(steps - (depth - 1)):
             a = time.perf_counter()
             eng.decode_features(th, to, 4, 4, 'bicubic', tables, fetch=False)
             b = time.perf_counter()
@@ -38,10 +40,11 @@ def main():
             c = time.perf_counter()
             t_launch.append(b - a)
             t_fetch.append(c - b)
-        eng.fetch(64)
+        for _ in range(depth - 1):
+            eng.fetch(64)
         torch.cuda.synchronize()
         total = time.perf_counter() - t0
-        print(json.dumps({'stage_timing': timing, 'ms_per_step': 1e3 * total / steps,
+        print(json.dumps({'stage_timing': timing, 'depth': depth, 'ms_per_step': 1e3 * total / steps,
                           'launch_call_us': 1e6 * float(np.median(t_launch)),
                           'fetch_call_us': 1e6 * float(np.median(t_fetch)),
                           'images_per_s': 64 * steps / total}))

@@ -49,7 +49,7 @@ def main():
         k = order[rng.randint(len(order))]
         calls[k](False)
         pending.append(k)
-        if len(pending) == 2:                       # two calls in flight, mixed paths
+        if len(pending) == 3:                       # three calls in flight, mixed paths
             kk = pending.pop(0)
             if not same(eng.fetch(n), ref[kk]):
                 bad[kk] += 1

@@ -717,9 +717,9 @@ def test_handles_with_different_table_sizes_coexist(cuda_device):
         assert np.array_equal(a, b)
 
 
-def test_two_decodes_in_flight(cuda_device):
-    """The handle queues up to two decode calls; results come back oldest first and equal
-    the synchronous results; a third un-fetched call is refused."""
+def test_decodes_in_flight(cuda_device):
+    """The handle queues up to three decode calls; results come back oldest first and equal
+    the synchronous results; a fourth un-fetched call is refused."""
     from offsetguided_b200 import _lib
     skel = cfg.COCO_PERSON_SKELETON
     heat, offs = scenes.synth_hires_batch(321, 4, 4, 320, 256, skel)
@@ -728,19 +728,22 @@ def test_two_decodes_in_flight(cuda_device):
     eng.enable_stage_timing(True)
     ref_a = eng.decode_maps(th[:3], to[:3])
     ref_b = eng.decode_maps(th[3:], to[3:])
+    ref_c = eng.decode_maps(th[1:3], to[1:3])
     assert eng.pending == 0
     na = eng.decode_maps(th[:3], to[:3], fetch=False)
     nb = eng.decode_maps(th[3:], to[3:], fetch=False)
-    assert eng.pending == 2
+    nc = eng.decode_maps(th[1:3], to[1:3], fetch=False)
+    assert eng.pending == 3
     with pytest.raises(_lib.OgError):
         eng.decode_maps(th[:1], to[:1], fetch=False)
     got_a = eng.fetch(na)
     t_a = eng.last_stage_times_ms()
-    nc = eng.decode_maps(th[:0], to[:0], fetch=False)          # empty batch in the queue
+    ne = eng.decode_maps(th[:0], to[:0], fetch=False)          # empty batch in the queue
     got_b = eng.fetch(nb)
-    assert eng.fetch(nc) == [] and eng.pending == 0
-    assert len(got_a) == 3 and len(got_b) == 1
-    for g, r in zip(got_a + got_b, ref_a + ref_b):
+    got_c = eng.fetch(nc)
+    assert eng.fetch(ne) == [] and eng.pending == 0
+    assert len(got_a) == 3 and len(got_b) == 1 and len(got_c) == 2
+    for g, r in zip(got_a + got_b + got_c, ref_a + ref_b + ref_c):
         assert np.array_equal(g, r)
     assert t_a['k1_stream'] > 0 and t_a['k3'] > 0
     with pytest.raises(_lib.OgError):
