@@ -173,3 +173,37 @@ def test_greedy_group_pickles_without_its_handles():
     clone = method.__self__
     assert clone._engines == {} and clone.dist_max == 40 and clone.use_scale is True
     assert clone.skeleton == g.skeleton and len(g._engines) == 1
+
+
+def test_abi_argument_checks_need_no_gpu():
+    """Argument validation of the C ABI happens before any CUDA call: status codes, error text and
+    the NULL-handle conventions can be checked on a machine without a GPU."""
+    lib = _lib.load()
+    assert lib.og_status_string(1) == b'invalid argument' and lib.og_status_string(5) == b'unsupported configuration'
+    assert lib.og_status_string(99) == b'unknown status'
+    handle = ctypes.c_void_p()
+    assert lib.og_create(None, ctypes.byref(handle)) == 1 and b'null' in lib.og_last_error()
+    frm, to = _lib.int32_array([0, 1]), _lib.int32_array([1, 2])
+
+    def cfg_with(**over):
+        base = dict(n_keypoints=3, n_limbs=2, limb_from=ctypes.cast(frm, _lib.c_int32_p),
+                    limb_to=ctypes.cast(to, _lib.c_int32_p), topk=8, thre_hmp=0.05, min_len=0.5,
+                    resize_factor=1.0, dist_max=20.0, use_scale=1, person_thre=0.05, sort_dim=2,
+                    device=-1, max_images=0)
+        base.update(over)
+        return _lib.OgConfig(**base)
+    for bad, word in ((dict(n_keypoints=0), b'n_keypoints'), (dict(n_keypoints=65), b'n_keypoints'),
+                      (dict(n_limbs=0), b'n_limbs'), (dict(topk=0), b'topk'), (dict(topk=129), b'topk'),
+                      (dict(sort_dim=6), b'sort_dim'),
+                      (dict(limb_from=ctypes.cast(None, _lib.c_int32_p)), b'skeleton')):
+        c = cfg_with(**bad)
+        assert lib.og_create(ctypes.byref(c), ctypes.byref(handle)) == 1, bad
+        assert word in lib.og_last_error(), (bad, lib.og_last_error())
+        assert not handle.value
+    far = _lib.int32_array([0, 7])                       # limb endpoint outside the keypoint list
+    c = cfg_with(limb_to=ctypes.cast(far, _lib.c_int32_p))
+    assert lib.og_create(ctypes.byref(c), ctypes.byref(handle)) == 1 and b'keypoint' in lib.og_last_error()
+    assert lib.og_launch_count(None) == 0 and lib.og_pending(None) == 0
+    assert lib.og_fused_redo_count(None) == 0 and lib.og_zero_copy_count(None) == 0
+    assert lib.og_destroy(None) == 0
+    assert lib.og_set_fused(None, 1) == 1 and lib.og_set_zero_copy(None, 1) == 1
