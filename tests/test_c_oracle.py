@@ -80,3 +80,35 @@ def test_c_oracle_random_groups_equal_numpy_oracle():
         a = co.group_skeletons(limbs, skel, 17, 0.06, 2, 40, True)
         b = ro.group_skeletons(limbs, skel, 17, 0.06, 2, 40, True)
         assert a.shape == b.shape and np.array_equal(a, b), case
+
+
+def test_c_oracle_random_maps_equal_numpy_oracle():
+    """Random full decode (flip fusion, x2 / x4 resize in both modes, NMS / top-K with plateaus and
+    negative borders, limbs, grouping) through both oracles: the multi-threaded C restatement that
+    checks the large GPU cases must agree with the numpy restatement it was derived from."""
+    rng = np.random.RandomState(11)
+    skel = [(0, 1), (1, 2), (0, 2), (2, 3)]
+    kp_flips, limb_flips, limb_reserve = [0, 2, 1, 3], [2, 1, 0, 3], [1]
+    for case in range(6):
+        stride = int(rng.choice([2, 4]))
+        mode = str(rng.choice(['bicubic', 'bilinear']))
+        flip = bool(case % 2)
+        n, h, w = 2, int(rng.randint(20, 30)), int(rng.randint(40, 52))      # output H + W > 128
+        hmp = np.zeros((2 * n if flip else n, 4, h, w), np.float32)
+        for img in range(hmp.shape[0]):
+            for c in range(4):
+                for _ in range(5):
+                    y, x = rng.randint(0, h), rng.randint(0, w)
+                    hmp[img, c, y, x] = rng.uniform(0.2, 1.0)
+                hmp[img, c, 3, 5:7] = 0.5                                   # plateau
+        hmp[:, :, 0, :] -= rng.uniform(0, 0.3, size=(hmp.shape[0], 4, w)).astype(np.float32)
+        omp = rng.uniform(-12, 12, size=(hmp.shape[0], 8, h, w)).astype(np.float32)
+        kw = dict(topk=8, thre_hmp=0.1, min_len=0.5, person_thre=0.1, dist_max=30.0, use_scale=True,
+                  hmp_stride=stride, off_stride=stride, resize_mode=mode, flip_test=flip,
+                  kp_flips=kp_flips, limb_flips=limb_flips, limb_reserve=limb_reserve, return_limbs=True)
+        pa, la = co.generate_poses(hmp, omp, skel, 4, **kw)
+        pb, lb = ro.generate_poses(hmp, omp, skel, 4, **kw)
+        assert gio.compare_limbs(la, lb, 0.1, rtol=1e-6) >= 4, case
+        assert len(pa) == len(pb) and sum(len(p) for p in pb) >= 2
+        for a, b in zip(pa, pb):
+            gio.compare_poses(a, b, rtol=1e-6)
