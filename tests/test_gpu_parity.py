@@ -527,6 +527,44 @@ def co_resize_plane(hmp, kp, flip, stride, mode):
     return co.resize(np.ascontiguousarray(plane), stride, mode)[0, 0]
 
 
+def test_random_maps_small_skeleton_full_decode(cuda_device):
+    """Random full decodes with a 4-keypoint / 4-limb skeleton and its own flip tables (nothing
+    COCO-specific in the kernels): fused path against the numpy oracle, strides 2 / 4, both resize
+    modes, plateaus, negative border values."""
+    rng = np.random.RandomState(11)
+    skel = [(0, 1), (1, 2), (0, 2), (2, 3)]
+    kp_flips, limb_flips, limb_reserve = [0, 2, 1, 3], [2, 1, 0, 3], [1]
+    for case in range(6):
+        stride = int(rng.choice([2, 4]))
+        mode = str(rng.choice(['bicubic', 'bilinear']))
+        flip = bool(case % 2)
+        n, h, w = 2, int(rng.randint(20, 30)), int(rng.randint(40, 52))
+        hmp = np.zeros((2 * n if flip else n, 4, h, w), np.float32)
+        for img in range(hmp.shape[0]):
+            for c in range(4):
+                for _ in range(5):
+                    y, x = rng.randint(0, h), rng.randint(0, w)
+                    hmp[img, c, y, x] = rng.uniform(0.2, 1.0)
+                hmp[img, c, 3, 5:7] = 0.5
+        hmp[:, :, 0, :] -= rng.uniform(0, 0.3, size=(hmp.shape[0], 4, w)).astype(np.float32)
+        omp = rng.uniform(-12, 12, size=(hmp.shape[0], 8, h, w)).astype(np.float32)
+        eng = DecoderEngine(4, skel, topk=8, thre_hmp=0.1, min_len=0.5, dist_max=30.0, use_scale=True,
+                            person_thre=0.1)
+        tables = (kp_flips, limb_flips, limb_reserve) if flip else None
+        got = eng.decode_features(torch.from_numpy(hmp).cuda(), torch.from_numpy(omp).cuda(), stride, stride,
+                                  mode, tables)
+        assert eng.fused_redo_count == 0
+        _, _, lb = eng.last_intermediates(n)
+        ref, ref_limbs = ro.generate_poses(hmp, omp, skel, 4, topk=8, thre_hmp=0.1, min_len=0.5, person_thre=0.1,
+                                           dist_max=30.0, use_scale=True, hmp_stride=stride, off_stride=stride,
+                                           resize_mode=mode, flip_test=flip, kp_flips=kp_flips,
+                                           limb_flips=limb_flips, limb_reserve=limb_reserve, return_limbs=True)
+        assert gio.compare_limbs(lb.cpu().numpy(), ref_limbs, 0.1, rtol=RTOL) >= 4, case
+        assert sum(len(p) for p in ref) >= 2
+        _pose_lists_equal(got, ref)
+        eng.close()
+
+
 def test_fused_path_overflow_reruns_exactly(cuda_device):
     """Noise heat maps overflow the per-plane candidate lists; the batch is then re-run on the
     GPU through the materialising path and must equal it."""
