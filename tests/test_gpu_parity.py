@@ -565,6 +565,26 @@ def test_random_maps_small_skeleton_full_decode(cuda_device):
         eng.close()
 
 
+@pytest.mark.parametrize('thre', [0.0, -1.0])
+def test_non_positive_threshold_takes_the_exact_path(cuda_device, thre):
+    """thre_hmp <= 0 makes every NMS survivor (also the zero plateau) a candidate: the fused path is
+    not eligible, the materialising path selects with the exact radix selection, and the result
+    equals the oracle's top-K with its canonical tie order."""
+    skel = cfg.COCO_PERSON_SKELETON
+    hmp, omp = scenes.render_batch(77, 2, 3, 256, 192, skel)
+    eng = DecoderEngine(17, skel, topk=16, thre_hmp=thre, min_len=0.5, dist_max=40, use_scale=True,
+                        person_thre=0.05)
+    got = eng.decode_features(torch.from_numpy(hmp).cuda(), torch.from_numpy(omp).cuda(), 4, 4, 'bicubic', None)
+    ds, di, _ = [t.cpu().numpy() for t in eng.last_intermediates(2)]
+    ref = ro.generate_poses(hmp, omp, skel, 17, topk=16, thre_hmp=thre, min_len=0.5, person_thre=0.05,
+                            dist_max=40, use_scale=True)
+    heat = ro.resize(hmp, 4, 'bicubic')
+    rs, ri, _, _ = ro.topk_channel(ro.hmp_nms(heat), 16)
+    assert np.array_equal(di, ri) and np.array_equal(ds, rs)
+    assert sum(len(p) for p in ref) >= 4
+    _pose_lists_equal(got, ref)
+
+
 def test_fused_path_overflow_reruns_exactly(cuda_device):
     """Noise heat maps overflow the per-plane candidate lists; the batch is then re-run on the
     GPU through the materialising path and must equal it."""
