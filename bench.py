@@ -352,6 +352,36 @@ def run_b200(args):
     barrier()
     dev_ms = f0.elapsed_time(f1)
     dev_launches = eng.launch_count - dev_l0
+
+    # ---- the same decode with stock PyTorch operators on this GPU (eager ATen kernels for flip
+    #      fusion, resize, NMS, top-K and limbs, limbs to the host, multi-threaded CPU grouping):
+    #      what the reference's own formulation costs on the same silicon (oracle/torch_eager.py)
+    eager_block = None
+    if rank == 0 and world == 1 and not os.environ.get('OG_BENCH_SKIP_EAGER'):      # like cpu_baseline: N = 1 only
+        try:
+            from oracle import torch_eager
+            eager_kw = dict(topk=TOPK, thre_hmp=THRE_HMP, min_len=MIN_LEN, person_thre=PERSON_THRE,
+                            dist_max=DIST_MAX, use_scale=True, stride=4, resize_mode='bicubic', flip_test=flip,
+                            kp_flips=tables[0] if flip else None, limb_flips=tables[1] if flip else None,
+                            limb_reserve=tables[2] if flip else None)
+            with torch.no_grad():
+                eager_out = torch_eager.generate_poses(hmp_d, omp_d, skel, 17, **eager_kw)      # warm-up
+                torch.cuda.synchronize(dev)
+                eager_steps = max(2, args.steps // 5)
+                t0 = time.perf_counter()
+                for _ in range(eager_steps):
+                    eager_out = torch_eager.generate_poses(hmp_d, omp_d, skel, 17, **eager_kw)
+                torch.cuda.synchronize(dev)
+                eager_ms = (time.perf_counter() - t0) * 1e3 / eager_steps
+            eager_block = {'value': B / (eager_ms * 1e-3), 'unit': UNIT, 'ms_per_step': eager_ms,
+                           'steps': eager_steps, 'persons_per_step': sum(len(p) for p in eager_out),
+                           'note': 'stock PyTorch operators on the same GPU, device-resident network-resolution '
+                                   'maps (compare with features_dev), grouping on the host cores with the C '
+                                   'oracle; one GPU (rank 0), not part of the timed arms'}
+            del eager_out
+            torch.cuda.empty_cache()
+        except Exception as exc:                      # a baseline must never break the bench line
+            eager_block = {'unavailable': repr(exc)[:200]}
     del hmp_d, omp_d
     feats = [[[hmp_h], [[]], [[]]], [[omp_h], [[]], [[]]]]
     e2e_eng = post._engine(dev)
@@ -460,6 +490,7 @@ def run_b200(args):
                                      'hands over after model(images)): fused flip + x4 bicubic + NMS (K1f), '
                                      'offsets sampled at the candidates; 223 MB of heat maps read per step, '
                                      'no full-resolution map written; three batches in flight'},
+            'eager_torch_gpu': eager_block,
             'gpu_launches': hot_launches + e2e_launches_all + dev_launches,
             'gpu_launches_detail': {'hot_path': hot_launches, 'e2e': e2e_launches,
                                     'e2e_full_copy': e2e_launches_all - e2e_launches,

@@ -154,3 +154,22 @@ def test_optional_heads_match_reference(name):
         gio.compare_poses(p, r, rtol=1e-6) if not inc_jit or not use_jit else None
         assert p.shape == r.shape and np.array_equal(p[..., 5], r[..., 5])
         np.testing.assert_allclose(p, r, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['poses_cfg1', 'poses_cfg2_flip', 'poses_bilinear_flip'])
+def test_torch_eager_baseline_matches_reference_fixtures(name):
+    """oracle/torch_eager.py (bench.py's eager-PyTorch baseline, an independent formulation of the
+    path with stock ATen operators) decodes the reference fixtures to the reference's poses."""
+    import torch
+    from oracle import torch_eager as te
+    d = gio.load_poses_case(name)
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, cfg.COCO_PERSON_SKELETON)
+    got = te.generate_poses(torch.from_numpy(d['hmp']), torch.from_numpy(d['omp']), cfg.COCO_PERSON_SKELETON, 17,
+                            topk=d['topk'], thre_hmp=d['thre_hmp'], min_len=d['min_len'],
+                            person_thre=d['person_thre'], dist_max=d['dist_max'], use_scale=True, stride=4,
+                            resize_mode=d['resize_mode'], flip_test=d['flip_test'],
+                            kp_flips=cfg.heatmap_hflip(cfg.COCO_KEYPOINTS), limb_flips=fl, limb_reserve=rs)
+    ref = gio.split_poses(d['poses'], d['pose_counts'])
+    assert len(got) == len(ref)
+    for p, r in zip(got, ref):
+        gio.compare_poses(p, r, rtol=1e-6)
