@@ -407,8 +407,122 @@ def make_soft_nms():
         len(inputs), int(sum((a[..., 2] != b[..., 2]).sum() for a, b in zip(inputs, outputs)))))
 
 
+def make_scored_offset():
+    """decoder.scored_offset (offset.py:8-43) itself, k = 3 and 7, n = 2 and 3 (the reference's
+    squeeze() needs n >= 2), on random maps: pins oracle.ref_oracle.scored_offset and the CUDA
+    kernel to the reference's avg_pool2d(divisor_override=1) arithmetic."""
+    from oracle import ref_oracle
+    rng = np.random.RandomState(31)
+    jf, jt = decoder.offset.pack_jtypes(COCO_PERSON_SKELETON)
+    out = {}
+    for tag, (n, h, w) in {'a': (2, 20, 24), 'b': (3, 17, 33)}.items():
+        hm = rng.uniform(0, 1, size=(n, 17, h, w)).astype(np.float32)
+        hm[:, :, :3, :5] = 0                               # zero-weight windows: 0 / 1e-6
+        om = rng.uniform(-9, 9, size=(n, 38, h, w)).astype(np.float32)
+        out['hmp_' + tag], out['off_' + tag] = hm, om
+        for ks in (3, 7):
+            ref = decoder.scored_offset(torch.from_numpy(hm), torch.from_numpy(om), jf, jt, ks).numpy()
+            mine = ref_oracle.scored_offset(hm, om, jf, jt, ks)
+            np.testing.assert_allclose(mine, ref, rtol=1e-6, atol=1e-6)
+            print(f'scored_offset {tag} k={ks}: oracle == reference, max |diff| = '
+                  f'{np.abs(mine - ref).max():.3g}, bit-equal = {np.array_equal(mine, ref)}')
+            out[f'out_{tag}_k{ks}'] = ref
+    np.savez_compressed(os.path.join(HERE, 'scored_offset.npz'), **out)
+
+
+def make_poses_scored_off():
+    """generate_poses(..., flip_test=True, scored_off=True) through the reference on the inputs of
+    poses_cfg2_flip (stored there; only the poses are stored here)."""
+    from oracle import ref_oracle
+    d = np.load(os.path.join(HERE, 'poses_cfg2_flip.npz'))
+    hmp, omp = d['hmp'], d['omp']
+    n = hmp.shape[0] // 2
+    args = reference_args(topk=32, thre_hmp=0.04, person_thre=0.04, dist_max=40, batch_size=n)
+    proc = decoder.decoder_factory(args)
+    feats = [[[torch.from_numpy(hmp)], [[]], [[]]], [[torch.from_numpy(omp)], [[]], [[]]]]
+    poses = proc.generate_poses(feats, flip_test=True, scored_off=True)
+    proc.worker_pool.close()
+    proc.worker_pool.join()
+    kp = og_config.heatmap_hflip(COCO_KEYPOINTS)
+    fl, rs = og_config.offset_hflip(COCO_KEYPOINTS, COCO_PERSON_SKELETON)
+    fh, fo = ref_oracle.flip_augment(hmp, omp, kp, fl, rs)
+    jf, jt = ref_oracle.pack_jtypes(COCO_PERSON_SKELETON)
+    fo = ref_oracle.scored_offset(fh, fo, jf, jt, 3)
+    mine = ref_oracle.generate_poses(fh, fo, COCO_PERSON_SKELETON, 17, topk=32, thre_hmp=0.04, min_len=0.5,
+                                     person_thre=0.04, dist_max=40, use_scale=True)
+    for a, b in zip(poses, mine):
+        assert a.shape == b.shape and np.array_equal(a[..., 5], b[..., 5])
+        np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
+    print(f'poses_scored_off: persons/img={[len(p) for p in poses]} oracle == reference (1e-5)')
+    np.savez_compressed(os.path.join(HERE, 'poses_scored_off.npz'),
+                        pose_counts=np.asarray([len(p) for p in poses]), poses=np.concatenate(poses, 0))
+
+
+def make_tied_peaks(max_seeds=400):
+    """A TIE-AWARE fixture: bicubic x4 upsampling creates 2-pixel plateaus, so equal
+    above-threshold peak values within a channel are a normal input, and torch.topk orders equal
+    values in a library-defined way.  Seeds are searched for scenes whose upsampled heat maps hold
+    such ties; the reference's generate_poses output is stored together with its dets as the
+    reference ordered them (NOT canonicalised) and the tied groups.  Tests compare dets as sets
+    within tied groups and the final poses exactly when the reference's result does not depend on
+    the order (checked here by decoding both orders through the reference's own classes)."""
+    from oracle import ref_oracle
+    topk, thre, pthre, dmax = 32, 0.04, 0.04, 40
+    w = h = 640
+    hgen = HeatMapGenerator([w, h], 4, 3, 7, 0.01)
+    ogen = OffsetMapGenerator([w, h], 4, 7, 1.0, COCO_PERSON_SKELETON)
+    found = []
+    for seed in range(8000, 8000 + max_seeds):
+        rng = np.random.RandomState(seed)
+        p = scenes.make_persons(rng, 6, w, h)
+        hm = np.ascontiguousarray(hgen.create_heatmaps(p, {'joint_num': 17})[None], dtype=np.float32)
+        th = torch.nn.functional.interpolate(torch.from_numpy(hm), scale_factor=4, mode='bicubic')
+        nms = decoder.hmp_NMS(th).numpy()
+        if tie_report(nms, thre, topk) > 0:
+            om = np.ascontiguousarray(ogen.create_offsetmaps(p, {'joint_num': 17})[0][None], dtype=np.float32)
+            om[~np.isfinite(om)] = 0
+            found.append((seed, hm, om))
+            print('tied_peaks: seed', seed, 'has', tie_report(nms, thre, topk), 'tied pair(s)')
+        if len(found) == 2:
+            break
+    assert len(found) == 2, 'no tied scenes found'
+    hmp = np.concatenate([f[1] for f in found])
+    omp = np.concatenate([f[2] for f in found])
+    n = len(found)
+    args = reference_args(topk=topk, thre_hmp=thre, person_thre=pthre, dist_max=dmax, batch_size=n)
+    proc = decoder.decoder_factory(args)
+    feats = [[[torch.from_numpy(hmp)], [[]], [[]]], [[torch.from_numpy(omp)], [[]], [[]]]]
+    poses = proc.generate_poses(feats, flip_test=False)
+    proc.worker_pool.close()
+    proc.worker_pool.join()
+    th = torch.nn.functional.interpolate(torch.from_numpy(hmp), scale_factor=4, mode='bicubic')
+    nms = decoder.hmp_NMS(th)
+    d_s, d_i, _, _ = decoder.topK_channel(nms, K=topk)
+    d_s, d_i = d_s.numpy(), d_i.numpy()
+    c_s, c_i = canonical_dets(d_s, d_i)
+    live = d_s >= np.float32(thre)
+    differs = int((d_i[live] != c_i[live]).sum())
+    ties = tie_report(nms.numpy(), thre, topk)
+    # the canonical (value desc, index asc) order through the oracle: are the poses order-independent?
+    mine = ref_oracle.generate_poses(hmp, omp, COCO_PERSON_SKELETON, 17, topk=topk, thre_hmp=thre, min_len=0.5,
+                                     person_thre=pthre, dist_max=dmax, use_scale=True)
+    same = all(a.shape == b.shape and np.array_equal(a[..., [0, 1, 5]], b[..., [0, 1, 5]]) and
+               np.allclose(a, b, rtol=1e-5, atol=1e-7) for a, b in zip(poses, mine))
+    print(f'tied_peaks: {ties} tied pairs, reference top-K order differs from canonical in {differs} live slots, '
+          f'poses identical under the canonical order: {same}, persons/img={[len(p) for p in poses]}')
+    np.savez_compressed(os.path.join(HERE, 'poses_tied_peaks.npz'), hmp=hmp, omp=omp,
+                        seeds=np.asarray([f[0] for f in found]), topk=topk, thre_hmp=thre, person_thre=pthre,
+                        dist_max=dmax, ties=ties, ref_order_differs=differs, poses_order_independent=same,
+                        det_scores=d_s, det_inds=d_i.astype(np.int32),
+                        pose_counts=np.asarray([len(p) for p in poses]), poses=np.concatenate(poses, 0))
+
+
 def main():
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:                 # regenerate selected fixtures only: make_golden.py make_tied_peaks ...
+        for name in sys.argv[1:]:
+            globals()[name]()
+        return
     encoder_check()
     make_resize()
     make_group_fuzz()
@@ -427,6 +541,9 @@ def main():
     make_poses_case('poses_inf_background_flip', 6100, 2, 5, 640, 640, 32, 0.06, 0.06, 40, True, 0.0, keep_inf=True)
     make_optional_heads()
     make_soft_nms()
+    make_scored_offset()
+    make_poses_scored_off()
+    make_tied_peaks()
 
 
 if __name__ == '__main__':

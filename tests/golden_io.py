@@ -123,3 +123,24 @@ def compare_poses(got, ref, rtol=1e-5, exact=False):
         assert np.array_equal(got[..., col], ref[..., col]), f'pose column {col} differs'
     for col in (2, 3, 4):
         np.testing.assert_allclose(got[..., col], ref[..., col], rtol=rtol, atol=1e-7)
+
+
+def compare_dets_tie_aware(got_s, got_i, ref_s, ref_i, thre):
+    """Top-K tables (N, C, K) against the reference's own torch.topk output, TIE-AWARE: within a
+    plane the live (score >= thre) scores must be equal slot by slot (both are sorted descending),
+    and for every distinct score the SET of indices must be equal — the order of equal values is
+    library-defined in torch.topk.  Returns the number of tied groups seen."""
+    assert got_s.shape == ref_s.shape and got_i.shape == ref_i.shape
+    groups = 0
+    n, c, _ = ref_s.shape
+    for i in range(n):
+        for j in range(c):
+            live = ref_s[i, j] >= np.float32(thre)
+            assert np.array_equal(got_s[i, j] >= np.float32(thre), live)
+            assert np.array_equal(got_s[i, j][live], ref_s[i, j][live]), 'live scores differ'
+            for v in np.unique(ref_s[i, j][live]):
+                a = np.sort(got_i[i, j][live & (got_s[i, j] == v)])
+                b = np.sort(ref_i[i, j][live & (ref_s[i, j] == v)])
+                assert np.array_equal(a, b), 'index sets of a tied group differ'
+                groups += int(len(b) > 1)
+    return groups

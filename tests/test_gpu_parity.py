@@ -292,15 +292,18 @@ def test_flip_augment_method_matches_reference_semantics(cuda_device):
     assert th.shape[0] == 2 * n and np.array_equal(th.cpu().numpy(), hm)          # inputs untouched
 
 
-def test_scored_offset_matches_oracle(cuda_device):
-    rng = np.random.RandomState(4)
-    hm = rng.uniform(0, 1, size=(2, 17, 20, 24)).astype(np.float32)
-    om = rng.uniform(-9, 9, size=(2, 38, 20, 24)).astype(np.float32)
+def test_scored_offset_matches_reference(cuda_device):
+    """decoder.scored_offset against the reference's own output (tests/golden/scored_offset.npz,
+    decoder/offset.py:8-43), k = 3 (the call site) and 7 (the default); 1e-5 relative."""
+    d = gio.load('scored_offset')
     jf, jt = ro.pack_jtypes(cfg.COCO_PERSON_SKELETON)
-    for ks in (3, 7):
-        got = decoder.scored_offset(torch.from_numpy(hm).cuda(), torch.from_numpy(om).cuda(), jf, jt, ks)
-        ref = ro.scored_offset(hm, om, jf, jt, ks)
-        np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=RTOL, atol=1e-6)
+    for tag in ('a', 'b'):
+        hm, om = torch.from_numpy(d['hmp_' + tag]).cuda(), torch.from_numpy(d['off_' + tag]).cuda()
+        for ks in (3, 7):
+            got = decoder.scored_offset(hm, om, jf, jt, ks).cpu().numpy()
+            ref = d['out_%s_k%d' % (tag, ks)]
+            np.testing.assert_allclose(got, ref, rtol=RTOL, atol=1e-6)
+            assert np.array_equal(got, ro.scored_offset(d['hmp_' + tag], d['off_' + tag], jf, jt, ks))
 
 
 # --------------------------------------------------------------------------- whole path
@@ -365,18 +368,12 @@ def test_generate_poses_scored_off_and_last_partial_batch(cuda_device):
     hmp, omp = torch.from_numpy(d['hmp']).cuda(), torch.from_numpy(d['omp']).cuda()
     feats = [[[hmp], [[]], [[]]], [[omp], [[]], [[]]]]
     got = pp.generate_poses(feats, flip_test=True, scored_off=True)
-    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
-    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, cfg.COCO_PERSON_SKELETON)
-    fh, fo = ro.flip_augment(d['hmp'], d['omp'], kp, fl, rs)
-    jf, jt = ro.pack_jtypes(cfg.COCO_PERSON_SKELETON)
-    fo = ro.scored_offset(fh, fo, jf, jt, 3)
-    ref = ro.generate_poses(fh, fo, cfg.COCO_PERSON_SKELETON, 17, topk=32, thre_hmp=0.04, min_len=0.5,
-                            person_thre=0.04, dist_max=40, use_scale=True)
+    # the reference's own generate_poses(flip_test=True, scored_off=True) on these inputs
+    s = gio.load('poses_scored_off')
+    ref = gio.split_poses(s['poses'], s['pose_counts'])
     assert len(got) == len(ref) == 2
     for p, r in zip(got, ref):
-        assert p.shape == r.shape
-        assert np.array_equal(p[..., 5], r[..., 5])
-        np.testing.assert_allclose(p, r, rtol=1e-4, atol=1e-3)
+        gio.compare_poses(p, r, rtol=RTOL)
     # a smaller last batch through the same PostProcess
     feats1 = [[[hmp[[0, 2]]], [[]], [[]]], [[omp[[0, 2]]], [[]], [[]]]]
     one = pp.generate_poses(feats1, flip_test=True)
@@ -951,3 +948,24 @@ def test_optional_heads_match_reference(cuda_device, name):
         np.testing.assert_allclose(p, r, rtol=RTOL, atol=1e-5)
         if not (inc_jit and use_jit):
             assert np.array_equal(p[..., :2], r[..., :2])
+
+
+def test_tied_peaks_tie_aware_against_reference(cuda_device):
+    """Bicubic x4 plateaus: equal-valued above-threshold peaks within a channel.  Dets are
+    compared with the reference's own torch.topk output as sets within tied groups; final poses must
+    equal the reference's (the generator verified they do not depend on the order of the tie)."""
+    d = gio.load('poses_tied_peaks')
+    thre = float(d['thre_hmp'])
+    pp = decoder.decoder_factory(_args(topk=int(d['topk']), thre_hmp=thre, person_thre=float(d['person_thre']),
+                                       dist_max=float(d['dist_max'])))
+    for host in (False, True):
+        hmp, omp = torch.from_numpy(d['hmp']), torch.from_numpy(d['omp'])
+        hmp, omp = (hmp.pin_memory(), omp.pin_memory()) if host else (hmp.cuda(), omp.cuda())
+        poses = pp.generate_poses([[[hmp], [[]], [[]]], [[omp], [[]], [[]]]])
+        ref = gio.split_poses(d['poses'], d['pose_counts'])
+        assert len(poses) == len(ref)
+        for p, r in zip(poses, ref):
+            gio.compare_poses(p, r, rtol=RTOL)
+        ds, di, _ = pp._engine(torch.device('cuda', 0)).last_intermediates(len(ref))
+        groups = gio.compare_dets_tie_aware(ds.cpu().numpy(), di.cpu().numpy(), d['det_scores'], d['det_inds'], thre)
+        assert groups >= int(d['ties'])

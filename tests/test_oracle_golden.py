@@ -173,3 +173,48 @@ def test_torch_eager_baseline_matches_reference_fixtures(name):
     assert len(got) == len(ref)
     for p, r in zip(got, ref):
         gio.compare_poses(p, r, rtol=1e-6)
+
+
+def test_scored_offset_matches_reference_fixture():
+    """oracle scored_offset == the reference's decoder.scored_offset output, bit for bit
+    (decoder/offset.py:8-43; k = 3 is the call site's window, 7 the default)."""
+    d = gio.load('scored_offset')
+    jf, jt = ro.pack_jtypes(cfg.COCO_PERSON_SKELETON)
+    for tag in ('a', 'b'):
+        for ks in (3, 7):
+            got = ro.scored_offset(d['hmp_' + tag], d['off_' + tag], jf, jt, ks)
+            assert np.array_equal(got, d['out_%s_k%d' % (tag, ks)])
+
+
+def test_generate_poses_scored_off_matches_reference():
+    """generate_poses(flip_test=True, scored_off=True) of the reference on the config-2 inputs."""
+    d = gio.load_poses_case('poses_cfg2_flip')
+    s = gio.load('poses_scored_off')
+    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, cfg.COCO_PERSON_SKELETON)
+    fh, fo = ro.flip_augment(d['hmp'], d['omp'], kp, fl, rs)
+    jf, jt = ro.pack_jtypes(cfg.COCO_PERSON_SKELETON)
+    fo = ro.scored_offset(fh, fo, jf, jt, 3)
+    got = ro.generate_poses(fh, fo, cfg.COCO_PERSON_SKELETON, 17, topk=32, thre_hmp=0.04, min_len=0.5,
+                            person_thre=0.04, dist_max=40, use_scale=True)
+    ref = gio.split_poses(s['poses'], s['pose_counts'])
+    assert len(got) == len(ref) == 2
+    for p, r in zip(got, ref):
+        gio.compare_poses(p, r, rtol=1e-5)
+
+
+def test_tied_peaks_fixture_tie_aware():
+    """Scenes whose bicubic x4 heat maps hold equal-valued above-threshold peaks (2-pixel plateaus,
+    SURVEY 8c): dets compared with the reference's torch.topk output as sets within tied groups,
+    final poses exactly (the generator checked that they do not depend on the order)."""
+    d = gio.load('poses_tied_peaks')
+    assert int(d['ties']) >= 2 and bool(d['poses_order_independent'])
+    thre = float(d['thre_hmp'])
+    k, pt, dm = int(d['topk']), float(d['person_thre']), float(d['dist_max'])
+    hr = ro.resize(d['hmp'], 4, 'bicubic')
+    limbs, dets = ro.generate_limbs(hr, ro.resize(d['omp'], 4, 'bilinear'), cfg.COCO_PERSON_SKELETON, k, thre,
+                                    0.5, 4, 4, return_dets=True)
+    poses = [ro.group_skeletons(l, cfg.COCO_PERSON_SKELETON, 17, pt, 2, dm, True) for l in limbs]
+    assert gio.compare_dets_tie_aware(dets[0], dets[1], d['det_scores'], d['det_inds'], thre) >= 2
+    for p, r in zip(poses, gio.split_poses(d['poses'], d['pose_counts'])):
+        gio.compare_poses(p, r, rtol=1e-5)
