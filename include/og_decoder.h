@@ -20,9 +20,11 @@
  *     bfloat16 / float16 maps and image-strided views); "dev" pointers are device
  *     memory of the handle's GPU, "host" pointers are host memory (pinned memory makes
  *     the copies asynchronous and lets the offset maps stay on the host);
- *   - `stream` is the caller's stream: inputs are consumed in its order.  A handle owns
- *     two more streams (grouping / result copy, host-input copies); og_fetch_poses is the
- *     synchronisation point, and inputs must stay valid until it returns;
+ *   - `stream` is the caller's stream: inputs are consumed in its order.  A handle owns one
+ *     stream per result slot (the decode chain of a call) and one for host-input copies;
+ *     og_fetch_result / og_fetch_poses is the synchronisation point, and inputs must stay
+ *     valid until it returns.  Calls on one handle may come from different caller streams:
+ *     every call has its own scratch and result slot;
  *   - a handle is bound to one GPU and one configuration and is not thread-safe;
  *     distinct handles are independent (the image-sharding driver keeps one per GPU);
  *   - there is no CPU fallback: every entry point launches sm_100a kernels.
@@ -39,7 +41,8 @@
 extern "C" {
 #endif
 
-#define OG_ABI_VERSION 1
+#define OG_ABI_VERSION 2
+#define OG_MAX_IN_FLIGHT 8   /* decode calls a handle keeps in flight (result slots) */
 #define OG_LIMB_COLS 13      /* decoder/collect.py:220-222 */
 #define OG_POSE_COLS 6       /* decoder/group.py:48  [x, y, v, s, limb_score, ind] */
 #define OG_MAX_KEYPOINTS 64
@@ -171,11 +174,11 @@ int og_resize_f32(const float *in_dev, float *out_dev, int planes, int hgt, int 
 /* ---- whole path ----------------------------------------------------------- */
 
 /* generate_limbs + group_skeletons on full-resolution device maps: K1 on `stream`
- * (after whatever produced the maps there), then K2 -> K3 -> an asynchronous copy of the
- * packed poses into pinned memory of the handle on a high-priority stream OWNED BY THE
- * HANDLE, ordered after K1 by an event.  K2 / K3 are latency-bound and fill a fraction of
- * the SMs, so the next call's K1 (HBM-bound) runs beside them instead of behind them.
- * Returns immediately; og_fetch_poses() synchronises.  Every input buffer of an og_decode_*
+ * (after whatever produced the maps there), then K2 -> K3 on a high-priority stream OWNED BY
+ * THE HANDLE (one per result slot), ordered after K1 by an event; K3 writes the packed poses
+ * straight into pinned host memory of the handle.  K2 / K3 are latency-bound and fill a
+ * fraction of the SMs, so the next call's K1 (HBM-bound) runs beside them instead of behind them.
+ * Returns immediately; og_fetch_result() synchronises.  Every input buffer of an og_decode_*
  * call must stay valid and unmodified until its og_fetch_poses returns (K2 reads the offset
  * maps after the call has returned, not in `stream` order). */
 int og_decode_maps(og_handle *h, const float *heat_dev, const float *offs_dev,
@@ -196,7 +199,12 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
                             const int32_t *kp_flip, const int32_t *limb_flip,
                             const int32_t *limb_reserve, int n_reserve, void *stream);
 
-/* Same on device-resident network-resolution maps (what evaluate.py:215 hands over). */
+/* Same on device-resident network-resolution maps (what evaluate.py:215 hands over).
+ * `stream` is only waited on: the whole chain (fused flip + resize + NMS, selection, limb
+ * scoring, grouping) runs on the result slot's own stream, as ONE CUDA graph captured per slot
+ * and replayed while the input pointers, shapes, flags and flip tables stay the same (the
+ * usual case: a network writes its outputs to the same buffers every iteration); anything
+ * else re-captures.  og_set_graph(h, 0) launches the kernels one by one instead. */
 int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_dev,
                            int n, int hgt, int w, int hmp_stride, int off_stride,
                            int resize_mode, int flip_test,
@@ -218,14 +226,28 @@ int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off
                               const int32_t *kp_flip, const int32_t *limb_flip,
                               const int32_t *limb_reserve, int n_reserve, void *stream);
 
-/* Up to three og_decode_* calls may be in flight on a handle (results are queued in order),
- * so the launches of the next batches overlap the kernels and the host-side consumption of
- * batch i (two in flight hide the host round trip when K1 is long; a third also hides the
- * launch calls themselves when the kernels take ~0.1 ms).
- * og_fetch_poses waits for the OLDEST unfetched call and exposes its result: *poses_host
- * points into pinned memory owned by the handle ([total, C, 6] float32), offsets / counts are
- * [n] int32; the pointers stay valid until the third next og_decode_* call.
- * og_pending returns the number of unfetched calls. */
+/* Up to OG_MAX_IN_FLIGHT og_decode_* calls may be in flight on a handle (results are queued in
+ * order): every call owns a result slot with its own stream, scratch and pinned result buffer,
+ * so the kernels of consecutive calls overlap each other and the host-side consumption of
+ * batch i (two in flight hide the host round trip when K1 is long; with 8-image shards of a
+ * batch split over several GPUs a call is ~0.05 ms of latency-bound kernels and only several
+ * calls in flight keep a GPU busy).
+ * og_fetch_result waits for the OLDEST unfetched call and exposes its result: `poses` points
+ * into pinned memory owned by the handle ([total_rows, C, 6] float32, written there by the
+ * grouping kernel itself), image i owns rows [offsets[i], offsets[i] + counts[i]); the
+ * pointers stay valid until OG_MAX_IN_FLIGHT further og_decode_* calls have been made.
+ * og_fetch_poses is the same without the image count; og_pending returns the number of
+ * unfetched calls. */
+typedef struct og_result {
+    const float *poses;          /* [total_rows, n_keypoints, 6] */
+    const int32_t *offsets;      /* [n_images] first row of every image */
+    const int32_t *counts;       /* [n_images] persons of every image   */
+    int32_t n_images;            /* images of the decode call this result belongs to */
+    int32_t total_rows;
+    int32_t n_keypoints;
+    int32_t reserved;
+} og_result;
+int og_fetch_result(og_handle *h, og_result *out);
 int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offset_host,
                    const int32_t **count_host, int32_t *total_rows);
 int og_pending(const og_handle *h);
@@ -248,6 +270,12 @@ int64_t og_launch_count(const og_handle *h);
  * path; og_fused_redo_count reports how many batches were re-run. */
 int og_set_fused(og_handle *h, int enable);
 
+/* Device path of og_decode_features_dev[_ex]: replay a captured CUDA graph per result slot
+ * (default) or launch kernel by kernel; the counters report replays and (re)captures. */
+int og_set_graph(og_handle *h, int enable);
+int64_t og_graph_replay_count(const og_handle *h);
+int64_t og_graph_build_count(const og_handle *h);
+
 /* Development aid: per-phase clock64() totals of the K3 CTA kernel; only in builds with
  * -DOG_K3_PROFILE (returns OG_ERR_UNSUPPORTED otherwise). */
 int og_debug_k3_profile(uint64_t *out16, int reset);
@@ -265,10 +293,11 @@ int og_set_zero_copy(og_handle *h, int enable);
 int64_t og_zero_copy_count(const og_handle *h);
 
 /* Per-stage device timing of og_decode_* calls with CUDA events recorded on the stream
- * each stage is launched on (input staging and K1: the caller's stream; K2, K3, D2H: the
- * handle's stream).  og_last_stage_times_ms() reports the most recently FETCHED decode call:
- * out6 = { input copy + flip + resize, K1 pass 1 (NMS stream), K1 pass 2 (select),
- *          K2, K3, pose D2H } in milliseconds. */
+ * each stage is launched on (while it is enabled the device path launches kernel by kernel
+ * instead of replaying its graph).  og_last_stage_times_ms() reports the most recently FETCHED
+ * decode call: out6 = { input copy + flip + resize, K1 pass 1 (NMS stream / fused scan + list +
+ * blocks), K1 pass 2 (select), K2 (+ row preparation), K3, end-of-chain marker (the poses are
+ * written to host memory by K3 itself: ~0) } in milliseconds. */
 int og_enable_stage_timing(og_handle *h, int enable);
 int og_last_stage_times_ms(og_handle *h, float *out6);
 

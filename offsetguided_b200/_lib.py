@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_PKG_DIR, 'libogdecoder.so')
 OG_LIMB_COLS = 13
 OG_POSE_COLS = 6
 OG_MAX_TOPK = 128
+OG_MAX_IN_FLIGHT = 8
 OG_DTYPE_F32 = 0
 OG_DTYPE_BF16 = 1
 OG_DTYPE_F16 = 2
@@ -37,6 +38,18 @@ class OgConfig(ctypes.Structure):
         ('sort_dim', ctypes.c_int32),
         ('device', ctypes.c_int32),
         ('max_images', ctypes.c_int32),
+    ]
+
+
+class OgResult(ctypes.Structure):
+    _fields_ = [
+        ('poses', c_float_p),
+        ('offsets', c_int32_p),
+        ('counts', c_int32_p),
+        ('n_images', ctypes.c_int32),
+        ('total_rows', ctypes.c_int32),
+        ('n_keypoints', ctypes.c_int32),
+        ('reserved', ctypes.c_int32),
     ]
 
 
@@ -74,10 +87,14 @@ SIGNATURES = {
                                        _i, _i, c_int32_p, c_int32_p, c_int32_p, _i, _vp]),
     'og_fetch_poses': (_i, [_vp, ctypes.POINTER(c_float_p), ctypes.POINTER(c_int32_p),
                             ctypes.POINTER(c_int32_p), ctypes.POINTER(ctypes.c_int32)]),
+    'og_fetch_result': (_i, [_vp, ctypes.POINTER(OgResult)]),
     'og_pending': (_i, [_vp]),
     'og_copy_intermediates': (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     'og_launch_count': (ctypes.c_int64, [_vp]),
     'og_set_fused': (_i, [_vp, _i]),
+    'og_set_graph': (_i, [_vp, _i]),
+    'og_graph_replay_count': (ctypes.c_int64, [_vp]),
+    'og_graph_build_count': (ctypes.c_int64, [_vp]),
     'og_debug_k3_profile': (_i, [ctypes.POINTER(ctypes.c_uint64), _i]),
     'og_fused_redo_count': (ctypes.c_int64, [_vp]),
     'og_set_zero_copy': (_i, [_vp, _i]),
@@ -103,7 +120,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.og_abi_version() != 1:
+    if lib.og_abi_version() != 2:
         raise OgError(f'ABI version mismatch: library reports {lib.og_abi_version()}')
     _lib = lib
     return lib

@@ -70,10 +70,9 @@ struct PinnedBuf {
 
 }  // namespace
 
-constexpr int kSlots = 3;          // decode calls that may be in flight before a fetch
+constexpr int kSlots = OG_MAX_IN_FLIGHT;   // decode calls that may be in flight before a fetch
 constexpr int kMaxChunks = 8;      // image ranges of one host-API call (copy / decode pipeline)
-// start, after prep, K1 pass 1 (caller's stream) | select start, select = K2 start, K2, K3, D2H
-// (handle's stream)
+// start, after prep, K1 pass 1 | select start, select = K2 start, K2, K3, end (see mark())
 constexpr int kStageEvents = 8;
 
 struct FeatureArgs {               // arguments of a features decode, kept for the exact redo
@@ -83,30 +82,77 @@ struct FeatureArgs {               // arguments of a features decode, kept for t
     MapView hmp_view, off_view;    // og_decode_features_dev_ex: bf16 / strided maps (ptr != nullptr)
 };
 
-// Everything that belongs to ONE decode call until its result has been fetched.
+// What identifies a captured decode chain: replaying the graph is only valid for the same
+// inputs, shapes, flags and slot buffers.
+struct GraphKey {
+    const void *hmp, *off;
+    int dtype;
+    size_t hmp_image_stride, off_image_stride;
+    int n, hgt, w, stride, mode, flip;
+    uint64_t tables_version, buffers_version;
+    bool operator==(const GraphKey &o) const {
+        return hmp == o.hmp && off == o.off && dtype == o.dtype && hmp_image_stride == o.hmp_image_stride &&
+               off_image_stride == o.off_image_stride && n == o.n && hgt == o.hgt && w == o.w &&
+               stride == o.stride && mode == o.mode && flip == o.flip &&
+               tables_version == o.tables_version && buffers_version == o.buffers_version;
+    }
+};
+
+// K2 -> K3 hand-over and K3's tables
+struct GroupScratch {
+    DevBuf<int32_t> prep, cnt, redo;
+    DevBuf<float4> rec;
+    DevBuf<float> slab;
+    void release() {
+        prep.release();
+        cnt.release();
+        redo.release();
+        rec.release();
+        slab.release();
+    }
+};
+
+// Everything that belongs to ONE decode call until its result has been fetched.  Calls in
+// flight share nothing but the read-only configuration, so they overlap freely: each slot
+// has its own stream, scratch and result buffer.
 struct ResultSlot {
-    DevBuf<unsigned char> out;          // [meta int32][pose rows float]
-    PinnedBuf<unsigned char> out_host;
+    // result: [meta int32: offset[n], count[n], overflow flag, -][pose rows float], pinned and
+    // mapped — K3 writes the rows of every person straight into host memory (posted PCIe
+    // writes from its epilogue), so there is no device copy of the poses and no D2H memcpy
+    unsigned char *out_host = nullptr;
+    unsigned char *out_dev = nullptr;   // the same memory as the device addresses it
+    size_t out_cap = 0;
+    DevBuf<int32_t> total;              // K3's row allocator
     DevBuf<float> in_hmp, in_off;       // staged network-resolution inputs (host API)
-    DevBuf<float> det_score;            // K1 output of this call (written on the caller's stream,
-    DevBuf<int32_t> det_index;          //  read by K2 on the handle's stream while the next
-    DevBuf<int32_t> det_count;          //  call's K1 already runs)
-    DevBuf<uint32_t> cand_count;        // K1 pass 1 -> pass 2 hand-over, same reason
+    DevBuf<float> det_score;            // K1 output
+    DevBuf<int32_t> det_index;
+    DevBuf<int32_t> det_count;
+    DevBuf<uint32_t> cand_count;        // K1 pass 1 -> pass 2 hand-over; zero between calls
     DevBuf<uint64_t> cand_keys;
+    DevBuf<uint8_t> tile_flag;          // fused K1 scratch: one flag per work block, zero between calls
+    DevBuf<int32_t> tile_list;          // [blocks] work list + the active-block counter at the end
+    DevBuf<float> limbs;                // K2 output
+    GroupScratch group;
+    cudaStream_t work = nullptr;        // high priority: K2 -> K3 of every call, the whole chain on the device path
     cudaEvent_t k1_done[kMaxChunks] = {nullptr};
     cudaEvent_t copied[kMaxChunks] = {nullptr};
     cudaEvent_t call_start = nullptr;
     cudaEvent_t done = nullptr;
     cudaEvent_t ev[kStageEvents] = {nullptr};
-    cudaStream_t stream = nullptr;
+    cudaGraphExec_t graph = nullptr;    // the device-path chain of this slot, replayed while `key` matches
+    GraphKey key = {};
+    uint64_t buffers_version = 1;       // bumped whenever a buffer of the slot moves
+    cudaStream_t stream = nullptr;      // the caller's stream of the call
     int n = 0;
     size_t meta_bytes = 0;
-    int rows_copied = 0;
     int capacity_rows = 0;
     bool pending = false;
     bool fused = false;
     bool timed = false;
     bool prep_marked = false;
+    bool scratch_dirty = true;          // counters / flags are not known to be zero (fresh slot or failed call)
+    bool has_limbs = false;             // limbs / group scratch hold this call's rows (K3 can be re-run)
+    int k3_images = 0, k3_first = 0;    // image range of the last K3 launch (single-range calls)
     FeatureArgs args = {};
 };
 
@@ -114,26 +160,23 @@ struct og_handle {
     og_config cfg;
     SkeletonDev sk;
     int device;
-    int smem_rows;               // person-table rows in shared memory, batches up to one image per SM
+    int warp_rows;               // person-table rows of the one-warp-per-image K3 kernel (0 = off)
+    int result_rows;             // pose rows per image the pinned result buffer starts with
+    int smem_rows;               // person-table rows of the CTA kernel, batches up to one image per SM
     int smem_rows_dense;         // ... larger batches (several K3 CTAs per SM)
     size_t group_smem;
     int64_t launches;
 
-    // intermediates, reused by consecutive calls in stream order
+    // stand-alone stage APIs (og_nms_topk_f32, og_group_f32, ...): scratch in caller-stream order
     DevBuf<uint32_t> cand_count;
     DevBuf<uint64_t> cand_keys;
-    cudaStream_t aux;                   // K2 -> K3 -> D2H of every call, high priority
+    GroupScratch group;
     cudaStream_t cp;                    // host API: input copies, one image range ahead of the kernels
-    DevBuf<float> limbs;
-    DevBuf<float> slab;
-    DevBuf<int32_t> group_prep;
-    DevBuf<uint8_t> tile_flag;          // fused path scratch: one flag per work block, zero between calls
-    DevBuf<int32_t> tile_list;          // [blocks] work list + the active-block counter at the end
     int sm_count;
     DevBuf<float> fused_hmp, fused_off;     // materialising path only
     DevBuf<float> hr_hmp, hr_off;
-    DevBuf<int32_t> kp_flip, limb_flip;
-    DevBuf<uint8_t> limb_reserved;
+    FlipTablesDev ft;                   // flip-test tables, passed to the kernels by value
+    uint64_t tables_version;
 
     ResultSlot slots[kSlots];
     int head;                    // slot the next decode call uses
@@ -141,16 +184,17 @@ struct og_handle {
     int pending;                 // decode calls in flight
     int last_slot;               // slot of the most recent decode call (intermediates)
     int fetched_slot;            // slot of the most recently fetched result (stage times)
-    int rows_hint;
 
     bool fused_enabled;
+    bool graph_enabled;          // device path: replay a captured CUDA graph per slot
     bool zero_copy_enabled;      // host API: K2 gathers offsets straight from pinned host memory
     int host_chunks;             // host API: image ranges of the copy / decode pipeline
     int host_tail;               // ... with a short last range (tuning aid: OG_HOST_TAIL=0 disables)
-    int select_on_aux;           // 0: never, 1: fused path only, 2: always (tuning aid)
+    int select_on_aux;           // host / full-resolution paths: 0 never, 1 fused path only, 2 always (tuning aid)
     int64_t fused_redos;
     int64_t zero_copy_calls;
-    bool tables_valid;           // device flip tables match the cached host copies
+    int64_t graph_replays, graph_builds;
+    bool tables_valid;           // ft matches the cached host copies
     int32_t kp_cache[OG_MAX_KEYPOINTS];
     int32_t limb_cache[OG_MAX_LIMBS];
     uint8_t reserved_cache[OG_MAX_LIMBS];
@@ -160,7 +204,7 @@ struct og_handle {
 
 namespace {
 
-// meta words: offset[n], count[n], total, overflow flag of the fused path
+// meta words: offset[n], count[n], overflow flag of the fused path, one spare
 inline size_t meta_bytes_for(int n) { return ((size_t)(2 * n + 2) * sizeof(int32_t) + 15) / 16 * 16; }
 inline size_t pose_row_bytes(const og_handle *h) {
     return (size_t)h->cfg.n_keypoints * OG_POSE_COLS * sizeof(float);
@@ -183,6 +227,29 @@ int check_maps(int n, int hgt, int w, int c) {
 
 inline int mark(og_handle *h, ResultSlot *slot, int which, cudaStream_t s) {
     if (h->timing) OG_CUDA_TRY(cudaEventRecord(slot->ev[which], s));
+    return OG_OK;
+}
+
+// ensure() that reports a moved buffer (a captured graph holds the old address)
+template <typename Buf>
+int ensure_tracked(Buf &buf, size_t need, ResultSlot *slot) {
+    const auto *before = buf.ptr;
+    OG_TRY(buf.ensure(need));
+    if (buf.ptr != before) slot->buffers_version += 1;
+    return OG_OK;
+}
+
+int ensure_result(og_handle *h, ResultSlot *slot, size_t bytes) {
+    if (bytes <= slot->out_cap) return OG_OK;
+    if (slot->out_host) OG_CUDA_TRY(cudaFreeHost(slot->out_host));
+    slot->out_host = slot->out_dev = nullptr;
+    slot->out_cap = 0;
+    const size_t grow = bytes + bytes / 4;
+    OG_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&slot->out_host), grow, cudaHostAllocMapped));
+    OG_CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&slot->out_dev), slot->out_host, 0));
+    slot->out_cap = grow;
+    slot->buffers_version += 1;
+    (void)h;
     return OG_OK;
 }
 
@@ -209,11 +276,9 @@ int run_k1(og_handle *h, const float *heat, int n, int hgt, int w, float thre, f
                            after_pass1);
 }
 
-int run_k3(og_handle *h, const float *limbs, int n, float *out_poses, int capacity_rows,
-           int32_t *out_offset, int32_t *out_count, int32_t *out_total, cudaStream_t s,
-           bool zero_total = true) {
+GroupLaunch group_launch(const og_handle *h, int n) {
     const og_config &c = h->cfg;
-    GroupLaunch g;
+    GroupLaunch g = {};
     g.n = n;
     g.c = c.n_keypoints;
     g.l = c.n_limbs;
@@ -223,21 +288,46 @@ int run_k3(og_handle *h, const float *limbs, int n, float *out_poses, int capaci
     g.use_scale = c.use_scale;
     g.person_thre = c.person_thre;
     g.sort_dim = c.sort_dim;
+    g.warp_rows = h->warp_rows;
     g.smem_rows = n > h->sm_count ? h->smem_rows_dense : h->smem_rows;
-    g.slab = nullptr;
-    g.slab_stride = 0;
-    OG_TRY(h->group_prep.ensure(group_prep_ints(g)));
-    g.prep = h->group_prep.ptr;
-    const int pmax = c.n_limbs * c.topk;
-    if (g.smem_rows < pmax) {
-        g.slab_stride = ((size_t)pmax * c.n_keypoints * 6 + 3) / 4 * 4;
-        OG_TRY(h->slab.ensure(g.slab_stride * (size_t)n));
-        g.slab = h->slab.ptr;
+    return g;
+}
+
+// Buffers K2's prepare tail and K3 need for n images.
+int ensure_group_scratch(og_handle *h, GroupScratch &gs, int n, ResultSlot *slot) {
+    GroupLaunch g = group_launch(h, n);
+    const og_config &c = h->cfg;
+    const size_t slab = ((size_t)c.n_limbs * c.topk * c.n_keypoints * 6 + 3) / 4 * 4 * (size_t)n;
+    if (slot) {
+        OG_TRY(ensure_tracked(gs.prep, group_prep_ints(g), slot));
+        OG_TRY(ensure_tracked(gs.rec, group_rec_vec4(g), slot));
+        OG_TRY(ensure_tracked(gs.cnt, (size_t)n * c.n_limbs, slot));
+        OG_TRY(ensure_tracked(gs.redo, (size_t)n, slot));
+        OG_TRY(ensure_tracked(gs.slab, slab, slot));
+    } else {
+        OG_TRY(gs.prep.ensure(group_prep_ints(g)));
+        OG_TRY(gs.rec.ensure(group_rec_vec4(g)));
+        OG_TRY(gs.cnt.ensure((size_t)n * c.n_limbs));
+        OG_TRY(gs.redo.ensure((size_t)n));
+        OG_TRY(gs.slab.ensure(slab));
     }
-    if (zero_total) OG_CUDA_TRY(cudaMemsetAsync(out_total, 0, sizeof(int32_t), s));
-    OG_TRY(launch_group(g, limbs, out_poses, capacity_rows, out_offset, out_count, out_total, s));
-    h->launches += 2;       // prepare + grouping
     return OG_OK;
+}
+
+// K3 on `n` images whose scratch rows start at image `i0` of the scratch buffers.
+int run_k3(og_handle *h, GroupScratch &gs, int i0, const float *limbs, bool prepared, int n,
+           float *out_poses, int capacity_rows, int32_t *out_offset, int32_t *out_count,
+           int32_t *out_total, cudaStream_t s) {
+    const og_config &c = h->cfg;
+    GroupLaunch g = group_launch(h, n);
+    g.prep = gs.prep.ptr + (size_t)i0 * c.n_limbs * (c.topk + 1);
+    g.rec = gs.rec.ptr + (size_t)i0 * c.n_limbs * c.topk * 3;
+    g.cnt = gs.cnt.ptr + (size_t)i0 * c.n_limbs;
+    g.redo = gs.redo.ptr + i0;
+    g.slab_stride = ((size_t)c.n_limbs * c.topk * c.n_keypoints * 6 + 3) / 4 * 4;
+    g.slab = gs.slab.ptr + (size_t)i0 * g.slab_stride;
+    return launch_group(g, limbs, prepared, out_poses, capacity_rows, out_offset, out_count, out_total, s,
+                        &h->launches);
 }
 
 struct K1Fused {
@@ -254,53 +344,81 @@ inline MapView shift_images(MapView v, size_t images) {
 }
 
 // One decode call = begin_call, decode_range over one or more image ranges, finish_call.
-// begin_call: buffers of the slot, meta words cleared, first stage marks.
-int begin_call(og_handle *h, ResultSlot *slot, bool fused, int n, int hgt, int w, cudaStream_t s) {
+// begin_call: buffers of the slot (nothing is allocated after this point: the ranges may be
+// captured into a graph), counters known to be zero, first stage mark.
+int begin_call(og_handle *h, ResultSlot *slot, const K1Fused *fused, int n, int hgt, int w, cudaStream_t s) {
     const og_config &c = h->cfg;
     OG_TRY(check_maps(n, hgt, w, c.n_keypoints));
     const size_t dets = (size_t)n * c.n_keypoints * c.topk;
-    OG_TRY(slot->det_score.ensure(dets));
-    OG_TRY(slot->det_index.ensure(dets));
-    OG_TRY(slot->det_count.ensure((size_t)n * c.n_keypoints));
-    OG_TRY(h->limbs.ensure((size_t)n * c.n_limbs * c.topk * OG_LIMB_COLS));
-    const int capacity_rows = n * c.n_limbs * c.topk;
+    OG_TRY(ensure_tracked(slot->det_score, dets, slot));
+    OG_TRY(ensure_tracked(slot->det_index, dets, slot));
+    OG_TRY(ensure_tracked(slot->det_count, (size_t)n * c.n_keypoints, slot));
+    OG_TRY(ensure_tracked(slot->limbs, (size_t)n * c.n_limbs * c.topk * OG_LIMB_COLS, slot));
+    OG_TRY(ensure_tracked(slot->total, 4, slot));
+    // Pose rows: every person consumes at least one limb row, so n * L * K rows can never
+    // overflow; real scenes hold tens of persons per image, so the pinned buffer starts at 64
+    // rows per image and og_fetch_poses re-runs K3 into a worst-case buffer if a batch ever
+    // needs more (it sees the counts either way).
+    const long long worst = (long long)n * c.n_limbs * c.topk;
+    int capacity_rows = (int)std::min<long long>(worst, std::max<long long>((long long)n * h->result_rows, 256));
+    if (h->result_rows < 64) capacity_rows = (int)std::min<long long>(worst, (long long)n * h->result_rows);   // test aid
     const size_t mbytes = meta_bytes_for(n);
-    OG_TRY(slot->out.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
-    OG_TRY(slot->out_host.ensure(mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
+    if (slot->out_cap >= mbytes + (size_t)worst * pose_row_bytes(h)) capacity_rows = (int)worst;
+    OG_TRY(ensure_result(h, slot, mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
+    const int planes = n * c.n_keypoints;
+    bool fresh_scratch = slot->scratch_dirty;
     if (n > 0) {
-        const int planes = n * c.n_keypoints;
-        OG_TRY(slot->cand_count.ensure(planes));
-        OG_TRY(slot->cand_keys.ensure((size_t)planes * kCandCap));
+        const uint32_t *before = slot->cand_count.ptr;
+        OG_TRY(ensure_tracked(slot->cand_count, planes, slot));
+        fresh_scratch = fresh_scratch || slot->cand_count.ptr != before;
+        OG_TRY(ensure_tracked(slot->cand_keys, (size_t)planes * kCandCap, slot));
+        OG_TRY(ensure_group_scratch(h, slot->group, n, slot));
+        if (fused) {
+            size_t flag_bytes = 0, tiles = 0;
+            fused_scratch(n, c.n_keypoints, fused->h, fused->w, fused->scale, &flag_bytes, &tiles);
+            const uint8_t *fb = slot->tile_flag.ptr;
+            const int32_t *lb = slot->tile_list.ptr;
+            OG_TRY(ensure_tracked(slot->tile_flag, flag_bytes, slot));
+            OG_TRY(ensure_tracked(slot->tile_list, tiles + 1, slot));
+            fresh_scratch = fresh_scratch || slot->tile_flag.ptr != fb || slot->tile_list.ptr != lb;
+        }
     }
+    if (fresh_scratch) {
+        // the kernels keep these zero from call to call; a new buffer (or a failed call) does not
+        cudaStream_t w = slot->work;
+        if (slot->cand_count.ptr) OG_CUDA_TRY(cudaMemsetAsync(slot->cand_count.ptr, 0, slot->cand_count.cap * sizeof(uint32_t), w));
+        if (slot->tile_flag.ptr) OG_CUDA_TRY(cudaMemsetAsync(slot->tile_flag.ptr, 0, slot->tile_flag.cap, w));
+        if (slot->tile_list.ptr) OG_CUDA_TRY(cudaMemsetAsync(slot->tile_list.ptr, 0, slot->tile_list.cap * sizeof(int32_t), w));
+        OG_CUDA_TRY(cudaMemsetAsync(slot->total.ptr, 0, 4 * sizeof(int32_t), w));
+        OG_CUDA_TRY(cudaStreamSynchronize(w));
+    }
+    slot->scratch_dirty = true;            // until finish_call: an error in between leaves them unknown
     slot->n = n;
     slot->meta_bytes = mbytes;
     slot->capacity_rows = capacity_rows;
     slot->stream = s;
-    slot->fused = fused;
+    slot->fused = fused != nullptr;
     slot->timed = false;
-    slot->rows_copied = 0;
+    slot->has_limbs = false;
     if (!slot->prep_marked) OG_TRY(mark(h, slot, 0, s));
     slot->prep_marked = false;
-    if (n > 0) {
-        // total, overflow: first written by pass 2 / K3 of this call, which follow on the same stream
-        int32_t *meta = reinterpret_cast<int32_t *>(slot->out.ptr);
-        (void)s;
-        OG_CUDA_TRY(cudaMemsetAsync(meta + 2 * n, 0, 2 * sizeof(int32_t), h->aux));
-    }
+    if (n > 0) reinterpret_cast<volatile int32_t *>(slot->out_host)[2 * n] = 0;      // overflow flag
     return OG_OK;
 }
 
-// Images [i0, i0 + cn) of the call: K1 (full-resolution stream, or the fused network-resolution
-// kernels) on the caller's stream, then K2 -> K3 on the handle's stream.  `timed` ranges record
-// the stage events (the last range of a call).  All map pointers address image 0 of the call.
+// Images [i0, i0 + cn) of the call.  K1 (full-resolution stream, or the fused network-resolution
+// kernels) on `k1s`, then K2 -> K3 on the slot's stream `a`; when both are the same stream the
+// whole range is one linear chain (device path; this is what gets captured into a graph) and
+// the kernels clear each other's counters instead of memsets.  `timed` ranges record the stage
+// events (the last range of a call).  All map pointers address image 0 of the call.
 int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, const float *heat,
                  const K1Fused *fused, const float *offs, const OffsetSource *offs_lowres,
-                 const float *scales, int hgt, int w, cudaStream_t s, const LimbExtras *extras,
+                 const float *scales, int hgt, int w, cudaStream_t k1s, const LimbExtras *extras,
                  bool timed) {
     const og_config &c = h->cfg;
     const int n = slot->n;
-    int32_t *meta = reinterpret_cast<int32_t *>(slot->out.ptr);
-    float *poses = reinterpret_cast<float *>(slot->out.ptr + slot->meta_bytes);
+    int32_t *meta = reinterpret_cast<int32_t *>(slot->out_dev);
+    float *poses = reinterpret_cast<float *>(slot->out_dev + slot->meta_bytes);
     const size_t HW = (size_t)hgt * w;
     const size_t det0 = (size_t)i0 * c.n_keypoints * c.topk;
     const size_t plane0 = (size_t)i0 * c.n_keypoints;
@@ -310,44 +428,42 @@ int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, cons
     uint32_t *cand_count = slot->cand_count.ptr + plane0;
     uint64_t *cand_keys = slot->cand_keys.ptr + plane0 * kCandCap;
     const int planes = cn * c.n_keypoints;
-    if (timed) OG_TRY(mark(h, slot, 1, s));
+    cudaStream_t a = slot->work;
+    const bool chain = k1s == a;
+    if (timed) OG_TRY(mark(h, slot, 1, k1s));
+    int32_t *n_active = nullptr;
     if (fused) {
         size_t flag_bytes = 0, tiles = 0;
-        fused_scratch(cn, c.n_keypoints, fused->h, fused->w, fused->scale, &flag_bytes, &tiles);
-        if (flag_bytes > h->tile_flag.cap) {        // a fresh buffer starts out clear; the kernels keep it so
-            OG_TRY(h->tile_flag.ensure(flag_bytes));
-            OG_CUDA_TRY(cudaMemsetAsync(h->tile_flag.ptr, 0, h->tile_flag.cap, s));
-        }
-        OG_TRY(h->tile_list.ensure(tiles + 1));
+        fused_scratch(n, c.n_keypoints, fused->h, fused->w, fused->scale, &flag_bytes, &tiles);
+        n_active = slot->tile_list.ptr + tiles;
         // the mirrored copy of image i sits n images behind it: shifting the base keeps that offset
-        OG_TRY(launch_fused_candidates(shift_images(fused->hmp, i0), h->kp_flip.ptr, cn, n,
+        OG_TRY(launch_fused_candidates(shift_images(fused->hmp, i0), h->ft, cn, n,
                                        c.n_keypoints, fused->h, fused->w, fused->scale, fused->cubic,
-                                       fused->flip, c.thre_hmp, cand_count, cand_keys, h->tile_flag.ptr,
-                                       h->tile_list.ptr, h->tile_list.ptr + tiles, h->sm_count, s,
+                                       fused->flip, c.thre_hmp, cand_count, cand_keys, slot->tile_flag.ptr,
+                                       slot->tile_list.ptr, n_active, h->sm_count, !chain, k1s,
                                        &h->launches));
     } else {
         OG_TRY(launch_nms_candidates(heat + plane0 * HW, planes, hgt, w, c.thre_hmp, cand_count, cand_keys,
-                                     s, &h->launches));
+                                     k1s, &h->launches));
     }
-    if (timed) OG_TRY(mark(h, slot, 2, s));
-    // Everything after the streaming pass runs on the handle's own high-priority stream: the
-    // per-plane selection, K2, K3 and the D2H are latency-bound and occupy a fraction of the
-    // SMs, so the next K1 pass (HBM-bound, on the caller's stream) overlaps them instead of
-    // queueing behind them.
-    cudaStream_t a = h->aux;
-    const bool sel_on_aux = h->select_on_aux == 2 || (h->select_on_aux == 1 && fused != nullptr);
-    if (sel_on_aux) {
-        OG_CUDA_TRY(cudaEventRecord(slot->k1_done[chunk], s));
+    if (timed) OG_TRY(mark(h, slot, 2, k1s));
+    // Host / full-resolution paths: everything after the streaming pass runs on the slot's own
+    // high-priority stream — the per-plane selection, K2 and K3 are latency-bound and occupy
+    // a fraction of the SMs, so the next K1 pass (HBM-bound, on the caller's stream) overlaps
+    // them instead of queueing behind them.
+    const bool sel_on_aux = chain || h->select_on_aux == 2 || (h->select_on_aux == 1 && fused != nullptr);
+    if (!chain && sel_on_aux) {
+        OG_CUDA_TRY(cudaEventRecord(slot->k1_done[chunk], k1s));
         OG_CUDA_TRY(cudaStreamWaitEvent(a, slot->k1_done[chunk], 0));
     }
-    cudaStream_t sel = sel_on_aux ? a : s;
+    cudaStream_t sel = sel_on_aux ? a : k1s;
     if (timed) OG_TRY(mark(h, slot, 3, sel));
     OG_TRY(launch_select_topk(fused ? nullptr : heat + plane0 * HW, planes, hgt, w, c.thre_hmp, c.topk,
                               cand_count, cand_keys, det_score, det_index, det_count,
-                              fused ? meta + 2 * n + 1 : nullptr, sel));
+                              fused ? meta + 2 * n : nullptr, chain ? n_active : nullptr, sel));
     h->launches += 1;
-    if (!sel_on_aux) {
-        OG_CUDA_TRY(cudaEventRecord(slot->k1_done[chunk], s));
+    if (!chain && !sel_on_aux) {
+        OG_CUDA_TRY(cudaEventRecord(slot->k1_done[chunk], k1s));
         OG_CUDA_TRY(cudaStreamWaitEvent(a, slot->k1_done[chunk], 0));
     }
     if (timed) OG_TRY(mark(h, slot, 4, a));
@@ -362,31 +478,35 @@ int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, cons
         ex = *extras;
         if (ex.jomps) ex.jomps += (size_t)i0 * 2 * HW;
     }
-    float *limbs = h->limbs.ptr + (size_t)i0 * c.n_limbs * c.topk * OG_LIMB_COLS;
+    float *limbs = slot->limbs.ptr + (size_t)i0 * c.n_limbs * c.topk * OG_LIMB_COLS;
+    GroupScratch &gs = slot->group;
+    PrepOut po = {gs.prep.ptr + (size_t)i0 * c.n_limbs * (c.topk + 1),
+                  gs.rec.ptr + (size_t)i0 * c.n_limbs * c.topk * 3, gs.cnt.ptr + (size_t)i0 * c.n_limbs,
+                  c.dist_max, c.use_scale, chunk == 0 ? slot->total.ptr : nullptr};
     OG_TRY(launch_limb_score(det_score, det_index, offs ? offs + (size_t)i0 * nd * c.n_limbs * HW : nullptr,
-                             offs_lowres ? &src : nullptr, scales ? scales + plane0 * HW : nullptr,
+                             offs_lowres ? &src : nullptr, &h->ft, scales ? scales + plane0 * HW : nullptr,
                              extras ? &ex : nullptr, cn, c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk,
-                             c.thre_hmp, c.min_len, c.resize_factor, limbs, a));
+                             c.thre_hmp, c.min_len, c.resize_factor, limbs, &po, a));
     h->launches += 1;
     if (timed) OG_TRY(mark(h, slot, 5, a));
-    OG_TRY(run_k3(h, limbs, cn, poses, slot->capacity_rows, meta + i0, meta + n + i0, meta + 2 * n, a, false));
+    OG_TRY(run_k3(h, gs, i0, limbs, true, cn, poses, slot->capacity_rows, meta + i0, meta + n + i0,
+                  slot->total.ptr, a));
     if (timed) OG_TRY(mark(h, slot, 6, a));
+    slot->k3_first = i0;
+    slot->k3_images = cn;
     return OG_OK;
 }
 
-// finish_call: one asynchronous copy of meta + the pose rows the previous batches suggest
 int finish_call(og_handle *h, ResultSlot *slot) {
     const int n = slot->n;
     if (n > 0) {
-        cudaStream_t a = h->aux;
-        const int rows = std::min(slot->capacity_rows, h->rows_hint > 0 ? h->rows_hint : n * 32);
-        const size_t bytes = slot->meta_bytes + (size_t)rows * pose_row_bytes(h);
-        OG_CUDA_TRY(cudaMemcpyAsync(slot->out_host.ptr, slot->out.ptr, bytes, cudaMemcpyDeviceToHost, a));
+        cudaStream_t a = slot->work;
         OG_TRY(mark(h, slot, 7, a));
         slot->timed = h->timing;
-        slot->rows_copied = rows;
         OG_CUDA_TRY(cudaEventRecord(slot->done, a));
+        slot->has_limbs = true;
     }
+    slot->scratch_dirty = false;
     if (!slot->pending) {           // a redo keeps its place in the queue
         slot->pending = true;
         h->pending += 1;
@@ -396,11 +516,12 @@ int finish_call(og_handle *h, ResultSlot *slot) {
     return OG_OK;
 }
 
-// The whole batch as one range.
+// The whole batch as one range (full-resolution maps, or the materialising features path):
+// K1 on the caller's stream, the rest on the slot's.
 int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused *fused,
                 const float *offs, const OffsetSource *offs_lowres, const float *scales, int n,
                 int hgt, int w, cudaStream_t s, const LimbExtras *extras = nullptr) {
-    OG_TRY(begin_call(h, slot, fused != nullptr, n, hgt, w, s));
+    OG_TRY(begin_call(h, slot, fused, n, hgt, w, s));
     if (n > 0)
         OG_TRY(decode_range(h, slot, 0, 0, n, heat, fused, offs, offs_lowres, scales, hgt, w, s, extras, true));
     else
@@ -408,8 +529,72 @@ int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused
     return finish_call(h, slot);
 }
 
+// Device path of the fused decode: the caller's stream is only waited on; the whole chain
+// (K1f scan -> list -> blocks -> select -> K2 + prepare -> K3) runs on the slot's stream, so
+// calls in flight overlap each other and the caller's stream is free at once.  Without stage
+// timing the chain is a CUDA graph captured once per slot and replayed while the inputs, the
+// shapes and the slot's buffers stay the same: one cudaGraphLaunch instead of six kernel
+// launches.
+int decode_chain(og_handle *h, ResultSlot *slot, const K1Fused &k1, const OffsetSource &src, int n,
+                 int H, int W, cudaStream_t s) {
+    OG_TRY(begin_call(h, slot, &k1, n, H, W, s));
+    cudaStream_t a = slot->work;
+    if (n == 0) {
+        OG_TRY(mark(h, slot, 1, s));
+        return finish_call(h, slot);
+    }
+    OG_CUDA_TRY(cudaEventRecord(slot->call_start, s));
+    OG_CUDA_TRY(cudaStreamWaitEvent(a, slot->call_start, 0));
+    if (!h->graph_enabled || h->timing) {
+        OG_TRY(decode_range(h, slot, 0, 0, n, nullptr, &k1, nullptr, &src, nullptr, H, W, a, nullptr, true));
+        return finish_call(h, slot);
+    }
+    const GraphKey key = {k1.hmp.ptr, src.maps.ptr, k1.hmp.dtype, k1.hmp.image_stride, src.maps.image_stride,
+                          n, k1.h, k1.w, k1.scale, k1.cubic ? 1 : 0, k1.flip ? 1 : 0,
+                          h->tables_version, slot->buffers_version};
+    if (slot->graph == nullptr || !(slot->key == key)) {
+        cudaGraph_t graph = nullptr;
+        OG_CUDA_TRY(cudaStreamBeginCapture(a, cudaStreamCaptureModeRelaxed));
+        const int st = decode_range(h, slot, 0, 0, n, nullptr, &k1, nullptr, &src, nullptr, H, W, a, nullptr, false);
+        const cudaError_t end = cudaStreamEndCapture(a, &graph);
+        if (st != OG_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return st;
+        }
+        OG_CUDA_TRY(end);
+        bool updated = false;
+        if (slot->graph != nullptr) {
+            cudaGraphExecUpdateResultInfo info;
+            updated = cudaGraphExecUpdate(slot->graph, graph, &info) == cudaSuccess;
+            if (!updated) {
+                (void)cudaGetLastError();
+                cudaGraphExecDestroy(slot->graph);
+                slot->graph = nullptr;
+            }
+        }
+        if (!updated) {
+            const cudaError_t inst = cudaGraphInstantiate(&slot->graph, graph, 0);
+            if (inst != cudaSuccess) {
+                cudaGraphDestroy(graph);
+                slot->graph = nullptr;
+                OG_CUDA_TRY(inst);
+            }
+        }
+        cudaGraphDestroy(graph);
+        slot->key = key;
+        h->graph_builds += 1;
+    } else {
+        h->launches += 7;           // scan, list, blocks, select, K2, K3 warp, K3 CTA: the graph's kernel nodes
+        slot->k3_first = 0;
+        slot->k3_images = n;
+    }
+    OG_CUDA_TRY(cudaGraphLaunch(slot->graph, a));
+    h->graph_replays += 1;
+    return finish_call(h, slot);
+}
+
 int upload_flip_tables(og_handle *h, const int32_t *kp_flip, const int32_t *limb_flip,
-                       const int32_t *limb_reserve, int n_reserve, cudaStream_t s) {
+                       const int32_t *limb_reserve, int n_reserve) {
     const og_config &c = h->cfg;
     OG_REQUIRE(kp_flip && limb_flip && (n_reserve == 0 || limb_reserve),
                "flip_test needs the keypoint / limb flip tables");
@@ -425,21 +610,19 @@ int upload_flip_tables(og_handle *h, const int32_t *kp_flip, const int32_t *limb
     if (h->tables_valid && memcmp(h->kp_cache, kp_flip, sizeof(int32_t) * c.n_keypoints) == 0 &&
         memcmp(h->limb_cache, limb_flip, sizeof(int32_t) * c.n_limbs) == 0 &&
         memcmp(h->reserved_cache, reserved, c.n_limbs) == 0)
-        return OG_OK;                      // device copies are current
-    OG_TRY(h->kp_flip.ensure(c.n_keypoints));
-    OG_TRY(h->limb_flip.ensure(c.n_limbs));
-    OG_TRY(h->limb_reserved.ensure(c.n_limbs));
-    // the tables may still be read by a decode in flight: drain the device first (rare: tables change
-    // only when the caller switches skeleton tables)
-    OG_CUDA_TRY(cudaDeviceSynchronize());
-    OG_CUDA_TRY(cudaMemcpy(h->kp_flip.ptr, kp_flip, sizeof(int32_t) * c.n_keypoints, cudaMemcpyHostToDevice));
-    OG_CUDA_TRY(cudaMemcpy(h->limb_flip.ptr, limb_flip, sizeof(int32_t) * c.n_limbs, cudaMemcpyHostToDevice));
-    OG_CUDA_TRY(cudaMemcpy(h->limb_reserved.ptr, reserved, c.n_limbs, cudaMemcpyHostToDevice));
-    (void)s;
+        return OG_OK;                      // unchanged
+    // the tables travel by value with every launch: nothing on the device to update or wait for
+    memset(&h->ft, 0, sizeof(h->ft));
+    for (int i = 0; i < c.n_keypoints; ++i) h->ft.kp[i] = (int8_t)kp_flip[i];
+    for (int i = 0; i < c.n_limbs; ++i) {
+        h->ft.limb[i] = (int8_t)limb_flip[i];
+        if (reserved[i]) h->ft.reserved |= 1ull << i;
+    }
     memcpy(h->kp_cache, kp_flip, sizeof(int32_t) * c.n_keypoints);
     memcpy(h->limb_cache, limb_flip, sizeof(int32_t) * c.n_limbs);
     memcpy(h->reserved_cache, reserved, c.n_limbs);
     h->tables_valid = true;
+    h->tables_version += 1;
     return OG_OK;
 }
 
@@ -465,20 +648,18 @@ int decode_features_impl(og_handle *h, ResultSlot *slot, const float *hmp, const
         K1Fused k1 = {dense_f32(hmp, (size_t)c.n_keypoints * hw), hgt, w, hmp_stride, resize_mode == 1,
                       flip_test != 0};
         OffsetSource src = {dense_f32(off, (size_t)2 * c.n_limbs * hw), hgt, w, off_stride,
-                            flip_test ? 1 : 0, n, h->limb_flip.ptr, h->limb_reserved.ptr};
-        return decode_core(h, slot, nullptr, &k1, nullptr, &src, nullptr, n, hgt * hmp_stride,
-                           w * hmp_stride, s);
+                            flip_test ? 1 : 0, n};
+        return decode_chain(h, slot, k1, src, n, hgt * hmp_stride, w * hmp_stride, s);
     }
     // Materialising path: the flip / resize outputs below are handle-owned and still read by
-    // K2 of an earlier call on the handle's stream, so this call's writes wait for those calls.
+    // K2 of an earlier call on its slot's stream, so this call's writes wait for those calls.
     for (int i = 0; i < kSlots; ++i)
         if (&h->slots[i] != slot && h->slots[i].pending && h->slots[i].n > 0)
             OG_CUDA_TRY(cudaStreamWaitEvent(s, h->slots[i].done, 0));
     if (flip_test) {
         OG_TRY(h->fused_hmp.ensure((size_t)n * c.n_keypoints * hw));
         OG_TRY(h->fused_off.ensure((size_t)n * 2 * c.n_limbs * hw));
-        OG_TRY(launch_flip_fuse(cur_h, cur_o, h->kp_flip.ptr, h->limb_flip.ptr, h->limb_reserved.ptr,
-                                n, c.n_keypoints, c.n_limbs, hgt, w, h->fused_hmp.ptr,
+        OG_TRY(launch_flip_fuse(cur_h, cur_o, h->ft, n, c.n_keypoints, c.n_limbs, hgt, w, h->fused_hmp.ptr,
                                 h->fused_off.ptr, s));
         h->launches += 1;
         cur_h = h->fused_hmp.ptr;
@@ -502,8 +683,7 @@ int decode_features_impl(og_handle *h, ResultSlot *slot, const float *hmp, const
 
 int check_feature_args(og_handle *h, int n, int hgt, int w, int hmp_stride, int off_stride,
                        int resize_mode, int flip_test, const int32_t *kp_flip,
-                       const int32_t *limb_flip, const int32_t *limb_reserve, int n_reserve,
-                       cudaStream_t s) {
+                       const int32_t *limb_flip, const int32_t *limb_reserve, int n_reserve) {
     OG_TRY(check_device(h));
     OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
     OG_REQUIRE(hmp_stride >= 1 && off_stride >= 1, "strides must be >= 1");
@@ -511,7 +691,7 @@ int check_feature_args(og_handle *h, int n, int hgt, int w, int hmp_stride, int 
                "heat and offset maps must reach the same resolution (collect.py:81): strides %d vs %d",
                hmp_stride, off_stride);
     OG_REQUIRE(resize_mode == 0 || resize_mode == 1, "resize_mode must be 0 (bilinear) or 1 (bicubic)");
-    if (flip_test) OG_TRY(upload_flip_tables(h, kp_flip, limb_flip, limb_reserve, n_reserve, s));
+    if (flip_test) OG_TRY(upload_flip_tables(h, kp_flip, limb_flip, limb_reserve, n_reserve));
     return OG_OK;
 }
 
@@ -587,11 +767,19 @@ int og_create(const og_config *cfg, og_handle **out) {
     h->head = h->tail = h->pending = 0;
     h->last_slot = 0;
     h->fetched_slot = -1;
-    h->rows_hint = 0;
     h->timing = false;
-    h->aux = nullptr;
     h->cp = nullptr;
     h->fused_enabled = true;
+    h->graph_enabled = true;
+    if (const char *env = getenv("OG_GRAPH")) h->graph_enabled = atoi(env) != 0;     // tuning aid
+    h->graph_replays = h->graph_builds = 0;
+    h->result_rows = 64;
+    if (const char *env = getenv("OG_RESULT_ROWS")) {          // test aid: force the regroup path
+        const int v = atoi(env);
+        if (v >= 1) h->result_rows = v;
+    }
+    h->tables_version = 1;
+    memset(&h->ft, 0, sizeof(h->ft));
     h->zero_copy_enabled = true;
     h->host_chunks = 4;
     if (const char *env = getenv("OG_HOST_CHUNKS")) {          // tuning aid
@@ -607,7 +795,7 @@ int og_create(const og_config *cfg, og_handle **out) {
     h->tables_valid = false;
 
     // person-table rows held in shared memory: as many as fit beside the work arrays
-    GroupLaunch g;
+    GroupLaunch g = {};
     g.c = cfg->n_keypoints;
     g.l = cfg->n_limbs;
     g.k = cfg->topk;
@@ -646,7 +834,17 @@ int og_create(const og_config *cfg, og_handle **out) {
     g.smem_rows = rows;
     h->smem_rows = rows;
     h->group_smem = group_smem_bytes(g);
-    int st = prepare_group_kernel(h->group_smem);
+    // One-warp-per-image kernel: 64 person rows (26 KB of shared memory for 17 keypoints, eight
+    // images per SM) hold every real scene; an image that needs more is redone by the CTA kernel.
+    h->warp_rows = std::min(64, pmax);
+    if (const char *env = getenv("OG_K3_WARP_ROWS")) {         // tuning aid; 0 = CTA kernel only
+        const int v = atoi(env);
+        if (v >= 0 && v <= 256) h->warp_rows = std::min(v, pmax);
+    }
+    g.warp_rows = h->warp_rows;
+    while (g.warp_rows > 8 && group_warp_smem_bytes(g) > 96 * 1024) g.warp_rows /= 2;
+    h->warp_rows = g.warp_rows;
+    int st = prepare_group_kernel(h->group_smem, group_warp_smem_bytes(g));
     if (st != OG_OK) {
         delete h;
         return st;
@@ -655,9 +853,9 @@ int og_create(const og_config *cfg, og_handle **out) {
         int least = 0, greatest = 0;
         cudaError_t err = cudaDeviceGetStreamPriorityRange(&least, &greatest);
         if (const char *env = getenv("OG_AUX_PRIORITY")) if (atoi(env) == 0) greatest = least;   // tuning aid
-        if (err == cudaSuccess) err = cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, greatest);
+        for (int i = 0; i < kSlots && err == cudaSuccess; ++i)
+            err = cudaStreamCreateWithPriority(&h->slots[i].work, cudaStreamNonBlocking, greatest);
         if (err != cudaSuccess) {
-            h->aux = nullptr;
             og_destroy(h);
             set_error("cudaStreamCreateWithPriority failed: %s", cudaGetErrorString(err));
             return OG_ERR_CUDA;
@@ -691,22 +889,16 @@ int og_destroy(og_handle *h) {
     cudaDeviceSynchronize();
     h->cand_count.release();
     h->cand_keys.release();
-    h->limbs.release();
-    h->slab.release();
-    h->group_prep.release();
-    h->tile_flag.release();
-    h->tile_list.release();
+    h->group.release();
     h->fused_hmp.release();
     h->fused_off.release();
     h->hr_hmp.release();
     h->hr_off.release();
-    h->kp_flip.release();
-    h->limb_flip.release();
-    h->limb_reserved.release();
     for (int i = 0; i < kSlots; ++i) {
         ResultSlot &sl = h->slots[i];
-        sl.out.release();
-        sl.out_host.release();
+        if (sl.graph) cudaGraphExecDestroy(sl.graph);
+        if (sl.out_host) cudaFreeHost(sl.out_host);
+        sl.total.release();
         sl.in_hmp.release();
         sl.in_off.release();
         sl.det_score.release();
@@ -714,6 +906,10 @@ int og_destroy(og_handle *h) {
         sl.det_count.release();
         sl.cand_count.release();
         sl.cand_keys.release();
+        sl.tile_flag.release();
+        sl.tile_list.release();
+        sl.limbs.release();
+        sl.group.release();
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.call_start) cudaEventDestroy(sl.call_start);
         for (int j = 0; j < kMaxChunks; ++j) {
@@ -722,8 +918,8 @@ int og_destroy(og_handle *h) {
         }
         for (int e = 0; e < kStageEvents; ++e)
             if (sl.ev[e]) cudaEventDestroy(sl.ev[e]);
+        if (sl.work) cudaStreamDestroy(sl.work);
     }
-    if (h->aux) cudaStreamDestroy(h->aux);
     if (h->cp) cudaStreamDestroy(h->cp);
     delete h;
     return OG_OK;
@@ -765,9 +961,9 @@ int og_limb_score_f32(og_handle *h, const float *det_score_dev, const int32_t *d
     OG_TRY(check_device(h));
     OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
     const og_config &c = h->cfg;
-    OG_TRY(launch_limb_score(det_score_dev, det_index_dev, offs_dev, nullptr, scales_dev, nullptr, n,
+    OG_TRY(launch_limb_score(det_score_dev, det_index_dev, offs_dev, nullptr, nullptr, scales_dev, nullptr, n,
                              c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp, c.min_len,
-                             c.resize_factor, out_limbs_dev, static_cast<cudaStream_t>(stream)));
+                             c.resize_factor, out_limbs_dev, nullptr, static_cast<cudaStream_t>(stream)));
     h->launches += 1;
     return OG_OK;
 }
@@ -785,9 +981,9 @@ int og_limb_score_ex_f32(og_handle *h, const float *det_score_dev, const int32_t
     OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
     const og_config &c = h->cfg;
     LimbExtras ex = {jomps_dev, vector_nd, use_jitter};
-    OG_TRY(launch_limb_score(det_score_dev, det_index_dev, offs_dev, nullptr, scales_dev, &ex, n,
+    OG_TRY(launch_limb_score(det_score_dev, det_index_dev, offs_dev, nullptr, nullptr, scales_dev, &ex, n,
                              c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk, c.thre_hmp, c.min_len,
-                             c.resize_factor, out_limbs_dev, static_cast<cudaStream_t>(stream)));
+                             c.resize_factor, out_limbs_dev, nullptr, static_cast<cudaStream_t>(stream)));
     h->launches += 1;
     return OG_OK;
 }
@@ -832,10 +1028,14 @@ int og_group_f32(og_handle *h, const float *limbs_dev, int n, float *out_poses_d
     OG_REQUIRE(h && limbs_dev && out_poses_dev && out_offset_dev && out_count_dev && out_total_dev,
                "og_group_f32: null pointer");
     OG_REQUIRE(n >= 0 && capacity_rows >= 0, "og_group_f32: negative size");
-    OG_REQUIRE(h->pending == 0, "og_group_f32: fetch the pending decode calls first (shared scratch)");
     OG_TRY(check_device(h));
-    return run_k3(h, limbs_dev, n, out_poses_dev, capacity_rows, out_offset_dev, out_count_dev,
-                  out_total_dev, static_cast<cudaStream_t>(stream));
+    if (n == 0) return OG_OK;
+    // the stand-alone stage APIs share one scratch set, ordered by the caller's stream
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OG_TRY(ensure_group_scratch(h, h->group, n, nullptr));
+    OG_CUDA_TRY(cudaMemsetAsync(out_total_dev, 0, sizeof(int32_t), s));
+    return run_k3(h, h->group, 0, limbs_dev, false, n, out_poses_dev, capacity_rows, out_offset_dev,
+                  out_count_dev, out_total_dev, s);
 }
 
 int og_scored_offset_f32(og_handle *h, const float *hmp_dev, const float *off_dev, int n, int hgt,
@@ -858,9 +1058,8 @@ int og_flip_fuse_f32(og_handle *h, const float *hmp2n_dev, const float *off2n_de
     OG_TRY(check_device(h));
     OG_TRY(check_maps(n, hgt, w, h->cfg.n_keypoints));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    OG_TRY(upload_flip_tables(h, kp_flip, limb_flip, limb_reserve, n_reserve, s));
-    OG_TRY(launch_flip_fuse(hmp2n_dev, off2n_dev, h->kp_flip.ptr, h->limb_flip.ptr,
-                            h->limb_reserved.ptr, n, h->cfg.n_keypoints, h->cfg.n_limbs, hgt, w,
+    OG_TRY(upload_flip_tables(h, kp_flip, limb_flip, limb_reserve, n_reserve));
+    OG_TRY(launch_flip_fuse(hmp2n_dev, off2n_dev, h->ft, n, h->cfg.n_keypoints, h->cfg.n_limbs, hgt, w,
                             out_hmp_dev, out_off_dev, s));
     h->launches += 1;
     return OG_OK;
@@ -908,7 +1107,7 @@ int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_
     OG_REQUIRE(h && (n == 0 || (hmp_dev && off_dev)), "og_decode_features_dev: null pointer");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
-                              limb_flip, limb_reserve, n_reserve, s));
+                              limb_flip, limb_reserve, n_reserve));
     ResultSlot *slot = nullptr;
     OG_TRY(acquire_slot(h, nullptr, &slot));
     return decode_features_impl(h, slot, hmp_dev, off_dev, n, hgt, w, hmp_stride, off_stride,
@@ -925,7 +1124,7 @@ int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off
                "dtype must be OG_DTYPE_F32, OG_DTYPE_BF16 or OG_DTYPE_F16");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
-                              limb_flip, limb_reserve, n_reserve, s));
+                              limb_flip, limb_reserve, n_reserve));
     const og_config &c = h->cfg;
     const size_t hw = (size_t)hgt * w;
     const size_t hmp_img = (size_t)c.n_keypoints * hw, off_img = (size_t)2 * c.n_limbs * hw;
@@ -951,8 +1150,8 @@ int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off
     slot->args = FeatureArgs{nullptr, nullptr, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test,
                              nullptr, hv, ov};
     K1Fused k1 = {hv, hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
-    OffsetSource src = {ov, hgt, w, off_stride, flip_test ? 1 : 0, n, h->limb_flip.ptr, h->limb_reserved.ptr};
-    return decode_core(h, slot, nullptr, &k1, nullptr, &src, nullptr, n, H, W, s);
+    OffsetSource src = {ov, hgt, w, off_stride, flip_test ? 1 : 0, n};
+    return decode_chain(h, slot, k1, src, n, H, W, s);
 }
 
 int og_decode_features_host(og_handle *h, const float *hmp_host, const float *off_host, int n,
@@ -962,7 +1161,7 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
     OG_REQUIRE(h && (n == 0 || (hmp_host && off_host)), "og_decode_features_host: null pointer");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
-                              limb_flip, limb_reserve, n_reserve, s));
+                              limb_flip, limb_reserve, n_reserve));
     ResultSlot *slot = nullptr;
     OG_TRY(acquire_slot(h, nullptr, &slot));
     const og_config &c = h->cfg;
@@ -984,13 +1183,13 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
             (void)cudaGetLastError();       // not registered: clear the error state
     }
     const size_t hmp_img = (size_t)c.n_keypoints * hw, off_img = (size_t)2 * c.n_limbs * hw;
-    OG_TRY(slot->in_hmp.ensure(std::max<size_t>(1, n_in * hmp_img)));
-    if (!off_alias) OG_TRY(slot->in_off.ensure(std::max<size_t>(1, n_in * off_img)));
+    OG_TRY(ensure_tracked(slot->in_hmp, std::max<size_t>(1, n_in * hmp_img), slot));
+    if (!off_alias) OG_TRY(ensure_tracked(slot->in_off, std::max<size_t>(1, n_in * off_img), slot));
     OG_TRY(mark(h, slot, 0, s));
     slot->prep_marked = h->timing;
 
     // The copies run on the handle's copy stream, one image range ahead of the kernels: while
-    // range j is decoded (K1f on `stream`, K2 / K3 on the handle's stream) range j + 1 crosses
+    // range j is decoded (K1f on `stream`, K2 / K3 on the slot's stream) range j + 1 crosses
     // PCIe.  The buffers are ready in `stream` order, so the copy stream starts behind it.
     OG_CUDA_TRY(cudaEventRecord(slot->call_start, s));
     OG_CUDA_TRY(cudaStreamWaitEvent(h->cp, slot->call_start, 0));
@@ -1020,7 +1219,7 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
         OG_CUDA_TRY(cudaEventRecord(slot->copied[0], h->cp));
         OG_CUDA_TRY(cudaStreamWaitEvent(s, slot->copied[0], 0));
         return decode_features_impl(h, slot, slot->in_hmp.ptr, off_src, n, hgt, w, hmp_stride,
-                                    off_stride, resize_mode, flip_test, s, true);
+                                    off_stride, resize_mode, flip_test, s, false);
     }
     const int H = hgt * hmp_stride, W = w * hmp_stride;
     OG_TRY(check_maps(n, H, W, c.n_keypoints));
@@ -1028,9 +1227,8 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
                              hmp_stride, off_stride, resize_mode, flip_test, off_alias ? off_host : nullptr,
                              MapView{nullptr, 0, 0}, MapView{nullptr, 0, 0}};
     K1Fused k1 = {dense_f32(slot->in_hmp.ptr, hmp_img), hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
-    OffsetSource src = {dense_f32(off_src, off_img), hgt, w, off_stride, flip_test ? 1 : 0, n,
-                        h->limb_flip.ptr, h->limb_reserved.ptr};
-    OG_TRY(begin_call(h, slot, true, n, H, W, s));
+    OffsetSource src = {dense_f32(off_src, off_img), hgt, w, off_stride, flip_test ? 1 : 0, n};
+    OG_TRY(begin_call(h, slot, &k1, n, H, W, s));
     // Image ranges: only the kernels of the LAST range run after the last byte has arrived, so
     // that range is kept small (n / 16, at least 4 images); the others share the rest evenly.
     int bounds[kMaxChunks + 1];
@@ -1053,26 +1251,45 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
         OG_CUDA_TRY(cudaStreamWaitEvent(s, slot->copied[chunk], 0));
         OG_TRY(decode_range(h, slot, chunk, i0, cn, nullptr, &k1, nullptr, &src, nullptr, H, W, s, nullptr, last));
     }
+    slot->k3_images = 0;                    // several K3 launches: a capacity redo regroups every range
     if (off_alias) h->zero_copy_calls += 1;
     return finish_call(h, slot);
 }
 
-int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offset_host,
-                   const int32_t **count_host, int32_t *total_rows) {
-    OG_REQUIRE(h && poses_host && offset_host && count_host && total_rows, "og_fetch_poses: null pointer");
-    *poses_host = nullptr;
-    *offset_host = nullptr;
-    *count_host = nullptr;
-    *total_rows = 0;
-    OG_REQUIRE(h->pending > 0, "og_fetch_poses: no decode call is pending");
+namespace {
+
+// Re-run K3 of a fetched call into a worst-case result buffer (more persons than the pinned
+// buffer was sized for: noise-like inputs only).
+int regroup_with_full_capacity(og_handle *h, ResultSlot *slot) {
+    const og_config &c = h->cfg;
+    const int n = slot->n;
+    const long long worst = (long long)n * c.n_limbs * c.topk;
+    OG_TRY(ensure_result(h, slot, slot->meta_bytes + (size_t)worst * pose_row_bytes(h)));
+    slot->capacity_rows = (int)worst;
+    int32_t *meta = reinterpret_cast<int32_t *>(slot->out_dev);
+    float *poses = reinterpret_cast<float *>(slot->out_dev + slot->meta_bytes);
+    cudaStream_t a = slot->work;
+    OG_CUDA_TRY(cudaMemsetAsync(slot->total.ptr, 0, sizeof(int32_t), a));
+    OG_TRY(run_k3(h, slot->group, 0, slot->limbs.ptr, true, n, poses, slot->capacity_rows, meta, meta + n,
+                  slot->total.ptr, a));
+    OG_CUDA_TRY(cudaStreamSynchronize(a));
+    return OG_OK;
+}
+
+}  // namespace
+
+int og_fetch_result(og_handle *h, og_result *out) {
+    OG_REQUIRE(h && out, "og_fetch_result: null pointer");
+    memset(out, 0, sizeof(*out));
+    OG_REQUIRE(h->pending > 0, "og_fetch_result: no decode call is pending");
     OG_TRY(check_device(h));
     ResultSlot *slot = &h->slots[h->tail];
     const int n = slot->n;
-    int total = 0;
-    const int32_t *meta = reinterpret_cast<const int32_t *>(slot->out_host.ptr);
+    long long total = 0;
     if (n > 0) {
-        OG_CUDA_TRY(cudaEventSynchronize(slot->done));
-        if (slot->fused && meta[2 * n + 1] != 0) {
+        OG_CUDA_TRY(cudaStreamSynchronize(slot->work));
+        const volatile int32_t *meta = reinterpret_cast<const volatile int32_t *>(slot->out_host);
+        if (slot->fused && meta[2 * n] != 0) {
             // Some plane produced more than kCandCap candidates (noise-like input): the fused
             // kernel cannot re-scan a map it never materialised, so this batch is decoded again
             // on the GPU through the materialising path, which selects exactly for any input.
@@ -1082,8 +1299,8 @@ int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offse
                 const int n_in = a.flip ? 2 * a.n : a.n;
                 const size_t hmp_img = (size_t)h->cfg.n_keypoints * a.hgt * a.w;
                 const size_t off_img = (size_t)2 * h->cfg.n_limbs * a.hgt * a.w;
-                OG_TRY(slot->in_hmp.ensure((size_t)n_in * hmp_img));
-                OG_TRY(slot->in_off.ensure((size_t)n_in * off_img));
+                OG_TRY(ensure_tracked(slot->in_hmp, (size_t)n_in * hmp_img, slot));
+                OG_TRY(ensure_tracked(slot->in_off, (size_t)n_in * off_img, slot));
                 OG_TRY(launch_densify(a.hmp_view, slot->in_hmp.ptr, n_in, hmp_img, slot->stream));
                 OG_TRY(launch_densify(a.off_view, slot->in_off.ptr, n_in, off_img, slot->stream));
                 h->launches += 2;
@@ -1092,40 +1309,54 @@ int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offse
             }
             if (a.off_host) {           // the materialising path reads every offset: copy them now
                 const size_t elems = (size_t)(a.flip ? 2 * a.n : a.n) * 2 * h->cfg.n_limbs * a.hgt * a.w;
-                OG_TRY(slot->in_off.ensure(elems));
+                OG_TRY(ensure_tracked(slot->in_off, elems, slot));
                 OG_CUDA_TRY(cudaMemcpyAsync(slot->in_off.ptr, a.off_host, elems * sizeof(float),
                                             cudaMemcpyHostToDevice, slot->stream));
                 a.off = slot->in_off.ptr;
             }
             OG_TRY(decode_features_impl(h, slot, a.hmp, a.off, a.n, a.hgt, a.w, a.hmp_stride,
                                         a.off_stride, a.resize_mode, a.flip, slot->stream, false));
-            OG_CUDA_TRY(cudaEventSynchronize(slot->done));
-            meta = reinterpret_cast<const int32_t *>(slot->out_host.ptr);
+            OG_CUDA_TRY(cudaStreamSynchronize(slot->work));
+            meta = reinterpret_cast<const volatile int32_t *>(slot->out_host);
         }
-        total = meta[2 * n];
-        if (total > slot->capacity_rows) {
-            set_error("internal: %d pose rows exceed the worst-case capacity %d", total, slot->capacity_rows);
-            return OG_ERR_CAPACITY;
+        for (int i = 0; i < n; ++i) total += meta[n + i];
+        if (total > slot->capacity_rows) {       // rare: more persons than the pinned buffer was sized for
+            OG_TRY(regroup_with_full_capacity(h, slot));
+            meta = reinterpret_cast<const volatile int32_t *>(slot->out_host);
+            total = 0;
+            for (int i = 0; i < n; ++i) total += meta[n + i];
+            if (total > slot->capacity_rows) {
+                set_error("internal: %lld pose rows exceed the worst-case capacity %d", total, slot->capacity_rows);
+                return OG_ERR_CAPACITY;
+            }
         }
-        if (total > slot->rows_copied) {     // rare: more persons than the speculative copy covered
-            const size_t row = pose_row_bytes(h);
-            const size_t at = slot->meta_bytes + (size_t)slot->rows_copied * row;
-            OG_CUDA_TRY(cudaMemcpyAsync(slot->out_host.ptr + at, slot->out.ptr + at,
-                                        (size_t)(total - slot->rows_copied) * row,
-                                        cudaMemcpyDeviceToHost, h->aux));
-            OG_CUDA_TRY(cudaStreamSynchronize(h->aux));
-            slot->rows_copied = total;
-        }
-        h->rows_hint = total + total / 2 + 16;      // speculative D2H size of the next batch
-        *offset_host = meta;
-        *count_host = meta + n;
-        *poses_host = reinterpret_cast<const float *>(slot->out_host.ptr + slot->meta_bytes);
+        out->offsets = reinterpret_cast<const int32_t *>(slot->out_host);
+        out->counts = out->offsets + n;
+        out->poses = reinterpret_cast<const float *>(slot->out_host + slot->meta_bytes);
     }
-    *total_rows = total;
+    out->n_images = n;
+    out->total_rows = (int32_t)total;
+    out->n_keypoints = h->cfg.n_keypoints;
     slot->pending = false;
     h->pending -= 1;
     h->fetched_slot = h->tail;
     h->tail = (h->tail + 1) % kSlots;
+    return OG_OK;
+}
+
+int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offset_host,
+                   const int32_t **count_host, int32_t *total_rows) {
+    OG_REQUIRE(h && poses_host && offset_host && count_host && total_rows, "og_fetch_poses: null pointer");
+    og_result r;
+    *poses_host = nullptr;
+    *offset_host = nullptr;
+    *count_host = nullptr;
+    *total_rows = 0;
+    OG_TRY(og_fetch_result(h, &r));
+    *poses_host = r.poses;
+    *offset_host = r.offsets;
+    *count_host = r.counts;
+    *total_rows = r.total_rows;
     return OG_OK;
 }
 
@@ -1149,7 +1380,7 @@ int og_copy_intermediates(og_handle *h, int n, float *det_score_dev, int32_t *de
         OG_CUDA_TRY(cudaMemcpyAsync(det_index_dev, slot->det_index.ptr, dets * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
     const size_t lim = (size_t)n * c.n_limbs * c.topk * OG_LIMB_COLS;
     if (limbs_dev && lim)
-        OG_CUDA_TRY(cudaMemcpyAsync(limbs_dev, h->limbs.ptr, lim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        OG_CUDA_TRY(cudaMemcpyAsync(limbs_dev, slot->limbs.ptr, lim * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return OG_OK;
 }
 
@@ -1170,6 +1401,15 @@ int og_set_zero_copy(og_handle *h, int enable) {
 }
 
 int64_t og_zero_copy_count(const og_handle *h) { return h ? h->zero_copy_calls : 0; }
+
+int og_set_graph(og_handle *h, int enable) {
+    OG_REQUIRE(h, "og_set_graph: null handle");
+    h->graph_enabled = enable != 0;
+    return OG_OK;
+}
+
+int64_t og_graph_replay_count(const og_handle *h) { return h ? h->graph_replays : 0; }
+int64_t og_graph_build_count(const og_handle *h) { return h ? h->graph_builds : 0; }
 
 int og_debug_k3_profile(uint64_t *out16, int reset) {
     OG_REQUIRE(out16, "og_debug_k3_profile: null pointer");

@@ -84,10 +84,12 @@ int launch_nms_candidates(const float *heat, int planes, int h, int w, float thr
                           int64_t *launches);
 // pass 2 alone on candidate lists some other kernel filled; with heat == nullptr a plane
 // with more than kCandCap candidates cannot be re-scanned and raises *overflow_flag.
+// Every plane's counter is left at ZERO for the next call (the lists are per result slot);
+// `clear_word`, when given, is zeroed as well (the fused path's active-block counter).
 int launch_select_topk(const float *heat, int planes, int h, int w, float thre, int k,
-                       const uint32_t *cand_count, const uint64_t *cand_keys, float *out_score,
+                       uint32_t *cand_count, const uint64_t *cand_keys, float *out_score,
                        int32_t *out_index, int32_t *out_count, int32_t *overflow_flag,
-                       cudaStream_t s);
+                       int32_t *clear_word, cudaStream_t s);
 
 // ---- network-resolution maps as the caller holds them ------------------------------
 // Element types: float32 (what the reference decodes, factory.py:59), or bfloat16 / float16
@@ -112,12 +114,19 @@ int launch_densify(const MapView &src, float *dst, int images, size_t per_image,
 
 // Offsets still at network resolution (fused path): K2 samples them bilinearly at the
 // candidate pixels instead of gathering from a materialised full-resolution map.
+// Flip-test tables (config/coco_data.py:119-153), passed to the kernels BY VALUE: they live in
+// the constant bank, so no kernel waits on a dependent global load for them and the handle keeps
+// no device copies.
+struct FlipTablesDev {
+    int8_t kp[OG_MAX_KEYPOINTS];    // heat-map channel of the mirrored image that matches channel c
+    int8_t limb[OG_MAX_LIMBS];      // limb type of the mirrored image that matches limb l
+    uint64_t reserved;              // bit l: limb l is its own mirror image, keep the original offsets
+};
+
 struct OffsetSource {
     MapView maps;                   // [n or 2n][2L][h][w]
     int h, w, scale;                // network resolution and the x scale to decode resolution
     int flip, n;                    // flip: maps = n originals then n mirrored copies
-    const int32_t *limb_flip;       // device tables (flip only)
-    const uint8_t *limb_reserved;
 };
 
 // Optional variants of generate_limbs (collect.py:127-138, 158-165, 213-218 and vector_nd = 4).
@@ -127,11 +136,22 @@ struct LimbExtras {
     int use_jitter;         // --use-jitter-offset
 };
 
+// What K2 hands to K3 besides the limb table (og_prep.cuh); prep == nullptr: scoring only.
+struct PrepOut {
+    int32_t *prep;                  // [n, L, K + 1]
+    float4 *rec;                    // [n, L, K, 3]
+    int32_t *cnt;                   // [n, L]
+    float dist_max;
+    int use_scale;
+    int32_t *clear_word;            // zeroed by the kernel (K3's row allocator), or nullptr
+};
+
 // `offs` = materialised full-resolution offsets, or nullptr with `lowres` set.
 int launch_limb_score(const float *det_score, const int32_t *det_index, const float *offs,
-                      const OffsetSource *lowres, const float *scales, const LimbExtras *extras,
-                      int n, int c, int l, int k, int h, int w, const SkeletonDev &sk, float thre_hmp,
-                      float min_len, float resize_factor, float *out_limbs, cudaStream_t s);
+                      const OffsetSource *lowres, const FlipTablesDev *flips, const float *scales,
+                      const LimbExtras *extras, int n, int c, int l, int k, int h, int w,
+                      const SkeletonDev &sk, float thre_hmp, float min_len, float resize_factor,
+                      float *out_limbs, const PrepOut *prep, cudaStream_t s);
 
 struct ChannelPerm {
     int32_t src[128];
@@ -150,10 +170,14 @@ void fused_scratch(int n, int c, int h, int w, int scale, size_t *flag_bytes, si
 // block_flag: fused_scratch() bytes, ALL ZERO on entry (the kernels leave them zero again);
 // block_list: fused_scratch() ints, n_active: one int
 // `n` images starting at hmp; the mirrored copy of image i is image n_total + i (flip only)
-int launch_fused_candidates(const MapView &hmp, const int32_t *kp_flip_dev, int n, int n_total, int c, int h, int w,
+// `clear_first`: zero the candidate counters / the active-block counter with memsets before the
+// kernels (a caller whose select pass runs on ANOTHER stream); otherwise they must be zero on
+// entry (launch_select_topk leaves them so).
+int launch_fused_candidates(const MapView &hmp, const FlipTablesDev &flips, int n, int n_total, int c, int h, int w,
                             int scale, bool cubic, bool flip, float thre, uint32_t *cand_count,
                             uint64_t *cand_keys, uint8_t *block_flag, int32_t *block_list,
-                            int32_t *n_active, int sm_count, cudaStream_t s, int64_t *launches);
+                            int32_t *n_active, int sm_count, bool clear_first, cudaStream_t s,
+                            int64_t *launches);
 
 struct GroupLaunch {
     int n, c, l, k;
@@ -162,22 +186,30 @@ struct GroupLaunch {
     int use_scale;
     double person_thre;
     int sort_dim;
-    int smem_rows;              // person-table rows kept in shared memory
+    int warp_rows;              // person-table rows of the one-warp-per-image kernel (0 = skip it)
+    int smem_rows;              // person-table rows the CTA kernel keeps in shared memory
     float *slab;                // global person tables, one per image (fallback)
     size_t slab_stride;         // floats between images, multiple of 4
-    int32_t *prep;              // scratch of group_prep_ints() ints: kept limb rows per (image, limb)
+    int32_t *prep;              // group_prep_ints() ints: kept limb rows per (image, limb)
+    float4 *rec;                // group_rec_vec4() float4: the kept rows themselves, compacted
+    int32_t *cnt;               // [n, L] kept rows per (image, limb)
+    int32_t *redo;              // [n] images the warp kernel handed to the CTA kernel
 };
 int read_k3_profile(unsigned long long *out16, bool reset);
 size_t group_smem_bytes(const GroupLaunch &g);
+size_t group_warp_smem_bytes(const GroupLaunch &g);
 size_t group_prep_ints(const GroupLaunch &g);
-int prepare_group_kernel(size_t smem_bytes);
-int launch_group(const GroupLaunch &g, const float *limbs, float *out_poses, int capacity_rows,
-                 int32_t *out_offset, int32_t *out_count, int32_t *out_total, cudaStream_t s);
+size_t group_rec_vec4(const GroupLaunch &g);
+int prepare_group_kernel(size_t smem_bytes, size_t warp_smem_bytes);
+// `prepared`: prep / rec / cnt already hold the rows (K2 wrote them); else the stand-alone
+// prepare kernel runs first.  *out_total must be zero on entry.
+int launch_group(const GroupLaunch &g, const float *limbs, bool prepared, float *out_poses,
+                 int capacity_rows, int32_t *out_offset, int32_t *out_count, int32_t *out_total,
+                 cudaStream_t s, int64_t *launches);
 
 int launch_scored_offset(const float *hmp, const float *off, int n, int c, int l, int h, int w,
                          int ksize, const SkeletonDev &sk, float *out, cudaStream_t s);
-int launch_flip_fuse(const float *hmp2n, const float *off2n, const int32_t *kp_flip_dev,
-                     const int32_t *limb_flip_dev, const uint8_t *limb_reserved_dev,
+int launch_flip_fuse(const float *hmp2n, const float *off2n, const FlipTablesDev &flips,
                      int n, int c, int l, int h, int w, float *out_hmp, float *out_off,
                      cudaStream_t s);
 int launch_resize(const float *in, float *out, int planes, int h, int w, int scale, int mode,

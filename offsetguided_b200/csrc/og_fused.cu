@@ -76,7 +76,7 @@ __device__ __forceinline__ unsigned abs_bits(float v) { return __float_as_uint(f
 // one thread per (plane, 8-row band, 4-cell column group)
 template <typename T, bool kFlip, bool kVec>
 __global__ void __launch_bounds__(kScanThreads)
-amax_scan_kernel(const T *__restrict__ hmp, size_t img_stride, const int32_t *__restrict__ kp_flip,
+amax_scan_kernel(const T *__restrict__ hmp, size_t img_stride, const FlipTablesDev ft,
                  int N, int C, int h, int w, int block_w, int halo, float limit,
                  uint8_t *__restrict__ block_flag, long long total) {
     const long long idx = (long long)blockIdx.x * kScanThreads + threadIdx.x;
@@ -90,7 +90,7 @@ amax_scan_kernel(const T *__restrict__ hmp, size_t img_stride, const int32_t *__
     const int n = plane / C, c = plane - n * C;
     const T *a = hmp + (size_t)n * img_stride + (size_t)c * h * w;
     const T *b = nullptr;
-    if (kFlip) b = hmp + (size_t)(N + n) * img_stride + (size_t)kp_flip[c] * h * w;
+    if (kFlip) b = hmp + (size_t)(N + n) * img_stride + (size_t)ft.kp[c] * h * w;
     const int y0 = band * 2 * kSub, x0 = sx * kSub;
     const int bxs = (w + block_w - 1) / block_w, bys = (h + kBlockCellsH - 1) / kBlockCellsH;
     uint8_t *flags = block_flag + (size_t)plane * bys * bxs;
@@ -152,7 +152,7 @@ amax_scan_kernel(const T *__restrict__ hmp, size_t img_stride, const int32_t *__
 // entry = {plane (image * C + channel), image, block row << 16 | block column,
 //          channel | channel of the mirrored map << 16}
 __global__ void __launch_bounds__(256)
-block_list_kernel(uint8_t *__restrict__ block_flag, const int32_t *__restrict__ kp_flip, int C,
+block_list_kernel(uint8_t *__restrict__ block_flag, const FlipTablesDev ft, int C,
                   int flip, int bxs, int bys, long long total, int4 *__restrict__ block_list,
                   int32_t *__restrict__ n_active) {
     __shared__ int s_warp[8];
@@ -183,7 +183,7 @@ block_list_kernel(uint8_t *__restrict__ block_flag, const int32_t *__restrict__ 
         const int by = (int)((g / bxs) % bys);
         const int plane = (int)(g / ((long long)bxs * bys));
         const int n = plane / C, c = plane - n * C;
-        const int cb = flip ? kp_flip[c] : c;
+        const int cb = flip ? (int)ft.kp[c] : c;
         block_list[s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))] =
             make_int4(plane, n, (by << 16) | bx, c | (cb << 16));
     }
@@ -457,12 +457,14 @@ void fused_scratch(int n, int c, int h, int w, int scale, size_t *flag_bytes, si
 
 namespace {
 template <typename T>
-int launch_fused_t(const T *hmp, size_t img_stride, const int32_t *kp_flip_dev, int n, int n_total,
+int launch_fused_t(const T *hmp, size_t img_stride, const FlipTablesDev &kp_flip_dev, int n, int n_total,
                    int c, int h, int w, int scale, bool cubic, bool flip, float thre,
                    uint32_t *cand_count, uint64_t *cand_keys, uint8_t *block_flag, int32_t *block_list,
-                   int32_t *n_active, int sm_count, cudaStream_t s, int64_t *launches) {
-    OG_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t) * (size_t)n * c, s));
-    OG_CUDA_TRY(cudaMemsetAsync(n_active, 0, sizeof(int32_t), s));
+                   int32_t *n_active, int sm_count, bool clear_first, cudaStream_t s, int64_t *launches) {
+    if (clear_first) {
+        OG_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t) * (size_t)n * c, s));
+        OG_CUDA_TRY(cudaMemsetAsync(n_active, 0, sizeof(int32_t), s));
+    }
 
     const int sxs = (w + kSub - 1) / kSub, bands = (h + 2 * kSub - 1) / (2 * kSub);
     const long long scan_threads = (long long)n * c * bands * sxs;
@@ -501,11 +503,11 @@ int launch_fused_t(const T *hmp, size_t img_stride, const int32_t *kp_flip_dev, 
 }
 }  // namespace
 
-int launch_fused_candidates(const MapView &hmp, const int32_t *kp_flip_dev, int n, int n_total, int c,
+int launch_fused_candidates(const MapView &hmp, const FlipTablesDev &kp_flip_dev, int n, int n_total, int c,
                             int h, int w, int scale, bool cubic, bool flip, float thre,
                             uint32_t *cand_count, uint64_t *cand_keys, uint8_t *block_flag,
-                            int32_t *block_list, int32_t *n_active, int sm_count, cudaStream_t s,
-                            int64_t *launches) {
+                            int32_t *block_list, int32_t *n_active, int sm_count, bool clear_first,
+                            cudaStream_t s, int64_t *launches) {
     if (n == 0) return OG_OK;
     if (!fused_supported(n, c, scale, h, w)) {
         set_error("fused K1: scale %d / %d x %d maps are outside the supported range", scale, h, w);
@@ -514,14 +516,14 @@ int launch_fused_candidates(const MapView &hmp, const int32_t *kp_flip_dev, int 
     if (hmp.dtype == OG_DTYPE_BF16)
         return launch_fused_t(static_cast<const __nv_bfloat16 *>(hmp.ptr), hmp.image_stride, kp_flip_dev, n,
                               n_total, c, h, w, scale, cubic, flip, thre, cand_count, cand_keys, block_flag,
-                              block_list, n_active, sm_count, s, launches);
+                              block_list, n_active, sm_count, clear_first, s, launches);
     if (hmp.dtype == OG_DTYPE_F16)
         return launch_fused_t(static_cast<const __half *>(hmp.ptr), hmp.image_stride, kp_flip_dev, n,
                               n_total, c, h, w, scale, cubic, flip, thre, cand_count, cand_keys, block_flag,
-                              block_list, n_active, sm_count, s, launches);
+                              block_list, n_active, sm_count, clear_first, s, launches);
     return launch_fused_t(static_cast<const float *>(hmp.ptr), hmp.image_stride, kp_flip_dev, n, n_total, c,
                           h, w, scale, cubic, flip, thre, cand_count, cand_keys, block_flag, block_list,
-                          n_active, sm_count, s, launches);
+                          n_active, sm_count, clear_first, s, launches);
 }
 
 // dense float32 copy of strided / bf16 maps (only the exact redo of an overflowed batch needs it)

@@ -1,12 +1,23 @@
 // K3 — greedy limb-ordered keypoint grouping (reference decoder/group.py:39-240, which
-// runs per image in a CPU process pool).  Two kernels:
+// runs per image in a CPU process pool).  Three kernels:
 //
-//   group_prepare_kernel   one CTA per (limb type, image): the part of every limb step that
+//   prepare (og_prep.cuh)  one CTA per (limb type, image): the part of every limb step that
 //       depends on the limb rows only — distance / border gate (group.py:64-76), sort by limb
 //       score (canonical stable order) and "best row per to-joint id" (group.py:222-240).
-//       It writes the kept row indices in order; all L x N instances run in parallel, off the
-//       sequential path.
-//   group_kernel           one CTA per image walks the skeleton in the reference's limb order.
+//       All L x N instances run in parallel, off the sequential path.  On the decode path it
+//       is the tail of K2's CTA (og_limbs.cu); group_prepare_kernel is the stand-alone form.
+//   group_warp_kernel      ONE WARP per image walks the skeleton in the reference's limb order
+//       over the compacted kept rows.  The walk is latency-bound (a few hundred pair tests per
+//       limb type), so what counts is the length of the dependent chain: lane = person, every
+//       person row is read and written by its own lane only, the cross-lane facts (how many
+//       persons matched limb j, did any replacement pass) are warp votes, and the phases are
+//       separated by __syncwarp instead of CTA barriers.  Loops are kept ROLLED: a lone warp
+//       has nobody to hide instruction fetches behind, and the unrolled body (58 KB of SASS)
+//       ran 5x slower than its dependent chain.  The person table is `warp_rows` rows
+//       of shared memory (26 KB for 64 rows x 17 joints), so eight images share an SM.
+//   group_kernel           one 256-thread CTA per image, table in shared memory or in a global
+//       slab of L*K rows: the images whose table outgrew the warp kernel's (noise inputs),
+//       flagged by it in `redo`; every other CTA of this launch exits at once.
 //
 // The person table lives in shared memory as three planes per (person row, joint):
 //   ids   int32   global keypoint id (-1 = unset)          pose column 5
@@ -30,6 +41,7 @@
 // the same CTA restarts that image with the table in a global slab of L*K rows, which cannot
 // overflow (every new person consumes one limb row).
 #include "og_common.cuh"
+#include "og_prep.cuh"
 
 #include <mutex>
 
@@ -68,6 +80,7 @@ struct GroupArgs {
     double person_thre;
     int sort_dim;
     int smem_rows;
+    int warp_rows;
     float *slab;     // per image: xyvs float4[PMAX*C], score float[PMAX*C], ids int[PMAX*C]
     size_t slab_stride;
 };
@@ -75,65 +88,25 @@ struct GroupArgs {
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------
-// prepare: gate + sort + dedup of one limb type's K rows.
-// prep[(image * L + limb) * (K + 1)] = kept row indices in order, then their count at [K].
+// prepare, stand-alone (limb tables supplied by the caller; the decode path runs the same
+// code at the end of K2): one CTA per (limb type, image)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPrepThreads)
 group_prepare_kernel(const float *__restrict__ limbs, int L, int K, float dist_max, int use_scale,
-                     int32_t *__restrict__ prep) {
-    __shared__ float s_conn[OG_MAX_TOPK * OG_LIMB_COLS];
-    __shared__ float s_sc[OG_MAX_TOPK];
-    __shared__ int s_id2[OG_MAX_TOPK];
-    __shared__ int s_sorted[OG_MAX_TOPK];
-    __shared__ uint8_t s_valid[OG_MAX_TOPK];
-    __shared__ uint8_t s_keep[OG_MAX_TOPK];
+                     int32_t *__restrict__ prep, float4 *__restrict__ rec, int32_t *__restrict__ cnt) {
+    __shared__ PrepShared sh;
     const int tid = threadIdx.x;
     const size_t inst = (size_t)blockIdx.y * L + blockIdx.x;          // (image, limb type)
-    const float *src = limbs + inst * K * OG_LIMB_COLS;
-    int32_t *out = prep + inst * (K + 1);
-    for (int i = tid; i < K * OG_LIMB_COLS; i += kPrepThreads) s_conn[i] = __ldg(src + i);
-    __syncthreads();
-    // gate (group.py:64-76): distance test and both endpoints strictly inside the image
-    bool valid = false;
-    float sc = 0.0f;
+    float r[OG_LIMB_COLS];
+#pragma unroll
+    for (int i = 0; i < OG_LIMB_COLS; ++i) r[i] = 0.0f;
     if (tid < K) {
-        const float *r = s_conn + tid * OG_LIMB_COLS;
-        float lim = dist_max;
-        if (use_scale) lim = (r[12] != r[12]) ? r[12] : fmaxf(dist_max, r[12]);
-        valid = (r[8] < lim) && (r[0] > 0.f) && (r[4] > 0.f) && (r[3] > 0.f) && (r[1] > 0.f) &&
-                (r[10] == r[10]);
-        sc = r[10];
-        s_sc[tid] = sc;
-        s_valid[tid] = valid ? 1 : 0;
+        const float *src = limbs + (inst * K + tid) * OG_LIMB_COLS;
+#pragma unroll
+        for (int i = 0; i < OG_LIMB_COLS; ++i) r[i] = __ldg(src + i);
     }
-    const int nvalid = __syncthreads_count(valid);
-    // rank = number of valid rows that precede this one: limb score desc, row asc
-    // (group.py:232 with the canonical stable order)
-    if (valid) {
-        int rank = 0;
-        for (int j = 0; j < K; ++j) {
-            const float sj = s_sc[j];
-            rank += (s_valid[j] && (sj > sc || (sj == sc && j < tid))) ? 1 : 0;
-        }
-        s_sorted[rank] = tid;
-        s_id2[rank] = (int)s_conn[tid * OG_LIMB_COLS + 7];
-    }
-    __syncthreads();
-    // keep the best row per distinct to-joint id (group.py:233-239)
-    bool keep = false;
-    if (tid < nvalid) {
-        const int t = s_id2[tid];
-        keep = true;
-        for (int r2 = 0; r2 < tid; ++r2) keep = keep && (s_id2[r2] != t);
-        s_keep[tid] = keep ? 1 : 0;
-    }
-    const int kk = __syncthreads_count(keep);
-    if (keep) {
-        int pos = 0;
-        for (int r2 = 0; r2 < tid; ++r2) pos += s_keep[r2];
-        out[pos] = s_sorted[tid];
-    }
-    if (tid == 0) out[K] = kk;
+    prepare_limb_rows(r, tid, K, dist_max, use_scale, sh, prep + inst * (K + 1), rec + inst * K * 3,
+                      cnt + inst);
 }
 
 // ---------------------------------------------------------------------------
@@ -224,8 +197,10 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) 
 __global__ void __launch_bounds__(kGroupThreads)
 group_kernel(GroupArgs a, const float *__restrict__ limbs, const int32_t *__restrict__ prep,
              float *__restrict__ out_poses, int capacity_rows, int32_t *__restrict__ out_offset,
-             int32_t *__restrict__ out_count, int32_t *__restrict__ out_total) {
+             int32_t *__restrict__ out_count, int32_t *__restrict__ out_total,
+             const int32_t *__restrict__ redo) {
     extern __shared__ __align__(16) unsigned char smem[];
+    if (redo != nullptr && redo[blockIdx.x] == 0) return;       // the warp kernel finished this image
 #ifdef OG_K3_PROFILE
     long long prof_acc[10] = {0};
     long long prof_last = clock64();
@@ -543,6 +518,550 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, const int32_t *__rest
 #endif
 }
 
+// ---------------------------------------------------------------------------
+// grouping, one warp per image
+// ---------------------------------------------------------------------------
+struct WarpLayout {
+    size_t xyvs, score, ids, rec, k_int, p_f64, p_i32, p_i16, p_u8, cnt, total;
+};
+
+// Person-table rows are CS entries apart, CS = the multiple of 4 >= C with CS % 8 == 4: a row of
+// ids is a few aligned 128-bit words (the pair test of the merge step compares whole rows), the
+// quarter-warps of such loads hit distinct banks, and column accesses of 32 different rows
+// conflict at most 4-way.  Pad columns hold "unset".
+__host__ __device__ inline int warp_row_stride(int C) {
+    int cs = (C + 3) / 4 * 4;
+    if (cs % 8 == 0) cs += 4;
+    return cs;
+}
+
+__host__ __device__ inline WarpLayout make_warp_layout(int C, int L, int K, int rows) {
+    const size_t cs = (size_t)warp_row_stride(C);
+    WarpLayout lo;
+    size_t at = 0;
+    lo.xyvs = at;  at += (size_t)rows * cs * 16;
+    lo.score = at; at += (size_t)rows * cs * 4;
+    lo.ids = at;   at += (size_t)rows * cs * 4;
+    at = align_up(at, 16);
+    lo.rec = at;   at += 2 * (size_t)K * 48;            // kept rows of two limb types (double buffer)
+    lo.k_int = at; at += (size_t)3 * K * 4;             // per kept row: persons matched at one / both ends, new list
+    at = align_up(at, 8);
+    lo.p_f64 = at; at += (size_t)rows * 8;              // person scores
+    lo.p_i32 = at; at += (size_t)2 * rows * 4;          // merge partner / kept list, rank
+    lo.p_i16 = at; at += align_up((size_t)rows * 2, 4); // order: logical position -> table row
+    lo.p_u8 = at;  at += align_up((size_t)rows, 4);     // deleted marks
+    lo.cnt = at;   at += (size_t)L * 4;
+    lo.total = align_up(at, 16);
+    return lo;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem_src));
+}
+
+// e / d for 0 <= e < 65536, 1 <= d <= 256 without an integer division: (e + 0.5) / d lies at
+// least 0.5 / d away from an integer, far more than the error of the approximate reciprocal
+__device__ __forceinline__ int small_div(int e, float inv_d) {
+    return __float2int_rz(((float)e + 0.5f) * inv_d);
+}
+
+__global__ void __launch_bounds__(32)
+group_warp_kernel(GroupArgs a, const float4 *__restrict__ rec, const int32_t *__restrict__ cnt,
+                  float *__restrict__ out_poses, int capacity_rows, int32_t *__restrict__ out_offset,
+                  int32_t *__restrict__ out_count, int32_t *__restrict__ out_total,
+                  int32_t *__restrict__ redo) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr unsigned kAll = 0xffffffffu;
+    const int C = a.C, L = a.L, K = a.K, R = a.warp_rows;
+    const int CS = warp_row_stride(C), NV = CS / 4;
+    const WarpLayout lo = make_warp_layout(C, L, K, R);
+#ifdef OG_K3_PROFILE
+    long long prof_acc[10] = {0};
+    long long prof_last = clock64();
+#endif
+    const int lane = threadIdx.x;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int img = blockIdx.x;
+
+    // every pointer below is derived from `smem` by plain arithmetic, so the accesses compile to
+    // LDS / STS (a pointer picked out of an array of pointers degrades to generic loads)
+    float4 *xyvs = reinterpret_cast<float4 *>(smem + lo.xyvs);
+    float *score = reinterpret_cast<float *>(smem + lo.score);
+    int *ids = reinterpret_cast<int *>(smem + lo.ids);
+    float4 *s_rec0 = reinterpret_cast<float4 *>(smem + lo.rec);
+    int *s_n1 = reinterpret_cast<int *>(smem + lo.k_int);
+    int *s_n2 = s_n1 + K;
+    int *s_new = s_n2 + K;
+    double *s_ps = reinterpret_cast<double *>(smem + lo.p_f64);
+    int *s_pa = reinterpret_cast<int *>(smem + lo.p_i32);     // per person: winning limb (one end known) / merge partner / kept list
+    int *s_pb = s_pa + R;                                     // per person: winning limb (both ends known) / rank
+    int16_t *s_order = reinterpret_cast<int16_t *>(smem + lo.p_i16);
+    uint8_t *s_del = smem + lo.p_u8;
+    int *s_cnt = reinterpret_cast<int *>(smem + lo.cnt);
+
+    const float4 *rec_img = rec + (size_t)img * L * K * 3;
+#pragma unroll 1
+    for (int l = lane; l < L; l += 32) s_cnt[l] = __ldg(cnt + (size_t)img * L + l);
+    __syncwarp();
+
+    // the kept rows of limb type li + 1 arrive (cp.async) while type li is processed
+    auto fetch_rows = [&](int li) {
+        const int n16 = s_cnt[li] * 3;
+        float4 *dst = s_rec0 + (size_t)(li & 1) * K * 3;
+        const float4 *src = rec_img + (size_t)li * K * 3;
+#pragma unroll 1
+        for (int i = lane; i < n16; i += 32) cp_async16(dst + i, src + i);
+        asm volatile("cp.async.commit_group;");
+    };
+    fetch_rows(0);
+
+    int mm = 0, nalloc = 0;
+#pragma unroll 1
+    for (int li = 0; li < L; ++li) {
+        const int kk = s_cnt[li];
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();          // rows of type li have landed; everybody is done with type li - 1
+        if (li + 1 < L) fetch_rows(li + 1);
+        OG_K3_PROF(0);
+        if (kk == 0) continue;                                             // group.py:84-85
+        const int jf = a.sk.from[li], jt = a.sk.to[li];
+        const float4 *s_rec = s_rec0 + (size_t)(li & 1) * K * 3;
+        if (mm <= 32 && kk <= 32) {
+            // ================= register path: at most 32 persons and 32 kept rows ==============
+            // lane = person AND lane = kept row.  The limb step is a chain of dependent steps, so
+            // what it costs is the length of that chain: here the table is touched twice (the
+            // person's two joints before the match, its id row before the merge test) and all
+            // cross-lane traffic is shuffles, votes and MATCH instead of shared-memory atomics.
+            float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+            if (lane < kk) {
+                r0 = s_rec[lane * 3];
+                r1 = s_rec[lane * 3 + 1];
+                r2 = s_rec[lane * 3 + 2];
+            }
+            const int my_id1 = __float_as_int(r0.x), my_id2 = __float_as_int(r0.y);
+            const bool live = lane < mm;
+            const int my_ord = live ? (int)s_order[lane] : 0;
+            const int row = my_ord * CS;
+            const int at_f = row + jf, at_t = row + jt;
+            int id_f = 0, id_t = 0;
+            float sc_f = 0.f, sc_t = 0.f;
+            if (live) {
+                id_f = ids[at_f];
+                id_t = ids[at_t];
+                sc_f = score[at_f];
+                sc_t = score[at_t];
+            }
+            // ---- match (group.py:87-109): every lane walks the kept rows; the last match wins
+            int pk1 = -1, pk2 = -1, n1 = 0, n2 = 0, pk1_i1 = 0, pk1_i2 = 0;
+            float pk1_sc = 0.f, pk2_sc = 0.f;
+#pragma unroll 2
+            for (int j = 0; j < kk; ++j) {
+                const int i1 = __shfl_sync(kAll, my_id1, j), i2 = __shfl_sync(kAll, my_id2, j);
+                const float sc = __shfl_sync(kAll, r0.z, j);
+                const int ms = live ? ((id_f == i1 ? 1 : 0) + (id_t == i2 ? 1 : 0)) : 0;
+                const unsigned b2 = __ballot_sync(kAll, ms == 2), b1 = __ballot_sync(kAll, ms == 1);
+                if (lane == j) {
+                    n2 = __popc(b2);
+                    n1 = __popc(b1);
+                }
+                const bool rep = (sc > sc_t) || (sc > sc_f);
+                if (ms == 2 && rep) {
+                    pk2 = j;
+                    pk2_sc = sc;
+                }
+                if (ms == 1 && rep) {
+                    pk1 = j;
+                    pk1_sc = sc;
+                    pk1_i1 = i1;
+                    pk1_i2 = i2;
+                }
+            }
+            const bool any_p2 = __any_sync(kAll, pk2 >= 0), any_p1 = __any_sync(kAll, pk1 >= 0);
+            OG_K3_PROF(1);
+            // ---- apply (group.py:114-135): both ends known, then one end known
+            if (pk2 >= 0) {
+                sc_f = fmaxf(pk2_sc, sc_f);
+                sc_t = fmaxf(pk2_sc, sc_t);
+            }
+            if (pk1 >= 0) {
+                ids[at_f] = pk1_i1;
+                ids[at_t] = pk1_i2;
+                xyvs[at_f] = s_rec[pk1 * 3 + 1];
+                xyvs[at_t] = s_rec[pk1 * 3 + 2];
+                sc_f = fmaxf(pk1_sc, sc_f);
+                sc_t = fmaxf(pk1_sc, sc_t);
+            }
+            if (pk1 >= 0 || pk2 >= 0) {
+                score[at_f] = sc_f;
+                score[at_t] = sc_t;
+            }
+            __syncwarp();
+            OG_K3_PROF(2);
+            // ---- merge (group.py:140-155).  Per joint column, MATCH gives every lane the set of
+            //      persons holding the same keypoint id; bit-sliced counters add these sets up over
+            //      the columns, and the persons sharing EXACTLY two ids fall out as one mask per lane.
+            int mm_after = mm;
+            if (mm >= 2) {
+                unsigned ones = 0u, twos = 0u, fours = 0u, over = 0u;
+                auto add_column = [&](int v) {
+                    unsigned m = __match_any_sync(kAll, v);
+                    m = (v == -1) ? 0u : (m & ~(1u << lane));
+                    const unsigned c0 = ones & m;
+                    ones ^= m;
+                    const unsigned c1 = twos & c0;
+                    twos ^= c0;
+                    over |= fours & c1;
+                    fours ^= c1;
+                };
+                if (NV == 5) {
+                    int4 x[5];
+#pragma unroll
+                    for (int v = 0; v < 5; ++v)
+                        x[v] = live ? reinterpret_cast<const int4 *>(ids + row)[v] : make_int4(-1, -1, -1, -1);
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) {
+                        add_column(x[v].x);
+                        add_column(x[v].y);
+                        add_column(x[v].z);
+                        add_column(x[v].w);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < C; ++c) add_column(live ? ids[row + c] : -1);
+                }
+                const unsigned two_shared = twos & ~ones & ~fours & ~over;
+                OG_K3_PROF(4);
+                if (__any_sync(kAll, two_shared != 0u)) {
+                    // the relation is symmetric: q is deleted iff it shares two ids with a smaller p;
+                    // a surviving p takes the element-wise maximum with its LARGEST partner
+                    const bool del = (two_shared & lt_mask) != 0u;
+                    const int partner = two_shared ? 31 - __clz(two_shared) : -1;
+                    if (live && !del && partner > lane) {
+                        const int rb = (int)s_order[partner] * CS;
+#pragma unroll 1
+                        for (int c = 0; c < C; ++c) {
+                            ids[row + c] = max(ids[row + c], ids[rb + c]);
+                            score[row + c] = fmaxf(score[row + c], score[rb + c]);
+                            xyvs[row + c] = max4(xyvs[row + c], xyvs[rb + c]);
+                        }
+                    }
+                    const bool keep = live && !del;
+                    const unsigned kb = __ballot_sync(kAll, keep);
+                    __syncwarp();
+                    if (keep) s_order[__popc(kb & lt_mask)] = (int16_t)my_ord;
+                    mm_after = __popc(kb);
+                }
+            }
+            OG_K3_PROF(5);
+            // ---- new persons (group.py:166-177), lane = kept row
+            const int w2 = any_p2 ? -1 : 2, w1 = any_p1 ? -1 : 1;
+            const bool isnew = lane < kk && (n2 * w2 + n1 * w1 == 0);
+            const unsigned nb = __ballot_sync(kAll, isnew);
+            const int nnew = __popc(nb);
+            if (nalloc + nnew > R) {
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                if (lane == 0) redo[img] = 1;
+                return;
+            }
+            if (isnew) {
+                const int q = __popc(nb & lt_mask);
+                const int base = (nalloc + q) * CS;
+                const int4 unset_i = make_int4(-1, -1, -1, -1);
+                const float4 unset_f = make_float4(-1.f, -1.f, -1.f, -1.f);
+#pragma unroll 1
+                for (int v = 0; v < NV; ++v) {
+                    reinterpret_cast<int4 *>(ids + base)[v] = unset_i;
+                    reinterpret_cast<float4 *>(score + base)[v] = unset_f;
+                }
+#pragma unroll 1
+                for (int c = 0; c < CS; ++c) xyvs[base + c] = unset_f;
+                ids[base + jf] = my_id1;
+                ids[base + jt] = my_id2;
+                score[base + jf] = r0.z;
+                score[base + jt] = r0.z;
+                xyvs[base + jf] = r1;
+                xyvs[base + jt] = r2;
+                s_order[mm_after + q] = (int16_t)(nalloc + q);
+            }
+            nalloc += nnew;
+            mm = mm_after + nnew;
+            OG_K3_PROF(6);
+            continue;
+        }
+        // ================= general path: any table size, shared-memory work arrays =============
+#pragma unroll 1
+        for (int j = lane; j < kk; j += 32) {
+            s_n1[j] = 0;
+            s_n2[j] = 0;
+        }
+#pragma unroll 1
+        for (int m = lane; m < mm; m += 32) {
+            s_pa[m] = -1;
+            s_pb[m] = -1;
+        }
+        __syncwarp();
+
+        // ---- match persons x kept limbs on the pre-update table (group.py:87-109), one lane per
+        //      pair: of the limbs that match a person the LAST one wins (fancy-index scatter in
+        //      row-major pair order = atomicMax over the pair lanes)
+        {
+            const float inv_kk = __frcp_rn((float)kk);
+#pragma unroll 1
+            for (int e = lane; e < mm * kk; e += 32) {
+                const int m = small_div(e, inv_kk), j = e - m * kk;
+                const int row = (int)s_order[m] * CS;
+                const float4 r0 = s_rec[j * 3];
+                const int ms = (ids[row + jf] == __float_as_int(r0.x) ? 1 : 0) +
+                               (ids[row + jt] == __float_as_int(r0.y) ? 1 : 0);
+                if (ms == 0) continue;
+                const bool rep = (r0.z > score[row + jt]) || (r0.z > score[row + jf]);
+                if (ms == 2) {
+                    atomicAdd(&s_n2[j], 1);
+                    if (rep) atomicMax(&s_pb[m], j);
+                } else {
+                    atomicAdd(&s_n1[j], 1);
+                    if (rep) atomicMax(&s_pa[m], j);
+                }
+            }
+        }
+        __syncwarp();
+        OG_K3_PROF(1);
+        // ---- apply, lane = person: both ends known (group.py:114-119), then one end known
+        //      (:124-135); the slots are re-armed for the merge step on the way
+        bool any_p1 = false, any_p2 = false;
+#pragma unroll 1
+        for (int mb = 0; mb < mm; mb += 32) {
+            const int m = mb + lane;
+            int pk1 = -1, pk2 = -1;
+            if (m < mm) {
+                pk1 = s_pa[m];
+                pk2 = s_pb[m];
+                s_pa[m] = -1;
+                s_del[m] = 0;
+                const int row = (int)s_order[m] * CS;
+                const int at_f = row + jf, at_t = row + jt;
+                if (pk2 >= 0) {
+                    const float sc = s_rec[pk2 * 3].z;
+                    score[at_f] = fmaxf(sc, score[at_f]);
+                    score[at_t] = fmaxf(sc, score[at_t]);
+                }
+                if (pk1 >= 0) {
+                    const float4 r0 = s_rec[pk1 * 3];
+                    ids[at_f] = __float_as_int(r0.x);
+                    ids[at_t] = __float_as_int(r0.y);
+                    xyvs[at_f] = s_rec[pk1 * 3 + 1];
+                    xyvs[at_t] = s_rec[pk1 * 3 + 2];
+                    score[at_f] = fmaxf(r0.z, score[at_f]);
+                    score[at_t] = fmaxf(r0.z, score[at_t]);
+                }
+            }
+            any_p2 = any_p2 || __any_sync(kAll, pk2 >= 0);
+            any_p1 = any_p1 || __any_sync(kAll, pk1 >= 0);
+        }
+        __syncwarp();
+        OG_K3_PROF(2);
+
+        // ---- merge persons sharing exactly two keypoint ids (group.py:140-155), one lane per
+        //      pair p < q (pair e = q (q - 1) / 2 + p); the largest partner of p wins
+        int mm_after = mm;
+        if (mm >= 2) {
+            bool found = false;
+            const int npairs = mm * (mm - 1) / 2;
+#pragma unroll 1
+            for (int e = lane; e < npairs; e += 32) {
+                int q = __float2int_rz((__fsqrt_rn(8.0f * (float)e + 1.0f) + 1.0f) * 0.5f);
+                if (q * (q - 1) / 2 > e) --q;
+                else if ((q + 1) * q / 2 <= e) ++q;
+                const int p = e - q * (q - 1) / 2;
+                const int4 *ia = reinterpret_cast<const int4 *>(ids + (int)s_order[p] * CS);
+                const int4 *ib = reinterpret_cast<const int4 *>(ids + (int)s_order[q] * CS);
+                int shared_ids = 0;
+                auto count4 = [&](const int4 &x, const int4 &y) {
+                    shared_ids += ((x.x != -1 && x.x == y.x) ? 1 : 0) + ((x.y != -1 && x.y == y.y) ? 1 : 0) +
+                                  ((x.z != -1 && x.z == y.z) ? 1 : 0) + ((x.w != -1 && x.w == y.w) ? 1 : 0);
+                };
+                if (NV == 5) {                      // 17 (COCO) and 14 (CrowdPose) keypoints: ten loads in flight
+                    int4 x[5], y[5];
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) {
+                        x[v] = ia[v];
+                        y[v] = ib[v];
+                    }
+#pragma unroll
+                    for (int v = 0; v < 5; ++v) count4(x[v], y[v]);
+                } else {
+#pragma unroll 1
+                    for (int v = 0; v < NV; ++v) count4(ia[v], ib[v]);
+                }
+                if (shared_ids == 2) {
+                    atomicMax(&s_pa[p], q);
+                    s_del[q] = 1;
+                    found = true;
+                }
+            }
+            __syncwarp();
+            OG_K3_PROF(4);
+            if (__any_sync(kAll, found)) {
+#pragma unroll 1
+                for (int p = lane; p < mm; p += 32) {
+                    const int q = s_pa[p];
+                    if (q < 0 || s_del[p]) continue;          // deleted rows are never read again
+                    const int ra = (int)s_order[p] * CS, rb = (int)s_order[q] * CS;
+#pragma unroll 1
+                    for (int c = 0; c < C; ++c) {
+                        ids[ra + c] = max(ids[ra + c], ids[rb + c]);
+                        score[ra + c] = fmaxf(score[ra + c], score[rb + c]);
+                        xyvs[ra + c] = max4(xyvs[ra + c], xyvs[rb + c]);
+                    }
+                }
+                __syncwarp();
+                int kept = 0;                                  // compact the order list in place
+#pragma unroll 1
+                for (int mb = 0; mb < mm; mb += 32) {
+                    const int m = mb + lane;
+                    const bool keep = m < mm && s_del[m] == 0;
+                    const int16_t row = keep ? s_order[m] : (int16_t)0;
+                    const unsigned ballot = __ballot_sync(kAll, keep);
+                    __syncwarp();
+                    if (keep) s_order[kept + __popc(ballot & lt_mask)] = row;
+                    kept += __popc(ballot);
+                }
+                mm_after = kept;
+                __syncwarp();
+            }
+        }
+        OG_K3_PROF(5);
+        // ---- unclaimed limbs start new persons (group.py:166-177): column-sum rule with its
+        //      (-1) + (+1) cancellation
+        const int w2 = any_p2 ? -1 : 2, w1 = any_p1 ? -1 : 1;
+        int nnew = 0;
+#pragma unroll 1
+        for (int j0 = 0; j0 < kk; j0 += 32) {
+            const int j = j0 + lane;
+            const bool isnew = j < kk && (s_n2[j] * w2 + s_n1[j] * w1 == 0);
+            const unsigned ballot = __ballot_sync(kAll, isnew);
+            if (isnew) s_new[nnew + __popc(ballot & lt_mask)] = j;
+            nnew += __popc(ballot);
+        }
+        if (nalloc + nnew > R) {            // warp-uniform: the CTA kernel redoes this image
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            if (lane == 0) redo[img] = 1;
+            return;
+        }
+        if (nnew > 0) {
+            __syncwarp();
+            const float inv_cs = __frcp_rn((float)CS);
+#pragma unroll 1
+            for (int e = lane; e < nnew * CS; e += 32) {        // one lane per (new person, column); pad columns stay "unset"
+                const int q = small_div(e, inv_cs), c = e - q * CS;
+                const int j = s_new[q];
+                const int at = (nalloc + q) * CS + c;
+                if (c == jt) {
+                    const float4 r0 = s_rec[j * 3];
+                    ids[at] = __float_as_int(r0.y);
+                    xyvs[at] = s_rec[j * 3 + 2];
+                    score[at] = r0.z;
+                } else if (c == jf) {
+                    const float4 r0 = s_rec[j * 3];
+                    ids[at] = __float_as_int(r0.x);
+                    xyvs[at] = s_rec[j * 3 + 1];
+                    score[at] = r0.z;
+                } else {
+                    ids[at] = -1;
+                    xyvs[at] = make_float4(-1.f, -1.f, -1.f, -1.f);
+                    score[at] = -1.0f;
+                }
+                if (c == 0) s_order[mm_after + q] = (int16_t)(nalloc + q);
+            }
+        }
+        nalloc += nnew;
+        mm = mm_after + nnew;
+        OG_K3_PROF(6);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+
+    // ---- person score, threshold, stable descending sort (group.py:188-219)
+#pragma unroll 1
+    for (int m = lane; m < mm; m += 32) {
+        const int row = (int)s_order[m] * CS;
+        float vals[OG_MAX_KEYPOINTS];
+        int n = 0;
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+            float v;
+            const float4 q = xyvs[row + c];
+            switch (a.sort_dim) {
+                case 0: v = q.x; break;
+                case 1: v = q.y; break;
+                case 2: v = q.z; break;
+                case 3: v = q.w; break;
+                case 4: v = score[row + c]; break;
+                default: v = (float)ids[row + c]; break;
+            }
+            if (v > 0.0f) vals[n++] = v;
+        }
+        const double ps = (double)numpy_sum_f32(vals, n) / (double)n;      // 0/0 -> NaN, kept
+        s_ps[m] = ps;
+        s_del[m] = (ps < a.person_thre) ? 1 : 0;
+    }
+    __syncwarp();
+    int nk = 0;                                     // s_pa: kept persons in their original order
+#pragma unroll 1
+    for (int mb = 0; mb < mm; mb += 32) {
+        const int m = mb + lane;
+        const bool keep = m < mm && s_del[m] == 0;
+        const unsigned ballot = __ballot_sync(kAll, keep);
+        if (keep) s_pa[nk + __popc(ballot & lt_mask)] = m;
+        nk += __popc(ballot);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int q = lane; q < nk; q += 32) {
+        double ps = s_ps[s_pa[q]];
+        if (ps != ps) ps = -1.0e300;        // documented deviation: NaN scores sort last
+        int rank = 0;
+#pragma unroll 1
+        for (int q2 = 0; q2 < nk; ++q2) {
+            double p2 = s_ps[s_pa[q2]];
+            if (p2 != p2) p2 = -1.0e300;
+            rank += (p2 > ps || (p2 == ps && q2 < q)) ? 1 : 0;
+        }
+        s_pb[q] = rank;
+    }
+    int off = 0;
+    if (lane == 0) {
+        off = atomicAdd(out_total, nk);
+        out_offset[img] = off;
+        out_count[img] = nk;
+        redo[img] = 0;
+    }
+    off = __shfl_sync(kAll, off, 0);
+    __syncwarp();
+    OG_K3_PROF(7);
+    const float inv_c = __frcp_rn((float)C);
+#pragma unroll 1
+    for (int e = lane; e < nk * C; e += 32) {       // one lane per (person, joint): 24 bytes each
+        const int q = small_div(e, inv_c), c = e - q * C;
+        const int dst = off + s_pb[q];
+        if (dst >= capacity_rows) continue;
+        const int row = (int)s_order[s_pa[q]] * CS;
+        const float4 v = xyvs[row + c];
+        float2 *o = reinterpret_cast<float2 *>(out_poses + ((size_t)dst * C + c) * OG_POSE_COLS);
+        o[0] = make_float2(unset_to_zero(v.x), unset_to_zero(v.y));
+        o[1] = make_float2(unset_to_zero(v.z), unset_to_zero(v.w));
+        o[2] = make_float2(unset_to_zero(score[row + c]), unset_to_zero((float)ids[row + c]));
+    }
+#ifdef OG_K3_PROFILE
+    OG_K3_PROF(8);
+    if (threadIdx.x == 0) {
+        for (int ph = 0; ph < 10; ++ph) atomicAdd(&og_k3_prof[ph], (unsigned long long)prof_acc[ph]);
+        atomicAdd(&og_k3_prof[15], 1ull);
+    }
+#endif
+}
+
 GroupArgs to_args(const GroupLaunch &g) {
     GroupArgs a;
     a.C = g.c;
@@ -552,6 +1071,7 @@ GroupArgs to_args(const GroupLaunch &g) {
     a.person_thre = g.person_thre;
     a.sort_dim = g.sort_dim;
     a.smem_rows = g.smem_rows;
+    a.warp_rows = g.warp_rows;
     a.slab = g.slab;
     a.slab_stride = g.slab_stride;
     return a;
@@ -577,32 +1097,58 @@ int read_k3_profile(unsigned long long *out16, bool reset) {
 
 size_t group_smem_bytes(const GroupLaunch &g) { return make_layout(g.c, g.l, g.k, g.smem_rows).total; }
 
+size_t group_warp_smem_bytes(const GroupLaunch &g) {
+    return g.warp_rows > 0 ? make_warp_layout(g.c, g.l, g.k, g.warp_rows).total : 0;
+}
+
 size_t group_prep_ints(const GroupLaunch &g) { return (size_t)g.n * g.l * (g.k + 1); }
 
-// The attribute belongs to the kernel (per device), not to a handle: handles with different
-// table sizes coexist, so it is only ever raised.
-int prepare_group_kernel(size_t smem_bytes) {
+size_t group_rec_vec4(const GroupLaunch &g) { return (size_t)g.n * g.l * g.k * 3; }
+
+// The attributes belong to the kernels (per device), not to a handle: handles with different
+// table sizes coexist, so they are only ever raised.
+int prepare_group_kernel(size_t smem_bytes, size_t warp_smem_bytes) {
     static std::mutex mu;
-    static size_t granted[64] = {0};
+    static size_t granted[64] = {0}, granted_warp[64] = {0};
     int dev = 0;
     OG_CUDA_TRY(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(mu);
-    if (dev >= 0 && dev < 64 && smem_bytes <= granted[dev]) return OG_OK;
-    OG_CUDA_TRY(cudaFuncSetAttribute(group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem_bytes));
-    if (dev >= 0 && dev < 64) granted[dev] = smem_bytes;
+    const bool known = dev >= 0 && dev < 64;
+    if (!known || smem_bytes > granted[dev]) {
+        OG_CUDA_TRY(cudaFuncSetAttribute(group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes));
+        if (known) granted[dev] = smem_bytes;
+    }
+    if (warp_smem_bytes > 48 * 1024 && (!known || warp_smem_bytes > granted_warp[dev])) {
+        OG_CUDA_TRY(cudaFuncSetAttribute(group_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)warp_smem_bytes));
+        if (known) granted_warp[dev] = warp_smem_bytes;
+    }
     return OG_OK;
 }
 
-int launch_group(const GroupLaunch &g, const float *limbs, float *out_poses, int capacity_rows,
-                 int32_t *out_offset, int32_t *out_count, int32_t *out_total, cudaStream_t s) {
+int launch_group(const GroupLaunch &g, const float *limbs, bool prepared, float *out_poses,
+                 int capacity_rows, int32_t *out_offset, int32_t *out_count, int32_t *out_total,
+                 cudaStream_t s, int64_t *launches) {
     if (g.n == 0) return OG_OK;
-    group_prepare_kernel<<<dim3(g.l, g.n), kPrepThreads, 0, s>>>(limbs, g.l, g.k, g.dist_max,
-                                                                 g.use_scale, g.prep);
-    OG_CUDA_TRY(cudaGetLastError());
+    if (!prepared) {
+        group_prepare_kernel<<<dim3(g.l, g.n), kPrepThreads, 0, s>>>(limbs, g.l, g.k, g.dist_max,
+                                                                     g.use_scale, g.prep, g.rec, g.cnt);
+        OG_CUDA_TRY(cudaGetLastError());
+        if (launches) *launches += 1;
+    }
+    const int32_t *redo = nullptr;
+    if (g.warp_rows > 0) {
+        group_warp_kernel<<<g.n, 32, group_warp_smem_bytes(g), s>>>(
+            to_args(g), g.rec, g.cnt, out_poses, capacity_rows, out_offset, out_count, out_total, g.redo);
+        OG_CUDA_TRY(cudaGetLastError());
+        if (launches) *launches += 1;
+        redo = g.redo;
+    }
     group_kernel<<<g.n, kGroupThreads, group_smem_bytes(g), s>>>(
-        to_args(g), limbs, g.prep, out_poses, capacity_rows, out_offset, out_count, out_total);
+        to_args(g), limbs, g.prep, out_poses, capacity_rows, out_offset, out_count, out_total, redo);
     OG_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += 1;
     return OG_OK;
 }
 

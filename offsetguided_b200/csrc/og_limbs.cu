@@ -8,8 +8,17 @@
 // separate multiply / add where eager torch runs separate kernels, and
 // sqrt(fma(dy, dy, dx*dx)) for Tensor.norm over an (x, y) pair (probed against
 // ATen's CPU kernel).  ~40 eager launches of the reference collapse into this one.
+//
+// The nearest to-candidate is found on SQUARED distances (no square root in the K-long
+// dependent chain): sqrt is monotonic and correctly rounded, so min(sqrt(d2)) = sqrt(min(d2));
+// Tensor.min's first-index rule is then applied to the rounded distances themselves, which
+// only the few candidates within 2^-20 of the minimum have to be re-evaluated for.
+//
+// The same CTA then runs the row-only half of the grouping step for its K rows (og_prep.cuh:
+// gate, sort, best row per to-joint id), so K3 starts from compacted kept rows.
 #include "og_common.cuh"
 #include "og_interp.cuh"
+#include "og_prep.cuh"
 
 namespace og {
 
@@ -29,15 +38,15 @@ __device__ __forceinline__ float norm2(float dx, float dy) {
 // with the flip-test average (factory.py:128-139) — bit-identical to gathering from the
 // materialised F.interpolate(offs, scale_factor=S, mode='bilinear') map.
 template <typename T>
-__device__ __forceinline__ float sample_offset_t(const OffsetSource &src, int img, int L, int l,
-                                                 int comp, int X, int Y) {
+__device__ __forceinline__ float sample_offset_t(const OffsetSource &src, const FlipTablesDev &ft,
+                                                 int img, int L, int l, int comp, int X, int Y) {
     const int h = src.h, w = src.w;
     const size_t hw = (size_t)h * w;
     const T *base = static_cast<const T *>(src.maps.ptr);
     const T *a = base + (size_t)img * src.maps.image_stride + (size_t)(2 * l + comp) * hw;
-    const bool mirrored = src.flip && !src.limb_reserved[l];
+    const bool mirrored = src.flip && !((ft.reserved >> l) & 1ull);
     const T *b = mirrored ? base + (size_t)(src.n + img) * src.maps.image_stride +
-                                (size_t)(2 * src.limb_flip[l] + comp) * hw
+                                (size_t)(2 * (int)ft.limb[l] + comp) * hw
                           : nullptr;
     auto at = [&](int yy, int xx) {
         float v = load_cell(a + yy * w + xx);
@@ -59,38 +68,45 @@ __device__ __forceinline__ float sample_offset_t(const OffsetSource &src, int im
     return combine2(r0, r1, wy[0], wy[1]);
 }
 
-__device__ __forceinline__ float sample_offset(const OffsetSource &src, int img, int L, int l,
-                                               int comp, int X, int Y) {
-    if (src.maps.dtype == OG_DTYPE_BF16) return sample_offset_t<__nv_bfloat16>(src, img, L, l, comp, X, Y);
-    if (src.maps.dtype == OG_DTYPE_F16) return sample_offset_t<__half>(src, img, L, l, comp, X, Y);
-    return sample_offset_t<float>(src, img, L, l, comp, X, Y);
+__device__ __forceinline__ float sample_offset(const OffsetSource &src, const FlipTablesDev &ft, int img,
+                                               int L, int l, int comp, int X, int Y) {
+    if (src.maps.dtype == OG_DTYPE_BF16) return sample_offset_t<__nv_bfloat16>(src, ft, img, L, l, comp, X, Y);
+    if (src.maps.dtype == OG_DTYPE_F16) return sample_offset_t<__half>(src, ft, img, L, l, comp, X, Y);
+    return sample_offset_t<float>(src, ft, img, L, l, comp, X, Y);
 }
 
-// Tensor.norm over 4 components as ATen's CPU kernel evaluates it (probed): plain left-to-right
-// sum of squares, no fused multiply-add.
-__device__ __forceinline__ float norm4(float a, float b, float c, float d) {
+// Tensor.norm over 4 components as ATen's CPU kernel evaluates it (probed) is a plain left-to-right
+// sum of squares without fused multiply-add: sq4 below.
+
+// squared distances as Tensor.norm accumulates them before the root
+__device__ __forceinline__ float sq2(float dx, float dy) { return __fmaf_rn(dy, dy, __fmul_rn(dx, dx)); }
+__device__ __forceinline__ float sq4(float a, float b, float c, float d) {
     float acc = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
     acc = __fadd_rn(acc, __fmul_rn(c, c));
-    acc = __fadd_rn(acc, __fmul_rn(d, d));
-    return __fsqrt_rn(acc);
+    return __fadd_rn(acc, __fmul_rn(d, d));
 }
 
+template <bool kFour>
 __global__ void __launch_bounds__(128)
 limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict__ det_index,
-                  const float *__restrict__ offs, OffsetSource src, const float *__restrict__ scales,
-                  LimbExtras ex, int C, int L, int K, int H, int W, SkeletonDev sk, float thre_hmp,
-                  float min_len, float resize_factor, float *__restrict__ out_limbs) {
+                  const float *__restrict__ offs, OffsetSource src, FlipTablesDev ft,
+                  const float *__restrict__ scales, LimbExtras ex, int C, int L, int K, int H, int W,
+                  SkeletonDev sk, float thre_hmp, float min_len, float resize_factor,
+                  float *__restrict__ out_limbs, PrepOut po) {
     __shared__ ToCand s_to[OG_MAX_TOPK];
+    __shared__ PrepShared s_prep;
     const int l = blockIdx.x;
     const int n = blockIdx.y;
     const int jf = sk.from[l], jt = sk.to[l];
     const long long HW = (long long)H * W;
+    const int k = threadIdx.x;                     // blockDim.x >= K: one candidate pair per thread
+    if (po.clear_word != nullptr && l == 0 && n == 0 && k == 0) *po.clear_word = 0;
 
     // candidate k of channel j: position, score; sub-threshold candidates (and the
     // empty slots K1 leaves behind, index -1) are moved 100000 px off the image
     // (collect.py:253, integer arithmetic before the float conversion)
-    auto candidate = [&](int j, int k, float &x, float &y, float &s, int32_t &idx) {
-        const size_t at = ((size_t)n * C + j) * K + k;
+    auto candidate = [&](int j, int kk, float &x, float &y, float &s, int32_t &idx) {
+        const size_t at = ((size_t)n * C + j) * K + kk;
         s = det_score[at];
         idx = det_index[at];
         int xi = 0, yi = 0;
@@ -106,44 +122,48 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
         y = (float)yi;
     };
 
-    for (int m = threadIdx.x; m < K; m += blockDim.x) {
+    float row[OG_LIMB_COLS];
+#pragma unroll
+    for (int i = 0; i < OG_LIMB_COLS; ++i) row[i] = 0.0f;
+    float x1 = 0.f, y1 = 0.f, s1 = 0.f;
+    int32_t idx1 = -1;
+    if (k < K) {
         ToCand t;
-        candidate(jt, m, t.x, t.y, t.score, t.index);
+        candidate(jt, k, t.x, t.y, t.score, t.index);
+        candidate(jf, k, x1, y1, s1, idx1);
         t.scale = 4.0f;                                              // collect.py:120
         if (scales != nullptr && t.index >= 0)
             t.scale = __ldg(scales + ((size_t)n * C + jt) * HW + t.index);   // collect.py:114
-        s_to[m] = t;
+        s_to[k] = t;
+    }
+    // the guiding offset of this thread's from-candidate (global / PCIe gathers: issued before
+    // the barrier so that they overlap the staging of the to-candidates)
+    float ox = 0.0f, oy = 0.0f, ox2 = 0.0f, oy2 = 0.0f, scale1 = 4.0f;
+    if (k < K && idx1 >= 0) {
+        if (offs != nullptr) {
+            const int nd = kFour ? 4 : 2;
+            const float *o = offs + ((size_t)n * nd * L + nd * l) * HW + idx1;   // collect.py:143-147
+            ox = __ldg(o);
+            oy = __ldg(o + HW);
+            if (kFour) {
+                ox2 = __ldg(o + 2 * HW);
+                oy2 = __ldg(o + 3 * HW);
+            }
+        } else {
+            const int py = idx1 / W, px = idx1 - py * W;
+            ox = sample_offset(src, ft, n, L, l, 0, px, py);
+            oy = sample_offset(src, ft, n, L, l, 1, px, py);
+        }
+        if (scales != nullptr) scale1 = __ldg(scales + ((size_t)n * C + jf) * HW + idx1);
     }
     __syncthreads();
 
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        float x1, y1, s1;
-        int32_t idx1;
-        candidate(jf, k, x1, y1, s1, idx1);
-        float ox = 0.0f, oy = 0.0f, ox2 = 0.0f, oy2 = 0.0f, scale1 = 4.0f;
-        const bool four = ex.vector_nd == 4;          // cat_flip_offs: (x, y, x_flip, y_flip)
-        if (idx1 >= 0) {
-            if (offs != nullptr) {
-                const int nd = four ? 4 : 2;
-                const float *o = offs + ((size_t)n * nd * L + nd * l) * HW + idx1;   // collect.py:143-147
-                ox = __ldg(o);
-                oy = __ldg(o + HW);
-                if (four) {
-                    ox2 = __ldg(o + 2 * HW);
-                    oy2 = __ldg(o + 3 * HW);
-                }
-            } else {
-                const int py = idx1 / W, px = idx1 - py * W;
-                ox = sample_offset(src, n, L, l, 0, px, py);
-                oy = sample_offset(src, n, L, l, 1, px, py);
-            }
-            if (scales != nullptr) scale1 = __ldg(scales + ((size_t)n * C + jf) * HW + idx1);
-        }
+    if (k < K) {
         float gx = __fadd_rn(x1, __fmul_rn(ox, resize_factor));               // collect.py:152
         float gy = __fadd_rn(y1, __fmul_rn(oy, resize_factor));
         const float gx2 = __fadd_rn(x1, __fmul_rn(ox2, resize_factor));
         const float gy2 = __fadd_rn(y1, __fmul_rn(oy2, resize_factor));
-        if (ex.jomps != nullptr && ex.use_jitter && !four) {
+        if (ex.jomps != nullptr && ex.use_jitter && !kFour) {
             // jitter refinement of the guided point (collect.py:158-165), including the
             // reference's [x, y]-as-[row, col] indexing; .int() truncates toward zero.
             // (The reference raises IndexError when x >= H; such points are left unrefined.)
@@ -154,18 +174,29 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
                 gy = __fadd_rn(gy, __ldg(jm + HW));
             }
         }
-        auto dist_to = [&](int m) {
+        auto sq_to = [&](int m) {
             const float dx = __fsub_rn(gx, s_to[m].x), dy = __fsub_rn(gy, s_to[m].y);
-            if (!four) return norm2(dx, dy);
-            return norm4(dx, dy, __fsub_rn(gx2, s_to[m].x), __fsub_rn(gy2, s_to[m].y));
+            if (!kFour) return sq2(dx, dy);
+            return sq4(dx, dy, __fsub_rn(gx2, s_to[m].x), __fsub_rn(gy2, s_to[m].y));
         };
-        float best = dist_to(0);
+        // pass 1 (collect.py:171-177): the smallest squared distance; `<` skips a NaN candidate
+        // and keeps a NaN first one, like the rounded-distance scan it replaces
+        float best2 = sq_to(0);
+        for (int m = 1; m < K; ++m) {
+            const float d2 = sq_to(m);
+            if (d2 < best2) best2 = d2;
+        }
+        const float best = __fsqrt_rn(best2);
+        // pass 2: Tensor.min returns the FIRST index of the smallest ROUNDED distance.  Distinct
+        // squared distances within a few ulp can round to the same root, so every candidate
+        // within 2^-20 (relative) of the minimum is re-evaluated exactly.
+        const float window = __fmul_rn(best2, 1.00000095367431640625f);
         int best_m = 0;
-        for (int m = 1; m < K; ++m) {                                          // collect.py:171-177
-            const float d = dist_to(m);
-            if (d < best) {
-                best = d;
+        for (int m = 0; m < K; ++m) {
+            const float d2 = sq_to(m);
+            if (d2 <= window && __fsqrt_rn(d2) == best) {
                 best_m = m;
+                break;
             }
         }
         const ToCand t = s_to[best_m];
@@ -185,38 +216,56 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
                 y2o = __fadd_rn(y2o, __ldg(ex.jomps + (size_t)n * 2 * HW + HW + t.index));
             }
         }
-        float *o = out_limbs + (((size_t)n * L + l) * K + k) * OG_LIMB_COLS;    // collect.py:223-233
-        o[0] = x1o;
-        o[1] = y1o;
-        o[2] = s1;
-        o[3] = x2o;
-        o[4] = y2o;
-        o[5] = t.score;
-        o[6] = __ll2float_rn(g1);
-        o[7] = __ll2float_rn(g2);
-        o[8] = best;
-        o[9] = len;
-        o[10] = score;
-        o[11] = scale1;
-        o[12] = t.scale;
+        row[0] = x1o;                                                   // collect.py:223-233
+        row[1] = y1o;
+        row[2] = s1;
+        row[3] = x2o;
+        row[4] = y2o;
+        row[5] = t.score;
+        row[6] = __ll2float_rn(g1);
+        row[7] = __ll2float_rn(g2);
+        row[8] = best;
+        row[9] = len;
+        row[10] = score;
+        row[11] = scale1;
+        row[12] = t.scale;
+        float *o = out_limbs + (((size_t)n * L + l) * K + k) * OG_LIMB_COLS;
+#pragma unroll
+        for (int i = 0; i < OG_LIMB_COLS; ++i) o[i] = row[i];
+    }
+    if (po.prep != nullptr) {
+        const size_t inst = (size_t)n * L + l;
+        prepare_limb_rows(row, k, K, po.dist_max, po.use_scale, s_prep, po.prep + inst * (K + 1),
+                          po.rec + inst * K * 3, po.cnt + inst);
     }
 }
 
 }  // namespace
 
 int launch_limb_score(const float *det_score, const int32_t *det_index, const float *offs,
-                      const OffsetSource *lowres, const float *scales, const LimbExtras *extras,
-                      int n, int c, int l, int k, int h, int w, const SkeletonDev &sk, float thre_hmp,
-                      float min_len, float resize_factor, float *out_limbs, cudaStream_t s) {
+                      const OffsetSource *lowres, const FlipTablesDev *flips, const float *scales,
+                      const LimbExtras *extras, int n, int c, int l, int k, int h, int w,
+                      const SkeletonDev &sk, float thre_hmp, float min_len, float resize_factor,
+                      float *out_limbs, const PrepOut *prep, cudaStream_t s) {
     if (n == 0) return OG_OK;
     const int threads = k <= 32 ? 32 : (k <= 64 ? 64 : 128);
     dim3 grid(l, n);
     OffsetSource src = {};
     if (lowres) src = *lowres;
+    FlipTablesDev ft = {};
+    if (flips) ft = *flips;
     LimbExtras ex = {nullptr, 2, 0};
     if (extras) ex = *extras;
-    limb_score_kernel<<<grid, threads, 0, s>>>(det_score, det_index, offs, src, scales, ex, c, l, k, h,
-                                              w, sk, thre_hmp, min_len, resize_factor, out_limbs);
+    PrepOut po = {nullptr, nullptr, nullptr, 0.0f, 0, nullptr};
+    if (prep) po = *prep;
+    if (ex.vector_nd == 4)
+        limb_score_kernel<true><<<grid, threads, 0, s>>>(det_score, det_index, offs, src, ft, scales, ex, c, l,
+                                                         k, h, w, sk, thre_hmp, min_len, resize_factor,
+                                                         out_limbs, po);
+    else
+        limb_score_kernel<false><<<grid, threads, 0, s>>>(det_score, det_index, offs, src, ft, scales, ex, c, l,
+                                                          k, h, w, sk, thre_hmp, min_len, resize_factor,
+                                                          out_limbs, po);
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;
 }

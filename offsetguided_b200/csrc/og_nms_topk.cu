@@ -221,10 +221,11 @@ __device__ void write_ranked(const uint64_t *keys, int n, int K, float *out_scor
 
 __global__ void __launch_bounds__(kSelectThreads)
 select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int K,
-                   const uint32_t *__restrict__ cand_count,
+                   uint32_t *__restrict__ cand_count,
                    const uint64_t *__restrict__ cand_keys, float *__restrict__ out_score,
                    int32_t *__restrict__ out_index, int32_t *__restrict__ out_count,
-                   int force_radix, int apply_nms, int32_t *__restrict__ overflow_flag) {
+                   int force_radix, int apply_nms, int32_t *__restrict__ overflow_flag,
+                   int32_t *__restrict__ clear_word) {
     __shared__ uint64_t s_keys[kCandCap];
     __shared__ uint32_t s_hist[kRadixBins];
     __shared__ uint32_t s_part[kSelectThreads];
@@ -235,7 +236,16 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
     float *o_score = out_score + (size_t)plane * K;
     int32_t *o_index = out_index + (size_t)plane * K;
 
-    const uint32_t n_cand = force_radix ? (uint32_t)kCandCap + 1u : cand_count[plane];
+    // The plane's counter is read once and left at zero for the next call on these lists (they
+    // belong to a result slot); the fused path's active-block counter is cleared the same way.
+    if (tid == 0) {
+        s_scalar[0] = force_radix ? (uint32_t)kCandCap + 1u : cand_count[plane];
+        if (!force_radix) cand_count[plane] = 0u;
+        if (clear_word != nullptr && plane == 0) *clear_word = 0;
+    }
+    __syncthreads();
+    const uint32_t n_cand = s_scalar[0];
+    __syncthreads();
     if (n_cand <= (uint32_t)kCandCap) {
         const int n = (int)n_cand;
         for (int i = tid; i < n; i += blockDim.x) s_keys[i] = cand_keys[(size_t)plane * kCandCap + i];
@@ -247,7 +257,7 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
 
     if (heat == nullptr) {      // fused path: no materialised plane to re-scan; the host re-runs
         if (tid == 0) {         // the batch through the materialising path (og_fetch_poses)
-            atomicExch(overflow_flag, 1);
+            *reinterpret_cast<volatile int32_t *>(overflow_flag) = 1;      // may be mapped host memory
             if (out_count) out_count[plane] = 0;
         }
         write_ranked(s_keys, 0, K, o_score, o_index);
@@ -405,7 +415,7 @@ int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int
     if (after_pass1) OG_CUDA_TRY(cudaEventRecord(after_pass1, s));
     select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
                                                         out_score, out_index, out_count,
-                                                        force_radix ? 1 : 0, apply_nms ? 1 : 0, nullptr);
+                                                        force_radix ? 1 : 0, apply_nms ? 1 : 0, nullptr, nullptr);
     OG_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;
     return OG_OK;
@@ -433,13 +443,13 @@ int launch_nms_candidates(const float *heat, int planes, int h, int w, float thr
 }
 
 int launch_select_topk(const float *heat, int planes, int h, int w, float thre, int k,
-                       const uint32_t *cand_count, const uint64_t *cand_keys, float *out_score,
+                       uint32_t *cand_count, const uint64_t *cand_keys, float *out_score,
                        int32_t *out_index, int32_t *out_count, int32_t *overflow_flag,
-                       cudaStream_t s) {
+                       int32_t *clear_word, cudaStream_t s) {
     if (planes == 0) return OG_OK;
     select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
                                                         out_score, out_index, out_count, 0, 1,
-                                                        overflow_flag);
+                                                        overflow_flag, clear_word);
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;
 }

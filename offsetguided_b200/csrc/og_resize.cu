@@ -41,9 +41,7 @@ __global__ void resize_kernel(const float *__restrict__ in, float *__restrict__ 
 }
 
 __global__ void flip_fuse_kernel(const float *__restrict__ hmp2n, const float *__restrict__ off2n,
-                                 const int32_t *__restrict__ kp_flip,
-                                 const int32_t *__restrict__ limb_flip,
-                                 const uint8_t *__restrict__ limb_reserved, int n, int c, int l,
+                                 const FlipTablesDev ft, int n, int c, int l,
                                  int h, int w, float *__restrict__ out_hmp,
                                  float *__restrict__ out_off) {
     const long long hw = (long long)h * w;
@@ -57,7 +55,7 @@ __global__ void flip_fuse_kernel(const float *__restrict__ hmp2n, const float *_
             const int ch = (int)((g / hw) % c);
             const int img = (int)(g / (hw * c));
             const float a = hmp2n[g];
-            const float b = hmp2n[(((long long)(n + img) * c + kp_flip[ch]) * h + y) * w + (w - 1 - x)];
+            const float b = hmp2n[(((long long)(n + img) * c + ft.kp[ch]) * h + y) * w + (w - 1 - x)];
             out_hmp[g] = __fmul_rn(__fadd_rn(a, b), 0.5f);                  // factory.py:106
         } else {
             const long long q = g - n_h;
@@ -68,8 +66,8 @@ __global__ void flip_fuse_kernel(const float *__restrict__ hmp2n, const float *_
             const int limb = ch >> 1, comp = ch & 1;
             const float a = off2n[q];
             float r = a;                                                    // factory.py:134
-            if (!limb_reserved[limb]) {
-                float b = off2n[(((long long)(n + img) * 2 * l + 2 * limb_flip[limb] + comp) * h + y) * w + (w - 1 - x)];
+            if (!((ft.reserved >> limb) & 1ull)) {
+                float b = off2n[(((long long)(n + img) * 2 * l + 2 * (int)ft.limb[limb] + comp) * h + y) * w + (w - 1 - x)];
                 if (comp == 0) b = -b;                                      // factory.py:132
                 r = __fmul_rn(__fadd_rn(a, b), 0.5f);                       // factory.py:133
             }
@@ -158,13 +156,11 @@ int launch_resize(const float *in, float *out, int planes, int h, int w, int sca
     return OG_OK;
 }
 
-int launch_flip_fuse(const float *hmp2n, const float *off2n, const int32_t *kp_flip_dev,
-                     const int32_t *limb_flip_dev, const uint8_t *limb_reserved_dev, int n, int c,
+int launch_flip_fuse(const float *hmp2n, const float *off2n, const FlipTablesDev &flips, int n, int c,
                      int l, int h, int w, float *out_hmp, float *out_off, cudaStream_t s) {
     const long long total = (long long)n * (c + 2 * l) * h * w;
     if (total == 0) return OG_OK;
-    flip_fuse_kernel<<<grid_for(total, 256), 256, 0, s>>>(hmp2n, off2n, kp_flip_dev, limb_flip_dev,
-                                                         limb_reserved_dev, n, c, l, h, w, out_hmp,
+    flip_fuse_kernel<<<grid_for(total, 256), 256, 0, s>>>(hmp2n, off2n, flips, n, c, l, h, w, out_hmp,
                                                          out_off);
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;

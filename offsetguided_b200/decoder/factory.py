@@ -1,6 +1,7 @@
 """Post-processing entry point (reference decoder/factory.py): ``decoder_cli``,
 ``decoder_factory(args)`` -> ``PostProcess``, ``PostProcess.generate_poses``."""
 import argparse
+import collections
 import logging
 import re
 
@@ -53,6 +54,8 @@ class PostProcess(torch.nn.Module):
         self.limbs_flips = config.offset_hflip(keypoints, skeleton)
         self.worker_pool = None          # the reference forks Pool(batch_size) here
         self._engines = {}
+        self._flip_tables = (self.keypoints_flips, self.limbs_flips[0], self.limbs_flips[1])
+        self._submitted = collections.deque()
         LOG.info('use the inferred feature maps at stage %d, heatmap index is %d, offsetmap index '
                  'is %d, interpolate the predicted heatmaps using %s, grouping on the GPU',
                  feat_stage, hmp_index, omp_index, inter_mode)
@@ -96,8 +99,30 @@ class PostProcess(torch.nn.Module):
                                                cat_flip_offs, scored_off)
         device = hmps.device if hmps.is_cuda else torch.device('cuda', torch.cuda.current_device())
         eng = self._engine(device)
-        tables = (self.keypoints_flips, self.limbs_flips[0], self.limbs_flips[1]) if flip_test else None
+        tables = self._flip_tables if flip_test else None
         return eng.decode_features(hmps, offs, self.hmp_stride, self.off_stride, self.inter_mode, tables)
+
+    # ---- pipelined form of generate_poses ------------------------------------------------------
+    # The reference call is synchronous: the host waits for every batch.  A decode of a few images
+    # is ~0.05 ms of latency-bound kernels, so a caller that shards a batch over several GPUs (or
+    # decodes while the network already runs the next batch) keeps several calls in flight:
+    # submit() launches and returns at once, collect() returns the oldest result.
+    def submit(self, features, flip_test=False):
+        """generate_poses without the wait: launch the decode of ``features`` (default heads, no
+        scored_off / cat_flip_offs) and return the number of calls now in flight (at most
+        ``engine.OG_MAX_IN_FLIGHT``).  The tensors must stay unmodified until ``collect()``."""
+        hmps = features[self.hmp_index][0][self.feat_stage]
+        offs = features[self.omp_index][0][self.feat_stage]
+        device = hmps.device if hmps.is_cuda else torch.device('cuda', torch.cuda.current_device())
+        eng = self._engine(device)
+        eng.decode_features(hmps, offs, self.hmp_stride, self.off_stride, self.inter_mode,
+                            self._flip_tables if flip_test else None, fetch=False)
+        self._submitted.append(eng)
+        return len(self._submitted)
+
+    def collect(self):
+        """Poses of the oldest submitted batch: list of (M_i, C, 6) float32 arrays."""
+        return self._submitted.popleft().fetch()
 
     def flip_augment(self, hmps, jomps, offs, scmps, cat_flip_offs, vector_nd):
         """Fuse the outputs of the original and the W-flipped images (reference

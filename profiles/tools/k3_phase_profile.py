@@ -1,4 +1,6 @@
-"""Per-phase cycle profile of the K3 CTA kernel (library built with -DOG_K3_PROFILE)."""
+"""Per-phase cycle profile of the K3 grouping kernel (library built with -DOG_K3_PROFILE into
+build/k3_variants/prof.so: python -c "from offsetguided_b200 import build; build.build(defines={'OG_K3_PROFILE': 1}, out='build/k3_variants/prof.so')").
+Default: the one-warp-per-image kernel; OG_K3_WARP_ROWS=0 profiles the CTA kernel."""
 import ctypes
 import os
 import sys
@@ -12,8 +14,11 @@ from offsetguided_b200 import _lib, engine      # noqa: E402
 from offsetguided_b200 import config as cfg     # noqa: E402
 from oracle import scenes                       # noqa: E402
 
-NAMES = ['top (wait rows, flags)', 'stage kept rows', 'match pairs', 'apply', 'merge search',
-         'merge apply + new scan', 'init new rows', 'final (score/sort)', 'output', '-']
+NAMES_CTA = ['top (wait rows, flags)', 'stage kept rows', 'match pairs', 'apply', 'merge search',
+             'merge apply + new scan', 'init new rows', 'final (score/sort)', 'output', '-']
+NAMES_WARP = ['top (wait rows, prefetch)', 'match pairs', 'apply', '-', 'merge search',
+              'merge apply', 'new persons', 'final (score/sort)', 'output', '-']
+NAMES = NAMES_CTA if os.environ.get('OG_K3_WARP_ROWS') == '0' else NAMES_WARP
 
 
 def main():

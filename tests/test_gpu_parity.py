@@ -773,36 +773,161 @@ def test_handles_with_different_table_sizes_coexist(cuda_device):
 
 
 def test_decodes_in_flight(cuda_device):
-    """The handle queues up to three decode calls; results come back oldest first and equal
-    the synchronous results; a fourth un-fetched call is refused."""
+    """The handle queues up to OG_MAX_IN_FLIGHT decode calls; results come back oldest first and
+    equal the synchronous results; one more un-fetched call is refused, and a synchronous call
+    while others are pending raises instead of handing out somebody else's result."""
     from offsetguided_b200 import _lib
     skel = cfg.COCO_PERSON_SKELETON
     heat, offs = scenes.synth_hires_batch(321, 4, 4, 320, 256, skel)
     th, to = torch.from_numpy(heat).cuda(), torch.from_numpy(offs).cuda()
     eng = DecoderEngine(17, skel, topk=16, thre_hmp=0.05, dist_max=40, use_scale=True, person_thre=0.05)
     eng.enable_stage_timing(True)
-    ref_a = eng.decode_maps(th[:3], to[:3])
-    ref_b = eng.decode_maps(th[3:], to[3:])
-    ref_c = eng.decode_maps(th[1:3], to[1:3])
+    cuts = [slice(0, 3), slice(3, 4), slice(1, 3), slice(0, 4), slice(2, 3), slice(0, 1), slice(1, 4), slice(0, 2)]
+    assert len(cuts) == _lib.OG_MAX_IN_FLIGHT
+    refs = [eng.decode_maps(th[c], to[c]) for c in cuts]
     assert eng.pending == 0
-    na = eng.decode_maps(th[:3], to[:3], fetch=False)
-    nb = eng.decode_maps(th[3:], to[3:], fetch=False)
-    nc = eng.decode_maps(th[1:3], to[1:3], fetch=False)
-    assert eng.pending == 3
+    for c in cuts:
+        eng.decode_maps(th[c], to[c], fetch=False)
+    assert eng.pending == _lib.OG_MAX_IN_FLIGHT
     with pytest.raises(_lib.OgError):
         eng.decode_maps(th[:1], to[:1], fetch=False)
-    got_a = eng.fetch(na)
+    with pytest.raises(_lib.OgError):
+        eng.decode_maps(th[:1], to[:1])                        # fetch=True behind pending calls
+    got = [eng.fetch()]
     t_a = eng.last_stage_times_ms()
-    ne = eng.decode_maps(th[:0], to[:0], fetch=False)          # empty batch in the queue
-    got_b = eng.fetch(nb)
-    got_c = eng.fetch(nc)
-    assert eng.fetch(ne) == [] and eng.pending == 0
-    assert len(got_a) == 3 and len(got_b) == 1 and len(got_c) == 2
-    for g, r in zip(got_a + got_b + got_c, ref_a + ref_b + ref_c):
-        assert np.array_equal(g, r)
+    eng.decode_maps(th[:0], to[:0], fetch=False)               # empty batch in the queue
+    got += [eng.fetch() for _ in cuts[1:]]
+    assert eng.fetch() == [] and eng.pending == 0
+    for c, g, r in zip(cuts, got, refs):
+        assert len(g) == len(r) == c.stop - c.start
+        for a_, b_ in zip(g, r):
+            assert np.array_equal(a_, b_)
     assert t_a['k1_stream'] > 0 and t_a['k3'] > 0
     with pytest.raises(_lib.OgError):
-        eng.fetch(1)
+        eng.fetch()
+
+
+def _lowres_scene(seed, n, flip, edge=320):
+    """Network-resolution maps (stride 4) of n images, mirrored copies appended when flip."""
+    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    skel = cfg.COCO_PERSON_SKELETON
+    hs, os_, hf, of = [], [], [], []
+    for i in range(n):
+        rng = np.random.RandomState(seed + i)
+        p = scenes.make_persons(rng, 4, edge, edge, scale_range=(edge / 64.0, edge / 27.0))
+        hs.append(scenes.render_heatmaps(p, edge, edge) + rng.uniform(0, 0.02, size=(17, edge // 4, edge // 4)).astype(np.float32))
+        os_.append(scenes.render_offsets(p, edge, edge, skel))
+        if flip:
+            pf = scenes.mirror_persons(p, edge, kp)
+            hf.append(scenes.render_heatmaps(pf, edge, edge))
+            of.append(scenes.render_offsets(pf, edge, edge, skel))
+    hmp = np.stack(hs + hf).astype(np.float32)
+    omp = np.stack(os_ + of).astype(np.float32)
+    omp[~np.isfinite(omp)] = 0
+    return hmp, omp
+
+
+def test_graph_replay_and_recapture(cuda_device):
+    """Device path: the chain of a result slot is captured once and replayed while pointers and
+    shapes stay the same; other buffers / batch sizes re-capture; every result equals the
+    kernel-by-kernel launch (og_set_graph(0)) and the host path."""
+    skel = cfg.COCO_PERSON_SKELETON
+    tables = (cfg.heatmap_hflip(cfg.COCO_KEYPOINTS),) + tuple(cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel))
+    hmp, omp = _lowres_scene(77, 3, True)
+    hd, od = torch.from_numpy(hmp).cuda(), torch.from_numpy(omp).cuda()
+    eng = DecoderEngine(17, skel, topk=16, thre_hmp=0.05, dist_max=40, use_scale=True, person_thre=0.05)
+    eng.set_graph(False)
+    ref = eng.decode_features(hd, od, 4, 4, 'bicubic', tables)
+    assert sum(len(p) for p in ref) >= 6 and eng.graph_counts == (0, 0)
+    eng.set_graph(True)
+    for _ in range(2 * 8 + 1):                      # every slot captures once, then replays
+        got = eng.decode_features(hd, od, 4, 4, 'bicubic', tables)
+        for g, r in zip(got, ref):
+            assert np.array_equal(g, r)
+    replays, builds = eng.graph_counts
+    assert builds == 8 and replays == 17
+    # the same maps in other buffers, and a smaller batch: re-captured, same answers
+    hd2, od2 = hd.clone(), od.clone()
+    got = eng.decode_features(hd2, od2, 4, 4, 'bicubic', tables)
+    assert eng.graph_counts[1] == 9 and all(np.array_equal(g, r) for g, r in zip(got, ref))
+    sub = [0, 1, 3, 4]
+    got = eng.decode_features(hd[sub], od[sub], 4, 4, 'bicubic', tables)
+    assert all(np.array_equal(g, r) for g, r in zip(got, ref[:2]))
+    host = eng.decode_features(torch.from_numpy(hmp).pin_memory(), torch.from_numpy(omp).pin_memory(), 4, 4,
+                               'bicubic', tables)
+    assert all(np.array_equal(g, r) for g, r in zip(host, ref))
+    # a prepared plan: one foreign call per launch / fetch
+    plan = eng.plan_features(hd, od, 4, 4, 'bicubic', tables)
+    for _ in range(3):
+        plan.launch()
+    for _ in range(3):
+        assert all(np.array_equal(g, r) for g, r in zip(plan.fetch(), ref))
+
+
+def test_calls_in_flight_from_different_streams(cuda_device):
+    """Every call owns its scratch (candidate lists, block flags, work list): decode calls launched
+    from alternating caller streams with several in flight equal the synchronous results."""
+    skel = cfg.COCO_PERSON_SKELETON
+    eng = DecoderEngine(17, skel, topk=16, thre_hmp=0.05, dist_max=40, use_scale=True, person_thre=0.05)
+    batches = []
+    for i in range(4):
+        hmp, omp = _lowres_scene(500 + 10 * i, 2 + i % 2, False)
+        batches.append((torch.from_numpy(hmp).cuda(), torch.from_numpy(omp).cuda()))
+    refs = [eng.decode_features(h_, o_, 4, 4, 'bicubic') for h_, o_ in batches]
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    torch.cuda.synchronize()
+    for rep in range(6):
+        for graph in (True, False):
+            eng.set_graph(graph)
+            for i, (h_, o_) in enumerate(batches):
+                with torch.cuda.stream(streams[(i + rep) % 3]):
+                    eng.decode_features(h_, o_, 4, 4, 'bicubic', fetch=False)
+            for r in refs:
+                got = eng.fetch()
+                assert len(got) == len(r) and all(np.array_equal(a_, b_) for a_, b_ in zip(got, r))
+
+
+def test_mismatched_heads_are_rejected(cuda_device):
+    """Channel counts / resolutions that do not fit the configuration raise before the library is
+    called (the C ABI infers the channel counts from the configuration)."""
+    skel = cfg.COCO_PERSON_SKELETON
+    eng = DecoderEngine(17, skel, topk=8, thre_hmp=0.05, dist_max=40, use_scale=True, person_thre=0.05)
+    z = lambda *s_: torch.zeros(s_, device='cuda')
+    with pytest.raises(ValueError):
+        eng.decode_features(z(2, 17, 16, 16), z(2, 62, 16, 16), 4, 4)          # omp31 maps, 19-limb skeleton
+    with pytest.raises(ValueError):
+        eng.decode_features(z(2, 14, 16, 16), z(2, 38, 16, 16), 4, 4)
+    with pytest.raises(ValueError):
+        eng.decode_features(z(2, 17, 16, 16), z(2, 38, 32, 32), 4, 4)
+    with pytest.raises(ValueError):
+        eng.decode_features(z(2, 17, 16, 16), z(4, 38, 16, 16), 4, 4)
+    tables = (cfg.heatmap_hflip(cfg.COCO_KEYPOINTS),) + tuple(cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel))
+    with pytest.raises(ValueError):
+        eng.decode_features(z(3, 17, 16, 16), z(3, 38, 16, 16), 4, 4, 'bicubic', tables)    # odd flip batch
+    with pytest.raises(ValueError):
+        eng.decode_maps(z(1, 17, 32, 32), z(1, 38, 16, 16))
+    assert eng.pending == 0 and eng.decode_features(z(2, 17, 16, 16), z(2, 38, 16, 16), 4, 4)[0].shape == (0, 17, 6)
+
+
+@pytest.mark.parametrize('env', [{'OG_K3_WARP_ROWS': '0'}, {'OG_K3_WARP_ROWS': '8'}, {'OG_RESULT_ROWS': '1'}])
+def test_k3_kernel_variants_agree(cuda_device, env, monkeypatch):
+    """The one-warp-per-image grouping kernel, the CTA kernel it hands oversized images to
+    (OG_K3_WARP_ROWS = 8: most fuzz tables overflow 8 person rows; 0: CTA kernel only) and the
+    regroup into a worst-case result buffer (OG_RESULT_ROWS = 1) all reproduce the reference."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cases = gio.load_group_fuzz()
+    for c in cases[::3]:
+        g = decoder.GreedyGroup(c['person_thre'], sort_dim=c['sort_dim'], dist_max=40, use_scale=c['use_scale'],
+                                keypoints=list(range(c['n_keypoints'])), skeleton=c['skeleton'])
+        stack = np.stack([c['limbs']] * 3)
+        for got in g.group_batch(stack):
+            gio.compare_poses(got, c['poses'], exact=True)
+    d = gio.load_limbs_case('limbs_crowdpose')
+    eng = _engine(d, d['n_keypoints'], d['skeleton'])
+    poses = eng.decode_maps(torch.from_numpy(d['heat']).cuda(), torch.from_numpy(d['offs']).cuda())
+    for p, r in zip(poses, gio.split_poses(d['poses'], d['pose_counts'])):
+        gio.compare_poses(p, r, rtol=RTOL)
 
 
 # --------------------------------------------------------------------------- BASELINE sizes

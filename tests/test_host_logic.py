@@ -89,7 +89,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f'{name} declared in og_decoder.h but not exported'
     assert declared == set(_lib.SIGNATURES), 'ctypes stub and header disagree'
     loaded = _lib.load()
-    assert loaded.og_abi_version() == 1
+    assert loaded.og_abi_version() == 2
     assert loaded.og_status_string(0) == b'ok'
 
 
