@@ -2,30 +2,34 @@
 """Benchmark of the OffsetGuided post-network decoder on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload cfg2|cfg3|cfg4] [--batch B] [--long-edge E]
 
-One "step" decodes one batch of synthetic network outputs: BASELINE.json configs[1]
-settings (COCO skeleton, flip-test fusion, x4 resize to 640x640, topk 32, thre-hmp 0.04,
-person-thre 0.04, dist-max 40) at the north-star batch of 64 images per GPU.
+One "step" decodes ONE GLOBAL BATCH of synthetic network outputs, sharded by image over the N
+ranks (strong scaling: ceil(B / N) images per GPU, no collective on the data path).  Default
+workload: BASELINE.json configs[1] settings (COCO skeleton, flip-test fusion, x4 bicubic resize
+to 640x640, topk 32, thre-hmp 0.04, person-thre 0.04, dist-max 40) at the north-star batch of 64.
+`--workload cfg4` is configs[3] (long edge 1024, batch 64), `--workload cfg3` configs[2]
+(CrowdPose 14 keypoints, 20 persons per image, topk 64, batch 32).
 
-  value     images/s of the hot path (K1 NMS+top-K -> K2 limb scoring -> K3 grouping, poses
-            copied to pinned memory and fetched) on full-resolution maps RESIDENT IN HBM, two
-            batches in flight, CUDA-event timed on the launching stream, max over ranks;
-  e2e       images/s through the reference-facing API PostProcess.generate_poses with
-            HOST (pinned) network-resolution maps: H2D copy, flip fusion, x4 resize,
-            K1..K3 and the D2H read of the poses are all inside the timed region;
-  features_dev  the same decode from DEVICE-resident network-resolution maps (the call
-            evaluate.py makes right after model(images)), extra key;
-  roofline  K1 (both passes) algorithmic bytes N*C*H*W*4 over its CUDA-event duration,
+  value     images/s of the PRODUCT PATH, the same work the reference arm does: device-resident
+            network-resolution maps (what evaluate.py holds after model(images)) -> flip fusion
+            + x4 resize + NMS + top-K -> limb scoring -> grouping -> poses in host memory,
+            through PostProcess.submit / collect (the pipelined form of generate_poses) with
+            up to eight batches in flight; max over ranks of the timed region;
+  e2e       the same through the reference's own synchronous call
+            PostProcess.generate_poses(features, flip_test) with HOST (pinned) maps: H2D copy
+            of this rank's shard, decode and the poses' way back are inside the timed region;
+  roofline  K1 on MATERIALISED full-resolution maps (SURVEY 8d's definition: N*C*H*W*4 bytes per
+            launch over the CUDA-event duration of nms_candidates + select, batch B per GPU)
             against the measured HBM copy peak (MEASURED_PEAKS.json);
-  cpu_baseline  the oracle port of the reference decoder (oracle/) on the host cores, on
-            a bounded sample of the same workload.
+  roofline_fused   the product path's own K1f: network-resolution bytes over scan + list + blocks;
+  cpu_baseline     the oracle port of the reference decoder on the host cores (N = 1 only).
 
-Multi-GPU: images are independent, every rank decodes its own batch (weak scaling, no
-collective on the data path); launched by torchrun for N > 1.
-`--impl reference` times the CPU oracle port alone (rank 0 only).
+`--impl reference` times the CPU oracle port alone on the same global batch (rank 0 only).
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -40,8 +44,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'decoded images/s @640 long-edge'
 UNIT = 'images/s'
-TOPK, THRE_HMP, PERSON_THRE, DIST_MAX, MIN_LEN = 32, 0.04, 0.04, 40.0, 0.5
-PERSONS = 6
+MIN_LEN = 0.5
+L2_BYTES = 126e6
 
 
 def parse_args():
@@ -50,55 +54,85 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=64, help='images per GPU per step')
-    ap.add_argument('--long-edge', type=int, default=640)
-    ap.add_argument('--no-flip', action='store_true', help='e2e without flip-test inputs')
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4'])
+    ap.add_argument('--batch', type=int, default=0, help='GLOBAL batch per step (0 = the workload default)')
+    ap.add_argument('--long-edge', type=int, default=0, help='0 = the workload default')
+    ap.add_argument('--no-flip', action='store_true', help='no flip-test inputs')
     ap.add_argument('--cpu-sample', type=int, default=0, help='images of the CPU sample (0 = auto)')
     ap.add_argument('--hot-only', action='store_true',
-                    help='run only the HBM-resident hot path (for ncu captures; prints no bench line)')
+                    help='run only the HBM-resident full-resolution hot path (for ncu captures; no bench line)')
+    ap.add_argument('--lean', action='store_true', help='skip the extra legs (weak scaling, sustained run, baselines)')
     return ap.parse_args()
 
 
-def workload_config(args, n_gpus):
+def workload(args):
+    from offsetguided_b200 import config as cfg
+    from oracle import scenes
+    if args.workload == 'cfg3':
+        w = dict(tag='BASELINE configs[2]: CrowdPose 14 keypoints / 15 limbs, 20 persons per image',
+                 keypoints=cfg.CROWDPOSE_KEYPOINTS, skeleton=cfg.CROWDPOSE_PERSON_SKELETON,
+                 template=scenes.TEMPLATE_CROWDPOSE, topk=64, persons=20, edge=640, batch=32)
+    else:
+        w = dict(tag='BASELINE configs[1] settings: COCO 17 keypoints / 19 limbs, 6 persons per image'
+                 if args.workload == 'cfg2' else
+                 'BASELINE configs[3]: long edge 1024 (256x256 maps), COCO 17 keypoints / 19 limbs, 6 persons per image',
+                 keypoints=cfg.COCO_KEYPOINTS, skeleton=cfg.COCO_PERSON_SKELETON,
+                 template=scenes.TEMPLATE_COCO, topk=32, persons=6,
+                 edge=1024 if args.workload == 'cfg4' else 640, batch=64)
+    w.update(thre_hmp=0.04, person_thre=0.04, dist_max=40.0, flip=not args.no_flip)
+    if args.batch:
+        w['batch'] = args.batch
+    if args.long_edge:
+        w['edge'] = args.long_edge
+    w['c'] = len(w['keypoints'])
+    w['l'] = len(w['skeleton'])
+    w['kp_flips'] = cfg.heatmap_hflip(w['keypoints'])
+    w['limb_flips'], w['limb_reserve'] = cfg.offset_hflip(w['keypoints'], w['skeleton'])
+    return w
+
+
+def workload_config(w, n_gpus, per_gpu):
+    e = w['edge']
     return {
-        'workload': 'BASELINE configs[1] settings at batch %d per GPU: COCO 17 keypoints / 19 limbs, '
-                    'network maps %dx%d (x4 -> %dx%d), %s, topk=%d, thre_hmp=%.2f, person_thre=%.2f, '
-                    'dist_max=%d' % (args.batch, args.long_edge // 4, args.long_edge // 4, args.long_edge,
-                                     args.long_edge, 'no flip' if args.no_flip else 'flip-test fusion',
-                                     TOPK, THRE_HMP, PERSON_THRE, int(DIST_MAX)),
-        'images_per_gpu_per_step': args.batch,
-        'global_batch': args.batch * n_gpus,
-        'parallelism': 'image-sharded x%d, no collective' % n_gpus,
-        'l2_policy': 'hot-path inputs are %.1f GB per step (heat %.2f GB + offsets %.2f GB) >> 126 MB L2; '
-                     'e2e / features_dev read %.0f MB of network-resolution heat maps per step'
-                     % (args.batch * 55 * args.long_edge ** 2 * 4 / 1e9, args.batch * 17 * args.long_edge ** 2 * 4 / 1e9,
-                        args.batch * 38 * args.long_edge ** 2 * 4 / 1e9,
-                        args.batch * (1 if args.no_flip else 2) * 17 * (args.long_edge // 4) ** 2 * 4 / 1e6),
-        'persons_per_image': PERSONS,
+        'workload': '%s; network maps %dx%d (x4 -> %dx%d), %s, topk=%d, thre_hmp=%.2f, person_thre=%.2f, '
+                    'dist_max=%d' % (w['tag'], e // 4, e // 4, e, e, 'flip-test fusion' if w['flip'] else 'no flip',
+                                     w['topk'], w['thre_hmp'], w['person_thre'], int(w['dist_max'])),
+        'global_batch': w['batch'],
+        'images_per_gpu_per_step': per_gpu,
+        'parallelism': 'one global batch image-sharded x%d (ceil(B / N) per GPU), no collective' % n_gpus,
+        'l2_policy': 'every step decodes another input buffer of a ring whose total size exceeds 2x the 126 MB L2 '
+                     '(network-resolution heat maps: %.0f MB per GPU per step); the full-resolution K1 roofline leg '
+                     'streams %.2f GB per launch' % (per_gpu * (2 if w['flip'] else 1) * w['c'] * (e // 4) ** 2 * 4 / 1e6,
+                                                     w['batch'] * w['c'] * e * e * 4 / 1e9),
+        'persons_per_image': w['persons'],
     }
 
 
 # --------------------------------------------------------------------------- inputs
-def lowres_inputs(seed, n, long_edge, flip):
+def lowres_inputs(seed, n, long_edge, flip, w=None):
     """Network-resolution maps as the reference encoder renders them (oracle/scenes.py
     restates encoder/heatmap.py and encoder/offset.py); flipped half from mirrored persons."""
     from oracle import scenes
     from offsetguided_b200 import config as cfg
-    skel = cfg.COCO_PERSON_SKELETON
-    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
+    if w is None:
+        w = dict(skeleton=cfg.COCO_PERSON_SKELETON, keypoints=cfg.COCO_KEYPOINTS, template=scenes.TEMPLATE_COCO,
+                 persons=6, c=17)
+    skel = w['skeleton']
+    kp = cfg.heatmap_hflip(w['keypoints'])
+    c = len(w['keypoints'])
     distinct = min(n, 16)
     hs, os_, hf, of = [], [], [], []
     for i in range(distinct):
         rng = np.random.RandomState(seed + i)
-        p = scenes.make_persons(rng, PERSONS, long_edge, long_edge,
+        p = scenes.make_persons(rng, w['persons'], long_edge, long_edge, w['template'],
                                 scale_range=(long_edge / 64.0, long_edge / 27.0))
         hs.append(scenes.render_heatmaps(p, long_edge, long_edge) +
-                  rng.uniform(0, 0.02, size=(17, long_edge // 4, long_edge // 4)).astype(np.float32))
+                  rng.uniform(0, 0.02, size=(c, long_edge // 4, long_edge // 4)).astype(np.float32))
         os_.append(scenes.render_offsets(p, long_edge, long_edge, skel))
         if flip:
             pf = scenes.mirror_persons(p, long_edge, kp)
             hf.append(scenes.render_heatmaps(pf, long_edge, long_edge) +
-                      rng.uniform(0, 0.02, size=(17, long_edge // 4, long_edge // 4)).astype(np.float32))
+                      rng.uniform(0, 0.02, size=(c, long_edge // 4, long_edge // 4)).astype(np.float32))
             of.append(scenes.render_offsets(pf, long_edge, long_edge, skel))
     reps = (n + distinct - 1) // distinct
 
@@ -134,6 +168,7 @@ class ClockSampler(object):
             self.thread.start()
         except OSError:
             self.proc = None
+        return self
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -168,38 +203,33 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------- CPU arm
-def cpu_decode_fn():
+def cpu_decode_fn(w):
     """The oracle port of the reference decoder: multi-threaded C restatement when it has
     been built (oracle/og_oracle.c), else the numpy restatement (single thread)."""
-    from offsetguided_b200 import config as cfg
-    skel = cfg.COCO_PERSON_SKELETON
-    kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
-    fl, rs = cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel)
+    kw = dict(topk=w['topk'], thre_hmp=w['thre_hmp'], min_len=MIN_LEN, person_thre=w['person_thre'],
+              dist_max=w['dist_max'], use_scale=True, kp_flips=w['kp_flips'], limb_flips=w['limb_flips'],
+              limb_reserve=w['limb_reserve'])
     try:
         from oracle import c_oracle
         c_oracle.load()
         cores = c_oracle.num_threads()
 
         def run(hmp, omp, flip, stage_seconds=None):
-            return c_oracle.generate_poses(hmp, omp, skel, 17, topk=TOPK, thre_hmp=THRE_HMP,
-                                           min_len=MIN_LEN, person_thre=PERSON_THRE, dist_max=DIST_MAX,
-                                           use_scale=True, flip_test=flip, kp_flips=kp, limb_flips=fl,
-                                           limb_reserve=rs, stage_seconds=stage_seconds)
+            return c_oracle.generate_poses(hmp, omp, w['skeleton'], w['c'], flip_test=flip,
+                                           stage_seconds=stage_seconds, **kw)
         return run, cores, 'oracle/og_oracle.c (C + OpenMP restatement of the reference decoder)'
     except Exception:
         from oracle import ref_oracle as ro
 
         def run(hmp, omp, flip, stage_seconds=None):
-            return ro.generate_poses(hmp, omp, skel, 17, topk=TOPK, thre_hmp=THRE_HMP, min_len=MIN_LEN,
-                                     person_thre=PERSON_THRE, dist_max=DIST_MAX, use_scale=True,
-                                     flip_test=flip, kp_flips=kp, limb_flips=fl, limb_reserve=rs)
+            return ro.generate_poses(hmp, omp, w['skeleton'], w['c'], flip_test=flip, **kw)
         return run, 1, 'oracle/ref_oracle.py (numpy restatement of the reference decoder)'
 
 
-def time_cpu(args, n_images, repeats):
-    run, cores, what = cpu_decode_fn()
-    flip = not args.no_flip
-    hmp, omp = lowres_inputs(9000, n_images, args.long_edge, flip)
+def time_cpu(w, n_images, repeats):
+    run, cores, what = cpu_decode_fn(w)
+    flip = w['flip']
+    hmp, omp = lowres_inputs(9000, n_images, w['edge'], flip, w)
     run(hmp[:1] if not flip else np.concatenate((hmp[:1], hmp[n_images:n_images + 1])),
         omp[:1] if not flip else np.concatenate((omp[:1], omp[n_images:n_images + 1])), flip)   # warm
     times, stage_runs = [], []
@@ -216,26 +246,30 @@ def time_cpu(args, n_images, repeats):
 
 
 def run_reference(args):
+    """The reference arm: the CPU port of the reference decoder with all host threads, one step =
+    the whole global batch (the same unit of work as the B200 arm), same warm-up."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    run, cores, what = cpu_decode_fn()
-    n_images = args.cpu_sample or (8 if cores > 1 else 1)
-    flip = not args.no_flip
-    hmp, omp = lowres_inputs(9000, n_images, args.long_edge, flip)
-    for _ in range(min(args.warmup, 1)):
+    w = workload(args)
+    run, cores, what = cpu_decode_fn(w)
+    n_images = args.cpu_sample or (w['batch'] if cores > 1 else 1)
+    flip = w['flip']
+    hmp, omp = lowres_inputs(5000, n_images, w['edge'], flip, w)
+    for _ in range(args.warmup):
         run(hmp, omp, flip)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         run(hmp, omp, flip)
     dt = time.perf_counter() - t0
     value = n_images * args.steps / dt
-    sample = '%d images per step (of the %d-image batch), %d steps, %s' % (n_images, args.batch, args.steps, what)
+    sample = '%d images per step (the global batch is %d), %d steps after %d warm-up steps, %s' % (
+        n_images, w['batch'], args.steps, args.warmup, what)
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * dt / args.steps,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': workload_config(args, args.gpus),
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': workload_config(w, args.gpus, -(-w['batch'] // args.gpus)),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -243,19 +277,97 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- B200 arm
+def make_post(w, batch):
+    """PostProcess of the workload: decoder_factory(args) for the COCO heads (the reference's own
+    construction path); the CrowdPose table is not reachable through parse_heads (it asserts 17
+    keypoints, decoder/factory.py:204), so config 3 builds the same classes directly."""
+    from offsetguided_b200 import decoder
+    if w['c'] == 17:
+        ap = argparse.ArgumentParser()
+        decoder.decoder_cli(ap)
+        dargs = ap.parse_args(['--topk', str(w['topk']), '--thre-hmp', str(w['thre_hmp']),
+                               '--person-thre', str(w['person_thre']), '--dist-max', str(w['dist_max'])])
+        dargs.headnets, dargs.strides, dargs.batch_size = ['hmp', 'omp'], [4, 4], batch
+        dargs.include_scale = dargs.include_jitter_offset = False
+        return decoder.decoder_factory(dargs)
+    from offsetguided_b200.decoder.factory import PostProcess
+    lc = decoder.LimbsCollect(4, 4, topk=w['topk'], thre_hmp=w['thre_hmp'], min_len=MIN_LEN,
+                              keypoints=w['keypoints'], skeleton=w['skeleton'])
+    lg = decoder.GreedyGroup(w['person_thre'], sort_dim=2, dist_max=w['dist_max'], use_scale=True,
+                             keypoints=w['keypoints'], skeleton=w['skeleton'])
+    return PostProcess(batch, 4, 4, 'bicubic', keypoints=w['keypoints'], skeleton=w['skeleton'],
+                       limb_collector=lc, limb_grouper=lg)
+
+
+def pipelined(post, feats_ring, flip, steps, depth, probe=None):
+    """`steps` decodes through submit / collect with up to `depth` in flight; every batch's poses
+    are collected.  Returns the last result.  `probe` (a dict) receives the median host
+    microseconds of a submit and of a collect (diagnostic passes only)."""
+    depth = max(1, min(depth, steps))
+    nb = len(feats_ring)
+    out = None
+    for i in range(depth - 1):
+        post.submit(feats_ring[i % nb], flip_test=flip)
+    if probe is None:
+        for i in range(depth - 1, steps):
+            post.submit(feats_ring[i % nb], flip_test=flip)
+            out = post.collect()
+    else:
+        ts, tc = [], []
+        for i in range(depth - 1, steps):
+            a = time.perf_counter()
+            post.submit(feats_ring[i % nb], flip_test=flip)
+            b = time.perf_counter()
+            out = post.collect()
+            tc.append(time.perf_counter() - b)
+            ts.append(b - a)
+        probe['submit_us'] = round(1e6 * statistics.median(ts), 2)
+        probe['collect_us'] = round(1e6 * statistics.median(tc), 2)
+        probe['collect_us_max'] = round(1e6 * max(tc), 2)
+    for _ in range(depth - 1):
+        out = post.collect()
+    return out
+
+
+def pin_to_own_core(local, local_world):
+    """One physical core per rank (both hardware threads): a step of the sharded batch is ~20 us of
+    host work, so two ranks sharing the sibling threads of one core show up in the max over ranks."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        cores = {}
+        for cpu in allowed:
+            try:
+                with open('/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list' % cpu) as f:
+                    sib = f.read().strip()
+            except OSError:
+                sib = str(cpu)
+            cores.setdefault(sib, []).append(cpu)
+        groups = sorted(cores.values())
+        if len(groups) >= 2 * local_world:           # leave the other cores to samplers / NCCL threads
+            os.sched_setaffinity(0, set(groups[(2 * local + 1) % len(groups)]))
+            return groups[(2 * local + 1) % len(groups)]
+    except (AttributeError, OSError):
+        pass
+    return None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from offsetguided_b200 import config as cfg
-    from offsetguided_b200 import decoder
+    from offsetguided_b200 import sharding
     from offsetguided_b200.engine import DecoderEngine
     from oracle import scenes
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
+    # Spread the ranks over the PCIe tree: with fewer ranks than GPUs, neighbouring ordinals share
+    # upstream links (profiles/r1_topo_8gpu.txt), so rank r takes GPU r * (G / N).
+    ndev = torch.cuda.device_count()
+    local_world = int(os.environ.get('LOCAL_WORLD_SIZE', str(world)))
+    dev_index = local * (ndev // local_world) if (ndev >= local_world and ndev % local_world == 0) else local
+    torch.cuda.set_device(dev_index)
+    dev = torch.device('cuda', dev_index)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         # This image exports NCCL_DEBUG=VERSION, which makes NCCL print its version banner on
@@ -266,103 +378,197 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=dev)
     n_gpus = world
 
-    skel = cfg.COCO_PERSON_SKELETON
-    B, E = args.batch, args.long_edge
-    flip = not args.no_flip
-
-    # ---- hot path on HBM-resident full-resolution maps
-    distinct = min(B, 8)
-    heat_np, offs_np = scenes.synth_hires_batch(1000 * (rank + 1), distinct, PERSONS, E, E, skel)
-    heat = torch.from_numpy(heat_np).to(dev).repeat((B + distinct - 1) // distinct, 1, 1, 1)[:B].contiguous()
-    offs = torch.from_numpy(offs_np).to(dev).repeat((B + distinct - 1) // distinct, 1, 1, 1)[:B].contiguous()
-    del heat_np, offs_np
-    eng = DecoderEngine(17, skel, topk=TOPK, thre_hmp=THRE_HMP, min_len=MIN_LEN, dist_max=DIST_MAX,
-                        use_scale=True, person_thre=PERSON_THRE, device=dev)
-    eng.enable_stage_timing(True)
+    w = workload(args)
+    skel, C, L, E, B, flip = w['skeleton'], w['c'], w['l'], w['edge'], w['batch'], w['flip']
+    start_i, stop_i = sharding.partition(B, world)[rank]
+    n_local = stop_i - start_i
+    per_gpu = -(-B // world)
+    tables = (w['kp_flips'], w['limb_flips'], w['limb_reserve']) if flip else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        poses = eng.decode_maps(heat, offs)
-    n_persons = sum(len(p) for p in poses)
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    launches0 = eng.launch_count
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stages = []
-    # two batches in flight: batch i + 1 is launched before batch i is fetched, so the GPU never
-    # waits for the host; every batch's poses are fetched (K launches, K fetches)
-    start.record()
-    eng.decode_maps(heat, offs, fetch=False)
-    for _ in range(args.steps - 1):
-        eng.decode_maps(heat, offs, fetch=False)
-        eng.fetch(B)
-        stages.append(eng.last_stage_times_ms())
-    poses = eng.fetch(B)
-    stages.append(eng.last_stage_times_ms())
-    stop.record()
-    barrier()
-    hot_ms = start.elapsed_time(stop)
-    hot_launches = eng.launch_count - launches0
+    post = make_post(w, per_gpu)
+    eng = post._engine(dev)
+    torch.set_num_threads(1)
+
+    # ---- ONE global batch, the same on every rank (same seed); this rank decodes its shard
+    hmp_np, omp_np = lowres_inputs(5000, B, E, flip, w)
+    feats_global = [[[torch.from_numpy(hmp_np)], [[]], [[]]], [[torch.from_numpy(omp_np)], [[]], [[]]]]
+    shard = sharding.shard_features(feats_global, rank, world, flip_test=flip)
+    hmp_h = shard[0][0][0].contiguous().pin_memory()
+    omp_h = shard[1][0][0].contiguous().pin_memory()
+    del hmp_np, omp_np, feats_global, shard
+    step_bytes = hmp_h.numel() * 4
+    ring = 1
+    while ring * step_bytes < 2 * L2_BYTES and ring < 16:
+        ring *= 2
+    feats_ring = []
+    for _ in range(ring):
+        feats_ring.append([[[hmp_h.to(dev)], [[]], [[]]], [[omp_h.to(dev)], [[]], [[]]]])
+
+    # ---- hot path on HBM-resident full-resolution maps (K1 roofline; B images on every GPU)
+    hot_n = B
+    distinct = min(hot_n, 8)
+    heat_np, offs_np = scenes.synth_hires_batch(1000 * (rank + 1), distinct, w['persons'], E, E, skel, n_channels=C)
+    reps = (hot_n + distinct - 1) // distinct
+    heat = torch.from_numpy(heat_np).to(dev).repeat(reps, 1, 1, 1)[:hot_n].contiguous()
+    offs = torch.from_numpy(offs_np).to(dev).repeat(reps, 1, 1, 1)[:hot_n].contiguous()
+    del heat_np, offs_np
+    hot_eng = DecoderEngine(C, skel, topk=w['topk'], thre_hmp=w['thre_hmp'], min_len=MIN_LEN,
+                            dist_max=w['dist_max'], use_scale=True, person_thre=w['person_thre'], device=dev)
+    hot_eng.enable_stage_timing(True)
+    for _ in range(max(3, args.warmup)):
+        hot_eng.decode_maps(heat, offs)
+    hot_eng.decode_maps(heat, offs, fetch=False)           # the timed loop keeps two calls in flight: warm both slots
+    hot_eng.decode_maps(heat, offs, fetch=False)
+    hot_eng.fetch()
+    hot_eng.fetch()
+    hot_steps = max(4, min(args.steps, 10))
+    torch.cuda.synchronize(dev)
+    hot_l0 = hot_eng.launch_count
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hot_stages = []
+    h0.record()
+    hot_eng.decode_maps(heat, offs, fetch=False)
+    for _ in range(hot_steps - 1):
+        hot_eng.decode_maps(heat, offs, fetch=False)
+        hot_eng.fetch()
+        hot_stages.append(hot_eng.last_stage_times_ms())
+    hot_eng.fetch()
+    hot_stages.append(hot_eng.last_stage_times_ms())
+    h1.record()
+    torch.cuda.synchronize(dev)
+    hot_ms = h0.elapsed_time(h1) / hot_steps
+    hot_launches = hot_eng.launch_count - hot_l0
     if args.hot_only:
-        sampler.stop()
-        print('hot-only: %.3f ms/step, stages %s' % (hot_ms / args.steps, stages[-1]), file=sys.stderr)
+        print('hot-only: %.3f ms/step, stages %s' % (hot_ms, hot_stages[-1]), file=sys.stderr)
         return
+    del heat, offs
+    hot_eng.close()
+    torch.cuda.empty_cache()
 
-    # ---- end to end through the reference-facing API, host buffers
-    ap = argparse.ArgumentParser()
-    decoder.decoder_cli(ap)
-    dargs = ap.parse_args(['--topk', str(TOPK), '--thre-hmp', str(THRE_HMP), '--person-thre', str(PERSON_THRE),
-                           '--dist-max', str(DIST_MAX)])
-    dargs.headnets, dargs.strides, dargs.batch_size = ['hmp', 'omp'], [4, 4], B
-    dargs.include_scale = dargs.include_jitter_offset = False
-    post = decoder.decoder_factory(dargs)
-    hmp_np, omp_np = lowres_inputs(5000 * (rank + 1), B, E, flip)
-    hmp_h = torch.from_numpy(hmp_np).pin_memory()
-    omp_h = torch.from_numpy(omp_np).pin_memory()
-
-    # ---- the call evaluate.py makes: DEVICE-resident network-resolution maps (right after
-    #      model(images)), fused flip + x4 resize + NMS, three batches in flight
-    hmp_d, omp_d = hmp_h.to(dev), omp_h.to(dev)
-    tables = (cfg.heatmap_hflip(cfg.COCO_KEYPOINTS),) + tuple(cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel))
-    tables = tables if flip else None
-    for _ in range(args.warmup):
-        eng.decode_features(hmp_d, omp_d, 4, 4, 'bicubic', tables)
-    barrier()
-    dev_l0 = eng.launch_count
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- stage times of the product path (kernel by kernel, stage events; graphs are off meanwhile)
+    eng.enable_stage_timing(True)
     dev_stages = []
-    f0.record()
-    depth = min(3, args.steps)            # calls in flight: this path is short enough for the host to matter
-    for _ in range(depth - 1):
-        eng.decode_features(hmp_d, omp_d, 4, 4, 'bicubic', tables, fetch=False)
-    for it in range(args.steps - (depth - 1)):
-        eng.decode_features(hmp_d, omp_d, 4, 4, 'bicubic', tables, fetch=False)
-        eng.fetch(B)
-        if it >= args.steps - depth - 4:  # reading the stage events costs host time this loop does not have
-            dev_stages.append(eng.last_stage_times_ms())
-    for _ in range(depth - 1):
-        eng.fetch(B)
-    dev_stages.append(eng.last_stage_times_ms())
-    f1.record()
-    barrier()
-    dev_ms = f0.elapsed_time(f1)
-    dev_launches = eng.launch_count - dev_l0
+    for i in range(max(3, min(args.warmup, 5)) + 4):
+        post.generate_poses(feats_ring[i % ring], flip_test=flip)
+        dev_stages.append(eng.last_stage_times_ms())
+    dev_stages = dev_stages[-4:]
+    eng.enable_stage_timing(False)
 
-    # ---- baseline leg (N = 1 only, reported inside cpu_baseline): the same decode with stock
-    #      PyTorch operators on this GPU (eager ATen kernels for flip fusion, resize, NMS, top-K and
-    #      limbs, limbs to the host, multi-threaded CPU grouping) — what the reference's own
-    #      formulation costs on the same silicon (oracle/torch_eager.py)
+    # ---- value: the product path, pipelined, one global batch per step
+    depth = 8
+    persons = pipelined(post, feats_ring, flip, args.warmup + 2 * depth, depth)      # warm-up: every slot has its graphs
+    n_persons = sum(len(p) for p in persons)
+    sampler = ClockSampler(dev_index).start()
+    pinned_cpus = pin_to_own_core(local, local_world) if world > 1 else None
+    host_probe = {}
+    pipelined(post, feats_ring, flip, 4 * depth, depth, host_probe)
+    barrier()
+    l0 = eng.launch_count
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    v0.record()
+    pipelined(post, feats_ring, flip, args.steps, depth)
+    v1.record()
+    torch.cuda.synchronize(dev)
+    value_wall_ms = (time.perf_counter() - t0) * 1e3
+    value_ms = v0.elapsed_time(v1)
+    barrier()
+    value_launches = eng.launch_count - l0
+    graph_counts = eng.graph_counts
+
+    # ---- e2e: the reference's synchronous call on pinned HOST maps (this rank's shard)
+    feats_host = [[[hmp_h], [[]], [[]]], [[omp_h], [[]], [[]]]]
+    eng.enable_stage_timing(True)
+    for _ in range(max(3, args.warmup)):
+        out = post.generate_poses(feats_host, flip_test=flip)
+    e2e_l0 = eng.launch_count
+    barrier()
+    t0 = time.perf_counter()
+    e2e_stages = []
+    for _ in range(args.steps):
+        out = post.generate_poses(feats_host, flip_test=flip)
+        e2e_stages.append(eng.last_stage_times_ms())
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    eng.enable_stage_timing(False)
+    e2e_launches = eng.launch_count - e2e_l0
+    d2h = sum(p.nbytes for p in out) + (2 * n_local + 2) * 4
+    zero_copy = eng.zero_copy_count > 0
+    _, det_idx, _ = eng.last_intermediates(n_local)
+    per_joint = (det_idx >= 0).sum(dim=2).cpu().numpy()                     # (n_local, C)
+    gathered = 0
+    for l, (jf, _jt) in enumerate(skel):
+        maps = 2 if (flip and l not in w['limb_reserve']) else 1
+        gathered += int(per_joint[:, jf].sum()) * 2 * 4 * 4 * maps
+    h2d_full = hmp_h.numel() * 4 + omp_h.numel() * 4
+    h2d = hmp_h.numel() * 4 + gathered if zero_copy else h2d_full
+    # pinned host -> device peak of this rank's link (the e2e roofline denominator), all ranks at once
+    probe_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    barrier()
+    best = 0.0
+    for _ in range(5):
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        probe_d.copy_(probe_h, non_blocking=True)
+        p1.record()
+        torch.cuda.synchronize(dev)
+        best = max(best, probe_h.numel() / (p0.elapsed_time(p1) * 1e-3) / 1e9)
+    h2d_peak = best
+    del probe_h, probe_d
+    clocks = sampler.stop()
+
+    # ---- extras: weak scaling (B images per GPU), a sustained run, the baselines
+    weak_block = sustained = None
+    if not args.lean:
+        hw_np, ow_np = lowres_inputs(7000 + 100 * rank, B, E, flip, w)
+        hw_d, ow_d = torch.from_numpy(hw_np).to(dev), torch.from_numpy(ow_np).to(dev)
+        del hw_np, ow_np
+        weak_ring = [[[[hw_d], [[]], [[]]], [[ow_d], [[]], [[]]]]]
+        if hw_d.numel() * 4 < 2 * L2_BYTES:
+            weak_ring.append([[[hw_d.clone()], [[]], [[]]], [[ow_d.clone()], [[]], [[]]]])
+        pipelined(post, weak_ring, flip, 3 * depth, depth)
+        barrier()
+        wk0, wk1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wk0.record()
+        pipelined(post, weak_ring, flip, args.steps, depth)
+        wk1.record()
+        torch.cuda.synchronize(dev)
+        weak_ms = wk0.elapsed_time(wk1)
+        barrier()
+        # sustained: >= 1 s of the product path back to back, clocks sampled meanwhile
+        s_sampler = ClockSampler(dev_index).start()
+        s_steps = max(args.steps, int(1.2e3 / max(weak_ms / args.steps, 1e-3)))
+        t0 = time.perf_counter()
+        pipelined(post, weak_ring, flip, s_steps, depth)
+        torch.cuda.synchronize(dev)
+        s_ms = (time.perf_counter() - t0) * 1e3
+        s_clocks = s_sampler.stop()
+        weak_t = torch.tensor([weak_ms, s_ms / s_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(weak_t, op=dist.ReduceOp.MAX)
+        weak_ms, s_step_ms = [float(v) for v in weak_t.cpu()]
+        weak_block = {'value': n_gpus * B * args.steps / (weak_ms * 1e-3), 'unit': UNIT,
+                      'ms_per_step': weak_ms / args.steps, 'images_per_gpu_per_step': B,
+                      'note': 'the same product path with %d images on EVERY GPU per step (round 1\'s scaling mode)' % B}
+        sustained = {'value': n_gpus * B / (s_step_ms * 1e-3), 'unit': UNIT, 'seconds': s_ms * 1e-3,
+                     'steps': s_steps, 'ms_per_step': s_step_ms, 'clocks': s_clocks,
+                     'note': 'product path, %d images per GPU per step, back to back for >= 1 s' % B}
+        del hw_d, ow_d, weak_ring
+
     eager_block = None
-    if rank == 0 and world == 1 and not os.environ.get('OG_BENCH_SKIP_EAGER'):      # like cpu_baseline: N = 1 only
+    if rank == 0 and world == 1 and not args.lean and C == 17 and not os.environ.get('OG_BENCH_SKIP_EAGER'):
         try:
             from oracle import torch_eager
-            eager_kw = dict(topk=TOPK, thre_hmp=THRE_HMP, min_len=MIN_LEN, person_thre=PERSON_THRE,
-                            dist_max=DIST_MAX, use_scale=True, stride=4, resize_mode='bicubic', flip_test=flip,
+            hmp_d, omp_d = feats_ring[0][0][0][0], feats_ring[0][1][0][0]
+            eager_kw = dict(topk=w['topk'], thre_hmp=w['thre_hmp'], min_len=MIN_LEN, person_thre=w['person_thre'],
+                            dist_max=w['dist_max'], use_scale=True, stride=4, resize_mode='bicubic', flip_test=flip,
                             kp_flips=tables[0] if flip else None, limb_flips=tables[1] if flip else None,
                             limb_reserve=tables[2] if flip else None)
             with torch.no_grad():
@@ -377,88 +583,56 @@ def run_b200(args):
             eager_block = {'value': B / (eager_ms * 1e-3), 'unit': UNIT, 'ms_per_step': eager_ms,
                            'steps': eager_steps, 'persons_per_step': sum(len(p) for p in eager_out),
                            'note': 'stock PyTorch operators on the same GPU, device-resident network-resolution '
-                                   'maps (compare with features_dev), grouping on the host cores with the C '
+                                   'maps (the same work as `value`), grouping on the host cores with the C '
                                    'oracle; one GPU (rank 0), not part of the timed arms'}
             del eager_out
             torch.cuda.empty_cache()
         except Exception as exc:                      # a baseline must never break the bench line
             eager_block = {'unavailable': repr(exc)[:200]}
-    del hmp_d, omp_d
-    feats = [[[hmp_h], [[]], [[]]], [[omp_h], [[]], [[]]]]
-    e2e_eng = post._engine(dev)
-    e2e_eng.enable_stage_timing(True)
-    for _ in range(args.warmup):
-        out = post.generate_poses(feats, flip_test=flip)
-    e2e_l0 = e2e_eng.launch_count
-    barrier()
-    t0 = time.perf_counter()
-    e2e_stages = []
-    for _ in range(args.steps):
-        out = post.generate_poses(feats, flip_test=flip)
-        e2e_stages.append(e2e_eng.last_stage_times_ms())
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    barrier()
-    clocks = sampler.stop()
-    e2e_launches = e2e_eng.launch_count - e2e_l0
-    d2h = sum(p.nbytes for p in out) + (2 * B + 1) * 4
-    # host -> device bytes of one step: the heat maps are copied; the offset maps stay in pinned
-    # host memory and K2 reads its bilinear samples over PCIe (counted from the candidates:
-    # 2 components x 4 taps x 4 bytes per from-candidate of every limb, twice where the mirrored
-    # map is averaged in)
-    zero_copy = e2e_eng.zero_copy_count > 0
-    _, det_idx, _ = e2e_eng.last_intermediates(B)
-    per_joint = (det_idx >= 0).sum(dim=2).cpu().numpy()                     # (B, C)
-    _, reserved = cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel)
-    gathered = 0
-    for l, (jf, _jt) in enumerate(skel):
-        maps = 2 if (flip and l not in reserved) else 1
-        gathered += int(per_joint[:, jf].sum()) * 2 * 4 * 4 * maps
-    h2d_full = hmp_h.numel() * 4 + omp_h.numel() * 4
-    h2d = hmp_h.numel() * 4 + gathered if zero_copy else h2d_full
-
-    # the same call with the offset maps copied as a whole (zero-copy off), for comparison
-    e2e_eng.set_zero_copy(False)
-    for _ in range(2):
-        post.generate_poses(feats, flip_test=flip)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    full_steps = max(3, args.steps // 2)
-    for _ in range(full_steps):
-        post.generate_poses(feats, flip_test=flip)
-    torch.cuda.synchronize(dev)
-    full_copy_ms = (time.perf_counter() - t0) * 1e3 / full_steps
-    e2e_launches_all = e2e_eng.launch_count - e2e_l0
-    e2e_eng.set_zero_copy(True)
 
     # ---- max over ranks
-    times = torch.tensor([hot_ms, e2e_s * 1e3, dev_ms], dtype=torch.float64, device=dev)
+    rank_ms = torch.zeros(world, dtype=torch.float64, device=dev)
+    rank_ms[rank] = value_ms / args.steps
+    if world > 1:
+        dist.all_reduce(rank_ms, op=dist.ReduceOp.SUM)
+    rank_ms = [round(float(v), 5) for v in rank_ms.cpu()]
+    times = torch.tensor([value_ms, value_wall_ms, e2e_ms, hot_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(value_launches + e2e_launches + hot_launches), float(h2d), float(d2h), float(n_persons),
+                         h2d_peak], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    hot_ms, e2e_ms, dev_ms = [float(v) for v in times.cpu()]
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    value_ms, value_wall_ms, e2e_ms, hot_ms = [float(v) for v in times.cpu()]
+    launches_all, h2d_all, d2h_all, persons_all, h2d_peak_all = [float(v) for v in sums.cpu()]
 
     if rank == 0:
-        k1_ms = statistics.mean(s['k1_stream'] + s['k1_select'] for s in stages)
-        k1_stream_ms = statistics.mean(s['k1_stream'] for s in stages)
-        stage_mean = {k: statistics.mean(s[k] for s in stages) for k in stages[0]}
-        alg_bytes = B * 17 * E * E * 4 + B * 17 * TOPK * 8
+        def mean_stage(stages):
+            return {k: statistics.mean(s[k] for s in stages) for k in stages[0]}
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
         try:
             mp = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
             peak, peak_src = float(mp['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
         except Exception:
             pass
+        hot_stage = mean_stage(hot_stages)
+        k1_ms = hot_stage['k1_stream'] + hot_stage['k1_select']
+        alg_bytes = hot_n * C * E * E * 4 + hot_n * C * w['topk'] * 8
         achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
         traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'k1_traffic.json')))['dram_bytes_per_launch']
-        except Exception:
-            pass
+        if args.workload == 'cfg2' and B == 64 and E == 640:
+            try:
+                traffic = json.load(open(os.path.join(ROOT, 'profiles', 'k1_traffic.json')))['dram_bytes_per_launch']
+            except Exception:
+                pass
+        dev_stage = mean_stage(dev_stages)
+        fused_bytes = hmp_h.numel() * 4
+        fused_gbs = fused_bytes / (dev_stage['k1_stream'] * 1e-3) / 1e9
+        e2e_step_ms = e2e_ms / args.steps
         cpu_block = None          # timed on rank 0 at N = 1 only (bench contract)
-        if n_gpus == 1:
-            run, cores, what = cpu_decode_fn()
+        if n_gpus == 1 and not args.lean:
+            run, cores, what = cpu_decode_fn(w)
             cpu_n = args.cpu_sample or (16 if cores > 1 else 1)
-            cpu_value, cores, what, cpu_times, cpu_stage = time_cpu(args, cpu_n, 2 if cores > 1 else 1)
+            cpu_value, cores, what, cpu_times, cpu_stage = time_cpu(w, cpu_n, 2 if cores > 1 else 1)
             cpu_block = {'value': cpu_value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d images of the same workload (flip fusion + x4 resize + NMS/top-K '
                                    '+ limbs + grouping), best of %d, %s' % (cpu_n, len(cpu_times), what),
@@ -466,44 +640,59 @@ def run_b200(args):
                          # second baseline of the same leg: the path with stock PyTorch operators on this GPU
                          'eager_torch_gpu': eager_block}
         line = {
-            'metric': METRIC, 'value': n_gpus * B * args.steps / (hot_ms * 1e-3), 'unit': UNIT,
+            'metric': METRIC, 'value': B * args.steps / (value_ms * 1e-3), 'unit': UNIT,
             'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': hot_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'ms_per_step': value_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args, n_gpus),
-            'e2e': {'value': n_gpus * B * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
-                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': e2e_ms / args.steps,
-                    'stage_ms': {k: statistics.mean(s[k] for s in e2e_stages) for k in e2e_stages[0]},
-                    'fused_redos': e2e_eng.fused_redo_count,
-                    'api': 'decoder_factory(args).generate_poses(features, flip_test=%s), pinned host maps' % flip,
-                    'h2d_detail': {'heat_maps_copied': hmp_h.numel() * 4,
-                                   'offset_samples_read_over_pcie': gathered if zero_copy else 0,
-                                   'offset_maps_left_on_host': omp_h.numel() * 4 if zero_copy else 0,
+            'config': workload_config(w, n_gpus, per_gpu),
+            'value_detail': {
+                'api': 'decoder_factory(args) -> PostProcess.submit(features, flip_test=%s) / collect(): the pipelined '
+                       'form of generate_poses, device-resident network-resolution maps -> poses in host memory' % flip,
+                'calls_in_flight': depth, 'input_buffers_in_rotation': ring,
+                'wall_ms_per_step': value_wall_ms / args.steps,
+                'ms_per_step_of_every_rank': rank_ms,
+                'host_cores_of_rank0': pinned_cpus, 'host_call_us_rank0': host_probe,
+                'graph_replays_and_captures': list(graph_counts),
+                'persons_per_step': persons_all,
+                'stage_ms': dev_stage,
+                'stage_note': 'per-call device times of one rank\'s shard, taken kernel by kernel with stage events '
+                              'in a separate pass (the timed loop replays CUDA graphs)'},
+            'e2e': {'value': B * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': int(h2d_all), 'd2h_bytes_per_step': int(d2h_all),
+                    'ms_per_step': e2e_step_ms,
+                    'stage_ms': mean_stage(e2e_stages),
+                    'fused_redos': eng.fused_redo_count,
+                    'api': 'decoder_factory(args).generate_poses(features, flip_test=%s) (synchronous), pinned host '
+                           'maps of this rank\'s shard' % flip,
+                    'roofline': {'bound': 'pcie', 'achieved': h2d_all / (e2e_step_ms * 1e-3) / 1e9,
+                                 'peak': h2d_peak_all, 'unit': 'GB/s',
+                                 'frac': h2d_all / (e2e_step_ms * 1e-3) / 1e9 / h2d_peak_all,
+                                 'peak_source': 'sum over ranks of a 256 MB pinned host -> device copy, best of 5, '
+                                                'all ranks copying at once'},
+                    'h2d_detail': {'heat_maps_copied': int(h2d_all) - (gathered if zero_copy else 0) if n_gpus == 1 else None,
+                                   'offset_samples_read_over_pcie_rank0': gathered if zero_copy else 0,
+                                   'offset_maps_left_on_host_rank0': omp_h.numel() * 4 if zero_copy else 0,
                                    'note': 'fused path: K2 needs 2*L*K bilinear samples per image, so pinned '
-                                           'offset maps are read in place (zero-copy) instead of copied'},
-                    'full_copy': {'value': n_gpus * B / (full_copy_ms * 1e-3), 'unit': UNIT,
-                                  'ms_per_step': full_copy_ms, 'h2d_bytes_per_step': h2d_full,
-                                  'note': 'same call with og_set_zero_copy(0): heat and offset maps both copied '
-                                          '(rank 0 time, %d steps)' % full_steps}},
-            'features_dev': {'value': n_gpus * B * args.steps / (dev_ms * 1e-3), 'unit': UNIT,
-                             'ms_per_step': dev_ms / args.steps,
-                             'stage_ms': {k: statistics.mean(s[k] for s in dev_stages) for k in dev_stages[0]},
-                             'note': 'same API on DEVICE-resident network-resolution maps (what evaluate.py '
-                                     'hands over after model(images)): fused flip + x4 bicubic + NMS (K1f), '
-                                     'offsets sampled at the candidates; 223 MB of heat maps read per step, '
-                                     'no full-resolution map written; three batches in flight'},
-            'gpu_launches': hot_launches + e2e_launches_all + dev_launches,
-            'gpu_launches_detail': {'hot_path': hot_launches, 'e2e': e2e_launches,
-                                    'e2e_full_copy': e2e_launches_all - e2e_launches,
-                                    'features_dev': dev_launches},
+                                           'offset maps are read in place (zero-copy) instead of copied'}},
+            'gpu_launches': int(launches_all),
+            'gpu_launches_detail': {'note': 'kernels of this library launched inside the three timed regions, all ranks; '
+                                            'a graph replay counts its 7 kernel nodes',
+                                    'value_rank0': value_launches, 'e2e_rank0': e2e_launches,
+                                    'k1_roofline_leg_rank0': hot_launches},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                         'kernel': 'K1 = nms_candidates_kernel + select_topk_kernel',
+                         'kernel': 'K1 = nms_candidates_kernel + select_topk_kernel on materialised %dx%d maps, '
+                                   '%d images per launch (SURVEY 8d definition)' % (E, E, hot_n),
                          'algorithmic_bytes_per_launch': alg_bytes, 'ms_per_launch': k1_ms,
-                         'stream_pass_only_gbs': alg_bytes / (k1_stream_ms * 1e-3) / 1e9},
-            'stage_ms': stage_mean,
-            'persons_per_step': n_persons,
+                         'stream_pass_only_gbs': alg_bytes / (hot_stage['k1_stream'] * 1e-3) / 1e9,
+                         'hot_path_ms_per_step': hot_ms, 'hot_path_stage_ms': hot_stage,
+                         'hot_path_images_per_s_per_gpu': hot_n / (hot_ms * 1e-3)},
+            'roofline_fused': {'bound': 'hbm', 'achieved': fused_gbs, 'peak': peak, 'unit': 'GB/s',
+                               'frac': fused_gbs / peak, 'kernel': 'K1f = amax_scan + block_list + fused_block '
+                               '(flip fusion + x4 resize + NMS over network-resolution maps), one rank\'s shard',
+                               'algorithmic_bytes_per_launch': fused_bytes, 'ms_per_launch': dev_stage['k1_stream']},
+            'weak_scaling': weak_block,
+            'sustained': sustained,
             'cpu_baseline': cpu_block,
             'clocks': clocks,
         }

@@ -72,6 +72,7 @@ struct PinnedBuf {
 
 constexpr int kSlots = OG_MAX_IN_FLIGHT;   // decode calls that may be in flight before a fetch
 constexpr int kMaxChunks = 8;      // image ranges of one host-API call (copy / decode pipeline)
+constexpr int kGraphsPerSlot = 4;  // captured device-path chains a result slot keeps
 // start, after prep, K1 pass 1 | select start, select = K2 start, K2, K3, end (see mark())
 constexpr int kStageEvents = 8;
 
@@ -139,8 +140,12 @@ struct ResultSlot {
     cudaEvent_t call_start = nullptr;
     cudaEvent_t done = nullptr;
     cudaEvent_t ev[kStageEvents] = {nullptr};
-    cudaGraphExec_t graph = nullptr;    // the device-path chain of this slot, replayed while `key` matches
-    GraphKey key = {};
+    // device-path chains of this slot, replayed while their key matches; a few per slot, so a
+    // caller that rotates through a ring of input buffers still replays (least recently used
+    // entry is re-captured)
+    cudaGraphExec_t graph[kGraphsPerSlot] = {nullptr};
+    GraphKey key[kGraphsPerSlot] = {};
+    uint64_t graph_used[kGraphsPerSlot] = {0};
     uint64_t buffers_version = 1;       // bumped whenever a buffer of the slot moves
     cudaStream_t stream = nullptr;      // the caller's stream of the call
     int n = 0;
@@ -179,8 +184,8 @@ struct og_handle {
     uint64_t tables_version;
 
     ResultSlot slots[kSlots];
-    int head;                    // slot the next decode call uses
-    int tail;                    // oldest slot whose result has not been fetched
+    int queue[kSlots];           // slots of the calls in flight, oldest first (ring buffer)
+    int tail;                    // position of the oldest unfetched call in `queue`
     int pending;                 // decode calls in flight
     int last_slot;               // slot of the most recent decode call (intermediates)
     int fetched_slot;            // slot of the most recently fetched result (stage times)
@@ -194,6 +199,7 @@ struct og_handle {
     int64_t fused_redos;
     int64_t zero_copy_calls;
     int64_t graph_replays, graph_builds;
+    uint64_t graph_clock;
     bool tables_valid;           // ft matches the cached host copies
     int32_t kp_cache[OG_MAX_KEYPOINTS];
     int32_t limb_cache[OG_MAX_LIMBS];
@@ -259,11 +265,17 @@ int acquire_slot(og_handle *h, ResultSlot *forced, ResultSlot **out) {
         *out = forced;
         return OG_OK;
     }
-    ResultSlot *slot = &h->slots[h->head];
-    OG_REQUIRE(!slot->pending,
-               "%d decode calls are already in flight; call og_fetch_poses before the next decode", kSlots);
-    *out = slot;
-    return OG_OK;
+    // the lowest free slot: a caller that keeps d calls in flight touches d slots (a synchronous
+    // caller one), so only those ever allocate their buffers and capture graphs
+    OG_REQUIRE(h->pending < kSlots,
+               "%d decode calls are already in flight; call og_fetch_result before the next decode", kSlots);
+    for (int i = 0; i < kSlots; ++i)
+        if (!h->slots[i].pending) {
+            *out = &h->slots[i];
+            return OG_OK;
+        }
+    set_error("internal: no free result slot");
+    return OG_ERR_CAPACITY;
 }
 
 int run_k1(og_handle *h, const float *heat, int n, int hgt, int w, float thre, float *score,
@@ -509,8 +521,8 @@ int finish_call(og_handle *h, ResultSlot *slot) {
     slot->scratch_dirty = false;
     if (!slot->pending) {           // a redo keeps its place in the queue
         slot->pending = true;
+        h->queue[(h->tail + h->pending) % kSlots] = (int)(slot - h->slots);
         h->pending += 1;
-        h->head = (h->head + 1) % kSlots;
     }
     h->last_slot = (int)(slot - h->slots);
     return OG_OK;
@@ -552,7 +564,13 @@ int decode_chain(og_handle *h, ResultSlot *slot, const K1Fused &k1, const Offset
     const GraphKey key = {k1.hmp.ptr, src.maps.ptr, k1.hmp.dtype, k1.hmp.image_stride, src.maps.image_stride,
                           n, k1.h, k1.w, k1.scale, k1.cubic ? 1 : 0, k1.flip ? 1 : 0,
                           h->tables_version, slot->buffers_version};
-    if (slot->graph == nullptr || !(slot->key == key)) {
+    int gi = -1, victim = 0;
+    for (int i = 0; i < kGraphsPerSlot; ++i) {
+        if (slot->graph[i] != nullptr && slot->key[i] == key) gi = i;
+        if (slot->graph_used[i] < slot->graph_used[victim]) victim = i;
+    }
+    if (gi < 0) {
+        gi = victim;
         cudaGraph_t graph = nullptr;
         OG_CUDA_TRY(cudaStreamBeginCapture(a, cudaStreamCaptureModeRelaxed));
         const int st = decode_range(h, slot, 0, 0, n, nullptr, &k1, nullptr, &src, nullptr, H, W, a, nullptr, false);
@@ -563,32 +581,33 @@ int decode_chain(og_handle *h, ResultSlot *slot, const K1Fused &k1, const Offset
         }
         OG_CUDA_TRY(end);
         bool updated = false;
-        if (slot->graph != nullptr) {
+        if (slot->graph[gi] != nullptr) {
             cudaGraphExecUpdateResultInfo info;
-            updated = cudaGraphExecUpdate(slot->graph, graph, &info) == cudaSuccess;
+            updated = cudaGraphExecUpdate(slot->graph[gi], graph, &info) == cudaSuccess;
             if (!updated) {
                 (void)cudaGetLastError();
-                cudaGraphExecDestroy(slot->graph);
-                slot->graph = nullptr;
+                cudaGraphExecDestroy(slot->graph[gi]);
+                slot->graph[gi] = nullptr;
             }
         }
         if (!updated) {
-            const cudaError_t inst = cudaGraphInstantiate(&slot->graph, graph, 0);
+            const cudaError_t inst = cudaGraphInstantiate(&slot->graph[gi], graph, 0);
             if (inst != cudaSuccess) {
                 cudaGraphDestroy(graph);
-                slot->graph = nullptr;
+                slot->graph[gi] = nullptr;
                 OG_CUDA_TRY(inst);
             }
         }
         cudaGraphDestroy(graph);
-        slot->key = key;
+        slot->key[gi] = key;
         h->graph_builds += 1;
     } else {
         h->launches += 7;           // scan, list, blocks, select, K2, K3 warp, K3 CTA: the graph's kernel nodes
         slot->k3_first = 0;
         slot->k3_images = n;
     }
-    OG_CUDA_TRY(cudaGraphLaunch(slot->graph, a));
+    slot->graph_used[gi] = ++h->graph_clock;
+    OG_CUDA_TRY(cudaGraphLaunch(slot->graph[gi], a));
     h->graph_replays += 1;
     return finish_call(h, slot);
 }
@@ -764,7 +783,7 @@ int og_create(const og_config *cfg, og_handle **out) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     h->launches = 0;
-    h->head = h->tail = h->pending = 0;
+    h->tail = h->pending = 0;
     h->last_slot = 0;
     h->fetched_slot = -1;
     h->timing = false;
@@ -773,6 +792,7 @@ int og_create(const og_config *cfg, og_handle **out) {
     h->graph_enabled = true;
     if (const char *env = getenv("OG_GRAPH")) h->graph_enabled = atoi(env) != 0;     // tuning aid
     h->graph_replays = h->graph_builds = 0;
+    h->graph_clock = 0;
     h->result_rows = 64;
     if (const char *env = getenv("OG_RESULT_ROWS")) {          // test aid: force the regroup path
         const int v = atoi(env);
@@ -896,7 +916,8 @@ int og_destroy(og_handle *h) {
     h->hr_off.release();
     for (int i = 0; i < kSlots; ++i) {
         ResultSlot &sl = h->slots[i];
-        if (sl.graph) cudaGraphExecDestroy(sl.graph);
+        for (int g = 0; g < kGraphsPerSlot; ++g)
+            if (sl.graph[g]) cudaGraphExecDestroy(sl.graph[g]);
         if (sl.out_host) cudaFreeHost(sl.out_host);
         sl.total.release();
         sl.in_hmp.release();
@@ -1283,7 +1304,7 @@ int og_fetch_result(og_handle *h, og_result *out) {
     memset(out, 0, sizeof(*out));
     OG_REQUIRE(h->pending > 0, "og_fetch_result: no decode call is pending");
     OG_TRY(check_device(h));
-    ResultSlot *slot = &h->slots[h->tail];
+    ResultSlot *slot = &h->slots[h->queue[h->tail]];
     const int n = slot->n;
     long long total = 0;
     if (n > 0) {
@@ -1339,7 +1360,7 @@ int og_fetch_result(og_handle *h, og_result *out) {
     out->n_keypoints = h->cfg.n_keypoints;
     slot->pending = false;
     h->pending -= 1;
-    h->fetched_slot = h->tail;
+    h->fetched_slot = h->queue[h->tail];
     h->tail = (h->tail + 1) % kSlots;
     return OG_OK;
 }

@@ -41,6 +41,29 @@ void set_error(const char *fmt, ...);
         if (st__ != OG_OK) return st__;                                            \
     } while (0)
 
+// ---- one shared-memory carve-out for every kernel of the decode chains ------------------
+// An SM changes its L1 / shared-memory split only when it is empty.  The chains of several calls
+// are in flight at once, so kernels that need no shared memory (the HBM-streaming passes) share the
+// SMs with kernels that need 3 .. 26 KB per CTA; left to the default ("the smallest split that
+// fits this kernel") every such neighbour forces SMs to drain before its CTAs can start — measured
+// on the full-resolution path: K1 0.266 -> 0.305 ms when the kernel running beside it grew from
+// 2.5 to 10.5 KB of shared memory per CTA.  All chain kernels therefore ask for the same split.
+constexpr int kChainCarveoutPercent = 58;      // -> 132 KB shared memory, 96 KB L1 per SM
+
+#ifdef __CUDACC__
+template <auto Kernel>
+inline void prefer_chain_carveout() {
+    static unsigned long long done = 0ull;      // one bit per device; a repeated call is harmless
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    if ((done >> dev) & 1ull) return;
+    if (cudaFuncSetAttribute(Kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kChainCarveoutPercent) !=
+        cudaSuccess)
+        (void)cudaGetLastError();
+    done |= 1ull << dev;
+}
+#endif
+
 // ---- K1 candidate buffers --------------------------------------------------
 // Survivors of "3x3 peak and value >= thre" are appended per (image, channel)
 // plane as 64-bit keys: high word = ~ordered(value), low word = flat index, so an

@@ -31,6 +31,8 @@
 #include "og_common.cuh"
 #include "og_interp.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 namespace og {
@@ -399,13 +401,21 @@ fused_block_kernel(const T *__restrict__ hmp, size_t img_stride, int N, int h, i
     }
 }
 
+// resident CTAs per SM of one instantiation (queried once: the answer is a property of the kernel)
 template <typename Kernel>
-int resident_grid(Kernel kernel, int sm_count) {
+int resident_per_sm(Kernel kernel) {
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFusedThreads, 0) != cudaSuccess ||
         per_sm < 1)
         per_sm = 1;
-    return sm_count * per_sm;
+    return per_sm;
+}
+
+// tuning aids (read once): OG_K1F_CTAS_PER_SM caps the CTAs of the block kernel per SM (0 = all
+// that fit), OG_K1F_WAVES the CTA waves of its grid
+inline int env_int(const char *name, int fallback) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : fallback;
 }
 
 template <typename T, int S, bool kCubic, bool kFlip>
@@ -415,11 +425,15 @@ int launch_blocks_t(const T *hmp, size_t img_stride, int n_total, int h, int w, 
     auto kernel = fused_block_kernel<T, S, kCubic, kFlip>;
     // Warps stride over the work list.  kCtaWaves x the resident CTA count: the per-warp setup
     // (weights) is still amortised over several blocks, but CTAs retire during the kernel, so the
-    // high-priority K3 CTAs of the previous call (one per image, 200 KB of shared memory) find
-    // room instead of waiting for a fully persistent grid to drain.
-    constexpr int kCtaWaves = 4;
+    // high-priority K3 CTAs of the previous call find room instead of waiting for a fully
+    // persistent grid to drain.
+    static const int per_sm_fit = resident_per_sm(kernel);
+    static const int per_sm_cap = env_int("OG_K1F_CTAS_PER_SM", 0);
+    static const int waves = std::max(1, env_int("OG_K1F_WAVES", 4));
+    const int per_sm = per_sm_cap > 0 ? std::min(per_sm_cap, per_sm_fit) : per_sm_fit;
     const int grid = (int)std::min<size_t>((blocks + kFusedThreads / 32 - 1) / (kFusedThreads / 32),
-                                           (size_t)resident_grid(kernel, sm_count) * kCtaWaves);
+                                           (size_t)sm_count * per_sm * waves);
+    prefer_chain_carveout<fused_block_kernel<T, S, kCubic, kFlip>>();
     kernel<<<grid, kFusedThreads, 0, s>>>(hmp, img_stride, n_total, h, w, thre, block_list, n_active,
                                           cand_count, cand_keys);
     OG_CUDA_TRY(cudaGetLastError());
@@ -477,16 +491,17 @@ int launch_fused_t(const T *hmp, size_t img_stride, const FlipTablesDev &kp_flip
     const bool vec = (w % kSub) == 0 && (reinterpret_cast<uintptr_t>(hmp) % vec_bytes) == 0 &&
                      (img_stride * sizeof(T)) % vec_bytes == 0;
     if (flip) {
-        if (vec) amax_scan_kernel<T, true, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
-        else amax_scan_kernel<T, true, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
+        if (vec) prefer_chain_carveout<amax_scan_kernel<T, true, true>>(), amax_scan_kernel<T, true, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
+        else prefer_chain_carveout<amax_scan_kernel<T, true, false>>(), amax_scan_kernel<T, true, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
     } else {
-        if (vec) amax_scan_kernel<T, false, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
-        else amax_scan_kernel<T, false, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
+        if (vec) prefer_chain_carveout<amax_scan_kernel<T, false, true>>(), amax_scan_kernel<T, false, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
+        else prefer_chain_carveout<amax_scan_kernel<T, false, false>>(), amax_scan_kernel<T, false, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
     }
     OG_CUDA_TRY(cudaGetLastError());
 
     const size_t blocks = block_count(n, c, h, w, scale);
     int4 *list4 = reinterpret_cast<int4 *>(block_list);
+    prefer_chain_carveout<block_list_kernel>();
     block_list_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, s>>>(
         block_flag, kp_flip_dev, c, flip ? 1 : 0, (w + block_w - 1) / block_w,
         (h + kBlockCellsH - 1) / kBlockCellsH, (long long)blocks, list4, n_active);

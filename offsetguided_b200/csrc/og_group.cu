@@ -94,7 +94,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 __global__ void __launch_bounds__(kPrepThreads)
 group_prepare_kernel(const float *__restrict__ limbs, int L, int K, float dist_max, int use_scale,
                      int32_t *__restrict__ prep, float4 *__restrict__ rec, int32_t *__restrict__ cnt) {
-    __shared__ PrepShared sh;
+    __shared__ PrepShared<kPrepThreads> sh;
     const int tid = threadIdx.x;
     const size_t inst = (size_t)blockIdx.y * L + blockIdx.x;          // (image, limb type)
     float r[OG_LIMB_COLS];
@@ -1132,21 +1132,30 @@ int launch_group(const GroupLaunch &g, const float *limbs, bool prepared, float 
                  cudaStream_t s, int64_t *launches) {
     if (g.n == 0) return OG_OK;
     if (!prepared) {
+        prefer_chain_carveout<group_prepare_kernel>();
         group_prepare_kernel<<<dim3(g.l, g.n), kPrepThreads, 0, s>>>(limbs, g.l, g.k, g.dist_max,
                                                                      g.use_scale, g.prep, g.rec, g.cnt);
         OG_CUDA_TRY(cudaGetLastError());
         if (launches) *launches += 1;
     }
     const int32_t *redo = nullptr;
+    GroupLaunch cta = g;
     if (g.warp_rows > 0) {
+        prefer_chain_carveout<group_warp_kernel>();
         group_warp_kernel<<<g.n, 32, group_warp_smem_bytes(g), s>>>(
             to_args(g), g.rec, g.cnt, out_poses, capacity_rows, out_offset, out_count, out_total, g.redo);
         OG_CUDA_TRY(cudaGetLastError());
         if (launches) *launches += 1;
         redo = g.redo;
+        // Behind the warp kernel the CTA kernel only redoes images whose table outgrew 64 rows, and
+        // nearly every CTA of this launch exits at once: it gets NO shared-memory table (the image
+        // goes straight to its global slab), so that a launch of early-exit CTAs does not ask every
+        // SM for 200 KB of shared memory while the next call's streaming kernels are resident.
+        cta.smem_rows = 0;
     }
-    group_kernel<<<g.n, kGroupThreads, group_smem_bytes(g), s>>>(
-        to_args(g), limbs, g.prep, out_poses, capacity_rows, out_offset, out_count, out_total, redo);
+    if (g.warp_rows > 0) prefer_chain_carveout<group_kernel>();      // early-exit launch: blend in
+    group_kernel<<<g.n, kGroupThreads, group_smem_bytes(cta), s>>>(
+        to_args(cta), limbs, g.prep, out_poses, capacity_rows, out_offset, out_count, out_total, redo);
     OG_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;
     return OG_OK;

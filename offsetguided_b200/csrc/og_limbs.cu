@@ -86,15 +86,15 @@ __device__ __forceinline__ float sq4(float a, float b, float c, float d) {
     return __fadd_rn(acc, __fmul_rn(d, d));
 }
 
-template <bool kFour>
-__global__ void __launch_bounds__(128)
+template <bool kFour, int KMAX>
+__global__ void __launch_bounds__(KMAX)
 limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict__ det_index,
                   const float *__restrict__ offs, OffsetSource src, FlipTablesDev ft,
                   const float *__restrict__ scales, LimbExtras ex, int C, int L, int K, int H, int W,
                   SkeletonDev sk, float thre_hmp, float min_len, float resize_factor,
                   float *__restrict__ out_limbs, PrepOut po) {
-    __shared__ ToCand s_to[OG_MAX_TOPK];
-    __shared__ PrepShared s_prep;
+    __shared__ ToCand s_to[KMAX];
+    __shared__ PrepShared<KMAX> s_prep;
     const int l = blockIdx.x;
     const int n = blockIdx.y;
     const int jf = sk.from[l], jt = sk.to[l];
@@ -258,14 +258,22 @@ int launch_limb_score(const float *det_score, const int32_t *det_index, const fl
     if (extras) ex = *extras;
     PrepOut po = {nullptr, nullptr, nullptr, 0.0f, 0, nullptr};
     if (prep) po = *prep;
-    if (ex.vector_nd == 4)
-        limb_score_kernel<true><<<grid, threads, 0, s>>>(det_score, det_index, offs, src, ft, scales, ex, c, l,
-                                                         k, h, w, sk, thre_hmp, min_len, resize_factor,
-                                                         out_limbs, po);
-    else
-        limb_score_kernel<false><<<grid, threads, 0, s>>>(det_score, det_index, offs, src, ft, scales, ex, c, l,
-                                                          k, h, w, sk, thre_hmp, min_len, resize_factor,
-                                                          out_limbs, po);
+#define OG_LAUNCH_K2(FOUR, KMAX)                                                                                  \
+    do {                                                                                                          \
+        prefer_chain_carveout<limb_score_kernel<FOUR, KMAX>>();                                                   \
+        limb_score_kernel<FOUR, KMAX><<<grid, KMAX, 0, s>>>(det_score, det_index, offs, src, ft, scales, ex, c,   \
+                                                            l, k, h, w, sk, thre_hmp, min_len, resize_factor,     \
+                                                            out_limbs, po);                                       \
+    } while (0)
+    const bool four = ex.vector_nd == 4;
+    if (threads == 32) {
+        if (four) OG_LAUNCH_K2(true, 32); else OG_LAUNCH_K2(false, 32);
+    } else if (threads == 64) {
+        if (four) OG_LAUNCH_K2(true, 64); else OG_LAUNCH_K2(false, 64);
+    } else {
+        if (four) OG_LAUNCH_K2(true, 128); else OG_LAUNCH_K2(false, 128);
+    }
+#undef OG_LAUNCH_K2
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;
 }

@@ -413,6 +413,7 @@ int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int
     if (planes == 0) return OG_OK;
     if (!force_radix) OG_TRY(launch_nms_candidates(heat, planes, h, w, thre, cand_count, cand_keys, s, launches));
     if (after_pass1) OG_CUDA_TRY(cudaEventRecord(after_pass1, s));
+    prefer_chain_carveout<select_topk_kernel>();
     select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
                                                         out_score, out_index, out_count,
                                                         force_radix ? 1 : 0, apply_nms ? 1 : 0, nullptr, nullptr);
@@ -436,6 +437,10 @@ int launch_nms_candidates(const float *heat, int planes, int h, int w, float thr
     const bool pos = thre > 0.0f;
     auto kern = pos ? (vec4 ? nms_candidates_kernel<true, true> : nms_candidates_kernel<true, false>)
                     : (vec4 ? nms_candidates_kernel<false, true> : nms_candidates_kernel<false, false>);
+    prefer_chain_carveout<nms_candidates_kernel<true, true>>();
+    prefer_chain_carveout<nms_candidates_kernel<true, false>>();
+    prefer_chain_carveout<nms_candidates_kernel<false, true>>();
+    prefer_chain_carveout<nms_candidates_kernel<false, false>>();
     kern<<<(unsigned)blocks, threads, 0, s>>>(heat, planes, h, w, thre, cand_count, cand_keys);
     OG_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;
@@ -447,6 +452,7 @@ int launch_select_topk(const float *heat, int planes, int h, int w, float thre, 
                        int32_t *out_index, int32_t *out_count, int32_t *overflow_flag,
                        int32_t *clear_word, cudaStream_t s) {
     if (planes == 0) return OG_OK;
+    prefer_chain_carveout<select_topk_kernel>();
     select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
                                                         out_score, out_index, out_count, 0, 1,
                                                         overflow_flag, clear_word);

@@ -15,19 +15,24 @@
 
 namespace og {
 
+// KMAX = the CTA size (32 / 64 / 128 >= K): the scratch is sized by it, because a CTA that asks
+// for more than a few KB of shared memory cannot join an SM whose carve-out the streaming kernels
+// of the next call (no shared memory at all) have set to "all L1" until that SM has drained.
+template <int KMAX>
 struct PrepShared {
-    float4 rec[OG_MAX_TOPK * 3];
-    float sc[OG_MAX_TOPK];
-    int id2[OG_MAX_TOPK];
-    int sorted[OG_MAX_TOPK];
-    uint8_t valid[OG_MAX_TOPK];
-    uint8_t keep[OG_MAX_TOPK];
+    float4 rec[KMAX * 3];
+    float sc[KMAX];
+    int id2[KMAX];
+    int sorted[KMAX];
+    uint8_t valid[KMAX];
+    uint8_t keep[KMAX];
 };
 
 // Every thread of the CTA calls this (blockDim.x >= K); thread tid < K owns limb row `r`
 // (the 13 columns of decoder/collect.py:220-222).
+template <int KMAX>
 __device__ __forceinline__ void prepare_limb_rows(const float (&r)[OG_LIMB_COLS], int tid, int K,
-                                                  float dist_max, int use_scale, PrepShared &sh,
+                                                  float dist_max, int use_scale, PrepShared<KMAX> &sh,
                                                   int32_t *__restrict__ prep_out,
                                                   float4 *__restrict__ rec_out,
                                                   int32_t *__restrict__ cnt_out) {

@@ -76,35 +76,36 @@ class GreedyGroup(object):
 
 
 def soft_nms(subset, suppressed_v=0):
-    """Occupancy-based suppression of duplicate keypoints (reference decoder/group.py:249-283).
-    Host-side utility: the reference never calls it (the call at group.py:183 is commented
-    out), it is kept only so that ``from decoder import soft_nms`` keeps working."""
+    """Suppress duplicate keypoints (reference decoder/group.py:249-283; the reference never calls
+    it — the call at group.py:183 is commented out — it is kept so that ``from decoder import
+    soft_nms`` keeps working).  Poses are visited in order; a keypoint whose (clipped, truncated)
+    position falls into the square of half-width max(10, scale) round an EARLIER surviving
+    keypoint of the same type gets ``v = suppressed_v``.  ``subset`` is modified in place.
+
+    Instead of rasterising the squares into a (C, H, W) occupancy field, the accepted squares of a
+    keypoint type are kept as a list and tested directly (the same integer bounds, clipped to the
+    extent the reference's field would have)."""
     if not len(subset):
         return subset
     n_kp = len(subset[0])
-    height = int(max(np.max(ann[:, 1]) for ann in subset) + 1)
-    width = int(max(np.max(ann[:, 0]) for ann in subset) + 1)
-    occupied = np.zeros((n_kp, height, width), dtype=np.uint8)
-    for ann in subset:
-        widths = np.maximum(10.0, ann[:, 3])
-        assert len(occupied) == len(ann)
-        for xyv, occ, jw in zip(ann[:, :3], occupied, widths):
-            if xyv[2] == -1:
+    field_h = int(max(np.max(pose[:, 1]) for pose in subset) + 1)
+    field_w = int(max(np.max(pose[:, 0]) for pose in subset) + 1)
+    for joint in range(n_kp):
+        lo_x, hi_x, lo_y, hi_y = [], [], [], []           # half-open pixel ranges of the accepted squares
+        for pose in subset:
+            assert len(pose) == n_kp
+            px, py, v = pose[joint, 0], pose[joint, 1], pose[joint, 2]
+            if v == -1:
                 continue
-            x = np.clip(xyv[0], 0.0, occ.shape[1] - 1).astype(int)
-            y = np.clip(xyv[1], 0.0, occ.shape[0] - 1).astype(int)
-            if occ[y, x]:
-                xyv[2] = suppressed_v
-            else:
-                scalar_square_add_single(occ, xyv[0], xyv[1], jw, 1)
+            half = max(10.0, float(pose[joint, 3]))
+            cx = int(np.clip(px, 0.0, field_w - 1))
+            cy = int(np.clip(py, 0.0, field_h - 1))
+            if any(a <= cx < b and c <= cy < d for a, b, c, d in zip(lo_x, hi_x, lo_y, hi_y)):
+                pose[joint, 2] = suppressed_v
+                continue
+            x0, y0 = max(0, int(px - half)), max(0, int(py - half))
+            lo_x.append(x0)
+            lo_y.append(y0)
+            hi_x.append(min(field_w, max(x0 + 1, min(field_w, int(px + half) + 1))))
+            hi_y.append(min(field_h, max(y0 + 1, min(field_h, int(py + half) + 1))))
     return subset
-
-
-def scalar_square_add_single(field, x, y, width, value):
-    """Add ``value`` to the square of half-width ``width`` round (x, y), clipped to the field and
-    at least one pixel large (reference decoder/group.py:278-283; used by soft_nms)."""
-    x0 = max(0, int(x - width))
-    y0 = max(0, int(y - width))
-    x1 = max(x0 + 1, min(field.shape[1], int(x + width) + 1))
-    y1 = max(y0 + 1, min(field.shape[0], int(y + width) + 1))
-    field[y0:y1, x0:x1] += value

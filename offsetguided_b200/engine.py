@@ -92,6 +92,8 @@ class DecoderEngine(object):
         self._result_ref = ctypes.byref(self._result)
         # prepared ctypes argument tuples of device-path decodes, keyed by buffers / shapes / flags
         self._arg_cache = collections.OrderedDict()
+        self._meta_views = {}
+        self._pose_views = {}
 
     def close(self):
         if getattr(self, '_h', None):
@@ -198,11 +200,25 @@ class DecoderEngine(object):
             return []
         if total == 0:
             return [np.zeros((0, c, _lib.OG_POSE_COLS), dtype=np.float32) for _ in range(n)]
-        offs = _view(r.offsets, ctypes.c_int32, n, np.int32).tolist()
-        cnts = _view(r.counts, ctypes.c_int32, n, np.int32).tolist()
+        # numpy views over the result slot's pinned buffers are made once per buffer (they are
+        # re-created only when the library has re-allocated one)
+        addr = ctypes.cast(r.offsets, ctypes.c_void_p).value
+        meta = self._meta_views.get(addr)
+        if meta is None or meta.size < 2 * n:
+            meta = self._meta_views[addr] = np.frombuffer((ctypes.c_int32 * (2 * n)).from_address(addr), dtype=np.int32)
+        per_row = c * _lib.OG_POSE_COLS
+        paddr = ctypes.cast(r.poses, ctypes.c_void_p).value
+        pool = self._pose_views.get(paddr)
+        if pool is None or pool.size < total * per_row:
+            grow = max(total, 64 * n) * per_row
+            pool = self._pose_views[paddr] = np.frombuffer((ctypes.c_float * grow).from_address(paddr), dtype=np.float32)
+            if len(self._pose_views) > 4 * _lib.OG_MAX_IN_FLIGHT:          # buffers the library has replaced
+                self._pose_views = {paddr: pool}
+                self._meta_views = {addr: meta}
+        offs = meta[:n].tolist()
+        cnts = meta[n:2 * n].tolist()
         # one copy out of the handle's pinned buffer; the per-image arrays are views of it
-        rows = _view(r.poses, ctypes.c_float, total * c * _lib.OG_POSE_COLS, np.float32).copy()
-        rows = rows.reshape(total, c, _lib.OG_POSE_COLS)
+        rows = pool[:total * per_row].copy().reshape(total, c, _lib.OG_POSE_COLS)
         return [rows[o:o + k] for o, k in zip(offs, cnts)]
 
     def _finish(self, keep_alive, fetch, n):
@@ -407,7 +423,9 @@ class DecoderEngine(object):
 
 
 class FeaturePlan(object):
-    """See DecoderEngine.plan_features."""
+    """See DecoderEngine.plan_features.  The plan holds converted arguments only: ``launch(keep)``
+    takes the tensors to keep referenced until the call has been fetched (default: the ones the
+    plan was made from)."""
 
     def __init__(self, eng, hmp, off, hmp_stride, off_stride, resize_mode, flip_tables):
         if not (hmp.is_cuda and off.is_cuda):
@@ -416,6 +434,7 @@ class FeaturePlan(object):
         eng._check_heads(hmp.shape, off.shape, 2, flip)
         mode = {'bilinear': 0, 'bicubic': 1}[resize_mode]
         args = eng._flip_args(flip_tables) if flip else (None, None, None, 0)
+        src = (hmp, off)
         if hmp.dtype != off.dtype or hmp.dtype not in _DTYPES:
             hmp, off = hmp.float(), off.float()
         hmp, hmp_is = _image_strided(hmp)
@@ -423,20 +442,28 @@ class FeaturePlan(object):
         n_in, _, h, w = hmp.shape
         self.n = n_in // 2 if flip else n_in
         self.eng = eng
-        self.keep = (hmp, off, flip_tables)
+        self.in_place = hmp is src[0] and off is src[1]      # the library reads the caller's own buffers
+        self.keep = (hmp, off)
+        self.flip_tables = flip_tables
         self._fn = eng.lib.og_decode_features_dev_ex
-        self._stream = torch.cuda.current_stream(eng.device)
+        self.stream_ptr = torch.cuda.current_stream(eng.device).cuda_stream
         self._args = (eng._h, _ptr(hmp), _ptr(off), _DTYPES[hmp.dtype], hmp_is, off_is, self.n, h, w,
                       int(hmp_stride), int(off_stride), mode, 1 if flip else 0) + tuple(args) + \
-                     (ctypes.c_void_p(self._stream.cuda_stream),)
+                     (ctypes.c_void_p(self.stream_ptr),)
 
-    def launch(self):
+    def launch(self, keep=None):
         """Launch one decode of the planned buffers on the stream that was current when the plan
         was made (the CUDA device of the engine must be current)."""
         st = self._fn(*self._args)
         if st != 0:
             _lib.check(st)
-        self.eng._inflight.append(self.keep)
+        self.eng._inflight.append(self.keep if keep is None else keep)
+
+    def release(self):
+        """Drop the references to the planned tensors (a cached plan is launched with the caller's
+        current tensor objects as ``keep``)."""
+        self.keep = None
+        return self
 
     def fetch(self):
         return self.eng._fetch()

@@ -840,16 +840,21 @@ def test_graph_replay_and_recapture(cuda_device):
     ref = eng.decode_features(hd, od, 4, 4, 'bicubic', tables)
     assert sum(len(p) for p in ref) >= 6 and eng.graph_counts == (0, 0)
     eng.set_graph(True)
-    for _ in range(2 * 8 + 1):                      # every slot captures once, then replays
+    for _ in range(17):                             # a synchronous caller stays on one slot: one capture, then replays
         got = eng.decode_features(hd, od, 4, 4, 'bicubic', tables)
         for g, r in zip(got, ref):
             assert np.array_equal(g, r)
     replays, builds = eng.graph_counts
-    assert builds == 8 and replays == 17
+    assert builds == 1 and replays == 17
+    for _ in range(3):                              # three in flight: two more slots capture
+        eng.decode_features(hd, od, 4, 4, 'bicubic', tables, fetch=False)
+    for _ in range(3):
+        assert all(np.array_equal(g, r) for g, r in zip(eng.fetch(), ref))
+    assert eng.graph_counts[1] == 3
     # the same maps in other buffers, and a smaller batch: re-captured, same answers
     hd2, od2 = hd.clone(), od.clone()
     got = eng.decode_features(hd2, od2, 4, 4, 'bicubic', tables)
-    assert eng.graph_counts[1] == 9 and all(np.array_equal(g, r) for g, r in zip(got, ref))
+    assert eng.graph_counts[1] == 4 and all(np.array_equal(g, r) for g, r in zip(got, ref))
     sub = [0, 1, 3, 4]
     got = eng.decode_features(hd[sub], od[sub], 4, 4, 'bicubic', tables)
     assert all(np.array_equal(g, r) for g, r in zip(got, ref[:2]))
@@ -1094,3 +1099,46 @@ def test_tied_peaks_tie_aware_against_reference(cuda_device):
         ds, di, _ = pp._engine(torch.device('cuda', 0)).last_intermediates(len(ref))
         groups = gio.compare_dets_tie_aware(ds.cpu().numpy(), di.cpu().numpy(), d['det_scores'], d['det_inds'], thre)
         assert groups >= int(d['ties'])
+
+
+def test_submit_collect_equals_generate_poses(cuda_device):
+    """PostProcess.submit / collect (the pipelined form of generate_poses): same results as the
+    synchronous call, in launch order, for device maps (cached plan, replayed graph — also when
+    the buffers are refilled with other images), packed bf16 slices and pinned host maps."""
+    pp = decoder.decoder_factory(_args(topk=16, thre_hmp=0.05, person_thre=0.05, dist_max=40))
+    batches = [_lowres_scene(900 + 7 * i, 2, True) for i in range(3)]
+    refs = []
+    for hmp, omp in batches:
+        feats = [[[torch.from_numpy(hmp).cuda()], [[]], [[]]], [[torch.from_numpy(omp).cuda()], [[]], [[]]]]
+        refs.append(pp.generate_poses(feats, flip_test=True))
+    assert sum(len(p) for r in refs for p in r) > 10
+    # the same two device buffers refilled batch after batch (what a network does)
+    hd = torch.empty_like(torch.from_numpy(batches[0][0])).cuda()
+    od = torch.empty_like(torch.from_numpy(batches[0][1])).cuda()
+    for rep in range(3):
+        for i, (hmp, omp) in enumerate(batches):
+            hd.copy_(torch.from_numpy(hmp))
+            od.copy_(torch.from_numpy(omp))
+            torch.cuda.synchronize()
+            pp.submit([[[hd.view_as(hd)], [[]], [[]]], [[od.view_as(od)], [[]], [[]]]], flip_test=True)
+            got = pp.collect()
+            assert all(np.array_equal(g, r) for g, r in zip(got, refs[i])) and len(got) == len(refs[i])
+    assert len(pp._plans) == 1
+    # several in flight, distinct buffers, plus a pinned-host and a packed bf16 submission
+    dev = [(torch.from_numpy(h_).cuda(), torch.from_numpy(o_).cuda()) for h_, o_ in batches]
+    for h_, o_ in dev:
+        pp.submit([[[h_], [[]], [[]]], [[o_], [[]], [[]]]], flip_test=True)
+    host = (torch.from_numpy(batches[1][0]).pin_memory(), torch.from_numpy(batches[1][1]).pin_memory())
+    pp.submit([[[host[0]], [[]], [[]]], [[host[1]], [[]], [[]]]], flip_test=True)
+    for i in range(3):
+        got = pp.collect()
+        assert all(np.array_equal(g, r) for g, r in zip(got, refs[i]))
+    got = pp.collect()
+    assert all(np.array_equal(g, r) for g, r in zip(got, refs[1]))
+    packed = torch.cat((dev[2][0], dev[2][1]), dim=1).to(torch.bfloat16)
+    f32 = packed.float()
+    ref_bf = pp.generate_poses([[[f32[:, :17].contiguous()], [[]], [[]]], [[f32[:, 17:].contiguous()], [[]], [[]]]],
+                               flip_test=True)
+    pp.submit([[[packed[:, :17]], [[]], [[]]], [[packed[:, 17:]], [[]], [[]]]], flip_test=True)
+    got = pp.collect()
+    assert len(got) == len(ref_bf) and all(np.array_equal(g, r) for g, r in zip(got, ref_bf))
