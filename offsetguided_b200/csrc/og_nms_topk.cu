@@ -61,8 +61,11 @@ __device__ __forceinline__ bool survives(float v, float m, float thre, float &nv
     return nv >= thre;
 }
 
+#ifndef OG_K1_MIN_CTAS
+#define OG_K1_MIN_CTAS 3
+#endif
 template <bool kThrePositive, bool kVec4>
-__global__ void __launch_bounds__(kK1Threads)
+__global__ void __launch_bounds__(kK1Threads, OG_K1_MIN_CTAS)
 nms_candidates_kernel(const float *__restrict__ heat, int planes, int H, int W, float thre,
                       uint32_t *__restrict__ cand_count, uint64_t *__restrict__ cand_keys) {
     const int lane = threadIdx.x & 31;
@@ -148,29 +151,102 @@ nms_candidates_kernel(const float *__restrict__ heat, int planes, int H, int W, 
         }
         return v;
     };
-    auto is_hot = [&](const float4 &v) {
-        return kThrePositive ? (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= thre) : true;
-    };
     const float *row = p + (size_t)r_begin * W + x0;
-    int r = r_begin;
-    for (; r + kUnroll <= r_end; r += kUnroll) {
-        float4 v[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) v[u] = stream_row(row + (size_t)u * W);
-        row += (size_t)kUnroll * W;
-        unsigned hot = 0;
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) hot |= is_hot(v[u]) ? (1u << u) : 0u;
-        hot = __reduce_or_sync(0xffffffffu, hot);
-        while (hot) {                       // warp-uniform
-            const int u = __ffs(hot) - 1;
-            hot &= hot - 1;
-            check_row(r + u);
-        }
+
+    if (!kThrePositive) {
+        // thre <= 0: every pixel qualifies (non-peaks with their NMS value 0), so every row runs the
+        // full test; this variant only serves the exact joint_dets / topK_channel API
+        for (int r = r_begin; r < r_end; ++r) check_row(r);
+        return;
     }
-    for (; r < r_end; ++r, row += W) {      // fewer than kUnroll rows left
-        const float4 v = stream_row(row);
-        if (__any_sync(0xffffffffu, is_hot(v))) check_row(r);
+
+    // thre > 0.  The whole 8-row chunk is held in registers (8 independent 128-bit loads in flight per
+    // lane).  A row is looked at again only if some lane holds a value >= thre, and then the test
+    // runs from the registers: first the two VERTICAL neighbours (this lane's own rows above and
+    // below — no traffic, no shuffle), and only for a row in which some pixel survives that — a blob
+    // of many rows has its vertical maxima on one or two of them — the horizontal and diagonal
+    // neighbours through two shuffles of the column maxima.  The rows just outside the chunk and the
+    // columns just outside the strip are fetched on demand (L2 hits: a neighbouring warp streams them).
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+        v[u] = (r_begin + u < r_end) ? stream_row(row + (size_t)u * W) : make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned hot = 0;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+        hot |= (fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)) >= thre) ? (1u << u) : 0u;
+    hot = __reduce_or_sync(0xffffffffu, hot);
+    if (hot == 0u) return;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 above = (hot & 1u) ? load_row(r_begin - 1) : zero4;                     // zero padding outside
+    const float4 below = ((hot >> (kUnroll - 1)) & 1u) ? load_row(r_begin + kUnroll) : zero4;
+    auto vertical = [&](float c, float up, float dn) {       // fmaxf semantics: a NaN neighbour is ignored
+        return c >= thre && !(up > c) && !(dn > c);
+    };
+    auto side_column = [&](int rr, int col) {                // maximum of a column just outside the strip over 3 rows
+        float m = 0.0f;                                       // zero padding
+        if (col >= 0 && col < W) {
+            const float a0 = rr - 1 >= 0 ? __ldg(p + (size_t)(rr - 1) * W + col) : 0.0f;
+            const float a1 = __ldg(p + (size_t)rr * W + col);
+            const float a2 = rr + 1 < H ? __ldg(p + (size_t)(rr + 1) * W + col) : 0.0f;
+            m = max3(a0, a1, a2);
+        }
+        return m;
+    };
+    unsigned peaks = 0u;             // bit 4 u + k: pixel k of this lane's four in row u is a peak
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        if (!((hot >> u) & 1u)) continue;                    // warp-uniform
+        const float4 up = u == 0 ? above : v[u == 0 ? 0 : u - 1];
+        const float4 dn = u == kUnroll - 1 ? below : v[u == kUnroll - 1 ? u : u + 1];
+        const float4 c = v[u];
+        const bool cx = vertical(c.x, up.x, dn.x), cy = vertical(c.y, up.y, dn.y);
+        const bool cz = vertical(c.z, up.z, dn.z), cw = vertical(c.w, up.w, dn.w);
+        if (!__any_sync(0xffffffffu, cx || cy || cz || cw)) continue;
+        const int rr = r_begin + u;
+        // column maxima over the three rows; the neighbours' outer columns come by shuffle
+        const float mx = max3(up.x, c.x, dn.x), my = max3(up.y, c.y, dn.y);
+        const float mz = max3(up.z, c.z, dn.z), mw = max3(up.w, c.w, dn.w);
+        float left = __shfl_up_sync(0xffffffffu, mw, 1);
+        float right = __shfl_down_sync(0xffffffffu, mx, 1);
+        if (lane == 0) left = cx ? side_column(rr, x0 - 1) : 0.0f;
+        if (lane == 31) right = cw ? side_column(rr, x0 + 4) : 0.0f;
+        unsigned m4 = 0u;
+        if (cx && !(left > c.x) && !(my > c.x) && x0 + 0 < W) m4 |= 1u;
+        if (cy && !(mx > c.y) && !(mz > c.y) && x0 + 1 < W) m4 |= 2u;
+        if (cz && !(my > c.z) && !(mw > c.z) && x0 + 2 < W) m4 |= 4u;
+        if (cw && !(mz > c.w) && !(right > c.w) && x0 + 3 < W) m4 |= 8u;
+        peaks |= m4 << (4 * u);
+    }
+    if (!__any_sync(0xffffffffu, peaks != 0u)) return;
+    // one atomic per warp and chunk reserves the list slots of all its peaks
+    const int mine = __popc(peaks);
+    int before = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, before, d);
+        if (lane >= d) before += t;
+    }
+    const int total_peaks = __shfl_sync(0xffffffffu, before, 31);
+    if (total_peaks == 0) return;
+    uint32_t base = 0u;
+    if (lane == 31) base = atomicAdd(&cand_count[plane], (uint32_t)total_peaks);
+    base = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(before - mine);
+    if (mine == 0) return;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        const unsigned m4 = (peaks >> (4 * u)) & 15u;
+        if (m4 == 0u) continue;
+        const float vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if ((m4 >> k) & 1u) {
+                if (base < (uint32_t)kCandCap)
+                    cand_keys[(size_t)plane * kCandCap + base] =
+                        make_key(vals[k] + 0.0f, (uint32_t)((r_begin + u) * W + x0 + k));
+                ++base;
+            }
+        }
     }
 }
 
