@@ -246,8 +246,23 @@ typedef struct og_result {
     int32_t total_rows;
     int32_t n_keypoints;
     int32_t reserved;
+    /* only after og_set_frames (else NULL): the result rows of the reference's evaluation loop,
+     * row r of these arrays = pose row r */
+    const float *coco_keypoints; /* [total_rows, 3 * n_keypoints]  x, y, flag per keypoint */
+    const double *coco_scores;   /* [total_rows]  mean keypoint score                      */
+    const int32_t *coco_images;  /* [total_rows]  image index within the call              */
 } og_result;
 int og_fetch_result(og_handle *h, og_result *out);
+
+/* Pose back-projection and result rows on the GPU (replaces the per-image / per-person /
+ * per-keypoint Python loops of transforms/preprocess.py:33-63 annotations_inverse and
+ * evaluate.py:227-265).  og_set_frames stages, for the NEXT og_decode_* call on the handle, the
+ * frame of each of its n images: frames_host[4 i ..] = { offset_x, offset_y, scale_x, scale_y }
+ * (meta['offset'], meta['scale']).  The grouping kernel then also writes, for every person,
+ * x' = around((x + offset_x) / scale_x, 2), y' likewise, flag = (x' > 0 or y' > 0) per keypoint
+ * and score = sum(v) / C, with the reference's rounding (float64 steps rounded to float32, numpy's
+ * float32 around, float64 score); og_fetch_result exposes them next to the poses. */
+int og_set_frames(og_handle *h, const double *frames_host, int n);
 int og_fetch_poses(og_handle *h, const float **poses_host, const int32_t **offset_host,
                    const int32_t **count_host, int32_t *total_rows);
 int og_pending(const og_handle *h);

@@ -50,6 +50,9 @@ class OgResult(ctypes.Structure):
         ('total_rows', ctypes.c_int32),
         ('n_keypoints', ctypes.c_int32),
         ('reserved', ctypes.c_int32),
+        ('coco_keypoints', c_float_p),
+        ('coco_scores', ctypes.POINTER(ctypes.c_double)),
+        ('coco_images', c_int32_p),
     ]
 
 
@@ -88,6 +91,7 @@ SIGNATURES = {
     'og_fetch_poses': (_i, [_vp, ctypes.POINTER(c_float_p), ctypes.POINTER(c_int32_p),
                             ctypes.POINTER(c_int32_p), ctypes.POINTER(ctypes.c_int32)]),
     'og_fetch_result': (_i, [_vp, ctypes.POINTER(OgResult)]),
+    'og_set_frames': (_i, [_vp, ctypes.POINTER(ctypes.c_double), _i]),
     'og_pending': (_i, [_vp]),
     'og_copy_intermediates': (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     'og_launch_count': (ctypes.c_int64, [_vp]),

@@ -89,10 +89,10 @@ struct GraphKey {
     const void *hmp, *off;
     int dtype;
     size_t hmp_image_stride, off_image_stride;
-    int n, hgt, w, stride, mode, flip;
+    int n, hgt, w, stride, mode, flip, coco;
     uint64_t tables_version, buffers_version;
     bool operator==(const GraphKey &o) const {
-        return hmp == o.hmp && off == o.off && dtype == o.dtype && hmp_image_stride == o.hmp_image_stride &&
+        return hmp == o.hmp && off == o.off && dtype == o.dtype && coco == o.coco && hmp_image_stride == o.hmp_image_stride &&
                off_image_stride == o.off_image_stride && n == o.n && hgt == o.hgt && w == o.w &&
                stride == o.stride && mode == o.mode && flip == o.flip &&
                tables_version == o.tables_version && buffers_version == o.buffers_version;
@@ -124,6 +124,10 @@ struct ResultSlot {
     unsigned char *out_dev = nullptr;   // the same memory as the device addresses it
     size_t out_cap = 0;
     DevBuf<int32_t> total;              // K3's row allocator
+    double *frames_host = nullptr;      // [n][4] image frames of the call (pinned, mapped), see og_set_frames
+    double *frames_dev = nullptr;
+    int frames_cap = 0;
+    bool emit_coco = false;             // this call also writes back-projected result rows
     DevBuf<float> in_hmp, in_off;       // staged network-resolution inputs (host API)
     DevBuf<float> det_score;            // K1 output
     DevBuf<int32_t> det_index;
@@ -206,9 +210,38 @@ struct og_handle {
     uint8_t reserved_cache[OG_MAX_LIMBS];
 
     bool timing;
+    double *staged_frames;       // og_set_frames: frames of the NEXT decode call
+    int staged_n, staged_cap;
 };
 
 namespace {
+
+// Result buffer of a slot: [meta][pose rows][result-row keypoints][result-row scores][result-row images]
+inline size_t align16(size_t x) { return (x + 15) / 16 * 16; }
+struct ResultLayout {
+    size_t poses, coco_kp, coco_score, coco_image, total;
+};
+inline ResultLayout result_layout(const og_handle *h, int n, int capacity_rows) {
+    const size_t c = (size_t)h->cfg.n_keypoints;
+    ResultLayout lo;
+    lo.poses = ((size_t)(2 * n + 2) * sizeof(int32_t) + 15) / 16 * 16;
+    lo.coco_kp = align16(lo.poses + (size_t)capacity_rows * c * OG_POSE_COLS * sizeof(float));
+    lo.coco_score = align16(lo.coco_kp + (size_t)capacity_rows * c * 3 * sizeof(float));
+    lo.coco_image = align16(lo.coco_score + (size_t)capacity_rows * sizeof(double));
+    lo.total = align16(lo.coco_image + (size_t)capacity_rows * sizeof(int32_t));
+    return lo;
+}
+
+CocoOut coco_out(const og_handle *h, const ResultSlot *slot, int image0) {
+    CocoOut c = {nullptr, nullptr, nullptr, nullptr, image0};
+    if (!slot->emit_coco) return c;
+    const ResultLayout lo = result_layout(h, slot->n, slot->capacity_rows);
+    c.frames = slot->frames_dev;
+    c.keypoints = reinterpret_cast<float *>(slot->out_dev + lo.coco_kp);
+    c.scores = reinterpret_cast<double *>(slot->out_dev + lo.coco_score);
+    c.images = reinterpret_cast<int32_t *>(slot->out_dev + lo.coco_image);
+    return c;
+}
 
 // meta words: offset[n], count[n], overflow flag of the fused path, one spare
 inline size_t meta_bytes_for(int n) { return ((size_t)(2 * n + 2) * sizeof(int32_t) + 15) / 16 * 16; }
@@ -329,9 +362,10 @@ int ensure_group_scratch(og_handle *h, GroupScratch &gs, int n, ResultSlot *slot
 // K3 on `n` images whose scratch rows start at image `i0` of the scratch buffers.
 int run_k3(og_handle *h, GroupScratch &gs, int i0, const float *limbs, bool prepared, int n,
            float *out_poses, int capacity_rows, int32_t *out_offset, int32_t *out_count,
-           int32_t *out_total, cudaStream_t s) {
+           int32_t *out_total, cudaStream_t s, const CocoOut *coco = nullptr) {
     const og_config &c = h->cfg;
     GroupLaunch g = group_launch(h, n);
+    if (coco) g.coco = *coco;
     g.prep = gs.prep.ptr + (size_t)i0 * c.n_limbs * (c.topk + 1);
     g.rec = gs.rec.ptr + (size_t)i0 * c.n_limbs * c.topk * 3;
     g.cnt = gs.cnt.ptr + (size_t)i0 * c.n_limbs;
@@ -375,8 +409,28 @@ int begin_call(og_handle *h, ResultSlot *slot, const K1Fused *fused, int n, int 
     int capacity_rows = (int)std::min<long long>(worst, std::max<long long>((long long)n * h->result_rows, 256));
     if (h->result_rows < 64) capacity_rows = (int)std::min<long long>(worst, (long long)n * h->result_rows);   // test aid
     const size_t mbytes = meta_bytes_for(n);
-    if (slot->out_cap >= mbytes + (size_t)worst * pose_row_bytes(h)) capacity_rows = (int)worst;
-    OG_TRY(ensure_result(h, slot, mbytes + (size_t)capacity_rows * pose_row_bytes(h)));
+    if (slot->out_cap >= result_layout(h, n, (int)worst).total) capacity_rows = (int)worst;
+    OG_TRY(ensure_result(h, slot, result_layout(h, n, capacity_rows).total));
+    // image frames staged by og_set_frames belong to this call
+    slot->emit_coco = false;
+    if (h->staged_n >= 0) {
+        const int staged = h->staged_n;
+        h->staged_n = -1;
+        OG_REQUIRE(staged == n, "og_set_frames staged %d image frames but the decode call has %d images", staged, n);
+        if (n > slot->frames_cap) {
+            if (slot->frames_host) OG_CUDA_TRY(cudaFreeHost(slot->frames_host));
+            slot->frames_host = slot->frames_dev = nullptr;
+            slot->frames_cap = 0;
+            const int grow = n + n / 4 + 8;
+            OG_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&slot->frames_host), (size_t)grow * 4 * sizeof(double),
+                                      cudaHostAllocMapped));
+            OG_CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&slot->frames_dev), slot->frames_host, 0));
+            slot->frames_cap = grow;
+            slot->buffers_version += 1;
+        }
+        memcpy(slot->frames_host, h->staged_frames, (size_t)n * 4 * sizeof(double));
+        slot->emit_coco = n > 0;
+    }
     const int planes = n * c.n_keypoints;
     bool fresh_scratch = slot->scratch_dirty;
     if (n > 0) {
@@ -501,8 +555,9 @@ int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, cons
                              c.thre_hmp, c.min_len, c.resize_factor, limbs, &po, a));
     h->launches += 1;
     if (timed) OG_TRY(mark(h, slot, 5, a));
+    const CocoOut coco = coco_out(h, slot, i0);
     OG_TRY(run_k3(h, gs, i0, limbs, true, cn, poses, slot->capacity_rows, meta + i0, meta + n + i0,
-                  slot->total.ptr, a));
+                  slot->total.ptr, a, &coco));
     if (timed) OG_TRY(mark(h, slot, 6, a));
     slot->k3_first = i0;
     slot->k3_images = cn;
@@ -562,7 +617,7 @@ int decode_chain(og_handle *h, ResultSlot *slot, const K1Fused &k1, const Offset
         return finish_call(h, slot);
     }
     const GraphKey key = {k1.hmp.ptr, src.maps.ptr, k1.hmp.dtype, k1.hmp.image_stride, src.maps.image_stride,
-                          n, k1.h, k1.w, k1.scale, k1.cubic ? 1 : 0, k1.flip ? 1 : 0,
+                          n, k1.h, k1.w, k1.scale, k1.cubic ? 1 : 0, k1.flip ? 1 : 0, slot->emit_coco ? 1 : 0,
                           h->tables_version, slot->buffers_version};
     int gi = -1, victim = 0;
     for (int i = 0; i < kGraphsPerSlot; ++i) {
@@ -793,6 +848,9 @@ int og_create(const og_config *cfg, og_handle **out) {
     if (const char *env = getenv("OG_GRAPH")) h->graph_enabled = atoi(env) != 0;     // tuning aid
     h->graph_replays = h->graph_builds = 0;
     h->graph_clock = 0;
+    h->staged_frames = nullptr;
+    h->staged_n = -1;
+    h->staged_cap = 0;
     h->result_rows = 64;
     if (const char *env = getenv("OG_RESULT_ROWS")) {          // test aid: force the regroup path
         const int v = atoi(env);
@@ -919,6 +977,7 @@ int og_destroy(og_handle *h) {
         for (int g = 0; g < kGraphsPerSlot; ++g)
             if (sl.graph[g]) cudaGraphExecDestroy(sl.graph[g]);
         if (sl.out_host) cudaFreeHost(sl.out_host);
+        if (sl.frames_host) cudaFreeHost(sl.frames_host);
         sl.total.release();
         sl.in_hmp.release();
         sl.in_off.release();
@@ -942,6 +1001,7 @@ int og_destroy(og_handle *h) {
         if (sl.work) cudaStreamDestroy(sl.work);
     }
     if (h->cp) cudaStreamDestroy(h->cp);
+    free(h->staged_frames);
     delete h;
     return OG_OK;
 }
@@ -1285,14 +1345,15 @@ int regroup_with_full_capacity(og_handle *h, ResultSlot *slot) {
     const og_config &c = h->cfg;
     const int n = slot->n;
     const long long worst = (long long)n * c.n_limbs * c.topk;
-    OG_TRY(ensure_result(h, slot, slot->meta_bytes + (size_t)worst * pose_row_bytes(h)));
+    OG_TRY(ensure_result(h, slot, result_layout(h, n, (int)worst).total));
     slot->capacity_rows = (int)worst;
     int32_t *meta = reinterpret_cast<int32_t *>(slot->out_dev);
     float *poses = reinterpret_cast<float *>(slot->out_dev + slot->meta_bytes);
     cudaStream_t a = slot->work;
     OG_CUDA_TRY(cudaMemsetAsync(slot->total.ptr, 0, sizeof(int32_t), a));
+    const CocoOut coco = coco_out(h, slot, 0);
     OG_TRY(run_k3(h, slot->group, 0, slot->limbs.ptr, true, n, poses, slot->capacity_rows, meta, meta + n,
-                  slot->total.ptr, a));
+                  slot->total.ptr, a, &coco));
     OG_CUDA_TRY(cudaStreamSynchronize(a));
     return OG_OK;
 }
@@ -1354,6 +1415,12 @@ int og_fetch_result(og_handle *h, og_result *out) {
         out->offsets = reinterpret_cast<const int32_t *>(slot->out_host);
         out->counts = out->offsets + n;
         out->poses = reinterpret_cast<const float *>(slot->out_host + slot->meta_bytes);
+        if (slot->emit_coco) {
+            const ResultLayout lo = result_layout(h, n, slot->capacity_rows);
+            out->coco_keypoints = reinterpret_cast<const float *>(slot->out_host + lo.coco_kp);
+            out->coco_scores = reinterpret_cast<const double *>(slot->out_host + lo.coco_score);
+            out->coco_images = reinterpret_cast<const int32_t *>(slot->out_host + lo.coco_image);
+        }
     }
     out->n_images = n;
     out->total_rows = (int32_t)total;
@@ -1422,6 +1489,25 @@ int og_set_zero_copy(og_handle *h, int enable) {
 }
 
 int64_t og_zero_copy_count(const og_handle *h) { return h ? h->zero_copy_calls : 0; }
+
+int og_set_frames(og_handle *h, const double *frames_host, int n) {
+    OG_REQUIRE(h && n >= 0 && (n == 0 || frames_host), "og_set_frames: null pointer");
+    for (int i = 0; i < n; ++i)
+        OG_REQUIRE(frames_host[4 * i + 2] != 0.0 && frames_host[4 * i + 3] != 0.0,
+                   "og_set_frames: image %d has a zero scale", i);
+    if (n > h->staged_cap) {
+        double *grown = static_cast<double *>(realloc(h->staged_frames, (size_t)(n + 8) * 4 * sizeof(double)));
+        if (!grown) {
+            set_error("host allocation failed");
+            return OG_ERR_OUT_OF_MEMORY;
+        }
+        h->staged_frames = grown;
+        h->staged_cap = n + 8;
+    }
+    if (n) memcpy(h->staged_frames, frames_host, (size_t)n * 4 * sizeof(double));
+    h->staged_n = n;
+    return OG_OK;
+}
 
 int og_set_graph(og_handle *h, int enable) {
     OG_REQUIRE(h, "og_set_graph: null handle");

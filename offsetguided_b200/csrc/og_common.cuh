@@ -202,6 +202,15 @@ int launch_fused_candidates(const MapView &hmp, const FlipTablesDev &flips, int 
                             int32_t *n_active, int sm_count, bool clear_first, cudaStream_t s,
                             int64_t *launches);
 
+// optional second output of K3: result rows back-projected into the original image frames
+struct CocoOut {
+    const double *frames;       // [images of the call][4] offset_x, offset_y, scale_x, scale_y; nullptr = off
+    float *keypoints;           // [capacity_rows][3 C]  x, y, flag
+    double *scores;             // [capacity_rows]
+    int32_t *images;            // [capacity_rows] image index within the call
+    int image0;                 // index of this launch's first image within the call
+};
+
 struct GroupLaunch {
     int n, c, l, k;
     SkeletonDev sk;
@@ -217,6 +226,7 @@ struct GroupLaunch {
     float4 *rec;                // group_rec_vec4() float4: the kept rows themselves, compacted
     int32_t *cnt;               // [n, L] kept rows per (image, limb)
     int32_t *redo;              // [n] images the warp kernel handed to the CTA kernel
+    CocoOut coco;
 };
 int read_k3_profile(unsigned long long *out16, bool reset);
 size_t group_smem_bytes(const GroupLaunch &g);

@@ -83,7 +83,26 @@ struct GroupArgs {
     int warp_rows;
     float *slab;     // per image: xyvs float4[PMAX*C], score float[PMAX*C], ids int[PMAX*C]
     size_t slab_stride;
+    CocoOut coco;    // optional back-projected result rows (frames == nullptr: off)
 };
+
+// Result rows as the reference's evaluation loop builds them from the poses of one image
+// (evaluate.py:227-265 after transforms/preprocess.py:33-63 annotations_inverse): per joint
+// x, y moved back into the original image frame — (x + offset) / scale, each step evaluated in
+// float64 and rounded to float32 like numpy's in-place updates of a float32 array — then
+// np.around(., 2) in float32 (multiply by 100, rint, divide), and the flag "x > 0 or y > 0".
+__device__ __forceinline__ void coco_joint(const double *__restrict__ frame, float x, float y,
+                                           float *__restrict__ o) {
+    const float x1 = __double2float_rn((double)x + frame[0]);
+    const float y1 = __double2float_rn((double)y + frame[1]);
+    const float x2 = __double2float_rn((double)x1 / frame[2]);
+    const float y2 = __double2float_rn((double)y1 / frame[3]);
+    const float x3 = __fdiv_rn(rintf(__fmul_rn(x2, 100.0f)), 100.0f);
+    const float y3 = __fdiv_rn(rintf(__fmul_rn(y2, 100.0f)), 100.0f);
+    o[0] = x3;
+    o[1] = y3;
+    o[2] = (x3 > 0.0f || y3 > 0.0f) ? 1.0f : 0.0f;
+}
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -508,6 +527,16 @@ group_kernel(GroupArgs a, const float *__restrict__ limbs, const int32_t *__rest
         o[3] = unset_to_zero(v.w);
         o[4] = unset_to_zero(score[row * C + c]);
         o[5] = unset_to_zero((float)ids[row * C + c]);
+        if (a.coco.frames != nullptr) {
+            coco_joint(a.coco.frames + (size_t)(a.coco.image0 + img) * 4, unset_to_zero(v.x), unset_to_zero(v.y),
+                       a.coco.keypoints + ((size_t)dst * C + c) * 3);
+            if (c == 0) {       // score = sum(v) / len(v), float64, left to right (evaluate.py:250)
+                double acc = 0.0;
+                for (int cc = 0; cc < C; ++cc) acc += (double)unset_to_zero(xyvs[row * C + cc].z);
+                a.coco.scores[dst] = acc / (double)C;
+                a.coco.images[dst] = a.coco.image0 + img;
+            }
+        }
     }
 #ifdef OG_K3_PROFILE
     OG_K3_PROF(8);
@@ -1052,6 +1081,17 @@ group_warp_kernel(GroupArgs a, const float4 *__restrict__ rec, const int32_t *__
         o[0] = make_float2(unset_to_zero(v.x), unset_to_zero(v.y));
         o[1] = make_float2(unset_to_zero(v.z), unset_to_zero(v.w));
         o[2] = make_float2(unset_to_zero(score[row + c]), unset_to_zero((float)ids[row + c]));
+        if (a.coco.frames != nullptr) {
+            coco_joint(a.coco.frames + (size_t)(a.coco.image0 + img) * 4, unset_to_zero(v.x), unset_to_zero(v.y),
+                       a.coco.keypoints + ((size_t)dst * C + c) * 3);
+            if (c == 0) {       // score = sum(v) / len(v), float64, left to right (evaluate.py:250)
+                double acc = 0.0;
+#pragma unroll 1
+                for (int cc = 0; cc < C; ++cc) acc += (double)unset_to_zero(xyvs[row + cc].z);
+                a.coco.scores[dst] = acc / (double)C;
+                a.coco.images[dst] = a.coco.image0 + img;
+            }
+        }
     }
 #ifdef OG_K3_PROFILE
     OG_K3_PROF(8);
@@ -1074,6 +1114,7 @@ GroupArgs to_args(const GroupLaunch &g) {
     a.warp_rows = g.warp_rows;
     a.slab = g.slab;
     a.slab_stride = g.slab_stride;
+    a.coco = g.coco;
     return a;
 }
 

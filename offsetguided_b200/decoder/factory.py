@@ -103,6 +103,25 @@ class PostProcess(torch.nn.Module):
         tables = self._flip_tables if flip_test else None
         return eng.decode_features(hmps, offs, self.hmp_stride, self.off_stride, self.inter_mode, tables)
 
+    def generate_results(self, features, metas, flip_test=False):
+        """generate_poses plus the caller's next step on the GPU: every pose back-projected into
+        its original image frame and turned into the evaluation's result row (reference
+        transforms/preprocess.py:33-63 + evaluate.py:227-265, per-image / per-person /
+        per-keypoint Python loops there).  ``metas``: the batch's meta dictionaries ('offset',
+        'scale', 'hflip', 'image_id').  Returns (batch_poses, keypoints (T, 3C) float32,
+        scores (T,) float64, image_index (T,)): rows ordered by image then person rank, an image
+        without persons holds the reference's all-zero row with score 0.01;
+        ``results.rows_from_arrays`` turns the arrays into the COCO dictionaries."""
+        from .. import results
+        hmps = features[self.hmp_index][0][self.feat_stage]
+        offs = features[self.omp_index][0][self.feat_stage]
+        device = hmps.device if hmps.is_cuda else torch.device('cuda', torch.cuda.current_device())
+        eng = self._engine(device)
+        tables = self._flip_tables if flip_test else None
+        poses = eng.decode_features(hmps, offs, self.hmp_stride, self.off_stride, self.inter_mode, tables,
+                                    frames=results.frames_of(metas))
+        return (poses,) + results.result_arrays(eng.last_result_rows, len(self.keypoints))
+
     # ---- pipelined form of generate_poses ------------------------------------------------------
     # The reference call is synchronous: the host waits for every batch.  A decode of a few images
     # is ~0.05 ms of latency-bound kernels, so a caller that shards a batch over several GPUs (or

@@ -94,6 +94,7 @@ class DecoderEngine(object):
         self._arg_cache = collections.OrderedDict()
         self._meta_views = {}
         self._pose_views = {}
+        self.last_result_rows = None
 
     def close(self):
         if getattr(self, '_h', None):
@@ -196,6 +197,21 @@ class DecoderEngine(object):
             self._inflight.popleft()
         r = self._result
         n, total, c = r.n_images, r.total_rows, self.n_keypoints
+        self.last_result_rows = None
+        if r.coco_keypoints:
+            # (keypoints (T, 3C) float32, scores (T,) float64, image index (T,) int32, persons per image (n,))
+            if total:
+                kp = np.frombuffer((ctypes.c_float * (total * 3 * c)).from_address(
+                    ctypes.cast(r.coco_keypoints, ctypes.c_void_p).value), dtype=np.float32).reshape(total, 3 * c).copy()
+                sc = np.frombuffer((ctypes.c_double * total).from_address(
+                    ctypes.cast(r.coco_scores, ctypes.c_void_p).value), dtype=np.float64).copy()
+                im = np.frombuffer((ctypes.c_int32 * total).from_address(
+                    ctypes.cast(r.coco_images, ctypes.c_void_p).value), dtype=np.int32).copy()
+            else:
+                kp, sc, im = np.zeros((0, 3 * c), np.float32), np.zeros((0,), np.float64), np.zeros((0,), np.int32)
+            cn = np.frombuffer((ctypes.c_int32 * n).from_address(
+                ctypes.cast(r.counts, ctypes.c_void_p).value), dtype=np.int32).copy() if n else np.zeros((0,), np.int32)
+            self.last_result_rows = (kp, sc, im, cn)
         if n == 0:
             return []
         if total == 0:
@@ -279,12 +295,23 @@ class DecoderEngine(object):
             raise ValueError('flip-test inputs hold the originals followed by their mirrored copies: '
                              'the batch must be even, got %d' % hmp_shape[0])
 
+    def stage_frames(self, frames):
+        """Image frames of the NEXT decode call: (n, 4) float64 rows (offset_x, offset_y, scale_x,
+        scale_y) = meta['offset'], meta['scale'] of every image.  That call then also produces the
+        back-projected result rows on the GPU (``last_result_rows`` after its fetch)."""
+        frames = np.ascontiguousarray(frames, dtype=np.float64).reshape(-1, 4)
+        _lib.check(self.lib.og_set_frames(self._h, frames.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                          frames.shape[0]))
+
     def decode_features(self, hmp, off, hmp_stride, off_stride, resize_mode='bicubic',
-                        flip_tables=None, fetch=True):
+                        flip_tables=None, fetch=True, frames=None):
         """PostProcess.generate_poses on network-resolution maps.  ``hmp`` / ``off`` are
         either CUDA tensors or CPU tensors (pinned memory gives asynchronous copies).
         ``flip_tables`` = (kp_flips, limb_flips, limb_reserve) enables flip fusion; the
-        inputs then hold the originals followed by the W-flipped copies."""
+        inputs then hold the originals followed by the W-flipped copies.  ``frames``: see
+        ``stage_frames``."""
+        if frames is not None:
+            self.stage_frames(frames)
         on_host = not hmp.is_cuda
         flip = flip_tables is not None
         if not on_host:

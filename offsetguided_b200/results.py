@@ -63,3 +63,45 @@ def coco_results(batch_poses, metas):
             rows.append({'image_id': image_id, 'category_id': 1,
                          'keypoints': np.zeros((c * 3,)).tolist(), 'score': 0.01})
     return rows, image_ids, projected
+
+
+def frames_of(metas):
+    """(n, 4) float64 frames (offset_x, offset_y, scale_x, scale_y) of a batch's metas, the argument
+    of DecoderEngine.stage_frames / the ``frames`` of decode_features."""
+    out = np.empty((len(metas), 4), dtype=np.float64)
+    for i, meta in enumerate(metas):
+        if meta['hflip']:
+            raise NotImplementedError('horizontally flipped inputs are not back-projected '
+                                      '(the reference raises here as well)')
+        out[i, 0:2] = np.asarray(meta['offset'], dtype=np.float64)[:2]
+        out[i, 2:4] = np.asarray(meta['scale'], dtype=np.float64)[:2]
+    return out
+
+
+def result_arrays(gpu_rows, n_keypoints):
+    """The batch's result rows as arrays, from what the grouping kernel wrote (engine.last_result_rows):
+    rows ordered by image, then by person rank; an image without persons gets the reference's
+    all-zero row with score 0.01 (evaluate.py:258-265).
+    Returns (keypoints (T, 3C) float32, scores (T,) float64, image_index (T,) int64)."""
+    kp, sc, im, counts = gpu_rows
+    order = np.argsort(im, kind='stable')              # packed rows of one image are contiguous, in rank order
+    out_counts = np.maximum(counts, 1)
+    image_index = np.repeat(np.arange(len(counts)), out_counts)
+    real = np.repeat(counts > 0, out_counts)
+    keypoints = np.zeros((len(image_index), 3 * n_keypoints), dtype=np.float32)
+    scores = np.full((len(image_index),), 0.01, dtype=np.float64)
+    keypoints[real] = kp[order]
+    scores[real] = sc[order]
+    return keypoints, scores, image_index
+
+
+def rows_from_arrays(keypoints, scores, image_index, metas):
+    """COCO result dictionaries (evaluate.py:244-265) from result_arrays."""
+    ids = [meta['image_id'] for meta in metas]
+    kp64 = keypoints.astype(np.float64)
+    rows = []
+    for person, score, img in zip(kp64.tolist(), scores.tolist(), image_index.tolist()):
+        for j in range(2, len(person), 3):
+            person[j] = int(person[j])
+        rows.append({'image_id': ids[img], 'category_id': 1, 'keypoints': person, 'score': score})
+    return rows

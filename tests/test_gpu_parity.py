@@ -1142,3 +1142,34 @@ def test_submit_collect_equals_generate_poses(cuda_device):
     pp.submit([[[packed[:, :17]], [[]], [[]]], [[packed[:, 17:]], [[]], [[]]]], flip_test=True)
     got = pp.collect()
     assert len(got) == len(ref_bf) and all(np.array_equal(g, r) for g, r in zip(got, ref_bf))
+
+
+def test_result_rows_on_the_gpu_equal_the_reference_loops(cuda_device):
+    """PostProcess.generate_results: poses back-projected and formatted by the grouping kernel
+    equal the reference's loops (oracle restatement of preprocess.annotations_inverse +
+    evaluate.py:227-265) value for value, incl. an image without persons, through the graph
+    replay, the kernel-by-kernel launch and the host-input path."""
+    from offsetguided_b200 import results
+    pp = decoder.decoder_factory(_args(topk=16, thre_hmp=0.05, person_thre=0.05, dist_max=40))
+    hmp, omp = _lowres_scene(4242, 3, True)
+    hmp[1] = 0
+    hmp[4] = 0                                            # image 1 (and its mirrored copy): nobody there
+    rng = np.random.RandomState(5)
+    metas = [{'offset': np.array([-float(rng.randint(0, 90)), -float(rng.randint(0, 60))]),
+              'scale': np.array([rng.uniform(0.4, 1.7), rng.uniform(0.4, 1.7)]), 'hflip': False,
+              'width_height': (640, 480), 'image_id': 70 + i} for i in range(3)]
+    eng = pp._engine(torch.device('cuda', 0))
+    for mode in ('graph', 'kernels', 'host'):
+        eng.set_graph(mode == 'graph')
+        h_, o_ = torch.from_numpy(hmp), torch.from_numpy(omp)
+        h_, o_ = (h_.pin_memory(), o_.pin_memory()) if mode == 'host' else (h_.cuda(), o_.cuda())
+        feats = [[[h_], [[]], [[]]], [[o_], [[]], [[]]]]
+        for _ in range(2):
+            poses, kp, sc, img = pp.generate_results(feats, metas, flip_test=True)
+        ref_rows, ref_ids = ro.coco_result_rows(poses, metas)
+        rows = results.rows_from_arrays(kp, sc, img, metas)
+        assert len(poses[1]) == 0 and len(poses[0]) > 0 and len(rows) == len(ref_rows)
+        for a, b in zip(rows, ref_rows):
+            assert a['image_id'] == b['image_id'] and a['keypoints'] == b['keypoints'] and a['score'] == b['score']
+        plain = pp.generate_poses(feats, flip_test=True)              # no frames staged: no result rows
+        assert eng.last_result_rows is None and all(np.array_equal(a, b) for a, b in zip(plain, poses))
