@@ -676,7 +676,7 @@ def run_b200(args):
                                            'offset maps are read in place (zero-copy) instead of copied'}},
             'gpu_launches': int(launches_all),
             'gpu_launches_detail': {'note': 'kernels of this library launched inside the three timed regions, all ranks; '
-                                            'a graph replay counts its 7 kernel nodes',
+                                            'a graph replay counts its 6 kernel nodes',
                                     'value_rank0': value_launches, 'e2e_rank0': e2e_launches,
                                     'k1_roofline_leg_rank0': hot_launches},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',

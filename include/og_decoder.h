@@ -42,7 +42,7 @@ extern "C" {
 #endif
 
 #define OG_ABI_VERSION 2
-#define OG_MAX_IN_FLIGHT 8   /* decode calls a handle keeps in flight (result slots) */
+#define OG_MAX_IN_FLIGHT 16  /* decode calls a handle keeps in flight (result slots) */
 #define OG_LIMB_COLS 13      /* decoder/collect.py:220-222 */
 #define OG_POSE_COLS 6       /* decoder/group.py:48  [x, y, v, s, limb_score, ind] */
 #define OG_MAX_KEYPOINTS 64
@@ -226,6 +226,17 @@ int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off
                               const int32_t *kp_flip, const int32_t *limb_flip,
                               const int32_t *limb_reserve, int n_reserve, void *stream);
 
+/* A prepared og_decode_features_dev_ex: a network writes its outputs to the same buffers batch
+ * after batch, so a caller validates and records the arguments once (og_plan_features, which
+ * also installs the flip tables) and then launches each batch with three arguments.  A plan stays
+ * valid for the life of the handle while the buffers exist and the flip tables are unchanged. */
+int og_plan_features(og_handle *h, const void *hmp_dev, const void *off_dev, int dtype,
+                     int64_t hmp_image_stride, int64_t off_image_stride, int n, int hgt, int w,
+                     int hmp_stride, int off_stride, int resize_mode, int flip_test,
+                     const int32_t *kp_flip, const int32_t *limb_flip, const int32_t *limb_reserve,
+                     int n_reserve, int32_t *plan_id);
+int og_plan_launch(og_handle *h, int32_t plan_id, void *stream);
+
 /* Up to OG_MAX_IN_FLIGHT og_decode_* calls may be in flight on a handle (results are queued in
  * order): every call owns a result slot with its own stream, scratch and pinned result buffer,
  * so the kernels of consecutive calls overlap each other and the host-side consumption of
@@ -245,7 +256,7 @@ typedef struct og_result {
     int32_t n_images;            /* images of the decode call this result belongs to */
     int32_t total_rows;
     int32_t n_keypoints;
-    int32_t reserved;
+    int32_t buffer_id;           /* changes whenever the pointers refer to another (re-allocated) buffer */
     /* only after og_set_frames (else NULL): the result rows of the reference's evaluation loop,
      * row r of these arrays = pose row r */
     const float *coco_keypoints; /* [total_rows, 3 * n_keypoints]  x, y, flag per keypoint */
@@ -295,6 +306,10 @@ int64_t og_graph_build_count(const og_handle *h);
  * -DOG_K3_PROFILE (returns OG_ERR_UNSUPPORTED otherwise). */
 int og_debug_k3_profile(uint64_t *out16, int reset);
 int64_t og_fused_redo_count(const og_handle *h);
+/* K3 groups an image with one warp and a 64-row person table in shared memory.  An image that
+ * needs more rows (noise-like input) is grouped by the CTA kernel (tables in global memory)
+ * when its batch is fetched; og_k3_redo_count reports how many fetches did that. */
+int64_t og_k3_redo_count(const og_handle *h);
 
 /* og_decode_features_host, fused path: when `off_host` is pinned (device-accessible) host memory
  * the offset maps are NOT copied to the device — K2 reads its 2 * L * K bilinear samples per image

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG_DIR, 'libogdecoder.so')
 OG_LIMB_COLS = 13
 OG_POSE_COLS = 6
 OG_MAX_TOPK = 128
-OG_MAX_IN_FLIGHT = 8
+OG_MAX_IN_FLIGHT = 16
 OG_DTYPE_F32 = 0
 OG_DTYPE_BF16 = 1
 OG_DTYPE_F16 = 2
@@ -49,7 +49,7 @@ class OgResult(ctypes.Structure):
         ('n_images', ctypes.c_int32),
         ('total_rows', ctypes.c_int32),
         ('n_keypoints', ctypes.c_int32),
-        ('reserved', ctypes.c_int32),
+        ('buffer_id', ctypes.c_int32),
         ('coco_keypoints', c_float_p),
         ('coco_scores', ctypes.POINTER(ctypes.c_double)),
         ('coco_images', c_int32_p),
@@ -90,6 +90,9 @@ SIGNATURES = {
                                        _i, _i, c_int32_p, c_int32_p, c_int32_p, _i, _vp]),
     'og_fetch_poses': (_i, [_vp, ctypes.POINTER(c_float_p), ctypes.POINTER(c_int32_p),
                             ctypes.POINTER(c_int32_p), ctypes.POINTER(ctypes.c_int32)]),
+    'og_plan_features': (_i, [_vp, _vp, _vp, _i, ctypes.c_int64, ctypes.c_int64, _i, _i, _i, _i, _i,
+                              _i, _i, c_int32_p, c_int32_p, c_int32_p, _i, ctypes.POINTER(ctypes.c_int32)]),
+    'og_plan_launch': (_i, [_vp, ctypes.c_int32, _vp]),
     'og_fetch_result': (_i, [_vp, ctypes.POINTER(OgResult)]),
     'og_set_frames': (_i, [_vp, ctypes.POINTER(ctypes.c_double), _i]),
     'og_pending': (_i, [_vp]),
@@ -101,6 +104,7 @@ SIGNATURES = {
     'og_graph_build_count': (ctypes.c_int64, [_vp]),
     'og_debug_k3_profile': (_i, [ctypes.POINTER(ctypes.c_uint64), _i]),
     'og_fused_redo_count': (ctypes.c_int64, [_vp]),
+    'og_k3_redo_count': (ctypes.c_int64, [_vp]),
     'og_set_zero_copy': (_i, [_vp, _i]),
     'og_zero_copy_count': (ctypes.c_int64, [_vp]),
     'og_enable_stage_timing': (_i, [_vp, _i]),

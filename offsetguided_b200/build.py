@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.path.join(PKG_DIR, 'libogdecoder.so')
 SOURCES = ['og_api.cu', 'og_nms_topk.cu', 'og_fused.cu', 'og_limbs.cu', 'og_group.cu', 'og_resize.cu']
-HEADERS = ['og_common.cuh', 'og_interp.cuh', os.path.join('..', '..', 'include', 'og_decoder.h')]
+HEADERS = ['og_common.cuh', 'og_interp.cuh', 'og_prep.cuh', os.path.join('..', '..', 'include', 'og_decoder.h')]
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',

@@ -20,6 +20,14 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int chain_carveout_percent() {
+    static const int value = [] {
+        const char *env = getenv("OG_CARVEOUT");
+        return env ? atoi(env) : kChainCarveoutPercent;
+    }();
+    return value;
+}
+
 }  // namespace og
 
 using namespace og;
@@ -201,6 +209,7 @@ struct og_handle {
     int host_tail;               // ... with a short last range (tuning aid: OG_HOST_TAIL=0 disables)
     int select_on_aux;           // host / full-resolution paths: 0 never, 1 fused path only, 2 always (tuning aid)
     int64_t fused_redos;
+    int64_t k3_redos;            // fetches that ran the CTA grouping kernel for images the warp kernel gave up
     int64_t zero_copy_calls;
     int64_t graph_replays, graph_builds;
     uint64_t graph_clock;
@@ -210,6 +219,15 @@ struct og_handle {
     uint8_t reserved_cache[OG_MAX_LIMBS];
 
     bool timing;
+    struct Plan {                // og_plan_features: the arguments of a repeated device-path decode
+        const void *hmp, *off;
+        int dtype;
+        int64_t hmp_is, off_is;
+        int n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test;
+        uint64_t tables_version;
+    };
+    Plan *plans;
+    int n_plans, cap_plans;
     double *staged_frames;       // og_set_frames: frames of the NEXT decode call
     int staged_n, staged_cap;
 };
@@ -362,16 +380,21 @@ int ensure_group_scratch(og_handle *h, GroupScratch &gs, int n, ResultSlot *slot
 // K3 on `n` images whose scratch rows start at image `i0` of the scratch buffers.
 int run_k3(og_handle *h, GroupScratch &gs, int i0, const float *limbs, bool prepared, int n,
            float *out_poses, int capacity_rows, int32_t *out_offset, int32_t *out_count,
-           int32_t *out_total, cudaStream_t s, const CocoOut *coco = nullptr) {
+           int32_t *out_total, cudaStream_t s, const CocoOut *coco = nullptr, int32_t *lazy_flag = nullptr,
+           bool redo_only = false) {
     const og_config &c = h->cfg;
     GroupLaunch g = group_launch(h, n);
     if (coco) g.coco = *coco;
+    g.lazy_flag = lazy_flag;
     g.prep = gs.prep.ptr + (size_t)i0 * c.n_limbs * (c.topk + 1);
     g.rec = gs.rec.ptr + (size_t)i0 * c.n_limbs * c.topk * 3;
     g.cnt = gs.cnt.ptr + (size_t)i0 * c.n_limbs;
     g.redo = gs.redo.ptr + i0;
     g.slab_stride = ((size_t)c.n_limbs * c.topk * c.n_keypoints * 6 + 3) / 4 * 4;
     g.slab = gs.slab.ptr + (size_t)i0 * g.slab_stride;
+    if (redo_only)
+        return launch_group_redo(g, limbs, out_poses, capacity_rows, out_offset, out_count, out_total, s,
+                                 &h->launches);
     return launch_group(g, limbs, prepared, out_poses, capacity_rows, out_offset, out_count, out_total, s,
                         &h->launches);
 }
@@ -468,7 +491,10 @@ int begin_call(og_handle *h, ResultSlot *slot, const K1Fused *fused, int n, int 
     slot->has_limbs = false;
     if (!slot->prep_marked) OG_TRY(mark(h, slot, 0, s));
     slot->prep_marked = false;
-    if (n > 0) reinterpret_cast<volatile int32_t *>(slot->out_host)[2 * n] = 0;      // overflow flag
+    if (n > 0) {
+        reinterpret_cast<volatile int32_t *>(slot->out_host)[2 * n] = 0;          // candidate-list overflow flag
+        reinterpret_cast<volatile int32_t *>(slot->out_host)[2 * n + 1] = 0;      // K3: images left to the CTA kernel
+    }
     return OG_OK;
 }
 
@@ -556,8 +582,12 @@ int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, cons
     h->launches += 1;
     if (timed) OG_TRY(mark(h, slot, 5, a));
     const CocoOut coco = coco_out(h, slot, i0);
+    // A call that is one range leaves the images whose person table outgrows the warp kernel's
+    // (noise-like inputs) to og_fetch_result: the kernel raises meta[2n + 1] and the fetch runs the
+    // CTA kernel for them, instead of a launch of early-exit CTAs behind every call.
+    int32_t *lazy_flag = (i0 == 0 && cn == n) ? meta + 2 * n + 1 : nullptr;
     OG_TRY(run_k3(h, gs, i0, limbs, true, cn, poses, slot->capacity_rows, meta + i0, meta + n + i0,
-                  slot->total.ptr, a, &coco));
+                  slot->total.ptr, a, &coco, lazy_flag));
     if (timed) OG_TRY(mark(h, slot, 6, a));
     slot->k3_first = i0;
     slot->k3_images = cn;
@@ -657,7 +687,7 @@ int decode_chain(og_handle *h, ResultSlot *slot, const K1Fused &k1, const Offset
         slot->key[gi] = key;
         h->graph_builds += 1;
     } else {
-        h->launches += 7;           // scan, list, blocks, select, K2, K3 warp, K3 CTA: the graph's kernel nodes
+        h->launches += 6;           // scan, list, blocks, select, K2, K3: the graph's kernel nodes
         slot->k3_first = 0;
         slot->k3_images = n;
     }
@@ -847,7 +877,10 @@ int og_create(const og_config *cfg, og_handle **out) {
     h->graph_enabled = true;
     if (const char *env = getenv("OG_GRAPH")) h->graph_enabled = atoi(env) != 0;     // tuning aid
     h->graph_replays = h->graph_builds = 0;
+    h->k3_redos = 0;
     h->graph_clock = 0;
+    h->plans = nullptr;
+    h->n_plans = h->cap_plans = 0;
     h->staged_frames = nullptr;
     h->staged_n = -1;
     h->staged_cap = 0;
@@ -1002,6 +1035,7 @@ int og_destroy(og_handle *h) {
     }
     if (h->cp) cudaStreamDestroy(h->cp);
     free(h->staged_frames);
+    free(h->plans);
     delete h;
     return OG_OK;
 }
@@ -1195,17 +1229,12 @@ int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_
                                 resize_mode, flip_test, s, true);
 }
 
-int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off_dev, int dtype,
-                              int64_t hmp_image_stride, int64_t off_image_stride, int n, int hgt,
-                              int w, int hmp_stride, int off_stride, int resize_mode, int flip_test,
-                              const int32_t *kp_flip, const int32_t *limb_flip,
-                              const int32_t *limb_reserve, int n_reserve, void *stream) {
-    OG_REQUIRE(h && (n == 0 || (hmp_dev && off_dev)), "og_decode_features_dev_ex: null pointer");
-    OG_REQUIRE(dtype == OG_DTYPE_F32 || dtype == OG_DTYPE_BF16 || dtype == OG_DTYPE_F16,
-               "dtype must be OG_DTYPE_F32, OG_DTYPE_BF16 or OG_DTYPE_F16");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
-                              limb_flip, limb_reserve, n_reserve));
+namespace {
+
+// og_decode_features_dev_ex behind its argument checks (also the body of a plan launch)
+int decode_dev_views(og_handle *h, const void *hmp_dev, const void *off_dev, int dtype,
+                     int64_t hmp_image_stride, int64_t off_image_stride, int n, int hgt, int w,
+                     int hmp_stride, int off_stride, int resize_mode, int flip_test, cudaStream_t s) {
     const og_config &c = h->cfg;
     const size_t hw = (size_t)hgt * w;
     const size_t hmp_img = (size_t)c.n_keypoints * hw, off_img = (size_t)2 * c.n_limbs * hw;
@@ -1215,10 +1244,12 @@ int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off
                "off_image_stride %lld is smaller than one image (%zu elements)", (long long)off_image_stride, off_img);
     MapView hv = {hmp_dev, dtype, hmp_image_stride ? (size_t)hmp_image_stride : hmp_img};
     MapView ov = {off_dev, dtype, off_image_stride ? (size_t)off_image_stride : off_img};
-    if (dtype == OG_DTYPE_F32 && hv.image_stride == hmp_img && ov.image_stride == off_img)
-        return og_decode_features_dev(h, static_cast<const float *>(hmp_dev), static_cast<const float *>(off_dev),
-                                      n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
-                                      limb_flip, limb_reserve, n_reserve, stream);
+    if (dtype == OG_DTYPE_F32 && hv.image_stride == hmp_img && ov.image_stride == off_img) {
+        ResultSlot *slot = nullptr;
+        OG_TRY(acquire_slot(h, nullptr, &slot));
+        return decode_features_impl(h, slot, static_cast<const float *>(hmp_dev), static_cast<const float *>(off_dev),
+                                    n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, s, true);
+    }
     if (!(h->fused_enabled && c.thre_hmp > 0.0f && fused_supported(n, c.n_keypoints, hmp_stride, hgt, w))) {
         set_error("og_decode_features_dev_ex: bf16 / strided maps need the fused path (stride 2, 4 or 8, "
                   "thre_hmp > 0, fused enabled); convert to dense float32 and call og_decode_features_dev");
@@ -1233,6 +1264,60 @@ int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off
     K1Fused k1 = {hv, hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
     OffsetSource src = {ov, hgt, w, off_stride, flip_test ? 1 : 0, n};
     return decode_chain(h, slot, k1, src, n, H, W, s);
+}
+
+}  // namespace
+
+int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off_dev, int dtype,
+                              int64_t hmp_image_stride, int64_t off_image_stride, int n, int hgt,
+                              int w, int hmp_stride, int off_stride, int resize_mode, int flip_test,
+                              const int32_t *kp_flip, const int32_t *limb_flip,
+                              const int32_t *limb_reserve, int n_reserve, void *stream) {
+    OG_REQUIRE(h && (n == 0 || (hmp_dev && off_dev)), "og_decode_features_dev_ex: null pointer");
+    OG_REQUIRE(dtype == OG_DTYPE_F32 || dtype == OG_DTYPE_BF16 || dtype == OG_DTYPE_F16,
+               "dtype must be OG_DTYPE_F32, OG_DTYPE_BF16 or OG_DTYPE_F16");
+    OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
+                              limb_flip, limb_reserve, n_reserve));
+    return decode_dev_views(h, hmp_dev, off_dev, dtype, hmp_image_stride, off_image_stride, n, hgt, w, hmp_stride,
+                            off_stride, resize_mode, flip_test, static_cast<cudaStream_t>(stream));
+}
+
+int og_plan_features(og_handle *h, const void *hmp_dev, const void *off_dev, int dtype,
+                     int64_t hmp_image_stride, int64_t off_image_stride, int n, int hgt, int w,
+                     int hmp_stride, int off_stride, int resize_mode, int flip_test,
+                     const int32_t *kp_flip, const int32_t *limb_flip, const int32_t *limb_reserve,
+                     int n_reserve, int32_t *plan_id) {
+    OG_REQUIRE(h && plan_id, "og_plan_features: null pointer");
+    *plan_id = -1;
+    OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
+                              limb_flip, limb_reserve, n_reserve));
+    if (h->n_plans == h->cap_plans) {
+        const int cap = h->cap_plans ? 2 * h->cap_plans : 16;
+        og_handle::Plan *grown = static_cast<og_handle::Plan *>(realloc(h->plans, (size_t)cap * sizeof(og_handle::Plan)));
+        if (!grown) {
+            set_error("host allocation failed");
+            return OG_ERR_OUT_OF_MEMORY;
+        }
+        h->plans = grown;
+        h->cap_plans = cap;
+    }
+    OG_REQUIRE(hmp_dev && off_dev && n > 0, "og_plan_features: null pointer or empty batch");
+    OG_REQUIRE(dtype == OG_DTYPE_F32 || dtype == OG_DTYPE_BF16 || dtype == OG_DTYPE_F16,
+               "dtype must be OG_DTYPE_F32, OG_DTYPE_BF16 or OG_DTYPE_F16");
+    h->plans[h->n_plans] = og_handle::Plan{hmp_dev, off_dev, dtype, hmp_image_stride, off_image_stride, n, hgt, w,
+                                           hmp_stride, off_stride, resize_mode, flip_test, h->tables_version};
+    *plan_id = h->n_plans++;
+    return OG_OK;
+}
+
+int og_plan_launch(og_handle *h, int32_t plan_id, void *stream) {
+    OG_REQUIRE(h && plan_id >= 0 && plan_id < h->n_plans, "og_plan_launch: unknown plan %d", plan_id);
+    const og_handle::Plan &p = h->plans[plan_id];
+    OG_REQUIRE(!p.flip_test || p.tables_version == h->tables_version,
+               "og_plan_launch: the flip tables changed since plan %d was made", plan_id);
+    OG_TRY(check_device(h));
+    return decode_dev_views(h, p.hmp, p.off, p.dtype, p.hmp_is, p.off_is, p.n, p.hgt, p.w, p.hmp_stride, p.off_stride,
+                            p.resize_mode, p.flip_test, static_cast<cudaStream_t>(stream));
 }
 
 int og_decode_features_host(og_handle *h, const float *hmp_host, const float *off_host, int n,
@@ -1401,6 +1486,17 @@ int og_fetch_result(og_handle *h, og_result *out) {
             OG_CUDA_TRY(cudaStreamSynchronize(slot->work));
             meta = reinterpret_cast<const volatile int32_t *>(slot->out_host);
         }
+        if (meta[2 * n + 1] != 0) {
+            // some image's person table outgrew the warp kernel's rows: the CTA kernel (global
+            // slab tables) groups those images now, appending their rows behind the others
+            h->k3_redos += 1;
+            int32_t *meta_dev = reinterpret_cast<int32_t *>(slot->out_dev);
+            const CocoOut coco = coco_out(h, slot, 0);
+            OG_TRY(run_k3(h, slot->group, 0, slot->limbs.ptr, true, n, reinterpret_cast<float *>(slot->out_dev + slot->meta_bytes),
+                          slot->capacity_rows, meta_dev, meta_dev + n, slot->total.ptr, slot->work, &coco, nullptr, true));
+            OG_CUDA_TRY(cudaStreamSynchronize(slot->work));
+            reinterpret_cast<volatile int32_t *>(slot->out_host)[2 * n + 1] = 0;
+        }
         for (int i = 0; i < n; ++i) total += meta[n + i];
         if (total > slot->capacity_rows) {       // rare: more persons than the pinned buffer was sized for
             OG_TRY(regroup_with_full_capacity(h, slot));
@@ -1425,6 +1521,8 @@ int og_fetch_result(og_handle *h, og_result *out) {
     out->n_images = n;
     out->total_rows = (int32_t)total;
     out->n_keypoints = h->cfg.n_keypoints;
+    // identifies the pinned buffer behind the pointers (a binding can cache its views by it)
+    out->buffer_id = (int32_t)((slot - h->slots) | ((slot->buffers_version & 0x3ffffff) << 4));
     slot->pending = false;
     h->pending -= 1;
     h->fetched_slot = h->queue[h->tail];
@@ -1481,6 +1579,8 @@ int og_set_fused(og_handle *h, int enable) {
 }
 
 int64_t og_fused_redo_count(const og_handle *h) { return h ? h->fused_redos : 0; }
+
+int64_t og_k3_redo_count(const og_handle *h) { return h ? h->k3_redos : 0; }
 
 int og_set_zero_copy(og_handle *h, int enable) {
     OG_REQUIRE(h, "og_set_zero_copy: null handle");

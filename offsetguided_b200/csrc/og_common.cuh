@@ -49,6 +49,7 @@ void set_error(const char *fmt, ...);
 // on the full-resolution path: K1 0.266 -> 0.305 ms when the kernel running beside it grew from
 // 2.5 to 10.5 KB of shared memory per CTA.  All chain kernels therefore ask for the same split.
 constexpr int kChainCarveoutPercent = 58;      // -> 132 KB shared memory, 96 KB L1 per SM
+int chain_carveout_percent();                  // kChainCarveoutPercent, or OG_CARVEOUT (tuning aid; -1 = leave the default)
 
 #ifdef __CUDACC__
 template <auto Kernel>
@@ -57,8 +58,9 @@ inline void prefer_chain_carveout() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
     if ((done >> dev) & 1ull) return;
-    if (cudaFuncSetAttribute(Kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kChainCarveoutPercent) !=
-        cudaSuccess)
+    const int percent = chain_carveout_percent();
+    if (percent >= 0 &&
+        cudaFuncSetAttribute(Kernel, cudaFuncAttributePreferredSharedMemoryCarveout, percent) != cudaSuccess)
         (void)cudaGetLastError();
     done |= 1ull << dev;
 }
@@ -227,6 +229,9 @@ struct GroupLaunch {
     int32_t *cnt;               // [n, L] kept rows per (image, limb)
     int32_t *redo;              // [n] images the warp kernel handed to the CTA kernel
     CocoOut coco;
+    int32_t *lazy_flag;         // nullptr: the CTA kernel always follows the warp kernel (early-exit CTAs);
+                                // else the warp kernel sets *lazy_flag when an image needs it and the
+                                // caller runs launch_group_redo after looking at the flag
 };
 int read_k3_profile(unsigned long long *out16, bool reset);
 size_t group_smem_bytes(const GroupLaunch &g);
@@ -239,6 +244,11 @@ int prepare_group_kernel(size_t smem_bytes, size_t warp_smem_bytes);
 int launch_group(const GroupLaunch &g, const float *limbs, bool prepared, float *out_poses,
                  int capacity_rows, int32_t *out_offset, int32_t *out_count, int32_t *out_total,
                  cudaStream_t s, int64_t *launches);
+
+// the CTA kernel for the images the warp kernel flagged in g.redo (all images when warp_rows == 0)
+int launch_group_redo(const GroupLaunch &g, const float *limbs, float *out_poses, int capacity_rows,
+                      int32_t *out_offset, int32_t *out_count, int32_t *out_total, cudaStream_t s,
+                      int64_t *launches);
 
 int launch_scored_offset(const float *hmp, const float *off, int n, int c, int l, int h, int w,
                          int ksize, const SkeletonDev &sk, float *out, cudaStream_t s);

@@ -84,6 +84,7 @@ struct GroupArgs {
     float *slab;     // per image: xyvs float4[PMAX*C], score float[PMAX*C], ids int[PMAX*C]
     size_t slab_stride;
     CocoOut coco;    // optional back-projected result rows (frames == nullptr: off)
+    int32_t *lazy_flag;   // warp kernel: set when some image needs the CTA kernel (nullptr: it always follows)
 };
 
 // Result rows as the reference's evaluation loop builds them from the poses of one image
@@ -554,6 +555,10 @@ struct WarpLayout {
     size_t xyvs, score, ids, rec, k_int, p_f64, p_i32, p_i16, p_u8, cnt, total;
 };
 
+// Kept rows are fetched kRecRing - 1 limb types ahead: a limb step of the register path is ~1000
+// cycles, less than one L2 round trip of the rows behind it.
+constexpr int kRecRing = 4;
+
 // Person-table rows are CS entries apart, CS = the multiple of 4 >= C with CS % 8 == 4: a row of
 // ids is a few aligned 128-bit words (the pair test of the merge step compares whole rows), the
 // quarter-warps of such loads hit distinct banks, and column accesses of 32 different rows
@@ -572,7 +577,7 @@ __host__ __device__ inline WarpLayout make_warp_layout(int C, int L, int K, int 
     lo.score = at; at += (size_t)rows * cs * 4;
     lo.ids = at;   at += (size_t)rows * cs * 4;
     at = align_up(at, 16);
-    lo.rec = at;   at += 2 * (size_t)K * 48;            // kept rows of two limb types (double buffer)
+    lo.rec = at;   at += kRecRing * (size_t)K * 48;     // kept rows of the next limb types (prefetch ring)
     lo.k_int = at; at += (size_t)3 * K * 4;             // per kept row: persons matched at one / both ends, new list
     at = align_up(at, 8);
     lo.p_f64 = at; at += (size_t)rows * 8;              // person scores
@@ -634,28 +639,37 @@ group_warp_kernel(GroupArgs a, const float4 *__restrict__ rec, const int32_t *__
     for (int l = lane; l < L; l += 32) s_cnt[l] = __ldg(cnt + (size_t)img * L + l);
     __syncwarp();
 
-    // the kept rows of limb type li + 1 arrive (cp.async) while type li is processed
+    // the kept rows of limb types li + 1 .. li + kRecRing - 1 arrive (cp.async) while type li is
+    // processed; every call commits one group (an empty one past the last type), so "at most
+    // kRecRing - 2 groups pending" always means "type li has landed"
     auto fetch_rows = [&](int li) {
-        const int n16 = s_cnt[li] * 3;
-        float4 *dst = s_rec0 + (size_t)(li & 1) * K * 3;
-        const float4 *src = rec_img + (size_t)li * K * 3;
+        if (li < L) {
+            const int n16 = (s_cnt[li] & kPrepCountMask) * 3;
+            float4 *dst = s_rec0 + (size_t)(li % kRecRing) * K * 3;
+            const float4 *src = rec_img + (size_t)li * K * 3;
 #pragma unroll 1
-        for (int i = lane; i < n16; i += 32) cp_async16(dst + i, src + i);
+            for (int i = lane; i < n16; i += 32) cp_async16(dst + i, src + i);
+        }
         asm volatile("cp.async.commit_group;");
     };
-    fetch_rows(0);
+#pragma unroll 1
+    for (int li = 0; li < kRecRing - 1; ++li) fetch_rows(li);
 
     int mm = 0, nalloc = 0;
+    // `dirty`: some pair of persons may share exactly two ids although no id changes in this step
+    // (a merge or a "cancellation" person of an earlier step); see the merge step below
+    bool dirty = false;
 #pragma unroll 1
     for (int li = 0; li < L; ++li) {
-        const int kk = s_cnt[li];
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        const int kk = s_cnt[li] & kPrepCountMask;
+        const bool dup_from = (s_cnt[li] & kPrepDupFrom) != 0;     // two kept rows start at the same joint id
+        asm volatile("cp.async.wait_group %0;" ::"n"(kRecRing - 2) : "memory");
         __syncwarp();          // rows of type li have landed; everybody is done with type li - 1
-        if (li + 1 < L) fetch_rows(li + 1);
+        fetch_rows(li + kRecRing - 1);
         OG_K3_PROF(0);
         if (kk == 0) continue;                                             // group.py:84-85
         const int jf = a.sk.from[li], jt = a.sk.to[li];
-        const float4 *s_rec = s_rec0 + (size_t)(li & 1) * K * 3;
+        const float4 *s_rec = s_rec0 + (size_t)(li % kRecRing) * K * 3;
         if (mm <= 32 && kk <= 32) {
             // ================= register path: at most 32 persons and 32 kept rows ==============
             // lane = person AND lane = kept row.  The limb step is a chain of dependent steps, so
@@ -681,32 +695,51 @@ group_warp_kernel(GroupArgs a, const float4 *__restrict__ rec, const int32_t *__
                 sc_f = score[at_f];
                 sc_t = score[at_t];
             }
-            // ---- match (group.py:87-109): every lane walks the kept rows; the last match wins
-            int pk1 = -1, pk2 = -1, n1 = 0, n2 = 0, pk1_i1 = 0, pk1_i2 = 0;
-            float pk1_sc = 0.f, pk2_sc = 0.f;
-#pragma unroll 2
+            // ---- match (group.py:87-109): every lane walks the kept rows (one broadcast 128-bit
+            //      load each, no cross-lane traffic inside the loop) and collects three bit sets over
+            //      them: rows that start / end at this person's joint ids, rows whose score passes
+            //      the replacement test.  m1 / m2: rows matched at one end / at both ends; the LAST
+            //      replacing row of each kind wins (row-major fancy-index scatter).
+            unsigned mf = 0u, mt = 0u, mrep = 0u;
+            const float sc_min = fminf(sc_t, sc_f);         // sc > sc_t || sc > sc_f (fminf drops a NaN like the two tests do)
+#pragma unroll 4
             for (int j = 0; j < kk; ++j) {
-                const int i1 = __shfl_sync(kAll, my_id1, j), i2 = __shfl_sync(kAll, my_id2, j);
-                const float sc = __shfl_sync(kAll, r0.z, j);
-                const int ms = live ? ((id_f == i1 ? 1 : 0) + (id_t == i2 ? 1 : 0)) : 0;
-                const unsigned b2 = __ballot_sync(kAll, ms == 2), b1 = __ballot_sync(kAll, ms == 1);
-                if (lane == j) {
-                    n2 = __popc(b2);
-                    n1 = __popc(b1);
-                }
-                const bool rep = (sc > sc_t) || (sc > sc_f);
-                if (ms == 2 && rep) {
-                    pk2 = j;
-                    pk2_sc = sc;
-                }
-                if (ms == 1 && rep) {
-                    pk1 = j;
-                    pk1_sc = sc;
-                    pk1_i1 = i1;
-                    pk1_i2 = i2;
-                }
+                const float4 q = s_rec[j * 3];
+                const unsigned bit = 1u << j;
+                if (id_f == __float_as_int(q.x)) mf |= bit;
+                if (id_t == __float_as_int(q.y)) mt |= bit;
+                if (q.z > sc_min) mrep |= bit;
             }
+            if (!live) mf = mt = 0u;
+            const unsigned m2 = mf & mt, m1 = mf ^ mt;
+            const int pk2 = 31 - __clz(m2 & mrep), pk1 = 31 - __clz(m1 & mrep);      // -1: none
+            int pk1_i1 = 0, pk1_i2 = 0;
+            float pk1_sc = 0.f, pk2_sc = 0.f;
+            if (pk1 >= 0) {
+                const float4 q = s_rec[pk1 * 3];
+                pk1_i1 = __float_as_int(q.x);
+                pk1_i2 = __float_as_int(q.y);
+                pk1_sc = q.z;
+            }
+            if (pk2 >= 0) pk2_sc = s_rec[pk2 * 3].z;
+            const unsigned any1 = __reduce_or_sync(kAll, m1), any2 = __reduce_or_sync(kAll, m2);
+            const unsigned matched = any1 | any2;           // kept rows some person matches
             const bool any_p2 = __any_sync(kAll, pk2 >= 0), any_p1 = __any_sync(kAll, pk1 >= 0);
+            // ---- does the merge step have anything to find?  (group.py:140-155 compares every pair
+            //      of persons over all joints in every step.)  A pair's number of shared ids only
+            //      changes when a "one end known" update rewrites a joint id, and then only
+            //        - downwards, if the rewritten slot held an id before            (`lost`), or
+            //        - upwards, if two persons end up holding the same id of this limb type: both
+            //          match the same kept row (`overlap`), or their rows start at the same joint
+            //          (`dup_from`).
+            //      Without any of these — the normal step: unset joints filled in — no pair count
+            //      changes, and a table without a pair sharing exactly two ids (`!dirty`) stays so.
+            bool need_scan = dirty;
+            if (!need_scan && any_p1) {
+                const bool lost = pk1 >= 0 && ((id_t != pk1_i2 && id_t != -1) || (id_f != pk1_i1 && id_f != -1));
+                const bool overlap = __reduce_add_sync(kAll, (unsigned)__popc(m1 | m2)) > (unsigned)__popc(matched);
+                need_scan = overlap || dup_from || __any_sync(kAll, lost);
+            }
             OG_K3_PROF(1);
             // ---- apply (group.py:114-135): both ends known, then one end known
             if (pk2 >= 0) {
@@ -731,7 +764,8 @@ group_warp_kernel(GroupArgs a, const float4 *__restrict__ rec, const int32_t *__
             //      persons holding the same keypoint id; bit-sliced counters add these sets up over
             //      the columns, and the persons sharing EXACTLY two ids fall out as one mask per lane.
             int mm_after = mm;
-            if (mm >= 2) {
+            if (mm >= 2 && need_scan) {
+                dirty = false;
                 unsigned ones = 0u, twos = 0u, fours = 0u, over = 0u;
                 auto add_column = [&](int v) {
                     unsigned m = __match_any_sync(kAll, v);
@@ -780,17 +814,37 @@ group_warp_kernel(GroupArgs a, const float4 *__restrict__ rec, const int32_t *__
                     __syncwarp();
                     if (keep) s_order[__popc(kb & lt_mask)] = (int16_t)my_ord;
                     mm_after = __popc(kb);
+                    dirty = true;           // merged rows may share two ids with a third person
                 }
             }
             OG_K3_PROF(5);
-            // ---- new persons (group.py:166-177), lane = kept row
+            // ---- new persons (group.py:166-177), lane = kept row: column sum n2 * w2 + n1 * w1 == 0.
+            //      With both weights of one sign this is "nobody matches the row"; with opposite
+            //      signs a row matched at one end by as many persons as the weights balance
+            //      cancels to 0 as well (the reference's quirk) — counted only for such rows.
             const int w2 = any_p2 ? -1 : 2, w1 = any_p1 ? -1 : 1;
-            const bool isnew = lane < kk && (n2 * w2 + n1 * w1 == 0);
+            bool isnew = lane < kk && ((matched >> lane) & 1u) == 0u;
+            if (any_p1 != any_p2) {
+                unsigned both = any1 & any2;
+#pragma unroll 1
+                while (both) {
+                    const int j = __ffs(both) - 1;
+                    both &= both - 1u;
+                    const int n2 = __popc(__ballot_sync(kAll, (m2 >> j) & 1u));
+                    const int n1 = __popc(__ballot_sync(kAll, (m1 >> j) & 1u));
+                    if (lane == j) isnew = (n2 * w2 + n1 * w1 == 0);
+                }
+            }
+            // a person made from a row that somebody matches shares ids with that somebody
+            if (__any_sync(kAll, isnew && ((matched >> lane) & 1u))) dirty = true;
             const unsigned nb = __ballot_sync(kAll, isnew);
             const int nnew = __popc(nb);
             if (nalloc + nnew > R) {
                 asm volatile("cp.async.wait_all;" ::: "memory");
-                if (lane == 0) redo[img] = 1;
+                if (lane == 0) {
+                    redo[img] = 1;
+                    if (a.lazy_flag) *a.lazy_flag = 1;
+                }
                 return;
             }
             if (isnew) {
@@ -803,8 +857,8 @@ group_warp_kernel(GroupArgs a, const float4 *__restrict__ rec, const int32_t *__
                     reinterpret_cast<int4 *>(ids + base)[v] = unset_i;
                     reinterpret_cast<float4 *>(score + base)[v] = unset_f;
                 }
-#pragma unroll 1
-                for (int c = 0; c < CS; ++c) xyvs[base + c] = unset_f;
+#pragma unroll 4
+                for (int c = 0; c < CS; ++c) xyvs[base + c] = unset_f;          // CS is a multiple of 4
                 ids[base + jf] = my_id1;
                 ids[base + jt] = my_id2;
                 score[base + jf] = r0.z;
@@ -975,7 +1029,10 @@ group_warp_kernel(GroupArgs a, const float4 *__restrict__ rec, const int32_t *__
         }
         if (nalloc + nnew > R) {            // warp-uniform: the CTA kernel redoes this image
             asm volatile("cp.async.wait_all;" ::: "memory");
-            if (lane == 0) redo[img] = 1;
+            if (lane == 0) {
+                redo[img] = 1;
+                if (a.lazy_flag) *a.lazy_flag = 1;
+            }
             return;
         }
         if (nnew > 0) {
@@ -1006,6 +1063,7 @@ group_warp_kernel(GroupArgs a, const float4 *__restrict__ rec, const int32_t *__
         }
         nalloc += nnew;
         mm = mm_after + nnew;
+        dirty = true;           // the general path keeps no account of what it changed
         OG_K3_PROF(6);
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -1046,6 +1104,13 @@ group_warp_kernel(GroupArgs a, const float4 *__restrict__ rec, const int32_t *__
         nk += __popc(ballot);
     }
     __syncwarp();
+    int off = 0;
+    if (lane == 0) {        // the row allocation's round trip to L2 runs beside the ranking below
+        off = atomicAdd(out_total, nk);
+        out_offset[img] = off;
+        out_count[img] = nk;
+        redo[img] = 0;
+    }
 #pragma unroll 1
     for (int q = lane; q < nk; q += 32) {
         double ps = s_ps[s_pa[q]];
@@ -1058,13 +1123,6 @@ group_warp_kernel(GroupArgs a, const float4 *__restrict__ rec, const int32_t *__
             rank += (p2 > ps || (p2 == ps && q2 < q)) ? 1 : 0;
         }
         s_pb[q] = rank;
-    }
-    int off = 0;
-    if (lane == 0) {
-        off = atomicAdd(out_total, nk);
-        out_offset[img] = off;
-        out_count[img] = nk;
-        redo[img] = 0;
     }
     off = __shfl_sync(kAll, off, 0);
     __syncwarp();
@@ -1115,6 +1173,7 @@ GroupArgs to_args(const GroupLaunch &g) {
     a.slab = g.slab;
     a.slab_stride = g.slab_stride;
     a.coco = g.coco;
+    a.lazy_flag = g.lazy_flag;
     return a;
 }
 
@@ -1179,22 +1238,36 @@ int launch_group(const GroupLaunch &g, const float *limbs, bool prepared, float 
         OG_CUDA_TRY(cudaGetLastError());
         if (launches) *launches += 1;
     }
-    const int32_t *redo = nullptr;
-    GroupLaunch cta = g;
     if (g.warp_rows > 0) {
         prefer_chain_carveout<group_warp_kernel>();
         group_warp_kernel<<<g.n, 32, group_warp_smem_bytes(g), s>>>(
             to_args(g), g.rec, g.cnt, out_poses, capacity_rows, out_offset, out_count, out_total, g.redo);
         OG_CUDA_TRY(cudaGetLastError());
         if (launches) *launches += 1;
-        redo = g.redo;
-        // Behind the warp kernel the CTA kernel only redoes images whose table outgrew 64 rows, and
-        // nearly every CTA of this launch exits at once: it gets NO shared-memory table (the image
-        // goes straight to its global slab), so that a launch of early-exit CTAs does not ask every
-        // SM for 200 KB of shared memory while the next call's streaming kernels are resident.
-        cta.smem_rows = 0;
+        // lazy: the caller looks at *lazy_flag once the launch has finished and calls
+        // launch_group_redo for the (noise-like) batches that need it
+        if (g.lazy_flag != nullptr) return OG_OK;
     }
-    if (g.warp_rows > 0) prefer_chain_carveout<group_kernel>();      // early-exit launch: blend in
+    return launch_group_redo(g, limbs, out_poses, capacity_rows, out_offset, out_count, out_total, s, launches);
+}
+
+int launch_group_redo(const GroupLaunch &g, const float *limbs, float *out_poses, int capacity_rows,
+                      int32_t *out_offset, int32_t *out_count, int32_t *out_total, cudaStream_t s,
+                      int64_t *launches) {
+    if (g.n == 0) return OG_OK;
+    GroupLaunch cta = g;
+    cta.lazy_flag = nullptr;
+    const int32_t *redo = nullptr;
+    if (g.warp_rows > 0) {
+        redo = g.redo;
+        // Behind the warp kernel the CTA kernel only redoes images whose table outgrew the warp
+        // kernel's rows, and nearly every CTA of this launch exits at once: it gets NO shared-memory
+        // table (the image goes straight to its global slab), so that a launch of early-exit CTAs
+        // does not ask every SM for 200 KB of shared memory while the next call's streaming
+        // kernels are resident.
+        cta.smem_rows = 0;
+        prefer_chain_carveout<group_kernel>();      // early-exit launch: blend in
+    }
     group_kernel<<<g.n, kGroupThreads, group_smem_bytes(cta), s>>>(
         to_args(cta), limbs, g.prep, out_poses, capacity_rows, out_offset, out_count, out_total, redo);
     OG_CUDA_TRY(cudaGetLastError());

@@ -8,12 +8,17 @@
 //   prep[K + 1]   kept row indices in order, their count at [K]        (global-slab grouping kernel)
 //   rec[3 * K]    the kept rows, compacted, 48 bytes each              (warp grouping kernel):
 //                 {id1, id2 (int bits), limb score, -}, {x1, y1, v1, scale1}, {x2, y2, v2, scale2}
-//   cnt           the count again, dense per (image, limb)
+//   cnt           the count again, dense per (image, limb); bit 16 (kPrepDupFrom) is set when two
+//                 kept rows start at the same from-joint id (never on the decode path, where K2
+//                 makes one row per from-candidate; caller-supplied tables may)
 #pragma once
 
 #include "og_common.cuh"
 
 namespace og {
+
+constexpr int kPrepDupFrom = 1 << 16;
+constexpr int kPrepCountMask = 0xffff;
 
 // KMAX = the CTA size (32 / 64 / 128 >= K): the scratch is sized by it, because a CTA that asks
 // for more than a few KB of shared memory cannot join an SM whose carve-out the streaming kernels
@@ -73,17 +78,23 @@ __device__ __forceinline__ void prepare_limb_rows(const float (&r)[OG_LIMB_COLS]
         sh.keep[tid] = keep ? 1 : 0;
     }
     const int kk = __syncthreads_count(keep);
+    bool dup = false;
     if (keep) {
         int pos = 0;
-        for (int r2 = 0; r2 < tid; ++r2) pos += sh.keep[r2];
+        const float id1 = sh.rec[tid * 3].x;            // the int bits of the from-joint id
+        for (int r2 = 0; r2 < tid; ++r2) {
+            pos += sh.keep[r2];
+            dup = dup || (sh.keep[r2] && __float_as_int(sh.rec[r2 * 3].x) == __float_as_int(id1));
+        }
         prep_out[pos] = sh.sorted[tid];
         rec_out[pos * 3 + 0] = sh.rec[tid * 3 + 0];
         rec_out[pos * 3 + 1] = sh.rec[tid * 3 + 1];
         rec_out[pos * 3 + 2] = sh.rec[tid * 3 + 2];
     }
+    const int any_dup = __syncthreads_or(dup);
     if (tid == 0) {
         prep_out[K] = kk;
-        *cnt_out = kk;
+        *cnt_out = kk | (any_dup ? kPrepDupFrom : 0);
     }
 }
 

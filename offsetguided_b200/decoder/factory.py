@@ -139,9 +139,9 @@ class PostProcess(torch.nn.Module):
         # inside the library.  A plan keeps no reference to the tensors it was made from.
         if hmps.is_cuda:
             key = (hmps.data_ptr(), offs.data_ptr(), hmps.shape, offs.shape, hmps.stride(), offs.stride(),
-                   hmps.dtype, offs.dtype, flip_test, torch.cuda.current_stream(hmps.device).cuda_stream)
+                   hmps.dtype, offs.dtype, flip_test, torch._C._cuda_getCurrentRawStream(hmps.device.index))
             plan = self._plans.get(key)
-            if plan is not None and torch.cuda.current_device() == plan.eng.device.index:
+            if plan is not None and torch._C._cuda_getDevice() == plan.eng.device.index:
                 plan.launch((hmps, offs))
                 self._submitted.append(plan.eng)
                 return len(self._submitted)

@@ -92,8 +92,8 @@ class DecoderEngine(object):
         self._result_ref = ctypes.byref(self._result)
         # prepared ctypes argument tuples of device-path decodes, keyed by buffers / shapes / flags
         self._arg_cache = collections.OrderedDict()
-        self._meta_views = {}
-        self._pose_views = {}
+        self._views = {}
+        self._fetch_fn = self.lib.og_fetch_result
         self.last_result_rows = None
 
     def close(self):
@@ -186,11 +186,11 @@ class DecoderEngine(object):
     def _fetch(self):
         """Result of the OLDEST decode call in flight: list of (M_i, C, 6) arrays, one per image
         of that call (the library reports the image count of the slot it hands out)."""
-        if torch.cuda.current_device() == self.device.index:
-            st = self.lib.og_fetch_result(self._h, self._result_ref)
+        if torch._C._cuda_getDevice() == self.device.index:
+            st = self._fetch_fn(self._h, self._result_ref)
         else:
             with torch.cuda.device(self.device):
-                st = self.lib.og_fetch_result(self._h, self._result_ref)
+                st = self._fetch_fn(self._h, self._result_ref)
         if st != 0:
             _lib.check(st)
         if self._inflight:
@@ -216,21 +216,22 @@ class DecoderEngine(object):
             return []
         if total == 0:
             return [np.zeros((0, c, _lib.OG_POSE_COLS), dtype=np.float32) for _ in range(n)]
-        # numpy views over the result slot's pinned buffers are made once per buffer (they are
-        # re-created only when the library has re-allocated one)
-        addr = ctypes.cast(r.offsets, ctypes.c_void_p).value
-        meta = self._meta_views.get(addr)
-        if meta is None or meta.size < 2 * n:
-            meta = self._meta_views[addr] = np.frombuffer((ctypes.c_int32 * (2 * n)).from_address(addr), dtype=np.int32)
+        # numpy views over the result slot's pinned buffers are made once per (buffer, batch size):
+        # buffer_id changes when the library has re-allocated the buffer, and the pose rows start
+        # behind a header whose size depends on n
         per_row = c * _lib.OG_POSE_COLS
-        paddr = ctypes.cast(r.poses, ctypes.c_void_p).value
-        pool = self._pose_views.get(paddr)
-        if pool is None or pool.size < total * per_row:
+        view_key = (r.buffer_id, n)
+        views = self._views.get(view_key)
+        if views is None or views[1].size < total * per_row:
+            addr = ctypes.cast(r.offsets, ctypes.c_void_p).value
+            paddr = ctypes.cast(r.poses, ctypes.c_void_p).value
             grow = max(total, 64 * n) * per_row
-            pool = self._pose_views[paddr] = np.frombuffer((ctypes.c_float * grow).from_address(paddr), dtype=np.float32)
-            if len(self._pose_views) > 4 * _lib.OG_MAX_IN_FLIGHT:          # buffers the library has replaced
-                self._pose_views = {paddr: pool}
-                self._meta_views = {addr: meta}
+            views = (np.frombuffer((ctypes.c_int32 * (2 * n)).from_address(addr), dtype=np.int32),
+                     np.frombuffer((ctypes.c_float * grow).from_address(paddr), dtype=np.float32))
+            if len(self._views) > 4 * _lib.OG_MAX_IN_FLIGHT:          # buffers the library has replaced
+                self._views.clear()
+            self._views[view_key] = views
+        meta, pool = views
         offs = meta[:n].tolist()
         cnts = meta[n:2 * n].tolist()
         # one copy out of the handle's pinned buffer; the per-image arrays are views of it
@@ -408,6 +409,11 @@ class DecoderEngine(object):
     def fused_redo_count(self):
         return int(self.lib.og_fused_redo_count(self._h))
 
+    @property
+    def k3_redo_count(self):
+        """Fetches that ran the CTA grouping kernel for images whose person table outgrew the warp kernel's."""
+        return int(self.lib.og_k3_redo_count(self._h))
+
     def set_graph(self, on=True):
         """Device path: replay a captured CUDA graph per result slot (default) or launch kernel by kernel."""
         _lib.check(self.lib.og_set_graph(self._h, 1 if on else 0))
@@ -472,19 +478,25 @@ class FeaturePlan(object):
         self.in_place = hmp is src[0] and off is src[1]      # the library reads the caller's own buffers
         self.keep = (hmp, off)
         self.flip_tables = flip_tables
-        self._fn = eng.lib.og_decode_features_dev_ex
         self.stream_ptr = torch.cuda.current_stream(eng.device).cuda_stream
-        self._args = (eng._h, _ptr(hmp), _ptr(off), _DTYPES[hmp.dtype], hmp_is, off_is, self.n, h, w,
-                      int(hmp_stride), int(off_stride), mode, 1 if flip else 0) + tuple(args) + \
-                     (ctypes.c_void_p(self.stream_ptr),)
+        plan_id = ctypes.c_int32(-1)
+        with torch.cuda.device(eng.device):
+            _lib.check(eng.lib.og_plan_features(
+                eng._h, _ptr(hmp), _ptr(off), _DTYPES[hmp.dtype], hmp_is, off_is, self.n, h, w, int(hmp_stride),
+                int(off_stride), mode, 1 if flip else 0, *args, ctypes.byref(plan_id)))
+        self._fn = eng.lib.og_plan_launch
+        self._handle = eng._h
+        self._id = plan_id.value
+        self._stream = ctypes.c_void_p(self.stream_ptr)
+        self._append = eng._inflight.append
 
     def launch(self, keep=None):
         """Launch one decode of the planned buffers on the stream that was current when the plan
         was made (the CUDA device of the engine must be current)."""
-        st = self._fn(*self._args)
+        st = self._fn(self._handle, self._id, self._stream)
         if st != 0:
             _lib.check(st)
-        self.eng._inflight.append(self.keep if keep is None else keep)
+        self._append(self.keep if keep is None else keep)
 
     def release(self):
         """Drop the references to the planned tensors (a cached plan is launched with the caller's

@@ -2,7 +2,7 @@
 host microseconds per launch / fetch call, for batch shards of 8 .. 64 images, 1 .. 8 calls in
 flight, CUDA-graph replay on / off, through decode_features and through a prepared plan.
 
-    python profiles/tools/pipeline_probe.py [long_edge]
+    python profiles/tools/pipeline_probe.py [long_edge] [n,n,...] [depth,depth,...]
 """
 import json
 import os
@@ -51,7 +51,9 @@ def main():
     tables = (cfg.heatmap_hflip(cfg.COCO_KEYPOINTS),) + tuple(cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel))
     hmp, omp = bench.lowres_inputs(5000, 64, edge, True)
     eng = DecoderEngine(17, skel, topk=32, thre_hmp=0.04, dist_max=40, use_scale=True, person_thre=0.04)
-    for n in (8, 16, 32, 64):
+    ns = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [8, 16, 32, 64]
+    depths = [int(v) for v in sys.argv[3].split(',')] if len(sys.argv) > 3 else [1, 2, 4, 8, 16]
+    for n in ns:
         sel = list(range(n)) + list(range(64, 64 + n))
         th, to = torch.from_numpy(hmp[sel]).cuda(), torch.from_numpy(omp[sel]).cuda()
         # stage times, kernel by kernel
@@ -62,7 +64,7 @@ def main():
         eng.enable_stage_timing(False)
         for graph in (True, False):
             eng.set_graph(graph)
-            for depth in (1, 2, 4, 8):
+            for depth in depths:
                 steps = 400
                 r = run(eng, lambda: eng.decode_features(th, to, 4, 4, 'bicubic', tables, fetch=False),
                         lambda: eng.fetch(), n, depth, steps)
