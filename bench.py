@@ -354,7 +354,7 @@ def pin_to_own_core(local, local_world):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from offsetguided_b200 import sharding
+    from offsetguided_b200 import _lib, sharding
     from offsetguided_b200.engine import DecoderEngine
     from oracle import scenes
 
@@ -460,7 +460,7 @@ def run_b200(args):
     eng.enable_stage_timing(False)
 
     # ---- value: the product path, pipelined, one global batch per step
-    depth = 8
+    depth = _lib.OG_MAX_IN_FLIGHT
     persons = pipelined(post, feats_ring, flip, args.warmup + 2 * depth, depth)      # warm-up: every slot has its graphs
     n_persons = sum(len(p) for p in persons)
     sampler = ClockSampler(dev_index).start()

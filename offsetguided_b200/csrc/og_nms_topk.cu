@@ -20,6 +20,8 @@
 // every input — there is no approximate or host-side fallback.
 #include "og_common.cuh"
 
+#include <string.h>
+
 namespace og {
 
 namespace {
@@ -50,21 +52,10 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float *p) {
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-// NMS value of one pixel as the reference defines it: heat * (maxpool == heat).
-template <bool kThrePositive>
-__device__ __forceinline__ bool survives(float v, float m, float thre, float &nv) {
-    if (kThrePositive) {            // thre > 0: non-peaks (value 0) can never pass
-        nv = v;
-        return v >= fmaxf(m, thre);
-    }
-    nv = (v == m) ? v : 0.0f;
-    return nv >= thre;
-}
-
 #ifndef OG_K1_MIN_CTAS
 #define OG_K1_MIN_CTAS 3
 #endif
-template <bool kThrePositive, bool kVec4>
+template <bool kVec4>
 __global__ void __launch_bounds__(kK1Threads, OG_K1_MIN_CTAS)
 nms_candidates_kernel(const float *__restrict__ heat, int planes, int H, int W, float thre,
                       uint32_t *__restrict__ cand_count, uint64_t *__restrict__ cand_keys) {
@@ -84,11 +75,6 @@ nms_candidates_kernel(const float *__restrict__ heat, int planes, int H, int W, 
     const int r_begin = chunk * kRowsPerWarp;
     const int r_end = min(H, r_begin + kRowsPerWarp);
 
-    // lane 0 / lane 31 own the column just outside the warp's strip (slow path only)
-    int hx = -1;
-    if (lane == 0 && x0 > 0) hx = x0 - 1;
-    if (lane == 31 && x0 + 4 < W) hx = x0 + 4;
-
     auto load_row = [&](int r) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);      // zero padding outside the image
         if (r >= 0 && r < H) {
@@ -104,40 +90,6 @@ nms_candidates_kernel(const float *__restrict__ heat, int planes, int H, int W, 
         }
         return v;
     };
-    auto halo = [&](int r) {
-        return (hx >= 0 && r >= 0 && r < H) ? __ldg(p + (size_t)r * W + hx) : 0.0f;
-    };
-    auto hmax_row = [&](const float4 &v, float e) {
-        float left = __shfl_up_sync(0xffffffffu, v.w, 1);
-        float right = __shfl_down_sync(0xffffffffu, v.x, 1);
-        if (lane == 0) left = e;
-        if (lane == 31) right = e;
-        return make_float4(max3(left, v.x, v.y), max3(v.x, v.y, v.z),
-                           max3(v.y, v.z, v.w), max3(v.z, v.w, right));
-    };
-    auto emit = [&](float v, float m, int x, int r) {
-        float nv;
-        if (x < W && survives<kThrePositive>(v, m, thre, nv)) {
-            nv += 0.0f;     // -0 -> +0 so that equal values have equal keys
-            const uint32_t pos = atomicAdd(&cand_count[plane], 1u);
-            if (pos < (uint32_t)kCandCap)
-                cand_keys[(size_t)plane * kCandCap + pos] = make_key(nv, (uint32_t)(r * W + x));
-        }
-    };
-    // Full 3x3 test of one row; executed by the whole warp, only for rows in which some
-    // lane holds a value >= thre (a few percent of the rows of a real heat map).  The three
-    // rows are re-read (L2 hits: this warp or its neighbours streamed them just before).
-    auto check_row = [&](int row) {
-        const float4 mid = load_row(row);
-        const float4 h0 = hmax_row(load_row(row - 1), halo(row - 1));
-        const float4 h1 = hmax_row(mid, halo(row));
-        const float4 h2 = hmax_row(load_row(row + 1), halo(row + 1));
-        emit(mid.x, max3(h0.x, h1.x, h2.x), x0 + 0, row);
-        emit(mid.y, max3(h0.y, h1.y, h2.y), x0 + 1, row);
-        emit(mid.z, max3(h0.z, h1.z, h2.z), x0 + 2, row);
-        emit(mid.w, max3(h0.w, h1.w, h2.w), x0 + 3, row);
-    };
-
     // streaming pass: rows r_begin .. r_end-1 lie inside the image, no bounds tests needed
     auto stream_row = [&](const float *row) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -152,13 +104,6 @@ nms_candidates_kernel(const float *__restrict__ heat, int planes, int H, int W, 
         return v;
     };
     const float *row = p + (size_t)r_begin * W + x0;
-
-    if (!kThrePositive) {
-        // thre <= 0: every pixel qualifies (non-peaks with their NMS value 0), so every row runs the
-        // full test; this variant only serves the exact joint_dets / topK_channel API
-        for (int r = r_begin; r < r_end; ++r) check_row(r);
-        return;
-    }
 
     // thre > 0.  The whole 8-row chunk is held in registers (8 independent 128-bit loads in flight per
     // lane).  A row is looked at again only if some lane holds a value >= thre, and then the test
@@ -326,9 +271,42 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
         const int n = (int)n_cand;
         for (int i = tid; i < n; i += blockDim.x) s_keys[i] = cand_keys[(size_t)plane * kCandCap + i];
         __syncthreads();
-        write_ranked(s_keys, n, K, o_score, o_index);
-        if (tid == 0 && out_count) out_count[plane] = min(n, K);
-        return;
+        if (!(thre <= 0.0f) || n >= K || heat == nullptr) {
+            write_ranked(s_keys, n, K, o_score, o_index);
+            if (tid == 0 && out_count) out_count[plane] = min(n, K);
+            return;
+        }
+        // thre <= 0 (the exact joint_dets API): pass 1 listed the POSITIVE peaks only, fewer than K.
+        // Next in (value desc, index asc) order come the pixels whose NMS value is 0 — every
+        // non-peak — lowest index first, so the K - n first of them complete the list; the scan
+        // below stops after a few hundred pixels.  A plane that does not hold enough of them
+        // (then negative values follow) goes to the radix selection.
+        const uint32_t need = (uint32_t)(K - n);
+        uint32_t taken = 0;
+        const int lane = tid & 31, wid = tid >> 5;
+        const float *__restrict__ pz = heat + (size_t)plane * H * W;
+        for (int base = 0; base < H * W && taken < need; base += blockDim.x) {
+            const int i = base + tid;
+            const bool flag = i < H * W && nms_value(pz, H, W, i, apply_nms != 0) == 0.0f;
+            const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
+            if (lane == 0) s_part[wid] = __popc(ballot);
+            __syncthreads();
+            uint32_t before = 0, chunk_total = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+                const uint32_t c = s_part[w];
+                if (w < wid) before += c;
+                chunk_total += c;
+            }
+            const uint32_t pos = taken + before + __popc(ballot & ((1u << lane) - 1u));
+            if (flag && pos < need) s_keys[n + pos] = make_key(0.0f, (uint32_t)i);
+            taken += chunk_total;
+            __syncthreads();
+        }
+        if (taken >= need) {
+            write_ranked(s_keys, K, K, o_score, o_index);
+            if (tid == 0 && out_count) out_count[plane] = K;
+            return;
+        }
     }
 
     if (heat == nullptr) {      // fused path: no materialised plane to re-scan; the host re-runs
@@ -353,12 +331,20 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
         const uint32_t mask = (1u << widths[pass]) - 1u;
         for (int b = tid; b < kRadixBins; b += blockDim.x) s_hist[b] = 0;
         __syncthreads();
-        for (int i = tid; i < HW; i += blockDim.x) {
-            const float nv = nms_value(p, H, W, i, nms);
-            if (nv >= thre) {
-                const uint32_t key = ~ordered_bits(nv);
-                if ((key & prefix_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & mask], 1u);
+        // heat maps are mostly one value (the zero background): the lanes of a warp that hit the
+        // same bin add up first, one shared-memory atomic per distinct bin and warp
+        for (int base = 0; base < HW; base += blockDim.x) {
+            const int i = base + tid;
+            uint32_t bin = 0xffffffffu;
+            if (i < HW) {
+                const float nv = nms_value(p, H, W, i, nms);
+                if (nv >= thre) {
+                    const uint32_t key = ~ordered_bits(nv);
+                    if ((key & prefix_mask) == prefix) bin = (key >> shift) & mask;
+                }
             }
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (bin != 0xffffffffu && (tid & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
         }
         __syncthreads();
         // 256 partial sums of 8 bins each, then thread 0 walks them
@@ -498,6 +484,12 @@ int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int
     return OG_OK;
 }
 
+static inline float __int_as_float_host(int bits) {
+    float f;
+    memcpy(&f, &bits, sizeof(f));
+    return f;
+}
+
 // pass 1 alone: clear the counters, stream the maps, append the survivors
 int launch_nms_candidates(const float *heat, int planes, int h, int w, float thre,
                           uint32_t *cand_count, uint64_t *cand_keys, cudaStream_t s,
@@ -510,13 +502,13 @@ int launch_nms_candidates(const float *heat, int planes, int h, int w, float thr
     const int threads = kK1Threads;
     const long long blocks = (warps + (threads / 32) - 1) / (threads / 32);
     const bool vec4 = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
-    const bool pos = thre > 0.0f;
-    auto kern = pos ? (vec4 ? nms_candidates_kernel<true, true> : nms_candidates_kernel<true, false>)
-                    : (vec4 ? nms_candidates_kernel<false, true> : nms_candidates_kernel<false, false>);
-    prefer_chain_carveout<nms_candidates_kernel<true, true>>();
-    prefer_chain_carveout<nms_candidates_kernel<true, false>>();
-    prefer_chain_carveout<nms_candidates_kernel<false, true>>();
-    prefer_chain_carveout<nms_candidates_kernel<false, false>>();
+    // thre <= 0 (exact joint_dets API): every pixel qualifies, but all that can rank above the
+    // zeros of the non-peaks are the positive peaks — pass 1 lists those (threshold = the smallest
+    // positive float) and the selection completes the list from the zeros (select_topk_kernel)
+    if (!(thre > 0.0f)) thre = __int_as_float_host(1);
+    auto kern = vec4 ? nms_candidates_kernel<true> : nms_candidates_kernel<false>;
+    prefer_chain_carveout<nms_candidates_kernel<true>>();
+    prefer_chain_carveout<nms_candidates_kernel<false>>();
     kern<<<(unsigned)blocks, threads, 0, s>>>(heat, planes, h, w, thre, cand_count, cand_keys);
     OG_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;

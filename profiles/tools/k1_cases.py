@@ -1,6 +1,6 @@
 """K1 (og_nms_topk_f32: nms_candidates + select) alone on inputs that do not flatter it:
-BASELINE config 2 / 3 / 4 maps, a synthetic with 30 % hot warp-rows, and thre <= 0 (every pixel
-qualifies: the full-stencil variant).  GB/s = N*C*H*W*4 / time, against MEASURED_PEAKS hbm_gbs."""
+BASELINE config 2 / 3 / 4 maps, synthetics with 30 % hot warp-rows, and thre <= 0 (every pixel
+qualifies) on a dense noise floor and on a zero background.  GB/s = N*C*H*W*4 / time, against MEASURED_PEAKS hbm_gbs."""
 import json
 import os
 import sys
@@ -73,9 +73,16 @@ def main():
     heat_hot = torch.from_numpy(hot).cuda().repeat(8, 1, 1, 1).contiguous()
     report('960 isolated peaks per plane (30 % hot warp-rows): 64 x 17 x 640^2', e17, heat_hot, 0.04)
     del heat_hot
-    report('thre = 0 (full stencil): 64 x 17 x 640^2', e17, heat, 0.0, reps=5)
-    report('thre = -1 (exact joint_dets): 16 x 17 x 640^2', e17, heat[:16].contiguous(), -1.0, reps=3)
-    del heat
+    # thre <= 0 (the exact joint_dets API).  The rendered maps carry noise on every pixel (45 k positive
+    # local maxima per plane): every plane overflows its candidate list and is selected by the
+    # one-CTA-per-plane radix selection.  A map whose background is exactly zero (what hmp_NMS itself
+    # returns) is listed by the streaming pass and completed from the zeros.
+    report('thre = 0, dense noise floor (radix selection per plane): 64 x 17 x 640^2', e17, heat, 0.0, reps=5)
+    report('thre = -1 (exact joint_dets), dense noise floor: 16 x 17 x 640^2', e17, heat[:16].contiguous(), -1.0, reps=3)
+    sparse = torch.where(heat >= 0.02, heat, torch.zeros_like(heat))
+    report('thre = 0, zero background: 64 x 17 x 640^2', e17, sparse, 0.0)
+    report('thre = -1 (exact joint_dets), zero background: 64 x 17 x 640^2', e17, sparse, -1.0)
+    del heat, sparse
     h, _ = scenes.synth_hires_batch(2000, 8, 20, 640, 640, crowd, n_channels=14)
     heat = torch.from_numpy(h).cuda().repeat(4, 1, 1, 1).contiguous()
     report('cfg3: 32 x 14 x 640^2, 20 persons, K = 64', e14, heat, 0.04)

@@ -54,6 +54,35 @@ def test_k1_exact_joint_dets_radix_path(cuda_device):
     assert np.array_equal(s.cpu().numpy(), ref_s)
 
 
+@pytest.mark.parametrize('thre', [0.0, -0.5, float('-inf')])
+def test_k1_non_positive_threshold_lists_peaks_then_zeros(cuda_device, thre):
+    """thre <= 0: pass 1 lists the positive peaks, the selection completes the top-K with the
+    zeros of the non-peaks (lowest index first); planes without enough of them — constant
+    negative planes, whose interior is all peaks — take the radix selection, which then also
+    ranks the negative peaks above the threshold."""
+    rng = np.random.RandomState(11)
+    heat = np.zeros((2, 4, 48, 64), np.float32)
+    for c in range(4):                                   # a few positive and negative isolated peaks
+        for _ in range(5):
+            y, x = rng.randint(2, 46), rng.randint(2, 62)
+            heat[0, c, y, x] = rng.uniform(0.1, 1.0)
+            heat[1, c, y, x] = -rng.uniform(0.1, 1.0)
+    heat[0, 3] = rng.uniform(-1, 1, size=(48, 64))       # dense mixed-sign noise
+    heat[1, 3] = -0.25                                   # constant negative: zeros on the border ring only
+    small = np.full((1, 2, 3, 4), -0.25, np.float32)     # 10 border zeros, 2 interior peaks, K = 12
+    small[0, 1, 1, 1] = -0.75
+    for maps, k in ((heat, 40), (small, 12)):
+        eng = DecoderEngine(maps.shape[1], [(0, 1)], topk=k)
+        s, i, cnt = eng.nms_topk(torch.from_numpy(maps).cuda(), thre=thre)
+        nms = ro.hmp_nms(maps)
+        nms[nms < np.float32(thre)] = -np.inf
+        ref_s, ref_i, _, _ = ro.topk_channel(nms, k)
+        live = ref_s >= np.float32(thre)
+        assert np.array_equal(cnt.cpu().numpy(), live.sum(-1))
+        assert np.array_equal(i.cpu().numpy()[live], ref_i[live])
+        assert np.array_equal(s.cpu().numpy()[live], ref_s[live])
+
+
 def test_k1_overflow_planes_fall_back_to_radix(cuda_device):
     """Noise maps: > 2048 peaks per plane above the threshold."""
     rng = np.random.RandomState(1)
@@ -222,6 +251,49 @@ def test_k3_large_batch_uses_dense_tables(cuda_device):
     assert len(big) == 400
     for got, i in zip(big, order):
         assert got.shape == ref[i].shape and np.array_equal(got, ref[i])
+
+
+def _random_limb_tables(rng, count, skel, n_kp):
+    """Limb tables with tiny keypoint pools: persons share ids, kept rows start at the same joint,
+    slots are overwritten — everything the merge step of group.py:140-155 can meet."""
+    tables = []
+    for _ in range(count):
+        k = int(rng.choice([4, 8, 16, 32]))
+        pool = int(rng.choice([2, 3, 4, 5, 6, 8, 12, 20]))
+        limbs = np.zeros((len(skel), 32, 13), np.float32)
+        xy = rng.randint(1, 600, size=(n_kp, pool, 2)).astype(np.float32)
+        ids = rng.randint(0, 640 * 640, size=(n_kp, pool))
+        for l, (jf, jt) in enumerate(skel):
+            sc = (rng.permutation(k) + rng.uniform(0.1, 0.9, size=k)).astype(np.float32) / k
+            for r in range(k):
+                a, b = rng.randint(pool), rng.randint(pool)
+                limbs[l, r] = (xy[jf, a, 0], xy[jf, a, 1], 0.5, xy[jt, b, 0], xy[jt, b, 1], 0.6,
+                               ids[jf, a] + jf * 409600, ids[jt, b] + jt * 409600,
+                               rng.uniform(0, 55), 10, sc[r], 4, 4)
+            limbs[l, k:, 8] = 1000.0                       # rows beyond k fail the distance gate
+        tables.append(limbs)
+    return np.stack(tables)
+
+
+def test_k3_warp_kernel_skips_no_merge(cuda_device, monkeypatch):
+    """The one-warp kernel runs the all-pairs merge test only in steps where a pair's number of
+    shared ids can have changed; the CTA kernel runs it in every step like the reference.  2000
+    random tables with tiny keypoint pools (shared ids, duplicate from-joints, overwritten slots,
+    cancellation persons) must come out identically from both, and a sample equals the oracle."""
+    rng = np.random.RandomState(2025)
+    skel = cfg.COCO_PERSON_SKELETON
+    tables = _random_limb_tables(rng, 2000, skel, 17)
+    warp = decoder.GreedyGroup(0.06, sort_dim=2, dist_max=40, use_scale=True).group_batch(tables)
+    monkeypatch.setenv('OG_K3_WARP_ROWS', '0')
+    cta = decoder.GreedyGroup(0.06, sort_dim=2, dist_max=40, use_scale=True).group_batch(tables)
+    merged = 0
+    for i, (a, b) in enumerate(zip(warp, cta)):
+        assert a.shape == b.shape and np.array_equal(a, b), f'table {i}'
+    for i in range(0, 2000, 40):
+        ref = ro.group_skeletons(tables[i], skel, 17, 0.06, 2, 40, True)
+        assert warp[i].shape == ref.shape and np.array_equal(warp[i], ref), f'table {i}'
+        merged += 1
+    assert merged == 50
 
 
 def test_k3_empty_and_degenerate(cuda_device):
