@@ -226,6 +226,22 @@ int og_decode_features_dev_ex(og_handle *h, const void *hmp_dev, const void *off
                               const int32_t *kp_flip, const int32_t *limb_flip,
                               const int32_t *limb_reserve, int n_reserve, void *stream);
 
+/* og_decode_features_dev with the optional heads and flags of PostProcess.generate_poses
+ * (decoder/factory.py:52-96, collect.py:111-138, 158-165, 213-218), still on the fused path: the
+ * keypoint-scale maps `scale_dev` [n or 2n, C, hgt, w] (--include-scale; resized like the heat maps
+ * in the reference) and the jitter-offset maps `jitter_dev` [n or 2n, 2, hgt, w]
+ * (--include-jitter-offset; bilinear) are interpolated by K2 at the candidate pixels only, with
+ * their flip-test averages (factory.py:109-113, 141-144) fused in; `cat_flip_offs` scores the limbs
+ * on the 4-D vectors [original, mirrored copy] (factory.py:115-127) instead of their average.
+ * Either map pointer may be NULL.  Dense float32 maps; same results, bit for bit, as
+ * materialising every map and calling og_decode_maps_ex. */
+int og_decode_features_heads_dev(og_handle *h, const float *hmp_dev, const float *off_dev,
+                                 const float *scale_dev, const float *jitter_dev, int n, int hgt, int w,
+                                 int hmp_stride, int off_stride, int resize_mode, int flip_test,
+                                 int cat_flip_offs, int use_jitter, const int32_t *kp_flip,
+                                 const int32_t *limb_flip, const int32_t *limb_reserve, int n_reserve,
+                                 void *stream);
+
 /* A prepared og_decode_features_dev_ex: a network writes its outputs to the same buffers batch
  * after batch, so a caller validates and records the arguments once (og_plan_features, which
  * also installs the flip tables) and then launches each batch with three arguments.  A plan stays
@@ -290,10 +306,11 @@ int64_t og_launch_count(const og_handle *h);
 /* og_decode_features_* use a fused path by default (strides 2/4/8, thre_hmp > 0): flip
  * fusion + resize + NMS in one kernel over the network-resolution maps, offsets sampled at
  * the candidates; results are bit-identical to the materialising path.  If a heat-map plane
- * yields more than 2048 candidates (noise-like input) og_fetch_poses re-runs the batch on the
- * GPU through the materialising path; the input buffers of og_decode_features_dev must
- * therefore stay valid until og_fetch_poses returns.  og_set_fused(h, 0) disables the fused
- * path; og_fused_redo_count reports how many batches were re-run. */
+ * yields more than 2048 candidates (noise-like input), og_fetch_result materialises that plane
+ * alone at full resolution, selects its top-K exactly and runs the limb scoring and grouping of
+ * the batch again on the completed detections; the input buffers of og_decode_features_dev must
+ * therefore stay valid until the result has been fetched.  og_set_fused(h, 0) disables the fused
+ * path; og_fused_redo_count reports how many batches needed such a redo. */
 int og_set_fused(og_handle *h, int enable);
 
 /* Device path of og_decode_features_dev[_ex]: replay a captured CUDA graph per result slot

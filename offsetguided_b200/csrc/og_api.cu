@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <new>
+#include <vector>
 
 #include "og_common.cuh"
 
@@ -84,11 +85,20 @@ constexpr int kGraphsPerSlot = 4;  // captured device-path chains a result slot 
 // start, after prep, K1 pass 1 | select start, select = K2 start, K2, K3, end (see mark())
 constexpr int kStageEvents = 8;
 
-struct FeatureArgs {               // arguments of a features decode, kept for the exact redo
-    const float *hmp, *off;
-    int n, hgt, w, hmp_stride, off_stride, resize_mode, flip;
-    const float *off_host;         // offsets left in pinned host memory (zero-copy), else nullptr
-    MapView hmp_view, off_view;    // og_decode_features_dev_ex: bf16 / strided maps (ptr != nullptr)
+struct K1Fused {
+    MapView hmp;            // network-resolution heat maps (n or 2n images)
+    int h, w, scale;
+    bool cubic, flip;
+};
+
+// What a fused decode call ran on, kept until its result is fetched: og_fetch_result materialises
+// and selects the planes whose candidate lists overflowed from `k1`, then runs K2 / K3 again.
+struct CallCtx {
+    K1Fused k1;
+    OffsetSource src;
+    FlipTablesDev ft;
+    int H, W;               // full-resolution size
+    LimbExtras extras;      // optional heads sampled by K2 (vector_nd == 0: none)
 };
 
 // What identifies a captured decode chain: replaying the graph is only valid for the same
@@ -99,8 +109,11 @@ struct GraphKey {
     size_t hmp_image_stride, off_image_stride;
     int n, hgt, w, stride, mode, flip, coco;
     uint64_t tables_version, buffers_version;
+    const void *scale, *jitter;             // optional heads (og_decode_features_heads_dev)
+    int vector_nd, use_jitter;
     bool operator==(const GraphKey &o) const {
         return hmp == o.hmp && off == o.off && dtype == o.dtype && coco == o.coco && hmp_image_stride == o.hmp_image_stride &&
+               scale == o.scale && jitter == o.jitter && vector_nd == o.vector_nd && use_jitter == o.use_jitter &&
                off_image_stride == o.off_image_stride && n == o.n && hgt == o.hgt && w == o.w &&
                stride == o.stride && mode == o.mode && flip == o.flip &&
                tables_version == o.tables_version && buffers_version == o.buffers_version;
@@ -170,7 +183,9 @@ struct ResultSlot {
     bool scratch_dirty = true;          // counters / flags are not known to be zero (fresh slot or failed call)
     bool has_limbs = false;             // limbs / group scratch hold this call's rows (K3 can be re-run)
     int k3_images = 0, k3_first = 0;    // image range of the last K3 launch (single-range calls)
-    FeatureArgs args = {};
+    CallCtx ctx = {};
+    DevBuf<float> redo_lr, redo_hr;      // per-plane redo: fused network-resolution planes, their full-resolution maps
+    DevBuf<int32_t> redo_list;
 };
 
 struct og_handle {
@@ -399,12 +414,6 @@ int run_k3(og_handle *h, GroupScratch &gs, int i0, const float *limbs, bool prep
                         &h->launches);
 }
 
-struct K1Fused {
-    MapView hmp;            // network-resolution heat maps (n or 2n images)
-    int h, w, scale;
-    bool cubic, flip;
-};
-
 inline MapView dense_f32(const float *p, size_t per_image) { return MapView{p, OG_DTYPE_F32, per_image}; }
 inline size_t elem_size(int dtype) { return dtype == OG_DTYPE_F32 ? 4 : 2; }
 inline MapView shift_images(MapView v, size_t images) {
@@ -498,6 +507,57 @@ int begin_call(og_handle *h, ResultSlot *slot, const K1Fused *fused, int n, int 
     return OG_OK;
 }
 
+// K2 (+ the row preparation of K3) and K3 of images [i0, i0 + cn) on the slot's stream; the dets of
+// those images are in the slot's det arrays.
+int run_limbs_and_groups(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, const float *offs,
+                         const OffsetSource *offs_lowres, const FlipTablesDev *ft, const float *scales,
+                         int hgt, int w, const LimbExtras *extras, bool timed) {
+    const og_config &c = h->cfg;
+    const int n = slot->n;
+    int32_t *meta = reinterpret_cast<int32_t *>(slot->out_dev);
+    float *poses = reinterpret_cast<float *>(slot->out_dev + slot->meta_bytes);
+    const size_t HW = (size_t)hgt * w;
+    const size_t det0 = (size_t)i0 * c.n_keypoints * c.topk;
+    const size_t plane0 = (size_t)i0 * c.n_keypoints;
+    const float *det_score = slot->det_score.ptr + det0;
+    const int32_t *det_index = slot->det_index.ptr + det0;
+    cudaStream_t a = slot->work;
+    if (timed) OG_TRY(mark(h, slot, 4, a));
+    const int nd = extras ? extras->vector_nd : 2;
+    OffsetSource src = {};
+    if (offs_lowres) {
+        src = *offs_lowres;
+        src.maps = shift_images(src.maps, i0);
+    }
+    LimbExtras ex = {nullptr, 2, 0};
+    if (extras) {
+        ex = *extras;
+        if (ex.jomps) ex.jomps += (size_t)i0 * 2 * HW;
+    }
+    float *limbs = slot->limbs.ptr + (size_t)i0 * c.n_limbs * c.topk * OG_LIMB_COLS;
+    GroupScratch &gs = slot->group;
+    PrepOut po = {gs.prep.ptr + (size_t)i0 * c.n_limbs * (c.topk + 1),
+                  gs.rec.ptr + (size_t)i0 * c.n_limbs * c.topk * 3, gs.cnt.ptr + (size_t)i0 * c.n_limbs,
+                  c.dist_max, c.use_scale, chunk == 0 ? slot->total.ptr : nullptr};
+    OG_TRY(launch_limb_score(det_score, det_index, offs ? offs + (size_t)i0 * nd * c.n_limbs * HW : nullptr,
+                             offs_lowres ? &src : nullptr, ft, scales ? scales + plane0 * HW : nullptr,
+                             extras ? &ex : nullptr, cn, c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk,
+                             c.thre_hmp, c.min_len, c.resize_factor, limbs, &po, a));
+    h->launches += 1;
+    if (timed) OG_TRY(mark(h, slot, 5, a));
+    const CocoOut coco = coco_out(h, slot, i0);
+    // A call that is one range leaves the images whose person table outgrows the warp kernel's
+    // (noise-like inputs) to og_fetch_result: the kernel raises meta[2n + 1] and the fetch runs the
+    // CTA kernel for them, instead of a launch of early-exit CTAs behind every call.
+    int32_t *lazy_flag = (i0 == 0 && cn == n) ? meta + 2 * n + 1 : nullptr;
+    OG_TRY(run_k3(h, gs, i0, limbs, true, cn, poses, slot->capacity_rows, meta + i0, meta + n + i0,
+                  slot->total.ptr, a, &coco, lazy_flag));
+    if (timed) OG_TRY(mark(h, slot, 6, a));
+    slot->k3_first = i0;
+    slot->k3_images = cn;
+    return OG_OK;
+}
+
 // Images [i0, i0 + cn) of the call.  K1 (full-resolution stream, or the fused network-resolution
 // kernels) on `k1s`, then K2 -> K3 on the slot's stream `a`; when both are the same stream the
 // whole range is one linear chain (device path; this is what gets captured into a graph) and
@@ -510,7 +570,6 @@ int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, cons
     const og_config &c = h->cfg;
     const int n = slot->n;
     int32_t *meta = reinterpret_cast<int32_t *>(slot->out_dev);
-    float *poses = reinterpret_cast<float *>(slot->out_dev + slot->meta_bytes);
     const size_t HW = (size_t)hgt * w;
     const size_t det0 = (size_t)i0 * c.n_keypoints * c.topk;
     const size_t plane0 = (size_t)i0 * c.n_keypoints;
@@ -558,40 +617,11 @@ int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, cons
         OG_CUDA_TRY(cudaEventRecord(slot->k1_done[chunk], k1s));
         OG_CUDA_TRY(cudaStreamWaitEvent(a, slot->k1_done[chunk], 0));
     }
-    if (timed) OG_TRY(mark(h, slot, 4, a));
-    const int nd = extras ? extras->vector_nd : 2;
-    OffsetSource src = {};
-    if (offs_lowres) {
-        src = *offs_lowres;
-        src.maps = shift_images(src.maps, i0);
+    if (fused && offs_lowres) {
+        slot->ctx = CallCtx{*fused, *offs_lowres, h->ft, hgt, w, LimbExtras{}};
+        if (extras) slot->ctx.extras = *extras;
     }
-    LimbExtras ex = {nullptr, 2, 0};
-    if (extras) {
-        ex = *extras;
-        if (ex.jomps) ex.jomps += (size_t)i0 * 2 * HW;
-    }
-    float *limbs = slot->limbs.ptr + (size_t)i0 * c.n_limbs * c.topk * OG_LIMB_COLS;
-    GroupScratch &gs = slot->group;
-    PrepOut po = {gs.prep.ptr + (size_t)i0 * c.n_limbs * (c.topk + 1),
-                  gs.rec.ptr + (size_t)i0 * c.n_limbs * c.topk * 3, gs.cnt.ptr + (size_t)i0 * c.n_limbs,
-                  c.dist_max, c.use_scale, chunk == 0 ? slot->total.ptr : nullptr};
-    OG_TRY(launch_limb_score(det_score, det_index, offs ? offs + (size_t)i0 * nd * c.n_limbs * HW : nullptr,
-                             offs_lowres ? &src : nullptr, &h->ft, scales ? scales + plane0 * HW : nullptr,
-                             extras ? &ex : nullptr, cn, c.n_keypoints, c.n_limbs, c.topk, hgt, w, h->sk,
-                             c.thre_hmp, c.min_len, c.resize_factor, limbs, &po, a));
-    h->launches += 1;
-    if (timed) OG_TRY(mark(h, slot, 5, a));
-    const CocoOut coco = coco_out(h, slot, i0);
-    // A call that is one range leaves the images whose person table outgrows the warp kernel's
-    // (noise-like inputs) to og_fetch_result: the kernel raises meta[2n + 1] and the fetch runs the
-    // CTA kernel for them, instead of a launch of early-exit CTAs behind every call.
-    int32_t *lazy_flag = (i0 == 0 && cn == n) ? meta + 2 * n + 1 : nullptr;
-    OG_TRY(run_k3(h, gs, i0, limbs, true, cn, poses, slot->capacity_rows, meta + i0, meta + n + i0,
-                  slot->total.ptr, a, &coco, lazy_flag));
-    if (timed) OG_TRY(mark(h, slot, 6, a));
-    slot->k3_first = i0;
-    slot->k3_images = cn;
-    return OG_OK;
+    return run_limbs_and_groups(h, slot, chunk, i0, cn, offs, offs_lowres, &h->ft, scales, hgt, w, extras, timed);
 }
 
 int finish_call(og_handle *h, ResultSlot *slot) {
@@ -633,7 +663,7 @@ int decode_core(og_handle *h, ResultSlot *slot, const float *heat, const K1Fused
 // shapes and the slot's buffers stay the same: one cudaGraphLaunch instead of six kernel
 // launches.
 int decode_chain(og_handle *h, ResultSlot *slot, const K1Fused &k1, const OffsetSource &src, int n,
-                 int H, int W, cudaStream_t s) {
+                 int H, int W, cudaStream_t s, const LimbExtras *extras = nullptr) {
     OG_TRY(begin_call(h, slot, &k1, n, H, W, s));
     cudaStream_t a = slot->work;
     if (n == 0) {
@@ -643,12 +673,14 @@ int decode_chain(og_handle *h, ResultSlot *slot, const K1Fused &k1, const Offset
     OG_CUDA_TRY(cudaEventRecord(slot->call_start, s));
     OG_CUDA_TRY(cudaStreamWaitEvent(a, slot->call_start, 0));
     if (!h->graph_enabled || h->timing) {
-        OG_TRY(decode_range(h, slot, 0, 0, n, nullptr, &k1, nullptr, &src, nullptr, H, W, a, nullptr, true));
+        OG_TRY(decode_range(h, slot, 0, 0, n, nullptr, &k1, nullptr, &src, nullptr, H, W, a, extras, true));
         return finish_call(h, slot);
     }
     const GraphKey key = {k1.hmp.ptr, src.maps.ptr, k1.hmp.dtype, k1.hmp.image_stride, src.maps.image_stride,
                           n, k1.h, k1.w, k1.scale, k1.cubic ? 1 : 0, k1.flip ? 1 : 0, slot->emit_coco ? 1 : 0,
-                          h->tables_version, slot->buffers_version};
+                          h->tables_version, slot->buffers_version,
+                          extras ? extras->scale_lr.ptr : nullptr, extras ? extras->jitter_lr.ptr : nullptr,
+                          extras ? extras->vector_nd : 2, extras ? extras->use_jitter : 0};
     int gi = -1, victim = 0;
     for (int i = 0; i < kGraphsPerSlot; ++i) {
         if (slot->graph[i] != nullptr && slot->key[i] == key) gi = i;
@@ -658,7 +690,7 @@ int decode_chain(og_handle *h, ResultSlot *slot, const K1Fused &k1, const Offset
         gi = victim;
         cudaGraph_t graph = nullptr;
         OG_CUDA_TRY(cudaStreamBeginCapture(a, cudaStreamCaptureModeRelaxed));
-        const int st = decode_range(h, slot, 0, 0, n, nullptr, &k1, nullptr, &src, nullptr, H, W, a, nullptr, false);
+        const int st = decode_range(h, slot, 0, 0, n, nullptr, &k1, nullptr, &src, nullptr, H, W, a, extras, false);
         const cudaError_t end = cudaStreamEndCapture(a, &graph);
         if (st != OG_OK) {
             if (graph) cudaGraphDestroy(graph);
@@ -740,8 +772,6 @@ int decode_features_impl(og_handle *h, ResultSlot *slot, const float *hmp, const
         OG_TRY(mark(h, slot, 0, s));
         slot->prep_marked = h->timing;
     }
-    slot->args = FeatureArgs{hmp, off, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, nullptr,
-                             MapView{nullptr, 0, 0}, MapView{nullptr, 0, 0}};
 
     // Fused path: candidates straight from the network-resolution maps, offsets sampled at
     // the candidates; no full-resolution map is written.  thre_hmp <= 0 (every pixel is a
@@ -1022,6 +1052,9 @@ int og_destroy(og_handle *h) {
         sl.tile_flag.release();
         sl.tile_list.release();
         sl.limbs.release();
+        sl.redo_lr.release();
+        sl.redo_hr.release();
+        sl.redo_list.release();
         sl.group.release();
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.call_start) cudaEventDestroy(sl.call_start);
@@ -1194,7 +1227,6 @@ int og_decode_maps(og_handle *h, const float *heat_dev, const float *offs_dev,
     OG_TRY(check_device(h));
     ResultSlot *slot = nullptr;
     OG_TRY(acquire_slot(h, nullptr, &slot));
-    slot->args = FeatureArgs{};
     return decode_core(h, slot, heat_dev, nullptr, offs_dev, nullptr, scales_dev, n, hgt, w,
                        static_cast<cudaStream_t>(stream));
 }
@@ -1209,7 +1241,6 @@ int og_decode_maps_ex(og_handle *h, const float *heat_dev, const float *offs_dev
     OG_TRY(check_device(h));
     ResultSlot *slot = nullptr;
     OG_TRY(acquire_slot(h, nullptr, &slot));
-    slot->args = FeatureArgs{};
     LimbExtras ex = {jomps_dev, vector_nd, use_jitter};
     return decode_core(h, slot, heat_dev, nullptr, offs_dev, nullptr, scales_dev, n, hgt, w,
                        static_cast<cudaStream_t>(stream), &ex);
@@ -1227,6 +1258,42 @@ int og_decode_features_dev(og_handle *h, const float *hmp_dev, const float *off_
     OG_TRY(acquire_slot(h, nullptr, &slot));
     return decode_features_impl(h, slot, hmp_dev, off_dev, n, hgt, w, hmp_stride, off_stride,
                                 resize_mode, flip_test, s, true);
+}
+
+int og_decode_features_heads_dev(og_handle *h, const float *hmp_dev, const float *off_dev,
+                                 const float *scale_dev, const float *jitter_dev, int n, int hgt, int w,
+                                 int hmp_stride, int off_stride, int resize_mode, int flip_test,
+                                 int cat_flip_offs, int use_jitter, const int32_t *kp_flip,
+                                 const int32_t *limb_flip, const int32_t *limb_reserve, int n_reserve,
+                                 void *stream) {
+    OG_REQUIRE(h && (n == 0 || (hmp_dev && off_dev)), "og_decode_features_heads_dev: null pointer");
+    OG_REQUIRE(!cat_flip_offs || flip_test, "cat_flip_offs concatenates the mirrored copy's offsets: it needs flip_test");
+    OG_REQUIRE(!(cat_flip_offs && jitter_dev && use_jitter),
+               "jitter refinement of 4-D offset vectors is undefined (it raises in the reference too)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OG_TRY(check_feature_args(h, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test, kp_flip,
+                              limb_flip, limb_reserve, n_reserve));
+    const og_config &c = h->cfg;
+    if (!(h->fused_enabled && c.thre_hmp > 0.0f && fused_supported(n, c.n_keypoints, hmp_stride, hgt, w))) {
+        set_error("og_decode_features_heads_dev needs the fused path (stride 2, 4 or 8, thre_hmp > 0, fused "
+                  "enabled); resize the maps and call og_decode_maps_ex");
+        return OG_ERR_UNSUPPORTED;
+    }
+    ResultSlot *slot = nullptr;
+    OG_TRY(acquire_slot(h, nullptr, &slot));
+    const size_t hw = (size_t)hgt * w;
+    const int H = hgt * hmp_stride, W = w * hmp_stride;
+    OG_TRY(check_maps(n, H, W, c.n_keypoints));
+    K1Fused k1 = {dense_f32(hmp_dev, (size_t)c.n_keypoints * hw), hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
+    OffsetSource src = {dense_f32(off_dev, (size_t)2 * c.n_limbs * hw), hgt, w, off_stride, flip_test ? 1 : 0, n};
+    LimbExtras ex = {};
+    ex.vector_nd = cat_flip_offs ? 4 : 2;
+    ex.use_jitter = use_jitter ? 1 : 0;
+    // keypoint scales are resized like the heat maps (x off_stride, inter_mode), jitter offsets
+    // bilinearly x hmp_stride (factory.py:80-88)
+    ex.scale_lr = HeadSource{scale_dev, hgt, w, off_stride, resize_mode == 1 ? 1 : 0};
+    ex.jitter_lr = HeadSource{jitter_dev, hgt, w, hmp_stride, 0};
+    return decode_chain(h, slot, k1, src, n, H, W, s, &ex);
 }
 
 namespace {
@@ -1259,8 +1326,6 @@ int decode_dev_views(og_handle *h, const void *hmp_dev, const void *off_dev, int
     OG_TRY(acquire_slot(h, nullptr, &slot));
     const int H = hgt * hmp_stride, W = w * hmp_stride;
     OG_TRY(check_maps(n, H, W, c.n_keypoints));
-    slot->args = FeatureArgs{nullptr, nullptr, n, hgt, w, hmp_stride, off_stride, resize_mode, flip_test,
-                             nullptr, hv, ov};
     K1Fused k1 = {hv, hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
     OffsetSource src = {ov, hgt, w, off_stride, flip_test ? 1 : 0, n};
     return decode_chain(h, slot, k1, src, n, H, W, s);
@@ -1389,9 +1454,6 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
     }
     const int H = hgt * hmp_stride, W = w * hmp_stride;
     OG_TRY(check_maps(n, H, W, c.n_keypoints));
-    slot->args = FeatureArgs{slot->in_hmp.ptr, off_alias ? nullptr : slot->in_off.ptr, n, hgt, w,
-                             hmp_stride, off_stride, resize_mode, flip_test, off_alias ? off_host : nullptr,
-                             MapView{nullptr, 0, 0}, MapView{nullptr, 0, 0}};
     K1Fused k1 = {dense_f32(slot->in_hmp.ptr, hmp_img), hgt, w, hmp_stride, resize_mode == 1, flip_test != 0};
     OffsetSource src = {dense_f32(off_src, off_img), hgt, w, off_stride, flip_test ? 1 : 0, n};
     OG_TRY(begin_call(h, slot, &k1, n, H, W, s));
@@ -1423,6 +1485,48 @@ int og_decode_features_host(og_handle *h, const float *hmp_host, const float *of
 }
 
 namespace {
+
+// Fused decode whose candidate lists overflowed in some planes (det_count == -1 there): each such
+// plane is flip-fused at network resolution, resized to full resolution and selected by the exact
+// radix selection, a group of planes per launch; then K2 / K3 of the whole call run again.
+int redo_overflowed_planes(og_handle *h, ResultSlot *slot) {
+    const og_config &c = h->cfg;
+    const int n = slot->n, planes = n * c.n_keypoints;
+    const CallCtx &ctx = slot->ctx;
+    cudaStream_t a = slot->work;
+    std::vector<int32_t> counts((size_t)planes), list;
+    OG_CUDA_TRY(cudaMemcpyAsync(counts.data(), slot->det_count.ptr, sizeof(int32_t) * planes, cudaMemcpyDeviceToHost, a));
+    OG_CUDA_TRY(cudaStreamSynchronize(a));
+    for (int p = 0; p < planes; ++p)
+        if (counts[p] < 0) list.push_back(p);
+    if (!list.empty()) {
+        const size_t hw = (size_t)ctx.k1.h * ctx.k1.w, HW = (size_t)ctx.H * ctx.W;
+        const size_t group = std::max<size_t>(1, std::min(list.size(), ((size_t)256 << 20) / (HW * sizeof(float))));
+        OG_TRY(ensure_tracked(slot->redo_list, list.size(), slot));
+        OG_TRY(ensure_tracked(slot->redo_lr, group * hw, slot));
+        OG_TRY(ensure_tracked(slot->redo_hr, group * HW, slot));
+        OG_CUDA_TRY(cudaMemcpyAsync(slot->redo_list.ptr, list.data(), sizeof(int32_t) * list.size(),
+                                    cudaMemcpyHostToDevice, a));
+        for (size_t g0 = 0; g0 < list.size(); g0 += group) {
+            const int cnt = (int)std::min(group, list.size() - g0);
+            OG_TRY(launch_fuse_planes(ctx.k1.hmp, ctx.ft, n, c.n_keypoints, ctx.k1.h, ctx.k1.w, ctx.k1.flip,
+                                      slot->redo_list.ptr + g0, cnt, slot->redo_lr.ptr, a));
+            OG_TRY(launch_resize(slot->redo_lr.ptr, slot->redo_hr.ptr, cnt, ctx.k1.h, ctx.k1.w, ctx.k1.scale,
+                                 ctx.k1.cubic ? 1 : 0, a));
+            h->launches += 2;
+            OG_TRY(launch_nms_topk(slot->redo_hr.ptr, cnt, ctx.H, ctx.W, c.thre_hmp, c.topk, nullptr, nullptr,
+                                   slot->det_score.ptr, slot->det_index.ptr, slot->det_count.ptr, true, true, a,
+                                   &h->launches, nullptr, slot->redo_list.ptr + g0));
+        }
+    }
+    volatile int32_t *meta = reinterpret_cast<volatile int32_t *>(slot->out_host);
+    meta[2 * n] = 0;
+    meta[2 * n + 1] = 0;
+    OG_TRY(run_limbs_and_groups(h, slot, 0, 0, n, nullptr, &ctx.src, &ctx.ft, nullptr, ctx.H, ctx.W,
+                                ctx.extras.vector_nd ? &ctx.extras : nullptr, false));
+    OG_CUDA_TRY(cudaStreamSynchronize(a));       // `list` is read by the copy above until here
+    return OG_OK;
+}
 
 // Re-run K3 of a fetched call into a worst-case result buffer (more persons than the pinned
 // buffer was sized for: noise-like inputs only).
@@ -1457,33 +1561,11 @@ int og_fetch_result(og_handle *h, og_result *out) {
         OG_CUDA_TRY(cudaStreamSynchronize(slot->work));
         const volatile int32_t *meta = reinterpret_cast<const volatile int32_t *>(slot->out_host);
         if (slot->fused && meta[2 * n] != 0) {
-            // Some plane produced more than kCandCap candidates (noise-like input): the fused
-            // kernel cannot re-scan a map it never materialised, so this batch is decoded again
-            // on the GPU through the materialising path, which selects exactly for any input.
+            // Some plane produced more than kCandCap candidates (noise-like input).  The fused kernel
+            // cannot re-scan a map it never materialised, so those planes — and only those — are
+            // materialised now and selected exactly, and K2 / K3 run again on the completed dets.
             h->fused_redos += 1;
-            FeatureArgs a = slot->args;
-            if (a.hmp_view.ptr) {       // bf16 / strided maps: dense float32 copies for the exact path
-                const int n_in = a.flip ? 2 * a.n : a.n;
-                const size_t hmp_img = (size_t)h->cfg.n_keypoints * a.hgt * a.w;
-                const size_t off_img = (size_t)2 * h->cfg.n_limbs * a.hgt * a.w;
-                OG_TRY(ensure_tracked(slot->in_hmp, (size_t)n_in * hmp_img, slot));
-                OG_TRY(ensure_tracked(slot->in_off, (size_t)n_in * off_img, slot));
-                OG_TRY(launch_densify(a.hmp_view, slot->in_hmp.ptr, n_in, hmp_img, slot->stream));
-                OG_TRY(launch_densify(a.off_view, slot->in_off.ptr, n_in, off_img, slot->stream));
-                h->launches += 2;
-                a.hmp = slot->in_hmp.ptr;
-                a.off = slot->in_off.ptr;
-            }
-            if (a.off_host) {           // the materialising path reads every offset: copy them now
-                const size_t elems = (size_t)(a.flip ? 2 * a.n : a.n) * 2 * h->cfg.n_limbs * a.hgt * a.w;
-                OG_TRY(ensure_tracked(slot->in_off, elems, slot));
-                OG_CUDA_TRY(cudaMemcpyAsync(slot->in_off.ptr, a.off_host, elems * sizeof(float),
-                                            cudaMemcpyHostToDevice, slot->stream));
-                a.off = slot->in_off.ptr;
-            }
-            OG_TRY(decode_features_impl(h, slot, a.hmp, a.off, a.n, a.hgt, a.w, a.hmp_stride,
-                                        a.off_stride, a.resize_mode, a.flip, slot->stream, false));
-            OG_CUDA_TRY(cudaStreamSynchronize(slot->work));
+            OG_TRY(redo_overflowed_planes(h, slot));
             meta = reinterpret_cast<const volatile int32_t *>(slot->out_host);
         }
         if (meta[2 * n + 1] != 0) {

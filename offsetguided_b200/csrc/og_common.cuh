@@ -97,18 +97,20 @@ int launch_hmp_nms(const float *heat, float *out, int planes, int h, int w, cuda
 
 // pass 1: stream the heat map, append survivors; pass 2: per-plane select.
 // `force_radix` skips pass 1 and runs the exact radix selection on every plane;
-// `apply_nms` = 0 selects on the raw map (topK_channel).
+// `apply_nms` = 0 selects on the raw map (topK_channel).  `plane_map` (device, optional): the
+// results of plane b go to slot plane_map[b] of the output arrays.
 int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int k,
                     uint32_t *cand_count, uint64_t *cand_keys,
                     float *out_score, int32_t *out_index, int32_t *out_count,
                     bool force_radix, bool apply_nms, cudaStream_t s, int64_t *launches,
-                    cudaEvent_t after_pass1 = nullptr);
+                    cudaEvent_t after_pass1 = nullptr, const int32_t *plane_map = nullptr);
 // pass 1 alone (counters cleared, survivors appended)
 int launch_nms_candidates(const float *heat, int planes, int h, int w, float thre,
                           uint32_t *cand_count, uint64_t *cand_keys, cudaStream_t s,
                           int64_t *launches);
 // pass 2 alone on candidate lists some other kernel filled; with heat == nullptr a plane
-// with more than kCandCap candidates cannot be re-scanned and raises *overflow_flag.
+// with more than kCandCap candidates cannot be re-scanned: it raises *overflow_flag and its
+// out_count is -1 (og_fetch_result materialises and selects such planes one by one).
 // Every plane's counter is left at ZERO for the next call (the lists are per result slot);
 // `clear_word`, when given, is zeroed as well (the fused path's active-block counter).
 int launch_select_topk(const float *heat, int planes, int h, int w, float thre, int k,
@@ -135,7 +137,6 @@ __device__ __forceinline__ float load_cell(const __half *p) {
     return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short *>(p))));
 }
 #endif
-int launch_densify(const MapView &src, float *dst, int images, size_t per_image, cudaStream_t s);
 
 // Offsets still at network resolution (fused path): K2 samples them bilinearly at the
 // candidate pixels instead of gathering from a materialised full-resolution map.
@@ -154,11 +155,22 @@ struct OffsetSource {
     int flip, n;                    // flip: maps = n originals then n mirrored copies
 };
 
+// An optional head at NETWORK resolution (float32, dense [n or 2n][channels][h][w]; the flip layout
+// and image count are those of the OffsetSource of the call): K2 interpolates it at the few
+// pixels it needs instead of reading a materialised x scale map.
+struct HeadSource {
+    const float *ptr;       // nullptr: head not present
+    int h, w, scale;
+    int cubic;              // interpolation of the reference's resize (factory.py:80-88)
+};
+
 // Optional variants of generate_limbs (collect.py:127-138, 158-165, 213-218 and vector_nd = 4).
 struct LimbExtras {
     const float *jomps;     // [n, 2, H, W] jitter-offset maps at decode resolution, or nullptr
     int vector_nd;          // 2, or 4 for cat_flip_offs offsets ([n, 4L, H, W])
     int use_jitter;         // --use-jitter-offset
+    HeadSource scale_lr;    // keypoint-scale maps [.., C, h, w] (fused path; else `scales` at decode resolution)
+    HeadSource jitter_lr;   // jitter-offset maps [.., 2, h, w] (fused path; else `jomps`)
 };
 
 // What K2 hands to K3 besides the limb table (og_prep.cuh); prep == nullptr: scoring only.
@@ -203,6 +215,13 @@ int launch_fused_candidates(const MapView &hmp, const FlipTablesDev &flips, int 
                             uint64_t *cand_keys, uint8_t *block_flag, int32_t *block_list,
                             int32_t *n_active, int sm_count, bool clear_first, cudaStream_t s,
                             int64_t *launches);
+
+// Network-resolution planes plane_list[0 .. count) (plane = image * C + channel) of `hmp` as dense
+// float32, averaged with their mirrored partners when `flip` (factory.py:101-106): the input of the
+// exact per-plane redo of a fused decode.  `n` = images of the call (the mirrored copy of image i
+// is image n + i).
+int launch_fuse_planes(const MapView &hmp, const FlipTablesDev &flips, int n, int c, int h, int w, bool flip,
+                       const int32_t *plane_list, int count, float *out, cudaStream_t s);
 
 // optional second output of K3: result rows back-projected into the original image frames
 struct CocoOut {

@@ -541,29 +541,42 @@ int launch_fused_candidates(const MapView &hmp, const FlipTablesDev &kp_flip_dev
                           n_active, sm_count, clear_first, s, launches);
 }
 
-// dense float32 copy of strided / bf16 maps (only the exact redo of an overflowed batch needs it)
+// single network-resolution planes as dense float32, flip-fused (the exact per-plane redo of a
+// fused decode: og_fetch_result resizes and radix-selects the planes whose candidate lists
+// overflowed)
 namespace {
 template <typename T>
-__global__ void densify_kernel(const T *__restrict__ src, size_t img_stride, float *__restrict__ dst,
-                               size_t per_image, size_t total) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const size_t img = i / per_image, r = i - img * per_image;
-        dst[i] = load_cell(src + img * img_stride + r);
+__global__ void fuse_planes_kernel(const T *__restrict__ hmp, size_t img_stride, const FlipTablesDev ft, int n,
+                                   int C, int h, int w, int flip, const int32_t *__restrict__ plane_list,
+                                   float *__restrict__ out) {
+    const int plane = plane_list[blockIdx.y];
+    const int img = plane / C, c = plane - img * C;
+    const size_t hw = (size_t)h * w;
+    const T *a = hmp + (size_t)img * img_stride + (size_t)c * hw;
+    const T *b = flip ? hmp + (size_t)(n + img) * img_stride + (size_t)ft.kp[c] * hw : nullptr;
+    float *o = out + (size_t)blockIdx.y * hw;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
+        float v = load_cell(a + i);
+        if (flip) {                          // (orig + flip_W(flipped)[kp_flip]) / 2, factory.py:101-106
+            const int y = (int)(i / w), x = (int)(i - (size_t)y * w);
+            v = __fmul_rn(__fadd_rn(v, load_cell(b + (size_t)y * w + (w - 1 - x))), 0.5f);
+        }
+        o[i] = v;
     }
 }
 }  // namespace
 
-int launch_densify(const MapView &src, float *dst, int images, size_t per_image, cudaStream_t s) {
-    const size_t total = (size_t)images * per_image;
-    if (total == 0) return OG_OK;
-    const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
-    if (src.dtype == OG_DTYPE_BF16)
-        densify_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(src.ptr), src.image_stride, dst, per_image, total);
-    else if (src.dtype == OG_DTYPE_F16)
-        densify_kernel<<<grid, 256, 0, s>>>(static_cast<const __half *>(src.ptr), src.image_stride, dst, per_image, total);
+int launch_fuse_planes(const MapView &hmp, const FlipTablesDev &flips, int n, int c, int h, int w, bool flip,
+                       const int32_t *plane_list, int count, float *out, cudaStream_t s) {
+    if (count == 0) return OG_OK;
+    const size_t hw = (size_t)h * w;
+    const dim3 grid((unsigned)std::min<size_t>((hw + 255) / 256, 64), (unsigned)count);
+    if (hmp.dtype == OG_DTYPE_BF16)
+        fuse_planes_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(hmp.ptr), hmp.image_stride, flips, n, c, h, w, flip ? 1 : 0, plane_list, out);
+    else if (hmp.dtype == OG_DTYPE_F16)
+        fuse_planes_kernel<<<grid, 256, 0, s>>>(static_cast<const __half *>(hmp.ptr), hmp.image_stride, flips, n, c, h, w, flip ? 1 : 0, plane_list, out);
     else
-        densify_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(src.ptr), src.image_stride, dst, per_image, total);
+        fuse_planes_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(hmp.ptr), hmp.image_stride, flips, n, c, h, w, flip ? 1 : 0, plane_list, out);
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;
 }

@@ -33,46 +33,78 @@ __device__ __forceinline__ float norm2(float dx, float dy) {
     return __fsqrt_rn(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
-// Guiding offset (component comp of limb l) at full-resolution pixel (X, Y) when the offset
-// maps are still at network resolution: bilinear x S sampling on the fly, optionally fused
-// with the flip-test average (factory.py:128-139) — bit-identical to gathering from the
-// materialised F.interpolate(offs, scale_factor=S, mode='bilinear') map.
+// Value at full-resolution pixel (X, Y) of a map that is still at network resolution: x S
+// interpolation on the fly (bilinear or bicubic, ATen's taps and accumulation order, og_interp.cuh),
+// optionally fused with the flip-test combination of plane `a` (original image) and plane `b`
+// (mirrored image, read right-to-left) — bit-identical to gathering from the materialised
+// flip_augment + F.interpolate(scale_factor = S) map.
+enum FlipMode { kFlipNone = 0, kFlipAverage = 1, kFlipPartnerOnly = 2 };
+
 template <typename T>
-__device__ __forceinline__ float sample_offset_t(const OffsetSource &src, const FlipTablesDev &ft,
-                                                 int img, int L, int l, int comp, int X, int Y) {
-    const int h = src.h, w = src.w;
-    const size_t hw = (size_t)h * w;
-    const T *base = static_cast<const T *>(src.maps.ptr);
-    const T *a = base + (size_t)img * src.maps.image_stride + (size_t)(2 * l + comp) * hw;
-    const bool mirrored = src.flip && !((ft.reserved >> l) & 1ull);
-    const T *b = mirrored ? base + (size_t)(src.n + img) * src.maps.image_stride +
-                                (size_t)(2 * (int)ft.limb[l] + comp) * hw
-                          : nullptr;
+__device__ __forceinline__ float sample_lowres(const T *a, const T *b, int mode, bool negate_b, int h, int w,
+                                               int scale, bool cubic, int X, int Y) {
     auto at = [&](int yy, int xx) {
-        float v = load_cell(a + yy * w + xx);
-        if (mirrored) {
-            float m = load_cell(b + yy * w + (w - 1 - xx));
-            if (comp == 0) m = -m;
-            v = __fmul_rn(__fadd_rn(v, m), 0.5f);
-        }
-        return v;
+        if (mode == kFlipNone) return load_cell(a + yy * w + xx);
+        float m = load_cell(b + yy * w + (w - 1 - xx));
+        if (negate_b) m = -m;
+        if (mode == kFlipPartnerOnly) return m;
+        return __fmul_rn(__fadd_rn(load_cell(a + yy * w + xx), m), 0.5f);
     };
-    if (src.scale == 1) return at(Y, X);
-    const float inv = 1.0f / (float)src.scale;
+    if (scale == 1) return at(Y, X);
+    const float inv = 1.0f / (float)scale;
     int ix[4], iy[4];
     float wx[4], wy[4];
-    axis_taps(X, w, inv, false, ix, wx);
-    axis_taps(Y, h, inv, false, iy, wy);
-    const float r0 = combine2(at(iy[0], ix[0]), at(iy[0], ix[1]), wx[0], wx[1]);
-    const float r1 = combine2(at(iy[1], ix[0]), at(iy[1], ix[1]), wx[0], wx[1]);
-    return combine2(r0, r1, wy[0], wy[1]);
+    const int taps = axis_taps(X, w, inv, cubic, ix, wx);
+    axis_taps(Y, h, inv, cubic, iy, wy);
+    if (!cubic) {
+        const float r0 = combine2(at(iy[0], ix[0]), at(iy[0], ix[1]), wx[0], wx[1]);
+        const float r1 = combine2(at(iy[1], ix[0]), at(iy[1], ix[1]), wx[0], wx[1]);
+        return combine2(r0, r1, wy[0], wy[1]);
+    }
+    float rows[4];
+    for (int j = 0; j < taps; ++j)
+        rows[j] = combine4(at(iy[j], ix[0]), at(iy[j], ix[1]), at(iy[j], ix[2]), at(iy[j], ix[3]), wx[0], wx[1],
+                           wx[2], wx[3]);
+    return combine4(rows[0], rows[1], rows[2], rows[3], wy[0], wy[1], wy[2], wy[3]);
 }
 
-__device__ __forceinline__ float sample_offset(const OffsetSource &src, const FlipTablesDev &ft, int img,
-                                               int L, int l, int comp, int X, int Y) {
-    if (src.maps.dtype == OG_DTYPE_BF16) return sample_offset_t<__nv_bfloat16>(src, ft, img, L, l, comp, X, Y);
-    if (src.maps.dtype == OG_DTYPE_F16) return sample_offset_t<__half>(src, ft, img, L, l, comp, X, Y);
-    return sample_offset_t<float>(src, ft, img, L, l, comp, X, Y);
+// Guiding offset (component comp of limb l) at full-resolution pixel (X, Y) from the network-
+// resolution offset maps.  comp 0, 1: the flip-test average (factory.py:128-139), or the original
+// alone when `cat` (cat_flip_offs, factory.py:115-127); comp 2, 3 (cat only): the mirrored copy's
+// vector, x negated; limbs that are their own mirror image keep the original either way.
+template <typename T>
+__device__ __forceinline__ float sample_offset_t(const OffsetSource &src, const FlipTablesDev &ft, int img, int l,
+                                                 int comp, bool cat, int X, int Y) {
+    const size_t hw = (size_t)src.h * src.w;
+    const T *base = static_cast<const T *>(src.maps.ptr);
+    const int c2 = comp & 1;
+    const T *a = base + (size_t)img * src.maps.image_stride + (size_t)(2 * l + c2) * hw;
+    const bool mirrored = src.flip && !((ft.reserved >> l) & 1ull);
+    const T *b = mirrored ? base + (size_t)(src.n + img) * src.maps.image_stride +
+                                (size_t)(2 * (int)ft.limb[l] + c2) * hw
+                          : nullptr;
+    int mode = kFlipNone;
+    if (mirrored) mode = cat ? (comp >= 2 ? kFlipPartnerOnly : kFlipNone) : kFlipAverage;
+    return sample_lowres(a, b, mode, c2 == 0, src.h, src.w, src.scale, false, X, Y);
+}
+
+__device__ __forceinline__ float sample_offset(const OffsetSource &src, const FlipTablesDev &ft, int img, int l,
+                                               int comp, bool cat, int X, int Y) {
+    if (src.maps.dtype == OG_DTYPE_BF16) return sample_offset_t<__nv_bfloat16>(src, ft, img, l, comp, cat, X, Y);
+    if (src.maps.dtype == OG_DTYPE_F16) return sample_offset_t<__half>(src, ft, img, l, comp, cat, X, Y);
+    return sample_offset_t<float>(src, ft, img, l, comp, cat, X, Y);
+}
+
+// Channel ch of an optional head (keypoint scales: channels = C, mirrored partner ft.kp[ch],
+// factory.py:141-144; jitter offsets: channels = 2, partner = the same channel with x negated,
+// factory.py:109-113) at full-resolution pixel (X, Y).
+__device__ __forceinline__ float sample_head(const HeadSource &hs, const OffsetSource &src, int img, int channels,
+                                             int ch, int partner, bool negate_partner, int X, int Y) {
+    const size_t hw = (size_t)hs.h * hs.w;
+    const float *a = hs.ptr + ((size_t)img * channels + ch) * hw;
+    const float *b = src.flip ? hs.ptr + ((size_t)(src.n + img) * channels + partner) * hw : nullptr;
+    return sample_lowres(a, b, src.flip ? kFlipAverage : kFlipNone, negate_partner, hs.h, hs.w, hs.scale,
+                         hs.cubic != 0, X, Y);
 }
 
 // Tensor.norm over 4 components as ATen's CPU kernel evaluates it (probed) is a plain left-to-right
@@ -132,8 +164,12 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
         candidate(jt, k, t.x, t.y, t.score, t.index);
         candidate(jf, k, x1, y1, s1, idx1);
         t.scale = 4.0f;                                              // collect.py:120
-        if (scales != nullptr && t.index >= 0)
-            t.scale = __ldg(scales + ((size_t)n * C + jt) * HW + t.index);   // collect.py:114
+        if (t.index >= 0) {
+            if (scales != nullptr)
+                t.scale = __ldg(scales + ((size_t)n * C + jt) * HW + t.index);   // collect.py:114
+            else if (ex.scale_lr.ptr != nullptr)
+                t.scale = sample_head(ex.scale_lr, src, n, C, jt, ft.kp[jt], false, t.index % W, t.index / W);
+        }
         s_to[k] = t;
     }
     // the guiding offset of this thread's from-candidate (global / PCIe gathers: issued before
@@ -151,10 +187,17 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
             }
         } else {
             const int py = idx1 / W, px = idx1 - py * W;
-            ox = sample_offset(src, ft, n, L, l, 0, px, py);
-            oy = sample_offset(src, ft, n, L, l, 1, px, py);
+            ox = sample_offset(src, ft, n, l, 0, kFour, px, py);
+            oy = sample_offset(src, ft, n, l, 1, kFour, px, py);
+            if (kFour) {
+                ox2 = sample_offset(src, ft, n, l, 2, true, px, py);
+                oy2 = sample_offset(src, ft, n, l, 3, true, px, py);
+            }
         }
-        if (scales != nullptr) scale1 = __ldg(scales + ((size_t)n * C + jf) * HW + idx1);
+        if (scales != nullptr)
+            scale1 = __ldg(scales + ((size_t)n * C + jf) * HW + idx1);
+        else if (ex.scale_lr.ptr != nullptr)
+            scale1 = sample_head(ex.scale_lr, src, n, C, jf, ft.kp[jf], false, idx1 % W, idx1 / W);
     }
     __syncthreads();
 
@@ -163,15 +206,20 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
         float gy = __fadd_rn(y1, __fmul_rn(oy, resize_factor));
         const float gx2 = __fadd_rn(x1, __fmul_rn(ox2, resize_factor));
         const float gy2 = __fadd_rn(y1, __fmul_rn(oy2, resize_factor));
-        if (ex.jomps != nullptr && ex.use_jitter && !kFour) {
+        // jitter-offset component `comp` at decode-resolution pixel (row py, column px)
+        const bool have_jitter = ex.jomps != nullptr || ex.jitter_lr.ptr != nullptr;
+        auto jitter_at = [&](int comp, int px, int py) {
+            if (ex.jomps != nullptr) return __ldg(ex.jomps + ((size_t)n * 2 + comp) * HW + (size_t)py * W + px);
+            return sample_head(ex.jitter_lr, src, n, 2, comp, comp, comp == 0, px, py);
+        };
+        if (have_jitter && ex.use_jitter && !kFour) {
             // jitter refinement of the guided point (collect.py:158-165), including the
             // reference's [x, y]-as-[row, col] indexing; .int() truncates toward zero.
             // (The reference raises IndexError when x >= H; such points are left unrefined.)
             const int xi = (int)gx, yi = (int)gy;
             if (xi >= 0 && xi < W && yi >= 0 && yi < H && xi < H && yi < W) {
-                const float *jm = ex.jomps + (size_t)n * 2 * HW + (size_t)xi * W + yi;
-                gx = __fadd_rn(gx, __ldg(jm));
-                gy = __fadd_rn(gy, __ldg(jm + HW));
+                gx = __fadd_rn(gx, jitter_at(0, yi, xi));         // row xi, column yi
+                gy = __fadd_rn(gy, jitter_at(1, yi, xi));
             }
         }
         auto sq_to = [&](int m) {
@@ -206,14 +254,14 @@ limb_score_kernel(const float *__restrict__ det_score, const int32_t *__restrict
         const long long g2 = (long long)t.index + (long long)jt * HW;
 
         float x1o = x1, y1o = y1, x2o = t.x, y2o = t.y;
-        if (ex.jomps != nullptr && ex.use_jitter) {        // collect.py:213-218
+        if (have_jitter && ex.use_jitter) {        // collect.py:213-218
             if (idx1 >= 0) {
-                x1o = __fadd_rn(x1o, __ldg(ex.jomps + (size_t)n * 2 * HW + idx1));
-                y1o = __fadd_rn(y1o, __ldg(ex.jomps + (size_t)n * 2 * HW + HW + idx1));
+                x1o = __fadd_rn(x1o, jitter_at(0, idx1 % W, idx1 / W));
+                y1o = __fadd_rn(y1o, jitter_at(1, idx1 % W, idx1 / W));
             }
             if (t.index >= 0) {
-                x2o = __fadd_rn(x2o, __ldg(ex.jomps + (size_t)n * 2 * HW + t.index));
-                y2o = __fadd_rn(y2o, __ldg(ex.jomps + (size_t)n * 2 * HW + HW + t.index));
+                x2o = __fadd_rn(x2o, jitter_at(0, t.index % W, t.index / W));
+                y2o = __fadd_rn(y2o, jitter_at(1, t.index % W, t.index / W));
             }
         }
         row[0] = x1o;                                                   // collect.py:223-233
@@ -254,7 +302,8 @@ int launch_limb_score(const float *det_score, const int32_t *det_index, const fl
     if (lowres) src = *lowres;
     FlipTablesDev ft = {};
     if (flips) ft = *flips;
-    LimbExtras ex = {nullptr, 2, 0};
+    LimbExtras ex = {};
+    ex.vector_nd = 2;
     if (extras) ex = *extras;
     PrepOut po = {nullptr, nullptr, nullptr, 0.0f, 0, nullptr};
     if (prep) po = *prep;

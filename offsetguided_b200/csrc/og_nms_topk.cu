@@ -246,7 +246,7 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
                    const uint64_t *__restrict__ cand_keys, float *__restrict__ out_score,
                    int32_t *__restrict__ out_index, int32_t *__restrict__ out_count,
                    int force_radix, int apply_nms, int32_t *__restrict__ overflow_flag,
-                   int32_t *__restrict__ clear_word) {
+                   int32_t *__restrict__ clear_word, const int32_t *__restrict__ plane_map) {
     __shared__ uint64_t s_keys[kCandCap];
     __shared__ uint32_t s_hist[kRadixBins];
     __shared__ uint32_t s_part[kSelectThreads];
@@ -254,8 +254,12 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
 
     const int plane = blockIdx.x;
     const int tid = threadIdx.x;
-    float *o_score = out_score + (size_t)plane * K;
-    int32_t *o_index = out_index + (size_t)plane * K;
+    // results of plane b of `heat` go to slot plane_map[b] of the output arrays (the redo of single
+    // overflowed planes of a fused decode); the candidate lists are not used then (force_radix)
+    const int oplane = plane_map ? plane_map[plane] : plane;
+    float *o_score = out_score + (size_t)oplane * K;
+    int32_t *o_index = out_index + (size_t)oplane * K;
+    if (out_count) out_count += oplane - plane;
 
     // The plane's counter is read once and left at zero for the next call on these lists (they
     // belong to a result slot); the fused path's active-block counter is cleared the same way.
@@ -309,10 +313,10 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
         }
     }
 
-    if (heat == nullptr) {      // fused path: no materialised plane to re-scan; the host re-runs
-        if (tid == 0) {         // the batch through the materialising path (og_fetch_poses)
+    if (heat == nullptr) {      // fused path: no materialised plane to re-scan; og_fetch_result
+        if (tid == 0) {         // materialises the planes marked -1 and selects them exactly
             *reinterpret_cast<volatile int32_t *>(overflow_flag) = 1;      // may be mapped host memory
-            if (out_count) out_count[plane] = 0;
+            if (out_count) out_count[plane] = -1;
         }
         write_ranked(s_keys, 0, K, o_score, o_index);
         return;
@@ -471,14 +475,15 @@ int launch_hmp_nms(const float *heat, float *out, int planes, int h, int w, cuda
 int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int k,
                     uint32_t *cand_count, uint64_t *cand_keys, float *out_score,
                     int32_t *out_index, int32_t *out_count, bool force_radix, bool apply_nms,
-                    cudaStream_t s, int64_t *launches, cudaEvent_t after_pass1) {
+                    cudaStream_t s, int64_t *launches, cudaEvent_t after_pass1, const int32_t *plane_map) {
     if (planes == 0) return OG_OK;
     if (!force_radix) OG_TRY(launch_nms_candidates(heat, planes, h, w, thre, cand_count, cand_keys, s, launches));
     if (after_pass1) OG_CUDA_TRY(cudaEventRecord(after_pass1, s));
     prefer_chain_carveout<select_topk_kernel>();
     select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
                                                         out_score, out_index, out_count,
-                                                        force_radix ? 1 : 0, apply_nms ? 1 : 0, nullptr, nullptr);
+                                                        force_radix ? 1 : 0, apply_nms ? 1 : 0, nullptr, nullptr,
+                                                        plane_map);
     OG_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;
     return OG_OK;
@@ -523,7 +528,7 @@ int launch_select_topk(const float *heat, int planes, int h, int w, float thre, 
     prefer_chain_carveout<select_topk_kernel>();
     select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
                                                         out_score, out_index, out_count, 0, 1,
-                                                        overflow_flag, clear_word);
+                                                        overflow_flag, clear_word, nullptr);
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;
 }

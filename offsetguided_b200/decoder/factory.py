@@ -94,13 +94,17 @@ class PostProcess(torch.nn.Module):
         use_scale_maps = self.include_scale and lc.include_scale and isinstance(scmps, torch.Tensor)
         use_jitter_maps = (self.include_jitter_offset and lc.include_jitter_offset
                            and isinstance(jomps, torch.Tensor))
-        if scored_off or use_scale_maps or use_jitter_maps or (flip_test and cat_flip_offs):
-            return self._generate_poses_staged(hmps, jomps if use_jitter_maps else None, offs,
-                                               scmps if use_scale_maps else None, flip_test,
-                                               cat_flip_offs, scored_off)
         device = hmps.device if hmps.is_cuda else torch.device('cuda', torch.cuda.current_device())
         eng = self._engine(device)
         tables = self._flip_tables if flip_test else None
+        if scored_off or use_scale_maps or use_jitter_maps or (flip_test and cat_flip_offs):
+            jomps = jomps if use_jitter_maps else None
+            scmps = scmps if use_scale_maps else None
+            fused_ok = (eng._fused and eng.thre_hmp > 0 and int(self.hmp_stride) in (2, 4, 8)
+                        and int(self.hmp_stride) == int(self.off_stride) and hmps.shape[0] > 0)
+            if not fused_ok:
+                return self._generate_poses_staged(hmps, jomps, offs, scmps, flip_test, cat_flip_offs, scored_off)
+            return self._generate_poses_heads(eng, hmps, jomps, offs, scmps, flip_test, cat_flip_offs, scored_off)
         return eng.decode_features(hmps, offs, self.hmp_stride, self.off_stride, self.inter_mode, tables)
 
     def generate_results(self, features, metas, flip_test=False):
@@ -218,6 +222,26 @@ class PostProcess(torch.nn.Module):
             if use_scmps:                                           # factory.py:141-144
                 scmps = flip_average(scmps, self.keypoints_flips, False)
         return hmps, jomps, offs, scmps, vector_nd
+
+    def _generate_poses_heads(self, eng, hmps, jomps, offs, scmps, flip_test, cat_flip_offs, scored_off):
+        """The optional heads and flags on the fused path: no map is resized.  K2 interpolates the
+        keypoint-scale / jitter-offset maps at the candidate pixels and combines the flip-test
+        halves on the fly.  ``scored_off`` re-averages the offsets at NETWORK resolution
+        (decoder/offset.py:8-43 runs before the resize, factory.py:67-69), so the flip-test
+        halves are combined first, exactly as flip_augment does."""
+        tables = self._flip_tables if flip_test else None
+        if scored_off:
+            if flip_test and cat_flip_offs:
+                raise ValueError('scored_off cannot be combined with cat_flip_offs')
+            vector_nd = 2
+            if flip_test:
+                hmps, jomps, offs, scmps, vector_nd = self.flip_augment(hmps, jomps, offs, scmps, False, vector_nd)
+            jf, jt = _offset.pack_jtypes(self.skeleton)
+            offs = _offset.scored_offset(hmps, offs, jf, jt, kernel_size=3)
+            tables, cat_flip_offs = None, False
+        return eng.decode_features_heads(hmps, offs, scmps, jomps, self.hmp_stride, self.off_stride,
+                                         self.inter_mode, tables, cat_flip_offs,
+                                         self.limb_collect.use_jitter_offset)
 
     def _generate_poses_staged(self, hmps, jomps, offs, scmps, flip_test, cat_flip_offs, scored_off):
         """The optional heads and flags (scored_off, keypoint-scale maps, jitter-offset maps,

@@ -372,6 +372,37 @@ class DecoderEngine(object):
                 self._arg_cache.popitem(last=False)
         return self._finish((hmp, off), fetch, n)
 
+    def decode_features_heads(self, hmp, off, scales=None, jomps=None, hmp_stride=4, off_stride=4,
+                              resize_mode='bicubic', flip_tables=None, cat_flip_offs=False,
+                              use_jitter=False, fetch=True):
+        """decode_features with the optional heads on the fused path: keypoint-scale maps and
+        jitter-offset maps at NETWORK resolution are interpolated by K2 at the candidate pixels
+        (flip-test averages fused in), ``cat_flip_offs`` scores limbs on the 4-D [original,
+        mirrored] offset vectors.  Device-resident maps (anything else is converted to dense
+        float32 on the device first)."""
+        flip = flip_tables is not None
+        self._check_heads(hmp.shape, off.shape, 2, flip)
+        mode = {'bilinear': 0, 'bicubic': 1}[resize_mode]
+        hmp = as_cuda_f32(hmp, self.device)
+        off = as_cuda_f32(off, self.device)
+        n_in, c, h, w = hmp.shape
+        keep = [hmp, off]
+        for t, ch in ((scales, c), (jomps, 2)):
+            if t is not None and tuple(t.shape) != (n_in, ch, h, w):
+                raise ValueError('optional head of shape %s, expected %s' % (tuple(t.shape), (n_in, ch, h, w)))
+        scales = as_cuda_f32(scales, self.device) if scales is not None else None
+        jomps = as_cuda_f32(jomps, self.device) if jomps is not None else None
+        keep += [scales, jomps]
+        args = self._flip_args(flip_tables) if flip else (None, None, None, 0)
+        n = n_in // 2 if flip else n_in
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.og_decode_features_heads_dev(
+                self._h, _ptr(hmp), _ptr(off), _ptr(scales) if scales is not None else None,
+                _ptr(jomps) if jomps is not None else None, n, h, w, int(hmp_stride), int(off_stride), mode,
+                1 if flip else 0, 1 if cat_flip_offs else 0, 1 if use_jitter else 0, *args,
+                _stream_ptr(self.device)))
+        return self._finish(tuple(keep), fetch, n)
+
     def plan_features(self, hmp, off, hmp_stride, off_stride, resize_mode='bicubic', flip_tables=None):
         """A prepared decode of DEVICE-resident network-resolution maps for callers that decode the
         same buffers batch after batch (a network writes its outputs in place): shapes are

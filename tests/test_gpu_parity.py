@@ -655,8 +655,9 @@ def test_non_positive_threshold_takes_the_exact_path(cuda_device, thre):
 
 
 def test_fused_path_overflow_reruns_exactly(cuda_device):
-    """Noise heat maps overflow the per-plane candidate lists; the batch is then re-run on the
-    GPU through the materialising path and must equal it."""
+    """Noise heat maps overflow the per-plane candidate lists; the overflowed planes are then
+    materialised and selected exactly when the batch is fetched, and the result must equal the
+    materialising path."""
     rng = np.random.RandomState(3)
     hmp = torch.from_numpy(rng.uniform(0, 1, size=(1, 17, 160, 200)).astype(np.float32)).cuda()
     omp = torch.from_numpy(rng.uniform(-8, 8, size=(1, 38, 160, 200)).astype(np.float32)).cuda()
@@ -673,10 +674,39 @@ def test_fused_path_overflow_reruns_exactly(cuda_device):
     assert np.array_equal(fused[0], staged[0]) and len(fused[0]) > 10
 
 
+@pytest.mark.parametrize('flip', [False, True])
+def test_fused_path_redoes_only_the_overflowed_planes(cuda_device, flip):
+    """One noisy plane in a clean batch (flip-test too: its mirrored partner is another channel of
+    the second half): the fetch materialises that plane alone, the dets of every other plane are
+    the fused kernel's, and dets / limbs / poses equal the materialising path."""
+    import bench
+    skel = cfg.COCO_PERSON_SKELETON
+    hmp, omp = bench.lowres_inputs(777, 3, 640, flip)
+    rng = np.random.RandomState(9)
+    hmp[1, 5] = rng.uniform(0, 1, size=hmp.shape[2:]).astype(np.float32)
+    tables = (cfg.heatmap_hflip(cfg.COCO_KEYPOINTS),) + tuple(cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel)) if flip else None
+    th, to = torch.from_numpy(hmp).cuda(), torch.from_numpy(omp).cuda()
+    eng = DecoderEngine(17, skel, topk=32, thre_hmp=0.04, dist_max=40, use_scale=True, person_thre=0.04)
+    l0 = eng.launch_count
+    fused = eng.decode_features(th, to, 4, 4, 'bicubic', tables)
+    # K1f x3, select, K2, K3 + the redo: fuse, resize, radix select of ONE plane, K2, K3
+    assert eng.fused_redo_count == 1 and eng.launch_count - l0 == 6 + 5
+    f_int = [t.cpu().numpy() for t in eng.last_intermediates(3)]
+    eng.set_fused(False)
+    staged = eng.decode_features(th, to, 4, 4, 'bicubic', tables)
+    s_int = [t.cpu().numpy() for t in eng.last_intermediates(3)]
+    for a, b in zip(f_int, s_int):
+        assert np.array_equal(a, b)
+    assert sum(len(p) for p in fused) >= 6
+    for a, b in zip(fused, staged):
+        assert np.array_equal(a, b)
+
+
 def test_host_offsets_stay_on_the_host(cuda_device):
     """Host API, fused path: pinned offset maps are not copied (K2 gathers its samples over
-    PCIe); pageable maps are copied as a whole; a candidate overflow re-runs the batch exactly
-    after copying them.  All three give the results of the device-resident call."""
+    PCIe); pageable maps are copied as a whole; after a candidate overflow the overflowed planes
+    are redone exactly and K2 samples the host-resident offsets once more.  All three give the
+    results of the device-resident call."""
     import bench
     skel = cfg.COCO_PERSON_SKELETON
     kp = cfg.heatmap_hflip(cfg.COCO_KEYPOINTS)
@@ -1152,6 +1182,16 @@ def test_optional_heads_match_reference(cuda_device, name):
         np.testing.assert_allclose(p, r, rtol=RTOL, atol=1e-5)
         if not (inc_jit and use_jit):
             assert np.array_equal(p[..., :2], r[..., :2])
+    # that was the fused path (K2 interpolates the optional heads at the candidate pixels); the
+    # stage-by-stage path on materialised maps gives the same poses bit for bit
+    eng = pp._engine(torch.device('cuda', 0))
+    l0 = eng.launch_count
+    pp.generate_poses(feats, flip_test=flip, cat_flip_offs=cat)
+    assert eng.launch_count - l0 == 6 and eng.fused_redo_count == 0
+    eng.set_fused(False)
+    staged = pp.generate_poses(feats, flip_test=flip, cat_flip_offs=cat)
+    for p, q in zip(got, staged):
+        assert np.array_equal(p, q)
 
 
 def test_tied_peaks_tie_aware_against_reference(cuda_device):
