@@ -672,6 +672,10 @@ int decode_chain(og_handle *h, ResultSlot *slot, const K1Fused &k1, const Offset
     }
     OG_CUDA_TRY(cudaEventRecord(slot->call_start, s));
     OG_CUDA_TRY(cudaStreamWaitEvent(a, slot->call_start, 0));
+    // what this call runs on, for a redo at fetch time (a graph replay does not pass through
+    // decode_range, and the slot may have served other buffers since the graph was captured)
+    slot->ctx = CallCtx{k1, src, h->ft, H, W, LimbExtras{}};
+    if (extras) slot->ctx.extras = *extras;
     if (!h->graph_enabled || h->timing) {
         OG_TRY(decode_range(h, slot, 0, 0, n, nullptr, &k1, nullptr, &src, nullptr, H, W, a, extras, true));
         return finish_call(h, slot);

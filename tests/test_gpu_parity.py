@@ -702,6 +702,34 @@ def test_fused_path_redoes_only_the_overflowed_planes(cuda_device, flip):
         assert np.array_equal(a, b)
 
 
+def test_overflow_redo_after_graph_replay_reads_the_calls_own_buffers(cuda_device):
+    """A result slot replays the graph captured for buffers A after it has served buffers B in
+    between; when that replay overflows a plane, the redo at fetch time must materialise the plane
+    from A (the call's own buffers), not from whatever the slot decoded last."""
+    import bench
+    skel = cfg.COCO_PERSON_SKELETON
+    (ha, oa), (hb, ob) = bench.lowres_inputs(31, 2, 640, False), bench.lowres_inputs(32, 2, 640, False)
+    a_h, a_o = torch.from_numpy(ha).cuda(), torch.from_numpy(oa).cuda()
+    b_h, b_o = torch.from_numpy(hb).cuda(), torch.from_numpy(ob).cuda()
+    eng = DecoderEngine(17, skel, topk=32, thre_hmp=0.04, dist_max=40, use_scale=True, person_thre=0.04)
+    eng.decode_features(a_h, a_o, 4, 4, 'bicubic', None)          # captures the chain for A
+    eng.decode_features(b_h, b_o, 4, 4, 'bicubic', None)          # the same slot now serves B
+    assert eng.fused_redo_count == 0
+    rng = np.random.RandomState(4)
+    a_h[1, 3] = torch.from_numpy(rng.uniform(0, 1, size=ha.shape[2:]).astype(np.float32)).cuda()
+    replays = eng.graph_counts[0]
+    got = eng.decode_features(a_h, a_o, 4, 4, 'bicubic', None)    # replay of A's graph, plane (1, 3) overflows
+    assert eng.graph_counts[0] == replays + 1 and eng.fused_redo_count == 1
+    g_int = [t.cpu().numpy() for t in eng.last_intermediates(2)]
+    eng.set_fused(False)
+    ref = eng.decode_features(a_h, a_o, 4, 4, 'bicubic', None)
+    r_int = [t.cpu().numpy() for t in eng.last_intermediates(2)]
+    for x, y in zip(g_int, r_int):
+        assert np.array_equal(x, y)
+    for x, y in zip(got, ref):
+        assert np.array_equal(x, y)
+
+
 def test_host_offsets_stay_on_the_host(cuda_device):
     """Host API, fused path: pinned offset maps are not copied (K2 gathers its samples over
     PCIe); pageable maps are copied as a whole; after a candidate overflow the overflowed planes
