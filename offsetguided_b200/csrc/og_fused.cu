@@ -75,75 +75,92 @@ __device__ __forceinline__ float4 load_cells4(const __half *p) {
 __device__ __forceinline__ unsigned abs_bits(float v) { return __float_as_uint(fabsf(v)); }
 
 // ---- pass A: activity flags ----------------------------------------------------
-// one thread per (plane, 8-row band, 4-cell column group)
+// one thread per (plane, 8-row band, 4-cell column group); 32-bit index arithmetic (the host splits
+// calls of more than 2^31 threads into several launches over `plane0`)
 template <typename T, bool kFlip, bool kVec>
 __global__ void __launch_bounds__(kScanThreads)
 amax_scan_kernel(const T *__restrict__ hmp, size_t img_stride, const FlipTablesDev ft,
-                 int N, int C, int h, int w, int block_w, int halo, float limit,
-                 uint8_t *__restrict__ block_flag, long long total) {
-    const long long idx = (long long)blockIdx.x * kScanThreads + threadIdx.x;
-    if (idx >= total) return;
+                 int N, int C, int h, int w, int bw_shift, int halo, float limit,
+                 uint8_t *__restrict__ block_flag, int plane0, int planes, int per_plane) {
+    const unsigned idx = blockIdx.x * (unsigned)kScanThreads + threadIdx.x;
+    const unsigned pl = idx / (unsigned)per_plane;
+    if (pl >= (unsigned)planes) return;
+    const int local = (int)(idx - pl * (unsigned)per_plane);
     const int sxs = (w + kSub - 1) / kSub;
-    const int bands = (h + 2 * kSub - 1) / (2 * kSub);
-    const int sx = (int)(idx % sxs);
-    const long long t = idx / sxs;
-    const int band = (int)(t % bands);
-    const int plane = (int)(t / bands);
-    const int n = plane / C, c = plane - n * C;
-    const T *a = hmp + (size_t)n * img_stride + (size_t)c * h * w;
-    const T *b = nullptr;
-    if (kFlip) b = hmp + (size_t)(N + n) * img_stride + (size_t)ft.kp[c] * h * w;
+    const int band = local / sxs, sx = local - band * sxs;
     const int y0 = band * 2 * kSub, x0 = sx * kSub;
-    const int bxs = (w + block_w - 1) / block_w, bys = (h + kBlockCellsH - 1) / kBlockCellsH;
-    uint8_t *flags = block_flag + (size_t)plane * bys * bxs;
-    // Cells [xa, xb] of row y can reach the threshold (rare): flag every work block whose cells or
-    // tap halo they overlap.  Plain byte stores of the same value from many threads are benign.
-    auto flag_blocks = [&](int xa, int xb, int y) {
-        const int bx_lo = max(xa - halo, 0) / block_w, bx_hi = min((xb + halo) / block_w, bxs - 1);
-        const int by_lo = max(y - halo, 0) / kBlockCellsH, by_hi = min((y + halo) / kBlockCellsH, bys - 1);
-        for (int by = by_lo; by <= by_hi; ++by)
-            for (int bx = bx_lo; bx <= bx_hi; ++bx) flags[by * bxs + bx] = 1;
-    };
-    if (kVec) {
-        // two batches of kSub rows: 4 (8 with the mirrored copy) independent 128-bit loads in
-        // flight per thread keep the register count low enough for full occupancy
+    const int block_w = 1 << bw_shift;
+    const int bxs = (w + block_w - 1) >> bw_shift, bys = (h + kBlockCellsH - 1) / kBlockCellsH;
+    {
+        const int plane = plane0 + (int)pl;
+        const int n = plane / C, c = plane - n * C;
+        const T *a = hmp + (size_t)n * img_stride + (size_t)c * h * w;
+        const T *b = nullptr;
+        if (kFlip) b = hmp + (size_t)(N + n) * img_stride + (size_t)ft.kp[c] * h * w;
+        uint8_t *flags = block_flag + (size_t)plane * bys * bxs;
+        // Cells [xa, xb] of row y can reach the threshold (rare): flag every work block whose cells
+        // or tap halo they overlap.  Plain byte stores of the same value from many threads are benign.
+        auto flag_blocks = [&](int xa, int xb, int y) {
+            const int bx_lo = max(xa - halo, 0) >> bw_shift, bx_hi = min((xb + halo) >> bw_shift, bxs - 1);
+            const int by_lo = max(y - halo, 0) / kBlockCellsH, by_hi = min((y + halo) / kBlockCellsH, bys - 1);
+            for (int by = by_lo; by <= by_hi; ++by)
+                for (int bx = bx_lo; bx <= bx_hi; ++bx) flags[by * bxs + bx] = 1;
+        };
+        if (kVec) {
+            // two batches of kSub rows: 4 (8 with the mirrored copy) independent 128-bit loads in
+            // flight per thread keep the register count low enough for full occupancy
 #pragma unroll 1
-        for (int r0 = 0; r0 < 2 * kSub; r0 += kSub) {
-            float4 va[kSub], vb[kSub];
+            for (int r0 = 0; r0 < 2 * kSub; r0 += kSub) {
+                float4 va[kSub], vb[kSub];
 #pragma unroll
-            for (int r = 0; r < kSub; ++r) {
-                const int y = min(y0 + r0 + r, h - 1);     // rows below the image repeat the last one
-                va[r] = load_cells4(a + (size_t)y * w + x0);
-                if (kFlip) vb[r] = load_cells4(b + (size_t)y * w + (w - kSub - x0));
-            }
-#pragma unroll
-            for (int r = 0; r < kSub; ++r) {
-                float4 f = va[r];
-                if (kFlip) {                 // (orig + flip_W(flipped)[kp_flip]) / 2, factory.py:101-106
-                    f.x = __fmul_rn(__fadd_rn(f.x, vb[r].w), 0.5f);
-                    f.y = __fmul_rn(__fadd_rn(f.y, vb[r].z), 0.5f);
-                    f.z = __fmul_rn(__fadd_rn(f.z, vb[r].y), 0.5f);
-                    f.w = __fmul_rn(__fadd_rn(f.w, vb[r].x), 0.5f);
+                for (int r = 0; r < kSub; ++r) {
+                    const int y = min(y0 + r0 + r, h - 1);     // rows below the image repeat the last one
+                    va[r] = load_cells4(a + (size_t)y * w + x0);
+                    if (kFlip) vb[r] = load_cells4(b + (size_t)y * w + (w - kSub - x0));
                 }
-                const unsigned q = max(max(abs_bits(f.x), abs_bits(f.y)), max(abs_bits(f.z), abs_bits(f.w)));
-                if (__uint_as_float(q) < limit || y0 + r0 + r >= h) continue;   // NaN is not below: stays active
-                const bool c0 = !(fabsf(f.x) < limit), c1 = !(fabsf(f.y) < limit), c2 = !(fabsf(f.z) < limit),
-                           c3 = !(fabsf(f.w) < limit);
-                const int first = c0 ? 0 : (c1 ? 1 : (c2 ? 2 : 3));
-                const int last = c3 ? 3 : (c2 ? 2 : (c1 ? 1 : 0));
-                flag_blocks(x0 + first, x0 + last, y0 + r0 + r);
+                auto fused_row = [&](int r) {
+                    float4 f = va[r];
+                    if (kFlip) {             // (orig + flip_W(flipped)[kp_flip]) / 2, factory.py:101-106
+                        f.x = __fmul_rn(__fadd_rn(f.x, vb[r].w), 0.5f);
+                        f.y = __fmul_rn(__fadd_rn(f.y, vb[r].z), 0.5f);
+                        f.z = __fmul_rn(__fadd_rn(f.z, vb[r].y), 0.5f);
+                        f.w = __fmul_rn(__fadd_rn(f.w, vb[r].x), 0.5f);
+                    }
+                    return f;
+                };
+                // the streaming test: one bit per row, no branch; the rows that pass (2 % of the
+                // cells) are looked at again in ONE divergent region per batch
+                unsigned hot = 0u;
+#pragma unroll
+                for (int r = 0; r < kSub; ++r) {
+                    const float4 f = fused_row(r);
+                    const unsigned q = max(max(abs_bits(f.x), abs_bits(f.y)), max(abs_bits(f.z), abs_bits(f.w)));
+                    if (!(__uint_as_float(q) < limit) && y0 + r0 + r < h) hot |= 1u << r;   // NaN is not below: stays active
+                }
+                if (hot != 0u) {
+#pragma unroll
+                    for (int r = 0; r < kSub; ++r) {
+                        if (!((hot >> r) & 1u)) continue;
+                        const float4 f = fused_row(r);
+                        const bool c0 = !(fabsf(f.x) < limit), c1 = !(fabsf(f.y) < limit), c2 = !(fabsf(f.z) < limit),
+                                   c3 = !(fabsf(f.w) < limit);
+                        const int first = c0 ? 0 : (c1 ? 1 : (c2 ? 2 : 3));
+                        const int last = c3 ? 3 : (c2 ? 2 : (c1 ? 1 : 0));
+                        flag_blocks(x0 + first, x0 + last, y0 + r0 + r);
+                    }
+                }
             }
-        }
-    } else {
-        for (int r = 0; r < 2 * kSub; ++r) {
-            const int y = y0 + r;
-            if (y >= h) break;
-            for (int j = 0; j < kSub; ++j) {
-                const int x = x0 + j;
-                if (x >= w) break;
-                float v = load_cell(a + (size_t)y * w + x);
-                if (kFlip) v = __fmul_rn(__fadd_rn(v, load_cell(b + (size_t)y * w + (w - 1 - x))), 0.5f);
-                if (!(fabsf(v) < limit)) flag_blocks(x, x, y);
+        } else {
+            for (int r = 0; r < 2 * kSub; ++r) {
+                const int y = y0 + r;
+                if (y >= h) break;
+                for (int j = 0; j < kSub; ++j) {
+                    const int x = x0 + j;
+                    if (x >= w) break;
+                    float v = load_cell(a + (size_t)y * w + x);
+                    if (kFlip) v = __fmul_rn(__fadd_rn(v, load_cell(b + (size_t)y * w + (w - 1 - x))), 0.5f);
+                    if (!(fabsf(v) < limit)) flag_blocks(x, x, y);
+                }
             }
         }
     }
@@ -481,22 +498,31 @@ int launch_fused_t(const T *hmp, size_t img_stride, const FlipTablesDev &kp_flip
     }
 
     const int sxs = (w + kSub - 1) / kSub, bands = (h + 2 * kSub - 1) / (2 * kSub);
-    const long long scan_threads = (long long)n * c * bands * sxs;
-    const unsigned scan_grid = (unsigned)((scan_threads + kScanThreads - 1) / kScanThreads);
+    const int per_plane = bands * sxs, planes = n * c;
+    const int planes_per_launch = std::max(1, (int)std::min<long long>(planes, 0x7fffffffLL / per_plane - 1));
     const int block_w = 32 / scale, halo = cubic ? 2 : 1;
+    const int bw_shift = scale == 2 ? 4 : (scale == 4 ? 3 : 2);
     const float limit = thre / (cubic ? 1.95f : 1.001f);
     // vector loads need whole 4-cell groups and rows aligned to the 4-cell load size (also the
     // rows of the mirrored read and of every image)
     const size_t vec_bytes = 4 * sizeof(T);
     const bool vec = (w % kSub) == 0 && (reinterpret_cast<uintptr_t>(hmp) % vec_bytes) == 0 &&
                      (img_stride * sizeof(T)) % vec_bytes == 0;
-    if (flip) {
-        if (vec) prefer_chain_carveout<amax_scan_kernel<T, true, true>>(), amax_scan_kernel<T, true, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
-        else prefer_chain_carveout<amax_scan_kernel<T, true, false>>(), amax_scan_kernel<T, true, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
-    } else {
-        if (vec) prefer_chain_carveout<amax_scan_kernel<T, false, true>>(), amax_scan_kernel<T, false, true><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
-        else prefer_chain_carveout<amax_scan_kernel<T, false, false>>(), amax_scan_kernel<T, false, false><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, w, block_w, halo, limit, block_flag, scan_threads);
+#define OG_SCAN(FLIP, VEC)                                                                                     \
+    (prefer_chain_carveout<amax_scan_kernel<T, FLIP, VEC>>(),                                                  \
+     amax_scan_kernel<T, FLIP, VEC><<<scan_grid, kScanThreads, 0, s>>>(hmp, img_stride, kp_flip_dev, n_total, c, h, \
+                                                                      w, bw_shift, halo, limit, block_flag, p0, pn, \
+                                                                      per_plane))
+    for (int p0 = 0; p0 < planes; p0 += planes_per_launch) {
+        const int pn = std::min(planes_per_launch, planes - p0);
+        const unsigned scan_grid = (unsigned)(((long long)pn * per_plane + kScanThreads - 1) / kScanThreads);
+        if (flip) {
+            if (vec) OG_SCAN(true, true); else OG_SCAN(true, false);
+        } else {
+            if (vec) OG_SCAN(false, true); else OG_SCAN(false, false);
+        }
     }
+#undef OG_SCAN
     OG_CUDA_TRY(cudaGetLastError());
 
     const size_t blocks = block_count(n, c, h, w, scale);
