@@ -39,6 +39,9 @@ namespace og {
 
 namespace {
 
+#ifndef OG_K1F_MIN_CTAS
+#define OG_K1F_MIN_CTAS 4
+#endif
 constexpr int kFusedThreads = 256;
 constexpr int kScanThreads = 256;
 constexpr int kBlockCellsH = 8;       // cell rows of a block
@@ -229,7 +232,7 @@ __device__ __noinline__ float tile_value(const float *lo, int cx0, int cy0, int 
 }
 
 template <typename T, int S, bool kCubic, bool kFlip>
-__global__ void __launch_bounds__(kFusedThreads, S <= 4 ? 4 : 3)
+__global__ void __launch_bounds__(kFusedThreads, S <= 4 ? OG_K1F_MIN_CTAS : 3)
 fused_block_kernel(const T *__restrict__ hmp, size_t img_stride, int N, int h, int w, float thre,
                    const int4 *__restrict__ block_list,
                    const int32_t *__restrict__ n_active_ptr, uint32_t *__restrict__ cand_count,
