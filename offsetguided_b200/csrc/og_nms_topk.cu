@@ -240,44 +240,37 @@ __device__ void write_ranked(const uint64_t *keys, int n, int K, float *out_scor
     }
 }
 
-__global__ void __launch_bounds__(kSelectThreads)
-select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int K,
-                   uint32_t *__restrict__ cand_count,
-                   const uint64_t *__restrict__ cand_keys, float *__restrict__ out_score,
-                   int32_t *__restrict__ out_index, int32_t *__restrict__ out_count,
-                   int force_radix, int apply_nms, int32_t *__restrict__ overflow_flag,
-                   int32_t *__restrict__ clear_word, const int32_t *__restrict__ plane_map) {
-    __shared__ uint64_t s_keys[kCandCap];
-    __shared__ uint32_t s_hist[kRadixBins];
-    __shared__ uint32_t s_part[kSelectThreads];
-    __shared__ uint32_t s_scalar[4];
+constexpr int kSelectPlanes = kSelectThreads / 32;     // planes per CTA of the selection kernel
+constexpr int kSmallCand = 64;                         // candidates a single warp ranks
 
-    const int plane = blockIdx.x;
+struct SelectShared {
+    uint64_t keys[kCandCap];
+    uint32_t hist[kRadixBins];
+    uint32_t part[kSelectThreads];
+    uint32_t scalar[4];
+    uint64_t small[kSelectPlanes][kSmallCand];
+    uint32_t n_cand[kSelectPlanes];
+    uint8_t big[kSelectPlanes];
+};
+
+// One plane selected by the whole CTA: up to kCandCap listed candidates are ranked in shared
+// memory (completed from the zeros when thre <= 0); a plane with more goes through the exact
+// radix selection over the plane itself.  Every thread of the CTA calls this with the same arguments.
+__device__ void select_plane_cta(SelectShared &sh, const float *__restrict__ heat, int H, int W, float thre, int K,
+                                 int plane, uint32_t n_cand, const uint64_t *__restrict__ cand_keys,
+                                 float *__restrict__ o_score, int32_t *__restrict__ o_index,
+                                 int32_t *__restrict__ o_count, int apply_nms,
+                                 int32_t *__restrict__ overflow_flag) {
+    uint64_t *s_keys = sh.keys;
+    uint32_t *s_hist = sh.hist, *s_part = sh.part, *s_scalar = sh.scalar;
     const int tid = threadIdx.x;
-    // results of plane b of `heat` go to slot plane_map[b] of the output arrays (the redo of single
-    // overflowed planes of a fused decode); the candidate lists are not used then (force_radix)
-    const int oplane = plane_map ? plane_map[plane] : plane;
-    float *o_score = out_score + (size_t)oplane * K;
-    int32_t *o_index = out_index + (size_t)oplane * K;
-    if (out_count) out_count += oplane - plane;
-
-    // The plane's counter is read once and left at zero for the next call on these lists (they
-    // belong to a result slot); the fused path's active-block counter is cleared the same way.
-    if (tid == 0) {
-        s_scalar[0] = force_radix ? (uint32_t)kCandCap + 1u : cand_count[plane];
-        if (!force_radix) cand_count[plane] = 0u;
-        if (clear_word != nullptr && plane == 0) *clear_word = 0;
-    }
-    __syncthreads();
-    const uint32_t n_cand = s_scalar[0];
-    __syncthreads();
     if (n_cand <= (uint32_t)kCandCap) {
         const int n = (int)n_cand;
         for (int i = tid; i < n; i += blockDim.x) s_keys[i] = cand_keys[(size_t)plane * kCandCap + i];
         __syncthreads();
         if (!(thre <= 0.0f) || n >= K || heat == nullptr) {
             write_ranked(s_keys, n, K, o_score, o_index);
-            if (tid == 0 && out_count) out_count[plane] = min(n, K);
+            if (tid == 0 && o_count) *o_count = min(n, K);
             return;
         }
         // thre <= 0 (the exact joint_dets API): pass 1 listed the POSITIVE peaks only, fewer than K.
@@ -308,7 +301,7 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
         }
         if (taken >= need) {
             write_ranked(s_keys, K, K, o_score, o_index);
-            if (tid == 0 && out_count) out_count[plane] = K;
+            if (tid == 0 && o_count) *o_count = K;
             return;
         }
     }
@@ -316,7 +309,7 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
     if (heat == nullptr) {      // fused path: no materialised plane to re-scan; og_fetch_result
         if (tid == 0) {         // materialises the planes marked -1 and selects them exactly
             *reinterpret_cast<volatile int32_t *>(overflow_flag) = 1;      // may be mapped host memory
-            if (out_count) out_count[plane] = -1;
+            if (o_count) *o_count = -1;
         }
         write_ranked(s_keys, 0, K, o_score, o_index);
         return;
@@ -387,7 +380,7 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
     const uint32_t k_eff = min((uint32_t)K, total_q);
     if (k_eff == 0) {
         write_ranked(s_keys, 0, K, o_score, o_index);
-        if (tid == 0 && out_count) out_count[plane] = 0;
+        if (tid == 0 && o_count) *o_count = 0;
         return;
     }
     const uint32_t kth = prefix;                 // key of the k_eff-th element
@@ -432,7 +425,79 @@ select_topk_kernel(const float *__restrict__ heat, int H, int W, float thre, int
         __syncthreads();
     }
     write_ranked(s_keys, (int)k_eff, K, o_score, o_index);
-    if (tid == 0 && out_count) out_count[plane] = (int)k_eff;
+    if (tid == 0 && o_count) *o_count = (int)k_eff;
+}
+
+
+// Pass 2.  A CTA takes kSelectPlanes planes.  First every warp ranks its own plane if that plane
+// listed at most kSmallCand candidates (every real heat map: a handful per plane) — keys in a
+// per-warp slice of shared memory, rank = number of smaller keys, no CTA barrier; then the CTA
+// goes through the planes that need more (long lists, the zero completion of thre <= 0, the radix
+// selection) one after the other.
+__global__ void __launch_bounds__(kSelectThreads)
+select_topk_kernel(const float *__restrict__ heat, int planes, int H, int W, float thre, int K,
+                   uint32_t *__restrict__ cand_count,
+                   const uint64_t *__restrict__ cand_keys, float *__restrict__ out_score,
+                   int32_t *__restrict__ out_index, int32_t *__restrict__ out_count,
+                   int force_radix, int apply_nms, int32_t *__restrict__ overflow_flag,
+                   int32_t *__restrict__ clear_word, const int32_t *__restrict__ plane_map) {
+    __shared__ SelectShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int plane0 = blockIdx.x * kSelectPlanes;
+    // results of plane b of `heat` go to slot plane_map[b] of the output arrays (the redo of single
+    // overflowed planes of a fused decode); the candidate lists are not used then (force_radix)
+    auto out_plane = [&](int plane) { return plane_map ? plane_map[plane] : plane; };
+    {
+        const int plane = plane0 + warp;
+        bool big = false;
+        uint32_t n_cand = 0;
+        if (plane < planes) {
+            // The plane's counter is read once and left at zero for the next call on these lists
+            // (they belong to a result slot); the fused path's active-block counter likewise.
+            if (lane == 0) {
+                n_cand = force_radix ? (uint32_t)kCandCap + 1u : cand_count[plane];
+                if (!force_radix) cand_count[plane] = 0u;
+                if (clear_word != nullptr && plane == 0) *clear_word = 0;
+            }
+            n_cand = __shfl_sync(0xffffffffu, n_cand, 0);
+            const int n = (int)n_cand;
+            big = n_cand > (uint32_t)kSmallCand || (thre <= 0.0f && n < K && heat != nullptr);
+            if (!big) {
+                uint64_t *keys = sh.small[warp];
+                for (int i = lane; i < n; i += 32) keys[i] = cand_keys[(size_t)plane * kCandCap + i];
+                __syncwarp();
+                const int op = out_plane(plane);
+                float *o_score = out_score + (size_t)op * K;
+                int32_t *o_index = out_index + (size_t)op * K;
+                for (int i = lane; i < n; i += 32) {
+                    const uint64_t key = keys[i];
+                    int rank = 0;
+                    for (int j = 0; j < n; ++j) rank += (keys[j] < key) ? 1 : 0;
+                    if (rank < K) {
+                        o_score[rank] = key_value(key);
+                        o_index[rank] = (int32_t)(uint32_t)key;
+                    }
+                }
+                for (int r = n + lane; r < K; r += 32) {
+                    o_score[r] = 0.0f;
+                    o_index[r] = -1;
+                }
+                if (lane == 0 && out_count) out_count[op] = min(n, K);
+            }
+        }
+        if (lane == 0) {
+            sh.big[warp] = big ? 1 : 0;
+            sh.n_cand[warp] = n_cand;
+        }
+    }
+    __syncthreads();
+    for (int w = 0; w < kSelectPlanes; ++w) {
+        if (!sh.big[w]) continue;                          // CTA-uniform
+        const int plane = plane0 + w, op = out_plane(plane);
+        select_plane_cta(sh, heat, H, W, thre, K, plane, sh.n_cand[w], cand_keys, out_score + (size_t)op * K,
+                         out_index + (size_t)op * K, out_count ? out_count + op : nullptr, apply_nms, overflow_flag);
+        __syncthreads();
+    }
 }
 
 __global__ void hmp_nms_kernel(const float *__restrict__ heat, float *__restrict__ out,
@@ -480,7 +545,7 @@ int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int
     if (!force_radix) OG_TRY(launch_nms_candidates(heat, planes, h, w, thre, cand_count, cand_keys, s, launches));
     if (after_pass1) OG_CUDA_TRY(cudaEventRecord(after_pass1, s));
     prefer_chain_carveout<select_topk_kernel>();
-    select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
+    select_topk_kernel<<<(planes + kSelectPlanes - 1) / kSelectPlanes, kSelectThreads, 0, s>>>(heat, planes, h, w, thre, k, cand_count, cand_keys,
                                                         out_score, out_index, out_count,
                                                         force_radix ? 1 : 0, apply_nms ? 1 : 0, nullptr, nullptr,
                                                         plane_map);
@@ -526,7 +591,7 @@ int launch_select_topk(const float *heat, int planes, int h, int w, float thre, 
                        int32_t *clear_word, cudaStream_t s) {
     if (planes == 0) return OG_OK;
     prefer_chain_carveout<select_topk_kernel>();
-    select_topk_kernel<<<planes, kSelectThreads, 0, s>>>(heat, h, w, thre, k, cand_count, cand_keys,
+    select_topk_kernel<<<(planes + kSelectPlanes - 1) / kSelectPlanes, kSelectThreads, 0, s>>>(heat, planes, h, w, thre, k, cand_count, cand_keys,
                                                         out_score, out_index, out_count, 0, 1,
                                                         overflow_flag, clear_word, nullptr);
     OG_CUDA_TRY(cudaGetLastError());
