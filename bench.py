@@ -461,6 +461,8 @@ def run_b200(args):
 
     # ---- value: the product path, pipelined, one global batch per step
     depth = _lib.OG_MAX_IN_FLIGHT
+    if os.environ.get('OG_BENCH_DEPTH'):                      # tuning aid
+        depth = max(1, min(int(os.environ['OG_BENCH_DEPTH']), _lib.OG_MAX_IN_FLIGHT))
     persons = pipelined(post, feats_ring, flip, args.warmup + 2 * depth, depth)      # warm-up: every slot has its graphs
     n_persons = sum(len(p) for p in persons)
     sampler = ClockSampler(dev_index).start()
