@@ -241,7 +241,7 @@ __device__ void write_ranked(const uint64_t *keys, int n, int K, float *out_scor
 }
 
 constexpr int kSelectPlanes = kSelectThreads / 32;     // planes per CTA of the selection kernel
-constexpr int kSmallCand = 64;                         // candidates a single warp ranks
+constexpr int kSmallCand = 128;                        // candidates a single warp ranks
 
 struct SelectShared {
     uint64_t keys[kCandCap];
@@ -429,9 +429,10 @@ __device__ void select_plane_cta(SelectShared &sh, const float *__restrict__ hea
 }
 
 
-// Pass 2.  A CTA takes kSelectPlanes planes.  First every warp ranks its own plane if that plane
-// listed at most kSmallCand candidates (every real heat map: a handful per plane) — keys in a
-// per-warp slice of shared memory, rank = number of smaller keys, no CTA barrier; then the CTA
+// Pass 2.  A CTA takes `planes_per_cta` planes (kSelectPlanes, or 1 when long lists are expected
+// everywhere: thre <= 0, forced radix selection).  First every warp ranks its own plane if that
+// plane listed at most kSmallCand candidates (every real heat map: a handful per plane) — keys in
+// a per-warp slice of shared memory, rank = number of smaller keys, no CTA barrier; then the CTA
 // goes through the planes that need more (long lists, the zero completion of thre <= 0, the radix
 // selection) one after the other.
 __global__ void __launch_bounds__(kSelectThreads)
@@ -440,10 +441,10 @@ select_topk_kernel(const float *__restrict__ heat, int planes, int H, int W, flo
                    const uint64_t *__restrict__ cand_keys, float *__restrict__ out_score,
                    int32_t *__restrict__ out_index, int32_t *__restrict__ out_count,
                    int force_radix, int apply_nms, int32_t *__restrict__ overflow_flag,
-                   int32_t *__restrict__ clear_word, const int32_t *__restrict__ plane_map) {
+                   int32_t *__restrict__ clear_word, const int32_t *__restrict__ plane_map, int planes_per_cta) {
     __shared__ SelectShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int plane0 = blockIdx.x * kSelectPlanes;
+    const int plane0 = blockIdx.x * planes_per_cta;
     // results of plane b of `heat` go to slot plane_map[b] of the output arrays (the redo of single
     // overflowed planes of a fused decode); the candidate lists are not used then (force_radix)
     auto out_plane = [&](int plane) { return plane_map ? plane_map[plane] : plane; };
@@ -451,7 +452,7 @@ select_topk_kernel(const float *__restrict__ heat, int planes, int H, int W, flo
         const int plane = plane0 + warp;
         bool big = false;
         uint32_t n_cand = 0;
-        if (plane < planes) {
+        if (warp < planes_per_cta && plane < planes) {
             // The plane's counter is read once and left at zero for the next call on these lists
             // (they belong to a result slot); the fused path's active-block counter likewise.
             if (lane == 0) {
@@ -491,7 +492,7 @@ select_topk_kernel(const float *__restrict__ heat, int planes, int H, int W, flo
         }
     }
     __syncthreads();
-    for (int w = 0; w < kSelectPlanes; ++w) {
+    for (int w = 0; w < planes_per_cta; ++w) {
         if (!sh.big[w]) continue;                          // CTA-uniform
         const int plane = plane0 + w, op = out_plane(plane);
         select_plane_cta(sh, heat, H, W, thre, K, plane, sh.n_cand[w], cand_keys, out_score + (size_t)op * K,
@@ -545,10 +546,11 @@ int launch_nms_topk(const float *heat, int planes, int h, int w, float thre, int
     if (!force_radix) OG_TRY(launch_nms_candidates(heat, planes, h, w, thre, cand_count, cand_keys, s, launches));
     if (after_pass1) OG_CUDA_TRY(cudaEventRecord(after_pass1, s));
     prefer_chain_carveout<select_topk_kernel>();
-    select_topk_kernel<<<(planes + kSelectPlanes - 1) / kSelectPlanes, kSelectThreads, 0, s>>>(heat, planes, h, w, thre, k, cand_count, cand_keys,
-                                                        out_score, out_index, out_count,
-                                                        force_radix ? 1 : 0, apply_nms ? 1 : 0, nullptr, nullptr,
-                                                        plane_map);
+    const int ppc = (force_radix || !(thre > 0.0f)) ? 1 : kSelectPlanes;
+    select_topk_kernel<<<(planes + ppc - 1) / ppc, kSelectThreads, 0, s>>>(heat, planes, h, w, thre, k, cand_count, cand_keys,
+                                                                         out_score, out_index, out_count,
+                                                                         force_radix ? 1 : 0, apply_nms ? 1 : 0, nullptr,
+                                                                         nullptr, plane_map, ppc);
     OG_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;
     return OG_OK;
@@ -591,9 +593,10 @@ int launch_select_topk(const float *heat, int planes, int h, int w, float thre, 
                        int32_t *clear_word, cudaStream_t s) {
     if (planes == 0) return OG_OK;
     prefer_chain_carveout<select_topk_kernel>();
-    select_topk_kernel<<<(planes + kSelectPlanes - 1) / kSelectPlanes, kSelectThreads, 0, s>>>(heat, planes, h, w, thre, k, cand_count, cand_keys,
-                                                        out_score, out_index, out_count, 0, 1,
-                                                        overflow_flag, clear_word, nullptr);
+    const int ppc = !(thre > 0.0f) ? 1 : kSelectPlanes;
+    select_topk_kernel<<<(planes + ppc - 1) / ppc, kSelectThreads, 0, s>>>(heat, planes, h, w, thre, k, cand_count, cand_keys,
+                                                                         out_score, out_index, out_count, 0, 1,
+                                                                         overflow_flag, clear_word, nullptr, ppc);
     OG_CUDA_TRY(cudaGetLastError());
     return OG_OK;
 }
