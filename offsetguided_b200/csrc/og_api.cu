@@ -611,7 +611,12 @@ int decode_range(og_handle *h, ResultSlot *slot, int chunk, int i0, int cn, cons
     if (timed) OG_TRY(mark(h, slot, 3, sel));
     OG_TRY(launch_select_topk(fused ? nullptr : heat + plane0 * HW, planes, hgt, w, c.thre_hmp, c.topk,
                               cand_count, cand_keys, det_score, det_index, det_count,
-                              fused ? meta + 2 * n : nullptr, chain ? n_active : nullptr, sel));
+                              fused ? meta + 2 * n : nullptr,
+                              // the active-block counter must be zero when the next call on this slot
+                              // starts: the chain's selection clears it, and so does the selection of
+                              // the LAST range of a host call (earlier ranges clear it with a memset
+                              // before their scan, because the next range's scan may already run)
+                              (chain || timed) ? n_active : nullptr, sel));
     h->launches += 1;
     if (!chain && !sel_on_aux) {
         OG_CUDA_TRY(cudaEventRecord(slot->k1_done[chunk], k1s));

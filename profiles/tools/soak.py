@@ -1,7 +1,9 @@
-"""Soak test: thousands of pipelined decode calls on all three entry paths (full-resolution maps,
-device-resident network-resolution maps, pinned host maps), every result compared with the first
-one.  Catches rare ordering bugs between the caller's stream, the handle's stream and the copy
-stream that single-shot tests cannot."""
+"""Soak test: thousands of pipelined decode calls on all entry paths (full-resolution maps,
+device-resident network-resolution maps — direct call, prepared plan, a batch with a noisy plane
+that is redone at fetch time — and pinned host maps), a random number of calls (up to 12) in
+flight, every result compared with the first one.  Catches rare ordering bugs between the
+caller's stream, the result slots' streams, graph replays and the copy stream that single-shot
+tests cannot."""
 import json
 import sys
 import os
@@ -33,23 +35,38 @@ def main():
     th_h, to_h = torch.from_numpy(hmp).pin_memory(), torch.from_numpy(omp).pin_memory()
     heat_d, offs_d = torch.from_numpy(heat).cuda(), torch.from_numpy(offs).cuda()
     eng = DecoderEngine(17, skel, topk=32, thre_hmp=0.04, dist_max=40, use_scale=True, person_thre=0.04)
+    noisy = hmp.copy()
+    noisy[3, 7] = np.random.RandomState(1).uniform(0, 1, size=hmp.shape[2:]).astype(np.float32)
+    tn_d = torch.from_numpy(noisy).cuda()
+    plan = eng.plan_features(th_d.clone(), to_d.clone(), 4, 4, 'bicubic', tables)
+
+    def plan_call(fetch):
+        plan.launch()
+        return eng.fetch() if fetch else None
     calls = {
         'maps': lambda fetch: eng.decode_maps(heat_d, offs_d, fetch=fetch),
         'features_dev': lambda fetch: eng.decode_features(th_d, to_d, 4, 4, 'bicubic', tables, fetch=fetch),
         'features_host': lambda fetch: eng.decode_features(th_h, to_h, 4, 4, 'bicubic', tables, fetch=fetch),
+        'features_plan': plan_call,
+        'features_noisy_plane': lambda fetch: eng.decode_features(tn_d, to_d, 4, 4, 'bicubic', tables, fetch=fetch),
     }
     ref = {k: f(True) for k, f in calls.items()}
-    assert same(ref['features_dev'], ref['features_host'])
+    assert same(ref['features_dev'], ref['features_host']) and same(ref['features_dev'], ref['features_plan'])
     bad = {k: 0 for k in calls}
     order = list(calls)
     rng = np.random.RandomState(0)
+    weights = np.array([1.0 if k != 'features_noisy_plane' else 0.05 for k in order])
+    weights /= weights.sum()
     t0 = time.time()
     pending = []
+    depth = 3
     for it in range(iters):
-        k = order[rng.randint(len(order))]
+        k = order[rng.choice(len(order), p=weights)]
         calls[k](False)
         pending.append(k)
-        if len(pending) == 3:                       # three calls in flight, mixed paths
+        if it % 97 == 0:
+            depth = int(rng.randint(1, 13))
+        while len(pending) >= depth:                # up to 12 calls in flight, mixed paths
             kk = pending.pop(0)
             if not same(eng.fetch(n), ref[kk]):
                 bad[kk] += 1

@@ -730,6 +730,27 @@ def test_overflow_redo_after_graph_replay_reads_the_calls_own_buffers(cuda_devic
         assert np.array_equal(x, y)
 
 
+def test_device_call_after_host_call_on_the_same_slot(cuda_device):
+    """A result slot serves a host-maps call (several image ranges, counters cleared by memsets) and
+    then a device-maps call (one chain that expects its counters at zero): the second call must not
+    see the active-block count the first one left behind (found by profiles/tools/soak.py)."""
+    import bench
+    skel = cfg.COCO_PERSON_SKELETON
+    tables = (cfg.heatmap_hflip(cfg.COCO_KEYPOINTS),) + tuple(cfg.offset_hflip(cfg.COCO_KEYPOINTS, skel))
+    hmp, omp = bench.lowres_inputs(808, 16, 320, True)
+    th_d, to_d = torch.from_numpy(hmp).cuda(), torch.from_numpy(omp).cuda()
+    th_h, to_h = torch.from_numpy(hmp).pin_memory(), torch.from_numpy(omp).pin_memory()
+    kw = dict(topk=32, thre_hmp=0.04, dist_max=40, use_scale=True, person_thre=0.04)
+    ref = DecoderEngine(17, skel, **kw).decode_features(th_d, to_d, 4, 4, 'bicubic', tables)
+    assert sum(len(p) for p in ref) >= 16 * 4
+    eng = DecoderEngine(17, skel, **kw)
+    for rep in range(3):
+        host = eng.decode_features(th_h, to_h, 4, 4, 'bicubic', tables)
+        dev = eng.decode_features(th_d, to_d, 4, 4, 'bicubic', tables)        # captured, then replayed
+        for a, b, r in zip(host, dev, ref):
+            assert np.array_equal(a, r) and np.array_equal(b, r), rep
+
+
 def test_host_offsets_stay_on_the_host(cuda_device):
     """Host API, fused path: pinned offset maps are not copied (K2 gathers its samples over
     PCIe); pageable maps are copied as a whole; after a candidate overflow the overflowed planes
