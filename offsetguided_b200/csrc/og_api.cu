@@ -278,10 +278,6 @@ CocoOut coco_out(const og_handle *h, const ResultSlot *slot, int image0) {
 
 // meta words: offset[n], count[n], overflow flag of the fused path, one spare
 inline size_t meta_bytes_for(int n) { return ((size_t)(2 * n + 2) * sizeof(int32_t) + 15) / 16 * 16; }
-inline size_t pose_row_bytes(const og_handle *h) {
-    return (size_t)h->cfg.n_keypoints * OG_POSE_COLS * sizeof(float);
-}
-
 int check_device(const og_handle *h) {
     int cur = -1;
     OG_CUDA_TRY(cudaGetDevice(&cur));
